@@ -1,0 +1,169 @@
+/* hvi_b200.h -- C ABI of the B200-native negative-ELBO + gradient path.
+ *
+ * This is the boundary a Julia host binds with `ccall` (see INTEGRATION.md and
+ * julia/HVIB200.jl).  The reference (EarthyScience/HybridVariationalInference.jl, paths
+ * below relative to /root/reference) has no FFI of its own; every entry point names the
+ * reference interface it stands in for.
+ *
+ * Conventions: every function returns an `int` status (HVI_OK == 0); no exception crosses
+ * the boundary; the caller owns every pointer it passes; a plan owns its device buffers;
+ * one in-flight call per plan; calls are synchronous at return unless the name ends in
+ * `_async`.  Arrays are column-major with the reference's shapes (site = column).
+ */
+#ifndef HVI_B200_H
+#define HVI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVI_ABI_VERSION 1
+#define HVI_MAX_PAR 8      /* max n_θP and max n_θM */
+#define HVI_MAX_LAYERS 8
+#define HVI_MAX_WIDTH 64   /* widest layer of the CUDA-core MLP applicator */
+
+/* status codes (reference: Julia exceptions, src/elbo.jl:187-190,253-258) */
+enum {
+  HVI_OK = 0,
+  HVI_EINVAL = 1,       /* bad argument / unsupported configuration                */
+  HVI_ECUDA = 2,        /* CUDA runtime error, see hvi_last_error                   */
+  HVI_ENONFINITE = 3,   /* result evaluated but not finite ("inspect non-finite")   */
+  HVI_ENODATA = 4,      /* hvi_plan_set_data has not been called                    */
+  HVI_ENOMEM = 5
+};
+
+enum { HVI_F32 = 0, HVI_F64 = 1 };
+enum { HVI_MEM_HOST = 0, HVI_MEM_DEVICE = 1 };
+/* bijector per parameter column: identity | Exp | Logistic
+ * (src/bijectors_utils.jl:10-23, 38-52; Stacked columns :65-114) */
+enum { HVI_TR_IDENTITY = 0, HVI_TR_EXP = 1, HVI_TR_LOGISTIC = 2 };
+/* prior family per parameter (Distributions.logpdf call sites src/elbo.jl:217-235) */
+enum { HVI_PR_NONE = 0, HVI_PR_NORMAL = 1, HVI_PR_LOGNORMAL = 2 };
+/* where the process model takes (r0, r1, K1, K2) from: hcat(θP, θMs, θFix) addressed by
+ * name (src/PBMApplicator.jl:234-239, 283-287) */
+enum { HVI_SRC_P = 0, HVI_SRC_M = 1, HVI_SRC_FIX = 2 };
+enum { HVI_ACT_IDENTITY = 0, HVI_ACT_TANH = 1, HVI_ACT_LOGISTIC = 2 };
+/* output scaling of g: NormalScalingModelApplicator (src/ModelApplicator.jl:163-176) or
+ * RangeScalingModelApplicator (:191-194) */
+enum { HVI_SCALE_NORMAL = 0, HVI_SCALE_RANGE = 1 };
+enum { HVI_FLAG_OMIT_PRIORS = 1 };  /* is_omit_priors = Val(true), src/elbo.jl:203-206 */
+
+typedef struct hvi_layer {
+  int32_t n_in, n_out, act, has_bias; /* params per layer: vec(W[out x in]) col-major, then b */
+} hvi_layer;
+
+typedef struct hvi_prior {
+  int32_t kind;
+  int32_t _pad;
+  double a, b; /* Normal(a=μ, b=σ) | LogNormal(a=μ, b=σ) */
+} hvi_prior;
+
+/* Everything the Julia side reads from the problem accessors
+ * (get_hybridproblem_* generics, src/AbstractHybridProblem.jl:30-311) and passes as keyword
+ * arguments to neg_elbo_gtf (src/elbo.jl:46-66). */
+typedef struct hvi_desc {
+  int32_t struct_size; /* = sizeof(hvi_desc), checked */
+  int32_t dtype;       /* HVI_F32 | HVI_F64 : eltype(ϕ) */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t flags;
+  int32_t n_P, n_M, n_obs, n_covar;
+  int32_t n_layers;
+  hvi_layer layers[HVI_MAX_LAYERS];
+  int32_t scale_kind;
+  int32_t _pad0;
+  double scale_a[HVI_MAX_PAR]; /* μ_k  (normal) | offset_k (range) */
+  double scale_b[HVI_MAX_PAR]; /* σ_k  (normal) | width_k  (range) */
+  int32_t trans_P[HVI_MAX_PAR];
+  int32_t trans_M[HVI_MAX_PAR];
+  hvi_prior prior_P[HVI_MAX_PAR];
+  hvi_prior prior_M[HVI_MAX_PAR];
+  int32_t n_cor_ends_P; /* cor_ends.P: last column of each block (src/cholesky.jl:262-290) */
+  int32_t cor_ends_P[HVI_MAX_PAR];
+  int32_t n_cor_ends_M;
+  int32_t cor_ends_M[HVI_MAX_PAR];
+  int32_t slot_src[4]; /* order: r0, r1, K1, K2 (src/DoubleMM/f_doubleMM.jl:47-65,101-139) */
+  int32_t slot_idx[4]; /* 0-based index into θP or θM */
+  double slot_fix[4];  /* value if HVI_SRC_FIX */
+  int32_t n_pbm_covar; /* pbm_covar_indices (src/elbo.jl:549-557), 0-based into θP */
+  int32_t pbm_covar_idx[HVI_MAX_PAR];
+  /* site sharding: exactly one plan of a job adds the terms that exist once per
+   * evaluation (prior and log-Jacobian of θP, entropy of the P block). */
+  int32_t count_globals;
+} hvi_desc;
+
+typedef struct hvi_plan hvi_plan;
+
+/* ---- bookkeeping ------------------------------------------------------------------- */
+int hvi_version(void);
+/* message of the last failure on this plan (NULL plan: last failure of plan_create) */
+const char* hvi_last_error(const hvi_plan* plan);
+
+/* Build a plan for one problem description.  Stands in for the keyword set captured by
+ * get_loss_elbo (src/HybridSolver.jl:293-324). */
+int hvi_plan_create(const hvi_desc* desc, hvi_plan** out);
+int hvi_plan_destroy(hvi_plan* plan);
+
+/* ---- integer index maps (bit-exact contract) ---------------------------------------- */
+/* length of ϕ = [ϕg ; ϕq] (src/init_hybrid_params.jl:25-33) */
+int64_t hvi_phi_len(const hvi_plan* plan);
+/* 0-based offsets/lengths of (ϕg, logσ2_ζP, coef_logσ2_ζMs, ρsP, ρsM, μP) inside ϕ --
+ * what ComponentArrayInterpreter/get_positions yields
+ * (src/ComponentArrayInterpreter.jl:281-288; layout src/init_hybrid_params.jl:119-124,
+ * src/HybridProblem.jl:101-104) */
+int hvi_phi_positions(const hvi_plan* plan, int64_t off[6], int64_t len[6]);
+/* src/cholesky.jl:30-37, 42-50, 233-247 (one-based, like the reference) */
+int hvi_vec2utri_pos(int64_t s, int64_t* row, int64_t* col);
+int64_t hvi_utri2vec_pos(int64_t row, int64_t col);
+int64_t hvi_cor_count(const int32_t* cor_ends, int32_t n_cor_ends);
+
+/* ---- data --------------------------------------------------------------------------- */
+/* Register one batch (a DataLoader element (xM, xP, y_o, y_unc), src/AbstractHybridProblem.jl:
+ * 179-184,206-207): xM (n_covar x n_site), xP (2 n_obs x n_site) rows S1;S2, y_o and y_unc
+ * (n_obs x n_site).  The library copies and re-tiles the batch into its own HBM layout. */
+int hvi_plan_set_data(hvi_plan* plan, int64_t n_site, const void* xM, const void* xP,
+                      const void* y_o, const void* y_unc, int mem_kind);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* neg_elbo_gtf_components + gradient (src/elbo.jl:30-88 under Zygote, src/HybridSolver.jl:
+ * 256-258).  phi: length hvi_phi_len; zP (n_MC x n_P) and zMs (n_MC x n_M*n_site), the
+ * standard-normal draws of sample_ζresid_norm (src/elbo.jl:605-606), column-major.
+ * comps[6] = (nLjoint, entropy_ζ, loss_penalty, nLy, neg_log_prior, neg_log_jac) and
+ * *nL = nLjoint - entropy_ζ + loss_penalty, always double (src/logden_normal.jl:74).
+ * grad: same element type and layout as phi; NULL = value only.  All array pointers are
+ * host or all device, per mem_kind; comps/nL are host. */
+int hvi_neg_elbo_grad(hvi_plan* plan, int32_t n_MC, const void* phi, const void* zP,
+                      const void* zMs, int mem_kind, double comps[6], double* nL, void* grad);
+
+/* Same evaluation with the draws produced on the device by a counter-based generator keyed
+ * by (seed, global site index, draw, parameter): stands in for CUDA.randn
+ * (ext/HybridVariationalInferenceCUDAExt.jl:82-86).  site_offset = first global site of
+ * this plan's shard so that results do not depend on the sharding. */
+int hvi_neg_elbo_grad_rng(hvi_plan* plan, int32_t n_MC, const void* phi, uint64_t seed,
+                          int64_t site_offset, int mem_kind, double comps[6], double* nL,
+                          void* grad);
+
+/* Device-resident, stream-ordered variant for multi-GPU jobs: writes
+ * out_dev[0 .. n_phi) = gradient (double), out_dev[n_phi .. n_phi+6) = components,
+ * out_dev[n_phi+6] = nL, out_dev[n_phi+7] = count of non-finite terms.  The caller sums
+ * out_dev across ranks (ncclAllReduce) -- SURVEY 8(e).  zP_dev/zMs_dev NULL = generator. */
+int hvi_neg_elbo_grad_async(hvi_plan* plan, int32_t n_MC, const void* phi_dev,
+                            const void* zP_dev, const void* zMs_dev, uint64_t seed,
+                            int64_t site_offset, double* out_dev, void* cuda_stream);
+
+/* generate_ζ (src/elbo.jl:472-521) forward only: ζsP (n_P x n_MC), ζsMs_tr
+ * (n_site x n_M x n_MC), σ (n_P + n_M n_site).  Used by sample_posterior (:432-458). */
+int hvi_generate_zeta(hvi_plan* plan, int32_t n_MC, const void* phi, const void* zP,
+                      const void* zMs, int mem_kind, void* zetaP, void* zetaMs_tr, void* sigma);
+
+/* g(xM, ϕg) alone (src/ModelApplicator.jl:19-23,163-176): mu_zeta (n_M x n_site). */
+int hvi_apply_g(hvi_plan* plan, const void* phi, int mem_kind, void* mu_zeta);
+
+/* number of kernels launched by this plan since creation (bench.py's gpu_launches) */
+int64_t hvi_launch_count(const hvi_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVI_B200_H */
