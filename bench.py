@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- site·MC-sample neg-ELBO+gradient evaluations per second (BASELINE.json metric).
+
+One "step" = one full evaluation (value and ∇ϕ) of the DoubleMM negative ELBO over the batch
+registered on each GPU.  Workload (config.workload): BASELINE config 4's per-evaluation shape,
+DoubleMM default scenario, Float32, n_MC = 64, `--sites` sites PER GPU (weak scaling; default
+10^7/8 · 8 = 1.25e6·8 → see --sites), draws ξ resident in HBM for `value`.
+
+  value   : device-timed (CUDA events on the launching stream, max over ranks), inputs resident
+            in HBM (site records, xM, ξ).  Inputs are ≫ the 126 MB L2, so no flush is needed.
+  e2e     : the same evaluation through the public host API (`NegElboPlan.set_data` +
+            `neg_elbo_withgradient`) with the batch (xM, xP, y_o, y_unc) and ϕ in pinned HOST
+            memory every step, H2D copies and the D2H read of (nL, ∇ϕ) inside the timed region;
+            ξ is drawn on the device from a seed (as the reference's CUDA.randn override does).
+  roofline: the fused streaming kernel timed alone with CUDA events inside the library
+            (hvi_plan_set_profiling), algorithmic bytes = nb·(4·(2·nO + nO + nO) + 2·4·nM + 4·nM·M)
+            (site records + μ_ζ/μ̄_ζ hand-off + ξ) ÷ its duration ÷ MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline: oracle/_ref/liboracle.so (C restatement, "port") on a bounded sample.
+
+`--impl reference` times the CPU restatement with all host threads (the Julia reference cannot
+run here: no julia binary) and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "site·MC-sample neg-ELBO+grad evals/sec (DoubleMM)"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--sites", type=int, default=10_000_000, help="sites per GPU")
+    ap.add_argument("--n-mc", type=int, default=64)
+    ap.add_argument("--scenario", default="", help="comma-separated DoubleMMCase scenario flags")
+    ap.add_argument("--cpu-sample-sites", type=int, default=200_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, prob):
+    return {"workload": f"DoubleMM (BASELINE config 4 shape) {args.sites:.0e} sites/GPU x n_MC={args.n_mc}, "
+                        f"scenario=({args.scenario}), MLP {'-'.join(str(l[0]) for l in prob.layers)}-{prob.layers[-1][1]}",
+            "sites_per_gpu": args.sites, "n_MC": args.n_mc, "n_phi": prob.n_phi,
+            "parallelism": f"site-sharded x{args.gpus}, allreduce of [grad; components]",
+            "l2": "inputs (>= 600 B/site x sites) exceed the 126 MB L2; no flush needed"}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_baseline(prob, n_MC, sample_sites, nthreads):
+    """Time the C restatement (oracle) on a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hvi_b200
+    from helpers import c_oracle_value_and_grad
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, sample_sites, seed=111)
+    zP, zMs = hvi_b200.draw_ξ(prob, sample_sites, n_MC)
+    ϕ = prob.init_ϕ(perturbed=True)
+    c_oracle_value_and_grad(prob, ϕ, data, zP, zMs, nthreads=nthreads)  # warm
+    t0 = time.perf_counter()
+    c_oracle_value_and_grad(prob, ϕ, data, zP, zMs, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return sample_sites * n_MC / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation cannot run here (Julia absent), so
+    the CPU restatement of it (oracle port) is timed with all host threads on the same config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import hvi_b200
+    prob = hvi_b200.DoubleMMCase(tuple(s for s in args.scenario.split(",") if s), dtype="f32")
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample_sites
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import c_oracle_value_and_grad
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, sample, seed=111)
+    zP, zMs = hvi_b200.draw_ξ(prob, sample, args.n_mc)
+    ϕ = prob.init_ϕ(perturbed=True)
+    for _ in range(args.warmup):
+        c_oracle_value_and_grad(prob, ϕ, data, zP, zMs, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_oracle_value_and_grad(prob, ϕ, data, zP, zMs, nthreads=cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = sample * args.n_mc / dt
+    sample_txt = f"{sample} sites x n_MC={args.n_mc} per step (bounded sample of the {args.sites:.0e}-site workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, prob),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_txt,
+                         "note": "C restatement of the reference (oracle/hvi_oracle.c, OpenMP); the Julia reference "
+                                 "itself cannot run in this image"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import hvi_b200
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    prob = hvi_b200.DoubleMMCase(tuple(s for s in args.scenario.split(",") if s), dtype="f32")
+    nb, M = args.sites, args.n_mc
+    # synthetic batch of this rank's site shard (generator restates gen_hybridproblem_synthetic)
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=111 + rank)
+    ϕ = prob.init_ϕ(perturbed=True)
+    plan = hvi_b200.NegElboPlan(prob, device=local, count_globals=(rank == 0))
+    pin = {k: torch.from_numpy(np.ascontiguousarray(data[k].T)).pin_memory() for k in ("xM", "xP", "y_o", "y_unc")}
+    host = {k: pin[k].numpy().T for k in pin}  # column-major views of the pinned buffers
+    plan.set_data(host["xM"], host["xP"], host["y_o"], host["y_unc"])
+    n_phi = plan.n_phi
+    ϕ_dev = torch.from_numpy(ϕ).to(dev)
+    out_dev = torch.zeros(n_phi + 8, dtype=torch.float64, device=dev)
+    # ξ resident in HBM (generated once, outside the timed region, by the library's generator via
+    # a seeded evaluation that leaves the draws in the plan -- then re-used through explicit buffers)
+    g = torch.Generator(device=dev)
+    g.manual_seed(211 + rank)
+    zP_dev = torch.randn(M * max(prob.n_P, 1), device=dev, generator=g)
+    zMs_dev = torch.randn(M * prob.n_M * nb, device=dev, generator=g)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        plan.neg_elbo_async(ϕ_dev, zP_dev, zMs_dev, out_dev, M, stream.cuda_stream)
+        if dist is not None:
+            dist.all_reduce(out_dev)  # one all-reduce of [∇ϕ ; components]: SURVEY 8(e)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = plan.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = plan.launch_count - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * nb * M / (ms_step * 1e-3)
+    res = out_dev.cpu().numpy()
+
+    # ---- roofline of the dominant kernel, timed alone by the library's own events ----------
+    plan.set_profiling(True)
+    acc = {}
+    for _ in range(max(3, args.steps // 2)):
+        plan.neg_elbo_async(ϕ_dev, zP_dev, zMs_dev, out_dev, M, stream.cuda_stream)
+        torch.cuda.synchronize()
+        for k, v in plan.kernel_times_ms().items():
+            acc.setdefault(k, []).append(v)
+    plan.set_profiling(False)
+    kt = {k: float(np.mean(v)) for k, v in acc.items()}
+    nO, nM = prob.n_obs, prob.n_M
+    alg_bytes = nb * (4 * 4 * nO + 2 * 4 * nM + 4 * nM * M)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (kt["stream"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_stream<float,2,2,8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kt}
+
+    # ---- end to end through the public host API ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h2d = sum(pin[k].numel() * 4 for k in pin) + n_phi * 4
+        d2h = n_phi * 4 + 8 * 8
+        n_e2e = max(2, min(args.steps, 5))
+        plan.set_data(host["xM"], host["xP"], host["y_o"], host["y_unc"])
+        plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=1)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            plan.set_data(host["xM"], host["xP"], host["y_o"], host["y_unc"])     # the step's batch: host → device
+            nL, comps, grad = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=2 + i)   # ϕ host → device, (nL, ∇ϕ) → host
+            if dist is not None:
+                gt = torch.from_numpy(grad).to(dev)
+                dist.all_reduce(gt)
+                grad = gt.cpu().numpy()
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * nb * M / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": float(tt.item()) * 1e3,
+               "what": "set_data(host batch) + neg_elbo_withgradient(host ϕ, device-drawn ξ) per step, wall clock"}
+        # data-resident variant (batch registered once, as gdev_hybridproblem_dataloader does)
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=2 + i)
+        barrier()
+        e2e["resident_value"] = world * nb * M / ((time.perf_counter() - t0) / n_e2e)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, prob),
+                "clocks": sampler.summary(), "gpu_launches": int(launches), "roofline": roofline,
+                "nL": float(res[n_phi + 6]), "nonfinite": float(res[n_phi + 7])}
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            v, dt = cpu_baseline(prob, M, args.cpu_sample_sites, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{args.cpu_sample_sites} sites x n_MC={M}, one evaluation, {dt:.1f} s",
+                                    "note": "oracle/hvi_oracle.c (C restatement of the Julia reference), f32, 1 thread"}
+        print(json.dumps(line, ensure_ascii=False))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,602 @@
+// hvi_capi.cu -- plan management and the extern "C" boundary (include/hvi_b200.h).
+// Reference citations (file:line) are relative to /root/reference.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "hvi_internal.cuh"
+
+using namespace hvi;
+
+struct hvi_plan {
+  hvi_desc desc;
+  int dtype;
+  size_t es;  // element size
+  Cfg<float> cf;
+  Cfg<double> cd;
+  cudaStream_t stream;
+  int sm_count;
+  int64_t launches;
+  std::string err;
+  // data
+  int64_t nb;
+  void *d_xM, *d_rec, *d_mu, *d_mubar;
+  double const_nly;
+  int64_t anomalies;
+  // per-evaluation scratch
+  void* d_phi;
+  void* d_zP; int64_t cap_zP;
+  void* d_zMs; int64_t cap_zMs;
+  void* d_ec;
+  void* d_pdraw; int64_t cap_pdraw;
+  double* d_part_stream; int max_rows;
+  double* d_part_mlp; int max_blk;
+  double* d_out;
+  void* d_grad;
+  double* h_out;  // pinned
+  void* h_grad;   // pinned
+  // optional per-kernel timing (CUDA events on the launching stream)
+  int profiling;
+  cudaEvent_t ev[8];
+  int n_ev;
+};
+
+static thread_local std::string g_create_err;
+
+#define PLAN_FAIL(plan, code, ...)                    \
+  do {                                                \
+    char buf_[512];                                   \
+    snprintf(buf_, sizeof buf_, __VA_ARGS__);         \
+    (plan)->err = buf_;                               \
+    return (code);                                    \
+  } while (0)
+
+#define CU(plan, call)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) PLAN_FAIL(plan, HVI_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+static int cor_count_n(int n) { return (n - 1) * n / 2; }
+
+// per column: first column of its block, offset of its packed coefficients; returns Σ counts.
+// Uses the intended cumulative offsets (src/cholesky.jl:262-290).
+static int block_maps(const int32_t* ends, int n_ends, int n, int* blk_start, int* rho_off) {
+  int total = 0, start = 0;
+  if (n == 0) return 0;
+  if (n_ends == 0) {
+    for (int k = 0; k < n; k++) { blk_start[k] = k; rho_off[k] = 0; }
+    return 0;
+  }
+  for (int b = 0; b < n_ends; b++) {
+    const int end = ends[b];
+    for (int k = start; k < end; k++) {
+      const int kk = k - start;
+      blk_start[k] = start;
+      rho_off[k] = total + kk * (kk - 1) / 2;
+    }
+    total += cor_count_n(end - start);
+    start = end;
+  }
+  return total;
+}
+
+template <typename T>
+static void fill_cfg(const hvi_desc& d, Cfg<T>& c) {
+  memset(&c, 0, sizeof c);
+  c.nP = d.n_P; c.nM = d.n_M; c.nO = d.n_obs; c.nC = d.n_covar;
+  for (int i = 0; i < MAXP; i++) {
+    c.transP[i] = d.trans_P[i]; c.transM[i] = d.trans_M[i];
+    c.prP_kind[i] = i < d.n_P ? d.prior_P[i].kind : 0;
+    c.prM_kind[i] = i < d.n_M ? d.prior_M[i].kind : 0;
+    c.prP_a[i] = (T)d.prior_P[i].a; c.prM_a[i] = (T)d.prior_M[i].a;
+    c.prP_ib[i] = c.prP_kind[i] ? (T)(1.0 / d.prior_P[i].b) : T(0);
+    c.prM_ib[i] = c.prM_kind[i] ? (T)(1.0 / d.prior_M[i].b) : T(0);
+    c.prP_c0[i] = c.prP_kind[i] ? log(d.prior_P[i].b) + 0.9189385332046727418 : 0.0;
+    c.prM_c0[i] = c.prM_kind[i] ? log(d.prior_M[i].b) + 0.9189385332046727418 : 0.0;
+    c.scale_a[i] = (T)d.scale_a[i]; c.scale_b[i] = (T)d.scale_b[i];
+    c.pbm_covar_idx[i] = d.pbm_covar_idx[i];
+  }
+  for (int s = 0; s < 4; s++) {
+    c.slot_code[s] = d.slot_src[s] == HVI_SRC_P ? d.slot_idx[s] : d.slot_src[s] == HVI_SRC_M ? d.n_P + d.slot_idx[s] : -1;
+    c.slot_fix[s] = (T)d.slot_fix[s];
+  }
+  c.omit_priors = (d.flags & HVI_FLAG_OMIT_PRIORS) ? 1 : 0;
+  c.count_globals = d.count_globals;
+  if (sizeof(T) == 4) { c.clamp_lo = (T)sqrt(1.17549435082228750797e-38); c.clamp_hi = (T)sqrt(3.40282346638528859812e+38); }
+  else { c.clamp_lo = (T)sqrt(2.2250738585072014e-308); c.clamp_hi = (T)sqrt(1.7976931348623157e+308); }
+  int p = 0;
+  c.nL = d.n_layers; c.sum_width = 0; c.sum_out = 0; c.max_width = 0;
+  for (int l = 0; l < d.n_layers; l++) {
+    c.l_in[l] = d.layers[l].n_in; c.l_out[l] = d.layers[l].n_out; c.l_act[l] = d.layers[l].act;
+    c.l_bias[l] = d.layers[l].has_bias;
+    c.woff[l] = p; p += c.l_in[l] * c.l_out[l];
+    c.boff[l] = p; if (c.l_bias[l]) p += c.l_out[l];
+    c.sum_width += c.l_in[l]; c.sum_out += c.l_out[l];
+    if (c.l_in[l] > c.max_width) c.max_width = c.l_in[l];
+    if (c.l_out[l] > c.max_width) c.max_width = c.l_out[l];
+  }
+  c.sum_width += d.layers[d.n_layers - 1].n_out;
+  c.nphig = p;
+  c.o_ls2P = p; p += c.nP;
+  c.o_coef = p; p += 2 * c.nM;
+  c.o_rhoP = p; p += block_maps(d.cor_ends_P, d.n_cor_ends_P, c.nP, c.blkP_start, c.rhoP_off);
+  c.o_rhoM = p; p += block_maps(d.cor_ends_M, d.n_cor_ends_M, c.nM, c.blkM_start, c.rhoM_off);
+  c.o_muP = p; p += c.nP;
+  c.nphi = p;
+  c.scale_kind = d.scale_kind;
+  c.npc = d.n_pbm_covar;
+}
+
+static const char* validate(const hvi_desc* d) {
+  if (!d) return "desc is NULL";
+  if (d->struct_size != (int32_t)sizeof(hvi_desc)) return "hvi_desc.struct_size mismatch (ABI)";
+  if (d->dtype != HVI_F32 && d->dtype != HVI_F64) return "dtype must be HVI_F32 or HVI_F64";
+  if (d->n_P < 0 || d->n_P > MAXP || d->n_M < 1 || d->n_M > MAXP) return "n_P/n_M out of range";
+  if (d->n_layers < 1 || d->n_layers > MAXL) return "n_layers out of range";
+  if (d->n_pbm_covar < 0 || d->n_pbm_covar > d->n_P) return "n_pbm_covar out of range";
+  for (int c = 0; c < d->n_pbm_covar; c++)
+    if (d->pbm_covar_idx[c] < 0 || d->pbm_covar_idx[c] >= d->n_P) return "pbm_covar_idx out of range";
+  if (d->layers[0].n_in != d->n_covar + d->n_pbm_covar) return "first layer n_in != n_covar + n_pbm_covar";
+  for (int l = 0; l < d->n_layers; l++) {
+    if (d->layers[l].n_in < 1 || d->layers[l].n_out < 1) return "layer sizes must be positive";
+    if (l > 0 && d->layers[l].n_in != d->layers[l - 1].n_out) return "layer sizes do not chain";
+    if (d->layers[l].n_in > HVI_MAX_WIDTH || d->layers[l].n_out > HVI_MAX_WIDTH)
+      return "layer wider than HVI_MAX_WIDTH: not supported by the CUDA-core applicator";
+  }
+  if (d->layers[d->n_layers - 1].n_out < d->n_M) return "network has fewer outputs than n_M";
+  if (d->n_cor_ends_P < 0 || d->n_cor_ends_P > MAXP || d->n_cor_ends_M < 0 || d->n_cor_ends_M > MAXP)
+    return "n_cor_ends out of range";
+  if (d->n_P > 0 && d->n_cor_ends_P > 0 && d->cor_ends_P[d->n_cor_ends_P - 1] != d->n_P) return "cor_ends_P must end at n_P";
+  if (d->n_cor_ends_M > 0 && d->cor_ends_M[d->n_cor_ends_M - 1] != d->n_M) return "cor_ends_M must end at n_M";
+  for (int b = 1; b < d->n_cor_ends_P; b++) if (d->cor_ends_P[b] <= d->cor_ends_P[b - 1]) return "cor_ends_P not increasing";
+  for (int b = 1; b < d->n_cor_ends_M; b++) if (d->cor_ends_M[b] <= d->cor_ends_M[b - 1]) return "cor_ends_M not increasing";
+  for (int s = 0; s < 4; s++) {
+    if (d->slot_src[s] == HVI_SRC_P && (d->slot_idx[s] < 0 || d->slot_idx[s] >= d->n_P)) return "slot_idx (P) out of range";
+    if (d->slot_src[s] == HVI_SRC_M && (d->slot_idx[s] < 0 || d->slot_idx[s] >= d->n_M)) return "slot_idx (M) out of range";
+    if (d->slot_src[s] < 0 || d->slot_src[s] > 2) return "slot_src invalid";
+  }
+  for (int i = 0; i < d->n_P; i++) {
+    if (d->trans_P[i] < 0 || d->trans_P[i] > 2) return "trans_P invalid";
+    if (d->prior_P[i].kind < 0 || d->prior_P[i].kind > 2) return "prior_P kind invalid";
+    if (d->prior_P[i].kind && !(d->prior_P[i].b > 0)) return "prior_P scale must be positive";
+  }
+  for (int i = 0; i < d->n_M; i++) {
+    if (d->trans_M[i] < 0 || d->trans_M[i] > 2) return "trans_M invalid";
+    if (d->prior_M[i].kind < 0 || d->prior_M[i].kind > 2) return "prior_M kind invalid";
+    if (d->prior_M[i].kind && !(d->prior_M[i].b > 0)) return "prior_M scale must be positive";
+  }
+  if (!stream_supported(d->n_P, d->n_M, d->n_obs)) return "(n_P, n_M, n_obs) combination has no kernel instantiation";
+  if (d->n_pbm_covar > 0) return "pbm_covars not supported yet by this build";
+  return nullptr;
+}
+
+extern "C" int hvi_version(void) { return HVI_ABI_VERSION; }
+
+extern "C" const char* hvi_last_error(const hvi_plan* plan) { return plan ? plan->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
+  if (!out) { g_create_err = "out is NULL"; return HVI_EINVAL; }
+  *out = nullptr;
+  if (const char* msg = validate(desc)) { g_create_err = msg; return HVI_EINVAL; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this path has no CPU fallback)";
+    return HVI_ECUDA;
+  }
+  if (desc->device < 0 || desc->device >= ndev) { g_create_err = "device ordinal out of range"; return HVI_EINVAL; }
+  hvi_plan* p = new (std::nothrow) hvi_plan();
+  if (!p) { g_create_err = "out of host memory"; return HVI_ENOMEM; }
+  p->desc = *desc;
+  p->dtype = desc->dtype;
+  p->es = desc->dtype == HVI_F32 ? 4 : 8;
+  fill_cfg<float>(*desc, p->cf);
+  fill_cfg<double>(*desc, p->cd);
+  p->nb = 0; p->launches = 0;
+  p->d_xM = p->d_rec = p->d_mu = p->d_mubar = nullptr;
+  p->d_phi = p->d_zP = p->d_zMs = p->d_ec = p->d_pdraw = nullptr;
+  p->cap_zP = p->cap_zMs = p->cap_pdraw = 0;
+  p->d_part_stream = p->d_part_mlp = p->d_out = nullptr;
+  p->d_grad = nullptr; p->h_out = nullptr; p->h_grad = nullptr;
+  p->const_nly = 0; p->anomalies = 0;
+  p->profiling = 0; p->n_ev = 0;
+  for (auto& e_ : p->ev) e_ = nullptr;
+#define CRE(call)                                                                   \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      g_create_err = std::string(#call) + ": " + cudaGetErrorString(e_);            \
+      hvi_plan_destroy(p);                                                          \
+      return HVI_ECUDA;                                                             \
+    }                                                                               \
+  } while (0)
+  CRE(cudaSetDevice(desc->device));
+  cudaDeviceProp prop;
+  CRE(cudaGetDeviceProperties(&prop, desc->device));
+  p->sm_count = prop.multiProcessorCount;
+  p->stream = nullptr;
+  CRE(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  const int nphi = p->cf.nphi;
+  p->max_rows = stream_max_rows(p->sm_count);
+  p->max_blk = mlp_bwd_max_blocks(p->sm_count);
+  CRE(cudaMalloc(&p->d_phi, p->es * (size_t)nphi));
+  CRE(cudaMalloc(&p->d_ec, sizeof(EvalConsts<double>)));
+  CRE(cudaMalloc(&p->d_part_stream, sizeof(double) * (size_t)p->max_rows * nacc(p->cf.nP, p->cf.nM)));
+  CRE(cudaMalloc(&p->d_part_mlp, sizeof(double) * (size_t)p->max_blk * p->cf.nphig));
+  CRE(cudaMalloc(&p->d_out, sizeof(double) * (size_t)(nphi + 8)));
+  CRE(cudaMalloc(&p->d_grad, p->es * (size_t)nphi));
+  CRE(cudaMallocHost(&p->h_out, sizeof(double) * (size_t)(nphi + 8)));
+  CRE(cudaMallocHost(&p->h_grad, p->es * (size_t)nphi));
+#undef CRE
+  *out = p;
+  return HVI_OK;
+}
+
+extern "C" int hvi_plan_destroy(hvi_plan* p) {
+  if (!p) return HVI_OK;
+  cudaSetDevice(p->desc.device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  void* dev[] = {p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
+                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_grad};
+  for (void* q : dev) if (q) cudaFree(q);
+  if (p->h_out) cudaFreeHost(p->h_out);
+  if (p->h_grad) cudaFreeHost(p->h_grad);
+  for (auto& e_ : p->ev) if (e_) cudaEventDestroy(e_);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+  return HVI_OK;
+}
+
+extern "C" int64_t hvi_phi_len(const hvi_plan* p) { return p ? p->cf.nphi : -1; }
+
+extern "C" int hvi_phi_positions(const hvi_plan* p, int64_t off[6], int64_t len[6]) {
+  if (!p || !off || !len) return HVI_EINVAL;
+  const Cfg<float>& c = p->cf;
+  const int o[7] = {0, c.o_ls2P, c.o_coef, c.o_rhoP, c.o_rhoM, c.o_muP, c.nphi};
+  for (int i = 0; i < 6; i++) { off[i] = o[i]; len[i] = o[i + 1] - o[i]; }
+  return HVI_OK;
+}
+
+// src/cholesky.jl:30-37 (one-based)
+extern "C" int hvi_vec2utri_pos(int64_t s, int64_t* row, int64_t* col) {
+  if (s < 1 || !row || !col) return HVI_EINVAL;
+  int64_t c = (int64_t)ceil(-0.5 + sqrt(0.25 + 2.0 * (double)s));
+  while (c * (c + 1) / 2 < s) c++;          // guard the float inversion
+  while ((c - 1) * c / 2 >= s) c--;
+  const int64_t cl = c - 1;
+  *row = s - cl * (cl + 1) / 2;
+  *col = c;
+  return HVI_OK;
+}
+// src/cholesky.jl:42-50
+extern "C" int64_t hvi_utri2vec_pos(int64_t row, int64_t col) {
+  if (row < 1 || row > col) return -1;
+  return (col - 1) * col / 2 + row;
+}
+// src/cholesky.jl:233-247
+extern "C" int64_t hvi_cor_count(const int32_t* cor_ends, int32_t n) {
+  if (n <= 0 || !cor_ends) return 0;
+  int64_t tot = 0;
+  for (int i = 0; i < n; i++) {
+    const int nb = i == 0 ? cor_ends[0] : cor_ends[i] - cor_ends[i - 1];
+    tot += (int64_t)(nb - 1) * nb / 2;
+  }
+  return tot;
+}
+
+extern "C" int64_t hvi_launch_count(const hvi_plan* p) { return p ? p->launches : -1; }
+
+extern "C" int hvi_plan_set_profiling(hvi_plan* p, int on) {
+  if (!p) return HVI_EINVAL;
+  CU(p, cudaSetDevice(p->desc.device));
+  if (on)
+    for (auto& evt : p->ev) if (!evt) CU(p, cudaEventCreate(&evt));
+  p->profiling = on ? 1 : 0;
+  p->n_ev = 0;
+  return HVI_OK;
+}
+
+extern "C" int hvi_plan_kernel_times(hvi_plan* p, float ms[5]) {
+  if (!p || !ms) return HVI_EINVAL;
+  if (!p->profiling || p->n_ev < 6) PLAN_FAIL(p, HVI_EINVAL, "no profiled evaluation recorded");
+  CU(p, cudaEventSynchronize(p->ev[5]));
+  for (int i = 0; i < 5; i++) CU(p, cudaEventElapsedTime(&ms[i], p->ev[i], p->ev[i + 1]));
+  return HVI_OK;
+}
+
+static cudaError_t copy_in(void* dst, const void* src, size_t bytes, int mem_kind, cudaStream_t s) {
+  return cudaMemcpyAsync(dst, src, bytes, mem_kind == HVI_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
+}
+
+template <typename T>
+static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, const void* y_o, const void* y_unc,
+                      int mem_kind) {
+  const int nO = p->desc.n_obs, nC = p->desc.n_covar, nM = p->desc.n_M;
+  if (nb != p->nb) {
+    for (void** q : {&p->d_xM, &p->d_rec, &p->d_mu, &p->d_mubar}) { if (*q) cudaFree(*q); *q = nullptr; }
+    p->nb = 0;
+    const int64_t ntiles = (nb + 31) / 32;
+    CU(p, cudaMalloc(&p->d_xM, sizeof(T) * (size_t)nC * nb));
+    CU(p, cudaMalloc(&p->d_rec, sizeof(T) * (size_t)ntiles * 32 * 4 * nO));
+    CU(p, cudaMalloc(&p->d_mu, sizeof(T) * (size_t)nM * nb));
+    CU(p, cudaMalloc(&p->d_mubar, sizeof(T) * (size_t)nM * nb));
+    p->nb = nb;
+  }
+  CU(p, copy_in(p->d_xM, xM, sizeof(T) * (size_t)nC * nb, mem_kind, p->stream));
+  const T *dxP = (const T*)xP, *dyo = (const T*)y_o, *dyu = (const T*)y_unc;
+  void* tmp = nullptr;
+  if (mem_kind == HVI_MEM_HOST) {
+    const size_t n1 = (size_t)2 * nO * nb, n2 = (size_t)nO * nb;
+    CU(p, cudaMalloc(&tmp, sizeof(T) * (n1 + 2 * n2)));
+    T* t = (T*)tmp;
+    CU(p, copy_in(t, xP, sizeof(T) * n1, mem_kind, p->stream));
+    CU(p, copy_in(t + n1, y_o, sizeof(T) * n2, mem_kind, p->stream));
+    CU(p, copy_in(t + n1 + n2, y_unc, sizeof(T) * n2, mem_kind, p->stream));
+    dxP = t; dyo = t + n1; dyu = t + n1 + n2;
+  }
+  Launch L{p->stream, p->sm_count, &p->launches};
+  int nrows = 0;
+  // the stream partial buffer doubles as scratch for the 2·nwarps preprocess partials
+  const int NACC = nacc(p->cf.nP, p->cf.nM);
+  if ((size_t)2 * p->sm_count * 8 * 8 > (size_t)p->max_rows * NACC) PLAN_FAIL(p, HVI_EINVAL, "internal: scratch too small");
+  CU(p, launch_preprocess<T>(L, nO, nb, dxP, dyo, dyu, (T*)p->d_rec, p->d_part_stream, &nrows));
+  std::vector<double> h((size_t)2 * nrows);
+  CU(p, cudaMemcpyAsync(h.data(), p->d_part_stream, sizeof(double) * 2 * nrows, cudaMemcpyDeviceToHost, p->stream));
+  CU(p, cudaStreamSynchronize(p->stream));
+  if (tmp) cudaFree(tmp);
+  double c = 0, an = 0;
+  for (int r = 0; r < nrows; r++) { c += h[2 * r]; an += h[2 * r + 1]; }
+  p->const_nly = c;
+  p->anomalies = (int64_t)an;
+  return HVI_OK;
+}
+
+extern "C" int hvi_plan_set_data(hvi_plan* p, int64_t n_site, const void* xM, const void* xP, const void* y_o,
+                                 const void* y_unc, int mem_kind) {
+  if (!p) return HVI_EINVAL;
+  if (n_site < 1 || !xM || !xP || !y_o || !y_unc) PLAN_FAIL(p, HVI_EINVAL, "set_data: n_site must be >= 1 and arrays non-NULL");
+  if (mem_kind != HVI_MEM_HOST && mem_kind != HVI_MEM_DEVICE) PLAN_FAIL(p, HVI_EINVAL, "set_data: bad mem_kind");
+  CU(p, cudaSetDevice(p->desc.device));
+  return p->dtype == HVI_F32 ? set_data_t<float>(p, n_site, xM, xP, y_o, y_unc, mem_kind)
+                             : set_data_t<double>(p, n_site, xM, xP, y_o, y_unc, mem_kind);
+}
+
+static int ensure(hvi_plan* p, void** buf, int64_t* cap, int64_t need_bytes) {
+  if (*cap >= need_bytes) return HVI_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr; *cap = 0;
+  CU(p, cudaMalloc(buf, (size_t)need_bytes));
+  *cap = need_bytes;
+  return HVI_OK;
+}
+
+template <typename T> static const Cfg<T>& cfg_of(const hvi_plan* p);
+template <> const Cfg<float>& cfg_of<float>(const hvi_plan* p) { return p->cf; }
+template <> const Cfg<double>& cfg_of<double>(const hvi_plan* p) { return p->cd; }
+
+// enqueue the whole evaluation on `s`; all pointers are device pointers
+template <typename T>
+static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* zMs, double* out, T* grad_T,
+                        cudaStream_t s) {
+  const Cfg<T>& cfg = cfg_of<T>(p);
+  int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)sizeof(T) * 4 * (cfg.nP > 0 ? cfg.nP : 1) * M);
+  if (rc) return rc;
+  Launch L{s, p->sm_count, &p->launches};
+  EvalConsts<T>* ec = (EvalConsts<T>*)p->d_ec;
+  T* pdraw = (T*)p->d_pdraw;
+  int iev = 0;
+#define MARK() do { if (p->profiling) CU(p, cudaEventRecord(p->ev[iev++], s)); } while (0)
+  MARK();
+  CU(p, launch_prologue<T>(L, cfg, phi, zP, M, ec, pdraw));
+  MARK();
+  CU(p, launch_mlp_fwd<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (T*)p->d_mu));
+  MARK();
+  StreamArgs<T> a;
+  a.rec = (const T*)p->d_rec; a.mu = (const T*)p->d_mu; a.zMs = zMs;
+  a.thP = pdraw + (size_t)2 * cfg.nP * M; a.gP = pdraw + (size_t)3 * cfg.nP * M; a.zP = zP;
+  a.ec = ec; a.mubar = (T*)p->d_mubar; a.partials = p->d_part_stream; a.nb = p->nb; a.M = M;
+  a.staged = (M % (16 / (int)sizeof(T)) == 0) && (((uintptr_t)zMs & 15) == 0);
+  int nrows = 0, nblk = 0;
+  CU(p, launch_stream<T>(L, cfg, a, &nrows, p->max_rows));
+  MARK();
+  CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_mubar, p->nb, p->d_part_mlp, &nblk, p->max_blk));
+  MARK();
+  CU(p, launch_finalize<T>(L, cfg, phi, zP, pdraw, ec, p->d_part_stream, nrows, p->d_part_mlp, nblk, p->const_nly, p->nb,
+                           M, out, grad_T));
+  MARK();
+#undef MARK
+  p->n_ev = iev;
+  return HVI_OK;
+}
+
+template <typename T>
+static int eval_sync_t(hvi_plan* p, int M, const void* phi, const void* zP, const void* zMs, bool use_rng, uint64_t seed,
+                       int64_t site_offset, int mem_kind, double comps[6], double* nL, void* grad) {
+  const Cfg<T>& cfg = cfg_of<T>(p);
+  const int nphi = cfg.nphi;
+  cudaStream_t s = p->stream;
+  const T* dphi = (const T*)phi;
+  if (mem_kind == HVI_MEM_HOST) {
+    CU(p, cudaMemcpyAsync(p->d_phi, phi, sizeof(T) * nphi, cudaMemcpyHostToDevice, s));
+    dphi = (const T*)p->d_phi;
+  }
+  const int64_t nzP = (int64_t)M * (cfg.nP > 0 ? cfg.nP : 1), nzM = (int64_t)M * cfg.nM * p->nb;
+  const T *dzP = (const T*)zP, *dzM = (const T*)zMs;
+  if (use_rng || mem_kind == HVI_MEM_HOST) {
+    int rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)sizeof(T) * nzP);
+    if (rc) return rc;
+    rc = ensure(p, &p->d_zMs, &p->cap_zMs, (int64_t)sizeof(T) * nzM);
+    if (rc) return rc;
+    if (use_rng) {
+      Launch L{s, p->sm_count, &p->launches};
+      // global-block draws: columns keyed far above any site column
+      CU(p, launch_gen_normal<T>(L, (T*)p->d_zP, cfg.nP, M, seed, (int64_t)1 << 62));
+      CU(p, launch_gen_normal<T>(L, (T*)p->d_zMs, (int64_t)cfg.nM * p->nb, M, seed, site_offset * cfg.nM));
+    } else {
+      if (cfg.nP > 0) CU(p, cudaMemcpyAsync(p->d_zP, zP, sizeof(T) * (size_t)M * cfg.nP, cudaMemcpyHostToDevice, s));
+      CU(p, cudaMemcpyAsync(p->d_zMs, zMs, sizeof(T) * (size_t)nzM, cudaMemcpyHostToDevice, s));
+    }
+    dzP = (const T*)p->d_zP; dzM = (const T*)p->d_zMs;
+  }
+  const bool want_grad = grad != nullptr;
+  int rc = enqueue_eval<T>(p, M, dphi, dzP, dzM, p->d_out, want_grad ? (T*)p->d_grad : nullptr, s);
+  if (rc) return rc;
+  CU(p, cudaMemcpyAsync(p->h_out + nphi, p->d_out + nphi, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+  if (want_grad) {
+    if (mem_kind == HVI_MEM_HOST) CU(p, cudaMemcpyAsync(p->h_grad, p->d_grad, sizeof(T) * nphi, cudaMemcpyDeviceToHost, s));
+    else CU(p, cudaMemcpyAsync(grad, p->d_grad, sizeof(T) * nphi, cudaMemcpyDeviceToDevice, s));
+  }
+  CU(p, cudaStreamSynchronize(s));
+  if (want_grad && mem_kind == HVI_MEM_HOST) memcpy(grad, p->h_grad, sizeof(T) * nphi);
+  const double* C = p->h_out + nphi;
+  if (comps) for (int i = 0; i < 6; i++) comps[i] = C[i];
+  if (nL) *nL = C[6];
+  if (p->anomalies > 0) {
+    // reference behaviour: NaN loss; we evaluate the masked value and flag it
+    PLAN_FAIL(p, HVI_ENONFINITE, "%lld observation(s) are finite where a driver is not: the reference returns NaN here",
+              (long long)p->anomalies);
+  }
+  if (C[7] != 0.0) PLAN_FAIL(p, HVI_ENONFINITE, "non-finite value or gradient (%g entries)", C[7]);
+  return HVI_OK;
+}
+
+static int check_eval_args(hvi_plan* p, int32_t n_MC, const void* phi, int mem_kind) {
+  if (!p) return HVI_EINVAL;
+  if (p->nb <= 0) PLAN_FAIL(p, HVI_ENODATA, "hvi_plan_set_data has not been called");
+  if (n_MC < 1) PLAN_FAIL(p, HVI_EINVAL, "n_MC must be >= 1");
+  if (!phi) PLAN_FAIL(p, HVI_EINVAL, "phi is NULL");
+  if (mem_kind != HVI_MEM_HOST && mem_kind != HVI_MEM_DEVICE) PLAN_FAIL(p, HVI_EINVAL, "bad mem_kind");
+  CU(p, cudaSetDevice(p->desc.device));
+  return HVI_OK;
+}
+
+extern "C" int hvi_neg_elbo_grad(hvi_plan* p, int32_t n_MC, const void* phi, const void* zP, const void* zMs, int mem_kind,
+                                 double comps[6], double* nL, void* grad) {
+  int rc = check_eval_args(p, n_MC, phi, mem_kind);
+  if (rc) return rc;
+  if (!zMs || (p->desc.n_P > 0 && !zP)) PLAN_FAIL(p, HVI_EINVAL, "zP/zMs are NULL (use hvi_neg_elbo_grad_rng for device draws)");
+  return p->dtype == HVI_F32 ? eval_sync_t<float>(p, n_MC, phi, zP, zMs, false, 0, 0, mem_kind, comps, nL, grad)
+                             : eval_sync_t<double>(p, n_MC, phi, zP, zMs, false, 0, 0, mem_kind, comps, nL, grad);
+}
+
+extern "C" int hvi_neg_elbo_grad_rng(hvi_plan* p, int32_t n_MC, const void* phi, uint64_t seed, int64_t site_offset,
+                                     int mem_kind, double comps[6], double* nL, void* grad) {
+  int rc = check_eval_args(p, n_MC, phi, mem_kind);
+  if (rc) return rc;
+  return p->dtype == HVI_F32
+             ? eval_sync_t<float>(p, n_MC, phi, nullptr, nullptr, true, seed, site_offset, mem_kind, comps, nL, grad)
+             : eval_sync_t<double>(p, n_MC, phi, nullptr, nullptr, true, seed, site_offset, mem_kind, comps, nL, grad);
+}
+
+template <typename T>
+static int eval_async_t(hvi_plan* p, int M, const void* phi, const void* zP, const void* zMs, uint64_t seed,
+                        int64_t site_offset, double* out, cudaStream_t s) {
+  const Cfg<T>& cfg = cfg_of<T>(p);
+  const T *dzP = (const T*)zP, *dzM = (const T*)zMs;
+  if (!zMs) {
+    const int64_t nzP = (int64_t)M * (cfg.nP > 0 ? cfg.nP : 1), nzM = (int64_t)M * cfg.nM * p->nb;
+    int rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)sizeof(T) * nzP);
+    if (rc) return rc;
+    rc = ensure(p, &p->d_zMs, &p->cap_zMs, (int64_t)sizeof(T) * nzM);
+    if (rc) return rc;
+    Launch L{s, p->sm_count, &p->launches};
+    CU(p, launch_gen_normal<T>(L, (T*)p->d_zP, cfg.nP, M, seed, (int64_t)1 << 62));
+    CU(p, launch_gen_normal<T>(L, (T*)p->d_zMs, (int64_t)cfg.nM * p->nb, M, seed, site_offset * cfg.nM));
+    dzP = (const T*)p->d_zP; dzM = (const T*)p->d_zMs;
+  }
+  return enqueue_eval<T>(p, M, (const T*)phi, dzP, dzM, out, nullptr, s);
+}
+
+extern "C" int hvi_neg_elbo_grad_async(hvi_plan* p, int32_t n_MC, const void* phi_dev, const void* zP_dev,
+                                       const void* zMs_dev, uint64_t seed, int64_t site_offset, double* out_dev,
+                                       void* cuda_stream) {
+  int rc = check_eval_args(p, n_MC, phi_dev, HVI_MEM_DEVICE);
+  if (rc) return rc;
+  if (!out_dev) PLAN_FAIL(p, HVI_EINVAL, "out_dev is NULL");
+  if (zMs_dev && p->desc.n_P > 0 && !zP_dev) PLAN_FAIL(p, HVI_EINVAL, "zP_dev is NULL");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  return p->dtype == HVI_F32 ? eval_async_t<float>(p, n_MC, phi_dev, zP_dev, zMs_dev, seed, site_offset, out_dev, s)
+                             : eval_async_t<double>(p, n_MC, phi_dev, zP_dev, zMs_dev, seed, site_offset, out_dev, s);
+}
+
+template <typename T>
+static int generate_zeta_t(hvi_plan* p, int M, const void* phi, const void* zP, const void* zMs, int mem_kind, void* zetaP,
+                           void* zetaMs_tr, void* sigma) {
+  const Cfg<T>& cfg = cfg_of<T>(p);
+  cudaStream_t s = p->stream;
+  const int nphi = cfg.nphi, nP = cfg.nP, nM = cfg.nM;
+  const int64_t nb = p->nb;
+  const size_t nzP = (size_t)M * (nP > 0 ? nP : 1), nzM = (size_t)M * nM * nb;
+  const T *dphi = (const T*)phi, *dzP = (const T*)zP, *dzM = (const T*)zMs;
+  void *o1 = zetaP, *o2 = zetaMs_tr, *o3 = sigma, *tmp = nullptr;
+  if (mem_kind == HVI_MEM_HOST) {
+    CU(p, cudaMemcpyAsync(p->d_phi, phi, sizeof(T) * nphi, cudaMemcpyHostToDevice, s));
+    int rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)(sizeof(T) * nzP));
+    if (rc) return rc;
+    rc = ensure(p, &p->d_zMs, &p->cap_zMs, (int64_t)(sizeof(T) * nzM));
+    if (rc) return rc;
+    if (nP > 0) CU(p, cudaMemcpyAsync(p->d_zP, zP, sizeof(T) * (size_t)M * nP, cudaMemcpyHostToDevice, s));
+    CU(p, cudaMemcpyAsync(p->d_zMs, zMs, sizeof(T) * nzM, cudaMemcpyHostToDevice, s));
+    dphi = (const T*)p->d_phi; dzP = (const T*)p->d_zP; dzM = (const T*)p->d_zMs;
+    CU(p, cudaMalloc(&tmp, sizeof(T) * ((size_t)nP * M + nzM + nP + (size_t)nM * nb)));
+    o1 = tmp; o2 = (T*)tmp + (size_t)nP * M; o3 = (T*)o2 + nzM;
+  }
+  int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)sizeof(T) * 4 * (nP > 0 ? nP : 1) * M);
+  if (rc) { if (tmp) cudaFree(tmp); return rc; }
+  Launch L{s, p->sm_count, &p->launches};
+  EvalConsts<T>* ec = (EvalConsts<T>*)p->d_ec;
+  T* pdraw = (T*)p->d_pdraw;
+  StreamArgs<T> a;
+  memset(&a, 0, sizeof a);
+  a.mu = (const T*)p->d_mu; a.zMs = dzM; a.zP = dzP; a.ec = ec; a.nb = nb; a.M = M;
+  cudaError_t e = launch_prologue<T>(L, cfg, dphi, dzP, M, ec, pdraw);
+  if (e == cudaSuccess) e = launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, nb, (T*)p->d_mu);
+  if (e == cudaSuccess) e = launch_generate_zeta<T>(L, cfg, a, pdraw, (T*)o1, (T*)o2, (T*)o3);
+  if (e == cudaSuccess && mem_kind == HVI_MEM_HOST) {
+    if (nP > 0) e = cudaMemcpyAsync(zetaP, o1, sizeof(T) * (size_t)nP * M, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(zetaMs_tr, o2, sizeof(T) * nzM, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sigma, o3, sizeof(T) * (nP + (size_t)nM * nb), cudaMemcpyDeviceToHost, s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (tmp) cudaFree(tmp);
+  if (e != cudaSuccess) PLAN_FAIL(p, HVI_ECUDA, "generate_zeta: %s", cudaGetErrorString(e));
+  return HVI_OK;
+}
+
+extern "C" int hvi_generate_zeta(hvi_plan* p, int32_t n_MC, const void* phi, const void* zP, const void* zMs, int mem_kind,
+                                 void* zetaP, void* zetaMs_tr, void* sigma) {
+  int rc = check_eval_args(p, n_MC, phi, mem_kind);
+  if (rc) return rc;
+  if (!zMs || !zetaMs_tr || !sigma || (p->desc.n_P > 0 && (!zP || !zetaP))) PLAN_FAIL(p, HVI_EINVAL, "NULL array argument");
+  return p->dtype == HVI_F32 ? generate_zeta_t<float>(p, n_MC, phi, zP, zMs, mem_kind, zetaP, zetaMs_tr, sigma)
+                             : generate_zeta_t<double>(p, n_MC, phi, zP, zMs, mem_kind, zetaP, zetaMs_tr, sigma);
+}
+
+template <typename T>
+static int apply_g_t(hvi_plan* p, const void* phi, int mem_kind, void* mu) {
+  const Cfg<T>& cfg = cfg_of<T>(p);
+  cudaStream_t s = p->stream;
+  const T* dphi = (const T*)phi;
+  if (mem_kind == HVI_MEM_HOST) {
+    CU(p, cudaMemcpyAsync(p->d_phi, phi, sizeof(T) * cfg.nphi, cudaMemcpyHostToDevice, s));
+    dphi = (const T*)p->d_phi;
+  }
+  Launch L{s, p->sm_count, &p->launches};
+  CU(p, launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, p->nb, (T*)p->d_mu));
+  CU(p, cudaMemcpyAsync(mu, p->d_mu, sizeof(T) * (size_t)cfg.nM * p->nb,
+                        mem_kind == HVI_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+  CU(p, cudaStreamSynchronize(s));
+  return HVI_OK;
+}
+
+extern "C" int hvi_apply_g(hvi_plan* p, const void* phi, int mem_kind, void* mu_zeta) {
+  int rc = check_eval_args(p, 1, phi, mem_kind);
+  if (rc) return rc;
+  if (!mu_zeta) PLAN_FAIL(p, HVI_EINVAL, "mu_zeta is NULL");
+  return p->dtype == HVI_F32 ? apply_g_t<float>(p, phi, mem_kind, mu_zeta) : apply_g_t<double>(p, phi, mem_kind, mu_zeta);
+}

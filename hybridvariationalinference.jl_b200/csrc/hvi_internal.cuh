@@ -1,0 +1,103 @@
+// hvi_internal.cuh -- shared definitions of the B200 (sm_100a) neg-ELBO kernels.
+// Reference citations (file:line) are relative to /root/reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hvi_b200.h"
+
+namespace hvi {
+
+constexpr int MAXP = HVI_MAX_PAR;
+constexpr int MAXL = HVI_MAX_LAYERS;
+
+// Static description of the problem in the working type T, passed to kernels by value
+// (__grid_constant__), i.e. through the constant bank.
+template <typename T>
+struct Cfg {
+  int nP, nM, nO, nC;
+  int transP[MAXP], transM[MAXP];
+  int prP_kind[MAXP], prM_kind[MAXP];
+  T prP_a[MAXP], prP_ib[MAXP];  // prior location, 1/scale
+  T prM_a[MAXP], prM_ib[MAXP];
+  double prP_c0[MAXP], prM_c0[MAXP];  // log(scale) + log(2π)/2 (0 if no prior)
+  int slot_code[4];                   // -1: fixed; j<nP: θP[j]; nP+k: θM[k]
+  T slot_fix[4];
+  int omit_priors, count_globals;
+  T clamp_lo, clamp_hi;               // sqrt(floatmin), sqrt(floatmax) (src/elbo.jl:797-798)
+  int blkP_start[MAXP], rhoP_off[MAXP], blkM_start[MAXP], rhoM_off[MAXP];
+  int o_ls2P, o_coef, o_rhoP, o_rhoM, o_muP, nphig, nphi;
+  int nL, l_in[MAXL], l_out[MAXL], l_act[MAXL], l_bias[MAXL], woff[MAXL], boff[MAXL];
+  int sum_width;   // Σ_l n_in(l) + n_out(last): rows of the activation stack
+  int sum_out;     // Σ_l n_out(l): rows of the delta stack
+  int max_width;
+  int scale_kind;
+  T scale_a[MAXP], scale_b[MAXP];
+  int npc, pbm_covar_idx[MAXP];
+};
+
+// Per-evaluation constants derived from ϕq by the prologue kernel.
+template <typename T>
+struct EvalConsts {
+  T UM[MAXP][MAXP], UP[MAXP][MAXP];  // column-normalised unit-upper factors (src/cholesky.jl:156-174)
+  T nrmM[MAXP], nrmP[MAXP];
+  T coefA[MAXP], coefB[MAXP];        // coef_logσ2_ζMs[1,k], [2,k] (src/elbo.jl:652-653)
+  T sigP[MAXP], muP[MAXP];
+};
+
+// number of per-warp accumulators of the streaming kernel
+__host__ __device__ constexpr int tri(int n) { return n * (n + 1) / 2; }
+__host__ __device__ constexpr int nacc(int nP, int nM) { return 4 + 2 * nM + tri(nM) + nP + tri(nP); }
+// accumulator slots
+enum { ACC_NLY = 0, ACC_PRIOR = 1, ACC_LJ = 2, ACC_LOGSIG = 3, ACC_FIRST_VEC = 4 };
+
+template <typename T>
+struct StreamArgs {
+  const T* rec;      // tiled site records [tile][4*nO][32]: S1, S2, y_o, w = mask·exp(−y_unc)
+  const T* mu;       // μ_ζ (nM × nb) column-major
+  const T* zMs;      // (M × nM·nb) column-major
+  const T* thP;      // [nP][M] θP per draw
+  const T* gP;       // [nP][M] dθP/dζP (0 where clamped)
+  const T* zP;       // (M × nP) column-major
+  const EvalConsts<T>* ec;
+  T* mubar;          // cotangent of μ_ζ (nM × nb)
+  double* partials;  // [gridDim.x * warps][nacc]
+  int64_t nb;
+  int M;
+  int staged;        // 1: M % (16/sizeof(T)) == 0 and zMs 16-byte aligned → cp.async staging
+};
+
+struct Launch {
+  cudaStream_t stream;
+  int sm_count;
+  int64_t* counter;
+};
+
+// ---- kernel launchers (hvi_kernels.cu) -------------------------------------------------
+template <typename T>
+cudaError_t launch_preprocess(const Launch& L, int nO, int64_t nb, const T* xP, const T* y_o, const T* y_unc, T* rec,
+                              double* part /*[2*nwarps]*/, int* nrows_out);
+template <typename T>
+cudaError_t launch_prologue(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, int M, EvalConsts<T>* ec,
+                            T* pdraw /*4 arrays [nP][M]: rP, zetaP, thP, gP*/);
+template <typename T>
+cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu);
+template <typename T>
+cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, const T* mubar, int64_t nb,
+                           double* part /*[nblk][nphig]*/, int* nblk_out, int nblk_max);
+template <typename T>
+cudaError_t launch_stream(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, int* nrows_out, int nrows_max);
+template <typename T>
+cudaError_t launch_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, const T* pdraw,
+                            const EvalConsts<T>* ec, const double* part_stream, int nrows, const double* part_mlp,
+                            int nblk, double const_nly, int64_t nb, int M, double* out, T* grad_T);
+template <typename T>
+cudaError_t launch_gen_normal(const Launch& L, T* z, int64_t n_cols, int M, uint64_t seed, int64_t col_offset);
+template <typename T>
+cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, const T* pdraw, T* zetaP,
+                                 T* zetaMs_tr, T* sigma);
+int stream_max_rows(int sm_count);
+int mlp_bwd_max_blocks(int sm_count);
+bool stream_supported(int nP, int nM, int nO);
+
+}  // namespace hvi

@@ -1,0 +1,952 @@
+// hvi_kernels.cu -- sm_100a kernels of the negative-ELBO + gradient path.
+//
+// Pipeline per evaluation (one CUDA stream, no host round trips):
+//   k_prologue   ϕq → U_P, U_M, σ_P, per-draw θP / dθP      (src/elbo.jl:633-660, cholesky.jl:156-174)
+//   k_mlp_fwd    μ_ζ = g(xM; ϕg)                              (src/ModelApplicator.jl:163-176)
+//   k_stream     fused sample_ζ → T(ζ)+logjac → f_doubleMM → logden_normal → priors → adjoint,
+//                one thread per site, draws streamed through warp-private shared memory
+//                (src/elbo.jl:132-201,472-521,633-678,783-808; f_doubleMM.jl:101-139; logden_normal.jl:16-43)
+//   k_mlp_bwd    μ̄_ζ → ∇ϕg
+//   k_finalize   deterministic reduction of the per-warp partial sums, Cholesky adjoint,
+//                global-block terms, scatter into the ϕ layout (src/init_hybrid_params.jl:119-124)
+// All file:line citations are relative to /root/reference.
+#include <math.h>
+
+#include "hvi_internal.cuh"
+
+namespace hvi {
+
+// ---------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
+__device__ __forceinline__ float exp_t(float x) { return expf(x); }
+__device__ __forceinline__ double exp_t(double x) { return exp(x); }
+__device__ __forceinline__ float log_t(float x) { return logf(x); }
+__device__ __forceinline__ double log_t(double x) { return log(x); }
+__device__ __forceinline__ float tanh_t(float x) { return tanhf(x); }
+__device__ __forceinline__ double tanh_t(double x) { return tanh(x); }
+__device__ __forceinline__ float ndtri_t(float p) { return normcdfinvf(p); }
+__device__ __forceinline__ double ndtri_t(double p) { return normcdfinv(p); }
+__device__ __forceinline__ float log1p_t(float x) { return log1pf(x); }
+__device__ __forceinline__ double log1p_t(double x) { return log1p(x); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T act_f(int act, T z) {
+  if (act == HVI_ACT_TANH) return tanh_t(z);
+  if (act == HVI_ACT_LOGISTIC) return T(1) / (T(1) + exp_t(-z));
+  return z;
+}
+template <typename T>
+__device__ __forceinline__ T act_d(int act, T a) {
+  if (act == HVI_ACT_TANH) return T(1) - a * a;
+  if (act == HVI_ACT_LOGISTIC) return a * (T(1) - a);
+  return T(1);
+}
+
+// θ = T(ζ) with the reference's clamp (src/elbo.jl:783-808; bijectors_utils.jl:10-23,38-52) fused
+// with the prior on θ (src/elbo.jl:203-260).  Outputs: θ, dθ/dζ (0 when clamped), the variable part
+// of −logpdf(prior, θ) and its derivative w.r.t. ζ, the log-Jacobian term and its derivative.
+template <typename T>
+__device__ __forceinline__ void transform_prior(int tr, int pk, T a, T ib, T lo, T hi, T zeta, T& th, T& dth, T& pv,
+                                                T& dpz, T& lj, T& dlj) {
+  T raw, d;
+  if (tr == HVI_TR_EXP) {
+    raw = exp_t(zeta); d = raw; lj = zeta; dlj = T(1);
+  } else if (tr == HVI_TR_LOGISTIC) {
+    raw = T(1) / (T(1) + exp_t(-zeta)); d = raw * (T(1) - raw);
+    lj = -(log1p_t(exp_t(-zeta)) + log1p_t(exp_t(zeta))); dlj = T(1) - T(2) * raw;
+  } else {
+    raw = zeta; d = T(1); lj = T(0); dlj = T(0);
+  }
+  th = fmin(hi, raw);
+  th = fmax(lo, th);
+  const bool uncl = (th == raw);
+  dth = uncl ? d : T(0);
+  if (pk == HVI_PR_LOGNORMAL) {
+    const T lt = (tr == HVI_TR_EXP && uncl) ? zeta : log_t(th);
+    const T u = (lt - a) * ib;
+    pv = lt + T(0.5) * u * u;
+    // d/dθ = (1 + u·ib)/θ ; times dθ/dζ
+    dpz = (tr == HVI_TR_EXP) ? (uncl ? T(1) + u * ib : T(0)) : (T(1) + u * ib) / th * dth;
+  } else if (pk == HVI_PR_NORMAL) {
+    const T u = (th - a) * ib;
+    pv = T(0.5) * u * u;
+    dpz = u * ib * dth;
+  } else {
+    pv = T(0); dpz = T(0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// set_data: re-tile one batch into site records and fold the ϕ-independent part of the
+// likelihood, ½ Σ_{finite obs} y_unc (src/logden_normal.jl:34-39), into one constant.
+// record layout: [tile of 32 sites][field f = 0..4nO)[lane]; fields S1[o], S2[o], y_o[o], w[o]
+// w = exp(−y_unc) where the observation is finite and both drivers are finite, else 0
+// (is_valid masking, src/DoubleMM/f_doubleMM.jl:111-137).
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_preprocess(int nO, int64_t nb, const T* __restrict__ xP,
+                                                    const T* __restrict__ y_o, const T* __restrict__ y_unc,
+                                                    T* __restrict__ rec, double* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t ntiles = (nb + 31) / 32;
+  double cst = 0.0, anomalies = 0.0;
+  for (int64_t tile = gw; tile < ntiles; tile += nw) {
+    const int64_t site = tile * 32 + lane;
+    T* r = rec + (tile * 4 * nO) * 32 + lane;
+    for (int o = 0; o < nO; o++) {
+      T s1 = T(1), s2 = T(1), yo = T(0), w = T(0);
+      if (site < nb) {
+        const T a = xP[site * 2 * nO + o], b = xP[site * 2 * nO + nO + o];
+        const T y = y_o[site * nO + o], u = y_unc[site * nO + o];
+        const bool valid = isfinite(a) && isfinite(b);
+        const bool obs = !isnan(y);
+        if (valid) { s1 = a; s2 = b; }
+        if (obs && valid) { yo = y; w = exp_t(-u); cst += 0.5 * (double)u; }
+        // reference: invalid driver with a finite observation gives a NaN loss (SURVEY C-2)
+        if (obs && !valid) anomalies += 1.0;
+      }
+      r[(0 * nO + o) * 32] = s1;
+      r[(1 * nO + o) * 32] = s2;
+      r[(2 * nO + o) * 32] = yo;
+      r[(3 * nO + o) * 32] = w;
+    }
+  }
+  cst = warp_sum(cst);
+  anomalies = warp_sum(anomalies);
+  if (lane == 0) { part[2 * gw] = cst; part[2 * gw + 1] = anomalies; }
+}
+
+// ---------------------------------------------------------------------------------------
+// prologue: one block.  thread 0 builds the Cholesky factors; all threads do the draws of
+// the global block (src/elbo.jl:647-657,664-670,496; src/cholesky.jl:156-174,262-313).
+// pdraw = 4 arrays [nP][M]: rP, ζP, θP, gP = dθP/dζP.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__device__ void build_U(int n, const int* blk_start, const int* rho_off, const T* rho, T (*U)[MAXP], T* nrm) {
+  for (int k = 0; k < n; k++) {
+    T ss = T(1);
+    for (int i = 0; i < n; i++) U[i][k] = T(0);
+    for (int i = blk_start[k]; i < k; i++) {
+      const T v = rho[rho_off[k] + (i - blk_start[k])];
+      U[i][k] = v;
+      ss += v * v;
+    }
+    U[k][k] = T(1);
+    nrm[k] = sqrt(ss);
+    for (int i = blk_start[k]; i <= k; i++) U[i][k] /= nrm[k];
+  }
+}
+
+template <typename T>
+__global__ void k_prologue(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi, const T* __restrict__ zP,
+                           int M, EvalConsts<T>* __restrict__ ec, T* __restrict__ pdraw) {
+  __shared__ EvalConsts<T> s;
+  const int nP = cfg.nP, nM = cfg.nM;
+  if (threadIdx.x == 0) {
+    build_U<T>(nP, cfg.blkP_start, cfg.rhoP_off, phi + cfg.o_rhoP, s.UP, s.nrmP);
+    build_U<T>(nM, cfg.blkM_start, cfg.rhoM_off, phi + cfg.o_rhoM, s.UM, s.nrmM);
+    for (int k = 0; k < nM; k++) { s.coefA[k] = phi[cfg.o_coef + 2 * k]; s.coefB[k] = phi[cfg.o_coef + 2 * k + 1]; }
+    for (int j = 0; j < nP; j++) { s.sigP[j] = exp_t(phi[cfg.o_ls2P + j] / T(2)); s.muP[j] = phi[cfg.o_muP + j]; }
+    *ec = s;
+  }
+  __syncthreads();
+  T* rP = pdraw;
+  T* zetaP = pdraw + (size_t)nP * M;
+  T* thP = pdraw + (size_t)2 * nP * M;
+  T* gP = pdraw + (size_t)3 * nP * M;
+  for (int e = threadIdx.x; e < nP * M; e += blockDim.x) {
+    const int j = e / M, m = e % M;
+    T t = T(0);
+    for (int jj = cfg.blkP_start[j]; jj <= j; jj++) t += s.UP[jj][j] * zP[m + (size_t)M * jj];
+    const T r = s.sigP[j] * t;
+    const T zeta = s.muP[j] + r;
+    T th, dth, pv, dpz, lj, dlj;
+    transform_prior<T>(cfg.transP[j], HVI_PR_NONE, T(0), T(0), cfg.clamp_lo, cfg.clamp_hi, zeta, th, dth, pv, dpz, lj,
+                       dlj);
+    rP[e] = r; zetaP[e] = zeta; thP[e] = th; gP[e] = dth;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// g forward, CUDA-core version for narrow networks: one thread per site, weights and the
+// activation column of every thread in shared memory ([neuron][thread], conflict-free).
+// (src/ModelApplicator.jl:163-176; ext/HybridVariationalInferenceSimpleChainsExt.jl:43-52)
+// ---------------------------------------------------------------------------------------
+constexpr int MLP_BS = 128;
+
+template <typename T>
+__device__ __forceinline__ void mlp_forward_block(const Cfg<T>& cfg, const T* __restrict__ sW, T* __restrict__ acts,
+                                                  int t) {
+  // acts: stack of activation rows, layer l input at row offset Σ_{l'<l} n_in(l'), [row][MLP_BS]
+  int row_in = 0;
+  for (int l = 0; l < cfg.nL; l++) {
+    const int ni = cfg.l_in[l], no = cfg.l_out[l];
+    const int row_out = row_in + ni;
+    const T* W = sW + cfg.woff[l];
+    for (int j = 0; j < no; j++) {
+      T z = cfg.l_bias[l] ? sW[cfg.boff[l] + j] : T(0);
+      for (int i = 0; i < ni; i++) z = fma(W[i * no + j], acts[(row_in + i) * MLP_BS + t], z);
+      acts[(row_out + j) * MLP_BS + t] = act_f<T>(cfg.l_act[l], z);
+    }
+    row_in = row_out;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MLP_BS) k_mlp_fwd(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi,
+                                                    const T* __restrict__ xM, int64_t nb, T* __restrict__ mu) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sW = reinterpret_cast<T*>(smem_raw);
+  T* acts = sW + ((cfg.nphig + 3) & ~3);
+  const int t = threadIdx.x;
+  for (int e = t; e < cfg.nphig; e += MLP_BS) sW[e] = phi[e];
+  __syncthreads();
+  const int64_t ntiles = (nb + MLP_BS - 1) / MLP_BS;
+  const int out_row = cfg.sum_width - cfg.l_out[cfg.nL - 1];
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t site = tile * MLP_BS + t;
+    if (site < nb) {
+      for (int i = 0; i < cfg.nC; i++) acts[i * MLP_BS + t] = xM[site * cfg.nC + i];
+      for (int c = 0; c < cfg.npc; c++) acts[(cfg.nC + c) * MLP_BS + t] = phi[cfg.o_muP + cfg.pbm_covar_idx[c]];
+      mlp_forward_block<T>(cfg, sW, acts, t);
+      for (int k = 0; k < cfg.nM; k++) {
+        const T p = acts[(out_row + k) * MLP_BS + t];
+        mu[site * cfg.nM + k] = (cfg.scale_kind == HVI_SCALE_RANGE) ? p * cfg.scale_b[k] + cfg.scale_a[k]
+                                                                  : cfg.scale_a[k] + cfg.scale_b[k] * ndtri_t(p);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// g backward: recompute the forward per tile of 128 sites, back-propagate δ, then form the
+// weight gradient as (δ stack)·(activation stack)ᵀ over the tile with each thread owning
+// fixed gradient entries (deterministic; no atomics).  Per-block double partial sums.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(MLP_BS) k_mlp_bwd(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi,
+                                                    const T* __restrict__ xM, const T* __restrict__ mubar, int64_t nb,
+                                                    double* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* gacc = reinterpret_cast<double*>(smem_raw);                 // [nphig]
+  int2* tab = reinterpret_cast<int2*>(gacc + cfg.nphig);              // [nphig] (delta row, act row | -1)
+  T* sW = reinterpret_cast<T*>(tab + cfg.nphig);                      // [nphig]
+  T* acts = sW + ((cfg.nphig + 3) & ~3);                              // [sum_width][BS]
+  T* dl = acts + (size_t)cfg.sum_width * MLP_BS;                      // [sum_out][BS]
+  const int t = threadIdx.x;
+  for (int e = t; e < cfg.nphig; e += MLP_BS) { sW[e] = phi[e]; gacc[e] = 0.0; }
+  {  // gradient entry e ↔ (δ row, activation row)
+    int row_in = 0, drow = 0;
+    for (int l = 0; l < cfg.nL; l++) {
+      const int ni = cfg.l_in[l], no = cfg.l_out[l];
+      for (int e = t; e < ni * no; e += MLP_BS) tab[cfg.woff[l] + e] = make_int2(drow + e % no, row_in + e / no);
+      if (cfg.l_bias[l])
+        for (int e = t; e < no; e += MLP_BS) tab[cfg.boff[l] + e] = make_int2(drow + e, -1);
+      row_in += ni; drow += no;
+    }
+  }
+  __syncthreads();
+  const int64_t ntiles = (nb + MLP_BS - 1) / MLP_BS;
+  const int out_row = cfg.sum_width - cfg.l_out[cfg.nL - 1];
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t site = tile * MLP_BS + t;
+    const bool active = site < nb;
+    // forward
+    for (int i = 0; i < cfg.nC; i++) acts[i * MLP_BS + t] = active ? xM[site * cfg.nC + i] : T(0);
+    for (int c = 0; c < cfg.npc; c++) acts[(cfg.nC + c) * MLP_BS + t] = phi[cfg.o_muP + cfg.pbm_covar_idx[c]];
+    mlp_forward_block<T>(cfg, sW, acts, t);
+    // output delta: μ̄_ζ · σ_k · √(2π) e^{q²/2} · p(1−p)
+    int drow = cfg.sum_out - cfg.l_out[cfg.nL - 1];
+    for (int k = 0; k < cfg.l_out[cfg.nL - 1]; k++) {
+      T d = T(0);
+      if (active && k < cfg.nM) {
+        const T p = acts[(out_row + k) * MLP_BS + t];
+        const T mb = mubar[site * cfg.nM + k];
+        if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb * cfg.scale_b[k];
+        else { const T q = ndtri_t(p); d = mb * cfg.scale_b[k] * T(2.50662827463100050242) * exp_t(T(0.5) * q * q); }
+        d *= act_d<T>(cfg.l_act[cfg.nL - 1], p);
+      }
+      dl[(drow + k) * MLP_BS + t] = d;
+    }
+    // hidden deltas
+    int row_out = out_row;
+    for (int l = cfg.nL - 1; l >= 1; l--) {
+      const int ni = cfg.l_in[l], no = cfg.l_out[l];
+      const int row_in = row_out - ni;         // activations feeding layer l
+      const int drow_prev = drow - ni;         // delta rows of layer l-1 (n_out(l-1) == ni)
+      const T* W = sW + cfg.woff[l];
+      for (int i = 0; i < ni; i++) {
+        T s = T(0);
+        for (int j = 0; j < no; j++) s = fma(W[i * no + j], dl[(drow + j) * MLP_BS + t], s);
+        dl[(drow_prev + i) * MLP_BS + t] = s * act_d<T>(cfg.l_act[l - 1], acts[(row_in + i) * MLP_BS + t]);
+      }
+      row_out = row_in; drow = drow_prev;
+    }
+    __syncthreads();
+    // weight gradient: entry e owned by thread e % BS; site index rotated per thread so that the
+    // 32 lanes of a warp hit 32 different banks
+    for (int e = t; e < cfg.nphig; e += MLP_BS) {
+      const int2 rc = tab[e];
+      const T* dr = dl + (size_t)rc.x * MLP_BS;
+      T acc = T(0);
+      if (rc.y >= 0) {
+        const T* ar = acts + (size_t)rc.y * MLP_BS;
+        for (int s0 = 0; s0 < MLP_BS; s0++) { const int s = (s0 + t) & (MLP_BS - 1); acc = fma(dr[s], ar[s], acc); }
+      } else {
+        for (int s0 = 0; s0 < MLP_BS; s0++) { const int s = (s0 + t) & (MLP_BS - 1); acc += dr[s]; }
+      }
+      gacc[e] += (double)acc;
+    }
+    __syncthreads();
+  }
+  for (int e = t; e < cfg.nphig; e += MLP_BS) part[(size_t)blockIdx.x * cfg.nphig + e] = gacc[e];
+}
+
+// ---------------------------------------------------------------------------------------
+// The fused streaming kernel.  One thread owns one site for all draws; a warp owns a tile of
+// 32 consecutive sites.  The tile's draws ξ (32·NM rows of M values, contiguous in HBM) are
+// staged through warp-private shared memory with coalesced 16-byte cp.async and read back
+// transposed; 16-byte chunks are rotated by the owning lane so that the transposed LDS.128 is
+// bank-conflict free.  Everything between μ_ζ and (μ̄_ζ, partial sums of the shared-parameter
+// cotangents) stays in registers.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ constexpr int ut(int j, int k) { return k * (k + 1) / 2 + j; }  // packed upper incl. diag
+
+template <typename T, int NP, int NM, int NO>
+struct SiteState {
+  T S1[NO], S2[NO], S12[NO], yo[NO], w[NO];
+  T mu[NM], sig[NM];
+  T U[tri(NM)];
+  T smu[NM], sz[tri(NM)];        // Σ_m ζ̄[k],  Σ_m ζ̄[k]·z[j]
+  T aP[NP > 0 ? NP : 1], cP[NP > 0 ? tri(NP) : 1];
+  T nly, prior, lj;
+};
+
+template <typename T, int NP, int NM, int NO>
+__device__ __forceinline__ void do_draw(const Cfg<T>& cfg, const StreamArgs<T>& a, SiteState<T, NP, NM, NO>& st,
+                                        const T (&z)[NM], int m) {
+  T zeta[NM], th[NM], dth[NM], dpz[NM], dlj[NM];
+#pragma unroll
+  for (int k = 0; k < NM; k++) {
+    T t = T(0);
+#pragma unroll
+    for (int j = 0; j <= k; j++) t = fma(st.U[ut(j, k)], z[j], t);
+    zeta[k] = fma(st.sig[k], t, st.mu[k]);
+    T pv, lj;
+    transform_prior<T>(cfg.transM[k], cfg.omit_priors ? HVI_PR_NONE : cfg.prM_kind[k], cfg.prM_a[k], cfg.prM_ib[k],
+                       cfg.clamp_lo, cfg.clamp_hi, zeta[k], th[k], dth[k], pv, dpz[k], lj, dlj[k]);
+    st.prior += pv;
+    st.lj += lj;
+  }
+  T thp[NP > 0 ? NP : 1], gp[NP > 0 ? NP : 1];
+#pragma unroll
+  for (int j = 0; j < NP; j++) { thp[j] = __ldg(a.thP + (size_t)j * a.M + m); gp[j] = __ldg(a.gP + (size_t)j * a.M + m); }
+  // gather (r0, r1, K1, K2) by slot (src/PBMApplicator.jl:234-239,283-287)
+  T par[4];
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    T v = cfg.slot_fix[s];
+    const int c = cfg.slot_code[s];
+#pragma unroll
+    for (int j = 0; j < NP; j++) v = (c == j) ? thp[j] : v;
+#pragma unroll
+    for (int k = 0; k < NM; k++) v = (c == NP + k) ? th[k] : v;
+    par[s] = v;
+  }
+  // f_doubleMM + logden_normal + adjoint w.r.t. (r0, r1, K1, K2)
+  // y = r0 + r1·S1/(K1+S1)·S2/(K2+S2)   (src/DoubleMM/f_doubleMM.jl:137)
+  T g0 = T(0), g1 = T(0), gA = T(0), gB = T(0), nly = T(0);
+#pragma unroll
+  for (int o = 0; o < NO; o++) {
+    const T d1 = par[2] + st.S1[o], d2 = par[3] + st.S2[o];
+    const T rp = rcp_fast(d1 * d2);
+    const T ab = st.S12[o] * rp;
+    const T y = fma(par[1], ab, par[0]);
+    const T res = y - st.yo[o];
+    const T dy = res * st.w[o];
+    nly = fma(res, dy, nly);
+    g0 += dy;
+    const T t = dy * ab;
+    g1 += t;
+    gA = fma(t, d2 * rp, gA);
+    gB = fma(t, d1 * rp, gB);
+  }
+  st.nly += nly;
+  T pbar[4] = {g0, g1, -par[1] * gA, -par[1] * gB};
+  T thbar[NP + NM];
+#pragma unroll
+  for (int q = 0; q < NP + NM; q++) {
+    T v = T(0);
+#pragma unroll
+    for (int s = 0; s < 4; s++) v += (cfg.slot_code[s] == q) ? pbar[s] : T(0);
+    thbar[q] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < NM; k++) {
+    const T zb = fma(thbar[NP + k], dth[k], dpz[k] - dlj[k]);
+    st.smu[k] += zb;
+#pragma unroll
+    for (int j = 0; j <= k; j++) st.sz[ut(j, k)] = fma(zb, z[j], st.sz[ut(j, k)]);
+  }
+#pragma unroll
+  for (int j = 0; j < NP; j++) {
+    const T zb = thbar[j] * gp[j];
+    st.aP[j] += zb;
+#pragma unroll
+    for (int jj = 0; jj <= j; jj++) st.cP[ut(jj, j)] = fma(zb, __ldg(a.zP + (size_t)a.M * jj + m), st.cP[ut(jj, j)]);
+  }
+}
+
+constexpr int STREAM_THREADS = 256;
+
+template <typename T, int NP, int NM, int NO>
+__global__ void __launch_bounds__(STREAM_THREADS) k_stream(const __grid_constant__ Cfg<T> cfg,
+                                                           const __grid_constant__ StreamArgs<T> a) {
+  constexpr int CH = 16 / sizeof(T);  // elements per 16-byte chunk
+  constexpr int MC = 8 * CH;          // draws per stage (one 128-byte row)
+  constexpr int NUM = tri(NM), NUP = tri(NP);
+  constexpr int NACC = nacc(NP, NM);
+  constexpr int NWARP = STREAM_THREADS / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* ztile = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (32 * NM * MC);
+  double* wacc = reinterpret_cast<double*>(smem_raw + (size_t)NWARP * 32 * NM * MC * sizeof(T)) + warp * NACC;
+  if (lane == 0)
+    for (int i = 0; i < NACC; i++) wacc[i] = 0.0;
+
+  SiteState<T, NP, NM, NO> st;
+  T cA[NM], cB[NM];
+#pragma unroll
+  for (int k = 0; k < NM; k++) {
+    cA[k] = a.ec->coefA[k];
+    cB[k] = a.ec->coefB[k];
+#pragma unroll
+    for (int j = 0; j <= k; j++) st.U[ut(j, k)] = a.ec->UM[j][k];
+  }
+  const int M = a.M;
+  const T wM = T(1) / T(M);
+  const bool staged = a.staged != 0;
+  const int64_t ntiles = (a.nb + 31) / 32;
+  for (int64_t tile = (int64_t)blockIdx.x * NWARP + warp; tile < ntiles; tile += (int64_t)gridDim.x * NWARP) {
+    const int64_t site = tile * 32 + lane;
+    const bool active = site < a.nb;
+    {
+      const T* r = a.rec + (tile * 4 * NO) * 32 + lane;
+#pragma unroll
+      for (int o = 0; o < NO; o++) {
+        st.S1[o] = r[(0 * NO + o) * 32];
+        st.S2[o] = r[(1 * NO + o) * 32];
+        st.yo[o] = r[(2 * NO + o) * 32];
+        st.w[o] = r[(3 * NO + o) * 32];
+        st.S12[o] = st.S1[o] * st.S2[o];
+      }
+    }
+    T ls[NM];
+#pragma unroll
+    for (int k = 0; k < NM; k++) {
+      st.mu[k] = active ? a.mu[site * NM + k] : T(0);
+      ls[k] = fma(cB[k], st.mu[k], cA[k]);
+      st.sig[k] = exp_t(T(0.5) * ls[k]);
+      st.smu[k] = T(0);
+    }
+#pragma unroll
+    for (int i = 0; i < NUM; i++) st.sz[i] = T(0);
+#pragma unroll
+    for (int i = 0; i < (NP > 0 ? NP : 1); i++) st.aP[i] = T(0);
+#pragma unroll
+    for (int i = 0; i < (NP > 0 ? NUP : 1); i++) st.cP[i] = T(0);
+    st.nly = st.prior = st.lj = T(0);
+
+    if (staged) {
+      const T* gz = a.zMs + (size_t)tile * 32 * NM * M;  // row r of the tile at gz + r*M
+      const int64_t rows_valid = (a.nb - tile * 32 < 32 ? a.nb - tile * 32 : 32) * NM;
+      for (int m0 = 0; m0 < M; m0 += MC) {
+        const int nch = ((M - m0) < MC ? (M - m0) : MC) / CH;
+        __syncwarp();
+        for (int e = lane; e < 32 * NM * 8; e += 32) {
+          const int row = e >> 3, q = e & 7, owner = row / NM;
+          if (q < nch && row < rows_valid)
+            cp_async16(ztile + row * MC + ((q + owner) & 7) * CH, gz + (size_t)row * M + m0 + q * CH);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        if (active) {
+          for (int q = 0; q < nch; q++) {
+            T zc[NM][CH];
+#pragma unroll
+            for (int k = 0; k < NM; k++) {
+              const T* src = ztile + (lane * NM + k) * MC + ((q + lane) & 7) * CH;
+              if constexpr (sizeof(T) == 4) {
+                const float4 v = *reinterpret_cast<const float4*>(src);
+                zc[k][0] = v.x; zc[k][1] = v.y; zc[k][2] = v.z; zc[k][3] = v.w;
+              } else {
+                const double2 v = *reinterpret_cast<const double2*>(src);
+                zc[k][0] = v.x; zc[k][1] = v.y;
+              }
+            }
+#pragma unroll
+            for (int d = 0; d < CH; d++) {
+              T z[NM];
+#pragma unroll
+              for (int k = 0; k < NM; k++) z[k] = zc[k][d];
+              do_draw<T, NP, NM, NO>(cfg, a, st, z, m0 + q * CH + d);
+            }
+          }
+        }
+      }
+    } else if (active) {
+      for (int m = 0; m < M; m++) {
+        T z[NM];
+#pragma unroll
+        for (int k = 0; k < NM; k++) z[k] = a.zMs[((size_t)site * NM + k) * M + m];
+        do_draw<T, NP, NM, NO>(cfg, a, st, z, m);
+      }
+    }
+
+    // end of site: σ-path, entropy, μ̄_ζ  (SURVEY Appendix A adjoint)
+    T acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) acc[i] = T(0);
+    if (active) {
+      acc[ACC_NLY] = st.nly; acc[ACC_PRIOR] = st.prior; acc[ACC_LJ] = st.lj;
+#pragma unroll
+      for (int k = 0; k < NM; k++) {
+        T sr = T(0);
+#pragma unroll
+        for (int j = 0; j <= k; j++) sr = fma(st.U[ut(j, k)], st.sz[ut(j, k)], sr);
+        sr *= st.sig[k];                                  // Σ_m ζ̄[k,m]·r[k,m]
+        const T lsb = T(0.5) * wM * sr - T(0.5);          // −½ from the entropy
+        acc[ACC_LOGSIG] += T(0.5) * ls[k];
+        acc[ACC_FIRST_VEC + k] = lsb;
+        acc[ACC_FIRST_VEC + NM + k] = lsb * st.mu[k];
+        a.mubar[site * NM + k] = fma(wM, st.smu[k], lsb * cB[k]);
+#pragma unroll
+        for (int j = 0; j <= k; j++) acc[ACC_FIRST_VEC + 2 * NM + ut(j, k)] = st.sig[k] * st.sz[ut(j, k)];
+      }
+#pragma unroll
+      for (int j = 0; j < NP; j++) acc[ACC_FIRST_VEC + 2 * NM + NUM + j] = st.aP[j];
+#pragma unroll
+      for (int i = 0; i < NUP; i++) acc[ACC_FIRST_VEC + 2 * NM + NUM + NP + i] = st.cP[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NACC; i++) {
+      const T v = warp_sum(acc[i]);
+      if (lane == 0) wacc[i] += (double)v;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    double* out = a.partials + ((size_t)blockIdx.x * NWARP + warp) * NACC;
+    for (int i = 0; i < NACC; i++) out[i] = wacc[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// finalize: one block.  Fixed-order reduction of all partial sums, global-block terms,
+// Cholesky adjoint, scatter into the layout of ϕ.
+// out[0..nphi) gradient, out[nphi..nphi+6) components, out[nphi+6] nL, out[nphi+7] non-finite count
+// ---------------------------------------------------------------------------------------
+constexpr int FIN_THREADS = 256;
+
+__device__ __forceinline__ double block_sum_fixed(double v, double* sred) {
+  // fixed-shape tree: deterministic run to run
+  const int t = threadIdx.x;
+  sred[t] = v;
+  __syncthreads();
+  for (int s = FIN_THREADS / 2; s > 0; s >>= 1) {
+    if (t < s) sred[t] += sred[t + s];
+    __syncthreads();
+  }
+  const double r = sred[0];
+  __syncthreads();
+  return r;
+}
+
+template <typename T>
+__device__ void build_U_adj(int n, const int* blk_start, const int* rho_off, const T (*U)[MAXP], const T* nrm,
+                            const double (*Ubar)[MAXP], double* rho_bar) {
+  for (int k = 0; k < n; k++) {
+    double dot = 0;
+    for (int i = blk_start[k]; i <= k; i++) dot += (double)U[i][k] * Ubar[i][k];
+    for (int i = blk_start[k]; i < k; i++)
+      rho_bar[rho_off[k] + (i - blk_start[k])] += (Ubar[i][k] - (double)U[i][k] * dot) / (double)nrm[k];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant__ Cfg<T> cfg,
+                                                          const T* __restrict__ phi, const T* __restrict__ zP,
+                                                          const T* __restrict__ pdraw,
+                                                          const EvalConsts<T>* __restrict__ ecp,
+                                                          const double* __restrict__ part_stream, int nrows,
+                                                          const double* __restrict__ part_mlp, int nblk,
+                                                          double const_nly, int64_t nb, int M,
+                                                          double* __restrict__ out, T* __restrict__ grad_T) {
+  __shared__ double sred[FIN_THREADS];
+  __shared__ double sacc[128];
+  const int t = threadIdx.x;
+  const int nP = cfg.nP, nM = cfg.nM;
+  const int NACC = nacc(nP, nM);
+  for (int e = t; e < cfg.nphi + 8; e += FIN_THREADS) out[e] = 0.0;
+  // ∇ϕg: sum the per-block partials in block order
+  for (int e = t; e < cfg.nphig; e += FIN_THREADS) {
+    double s = 0;
+    for (int b = 0; b < nblk; b++) s += part_mlp[(size_t)b * cfg.nphig + e];
+    out[e] = s;
+  }
+  for (int a = 0; a < NACC; a++) {
+    double s = 0;
+    for (int r = t; r < nrows; r += FIN_THREADS) s += part_stream[(size_t)r * NACC + a];
+    s = block_sum_fixed(s, sred);
+    if (t == 0) sacc[a] = s;
+  }
+  __syncthreads();
+  if (t != 0) return;
+  const EvalConsts<T>& ec = *ecp;
+  const double w = 1.0 / (double)M;
+  const int NUM = tri(nM);
+  const double* abar = sacc + ACC_FIRST_VEC;
+  const double* bbar = abar + nM;
+  const double* cU = bbar + nM;
+  const double* aPs = cU + NUM;
+  const double* cPs = aPs + nP;
+  double* G = out;
+  double nLy = 0.5 * w * sacc[ACC_NLY] + const_nly;
+  double nlp = w * sacc[ACC_PRIOR];
+  double lj = w * sacc[ACC_LJ];
+  double logsig = sacc[ACC_LOGSIG];
+  if (!cfg.omit_priors)
+    for (int k = 0; k < nM; k++) nlp += (double)nb * cfg.prM_c0[k];
+  // coefficients of log σ²
+  for (int k = 0; k < nM; k++) { G[cfg.o_coef + 2 * k] = abar[k]; G[cfg.o_coef + 2 * k + 1] = bbar[k]; }
+  // M block: Ū = w·cU (columns restricted to their block) → ρ̄sM
+  double Ubar[MAXP][MAXP];
+  for (int k = 0; k < nM; k++)
+    for (int j = 0; j <= k; j++) Ubar[j][k] = w * cU[k * (k + 1) / 2 + j];
+  build_U_adj<T>(nM, cfg.blkM_start, cfg.rhoM_off, ec.UM, ec.nrmM, Ubar, G + cfg.o_rhoM);
+  // global block
+  const T* rP = pdraw;
+  const T* zetaP = pdraw + (size_t)nP * M;
+  const T* thP = pdraw + (size_t)2 * nP * M;
+  const T* gP = pdraw + (size_t)3 * nP * M;
+  double CP[MAXP][MAXP];
+  for (int j = 0; j < nP; j++) {
+    double aP = w * aPs[j];
+    for (int jj = 0; jj <= j; jj++) CP[jj][j] = w * cPs[j * (j + 1) / 2 + jj];
+    if (cfg.count_globals) {
+      // prior and log-Jacobian of θP, once per evaluation
+      double pv_sum = 0, lj_sum = 0;
+      for (int m = 0; m < M; m++) {
+        T th, dth, pv, dpz, ljm, dlj;
+        transform_prior<T>(cfg.transP[j], cfg.omit_priors ? HVI_PR_NONE : cfg.prP_kind[j], cfg.prP_a[j], cfg.prP_ib[j],
+                           cfg.clamp_lo, cfg.clamp_hi, zetaP[(size_t)j * M + m], th, dth, pv, dpz, ljm, dlj);
+        pv_sum += (double)pv;
+        lj_sum += (double)ljm;
+        const double zb = w * ((double)dpz - (double)dlj);
+        aP += zb;
+        for (int jj = 0; jj <= j; jj++) CP[jj][j] += zb * (double)zP[m + (size_t)M * jj];
+      }
+      nlp += w * pv_sum + (cfg.omit_priors ? 0.0 : cfg.prP_c0[j]);
+      lj += w * lj_sum;
+      logsig += 0.5 * (double)phi[cfg.o_ls2P + j];
+    }
+    G[cfg.o_muP + j] += aP;
+    // Σ_m ζ̄P[j,m]·rP[j,m] = σP[j] Σ_{jj} UP[jj][j]·CP[jj][j]
+    double sr = 0;
+    for (int jj = cfg.blkP_start[j]; jj <= j; jj++) sr += (double)ec.UP[jj][j] * CP[jj][j];
+    sr *= (double)ec.sigP[j];
+    G[cfg.o_ls2P + j] = 0.5 * sr - (cfg.count_globals ? 0.5 : 0.0);
+    for (int jj = 0; jj <= j; jj++) Ubar[jj][j] = (double)ec.sigP[j] * CP[jj][j];
+  }
+  build_U_adj<T>(nP, cfg.blkP_start, cfg.rhoP_off, ec.UP, ec.nrmP, Ubar, G + cfg.o_rhoP);
+  (void)rP; (void)thP; (void)gP;
+  const double Kdim = (double)nM * (double)nb + (cfg.count_globals ? nP : 0);
+  const double ent = 0.5 * Kdim * 2.8378770664093454836 + logsig;   // (K·log(2πe) + 2Σlog σ)/2, logden_normal.jl:74
+  const double nlj = -lj;
+  double* C = out + cfg.nphi;
+  C[0] = nLy + nlp + nlj; C[1] = ent; C[2] = 0.0; C[3] = nLy; C[4] = nlp; C[5] = nlj;
+  C[6] = C[0] - C[1] + C[2];
+  double bad = 0;
+  for (int e = 0; e < cfg.nphi + 7; e++) bad += isfinite(out[e]) ? 0.0 : 1.0;
+  C[7] = bad;
+  if (grad_T)
+    for (int e = 0; e < cfg.nphi; e++) grad_T[e] = (T)out[e];
+}
+
+// gradient entries of ϕg are written by many threads above; convert them after the block is done
+template <typename T>
+__global__ void k_cast_grad(int n, const double* __restrict__ out, T* __restrict__ grad_T) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) grad_T[e] = (T)out[e];
+}
+
+// ---------------------------------------------------------------------------------------
+// counter-based standard normals (Philox4x32-10 + Box-Muller), keyed by
+// (seed; global column, draw/4): independent of the sharding.  Stands in for CUDA.randn
+// (ext/HybridVariationalInferenceCUDAExt.jl:82-86).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&o)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_gen_normal(T* __restrict__ z, int64_t n_cols, int M, uint64_t seed,
+                                                    int64_t col_offset) {
+  const int M4 = (M + 3) / 4;
+  const int64_t n = n_cols * M4;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t col = e / M4;
+    const int m4 = (int)(e % M4);
+    const uint64_t gcol = (uint64_t)(col + col_offset);
+    uint32_t r[4];
+    philox4x32_10((uint32_t)gcol, (uint32_t)(gcol >> 32), (uint32_t)m4, 0x5eedu, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    float n4[4];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float u1 = ((float)r[2 * h] + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+      const float u2 = (float)r[2 * h + 1] * 2.3283064365386963e-10f;
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      n4[2 * h] = rad * cs; n4[2 * h + 1] = rad * sn;
+    }
+    for (int d = 0; d < 4; d++) {
+      const int m = m4 * 4 + d;
+      if (m < M) z[(size_t)col * M + m] = (T)n4[d];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// generate_ζ forward (src/elbo.jl:472-521): ζsP (nP×M), ζsMs_tr (nb×nM×M), σ.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_generate_zeta(const __grid_constant__ Cfg<T> cfg,
+                                                       const __grid_constant__ StreamArgs<T> a,
+                                                       const T* __restrict__ pdraw, T* __restrict__ zetaP,
+                                                       T* __restrict__ zetaMs_tr, T* __restrict__ sigma) {
+  const int nP = cfg.nP, nM = cfg.nM, M = a.M;
+  const EvalConsts<T>& ec = *a.ec;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid < (int64_t)nP * M) {
+    const int j = (int)(gid / M), m = (int)(gid % M);
+    zetaP[j + (size_t)nP * m] = pdraw[(size_t)nP * M + gid];  // ζP array of pdraw
+  }
+  if (gid < nP) sigma[gid] = ec.sigP[gid];
+  for (int64_t e = gid; e < a.nb * nM; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / nM;
+    const int k = (int)(e % nM);
+    const T mu = a.mu[i * nM + k];
+    const T sg = exp_t(T(0.5) * (ec.coefA[k] + ec.coefB[k] * mu));
+    sigma[nP + i * nM + k] = sg;
+    for (int m = 0; m < M; m++) {
+      T t = T(0);
+      for (int j = cfg.blkM_start[k]; j <= k; j++) t += ec.UM[j][k] * a.zMs[((size_t)i * nM + j) * M + m];
+      zetaMs_tr[i + a.nb * (k + (size_t)nM * m)] = mu + sg * t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+#define HVI_LAUNCH_CHECK()                         \
+  do {                                             \
+    cudaError_t e_ = cudaGetLastError();           \
+    if (e_ != cudaSuccess) return e_;              \
+    if (L.counter) ++*L.counter;                   \
+  } while (0)
+
+int stream_max_rows(int sm_count) { return sm_count * 8 * (STREAM_THREADS / 32); }
+int mlp_bwd_max_blocks(int sm_count) { return sm_count * 4; }
+
+template <typename T>
+cudaError_t launch_preprocess(const Launch& L, int nO, int64_t nb, const T* xP, const T* y_o, const T* y_unc, T* rec,
+                              double* part, int* nrows_out) {
+  const int64_t ntiles = (nb + 31) / 32;
+  int blocks = (int)((ntiles + 7) / 8);
+  if (blocks > L.sm_count * 8) blocks = L.sm_count * 8;
+  if (blocks < 1) blocks = 1;
+  k_preprocess<T><<<blocks, 256, 0, L.stream>>>(nO, nb, xP, y_o, y_unc, rec, part);
+  HVI_LAUNCH_CHECK();
+  *nrows_out = blocks * 8;
+  return cudaSuccess;
+}
+
+template <typename T>
+cudaError_t launch_prologue(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, int M, EvalConsts<T>* ec,
+                            T* pdraw) {
+  k_prologue<T><<<1, 128, 0, L.stream>>>(cfg, phi, zP, M, ec, pdraw);
+  HVI_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+template <typename T>
+static size_t mlp_fwd_smem(const Cfg<T>& cfg) {
+  return sizeof(T) * (((cfg.nphig + 3) & ~3) + (size_t)cfg.sum_width * MLP_BS);
+}
+template <typename T>
+static size_t mlp_bwd_smem(const Cfg<T>& cfg) {
+  return (sizeof(double) + sizeof(int2)) * cfg.nphig +
+         sizeof(T) * (((cfg.nphig + 3) & ~3) + (size_t)(cfg.sum_width + cfg.sum_out) * MLP_BS);
+}
+
+template <typename T>
+cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu) {
+  const size_t smem = mlp_fwd_smem(cfg);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(k_mlp_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t ntiles = (nb + MLP_BS - 1) / MLP_BS;
+  int blocks = (int)(ntiles < (int64_t)L.sm_count * 4 ? ntiles : (int64_t)L.sm_count * 4);
+  if (blocks < 1) blocks = 1;
+  k_mlp_fwd<T><<<blocks, MLP_BS, smem, L.stream>>>(cfg, phi, xM, nb, mu);
+  HVI_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+template <typename T>
+cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, const T* mubar, int64_t nb,
+                           double* part, int* nblk_out, int nblk_max) {
+  const size_t smem = mlp_bwd_smem(cfg);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(k_mlp_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t ntiles = (nb + MLP_BS - 1) / MLP_BS;
+  int blocks = (int)(ntiles < (int64_t)nblk_max ? ntiles : (int64_t)nblk_max);
+  if (blocks < 1) blocks = 1;
+  k_mlp_bwd<T><<<blocks, MLP_BS, smem, L.stream>>>(cfg, phi, xM, mubar, nb, part);
+  HVI_LAUNCH_CHECK();
+  *nblk_out = blocks;
+  return cudaSuccess;
+}
+
+template <typename T, int NP, int NM, int NO>
+static cudaError_t launch_stream_inst(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, int* nrows_out,
+                                      int nrows_max) {
+  constexpr int CH = 16 / sizeof(T), MC = 8 * CH, NWARP = STREAM_THREADS / 32;
+  const size_t smem = (size_t)NWARP * 32 * NM * MC * sizeof(T) + (size_t)NWARP * nacc(NP, NM) * sizeof(double);
+  auto kern = k_stream<T, NP, NM, NO>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, STREAM_THREADS, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  const int64_t ntiles = (a.nb + 31) / 32;
+  int64_t blocks = (ntiles + NWARP - 1) / NWARP;
+  if (blocks > (int64_t)L.sm_count * occ) blocks = (int64_t)L.sm_count * occ;
+  if (blocks * NWARP > nrows_max) blocks = nrows_max / NWARP;
+  if (blocks < 1) blocks = 1;
+  kern<<<(int)blocks, STREAM_THREADS, smem, L.stream>>>(cfg, a);
+  HVI_LAUNCH_CHECK();
+  *nrows_out = (int)blocks * NWARP;
+  return cudaSuccess;
+}
+
+#define HVI_STREAM_CASES(X) \
+  X(0, 2, 8) X(1, 2, 8) X(2, 2, 8) X(0, 3, 8) X(1, 3, 8) X(2, 3, 8) X(3, 2, 8) X(2, 1, 8) X(2, 2, 4)
+
+bool stream_supported(int nP, int nM, int nO) {
+#define X(P, M_, O) if (nP == P && nM == M_ && nO == O) return true;
+  HVI_STREAM_CASES(X)
+#undef X
+  return false;
+}
+
+template <typename T>
+cudaError_t launch_stream(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, int* nrows_out, int nrows_max) {
+#define X(P, M_, O) \
+  if (cfg.nP == P && cfg.nM == M_ && cfg.nO == O) return launch_stream_inst<T, P, M_, O>(L, cfg, a, nrows_out, nrows_max);
+  HVI_STREAM_CASES(X)
+#undef X
+  return cudaErrorInvalidConfiguration;
+}
+
+template <typename T>
+cudaError_t launch_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, const T* pdraw,
+                            const EvalConsts<T>* ec, const double* part_stream, int nrows, const double* part_mlp,
+                            int nblk, double const_nly, int64_t nb, int M, double* out, T* grad_T) {
+  k_finalize<T><<<1, FIN_THREADS, 0, L.stream>>>(cfg, phi, zP, pdraw, ec, part_stream, nrows, part_mlp, nblk, const_nly,
+                                                nb, M, out, nullptr);
+  HVI_LAUNCH_CHECK();
+  if (grad_T) {
+    k_cast_grad<T><<<(cfg.nphi + 255) / 256, 256, 0, L.stream>>>(cfg.nphi, out, grad_T);
+    HVI_LAUNCH_CHECK();
+  }
+  return cudaSuccess;
+}
+
+template <typename T>
+cudaError_t launch_gen_normal(const Launch& L, T* z, int64_t n_cols, int M, uint64_t seed, int64_t col_offset) {
+  if (n_cols <= 0) return cudaSuccess;
+  const int64_t n = n_cols * ((M + 3) / 4);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)L.sm_count * 16) blocks = (int64_t)L.sm_count * 16;
+  k_gen_normal<T><<<(int)blocks, 256, 0, L.stream>>>(z, n_cols, M, seed, col_offset);
+  HVI_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+template <typename T>
+cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, const T* pdraw, T* zetaP,
+                                 T* zetaMs_tr, T* sigma) {
+  int64_t n = a.nb * cfg.nM;
+  if (n < (int64_t)cfg.nP * a.M) n = (int64_t)cfg.nP * a.M;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > (int64_t)L.sm_count * 16) blocks = (int64_t)L.sm_count * 16;
+  // the first nP*M threads also copy ζP; make sure they exist
+  if (blocks * 256 < (int64_t)cfg.nP * a.M) return cudaErrorInvalidConfiguration;
+  k_generate_zeta<T><<<(int)blocks, 256, 0, L.stream>>>(cfg, a, pdraw, zetaP, zetaMs_tr, sigma);
+  HVI_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+#define HVI_INSTANTIATE(T)                                                                                              \
+  template cudaError_t launch_preprocess<T>(const Launch&, int, int64_t, const T*, const T*, const T*, T*, double*, int*); \
+  template cudaError_t launch_prologue<T>(const Launch&, const Cfg<T>&, const T*, const T*, int, EvalConsts<T>*, T*);    \
+  template cudaError_t launch_mlp_fwd<T>(const Launch&, const Cfg<T>&, const T*, const T*, int64_t, T*);                 \
+  template cudaError_t launch_mlp_bwd<T>(const Launch&, const Cfg<T>&, const T*, const T*, const T*, int64_t, double*,   \
+                                         int*, int);                                                                     \
+  template cudaError_t launch_stream<T>(const Launch&, const Cfg<T>&, const StreamArgs<T>&, int*, int);                  \
+  template cudaError_t launch_finalize<T>(const Launch&, const Cfg<T>&, const T*, const T*, const T*,                    \
+                                          const EvalConsts<T>*, const double*, int, const double*, int, double, int64_t, \
+                                          int, double*, T*);                                                             \
+  template cudaError_t launch_gen_normal<T>(const Launch&, T*, int64_t, int, uint64_t, int64_t);                         \
+  template cudaError_t launch_generate_zeta<T>(const Launch&, const Cfg<T>&, const StreamArgs<T>&, const T*, T*, T*, T*);
+HVI_INSTANTIATE(float)
+HVI_INSTANTIATE(double)
+
+}  // namespace hvi

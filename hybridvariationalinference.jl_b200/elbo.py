@@ -1,0 +1,249 @@
+"""Host-side mirror of the reference's cost-function interface for the neg-ELBO path, on top of
+the C-ABI library (include/hvi_b200.h).
+
+Reference interface mirrored (paths relative to /root/reference):
+  * ``get_loss_elbo`` closure ``loss_elbo(ϕ, rng, xM, xP, y_o, y_unc, i_sites)`` (src/HybridSolver.jl:293-324)
+  * ``neg_elbo_gtf`` / ``neg_elbo_gtf_components`` (src/elbo.jl:30-88)
+  * ``generate_ζ`` (src/elbo.jl:472-521), ``transformU_block_cholesky1`` positions
+    (src/cholesky.jl:30-50,233-247), ``ComponentArrayInterpreter`` positions
+    (src/ComponentArrayInterpreter.jl:281-288)
+
+The draws ξ = (zP, zMs) of ``sample_ζresid_norm`` (src/elbo.jl:605-606) are either passed in (bit
+reproducible, used for parity) or produced on the device from a seed (like the reference's
+CUDA.randn override, ext/HybridVariationalInferenceCUDAExt.jl:82-86).
+
+No CPU fallback: every call goes through the CUDA library and raises if it is not available.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import numpy as np
+
+from . import _abi as A
+from .problem import HybridProblem
+
+COMPONENT_NAMES = ("nLjoint", "entropy_ζ", "loss_penalty", "nLy", "neg_log_prior", "neg_log_jac")
+
+
+class HVIError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"hvi_b200 error {code}: {msg}")
+        self.code = code
+
+
+class NegElboComponents(NamedTuple):
+    """NamedTuple returned by neg_elbo_gtf_components (src/elbo.jl:200)."""
+    nLjoint: float
+    entropy_ζ: float
+    loss_penalty: float
+    nLy: float
+    neg_log_prior: float
+    neg_log_jac: float
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):  # torch tensor (device memory handle only)
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(int(a))
+
+
+def _is_device(a):
+    return hasattr(a, "data_ptr") and a.is_cuda
+
+
+class NegElboPlan:
+    """One problem description bound to one GPU: owns the `hvi_plan`.  Stands in for the keyword
+    set that `get_loss_elbo` captures (src/HybridSolver.jl:240-245)."""
+
+    def __init__(self, prob: HybridProblem, device: int = 0, count_globals: bool = True, lib_path: Optional[str] = None):
+        self.lib = A.load_library(lib_path)
+        self.prob = prob
+        self.desc = prob.to_desc(device, count_globals)
+        self.device = device
+        h = C.c_void_p()
+        rc = self.lib.hvi_plan_create(C.byref(self.desc), C.byref(h))
+        if rc != A.HVI_OK:
+            raise HVIError(rc, (self.lib.hvi_last_error(None) or b"").decode())
+        self._h = h
+        self.n_phi = int(self.lib.hvi_phi_len(self._h))
+        self.n_site = 0
+        self.dt = prob.np_dtype
+
+    # -- lifetime ------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.hvi_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, allow_nonfinite=False):
+        if rc == A.HVI_OK or (allow_nonfinite and rc == A.HVI_ENONFINITE):
+            return rc
+        raise HVIError(rc, (self.lib.hvi_last_error(self._h) or b"").decode())
+
+    # -- index maps ----------------------------------------------------------------------
+    def positions(self):
+        """0-based (offset, length) of (ϕg, logσ2_ζP, coef_logσ2_ζMs, ρsP, ρsM, μP) as the library
+        lays ϕ out -- must equal `prob.positions()` bit for bit."""
+        off = (C.c_int64 * 6)()
+        ln = (C.c_int64 * 6)()
+        self._check(self.lib.hvi_phi_positions(self._h, off, ln))
+        names = ("ϕg", "logσ2_ζP", "coef_logσ2_ζMs", "ρsP", "ρsM", "μP")
+        return {n: range(off[i], off[i] + ln[i]) for i, n in enumerate(names)}
+
+    @property
+    def launch_count(self):
+        return int(self.lib.hvi_launch_count(self._h))
+
+    def set_profiling(self, on: bool):
+        self._check(self.lib.hvi_plan_set_profiling(self._h, int(on)))
+
+    def kernel_times_ms(self):
+        """(prologue, g forward, fused stream, g backward, finalize) of the last profiled evaluation."""
+        ms = (C.c_float * 5)()
+        self._check(self.lib.hvi_plan_kernel_times(self._h, ms))
+        return dict(zip(("prologue", "mlp_fwd", "stream", "mlp_bwd", "finalize"), map(float, ms)))
+
+    # -- data ----------------------------------------------------------------------------
+    def set_data(self, xM, xP, y_o, y_unc):
+        """Register one batch (xM, xP, y_o, y_unc) -- a DataLoader element of the reference
+        (src/AbstractHybridProblem.jl:179-184).  numpy arrays (host) or CUDA tensors (device),
+        column = site."""
+        dev = _is_device(xM)
+        if dev:
+            n_site = xM.shape[-1] if xM.dim() == 2 else xM.numel() // self.prob.n_covar
+            args = (xM, xP, y_o, y_unc)
+        else:
+            f = lambda a: np.asfortranarray(a, dtype=self.dt)
+            args = tuple(map(f, (xM, xP, y_o, y_unc)))
+            n_site = args[0].shape[1]
+            assert args[1].shape == (2 * self.prob.n_obs, n_site) and args[2].shape == (self.prob.n_obs, n_site)
+            assert args[3].shape == args[2].shape and args[0].shape[0] == self.prob.n_covar
+        self._keep = args
+        self._check(self.lib.hvi_plan_set_data(self._h, n_site, *map(_ptr, args),
+                                               A.HVI_MEM_DEVICE if dev else A.HVI_MEM_HOST))
+        self.n_site = n_site
+
+    # -- the hot path ----------------------------------------------------------------------
+    def neg_elbo_withgradient(self, ϕ, zP=None, zMs=None, *, n_MC=None, seed=None, site_offset=0,
+                              want_grad=True, allow_nonfinite=False):
+        """(nL, components, ∇ϕ) -- `Zygote.withgradient(loss_elbo, ϕ)` of the reference
+        (src/HybridSolver.jl:256-258).  Host arrays in, host results out."""
+        comps = (C.c_double * 6)()
+        nL = C.c_double()
+        dev = _is_device(ϕ)
+        if dev:
+            import torch
+            grad = torch.empty_like(ϕ) if want_grad else None
+            ϕ_ = ϕ
+        else:
+            ϕ_ = np.ascontiguousarray(ϕ, dtype=self.dt)
+            assert ϕ_.shape == (self.n_phi,), (ϕ_.shape, self.n_phi)
+            grad = np.empty(self.n_phi, dtype=self.dt) if want_grad else None
+        mem = A.HVI_MEM_DEVICE if dev else A.HVI_MEM_HOST
+        if zMs is None:
+            assert seed is not None and n_MC is not None, "pass ξ=(zP, zMs) or (n_MC, seed)"
+            rc = self.lib.hvi_neg_elbo_grad_rng(self._h, n_MC, _ptr(ϕ_), seed, site_offset, mem, comps, C.byref(nL), _ptr(grad))
+        else:
+            if dev:
+                zP_, zMs_ = zP, zMs
+                M = zMs.shape[0] if zMs.dim() == 2 and zMs.stride(0) == 1 else int(n_MC)
+            else:
+                zP_ = np.asfortranarray(zP, dtype=self.dt)
+                zMs_ = np.asfortranarray(zMs, dtype=self.dt)
+                M = zMs_.shape[0]
+                assert zMs_.shape == (M, self.prob.n_M * self.n_site), zMs_.shape
+                assert zP_.shape == (M, self.prob.n_P), zP_.shape
+            rc = self.lib.hvi_neg_elbo_grad(self._h, M, _ptr(ϕ_), _ptr(zP_), _ptr(zMs_), mem, comps, C.byref(nL), _ptr(grad))
+        self._check(rc, allow_nonfinite)
+        return float(nL.value), NegElboComponents(*comps), grad
+
+    def neg_elbo_async(self, ϕ_dev, zP_dev, zMs_dev, out_dev, n_MC, stream_ptr, seed=0, site_offset=0):
+        """Stream-ordered device variant (multi-GPU jobs): out_dev (float64, n_phi+8)."""
+        self._check(self.lib.hvi_neg_elbo_grad_async(self._h, n_MC, _ptr(ϕ_dev), _ptr(zP_dev), _ptr(zMs_dev), seed,
+                                                     site_offset, _ptr(out_dev), C.c_void_p(stream_ptr)))
+
+    def generate_ζ(self, ϕ, zP, zMs):
+        """generate_ζ (src/elbo.jl:472-521): ζsP (n_θP×n_MC), ζsMs_tr (n_site×n_θM×n_MC), σ."""
+        ϕ_ = np.ascontiguousarray(ϕ, dtype=self.dt)
+        zP_ = np.asfortranarray(zP, dtype=self.dt)
+        zMs_ = np.asfortranarray(zMs, dtype=self.dt)
+        M = zMs_.shape[0]
+        nP, nM, nb = self.prob.n_P, self.prob.n_M, self.n_site
+        ζP = np.empty((nP, M), dtype=self.dt, order="F")
+        ζMs = np.empty((nb, nM, M), dtype=self.dt, order="F")
+        σ = np.empty(nP + nM * nb, dtype=self.dt)
+        self._check(self.lib.hvi_generate_zeta(self._h, M, _ptr(ϕ_), _ptr(zP_), _ptr(zMs_), A.HVI_MEM_HOST,
+                                               _ptr(ζP), _ptr(ζMs), _ptr(σ)))
+        return ζP, ζMs, σ
+
+    def apply_g(self, ϕ):
+        """g(xM, ϕg) → μ_ζMs (n_θM × n_site) (src/ModelApplicator.jl:19-23,163-176)."""
+        ϕ_ = np.ascontiguousarray(ϕ, dtype=self.dt)
+        mu = np.empty((self.prob.n_M, self.n_site), dtype=self.dt, order="F")
+        self._check(self.lib.hvi_apply_g(self._h, _ptr(ϕ_), A.HVI_MEM_HOST, _ptr(mu)))
+        return mu
+
+
+# ---- functional spellings that read like the reference's -----------------------------------
+def neg_elbo_gtf_components(plan: NegElboPlan, ϕ, zP, zMs) -> NegElboComponents:
+    """src/elbo.jl:46-88"""
+    return plan.neg_elbo_withgradient(ϕ, zP, zMs, want_grad=False)[1]
+
+
+def neg_elbo_gtf(plan: NegElboPlan, ϕ, zP, zMs) -> float:
+    """src/elbo.jl:30-44: nL = nLjoint − entropy_ζ + loss_penalty (a Float64 even for Float32 ϕ)."""
+    return plan.neg_elbo_withgradient(ϕ, zP, zMs, want_grad=False)[0]
+
+
+def get_loss_elbo(prob: HybridProblem, device: int = 0, n_MC: int = 12):
+    """`get_loss_elbo` (src/HybridSolver.jl:293-324): returns
+    ``loss_elbo(ϕ, rng_seed, xM, xP, y_o, y_unc, i_sites) -> (nL, components, ∇ϕ)``; the batch is
+    re-registered only when it changes."""
+    plan = NegElboPlan(prob, device)
+    state = {"key": None}
+
+    def loss_elbo(ϕ, rng_seed, xM, xP, y_o, y_unc, i_sites=None):
+        key = (id(xM), id(xP), id(y_o), id(y_unc))
+        if key != state["key"]:
+            plan.set_data(xM, xP, y_o, y_unc)
+            state["key"] = key
+        return plan.neg_elbo_withgradient(ϕ, n_MC=n_MC, seed=int(rng_seed))
+
+    loss_elbo.plan = plan
+    return loss_elbo
+
+
+# ---- integer index maps exported by the library (bit-exact contract) ------------------------
+def vec2utri_pos(s: int):
+    """src/cholesky.jl:30-37 (one-based)"""
+    lib = A.load_library()
+    r, c = C.c_int64(), C.c_int64()
+    if lib.hvi_vec2utri_pos(s, C.byref(r), C.byref(c)) != 0:
+        raise ValueError(s)
+    return int(r.value), int(c.value)
+
+
+def utri2vec_pos(row: int, col: int) -> int:
+    """src/cholesky.jl:42-50"""
+    v = A.load_library().hvi_utri2vec_pos(row, col)
+    if v < 0:
+        raise AssertionError("row <= col")
+    return int(v)
+
+
+def get_cor_count(cor_ends) -> int:
+    """src/cholesky.jl:233-247"""
+    arr = (C.c_int32 * max(1, len(cor_ends)))(*cor_ends)
+    return int(A.load_library().hvi_cor_count(arr, len(cor_ends)))

@@ -163,6 +163,12 @@ int hvi_apply_g(hvi_plan* plan, const void* phi, int mem_kind, void* mu_zeta);
 /* number of kernels launched by this plan since creation (bench.py's gpu_launches) */
 int64_t hvi_launch_count(const hvi_plan* plan);
 
+/* Per-kernel device timing of the next evaluations: CUDA events recorded on the launching
+ * stream around each kernel.  ms[5] = (prologue, g forward, fused streaming kernel, g backward,
+ * finalize) of the last evaluation.  The reference has no tracing. */
+int hvi_plan_set_profiling(hvi_plan* plan, int on);
+int hvi_plan_kernel_times(hvi_plan* plan, float ms[5]);
+
 #ifdef __cplusplus
 }
 #endif

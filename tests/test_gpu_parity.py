@@ -1,0 +1,148 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the float64 oracle on identical inputs
+and identical standard-normal draws ξ.
+
+Tolerances (BASELINE.json north_star): value and gradient within rel 1e-10 (Float64) and 1e-4
+(Float32).  "rel" for the gradient is max|g − g_ref| / max|g_ref| per ϕ component block
+(ϕg, logσ2_ζP, coef_logσ2_ζMs, ρsP, ρsM, μP); for the scalar it is |v − v_ref| / |v_ref| and
+for the six components |c − c_ref| / max|c_ref|.
+"""
+import numpy as np
+import pytest
+
+from helpers import O, hvi_b200, oracle_spec
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f64": 1e-10, "f32": 1e-4}
+
+CASES = {
+    "C1_test_HybridProblem": lambda dt: hvi_b200.construct_problem_test_HybridProblem(dtype=dt),
+    "DoubleMM_default": lambda dt: hvi_b200.DoubleMMCase(dtype=dt),
+    "DoubleMM_omit_r0": lambda dt: hvi_b200.DoubleMMCase(("omit_r0",), dtype=dt),
+    "DoubleMM_K1global": lambda dt: hvi_b200.DoubleMMCase(("omit_r0", "K1global"), dtype=dt),
+    "DoubleMM_no_globals": lambda dt: hvi_b200.DoubleMMCase(("no_globals",), dtype=dt),
+    "DoubleMM_stackedMS": lambda dt: hvi_b200.DoubleMMCase(("stackedMS",), dtype=dt),
+    "DoubleMM_transIdent": lambda dt: hvi_b200.DoubleMMCase(("transIdent",), dtype=dt),
+    "DoubleMM_neglect_cor": lambda dt: hvi_b200.DoubleMMCase(("neglect_cor",), dtype=dt),
+    "DoubleMM_rangescaling": lambda dt: hvi_b200.DoubleMMCase(("use_rangescaling",), dtype=dt),
+}
+
+
+def check(prob, nb, M, nan_frac=0.0, perturbed=True, seed=111):
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=seed, driver_nan_frac=nan_frac)
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
+    ϕ = prob.init_ϕ(perturbed=perturbed)
+    plan = hvi_b200.NegElboPlan(prob)
+    assert {k: (r.start, r.stop) for k, r in plan.positions().items()} == \
+           {k: (r.start, r.stop) for k, r in prob.positions().items()}
+    plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    nL, comps, g = plan.neg_elbo_withgradient(ϕ, zP, zMs)
+    nL_o, comps_o, g_o = O.value_and_grad(oracle_spec(prob), ϕ, data["xM"], data["xP"], data["y_o"], data["y_unc"],
+                                          zP, zMs, prob.dtype)
+    tol = TOL[prob.dtype]
+    assert abs(nL - nL_o) <= tol * abs(nL_o), (nL, nL_o)
+    assert np.max(np.abs(np.array(comps) - comps_o)) <= tol * np.max(np.abs(comps_o)), (comps, comps_o)
+    for name, r in prob.positions().items():
+        if len(r) == 0:
+            continue
+        err = np.max(np.abs(g[r].astype(np.float64) - g_o[r]))
+        scale = np.max(np.abs(g_o[r]))
+        assert err <= tol * scale, (name, err, scale, g[r][:4], g_o[r][:4])
+    # value-only call gives the same scalar
+    nL2, _, g2 = plan.neg_elbo_withgradient(ϕ, zP, zMs, want_grad=False)
+    assert g2 is None and nL2 == nL
+    plan.close()
+    return nL, g
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_config1_sizes(case, dtype):
+    """BASELINE config 1 sizes: 20 sites, n_MC = 3 (test/test_HybridProblem.jl:252)."""
+    check(CASES[case](dtype), nb=20, M=3)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("nb,M", [(1, 4), (31, 8), (33, 32), (257, 64), (1000, 12), (64, 36)])
+def test_ragged_sizes_staged_and_direct(nb, M, dtype):
+    """site counts around the 32-site tile, draw counts on both the cp.async path (M % 4 == 0)
+    and the direct path, partial last stage (M = 36, 12)."""
+    check(hvi_b200.DoubleMMCase(dtype=dtype), nb=nb, M=M)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_missing_drivers(dtype):
+    """:driverNAN generalised (src/DoubleMM/f_doubleMM.jl:332-340): NaN drivers with NaN
+    observations are skipped in value and gradient (test/test_missingdriver.jl:84-137)."""
+    nL, g = check(hvi_b200.DoubleMMCase(dtype=dtype), nb=200, M=8, nan_frac=0.3)
+    assert np.isfinite(nL) and np.all(np.isfinite(g))
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_initial_parameters(dtype):
+    """ϕ as initialised by the reference (logσ2 = −10, ρ = 0)."""
+    check(hvi_b200.DoubleMMCase(dtype=dtype), nb=100, M=16, perturbed=False)
+
+
+def test_run_to_run_bit_reproducible():
+    prob = hvi_b200.DoubleMMCase(dtype="f32")
+    nb, M = 5000, 32
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb)
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
+    ϕ = prob.init_ϕ(perturbed=True)
+    plan = hvi_b200.NegElboPlan(prob)
+    plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    a = plan.neg_elbo_withgradient(ϕ, zP, zMs)
+    b = plan.neg_elbo_withgradient(ϕ, zP, zMs)
+    assert a[0] == b[0] and np.array_equal(a[2], b[2])
+
+
+def test_anomaly_flag_like_reference_nan():
+    """driver NaN but observation finite: the reference's loss is NaN;
+    the library reports HVI_ENONFINITE instead of silently masking."""
+    prob = hvi_b200.DoubleMMCase(dtype="f32")
+    nb, M = 40, 4
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb)
+    data["xP"][3, 5] = np.nan
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
+    plan = hvi_b200.NegElboPlan(prob)
+    plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    with pytest.raises(hvi_b200.HVIError) as ei:
+        plan.neg_elbo_withgradient(prob.init_ϕ(), zP, zMs)
+    assert ei.value.code == hvi_b200._abi.HVI_ENONFINITE
+
+
+def test_generate_zeta_matches_oracle():
+    import torch
+    prob = hvi_b200.DoubleMMCase(dtype="f64")
+    nb, M = 50, 7
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb)
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
+    ϕ = prob.init_ϕ(perturbed=True)
+    plan = hvi_b200.NegElboPlan(prob)
+    plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    ζP, ζMs, σ = plan.generate_ζ(ϕ, zP, zMs)
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+    ζP_o, ζMs_o, σ_o = O.generate_zeta(oracle_spec(prob), t(ϕ), t(data["xM"]), t(zP), t(zMs))
+    assert ζMs.shape == (nb, prob.n_M, M) and ζP.shape == (prob.n_P, M)   # test/test_elbo.jl:98-127
+    np.testing.assert_allclose(ζP, ζP_o.numpy(), rtol=1e-12)
+    np.testing.assert_allclose(ζMs, ζMs_o.numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(σ, σ_o.numpy(), rtol=1e-12)
+
+
+def test_device_rng_mode_statistics():
+    """device-side draws (CUDA.randn stand-in): finite, seed-reproducible, and the stochastic
+    ELBO agrees with an evaluation on explicit draws within Monte-Carlo noise."""
+    prob = hvi_b200.DoubleMMCase(dtype="f32")
+    nb, M = 2000, 32
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb)
+    ϕ = prob.init_ϕ(perturbed=True)
+    plan = hvi_b200.NegElboPlan(prob)
+    plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    a = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=7)
+    b = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=7)
+    c = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=8)
+    assert a[0] == b[0] and np.array_equal(a[2], b[2]) and a[0] != c[0]
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
+    d = plan.neg_elbo_withgradient(ϕ, zP, zMs)
+    assert abs(a[0] - d[0]) / abs(d[0]) < 0.2
