@@ -384,7 +384,7 @@ template <typename T>
 static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* zMs, double* out, T* grad_T,
                         cudaStream_t s) {
   const Cfg<T>& cfg = cfg_of<T>(p);
-  int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)sizeof(T) * 4 * (cfg.nP > 0 ? cfg.nP : 1) * M);
+  int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)(sizeof(T) * pdraw_elems(cfg.nP, M)));
   if (rc) return rc;
   Launch L{s, p->sm_count, &p->launches};
   EvalConsts<T>* ec = (EvalConsts<T>*)p->d_ec;
@@ -398,7 +398,7 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   MARK();
   StreamArgs<T> a;
   a.rec = (const T*)p->d_rec; a.mu = (const T*)p->d_mu; a.zMs = zMs;
-  a.thP = pdraw + (size_t)2 * cfg.nP * M; a.gP = pdraw + (size_t)3 * cfg.nP * M; a.zP = zP;
+  a.pd = pdraw + (((size_t)4 * (cfg.nP > 0 ? cfg.nP : 1) * M + 3) & ~(size_t)3); a.pd_in_smem = 0;
   a.ec = ec; a.mubar = (T*)p->d_mubar; a.partials = p->d_part_stream; a.nb = p->nb; a.M = M;
   a.staged = (M % (16 / (int)sizeof(T)) == 0) && (((uintptr_t)zMs & 15) == 0);
   int nrows = 0, nblk = 0;
@@ -546,14 +546,14 @@ static int generate_zeta_t(hvi_plan* p, int M, const void* phi, const void* zP, 
     CU(p, cudaMalloc(&tmp, sizeof(T) * ((size_t)nP * M + nzM + nP + (size_t)nM * nb)));
     o1 = tmp; o2 = (T*)tmp + (size_t)nP * M; o3 = (T*)o2 + nzM;
   }
-  int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)sizeof(T) * 4 * (nP > 0 ? nP : 1) * M);
+  int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)(sizeof(T) * pdraw_elems(nP, M)));
   if (rc) { if (tmp) cudaFree(tmp); return rc; }
   Launch L{s, p->sm_count, &p->launches};
   EvalConsts<T>* ec = (EvalConsts<T>*)p->d_ec;
   T* pdraw = (T*)p->d_pdraw;
   StreamArgs<T> a;
   memset(&a, 0, sizeof a);
-  a.mu = (const T*)p->d_mu; a.zMs = dzM; a.zP = dzP; a.ec = ec; a.nb = nb; a.M = M;
+  a.mu = (const T*)p->d_mu; a.zMs = dzM; a.ec = ec; a.nb = nb; a.M = M;
   cudaError_t e = launch_prologue<T>(L, cfg, dphi, dzP, M, ec, pdraw);
   if (e == cudaSuccess) e = launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, nb, (T*)p->d_mu);
   if (e == cudaSuccess) e = launch_generate_zeta<T>(L, cfg, a, pdraw, (T*)o1, (T*)o2, (T*)o3);

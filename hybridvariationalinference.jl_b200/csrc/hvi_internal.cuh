@@ -56,14 +56,13 @@ struct StreamArgs {
   const T* rec;      // tiled site records [tile][4*nO][32]: S1, S2, y_o, w = mask·exp(−y_unc)
   const T* mu;       // μ_ζ (nM × nb) column-major
   const T* zMs;      // (M × nM·nb) column-major
-  const T* thP;      // [nP][M] θP per draw
-  const T* gP;       // [nP][M] dθP/dζP (0 where clamped)
-  const T* zP;       // (M × nP) column-major
+  const T* pd;       // per-draw records of the global block [M][pd_stride(nP)]: θP, dθP/dζP, zP
   const EvalConsts<T>* ec;
   T* mubar;          // cotangent of μ_ζ (nM × nb)
   double* partials;  // [gridDim.x * warps][nacc]
   int64_t nb;
   int M;
+  int pd_in_smem;    // 1: the kernel copies pd into shared memory (it fits)
   int staged;        // 1: M % (16/sizeof(T)) == 0 and zMs 16-byte aligned → cp.async staging
 };
 
@@ -79,7 +78,7 @@ cudaError_t launch_preprocess(const Launch& L, int nO, int64_t nb, const T* xP, 
                               double* part /*[2*nwarps]*/, int* nrows_out);
 template <typename T>
 cudaError_t launch_prologue(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, int M, EvalConsts<T>* ec,
-                            T* pdraw /*4 arrays [nP][M]: rP, zetaP, thP, gP*/);
+                            T* pdraw /*4 arrays [nP][M]: rP, zetaP, thP, gP; then [M][pd_stride] records*/);
 template <typename T>
 cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu);
 template <typename T>
@@ -96,6 +95,8 @@ cudaError_t launch_gen_normal(const Launch& L, T* z, int64_t n_cols, int M, uint
 template <typename T>
 cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, const T* pdraw, T* zetaP,
                                  T* zetaMs_tr, T* sigma);
+__host__ __device__ constexpr int pd_stride(int nP) { return ((3 * nP + 3) / 4) * 4; }
+inline size_t pdraw_elems(int nP, int M) { return (size_t)4 * (nP > 0 ? nP : 1) * M + (size_t)M * pd_stride(nP) + 4; }
 int stream_max_rows(int sm_count);
 int mlp_bwd_max_blocks(int sm_count);
 bool stream_supported(int nP, int nM, int nO);

@@ -25,7 +25,12 @@ __device__ __forceinline__ float rcp_fast(float x) {
   return r;
 }
 __device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
-__device__ __forceinline__ float exp_t(float x) { return expf(x); }
+// ex2.approx of x·log2(e): relative error ≈ 2^-22 plus |x|·6e-8 from the argument rounding
+__device__ __forceinline__ float exp_t(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
 __device__ __forceinline__ double exp_t(double x) { return exp(x); }
 __device__ __forceinline__ float log_t(float x) { return logf(x); }
 __device__ __forceinline__ double log_t(double x) { return log(x); }
@@ -49,6 +54,20 @@ __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
+// two-wide values: float2 maps to the packed FP32 instructions of sm_100 (FADD2/FMUL2/FFMA2 --
+// same FLOP rate as the scalar forms on B200, half the issue slots), double2 is plain pairs
+template <typename T> struct PairT;
+template <> struct PairT<float> { using type = float2; };
+template <> struct PairT<double> { using type = double2; };
+__device__ __forceinline__ float2 mk2(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ double2 mk2(double x, double y) { return make_double2(x, y); }
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ double2 padd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 pmul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ double2 pfma(double2 a, double2 b, double2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
+
 template <typename T>
 __device__ __forceinline__ T act_f(int act, T z) {
   if (act == HVI_ACT_TANH) return tanh_t(z);
@@ -67,8 +86,8 @@ __device__ __forceinline__ T act_d(int act, T a) {
 // of −logpdf(prior, θ) and its derivative w.r.t. ζ, the log-Jacobian term and its derivative.
 template <typename T>
 __device__ __forceinline__ void transform_prior(int tr, int pk, T a, T ib, T lo, T hi, T zeta, T& th, T& dth, T& pv,
-                                                T& dpz, T& lj, T& dlj) {
-  T raw, d;
+                                                T& dz, T& lj) {
+  T raw, d, dlj, dpz;
   if (tr == HVI_TR_EXP) {
     raw = exp_t(zeta); d = raw; lj = zeta; dlj = T(1);
   } else if (tr == HVI_TR_LOGISTIC) {
@@ -86,7 +105,8 @@ __device__ __forceinline__ void transform_prior(int tr, int pk, T a, T ib, T lo,
     const T u = (lt - a) * ib;
     pv = lt + T(0.5) * u * u;
     // d/dθ = (1 + u·ib)/θ ; times dθ/dζ
-    dpz = (tr == HVI_TR_EXP) ? (uncl ? T(1) + u * ib : T(0)) : (T(1) + u * ib) / th * dth;
+    if (tr == HVI_TR_EXP) { dz = uncl ? u * ib : T(-1); return; }   // (1 + u·ib) − 1 when unclamped
+    dpz = (T(1) + u * ib) / th * dth;
   } else if (pk == HVI_PR_NORMAL) {
     const T u = (th - a) * ib;
     pv = T(0.5) * u * u;
@@ -94,6 +114,7 @@ __device__ __forceinline__ void transform_prior(int tr, int pk, T a, T ib, T lo,
   } else {
     pv = T(0); dpz = T(0);
   }
+  dz = dpz - dlj;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -182,10 +203,12 @@ __global__ void k_prologue(const __grid_constant__ Cfg<T> cfg, const T* __restri
     for (int jj = cfg.blkP_start[j]; jj <= j; jj++) t += s.UP[jj][j] * zP[m + (size_t)M * jj];
     const T r = s.sigP[j] * t;
     const T zeta = s.muP[j] + r;
-    T th, dth, pv, dpz, lj, dlj;
-    transform_prior<T>(cfg.transP[j], HVI_PR_NONE, T(0), T(0), cfg.clamp_lo, cfg.clamp_hi, zeta, th, dth, pv, dpz, lj,
-                       dlj);
+    T th, dth, pv, dz, lj;
+    transform_prior<T>(cfg.transP[j], HVI_PR_NONE, T(0), T(0), cfg.clamp_lo, cfg.clamp_hi, zeta, th, dth, pv, dz, lj);
     rP[e] = r; zetaP[e] = zeta; thP[e] = th; gP[e] = dth;
+    // packed per-draw record read by the streaming kernel
+    T* pd = pdraw + (((size_t)4 * (nP > 0 ? nP : 1) * M + 3) & ~(size_t)3) + (size_t)m * pd_stride(nP);
+    pd[j] = th; pd[nP + j] = dth; pd[2 * nP + j] = zP[m + (size_t)M * j];
   }
 }
 
@@ -331,81 +354,143 @@ __global__ void __launch_bounds__(MLP_BS) k_mlp_bwd(const __grid_constant__ Cfg<
 // transposed; 16-byte chunks are rotated by the owning lane so that the transposed LDS.128 is
 // bank-conflict free.  Everything between μ_ζ and (μ̄_ζ, partial sums of the shared-parameter
 // cotangents) stays in registers.
+//
+// Traits: the PBM slot map, the bijector codes and the prior kinds are either read from the
+// constant bank at run time (DynTraits: any configuration) or baked in at compile time
+// (StaTraits: the named configurations below), which removes every select from the draw loop.
 // ---------------------------------------------------------------------------------------
 __host__ __device__ constexpr int ut(int j, int k) { return k * (k + 1) / 2 + j; }  // packed upper incl. diag
 
-template <typename T, int NP, int NM, int NO>
-struct SiteState {
-  T S1[NO], S2[NO], S12[NO], yo[NO], w[NO];
-  T mu[NM], sig[NM];
-  T U[tri(NM)];
-  T smu[NM], sz[tri(NM)];        // Σ_m ζ̄[k],  Σ_m ζ̄[k]·z[j]
-  T aP[NP > 0 ? NP : 1], cP[NP > 0 ? tri(NP) : 1];
-  T nly, prior, lj;
+struct DynTraits {
+  static constexpr bool STATIC = false;
+};
+// SLOTS: 4 nibbles (r0, r1, K1, K2), nibble = slot code + 1 (0 = fixed value);
+// TRM: 2 bits per θM column (bijector code); PRM: 2 bits per θM column (prior kind, 0 if omitted)
+template <uint32_t SLOTS, uint32_t TRM, uint32_t PRM>
+struct StaTraits {
+  static constexpr bool STATIC = true;
+  static constexpr uint32_t slots = SLOTS, trm = TRM, prm = PRM;
 };
 
+template <class TR, typename T>
+__device__ __forceinline__ int tr_slot(const Cfg<T>& cfg, int s) {
+  if constexpr (TR::STATIC) return (int)((TR::slots >> (4 * s)) & 15u) - 1;
+  else return cfg.slot_code[s];
+}
+template <class TR, typename T>
+__device__ __forceinline__ int tr_transM(const Cfg<T>& cfg, int k) {
+  if constexpr (TR::STATIC) return (int)((TR::trm >> (2 * k)) & 3u);
+  else return cfg.transM[k];
+}
+template <class TR, typename T>
+__device__ __forceinline__ int tr_priorM(const Cfg<T>& cfg, int k) {
+  if constexpr (TR::STATIC) return (int)((TR::prm >> (2 * k)) & 3u);
+  else return cfg.omit_priors ? HVI_PR_NONE : cfg.prM_kind[k];
+}
+
+// per-draw block of the global parameters, one record per draw: θP[NP], dθP/dζP[NP], zP[NP]
 template <typename T, int NP, int NM, int NO>
-__device__ __forceinline__ void do_draw(const Cfg<T>& cfg, const StreamArgs<T>& a, SiteState<T, NP, NM, NO>& st,
-                                        const T (&z)[NM], int m) {
-  T zeta[NM], th[NM], dth[NM], dpz[NM], dlj[NM];
+struct SiteState {
+  static constexpr int NOP = (NO + 1) / 2;   // observation pairs
+  typename PairT<T>::type S1[NOP], S2[NOP], S12[NOP], nyo[NOP], w[NOP];   // nyo = −y_o
+  typename PairT<T>::type nly2;  // Σ w·res² over the draws, two lanes
+  T mu[NM];
+  T sU[tri(NM)];                 // σ[k]·U[j,k]
+  T smu[NM], sz[tri(NM)];        // Σ_m ζ̄[k],  Σ_m ζ̄[k]·z[j]
+  T aP[NP > 0 ? NP : 1], cP[NP > 0 ? tri(NP) : 1];
+  T prior, lj;
+};
+
+// f_doubleMM + logden_normal + adjoint w.r.t. (r0, r1, K1, K2), all observations of one site
+// and one draw:  y = r0 + r1·S1/(K1+S1)·S2/(K2+S2)   (src/DoubleMM/f_doubleMM.jl:137)
+// accumulates Σ w·res² into st.nly2; pbar = (Σ dy, Σ dy·ab, −r1 Σ dy·ab/d1, −r1 Σ dy·ab/d2),
+// dy = w·res.  14 FP32 operations + 1 reciprocal per observation, two observations per
+// instruction.
+template <typename T, int NP, int NM, int NO>
+__device__ __forceinline__ void obs_loop(SiteState<T, NP, NM, NO>& st, const T (&par)[4], T (&pbar)[4]) {
+  using P = typename PairT<T>::type;
+  const P r0 = mk2(par[0], par[0]), r1 = mk2(par[1], par[1]);
+  const P k1 = mk2(par[2], par[2]), k2 = mk2(par[3], par[3]);
+  P g0 = mk2(T(0), T(0)), g1 = g0, gA = g0, gB = g0;
+#pragma unroll
+  for (int o = 0; o < SiteState<T, NP, NM, NO>::NOP; o++) {
+    const P d1 = padd(k1, st.S1[o]), d2 = padd(k2, st.S2[o]);
+    const P p = pmul(d1, d2);
+    const P rp = mk2(rcp_fast(p.x), rcp_fast(p.y));
+    const P ab = pmul(st.S12[o], rp);
+    const P y = pfma(r1, ab, r0);
+    const P res = padd(y, st.nyo[o]);
+    const P dy = pmul(res, st.w[o]);
+    st.nly2 = pfma(res, dy, st.nly2);
+    g0 = padd(g0, dy);
+    const P t = pmul(dy, ab);
+    g1 = padd(g1, t);
+    const P u = pmul(t, rp);
+    gA = pfma(u, d2, gA);
+    gB = pfma(u, d1, gB);
+  }
+  pbar[0] = g0.x + g0.y;
+  pbar[1] = g1.x + g1.y;
+  pbar[2] = -par[1] * (gA.x + gA.y);
+  pbar[3] = -par[1] * (gB.x + gB.y);
+}
+
+template <class TR, typename T, int NP, int NM, int NO>
+__device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, NO>& st, const T (&z)[NM],
+                                        const T* __restrict__ pd) {
+  T th[NM], dth[NM], dz[NM];  // dz = d(prior − logjac)/dζ
 #pragma unroll
   for (int k = 0; k < NM; k++) {
-    T t = T(0);
+    T zeta = st.mu[k];
 #pragma unroll
-    for (int j = 0; j <= k; j++) t = fma(st.U[ut(j, k)], z[j], t);
-    zeta[k] = fma(st.sig[k], t, st.mu[k]);
+    for (int j = 0; j <= k; j++) zeta = fma(st.sU[ut(j, k)], z[j], zeta);
     T pv, lj;
-    transform_prior<T>(cfg.transM[k], cfg.omit_priors ? HVI_PR_NONE : cfg.prM_kind[k], cfg.prM_a[k], cfg.prM_ib[k],
-                       cfg.clamp_lo, cfg.clamp_hi, zeta[k], th[k], dth[k], pv, dpz[k], lj, dlj[k]);
+    transform_prior<T>(tr_transM<TR>(cfg, k), tr_priorM<TR>(cfg, k), cfg.prM_a[k], cfg.prM_ib[k], cfg.clamp_lo,
+                       cfg.clamp_hi, zeta, th[k], dth[k], pv, dz[k], lj);
     st.prior += pv;
     st.lj += lj;
   }
-  T thp[NP > 0 ? NP : 1], gp[NP > 0 ? NP : 1];
+  T thp[NP > 0 ? NP : 1], gp[NP > 0 ? NP : 1], zp[NP > 0 ? NP : 1];
+  if constexpr (NP == 2 && sizeof(T) == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(pd);
+    const float2 v2 = *reinterpret_cast<const float2*>(pd + 4);
+    thp[0] = v.x; thp[1] = v.y; gp[0] = v.z; gp[1] = v.w; zp[0] = v2.x; zp[1] = v2.y;
+  } else {
 #pragma unroll
-  for (int j = 0; j < NP; j++) { thp[j] = __ldg(a.thP + (size_t)j * a.M + m); gp[j] = __ldg(a.gP + (size_t)j * a.M + m); }
+    for (int j = 0; j < NP; j++) { thp[j] = pd[j]; gp[j] = pd[NP + j]; zp[j] = pd[2 * NP + j]; }
+  }
   // gather (r0, r1, K1, K2) by slot (src/PBMApplicator.jl:234-239,283-287)
   T par[4];
 #pragma unroll
   for (int s = 0; s < 4; s++) {
     T v = cfg.slot_fix[s];
-    const int c = cfg.slot_code[s];
+    const int c = tr_slot<TR>(cfg, s);
 #pragma unroll
     for (int j = 0; j < NP; j++) v = (c == j) ? thp[j] : v;
 #pragma unroll
     for (int k = 0; k < NM; k++) v = (c == NP + k) ? th[k] : v;
     par[s] = v;
   }
-  // f_doubleMM + logden_normal + adjoint w.r.t. (r0, r1, K1, K2)
-  // y = r0 + r1·S1/(K1+S1)·S2/(K2+S2)   (src/DoubleMM/f_doubleMM.jl:137)
-  T g0 = T(0), g1 = T(0), gA = T(0), gB = T(0), nly = T(0);
-#pragma unroll
-  for (int o = 0; o < NO; o++) {
-    const T d1 = par[2] + st.S1[o], d2 = par[3] + st.S2[o];
-    const T rp = rcp_fast(d1 * d2);
-    const T ab = st.S12[o] * rp;
-    const T y = fma(par[1], ab, par[0]);
-    const T res = y - st.yo[o];
-    const T dy = res * st.w[o];
-    nly = fma(res, dy, nly);
-    g0 += dy;
-    const T t = dy * ab;
-    g1 += t;
-    gA = fma(t, d2 * rp, gA);
-    gB = fma(t, d1 * rp, gB);
-  }
-  st.nly += nly;
-  T pbar[4] = {g0, g1, -par[1] * gA, -par[1] * gB};
+  T pbar[4];
+  obs_loop<T, NP, NM, NO>(st, par, pbar);
   T thbar[NP + NM];
 #pragma unroll
   for (int q = 0; q < NP + NM; q++) {
     T v = T(0);
+    bool first = true;
 #pragma unroll
-    for (int s = 0; s < 4; s++) v += (cfg.slot_code[s] == q) ? pbar[s] : T(0);
+    for (int s = 0; s < 4; s++) {
+      if constexpr (TR::STATIC) {
+        if (tr_slot<TR>(cfg, s) == q) { v = first ? pbar[s] : v + pbar[s]; first = false; }
+      } else {
+        v += (tr_slot<TR>(cfg, s) == q) ? pbar[s] : T(0);
+      }
+    }
     thbar[q] = v;
   }
 #pragma unroll
   for (int k = 0; k < NM; k++) {
-    const T zb = fma(thbar[NP + k], dth[k], dpz[k] - dlj[k]);
+    const T zb = fma(thbar[NP + k], dth[k], dz[k]);
     st.smu[k] += zb;
 #pragma unroll
     for (int j = 0; j <= k; j++) st.sz[ut(j, k)] = fma(zb, z[j], st.sz[ut(j, k)]);
@@ -415,37 +500,46 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, const StreamArgs<T>& 
     const T zb = thbar[j] * gp[j];
     st.aP[j] += zb;
 #pragma unroll
-    for (int jj = 0; jj <= j; jj++) st.cP[ut(jj, j)] = fma(zb, __ldg(a.zP + (size_t)a.M * jj + m), st.cP[ut(jj, j)]);
+    for (int jj = 0; jj <= j; jj++) st.cP[ut(jj, j)] = fma(zb, zp[jj], st.cP[ut(jj, j)]);
   }
 }
 
 constexpr int STREAM_THREADS = 256;
 
-template <typename T, int NP, int NM, int NO>
-__global__ void __launch_bounds__(STREAM_THREADS) k_stream(const __grid_constant__ Cfg<T> cfg,
-                                                           const __grid_constant__ StreamArgs<T> a) {
+template <class TR, typename T, int NP, int NM, int NO>
+__global__ void __launch_bounds__(STREAM_THREADS, sizeof(T) == 4 ? 2 : 1) k_stream(const __grid_constant__ Cfg<T> cfg,
+                                                              const __grid_constant__ StreamArgs<T> a) {
   constexpr int CH = 16 / sizeof(T);  // elements per 16-byte chunk
   constexpr int MC = 8 * CH;          // draws per stage (one 128-byte row)
   constexpr int NUM = tri(NM), NUP = tri(NP);
   constexpr int NACC = nacc(NP, NM);
   constexpr int NWARP = STREAM_THREADS / 32;
+  constexpr int PD = pd_stride(NP);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* ztile = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (32 * NM * MC);
   double* wacc = reinterpret_cast<double*>(smem_raw + (size_t)NWARP * 32 * NM * MC * sizeof(T)) + warp * NACC;
+  T* spd = reinterpret_cast<T*>(smem_raw + (size_t)NWARP * 32 * NM * MC * sizeof(T) + (size_t)NWARP * NACC * sizeof(double));
+  const int M = a.M;
+  // per-draw global-parameter records: shared memory if they fit, else read from global
+  const T* pdbase = a.pd;
+  if (a.pd_in_smem) {
+    for (int e = threadIdx.x; e < M * PD; e += STREAM_THREADS) spd[e] = a.pd[e];
+    pdbase = spd;
+  }
   if (lane == 0)
     for (int i = 0; i < NACC; i++) wacc[i] = 0.0;
+  __syncthreads();
 
   SiteState<T, NP, NM, NO> st;
-  T cA[NM], cB[NM];
+  T cA[NM], cB[NM], U[NUM];
 #pragma unroll
   for (int k = 0; k < NM; k++) {
     cA[k] = a.ec->coefA[k];
     cB[k] = a.ec->coefB[k];
 #pragma unroll
-    for (int j = 0; j <= k; j++) st.U[ut(j, k)] = a.ec->UM[j][k];
+    for (int j = 0; j <= k; j++) U[ut(j, k)] = a.ec->UM[j][k];
   }
-  const int M = a.M;
   const T wM = T(1) / T(M);
   const bool staged = a.staged != 0;
   const int64_t ntiles = (a.nb + 31) / 32;
@@ -454,22 +548,27 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const __grid_constant
     const bool active = site < a.nb;
     {
       const T* r = a.rec + (tile * 4 * NO) * 32 + lane;
+      constexpr int NOP = SiteState<T, NP, NM, NO>::NOP;
 #pragma unroll
-      for (int o = 0; o < NO; o++) {
-        st.S1[o] = r[(0 * NO + o) * 32];
-        st.S2[o] = r[(1 * NO + o) * 32];
-        st.yo[o] = r[(2 * NO + o) * 32];
-        st.w[o] = r[(3 * NO + o) * 32];
-        st.S12[o] = st.S1[o] * st.S2[o];
+      for (int o = 0; o < NOP; o++) {
+        const bool two = (2 * o + 1 < NO);   // odd n_obs: the last pair is padded with weight 0
+        const int o0 = 2 * o, o1 = two ? 2 * o + 1 : 2 * o;
+        st.S1[o] = mk2(r[(0 * NO + o0) * 32], r[(0 * NO + o1) * 32]);
+        st.S2[o] = mk2(r[(1 * NO + o0) * 32], r[(1 * NO + o1) * 32]);
+        st.nyo[o] = mk2(-r[(2 * NO + o0) * 32], -r[(2 * NO + o1) * 32]);
+        st.w[o] = mk2(r[(3 * NO + o0) * 32], two ? r[(3 * NO + o1) * 32] : T(0));
+        st.S12[o] = pmul(st.S1[o], st.S2[o]);
       }
     }
-    T ls[NM];
+    T ls[NM], sig[NM];
 #pragma unroll
     for (int k = 0; k < NM; k++) {
       st.mu[k] = active ? a.mu[site * NM + k] : T(0);
       ls[k] = fma(cB[k], st.mu[k], cA[k]);
-      st.sig[k] = exp_t(T(0.5) * ls[k]);
+      sig[k] = exp_t(T(0.5) * ls[k]);
       st.smu[k] = T(0);
+#pragma unroll
+      for (int j = 0; j <= k; j++) st.sU[ut(j, k)] = sig[k] * U[ut(j, k)];
     }
 #pragma unroll
     for (int i = 0; i < NUM; i++) st.sz[i] = T(0);
@@ -477,15 +576,18 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const __grid_constant
     for (int i = 0; i < (NP > 0 ? NP : 1); i++) st.aP[i] = T(0);
 #pragma unroll
     for (int i = 0; i < (NP > 0 ? NUP : 1); i++) st.cP[i] = T(0);
-    st.nly = st.prior = st.lj = T(0);
+    st.prior = st.lj = T(0);
+    st.nly2 = mk2(T(0), T(0));
 
     if (staged) {
       const T* gz = a.zMs + (size_t)tile * 32 * NM * M;  // row r of the tile at gz + r*M
-      const int64_t rows_valid = (a.nb - tile * 32 < 32 ? a.nb - tile * 32 : 32) * NM;
+      const int rows_valid = (int)(a.nb - tile * 32 < 32 ? a.nb - tile * 32 : 32) * NM;
       for (int m0 = 0; m0 < M; m0 += MC) {
         const int nch = ((M - m0) < MC ? (M - m0) : MC) / CH;
         __syncwarp();
-        for (int e = lane; e < 32 * NM * 8; e += 32) {
+#pragma unroll
+        for (int e0 = 0; e0 < 32 * NM * 8; e0 += 32) {
+          const int e = e0 + lane;
           const int row = e >> 3, q = e & 7, owner = row / NM;
           if (q < nch && row < rows_valid)
             cp_async16(ztile + row * MC + ((q + owner) & 7) * CH, gz + (size_t)row * M + m0 + q * CH);
@@ -506,12 +608,13 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const __grid_constant
                 zc[k][0] = v.x; zc[k][1] = v.y;
               }
             }
+            const T* pd = pdbase + (size_t)(m0 + q * CH) * PD;
 #pragma unroll
             for (int d = 0; d < CH; d++) {
               T z[NM];
 #pragma unroll
               for (int k = 0; k < NM; k++) z[k] = zc[k][d];
-              do_draw<T, NP, NM, NO>(cfg, a, st, z, m0 + q * CH + d);
+              do_draw<TR, T, NP, NM, NO>(cfg, st, z, pd + d * PD);
             }
           }
         }
@@ -521,7 +624,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const __grid_constant
         T z[NM];
 #pragma unroll
         for (int k = 0; k < NM; k++) z[k] = a.zMs[((size_t)site * NM + k) * M + m];
-        do_draw<T, NP, NM, NO>(cfg, a, st, z, m);
+        do_draw<TR, T, NP, NM, NO>(cfg, st, z, pdbase + (size_t)m * PD);
       }
     }
 
@@ -530,20 +633,19 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const __grid_constant
 #pragma unroll
     for (int i = 0; i < NACC; i++) acc[i] = T(0);
     if (active) {
-      acc[ACC_NLY] = st.nly; acc[ACC_PRIOR] = st.prior; acc[ACC_LJ] = st.lj;
+      acc[ACC_NLY] = st.nly2.x + st.nly2.y; acc[ACC_PRIOR] = st.prior; acc[ACC_LJ] = st.lj;
 #pragma unroll
       for (int k = 0; k < NM; k++) {
-        T sr = T(0);
+        T sr = T(0);                                      // Σ_m ζ̄[k,m]·r[k,m]
 #pragma unroll
-        for (int j = 0; j <= k; j++) sr = fma(st.U[ut(j, k)], st.sz[ut(j, k)], sr);
-        sr *= st.sig[k];                                  // Σ_m ζ̄[k,m]·r[k,m]
+        for (int j = 0; j <= k; j++) sr = fma(st.sU[ut(j, k)], st.sz[ut(j, k)], sr);
         const T lsb = T(0.5) * wM * sr - T(0.5);          // −½ from the entropy
         acc[ACC_LOGSIG] += T(0.5) * ls[k];
         acc[ACC_FIRST_VEC + k] = lsb;
         acc[ACC_FIRST_VEC + NM + k] = lsb * st.mu[k];
         a.mubar[site * NM + k] = fma(wM, st.smu[k], lsb * cB[k]);
 #pragma unroll
-        for (int j = 0; j <= k; j++) acc[ACC_FIRST_VEC + 2 * NM + ut(j, k)] = st.sig[k] * st.sz[ut(j, k)];
+        for (int j = 0; j <= k; j++) acc[ACC_FIRST_VEC + 2 * NM + ut(j, k)] = sig[k] * st.sz[ut(j, k)];
       }
 #pragma unroll
       for (int j = 0; j < NP; j++) acc[ACC_FIRST_VEC + 2 * NM + NUM + j] = st.aP[j];
@@ -562,6 +664,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const __grid_constant
     for (int i = 0; i < NACC; i++) out[i] = wacc[i];
   }
 }
+
 
 // ---------------------------------------------------------------------------------------
 // finalize: one block.  Fixed-order reduction of all partial sums, global-block terms,
@@ -659,12 +762,12 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
       // prior and log-Jacobian of θP, once per evaluation
       double pv_sum = 0, lj_sum = 0;
       for (int m = 0; m < M; m++) {
-        T th, dth, pv, dpz, ljm, dlj;
+        T th, dth, pv, dz, ljm;
         transform_prior<T>(cfg.transP[j], cfg.omit_priors ? HVI_PR_NONE : cfg.prP_kind[j], cfg.prP_a[j], cfg.prP_ib[j],
-                           cfg.clamp_lo, cfg.clamp_hi, zetaP[(size_t)j * M + m], th, dth, pv, dpz, ljm, dlj);
+                           cfg.clamp_lo, cfg.clamp_hi, zetaP[(size_t)j * M + m], th, dth, pv, dz, ljm);
         pv_sum += (double)pv;
         lj_sum += (double)ljm;
-        const double zb = w * ((double)dpz - (double)dlj);
+        const double zb = w * (double)dz;
         aP += zb;
         for (int jj = 0; jj <= j; jj++) CP[jj][j] += zb * (double)zP[m + (size_t)M * jj];
       }
@@ -852,12 +955,14 @@ cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, con
   return cudaSuccess;
 }
 
-template <typename T, int NP, int NM, int NO>
-static cudaError_t launch_stream_inst(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, int* nrows_out,
-                                      int nrows_max) {
+template <class TR, typename T, int NP, int NM, int NO>
+static cudaError_t launch_stream_inst(const Launch& L, const Cfg<T>& cfg, StreamArgs<T> a, int* nrows_out, int nrows_max) {
   constexpr int CH = 16 / sizeof(T), MC = 8 * CH, NWARP = STREAM_THREADS / 32;
-  const size_t smem = (size_t)NWARP * 32 * NM * MC * sizeof(T) + (size_t)NWARP * nacc(NP, NM) * sizeof(double);
-  auto kern = k_stream<T, NP, NM, NO>;
+  const size_t pd_bytes = (size_t)a.M * pd_stride(NP) * sizeof(T);
+  a.pd_in_smem = (NP > 0 && pd_bytes <= 16 * 1024) ? 1 : 0;
+  const size_t smem = (size_t)NWARP * 32 * NM * MC * sizeof(T) + (size_t)NWARP * nacc(NP, NM) * sizeof(double) +
+                      (a.pd_in_smem ? pd_bytes : 0) + 16;
+  auto kern = k_stream<TR, T, NP, NM, NO>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -885,10 +990,37 @@ bool stream_supported(int nP, int nM, int nO) {
   return false;
 }
 
+// compile-time specialisations: (slots, bijectors of θM, priors of θM) of the named problems
+//   DoubleMMCase default (src/DoubleMM/f_doubleMM.jl:161-243): θP=(r0,K2), θM=(r1,K1), Exp, LogNormal
+//   test/test_HybridProblem.jl:32-111: same slots, transM=(identity, Exp), priors (Normal, LogNormal)
+using TraitsDoubleMM = StaTraits<0x2431u, 0x5u, 0xAu>;
+using TraitsDoubleMMNoPrior = StaTraits<0x2431u, 0x5u, 0x0u>;
+using TraitsTestHybridProblem = StaTraits<0x2431u, 0x4u, 0x9u>;
+
+template <typename T>
+static void traits_key(const Cfg<T>& cfg, uint32_t& slots, uint32_t& trm, uint32_t& prm) {
+  slots = trm = prm = 0;
+  for (int s = 0; s < 4; s++) slots |= (uint32_t)(cfg.slot_code[s] + 1) << (4 * s);
+  for (int k = 0; k < cfg.nM; k++) {
+    trm |= (uint32_t)cfg.transM[k] << (2 * k);
+    prm |= (uint32_t)(cfg.omit_priors ? 0 : cfg.prM_kind[k]) << (2 * k);
+  }
+}
+
 template <typename T>
 cudaError_t launch_stream(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, int* nrows_out, int nrows_max) {
+  if (cfg.nP == 2 && cfg.nM == 2 && cfg.nO == 8) {
+    uint32_t slots, trm, prm;
+    traits_key(cfg, slots, trm, prm);
+#define Y(TRAITS) \
+    if (slots == TRAITS::slots && trm == TRAITS::trm && prm == TRAITS::prm) \
+      return launch_stream_inst<TRAITS, T, 2, 2, 8>(L, cfg, a, nrows_out, nrows_max);
+    Y(TraitsDoubleMM) Y(TraitsDoubleMMNoPrior) Y(TraitsTestHybridProblem)
+#undef Y
+  }
 #define X(P, M_, O) \
-  if (cfg.nP == P && cfg.nM == M_ && cfg.nO == O) return launch_stream_inst<T, P, M_, O>(L, cfg, a, nrows_out, nrows_max);
+  if (cfg.nP == P && cfg.nM == M_ && cfg.nO == O) \
+    return launch_stream_inst<DynTraits, T, P, M_, O>(L, cfg, a, nrows_out, nrows_max);
   HVI_STREAM_CASES(X)
 #undef X
   return cudaErrorInvalidConfiguration;
