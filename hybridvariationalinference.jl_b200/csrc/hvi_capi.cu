@@ -36,6 +36,7 @@ struct hvi_plan {
   double* d_part_stream; int max_rows;
   double* d_part_mlp; int max_blk;
   double* d_out;
+  double* d_red;
   void* d_grad;
   double* h_out;  // pinned
   void* h_grad;   // pinned
@@ -96,6 +97,7 @@ static void fill_cfg(const hvi_desc& d, Cfg<T>& c) {
     c.prP_a[i] = (T)d.prior_P[i].a; c.prM_a[i] = (T)d.prior_M[i].a;
     c.prP_ib[i] = c.prP_kind[i] ? (T)(1.0 / d.prior_P[i].b) : T(0);
     c.prM_ib[i] = c.prM_kind[i] ? (T)(1.0 / d.prior_M[i].b) : T(0);
+    c.prM_nab[i] = c.prM_kind[i] ? (T)(-d.prior_M[i].a / d.prior_M[i].b) : T(0);
     c.prP_c0[i] = c.prP_kind[i] ? log(d.prior_P[i].b) + 0.9189385332046727418 : 0.0;
     c.prM_c0[i] = c.prM_kind[i] ? log(d.prior_M[i].b) + 0.9189385332046727418 : 0.0;
     c.scale_a[i] = (T)d.scale_a[i]; c.scale_b[i] = (T)d.scale_b[i];
@@ -109,6 +111,7 @@ static void fill_cfg(const hvi_desc& d, Cfg<T>& c) {
   c.count_globals = d.count_globals;
   if (sizeof(T) == 4) { c.clamp_lo = (T)sqrt(1.17549435082228750797e-38); c.clamp_hi = (T)sqrt(3.40282346638528859812e+38); }
   else { c.clamp_lo = (T)sqrt(2.2250738585072014e-308); c.clamp_hi = (T)sqrt(1.7976931348623157e+308); }
+  c.ln_clamp_lo = (T)log((double)c.clamp_lo); c.ln_clamp_hi = (T)log((double)c.clamp_hi);
   int p = 0;
   c.nL = d.n_layers; c.sum_width = 0; c.sum_out = 0; c.max_width = 0;
   for (int l = 0; l < d.n_layers; l++) {
@@ -201,7 +204,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   p->d_xM = p->d_rec = p->d_mu = p->d_mubar = nullptr;
   p->d_phi = p->d_zP = p->d_zMs = p->d_ec = p->d_pdraw = nullptr;
   p->cap_zP = p->cap_zMs = p->cap_pdraw = 0;
-  p->d_part_stream = p->d_part_mlp = p->d_out = nullptr;
+  p->d_part_stream = p->d_part_mlp = p->d_out = p->d_red = nullptr;
   p->d_grad = nullptr; p->h_out = nullptr; p->h_grad = nullptr;
   p->const_nly = 0; p->anomalies = 0;
   p->profiling = 0; p->n_ev = 0;
@@ -229,6 +232,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   CRE(cudaMalloc(&p->d_part_stream, sizeof(double) * (size_t)p->max_rows * nacc(p->cf.nP, p->cf.nM)));
   CRE(cudaMalloc(&p->d_part_mlp, sizeof(double) * (size_t)p->max_blk * p->cf.nphig));
   CRE(cudaMalloc(&p->d_out, sizeof(double) * (size_t)(nphi + 8)));
+  CRE(cudaMalloc(&p->d_red, sizeof(double) * (size_t)(128 + (p->cf.nphig + 31) / 32 + 2)));
   CRE(cudaMalloc(&p->d_grad, p->es * (size_t)nphi));
   CRE(cudaMallocHost(&p->h_out, sizeof(double) * (size_t)(nphi + 8)));
   CRE(cudaMallocHost(&p->h_grad, p->es * (size_t)nphi));
@@ -242,7 +246,7 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   cudaSetDevice(p->desc.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   void* dev[] = {p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
-                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_grad};
+                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
   if (p->h_grad) cudaFreeHost(p->h_grad);
@@ -407,7 +411,7 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_mubar, p->nb, p->d_part_mlp, &nblk, p->max_blk));
   MARK();
   CU(p, launch_finalize<T>(L, cfg, phi, zP, pdraw, ec, p->d_part_stream, nrows, p->d_part_mlp, nblk, p->const_nly, p->nb,
-                           M, out, grad_T));
+                           M, out, grad_T, p->d_red));
   MARK();
 #undef MARK
   p->n_ev = iev;

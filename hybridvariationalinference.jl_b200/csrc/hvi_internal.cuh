@@ -20,11 +20,13 @@ struct Cfg {
   int prP_kind[MAXP], prM_kind[MAXP];
   T prP_a[MAXP], prP_ib[MAXP];  // prior location, 1/scale
   T prM_a[MAXP], prM_ib[MAXP];
+  T prM_nab[MAXP];                    // −a/b, so that u = fma(x, 1/b, −a/b)
   double prP_c0[MAXP], prM_c0[MAXP];  // log(scale) + log(2π)/2 (0 if no prior)
   int slot_code[4];                   // -1: fixed; j<nP: θP[j]; nP+k: θM[k]
   T slot_fix[4];
   int omit_priors, count_globals;
   T clamp_lo, clamp_hi;               // sqrt(floatmin), sqrt(floatmax) (src/elbo.jl:797-798)
+  T ln_clamp_lo, ln_clamp_hi;         // their logarithms
   int blkP_start[MAXP], rhoP_off[MAXP], blkM_start[MAXP], rhoM_off[MAXP];
   int o_ls2P, o_coef, o_rhoP, o_rhoM, o_muP, nphig, nphi;
   int nL, l_in[MAXL], l_out[MAXL], l_act[MAXL], l_bias[MAXL], woff[MAXL], boff[MAXL];
@@ -89,7 +91,8 @@ cudaError_t launch_stream(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T
 template <typename T>
 cudaError_t launch_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, const T* pdraw,
                             const EvalConsts<T>* ec, const double* part_stream, int nrows, const double* part_mlp,
-                            int nblk, double const_nly, int64_t nb, int M, double* out, T* grad_T);
+                            int nblk, double const_nly, int64_t nb, int M, double* out, T* grad_T,
+                            double* red /*[128 + ceil(nphig/32) + 1] scratch*/);
 template <typename T>
 cudaError_t launch_gen_normal(const Launch& L, T* z, int64_t n_cols, int M, uint64_t seed, int64_t col_offset);
 template <typename T>

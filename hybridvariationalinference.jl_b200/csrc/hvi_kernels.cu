@@ -11,6 +11,7 @@
 //                global-block terms, scatter into the ϕ layout (src/init_hybrid_params.jl:119-124)
 // All file:line citations are relative to /root/reference.
 #include <math.h>
+#include <stdlib.h>
 
 #include "hvi_internal.cuh"
 
@@ -46,6 +47,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
@@ -348,6 +352,348 @@ __global__ void __launch_bounds__(MLP_BS) k_mlp_bwd(const __grid_constant__ Cfg<
 }
 
 // ---------------------------------------------------------------------------------------
+// Register-tiled applicator for the reference's canonical network
+//   n_in → H1 tanh → H2 tanh → n_out logistic (no bias)   (ext/HybridVariationalInferenceSimpleChainsExt.jl:43-52)
+// with every dimension a compile-time constant.  Forward: one thread per site, activations in
+// registers, weights read from shared memory as broadcast LDS.128 (4 outputs per load).
+// Backward: phase A (thread per site) recomputes the forward, back-propagates δ and stores the
+// activation rows [x;1], [h1;1], [h2;1] and the δ rows of the tile's 128 sites in shared
+// memory; phase B forms the weight gradient Σ_sites δ·[a;1]ᵀ as 4×4 register tiles, one or two
+// tiles per lane, 2 LDS.128 per 16 FMA; the four warps split the tile's sites.  Row strides
+// are an odd number of 16-byte units so that the per-site STS.128/LDS.128 are conflict-free.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
+__host__ __device__ constexpr int oddpad(int n) { return (((n + 3) / 4) | 1) * 4; }
+
+template <typename T> struct V4 { T v[4]; };
+__device__ __forceinline__ V4<float> ld4(const float* p) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  return {{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ V4<double> ld4(const double* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  return {{a.x, a.y, b.x, b.y}};
+}
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void st4(double* p, double a, double b, double c, double d) {
+  *reinterpret_cast<double2*>(p) = make_double2(a, b);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
+}
+
+// tanh accurate to ≈1e-6 relative from 2 MUFU + a short odd polynomial near 0
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float ax = fabsf(x), x2 = x * x;
+  const float p = x * fmaf(x2, fmaf(x2, fmaf(x2, -17.0f / 315.0f, 2.0f / 15.0f), -1.0f / 3.0f), 1.0f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.885390081777927f));
+  const float r = copysignf(1.0f - 2.0f * rcp_fast(e + 1.0f), x);
+  return ax < 0.25f ? p : r;
+}
+__device__ __forceinline__ double tanh_fast(double x) { return tanh(x); }
+__device__ __forceinline__ float logistic_fast(float z) { return rcp_fast(1.0f + exp_t(-z)); }
+__device__ __forceinline__ double logistic_fast(double z) { return 1.0 / (1.0 + exp(-z)); }
+
+template <typename T, int NI, int H1, int H2, int NOUT>
+struct Mlp3 {
+  static constexpr int H1P = pad4(H1), H2P = pad4(H2), OP = pad4(NOUT);
+  // padded weights in shared memory: W_l as [i][out padded], biases padded with zeros
+  // (rows padded to a multiple of 4 inputs, zero-filled)
+  static constexpr int oW1 = 0, ob1 = oW1 + pad4(NI) * H1P, oW2 = ob1 + H1P, ob2 = oW2 + pad4(H1) * H2P,
+                       oW3 = ob2 + H2P, nW = oW3 + pad4(H2) * OP;
+  // per-site rows of the backward tile: [x;1] [h1;1] [h2;1] δ1 δ2 δ3
+  static constexpr int sA0 = oddpad(NI + 1), sA1 = oddpad(H1 + 1), sA2 = oddpad(H2 + 1), sD1 = oddpad(H1),
+                       sD2 = oddpad(H2), sD3 = oddpad(NOUT);
+  static constexpr int oA0 = 0, oA1 = oA0 + sA0, oA2 = oA1 + sA1, oD1 = oA2 + sA2, oD2 = oD1 + sD1, oD3 = oD2 + sD2,
+                       ROW = oddpad(oD3 + sD3);   // odd number of 16-byte units between consecutive sites
+  // 4×4 gradient tiles: layer l has ceil(out/4) × ceil((in+1)/4)
+  static constexpr int T1j = H1P / 4, T1i = pad4(NI + 1) / 4, T2j = H2P / 4, T2i = pad4(H1 + 1) / 4, T3j = OP / 4,
+                       T3i = pad4(H2 + 1) / 4;
+  static constexpr int NT1 = T1j * T1i, NT2 = T2j * T2i, NT3 = T3j * T3i, NT = NT1 + NT2 + NT3;
+  static constexpr int TPL = (NT + 31) / 32;   // tiles per lane
+
+  __device__ static void load_weights(const Cfg<T>& cfg, const T* __restrict__ phi, T* __restrict__ sW, int t, int nthr) {
+    for (int e = t; e < nW; e += nthr) sW[e] = T(0);
+    __syncthreads();
+    for (int e = t; e < NI * H1; e += nthr) sW[oW1 + (e / H1) * H1P + e % H1] = phi[cfg.woff[0] + e];  // [i][j]
+    for (int e = t; e < H1; e += nthr) sW[ob1 + e] = phi[cfg.boff[0] + e];
+    for (int e = t; e < H1 * H2; e += nthr) sW[oW2 + (e / H2) * H2P + e % H2] = phi[cfg.woff[1] + e];
+    for (int e = t; e < H2; e += nthr) sW[ob2 + e] = phi[cfg.boff[1] + e];
+    for (int e = t; e < H2 * NOUT; e += nthr) sW[oW3 + (e / NOUT) * OP + e % NOUT] = phi[cfg.woff[2] + e];
+    __syncthreads();
+  }
+
+  template <int NIN, int NOP_, bool BIAS>
+  __device__ __forceinline__ static void dense(const T* __restrict__ W, const T* __restrict__ b, const T* x, T* y) {
+#pragma unroll
+    for (int j4 = 0; j4 < NOP_ / 4; j4++) {
+      if (BIAS) { const V4<T> bb = ld4(b + 4 * j4); y[4 * j4] = bb.v[0]; y[4 * j4 + 1] = bb.v[1]; y[4 * j4 + 2] = bb.v[2]; y[4 * j4 + 3] = bb.v[3]; }
+      else { y[4 * j4] = y[4 * j4 + 1] = y[4 * j4 + 2] = y[4 * j4 + 3] = T(0); }
+    }
+#pragma unroll
+    for (int i = 0; i < NIN; i++) {
+#pragma unroll
+      for (int j4 = 0; j4 < NOP_ / 4; j4++) {
+        const V4<T> w = ld4(W + i * NOP_ + 4 * j4);
+#pragma unroll
+        for (int c = 0; c < 4; c++) y[4 * j4 + c] = fma(w.v[c], x[i], y[4 * j4 + c]);
+      }
+    }
+  }
+
+  // dprev[i] = Σ_j W[i][j]·d[j]
+  template <int NIN, int NOP_>
+  __device__ __forceinline__ static void dense_T(const T* __restrict__ W, const T* d, T* dprev) {
+#pragma unroll
+    for (int i = 0; i < NIN; i++) {
+      T s = T(0);
+#pragma unroll
+      for (int j4 = 0; j4 < NOP_ / 4; j4++) {
+        const V4<T> w = ld4(W + i * NOP_ + 4 * j4);
+#pragma unroll
+        for (int c = 0; c < 4; c++) s = fma(w.v[c], d[4 * j4 + c], s);
+      }
+      dprev[i] = s;
+    }
+  }
+
+  // shared-memory-row variants used by the backward kernel: inputs are read four at a time from
+  // this thread's site row, outputs stay in registers; loops over the inputs are not unrolled, so
+  // the register footprint is the output vector only
+  template <int NIN, int NOP_, bool BIAS>
+  __device__ __forceinline__ static void dense_row(const T* __restrict__ W, const T* __restrict__ b, const T* in_row, T* y) {
+#pragma unroll
+    for (int j4 = 0; j4 < NOP_ / 4; j4++) {
+      if (BIAS) { const V4<T> bb = ld4(b + 4 * j4); y[4 * j4] = bb.v[0]; y[4 * j4 + 1] = bb.v[1]; y[4 * j4 + 2] = bb.v[2]; y[4 * j4 + 3] = bb.v[3]; }
+      else { y[4 * j4] = y[4 * j4 + 1] = y[4 * j4 + 2] = y[4 * j4 + 3] = T(0); }
+    }
+#pragma unroll 1
+    for (int i4 = 0; i4 < pad4(NIN) / 4; i4++) {
+      const V4<T> x4 = ld4(in_row + 4 * i4);
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int j4 = 0; j4 < NOP_ / 4; j4++) {
+          const V4<T> w = ld4(W + (4 * i4 + c) * NOP_ + 4 * j4);
+#pragma unroll
+          for (int cc = 0; cc < 4; cc++) y[4 * j4 + cc] = fma(w.v[cc], x4.v[c], y[4 * j4 + cc]);
+        }
+    }
+  }
+  // δ_prev[i] = (Σ_j W[i][j]·d[j])·(1 − a[i]²), written to the site row (a = tanh activations)
+  template <int NIN, int NOP_>
+  __device__ __forceinline__ static void dense_T_row(const T* __restrict__ W, const T* d, const T* act_row, T* dprev_row) {
+#pragma unroll 1
+    for (int i4 = 0; i4 < pad4(NIN) / 4; i4++) {
+      const V4<T> a4 = ld4(act_row + 4 * i4);
+      T s[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        s[c] = T(0);
+#pragma unroll
+        for (int j4 = 0; j4 < NOP_ / 4; j4++) {
+          const V4<T> w = ld4(W + (4 * i4 + c) * NOP_ + 4 * j4);
+#pragma unroll
+          for (int cc = 0; cc < 4; cc++) s[c] = fma(w.v[cc], d[4 * j4 + cc], s[c]);
+        }
+        s[c] = (4 * i4 + c < NIN) ? s[c] * (T(1) - a4.v[c] * a4.v[c]) : T(0);
+      }
+      st4(dprev_row + 4 * i4, s[0], s[1], s[2], s[3]);
+    }
+  }
+
+  __device__ __forceinline__ static void forward(const T* __restrict__ sW, const T* x, T* h1, T* h2, T* p) {
+    dense<NI, H1P, true>(sW + oW1, sW + ob1, x, h1);
+#pragma unroll
+    for (int j = 0; j < H1P; j++) h1[j] = j < H1 ? tanh_fast(h1[j]) : T(0);
+    asm volatile("" ::: "memory");
+    dense<H1, H2P, true>(sW + oW2, sW + ob2, h1, h2);
+#pragma unroll
+    for (int j = 0; j < H2P; j++) h2[j] = j < H2 ? tanh_fast(h2[j]) : T(0);
+    dense<H2, OP, false>(sW + oW3, nullptr, h2, p);
+#pragma unroll
+    for (int j = 0; j < OP; j++) p[j] = j < NOUT ? logistic_fast(p[j]) : T(0);
+  }
+};
+
+constexpr int MLP3_BS = 128;
+
+template <typename T, int NI, int H1, int H2, int NOUT>
+__global__ void __launch_bounds__(MLP3_BS) k_mlp3_fwd(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi,
+                                                      const T* __restrict__ xM, int64_t nb, T* __restrict__ mu) {
+  using N = Mlp3<T, NI, H1, H2, NOUT>;
+  __shared__ __align__(16) T sW[N::nW];
+  const int t = threadIdx.x;
+  N::load_weights(cfg, phi, sW, t, MLP3_BS);
+  for (int64_t site = (int64_t)blockIdx.x * MLP3_BS + t; site < nb; site += (int64_t)gridDim.x * MLP3_BS) {
+    T x[NI], h1[N::H1P], h2[N::H2P], p[N::OP];
+#pragma unroll
+    for (int i = 0; i < NI; i++) x[i] = i < cfg.nC ? xM[site * cfg.nC + i] : phi[cfg.o_muP + cfg.pbm_covar_idx[i - cfg.nC]];
+    N::forward(sW, x, h1, h2, p);
+#pragma unroll
+    for (int k = 0; k < NOUT; k++)
+      if (k < cfg.nM)
+        mu[site * cfg.nM + k] = (cfg.scale_kind == HVI_SCALE_RANGE) ? p[k] * cfg.scale_b[k] + cfg.scale_a[k]
+                                                                    : cfg.scale_a[k] + cfg.scale_b[k] * ndtri_t(p[k]);
+  }
+}
+
+template <typename T, int NI, int H1, int H2, int NOUT>
+__global__ void __launch_bounds__(MLP3_BS, 3) k_mlp3_bwd(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi,
+                                                      const T* __restrict__ xM, const T* __restrict__ mubar,
+                                                      int64_t nb, double* __restrict__ part) {
+  using N = Mlp3<T, NI, H1, H2, NOUT>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sW = reinterpret_cast<T*>(smem_raw);
+  T* rows = sW + pad4(N::nW);                       // [MLP3_BS][ROW]
+  T* sacc = rows + (size_t)MLP3_BS * N::ROW;        // [4 warps][TPL*32 tiles][16]: gradient tiles between site tiles
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  N::load_weights(cfg, phi, sW, t, MLP3_BS);
+  for (int e = t; e < 4 * N::TPL * 32 * 16; e += MLP3_BS) sacc[e] = T(0);
+  // this lane's gradient tiles: offsets of the δ quad and of the activation quad inside a site row
+  int doff[N::TPL], aoff[N::TPL];
+#pragma unroll
+  for (int q = 0; q < N::TPL; q++) {
+    int tl = lane + 32 * q;
+    if (tl >= N::NT) tl = 0;   // idle slot: recompute tile 0, result discarded
+    if (tl < N::NT1) { doff[q] = N::oD1 + 4 * (tl % N::T1j); aoff[q] = N::oA0 + 4 * (tl / N::T1j); }
+    else if (tl < N::NT1 + N::NT2) { const int u = tl - N::NT1; doff[q] = N::oD2 + 4 * (u % N::T2j); aoff[q] = N::oA1 + 4 * (u / N::T2j); }
+    else { const int u = tl - N::NT1 - N::NT2; doff[q] = N::oD3 + 4 * (u % N::T3j); aoff[q] = N::oA2 + 4 * (u / N::T3j); }
+  }
+  const int64_t ntiles = (nb + MLP3_BS - 1) / MLP3_BS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t site = tile * MLP3_BS + t;
+    const bool active = site < nb;
+    {  // phase A: this thread's site; all vectors live in the site row r
+      T* r = rows + (size_t)t * N::ROW;
+      {
+        T x[pad4(NI + 1)];
+#pragma unroll
+        for (int i = 0; i < pad4(NI + 1); i++) x[i] = T(0);
+#pragma unroll
+        for (int i = 0; i < NI; i++)
+          x[i] = !active ? T(0) : i < cfg.nC ? xM[site * cfg.nC + i] : phi[cfg.o_muP + cfg.pbm_covar_idx[i - cfg.nC]];
+#pragma unroll
+        for (int i = 0; i < pad4(NI + 1); i += 4) st4(r + N::oA0 + i, x[i], x[i + 1], x[i + 2], x[i + 3]);
+      }
+      {
+        T h[pad4(H1 + 1)];
+#pragma unroll
+        for (int i = N::H1P; i < pad4(H1 + 1); i++) h[i] = T(0);
+        N::template dense_row<NI, N::H1P, true>(sW + N::oW1, sW + N::ob1, r + N::oA0, h);
+#pragma unroll
+        for (int j = 0; j < N::H1P; j++) h[j] = j < H1 ? tanh_fast(h[j]) : T(0);
+#pragma unroll
+        for (int i = 0; i < pad4(H1 + 1); i += 4) st4(r + N::oA1 + i, h[i], h[i + 1], h[i + 2], h[i + 3]);
+      }
+      {
+        T h[pad4(H2 + 1)];
+#pragma unroll
+        for (int i = N::H2P; i < pad4(H2 + 1); i++) h[i] = T(0);
+        N::template dense_row<H1, N::H2P, true>(sW + N::oW2, sW + N::ob2, r + N::oA1, h);
+#pragma unroll
+        for (int j = 0; j < N::H2P; j++) h[j] = j < H2 ? tanh_fast(h[j]) : T(0);
+#pragma unroll
+        for (int i = 0; i < pad4(H2 + 1); i += 4) st4(r + N::oA2 + i, h[i], h[i + 1], h[i + 2], h[i + 3]);
+      }
+      T d3[N::OP];
+      {
+        T p[N::OP];
+        N::template dense_row<H2, N::OP, false>(sW + N::oW3, nullptr, r + N::oA2, p);
+#pragma unroll
+        for (int k = 0; k < N::OP; k++) {
+          T d = T(0);
+          if (k < NOUT && k < cfg.nM && active) {
+            const T pk = logistic_fast(p[k]);
+            const T mb = mubar[site * cfg.nM + k];
+            if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb * cfg.scale_b[k];
+            else { const T q = ndtri_t(pk); d = mb * cfg.scale_b[k] * T(2.50662827463100050242) * exp_t(T(0.5) * q * q); }
+            d *= pk * (T(1) - pk);
+          }
+          d3[k] = d;
+        }
+#pragma unroll
+        for (int i = 0; i < N::OP; i += 4) st4(r + N::oD3 + i, d3[i], d3[i + 1], d3[i + 2], d3[i + 3]);
+      }
+      // δ2 = (W3ᵀ δ3)·(1 − h2²) → row; δ1 = (W2ᵀ δ2)·(1 − h1²) → row
+      N::template dense_T_row<H2, N::OP>(sW + N::oW3, d3, r + N::oA2, r + N::oD2);
+      {
+        T d2[N::H2P];
+#pragma unroll
+        for (int i4 = 0; i4 < N::H2P / 4; i4++) {
+          const V4<T> v = ld4(r + N::oD2 + 4 * i4);
+#pragma unroll
+          for (int c = 0; c < 4; c++) d2[4 * i4 + c] = v.v[c];
+        }
+        N::template dense_T_row<H1, N::H2P>(sW + N::oW2, d2, r + N::oA1, r + N::oD1);
+      }
+      // the constant 1 that multiplies the bias
+      r[N::oA0 + NI] = T(1); r[N::oA1 + H1] = T(1); r[N::oA2 + H2] = T(1);
+    }
+    __syncthreads();
+    // phase B: this warp's 32 sites of the tile
+    {
+      T acc[N::TPL][16];
+#pragma unroll
+      for (int q = 0; q < N::TPL; q++) {
+        const T* sa = sacc + ((size_t)(warp * N::TPL + q) * 32 + lane) * 16;
+#pragma unroll
+        for (int e4 = 0; e4 < 4; e4++) {
+          const V4<T> v = ld4(sa + 4 * e4);
+#pragma unroll
+          for (int c = 0; c < 4; c++) acc[q][4 * e4 + c] = v.v[c];
+        }
+      }
+#pragma unroll 4
+      for (int s = 0; s < 32; s++) {
+        const T* r = rows + (size_t)(warp * 32 + s) * N::ROW;
+#pragma unroll
+        for (int q = 0; q < N::TPL; q++) {
+          const V4<T> d = ld4(r + doff[q]), a = ld4(r + aoff[q]);
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) acc[q][4 * jj + ii] = fma(d.v[jj], a.v[ii], acc[q][4 * jj + ii]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < N::TPL; q++) {
+        T* sa = sacc + ((size_t)(warp * N::TPL + q) * 32 + lane) * 16;
+#pragma unroll
+        for (int e4 = 0; e4 < 4; e4++) st4(sa + 4 * e4, acc[q][4 * e4], acc[q][4 * e4 + 1], acc[q][4 * e4 + 2], acc[q][4 * e4 + 3]);
+      }
+    }
+    __syncthreads();
+  }
+  // block reduction over the 4 warps (fixed order), then scatter to the layout of ϕg
+  double* out = part + (size_t)blockIdx.x * cfg.nphig;
+  for (int e = t; e < N::NT * 16; e += MLP3_BS) {
+    const int tl = e / 16, jj = (e % 16) / 4, ii = e % 4;
+    double s = 0;
+    for (int w = 0; w < MLP3_BS / 32; w++)
+      s += (double)sacc[((size_t)(w * N::TPL + tl / 32) * 32 + (tl % 32)) * 16 + (e % 16)];
+    int l, j, i, nin, nout;
+    if (tl < N::NT1) { l = 0; j = 4 * (tl % N::T1j) + jj; i = 4 * (tl / N::T1j) + ii; nin = NI; nout = H1; }
+    else if (tl < N::NT1 + N::NT2) { const int u = tl - N::NT1; l = 1; j = 4 * (u % N::T2j) + jj; i = 4 * (u / N::T2j) + ii; nin = H1; nout = H2; }
+    else { const int u = tl - N::NT1 - N::NT2; l = 2; j = 4 * (u % N::T3j) + jj; i = 4 * (u / N::T3j) + ii; nin = H2; nout = NOUT; }
+    if (j < nout) {
+      if (i < nin) out[cfg.woff[l] + i * nout + j] = s;
+      else if (i == nin && cfg.l_bias[l]) out[cfg.boff[l] + j] = s;
+    }
+  }
+}
+
+#define HVI_MLP3_CASES(X) X(5, 20, 20, 2) X(6, 24, 24, 2)
+
+template <typename T>
+static bool mlp3_match(const Cfg<T>& c, int ni, int h1, int h2, int no) {
+  return c.nL == 3 && c.l_in[0] == ni && c.l_out[0] == h1 && c.l_out[1] == h2 && c.l_out[2] == no &&
+         c.l_act[0] == HVI_ACT_TANH && c.l_act[1] == HVI_ACT_TANH && c.l_act[2] == HVI_ACT_LOGISTIC && c.l_bias[0] &&
+         c.l_bias[1] && !c.l_bias[2];
+}
+
+// ---------------------------------------------------------------------------------------
 // The fused streaming kernel.  One thread owns one site for all draws; a warp owns a tile of
 // 32 consecutive sites.  The tile's draws ξ (32·NM rows of M values, contiguous in HBM) are
 // staged through warp-private shared memory with coalesced 16-byte cp.async and read back
@@ -388,6 +734,18 @@ __device__ __forceinline__ int tr_priorM(const Cfg<T>& cfg, int k) {
   else return cfg.omit_priors ? HVI_PR_NONE : cfg.prM_kind[k];
 }
 
+// all θM columns are Exp-transformed with LogNormal priors (known at compile time)
+template <class TR, int NM>
+__host__ __device__ constexpr bool all_exp_ln() {
+  if constexpr (TR::STATIC) {
+    for (int k = 0; k < NM; k++)
+      if (((TR::trm >> (2 * k)) & 3u) != HVI_TR_EXP || ((TR::prm >> (2 * k)) & 3u) != HVI_PR_LOGNORMAL) return false;
+    return true;
+  } else {
+    return false;
+  }
+}
+
 // per-draw block of the global parameters, one record per draw: θP[NP], dθP/dζP[NP], zP[NP]
 template <typename T, int NP, int NM, int NO>
 struct SiteState {
@@ -398,7 +756,8 @@ struct SiteState {
   T sU[tri(NM)];                 // σ[k]·U[j,k]
   T smu[NM], sz[tri(NM)];        // Σ_m ζ̄[k],  Σ_m ζ̄[k]·z[j]
   T aP[NP > 0 ? NP : 1], cP[NP > 0 ? tri(NP) : 1];
-  T prior, lj;
+  T prior, lj;                   // Σ of the generic prior terms / of all log-Jacobian terms
+  T u2, ljln;                    // Exp+LogNormal columns: Σ u² and Σ ζ  (prior = ζ + u²/2 when unclamped)
 };
 
 // f_doubleMM + logden_normal + adjoint w.r.t. (r0, r1, K1, K2), all observations of one site
@@ -444,11 +803,29 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, 
     T zeta = st.mu[k];
 #pragma unroll
     for (int j = 0; j <= k; j++) zeta = fma(st.sU[ut(j, k)], z[j], zeta);
-    T pv, lj;
-    transform_prior<T>(tr_transM<TR>(cfg, k), tr_priorM<TR>(cfg, k), cfg.prM_a[k], cfg.prM_ib[k], cfg.clamp_lo,
-                       cfg.clamp_hi, zeta, th[k], dth[k], pv, dz[k], lj);
-    st.prior += pv;
-    st.lj += lj;
+    const int trk = tr_transM<TR>(cfg, k), pkk = tr_priorM<TR>(cfg, k);
+    if (trk == HVI_TR_EXP && pkk == HVI_PR_LOGNORMAL) {
+      // θ = exp(ζ) with a LogNormal prior: −logpdf = ζ + ½u² + const, u = (ζ − μ)/σ; minus the
+      // log-Jacobian ζ the ζ's cancel in the gradient: d/dζ = u/σ
+      // the clamp θ ∈ [√floatmin, √floatmax] (src/elbo.jl:797-798) is applied to ζ before the
+      // exponential (same θ, no branch, no logarithm): ζc = clamp(ζ, ln lo, ln hi)
+      const T zc = fmax(cfg.ln_clamp_lo, fmin(cfg.ln_clamp_hi, zeta));
+      th[k] = exp_t(zc);
+      const bool uncl = (zc == zeta);
+      if (!uncl) st.prior += zc - zeta;   // log θ = ζc when clamped; predicated, almost never taken
+      const T u = fma(zc, cfg.prM_ib[k], cfg.prM_nab[k]);
+      st.u2 = fma(u, u, st.u2);
+      st.lj += zeta;
+      if constexpr (!all_exp_ln<TR, NM>()) st.ljln += zeta;
+      dth[k] = uncl ? th[k] : T(0);
+      dz[k] = uncl ? u * cfg.prM_ib[k] : T(-1);
+    } else {
+      T pv, lj;
+      transform_prior<T>(trk, pkk, cfg.prM_a[k], cfg.prM_ib[k], cfg.clamp_lo, cfg.clamp_hi, zeta, th[k], dth[k], pv,
+                         dz[k], lj);
+      st.prior += pv;
+      st.lj += lj;
+    }
   }
   T thp[NP > 0 ? NP : 1], gp[NP > 0 ? NP : 1], zp[NP > 0 ? NP : 1];
   if constexpr (NP == 2 && sizeof(T) == 4) {
@@ -504,11 +881,11 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, 
   }
 }
 
-constexpr int STREAM_THREADS = 256;
+constexpr int STREAM_THREADS_MAX = 256;
 
-template <class TR, typename T, int NP, int NM, int NO>
-__global__ void __launch_bounds__(STREAM_THREADS, sizeof(T) == 4 ? 2 : 1) k_stream(const __grid_constant__ Cfg<T> cfg,
-                                                              const __grid_constant__ StreamArgs<T> a) {
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB>
+__global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_constant__ Cfg<T> cfg,
+                                                                 const __grid_constant__ StreamArgs<T> a) {
   constexpr int CH = 16 / sizeof(T);  // elements per 16-byte chunk
   constexpr int MC = 8 * CH;          // draws per stage (one 128-byte row)
   constexpr int NUM = tri(NM), NUP = tri(NP);
@@ -576,30 +953,44 @@ __global__ void __launch_bounds__(STREAM_THREADS, sizeof(T) == 4 ? 2 : 1) k_stre
     for (int i = 0; i < (NP > 0 ? NP : 1); i++) st.aP[i] = T(0);
 #pragma unroll
     for (int i = 0; i < (NP > 0 ? NUP : 1); i++) st.cP[i] = T(0);
-    st.prior = st.lj = T(0);
+    st.prior = st.lj = st.u2 = st.ljln = T(0);
     st.nly2 = mk2(T(0), T(0));
 
     if (staged) {
+      // two half-row stages (MCS draws each) in flight: the next stage's cp.async is issued before
+      // the current one is consumed
+      constexpr int MCS = MC / 2, QS = 4;
       const T* gz = a.zMs + (size_t)tile * 32 * NM * M;  // row r of the tile at gz + r*M
       const int rows_valid = (int)(a.nb - tile * 32 < 32 ? a.nb - tile * 32 : 32) * NM;
-      for (int m0 = 0; m0 < M; m0 += MC) {
-        const int nch = ((M - m0) < MC ? (M - m0) : MC) / CH;
-        __syncwarp();
+      const int nst = (M + MCS - 1) / MCS;
+      auto issue = [&](int st_) {
+        const int m0 = st_ * MCS;
+        const int nch = ((M - m0) < MCS ? (M - m0) : MCS) / CH;
+        T* buf = ztile + (st_ & 1) * (32 * NM * MCS);
 #pragma unroll
-        for (int e0 = 0; e0 < 32 * NM * 8; e0 += 32) {
+        for (int e0 = 0; e0 < 32 * NM * QS; e0 += 32) {
           const int e = e0 + lane;
-          const int row = e >> 3, q = e & 7, owner = row / NM;
+          const int row = e >> 2, q = e & 3, owner = row / NM;
           if (q < nch && row < rows_valid)
-            cp_async16(ztile + row * MC + ((q + owner) & 7) * CH, gz + (size_t)row * M + m0 + q * CH);
+            cp_async16(buf + row * MCS + ((q + owner) & 3) * CH, gz + (size_t)row * M + m0 + q * CH);
         }
-        cp_async_wait_all();
+        cp_async_commit();
+      };
+      __syncwarp();
+      issue(0);
+      for (int st_ = 0; st_ < nst; st_++) {
+        if (st_ + 1 < nst) { issue(st_ + 1); cp_async_wait_group<1>(); }
+        else cp_async_wait_group<0>();
         __syncwarp();
+        const int m0 = st_ * MCS;
+        const int nch = ((M - m0) < MCS ? (M - m0) : MCS) / CH;
+        const T* buf = ztile + (st_ & 1) * (32 * NM * MCS);
         if (active) {
           for (int q = 0; q < nch; q++) {
             T zc[NM][CH];
 #pragma unroll
             for (int k = 0; k < NM; k++) {
-              const T* src = ztile + (lane * NM + k) * MC + ((q + lane) & 7) * CH;
+              const T* src = buf + (lane * NM + k) * MCS + ((q + lane) & 3) * CH;
               if constexpr (sizeof(T) == 4) {
                 const float4 v = *reinterpret_cast<const float4*>(src);
                 zc[k][0] = v.x; zc[k][1] = v.y; zc[k][2] = v.z; zc[k][3] = v.w;
@@ -618,6 +1009,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, sizeof(T) == 4 ? 2 : 1) k_stre
             }
           }
         }
+        __syncwarp();
       }
     } else if (active) {
       for (int m = 0; m < M; m++) {
@@ -633,7 +1025,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, sizeof(T) == 4 ? 2 : 1) k_stre
 #pragma unroll
     for (int i = 0; i < NACC; i++) acc[i] = T(0);
     if (active) {
-      acc[ACC_NLY] = st.nly2.x + st.nly2.y; acc[ACC_PRIOR] = st.prior; acc[ACC_LJ] = st.lj;
+      acc[ACC_NLY] = st.nly2.x + st.nly2.y; acc[ACC_LJ] = st.lj;
+      acc[ACC_PRIOR] = st.prior + T(0.5) * st.u2 + (all_exp_ln<TR, NM>() ? st.lj : st.ljln);
 #pragma unroll
       for (int k = 0; k < NM; k++) {
         T sr = T(0);                                      // Σ_m ζ̄[k,m]·r[k,m]
@@ -658,10 +1051,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, sizeof(T) == 4 ? 2 : 1) k_stre
       if (lane == 0) wacc[i] += (double)v;
     }
   }
-  __syncwarp();
-  if (lane == 0) {
-    double* out = a.partials + ((size_t)blockIdx.x * NWARP + warp) * NACC;
-    for (int i = 0; i < NACC; i++) out[i] = wacc[i];
+  // one row of partial sums per block: the warps' double accumulators added in warp order
+  __syncthreads();
+  {
+    const double* w0 = reinterpret_cast<const double*>(smem_raw + (size_t)NWARP * 32 * NM * MC * sizeof(T));
+    for (int i = threadIdx.x; i < NACC; i += STREAM_THREADS) {
+      double s = 0.0;
+      for (int w = 0; w < NWARP; w++) s += w0[w * NACC + i];
+      a.partials[(size_t)blockIdx.x * NACC + i] = s;
+    }
   }
 }
 
@@ -698,104 +1096,171 @@ __device__ void build_U_adj(int n, const int* blk_start, const int* rho_off, con
   }
 }
 
+// stage 1 of the reduction: many blocks, coalesced, fixed summation order.
+//   blocks [0, gridDim.x−1): 32 entries of ∇ϕg each, 8 row groups per entry
+//   last block            : the streaming kernel's per-warp partial sums, 32 columns at a time
+// red[0..NACC) = column sums; red[128 + b] = number of non-finite entries seen by block b
+constexpr int RED_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) k_reduce(int nphig, const double* __restrict__ part_mlp, int nblk,
+                                                        const double* __restrict__ part_stream, int nrows, int NACC,
+                                                        double* __restrict__ out, T* __restrict__ grad_T,
+                                                        double* __restrict__ red) {
+  __shared__ double sm[8][33];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  if ((int)blockIdx.x < (int)gridDim.x - 1) {
+    const int e = blockIdx.x * 32 + c;
+    double s0 = 0, s1 = 0;
+    if (e < nphig) {
+      int r = g;
+      for (; r + 8 < nblk; r += 16) {
+        s0 += part_mlp[(size_t)r * nphig + e];
+        s1 += part_mlp[(size_t)(r + 8) * nphig + e];
+      }
+      if (r < nblk) s0 += part_mlp[(size_t)r * nphig + e];
+    }
+    sm[g][c] = s0 + s1;
+    __syncthreads();
+    if (g == 0) {
+      double s = 0, bad = 0;
+      for (int gg = 0; gg < 8; gg++) s += sm[gg][c];
+      if (e < nphig) {
+        out[e] = s;
+        if (grad_T) grad_T[e] = (T)s;
+        bad = isfinite(s) ? 0.0 : 1.0;
+      }
+      bad = warp_sum(bad);
+      if (c == 0) red[128 + blockIdx.x] = bad;
+    }
+  } else {
+    for (int a0 = 0; a0 < NACC; a0 += 32) {
+      const int a = a0 + c;
+      double s0 = 0, s1 = 0;
+      if (a < NACC) {
+        int r = g;
+        for (; r + 8 < nrows; r += 16) {
+          s0 += part_stream[(size_t)r * NACC + a];
+          s1 += part_stream[(size_t)(r + 8) * NACC + a];
+        }
+        if (r < nrows) s0 += part_stream[(size_t)r * NACC + a];
+      }
+      sm[g][c] = s0 + s1;
+      __syncthreads();
+      if (g == 0 && a < NACC) {
+        double s = 0;
+        for (int gg = 0; gg < 8; gg++) s += sm[gg][c];
+        red[a] = s;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) red[128 + blockIdx.x] = 0.0;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant__ Cfg<T> cfg,
                                                           const T* __restrict__ phi, const T* __restrict__ zP,
                                                           const T* __restrict__ pdraw,
                                                           const EvalConsts<T>* __restrict__ ecp,
-                                                          const double* __restrict__ part_stream, int nrows,
-                                                          const double* __restrict__ part_mlp, int nblk,
+                                                          const double* __restrict__ red, int nred_blocks,
                                                           double const_nly, int64_t nb, int M,
                                                           double* __restrict__ out, T* __restrict__ grad_T) {
   __shared__ double sred[FIN_THREADS];
   __shared__ double sacc[128];
+  __shared__ double sq[8 * MAXP + 2 * MAXP * MAXP + 16];   // ∇ϕq then the 8 trailing scalars
   const int t = threadIdx.x;
   const int nP = cfg.nP, nM = cfg.nM;
   const int NACC = nacc(nP, nM);
-  for (int e = t; e < cfg.nphi + 8; e += FIN_THREADS) out[e] = 0.0;
-  // ∇ϕg: sum the per-block partials in block order
-  for (int e = t; e < cfg.nphig; e += FIN_THREADS) {
-    double s = 0;
-    for (int b = 0; b < nblk; b++) s += part_mlp[(size_t)b * cfg.nphig + e];
-    out[e] = s;
-  }
-  for (int a = 0; a < NACC; a++) {
-    double s = 0;
-    for (int r = t; r < nrows; r += FIN_THREADS) s += part_stream[(size_t)r * NACC + a];
-    s = block_sum_fixed(s, sred);
-    if (t == 0) sacc[a] = s;
+  const int nq = cfg.nphi - cfg.nphig;
+  double bad = 0.0;
+  for (int e = t; e < nred_blocks; e += FIN_THREADS) bad += red[128 + e];
+  for (int e = t; e < NACC; e += FIN_THREADS) sacc[e] = red[e];
+  for (int e = t; e < nq + 8; e += FIN_THREADS) sq[e] = 0.0;
+  // prior and log-Jacobian of θP and their cotangents, once per evaluation: the
+  // draws are spread over the threads, each sum is a fixed-shape tree
+  __shared__ double sPg[MAXP][3 + MAXP];   // per j: Σ pv, Σ lj, Σ zb, Σ zb·zP[m, jj]
+  {
+    const T* zetaP_ = pdraw + (size_t)nP * M;
+    for (int j = 0; j < nP; j++) {
+      double v[3 + MAXP];
+      for (int i = 0; i < 3 + MAXP; i++) v[i] = 0.0;
+      if (cfg.count_globals) {
+        for (int m = t; m < M; m += FIN_THREADS) {
+          T th, dth, pv, dz, ljm;
+          transform_prior<T>(cfg.transP[j], cfg.omit_priors ? HVI_PR_NONE : cfg.prP_kind[j], cfg.prP_a[j],
+                             cfg.prP_ib[j], cfg.clamp_lo, cfg.clamp_hi, zetaP_[(size_t)j * M + m], th, dth, pv, dz, ljm);
+          v[0] += (double)pv; v[1] += (double)ljm; v[2] += (double)dz;
+          for (int jj = 0; jj <= j; jj++) v[3 + jj] += (double)dz * (double)zP[m + (size_t)M * jj];
+        }
+      }
+      for (int i = 0; i < 3 + j + 1; i++) {
+        const double r = block_sum_fixed(v[i], sred);
+        if (t == 0) sPg[j][i] = r;
+      }
+    }
   }
   __syncthreads();
-  if (t != 0) return;
-  const EvalConsts<T>& ec = *ecp;
-  const double w = 1.0 / (double)M;
-  const int NUM = tri(nM);
-  const double* abar = sacc + ACC_FIRST_VEC;
-  const double* bbar = abar + nM;
-  const double* cU = bbar + nM;
-  const double* aPs = cU + NUM;
-  const double* cPs = aPs + nP;
-  double* G = out;
-  double nLy = 0.5 * w * sacc[ACC_NLY] + const_nly;
-  double nlp = w * sacc[ACC_PRIOR];
-  double lj = w * sacc[ACC_LJ];
-  double logsig = sacc[ACC_LOGSIG];
-  if (!cfg.omit_priors)
-    for (int k = 0; k < nM; k++) nlp += (double)nb * cfg.prM_c0[k];
-  // coefficients of log σ²
-  for (int k = 0; k < nM; k++) { G[cfg.o_coef + 2 * k] = abar[k]; G[cfg.o_coef + 2 * k + 1] = bbar[k]; }
-  // M block: Ū = w·cU (columns restricted to their block) → ρ̄sM
-  double Ubar[MAXP][MAXP];
-  for (int k = 0; k < nM; k++)
-    for (int j = 0; j <= k; j++) Ubar[j][k] = w * cU[k * (k + 1) / 2 + j];
-  build_U_adj<T>(nM, cfg.blkM_start, cfg.rhoM_off, ec.UM, ec.nrmM, Ubar, G + cfg.o_rhoM);
-  // global block
-  const T* rP = pdraw;
-  const T* zetaP = pdraw + (size_t)nP * M;
-  const T* thP = pdraw + (size_t)2 * nP * M;
-  const T* gP = pdraw + (size_t)3 * nP * M;
-  double CP[MAXP][MAXP];
-  for (int j = 0; j < nP; j++) {
-    double aP = w * aPs[j];
-    for (int jj = 0; jj <= j; jj++) CP[jj][j] = w * cPs[j * (j + 1) / 2 + jj];
-    if (cfg.count_globals) {
-      // prior and log-Jacobian of θP, once per evaluation
-      double pv_sum = 0, lj_sum = 0;
-      for (int m = 0; m < M; m++) {
-        T th, dth, pv, dz, ljm;
-        transform_prior<T>(cfg.transP[j], cfg.omit_priors ? HVI_PR_NONE : cfg.prP_kind[j], cfg.prP_a[j], cfg.prP_ib[j],
-                           cfg.clamp_lo, cfg.clamp_hi, zetaP[(size_t)j * M + m], th, dth, pv, dz, ljm);
-        pv_sum += (double)pv;
-        lj_sum += (double)ljm;
-        const double zb = w * (double)dz;
-        aP += zb;
-        for (int jj = 0; jj <= j; jj++) CP[jj][j] += zb * (double)zP[m + (size_t)M * jj];
+  if (t == 0) {
+    const EvalConsts<T>& ec = *ecp;
+    const double w = 1.0 / (double)M;
+    const int NUM = tri(nM);
+    const double* abar = sacc + ACC_FIRST_VEC;
+    const double* bbar = abar + nM;
+    const double* cU = bbar + nM;
+    const double* aPs = cU + NUM;
+    const double* cPs = aPs + nP;
+    double* G = sq - cfg.nphig;   // G[o] for o >= nphig
+    double nLy = 0.5 * w * sacc[ACC_NLY] + const_nly;
+    double nlp = w * sacc[ACC_PRIOR];
+    double lj = w * sacc[ACC_LJ];
+    double logsig = sacc[ACC_LOGSIG];
+    if (!cfg.omit_priors)
+      for (int k = 0; k < nM; k++) nlp += (double)nb * cfg.prM_c0[k];
+    // coefficients of log σ²
+    for (int k = 0; k < nM; k++) { G[cfg.o_coef + 2 * k] = abar[k]; G[cfg.o_coef + 2 * k + 1] = bbar[k]; }
+    // M block: Ū = w·cU (columns restricted to their block) → ρ̄sM
+    double Ubar[MAXP][MAXP];
+    for (int k = 0; k < nM; k++)
+      for (int j = 0; j <= k; j++) Ubar[j][k] = w * cU[k * (k + 1) / 2 + j];
+    build_U_adj<T>(nM, cfg.blkM_start, cfg.rhoM_off, ec.UM, ec.nrmM, Ubar, G + cfg.o_rhoM);
+    // global block
+    double CP[MAXP][MAXP];
+    for (int j = 0; j < nP; j++) {
+      double aP = w * aPs[j];
+      for (int jj = 0; jj <= j; jj++) CP[jj][j] = w * cPs[j * (j + 1) / 2 + jj];
+      if (cfg.count_globals) {
+        aP += w * sPg[j][2];
+        for (int jj = 0; jj <= j; jj++) CP[jj][j] += w * sPg[j][3 + jj];
+        nlp += w * sPg[j][0] + (cfg.omit_priors ? 0.0 : cfg.prP_c0[j]);
+        lj += w * sPg[j][1];
+        logsig += 0.5 * (double)phi[cfg.o_ls2P + j];
       }
-      nlp += w * pv_sum + (cfg.omit_priors ? 0.0 : cfg.prP_c0[j]);
-      lj += w * lj_sum;
-      logsig += 0.5 * (double)phi[cfg.o_ls2P + j];
+      G[cfg.o_muP + j] += aP;
+      // Σ_m ζ̄P[j,m]·rP[j,m] = σP[j] Σ_{jj} UP[jj][j]·CP[jj][j]
+      double sr = 0;
+      for (int jj = cfg.blkP_start[j]; jj <= j; jj++) sr += (double)ec.UP[jj][j] * CP[jj][j];
+      sr *= (double)ec.sigP[j];
+      G[cfg.o_ls2P + j] = 0.5 * sr - (cfg.count_globals ? 0.5 : 0.0);
+      for (int jj = 0; jj <= j; jj++) Ubar[jj][j] = (double)ec.sigP[j] * CP[jj][j];
     }
-    G[cfg.o_muP + j] += aP;
-    // Σ_m ζ̄P[j,m]·rP[j,m] = σP[j] Σ_{jj} UP[jj][j]·CP[jj][j]
-    double sr = 0;
-    for (int jj = cfg.blkP_start[j]; jj <= j; jj++) sr += (double)ec.UP[jj][j] * CP[jj][j];
-    sr *= (double)ec.sigP[j];
-    G[cfg.o_ls2P + j] = 0.5 * sr - (cfg.count_globals ? 0.5 : 0.0);
-    for (int jj = 0; jj <= j; jj++) Ubar[jj][j] = (double)ec.sigP[j] * CP[jj][j];
+    build_U_adj<T>(nP, cfg.blkP_start, cfg.rhoP_off, ec.UP, ec.nrmP, Ubar, G + cfg.o_rhoP);
+    const double Kdim = (double)nM * (double)nb + (cfg.count_globals ? nP : 0);
+    const double ent = 0.5 * Kdim * 2.8378770664093454836 + logsig;   // (K·log(2πe) + 2Σlog σ)/2, logden_normal.jl:74
+    const double nlj = -lj;
+    double* C = sq + nq;
+    C[0] = nLy + nlp + nlj; C[1] = ent; C[2] = 0.0; C[3] = nLy; C[4] = nlp; C[5] = nlj;
+    C[6] = C[0] - C[1] + C[2];
   }
-  build_U_adj<T>(nP, cfg.blkP_start, cfg.rhoP_off, ec.UP, ec.nrmP, Ubar, G + cfg.o_rhoP);
-  (void)rP; (void)thP; (void)gP;
-  const double Kdim = (double)nM * (double)nb + (cfg.count_globals ? nP : 0);
-  const double ent = 0.5 * Kdim * 2.8378770664093454836 + logsig;   // (K·log(2πe) + 2Σlog σ)/2, logden_normal.jl:74
-  const double nlj = -lj;
-  double* C = out + cfg.nphi;
-  C[0] = nLy + nlp + nlj; C[1] = ent; C[2] = 0.0; C[3] = nLy; C[4] = nlp; C[5] = nlj;
-  C[6] = C[0] - C[1] + C[2];
-  double bad = 0;
-  for (int e = 0; e < cfg.nphi + 7; e++) bad += isfinite(out[e]) ? 0.0 : 1.0;
-  C[7] = bad;
-  if (grad_T)
-    for (int e = 0; e < cfg.nphi; e++) grad_T[e] = (T)out[e];
+  __syncthreads();
+  for (int e = t; e < nq + 7; e += FIN_THREADS) {
+    const double v = sq[e];
+    out[cfg.nphig + e] = v;
+    if (grad_T && e < nq) grad_T[cfg.nphig + e] = (T)v;
+    bad += isfinite(v) ? 0.0 : 1.0;
+  }
+  bad = block_sum_fixed(bad, sred);
+  if (t == 0) out[cfg.nphi + 7] = bad;
 }
 
 // gradient entries of ϕg are written by many threads above; convert them after the block is done
@@ -891,8 +1356,8 @@ __global__ void __launch_bounds__(256) k_generate_zeta(const __grid_constant__ C
     if (L.counter) ++*L.counter;                   \
   } while (0)
 
-int stream_max_rows(int sm_count) { return sm_count * 8 * (STREAM_THREADS / 32); }
-int mlp_bwd_max_blocks(int sm_count) { return sm_count * 4; }
+int stream_max_rows(int sm_count) { return sm_count * 8 * (STREAM_THREADS_MAX / 32); }
+int mlp_bwd_max_blocks(int sm_count) { return sm_count * 2; }
 
 template <typename T>
 cudaError_t launch_preprocess(const Launch& L, int nO, int64_t nb, const T* xP, const T* y_o, const T* y_unc, T* rec,
@@ -927,6 +1392,16 @@ static size_t mlp_bwd_smem(const Cfg<T>& cfg) {
 
 template <typename T>
 cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu) {
+#define X(NI, H1, H2, NO_)                                                                     \
+  if (mlp3_match(cfg, NI, H1, H2, NO_)) {                                                      \
+    int64_t blocks = (nb + MLP3_BS - 1) / MLP3_BS;                                             \
+    if (blocks > (int64_t)L.sm_count * 8) blocks = (int64_t)L.sm_count * 8;                    \
+    k_mlp3_fwd<T, NI, H1, H2, NO_><<<(int)blocks, MLP3_BS, 0, L.stream>>>(cfg, phi, xM, nb, mu); \
+    HVI_LAUNCH_CHECK();                                                                        \
+    return cudaSuccess;                                                                        \
+  }
+  HVI_MLP3_CASES(X)
+#undef X
   const size_t smem = mlp_fwd_smem(cfg);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(k_mlp_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -942,6 +1417,23 @@ cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, con
 template <typename T>
 cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, const T* mubar, int64_t nb,
                            double* part, int* nblk_out, int nblk_max) {
+#define X(NI, H1, H2, NO_)                                                                                   \
+  if (mlp3_match(cfg, NI, H1, H2, NO_)) {                                                                    \
+    using N = Mlp3<T, NI, H1, H2, NO_>;                                                                      \
+    const size_t smem3 = sizeof(T) * (pad4(N::nW) + (size_t)MLP3_BS * N::ROW + (size_t)4 * N::TPL * 32 * 16); \
+    auto kern = k_mlp3_bwd<T, NI, H1, H2, NO_>;                                                              \
+    cudaError_t e3 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);    \
+    if (e3 != cudaSuccess) return e3;                                                                        \
+    const int64_t ntiles3 = (nb + MLP3_BS - 1) / MLP3_BS;                                                    \
+    int blocks3 = (int)(ntiles3 < (int64_t)nblk_max ? ntiles3 : (int64_t)nblk_max);                          \
+    if (blocks3 < 1) blocks3 = 1;                                                                            \
+    kern<<<blocks3, MLP3_BS, smem3, L.stream>>>(cfg, phi, xM, mubar, nb, part);                              \
+    HVI_LAUNCH_CHECK();                                                                                      \
+    *nblk_out = blocks3;                                                                                     \
+    return cudaSuccess;                                                                                      \
+  }
+  HVI_MLP3_CASES(X)
+#undef X
   const size_t smem = mlp_bwd_smem(cfg);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(k_mlp_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -955,14 +1447,14 @@ cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, con
   return cudaSuccess;
 }
 
-template <class TR, typename T, int NP, int NM, int NO>
-static cudaError_t launch_stream_inst(const Launch& L, const Cfg<T>& cfg, StreamArgs<T> a, int* nrows_out, int nrows_max) {
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB>
+static cudaError_t launch_stream_cfg(const Launch& L, const Cfg<T>& cfg, StreamArgs<T> a, int* nrows_out, int nrows_max) {
   constexpr int CH = 16 / sizeof(T), MC = 8 * CH, NWARP = STREAM_THREADS / 32;
   const size_t pd_bytes = (size_t)a.M * pd_stride(NP) * sizeof(T);
   a.pd_in_smem = (NP > 0 && pd_bytes <= 16 * 1024) ? 1 : 0;
   const size_t smem = (size_t)NWARP * 32 * NM * MC * sizeof(T) + (size_t)NWARP * nacc(NP, NM) * sizeof(double) +
                       (a.pd_in_smem ? pd_bytes : 0) + 16;
-  auto kern = k_stream<TR, T, NP, NM, NO>;
+  auto kern = k_stream<TR, T, NP, NM, NO, STREAM_THREADS, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -972,12 +1464,36 @@ static cudaError_t launch_stream_inst(const Launch& L, const Cfg<T>& cfg, Stream
   const int64_t ntiles = (a.nb + 31) / 32;
   int64_t blocks = (ntiles + NWARP - 1) / NWARP;
   if (blocks > (int64_t)L.sm_count * occ) blocks = (int64_t)L.sm_count * occ;
-  if (blocks * NWARP > nrows_max) blocks = nrows_max / NWARP;
+  if (blocks > nrows_max) blocks = nrows_max;
   if (blocks < 1) blocks = 1;
   kern<<<(int)blocks, STREAM_THREADS, smem, L.stream>>>(cfg, a);
   HVI_LAUNCH_CHECK();
-  *nrows_out = (int)blocks * NWARP;
+  *nrows_out = (int)blocks;
   return cudaSuccess;
+}
+
+// launch shape: Float32 runs 2 blocks of 256 threads per SM (128 registers), Float64 one block of
+// 256.  HVI_STREAM_VARIANT=1 selects 5 blocks of 128 threads (96 registers, spills; measured
+// 1.15 ms vs 0.88 ms at 2e6 sites x 64 draws) for experiments.
+static int stream_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HVI_STREAM_VARIANT"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+template <class TR, typename T, int NP, int NM, int NO>
+static cudaError_t launch_stream_inst(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, int* nrows_out,
+                                      int nrows_max) {
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (TR::STATIC) {
+      if (stream_variant() == 1) return launch_stream_cfg<TR, T, NP, NM, NO, 128, 5>(L, cfg, a, nrows_out, nrows_max);
+      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2>(L, cfg, a, nrows_out, nrows_max);
+    } else {
+      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2>(L, cfg, a, nrows_out, nrows_max);
+    }
+  } else {
+    return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1>(L, cfg, a, nrows_out, nrows_max);
+  }
 }
 
 #define HVI_STREAM_CASES(X) \
@@ -1029,14 +1545,13 @@ cudaError_t launch_stream(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T
 template <typename T>
 cudaError_t launch_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, const T* pdraw,
                             const EvalConsts<T>* ec, const double* part_stream, int nrows, const double* part_mlp,
-                            int nblk, double const_nly, int64_t nb, int M, double* out, T* grad_T) {
-  k_finalize<T><<<1, FIN_THREADS, 0, L.stream>>>(cfg, phi, zP, pdraw, ec, part_stream, nrows, part_mlp, nblk, const_nly,
-                                                nb, M, out, nullptr);
+                            int nblk, double const_nly, int64_t nb, int M, double* out, T* grad_T, double* red) {
+  const int nbg = (cfg.nphig + 31) / 32;
+  k_reduce<T><<<nbg + 1, RED_THREADS, 0, L.stream>>>(cfg.nphig, part_mlp, nblk, part_stream, nrows, nacc(cfg.nP, cfg.nM),
+                                                     out, grad_T, red);
   HVI_LAUNCH_CHECK();
-  if (grad_T) {
-    k_cast_grad<T><<<(cfg.nphi + 255) / 256, 256, 0, L.stream>>>(cfg.nphi, out, grad_T);
-    HVI_LAUNCH_CHECK();
-  }
+  k_finalize<T><<<1, FIN_THREADS, 0, L.stream>>>(cfg, phi, zP, pdraw, ec, red, nbg + 1, const_nly, nb, M, out, grad_T);
+  HVI_LAUNCH_CHECK();
   return cudaSuccess;
 }
 
@@ -1075,7 +1590,7 @@ cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const Strea
   template cudaError_t launch_stream<T>(const Launch&, const Cfg<T>&, const StreamArgs<T>&, int*, int);                  \
   template cudaError_t launch_finalize<T>(const Launch&, const Cfg<T>&, const T*, const T*, const T*,                    \
                                           const EvalConsts<T>*, const double*, int, const double*, int, double, int64_t, \
-                                          int, double*, T*);                                                             \
+                                          int, double*, T*, double*);                                                             \
   template cudaError_t launch_gen_normal<T>(const Launch&, T*, int64_t, int, uint64_t, int64_t);                         \
   template cudaError_t launch_generate_zeta<T>(const Launch&, const Cfg<T>&, const StreamArgs<T>&, const T*, T*, T*, T*);
 HVI_INSTANTIATE(float)
