@@ -33,6 +33,10 @@ struct hvi_plan {
   void* d_zMs; int64_t cap_zMs;
   void* d_ec;
   void* d_pdraw; int64_t cap_pdraw;
+  void* d_MU; int64_t cap_MU;        // pbm covariates: per-draw means [M][nM][nb]
+  void* d_MUBAR; int64_t cap_MUBAR;  // and their cotangents
+  double* d_part_x; int64_t cap_part_x;
+  double* d_xred; int64_t cap_xred;
   double* d_part_stream; int max_rows;
   double* d_part_mlp; int max_blk;
   double* d_out;
@@ -174,7 +178,8 @@ static const char* validate(const hvi_desc* d) {
     if (d->prior_M[i].kind && !(d->prior_M[i].b > 0)) return "prior_M scale must be positive";
   }
   if (!stream_supported(d->n_P, d->n_M, d->n_obs)) return "(n_P, n_M, n_obs) combination has no kernel instantiation";
-  if (d->n_pbm_covar > 0) return "pbm_covars not supported yet by this build";
+  if (d->n_pbm_covar > 0 && !mlp_supports_pbm(d))
+    return "pbm_covars need one of the register-tiled applicator shapes (5-20-20-2, 6-24-24-2)";
   return nullptr;
 }
 
@@ -204,6 +209,8 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   p->d_xM = p->d_rec = p->d_mu = p->d_mubar = nullptr;
   p->d_phi = p->d_zP = p->d_zMs = p->d_ec = p->d_pdraw = nullptr;
   p->cap_zP = p->cap_zMs = p->cap_pdraw = 0;
+  p->d_MU = p->d_MUBAR = nullptr; p->d_part_x = p->d_xred = nullptr;
+  p->cap_MU = p->cap_MUBAR = p->cap_part_x = p->cap_xred = 0;
   p->d_part_stream = p->d_part_mlp = p->d_out = p->d_red = nullptr;
   p->d_grad = nullptr; p->h_out = nullptr; p->h_grad = nullptr;
   p->const_nly = 0; p->anomalies = 0;
@@ -230,7 +237,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   CRE(cudaMalloc(&p->d_phi, p->es * (size_t)nphi));
   CRE(cudaMalloc(&p->d_ec, sizeof(EvalConsts<double>)));
   CRE(cudaMalloc(&p->d_part_stream, sizeof(double) * (size_t)p->max_rows * nacc(p->cf.nP, p->cf.nM)));
-  CRE(cudaMalloc(&p->d_part_mlp, sizeof(double) * (size_t)p->max_blk * p->cf.nphig));
+  CRE(cudaMalloc(&p->d_part_mlp, sizeof(double) * (size_t)2 * p->max_blk * p->cf.nphig));
   CRE(cudaMalloc(&p->d_out, sizeof(double) * (size_t)(nphi + 8)));
   CRE(cudaMalloc(&p->d_red, sizeof(double) * (size_t)(128 + (p->cf.nphig + 31) / 32 + 2)));
   CRE(cudaMalloc(&p->d_grad, p->es * (size_t)nphi));
@@ -246,7 +253,7 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   cudaSetDevice(p->desc.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   void* dev[] = {p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
-                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad};
+                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
   if (p->h_grad) cudaFreeHost(p->h_grad);
@@ -398,20 +405,41 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   MARK();
   CU(p, launch_prologue<T>(L, cfg, phi, zP, M, ec, pdraw));
   MARK();
+  const bool pbm = cfg.npc > 0;
+  const T* zetaP = pdraw + (size_t)cfg.nP * M;
   CU(p, launch_mlp_fwd<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (T*)p->d_mu));
+  if (pbm) {  // pass 2: g([xM; ζP_m[idx]]) for every draw (src/elbo.jl:508-515)
+    const int64_t nmu = (int64_t)sizeof(T) * M * cfg.nM * p->nb;
+    rc = ensure(p, &p->d_MU, &p->cap_MU, nmu);
+    if (rc) return rc;
+    rc = ensure(p, &p->d_MUBAR, &p->cap_MUBAR, nmu);
+    if (rc) return rc;
+    rc = ensure(p, (void**)&p->d_part_x, &p->cap_part_x, (int64_t)sizeof(double) * 2 * p->max_blk * (M + 1) * cfg.npc);
+    if (rc) return rc;
+    rc = ensure(p, (void**)&p->d_xred, &p->cap_xred, (int64_t)sizeof(double) * (M + 1) * cfg.npc);
+    if (rc) return rc;
+    CU(p, launch_mlp_fwd<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (T*)p->d_MU, M, zetaP));
+  }
   MARK();
   StreamArgs<T> a;
   a.rec = (const T*)p->d_rec; a.mu = (const T*)p->d_mu; a.zMs = zMs;
   a.pd = pdraw + (((size_t)4 * (cfg.nP > 0 ? cfg.nP : 1) * M + 3) & ~(size_t)3); a.pd_in_smem = 0;
   a.ec = ec; a.mubar = (T*)p->d_mubar; a.partials = p->d_part_stream; a.nb = p->nb; a.M = M;
+  a.MU = pbm ? (const T*)p->d_MU : nullptr; a.MUBAR = pbm ? (T*)p->d_MUBAR : nullptr;
   a.staged = (M % (16 / (int)sizeof(T)) == 0) && (((uintptr_t)zMs & 15) == 0);
-  int nrows = 0, nblk = 0;
+  int nrows = 0, nblk = 0, nblk2 = 0;
   CU(p, launch_stream<T>(L, cfg, a, &nrows, p->max_rows));
   MARK();
-  CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_mubar, p->nb, p->d_part_mlp, &nblk, p->max_blk));
+  double* part_xs = pbm ? p->d_part_x : nullptr;
+  double* part_xu = pbm ? p->d_part_x + (size_t)p->max_blk * cfg.npc : nullptr;
+  CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_mubar, p->nb, p->d_part_mlp, &nblk, p->max_blk, 0,
+                          nullptr, part_xs));
+  if (pbm)
+    CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_MUBAR, p->nb,
+                            p->d_part_mlp + (size_t)nblk * cfg.nphig, &nblk2, p->max_blk, M, zetaP, part_xu));
   MARK();
-  CU(p, launch_finalize<T>(L, cfg, phi, zP, pdraw, ec, p->d_part_stream, nrows, p->d_part_mlp, nblk, p->const_nly, p->nb,
-                           M, out, grad_T, p->d_red));
+  CU(p, launch_finalize<T>(L, cfg, phi, zP, pdraw, ec, p->d_part_stream, nrows, p->d_part_mlp, nblk + nblk2, p->const_nly,
+                           p->nb, M, out, grad_T, p->d_red, part_xs, nblk, part_xu, nblk2, p->d_xred));
   MARK();
 #undef MARK
   p->n_ev = iev;
@@ -558,8 +586,15 @@ static int generate_zeta_t(hvi_plan* p, int M, const void* phi, const void* zP, 
   StreamArgs<T> a;
   memset(&a, 0, sizeof a);
   a.mu = (const T*)p->d_mu; a.zMs = dzM; a.ec = ec; a.nb = nb; a.M = M;
+  if (cfg.npc > 0) {
+    rc = ensure(p, &p->d_MU, &p->cap_MU, (int64_t)sizeof(T) * M * nM * nb);
+    if (rc) { if (tmp) cudaFree(tmp); return rc; }
+    a.MU = (const T*)p->d_MU;
+  }
   cudaError_t e = launch_prologue<T>(L, cfg, dphi, dzP, M, ec, pdraw);
   if (e == cudaSuccess) e = launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, nb, (T*)p->d_mu);
+  if (e == cudaSuccess && cfg.npc > 0)
+    e = launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, nb, (T*)p->d_MU, M, pdraw + (size_t)nP * M);
   if (e == cudaSuccess) e = launch_generate_zeta<T>(L, cfg, a, pdraw, (T*)o1, (T*)o2, (T*)o3);
   if (e == cudaSuccess && mem_kind == HVI_MEM_HOST) {
     if (nP > 0) e = cudaMemcpyAsync(zetaP, o1, sizeof(T) * (size_t)nP * M, cudaMemcpyDeviceToHost, s);

@@ -61,6 +61,8 @@ struct StreamArgs {
   const T* pd;       // per-draw records of the global block [M][pd_stride(nP)]: θP, dθP/dζP, zP
   const EvalConsts<T>* ec;
   T* mubar;          // cotangent of μ_ζ (nM × nb)
+  const T* MU;       // pbm covariates only: per-draw means [M][nM][nb] (NULL otherwise)
+  T* MUBAR;          // and their cotangents, scaled by 1/n_MC
   double* partials;  // [gridDim.x * warps][nacc]
   int64_t nb;
   int M;
@@ -82,17 +84,21 @@ template <typename T>
 cudaError_t launch_prologue(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, int M, EvalConsts<T>* ec,
                             T* pdraw /*4 arrays [nP][M]: rP, zetaP, thP, gP; then [M][pd_stride] records*/);
 template <typename T>
-cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu);
+cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu,
+                           int M_units = 0, const T* zetaP = nullptr);
 template <typename T>
 cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, const T* mubar, int64_t nb,
-                           double* part /*[nblk][nphig]*/, int* nblk_out, int nblk_max);
+                           double* part /*[nblk][nphig]*/, int* nblk_out, int nblk_max, int M_units = 0,
+                           const T* zetaP = nullptr, double* part_x = nullptr /*[nblk][max(M_units,1)*npc]*/);
 template <typename T>
 cudaError_t launch_stream(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, int* nrows_out, int nrows_max);
 template <typename T>
 cudaError_t launch_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, const T* pdraw,
                             const EvalConsts<T>* ec, const double* part_stream, int nrows, const double* part_mlp,
                             int nblk, double const_nly, int64_t nb, int M, double* out, T* grad_T,
-                            double* red /*[128 + ceil(nphig/32) + 1] scratch*/);
+                            double* red /*[128 + ceil(nphig/32) + 1] scratch*/, const double* part_xs = nullptr,
+                            int nblk_xs = 0, const double* part_xu = nullptr, int nblk_xu = 0,
+                            double* xred = nullptr /*[(1 + M)·npc] scratch*/);
 template <typename T>
 cudaError_t launch_gen_normal(const Launch& L, T* z, int64_t n_cols, int M, uint64_t seed, int64_t col_offset);
 template <typename T>
@@ -103,5 +109,6 @@ inline size_t pdraw_elems(int nP, int M) { return (size_t)4 * (nP > 0 ? nP : 1) 
 int stream_max_rows(int sm_count);
 int mlp_bwd_max_blocks(int sm_count);
 bool stream_supported(int nP, int nM, int nO);
+bool mlp_supports_pbm(const hvi_desc* d);
 
 }  // namespace hvi

@@ -519,38 +519,71 @@ struct Mlp3 {
 
 constexpr int MLP3_BS = 128;
 
+// Columns of the applicator.  Site mode (M_units == 0): one column per site, the pbm covariates
+// (if any) are μP[idx] -- pass 1 of generate_ζ (src/elbo.jl:491-492).  Unit mode (M_units = n_MC):
+// one column per (draw m, site), the pbm covariates are ζP[idx, m] -- pass 2 (src/elbo.jl:508-515);
+// results go to / cotangents come from [m][k][site] arrays (site fastest: coalesced for the
+// thread-per-site kernels on both sides).
+struct MlpCols {
+  int M_units;       // 0: site mode
+  int64_t nb;
+};
+
 template <typename T, int NI, int H1, int H2, int NOUT>
 __global__ void __launch_bounds__(MLP3_BS) k_mlp3_fwd(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi,
-                                                      const T* __restrict__ xM, int64_t nb, T* __restrict__ mu) {
+                                                      const T* __restrict__ xM, const T* __restrict__ zetaP,
+                                                      MlpCols cols, T* __restrict__ mu) {
   using N = Mlp3<T, NI, H1, H2, NOUT>;
   __shared__ __align__(16) T sW[N::nW];
   const int t = threadIdx.x;
+  const int64_t nb = cols.nb;
   N::load_weights(cfg, phi, sW, t, MLP3_BS);
-  for (int64_t site = (int64_t)blockIdx.x * MLP3_BS + t; site < nb; site += (int64_t)gridDim.x * MLP3_BS) {
+  const int64_t ntiles = (nb + MLP3_BS - 1) / MLP3_BS;
+  const int64_t ntot = ntiles * (cols.M_units > 0 ? cols.M_units : 1);
+  for (int64_t g = blockIdx.x; g < ntot; g += gridDim.x) {
+    const int m = (int)(g / ntiles);
+    const int64_t site = (g % ntiles) * MLP3_BS + t;
+    if (site >= nb) continue;
     T x[NI], h1[N::H1P], h2[N::H2P], p[N::OP];
 #pragma unroll
-    for (int i = 0; i < NI; i++) x[i] = i < cfg.nC ? xM[site * cfg.nC + i] : phi[cfg.o_muP + cfg.pbm_covar_idx[i - cfg.nC]];
+    for (int i = 0; i < NI; i++) {
+      if (i < cfg.nC) x[i] = xM[site * cfg.nC + i];
+      else {
+        const int j = cfg.pbm_covar_idx[i - cfg.nC];
+        x[i] = cols.M_units > 0 ? zetaP[(size_t)j * cols.M_units + m] : phi[cfg.o_muP + j];
+      }
+    }
     N::forward(sW, x, h1, h2, p);
 #pragma unroll
     for (int k = 0; k < NOUT; k++)
-      if (k < cfg.nM)
-        mu[site * cfg.nM + k] = (cfg.scale_kind == HVI_SCALE_RANGE) ? p[k] * cfg.scale_b[k] + cfg.scale_a[k]
-                                                                    : cfg.scale_a[k] + cfg.scale_b[k] * ndtri_t(p[k]);
+      if (k < cfg.nM) {
+        const T v = (cfg.scale_kind == HVI_SCALE_RANGE) ? p[k] * cfg.scale_b[k] + cfg.scale_a[k]
+                                                        : cfg.scale_a[k] + cfg.scale_b[k] * ndtri_t(p[k]);
+        if (cols.M_units > 0) mu[((size_t)m * cfg.nM + k) * nb + site] = v;
+        else mu[site * cfg.nM + k] = v;
+      }
   }
 }
 
 template <typename T, int NI, int H1, int H2, int NOUT>
 __global__ void __launch_bounds__(MLP3_BS, 3) k_mlp3_bwd(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi,
-                                                      const T* __restrict__ xM, const T* __restrict__ mubar,
-                                                      int64_t nb, double* __restrict__ part) {
+                                                      const T* __restrict__ xM, const T* __restrict__ zetaP,
+                                                      const T* __restrict__ mubar, MlpCols cols,
+                                                      double* __restrict__ part, double* __restrict__ part_x) {
   using N = Mlp3<T, NI, H1, H2, NOUT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sW = reinterpret_cast<T*>(smem_raw);
   T* rows = sW + pad4(N::nW);                       // [MLP3_BS][ROW]
   T* sacc = rows + (size_t)MLP3_BS * N::ROW;        // [4 warps][TPL*32 tiles][16]: gradient tiles between site tiles
+  // cotangent of the pbm covariate inputs, summed over the sites: [max(M_units,1)][npc] doubles
+  double* xacc = reinterpret_cast<double*>(sacc + (size_t)4 * N::TPL * 32 * 16);
+  T* xred = reinterpret_cast<T*>(xacc + (size_t)(cols.M_units > 0 ? cols.M_units : 1) * cfg.npc);  // [4 warps][npc]
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t nb = cols.nb;
+  const int nxa = (cols.M_units > 0 ? cols.M_units : 1) * cfg.npc;
   N::load_weights(cfg, phi, sW, t, MLP3_BS);
   for (int e = t; e < 4 * N::TPL * 32 * 16; e += MLP3_BS) sacc[e] = T(0);
+  for (int e = t; e < nxa; e += MLP3_BS) xacc[e] = 0.0;
   // this lane's gradient tiles: offsets of the δ quad and of the activation quad inside a site row
   int doff[N::TPL], aoff[N::TPL];
 #pragma unroll
@@ -562,8 +595,10 @@ __global__ void __launch_bounds__(MLP3_BS, 3) k_mlp3_bwd(const __grid_constant__
     else { const int u = tl - N::NT1 - N::NT2; doff[q] = N::oD3 + 4 * (u % N::T3j); aoff[q] = N::oA2 + 4 * (u / N::T3j); }
   }
   const int64_t ntiles = (nb + MLP3_BS - 1) / MLP3_BS;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t site = tile * MLP3_BS + t;
+  const int64_t ntot = ntiles * (cols.M_units > 0 ? cols.M_units : 1);
+  for (int64_t g = blockIdx.x; g < ntot; g += gridDim.x) {
+    const int m = (int)(g / ntiles);
+    const int64_t site = (g % ntiles) * MLP3_BS + t;
     const bool active = site < nb;
     {  // phase A: this thread's site; all vectors live in the site row r
       T* r = rows + (size_t)t * N::ROW;
@@ -572,8 +607,14 @@ __global__ void __launch_bounds__(MLP3_BS, 3) k_mlp3_bwd(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < pad4(NI + 1); i++) x[i] = T(0);
 #pragma unroll
-        for (int i = 0; i < NI; i++)
-          x[i] = !active ? T(0) : i < cfg.nC ? xM[site * cfg.nC + i] : phi[cfg.o_muP + cfg.pbm_covar_idx[i - cfg.nC]];
+        for (int i = 0; i < NI; i++) {
+          if (!active) x[i] = T(0);
+          else if (i < cfg.nC) x[i] = xM[site * cfg.nC + i];
+          else {
+            const int j = cfg.pbm_covar_idx[i - cfg.nC];
+            x[i] = cols.M_units > 0 ? zetaP[(size_t)j * cols.M_units + m] : phi[cfg.o_muP + j];
+          }
+        }
 #pragma unroll
         for (int i = 0; i < pad4(NI + 1); i += 4) st4(r + N::oA0 + i, x[i], x[i + 1], x[i + 2], x[i + 3]);
       }
@@ -606,7 +647,7 @@ __global__ void __launch_bounds__(MLP3_BS, 3) k_mlp3_bwd(const __grid_constant__
           T d = T(0);
           if (k < NOUT && k < cfg.nM && active) {
             const T pk = logistic_fast(p[k]);
-            const T mb = mubar[site * cfg.nM + k];
+            const T mb = cols.M_units > 0 ? mubar[((size_t)m * cfg.nM + k) * nb + site] : mubar[site * cfg.nM + k];
             if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb * cfg.scale_b[k];
             else { const T q = ndtri_t(pk); d = mb * cfg.scale_b[k] * T(2.50662827463100050242) * exp_t(T(0.5) * q * q); }
             d *= pk * (T(1) - pk);
@@ -628,10 +669,29 @@ __global__ void __launch_bounds__(MLP3_BS, 3) k_mlp3_bwd(const __grid_constant__
         }
         N::template dense_T_row<H1, N::H2P>(sW + N::oW2, d2, r + N::oA1, r + N::oD1);
       }
+      // cotangent of the pbm covariate inputs: x̄[nC + c] = Σ_j W1[nC + c][j]·δ1[j], summed over
+      // the tile's sites in a fixed order (warp shuffle tree, then the 4 warps in order)
+      for (int c = 0; c < cfg.npc; c++) {
+        T xb = T(0);
+        const T* w1 = sW + N::oW1 + (cfg.nC + c) * N::H1P;
+#pragma unroll
+        for (int j4 = 0; j4 < N::H1P / 4; j4++) {
+          const V4<T> w = ld4(w1 + 4 * j4), d = ld4(r + N::oD1 + 4 * j4);
+#pragma unroll
+          for (int cc = 0; cc < 4; cc++) xb = fma(w.v[cc], d.v[cc], xb);
+        }
+        xb = warp_sum(xb);
+        if (lane == 0) xred[warp * cfg.npc + c] = xb;
+      }
       // the constant 1 that multiplies the bias
       r[N::oA0 + NI] = T(1); r[N::oA1 + H1] = T(1); r[N::oA2 + H2] = T(1);
     }
     __syncthreads();
+    if (t < cfg.npc) {
+      double sx = 0.0;
+      for (int w = 0; w < MLP3_BS / 32; w++) sx += (double)xred[w * cfg.npc + t];
+      xacc[(cols.M_units > 0 ? m : 0) * cfg.npc + t] += sx;
+    }
     // phase B: this warp's 32 sites of the tile
     {
       T acc[N::TPL][16];
@@ -682,6 +742,8 @@ __global__ void __launch_bounds__(MLP3_BS, 3) k_mlp3_bwd(const __grid_constant__
       else if (i == nin && cfg.l_bias[l]) out[cfg.boff[l] + j] = s;
     }
   }
+  if (part_x)
+    for (int e = t; e < nxa; e += MLP3_BS) part_x[(size_t)blockIdx.x * nxa + e] = xacc[e];
 }
 
 #define HVI_MLP3_CASES(X) X(5, 20, 20, 2) X(6, 24, 24, 2)
@@ -794,13 +856,15 @@ __device__ __forceinline__ void obs_loop(SiteState<T, NP, NM, NO>& st, const T (
   pbar[3] = -par[1] * (gB.x + gB.y);
 }
 
+// mud: the mean μ_ζ of this draw (st.mu without pbm covariates; g([xM; ζP_m]) with them,
+// src/elbo.jl:508-515); zbout: cotangent ζ̄M of this draw (unscaled by 1/n_MC)
 template <class TR, typename T, int NP, int NM, int NO>
 __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, NO>& st, const T (&z)[NM],
-                                        const T* __restrict__ pd) {
+                                        const T* __restrict__ pd, const T (&mud)[NM], T (&zbout)[NM]) {
   T th[NM], dth[NM], dz[NM];  // dz = d(prior − logjac)/dζ
 #pragma unroll
   for (int k = 0; k < NM; k++) {
-    T zeta = st.mu[k];
+    T zeta = mud[k];
 #pragma unroll
     for (int j = 0; j <= k; j++) zeta = fma(st.sU[ut(j, k)], z[j], zeta);
     const int trk = tr_transM<TR>(cfg, k), pkk = tr_priorM<TR>(cfg, k);
@@ -868,6 +932,7 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, 
 #pragma unroll
   for (int k = 0; k < NM; k++) {
     const T zb = fma(thbar[NP + k], dth[k], dz[k]);
+    zbout[k] = zb;
     st.smu[k] += zb;
 #pragma unroll
     for (int j = 0; j <= k; j++) st.sz[ut(j, k)] = fma(zb, z[j], st.sz[ut(j, k)]);
@@ -883,7 +948,7 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, 
 
 constexpr int STREAM_THREADS_MAX = 256;
 
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB>
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM>
 __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_constant__ Cfg<T> cfg,
                                                                  const __grid_constant__ StreamArgs<T> a) {
   constexpr int CH = 16 / sizeof(T);  // elements per 16-byte chunk
@@ -1000,12 +1065,22 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
               }
             }
             const T* pd = pdbase + (size_t)(m0 + q * CH) * PD;
+            T mud[CH][NM];
+#pragma unroll
+            for (int d = 0; d < CH; d++)
+#pragma unroll
+              for (int k = 0; k < NM; k++)
+                mud[d][k] = PBM ? a.MU[((size_t)(m0 + q * CH + d) * NM + k) * a.nb + site] : st.mu[k];
 #pragma unroll
             for (int d = 0; d < CH; d++) {
-              T z[NM];
+              T z[NM], zb[NM];
 #pragma unroll
               for (int k = 0; k < NM; k++) z[k] = zc[k][d];
-              do_draw<TR, T, NP, NM, NO>(cfg, st, z, pd + d * PD);
+              do_draw<TR, T, NP, NM, NO>(cfg, st, z, pd + d * PD, mud[d], zb);
+              if constexpr (PBM) {
+#pragma unroll
+                for (int k = 0; k < NM; k++) a.MUBAR[((size_t)(m0 + q * CH + d) * NM + k) * a.nb + site] = wM * zb[k];
+              }
             }
           }
         }
@@ -1013,10 +1088,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
       }
     } else if (active) {
       for (int m = 0; m < M; m++) {
-        T z[NM];
+        T z[NM], zb[NM], mud[NM];
 #pragma unroll
-        for (int k = 0; k < NM; k++) z[k] = a.zMs[((size_t)site * NM + k) * M + m];
-        do_draw<TR, T, NP, NM, NO>(cfg, st, z, pdbase + (size_t)m * PD);
+        for (int k = 0; k < NM; k++) {
+          z[k] = a.zMs[((size_t)site * NM + k) * M + m];
+          mud[k] = PBM ? a.MU[((size_t)m * NM + k) * a.nb + site] : st.mu[k];
+        }
+        do_draw<TR, T, NP, NM, NO>(cfg, st, z, pdbase + (size_t)m * PD, mud, zb);
+        if constexpr (PBM) {
+#pragma unroll
+          for (int k = 0; k < NM; k++) a.MUBAR[((size_t)m * NM + k) * a.nb + site] = wM * zb[k];
+        }
       }
     }
 
@@ -1036,7 +1118,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
         acc[ACC_LOGSIG] += T(0.5) * ls[k];
         acc[ACC_FIRST_VEC + k] = lsb;
         acc[ACC_FIRST_VEC + NM + k] = lsb * st.mu[k];
-        a.mubar[site * NM + k] = fma(wM, st.smu[k], lsb * cB[k]);
+        // with pbm covariates the pass-1 mean feeds σ only (src/elbo.jl:491-495)
+        a.mubar[site * NM + k] = PBM ? lsb * cB[k] : fma(wM, st.smu[k], lsb * cB[k]);
 #pragma unroll
         for (int j = 0; j <= k; j++) acc[ACC_FIRST_VEC + 2 * NM + ut(j, k)] = sig[k] * st.sz[ut(j, k)];
       }
@@ -1093,6 +1176,24 @@ __device__ void build_U_adj(int n, const int* blk_start, const int* rho_off, con
     for (int i = blk_start[k]; i <= k; i++) dot += (double)U[i][k] * Ubar[i][k];
     for (int i = blk_start[k]; i < k; i++)
       rho_bar[rho_off[k] + (i - blk_start[k])] += (Ubar[i][k] - (double)U[i][k] * dot) / (double)nrm[k];
+  }
+}
+
+// column sums of a [nrows][ncols] array of per-block partials, 32 columns per block, fixed order
+__global__ void __launch_bounds__(256) k_colsum(const double* __restrict__ part, int nrows, int ncols,
+                                                double* __restrict__ out) {
+  __shared__ double sm[8][33];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + c;
+  double s0 = 0;
+  if (e < ncols)
+    for (int r = g; r < nrows; r += 8) s0 += part[(size_t)r * ncols + e];
+  sm[g][c] = s0;
+  __syncthreads();
+  if (g == 0 && e < ncols) {
+    double s = 0;
+    for (int gg = 0; gg < 8; gg++) s += sm[gg][c];
+    out[e] = s;
   }
 }
 
@@ -1164,6 +1265,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
                                                           const T* __restrict__ pdraw,
                                                           const EvalConsts<T>* __restrict__ ecp,
                                                           const double* __restrict__ red, int nred_blocks,
+                                                          const double* __restrict__ xs, const double* __restrict__ xu,
                                                           double const_nly, int64_t nb, int M,
                                                           double* __restrict__ out, T* __restrict__ grad_T) {
   __shared__ double sred[FIN_THREADS];
@@ -1180,6 +1282,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
   // prior and log-Jacobian of θP and their cotangents, once per evaluation: the
   // draws are spread over the threads, each sum is a fixed-shape tree
   __shared__ double sPg[MAXP][3 + MAXP];   // per j: Σ pv, Σ lj, Σ zb, Σ zb·zP[m, jj]
+  __shared__ double sPx[MAXP][1 + MAXP];   // per j: Σ x̄, Σ x̄·zP[m, jj]  (pbm covariates)
   {
     const T* zetaP_ = pdraw + (size_t)nP * M;
     for (int j = 0; j < nP; j++) {
@@ -1197,6 +1300,22 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
       for (int i = 0; i < 3 + j + 1; i++) {
         const double r = block_sum_fixed(v[i], sred);
         if (t == 0) sPg[j][i] = r;
+      }
+      // cotangent that reaches ζP[j, m] through the pbm covariate inputs of g (already scaled by 1/n_MC)
+      if (xu) {
+        for (int i = 0; i < 1 + MAXP; i++) v[i] = 0.0;
+        for (int c = 0; c < cfg.npc; c++) {
+          if (cfg.pbm_covar_idx[c] != j) continue;
+          for (int m = t; m < M; m += FIN_THREADS) {
+            const double x = xu[(size_t)m * cfg.npc + c];
+            v[0] += x;
+            for (int jj = 0; jj <= j; jj++) v[1 + jj] += x * (double)zP[m + (size_t)M * jj];
+          }
+        }
+        for (int i = 0; i < 1 + j + 1; i++) {
+          const double r = block_sum_fixed(v[i], sred);
+          if (t == 0) sPx[j][i] = r;
+        }
       }
     }
   }
@@ -1236,6 +1355,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
         lj += w * sPg[j][1];
         logsig += 0.5 * (double)phi[cfg.o_ls2P + j];
       }
+      if (xu) {
+        aP += sPx[j][0];
+        for (int jj = 0; jj <= j; jj++) CP[jj][j] += sPx[j][1 + jj];
+      }
       G[cfg.o_muP + j] += aP;
       // Σ_m ζ̄P[j,m]·rP[j,m] = σP[j] Σ_{jj} UP[jj][j]·CP[jj][j]
       double sr = 0;
@@ -1245,6 +1368,9 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
       for (int jj = 0; jj <= j; jj++) Ubar[jj][j] = (double)ec.sigP[j] * CP[jj][j];
     }
     build_U_adj<T>(nP, cfg.blkP_start, cfg.rhoP_off, ec.UP, ec.nrmP, Ubar, G + cfg.o_rhoP);
+    // pass 1 of g took μP[idx] as input (src/elbo.jl:491)
+    if (xs)
+      for (int c = 0; c < cfg.npc; c++) G[cfg.o_muP + cfg.pbm_covar_idx[c]] += xs[c];
     const double Kdim = (double)nM * (double)nb + (cfg.count_globals ? nP : 0);
     const double ent = 0.5 * Kdim * 2.8378770664093454836 + logsig;   // (K·log(2πe) + 2Σlog σ)/2, logden_normal.jl:74
     const double nlj = -lj;
@@ -1341,7 +1467,8 @@ __global__ void __launch_bounds__(256) k_generate_zeta(const __grid_constant__ C
     for (int m = 0; m < M; m++) {
       T t = T(0);
       for (int j = cfg.blkM_start[k]; j <= k; j++) t += ec.UM[j][k] * a.zMs[((size_t)i * nM + j) * M + m];
-      zetaMs_tr[i + a.nb * (k + (size_t)nM * m)] = mu + sg * t;
+      const T mum = a.MU ? a.MU[((size_t)m * nM + k) * a.nb + i] : mu;   // pass-2 mean with pbm covariates
+      zetaMs_tr[i + a.nb * (k + (size_t)nM * m)] = mum + sg * t;
     }
   }
 }
@@ -1391,17 +1518,20 @@ static size_t mlp_bwd_smem(const Cfg<T>& cfg) {
 }
 
 template <typename T>
-cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu) {
-#define X(NI, H1, H2, NO_)                                                                     \
-  if (mlp3_match(cfg, NI, H1, H2, NO_)) {                                                      \
-    int64_t blocks = (nb + MLP3_BS - 1) / MLP3_BS;                                             \
-    if (blocks > (int64_t)L.sm_count * 8) blocks = (int64_t)L.sm_count * 8;                    \
-    k_mlp3_fwd<T, NI, H1, H2, NO_><<<(int)blocks, MLP3_BS, 0, L.stream>>>(cfg, phi, xM, nb, mu); \
-    HVI_LAUNCH_CHECK();                                                                        \
-    return cudaSuccess;                                                                        \
+cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu, int M_units,
+                           const T* zetaP) {
+#define X(NI, H1, H2, NO_)                                                                       \
+  if (mlp3_match(cfg, NI, H1, H2, NO_)) {                                                        \
+    int64_t blocks = ((nb + MLP3_BS - 1) / MLP3_BS) * (M_units > 0 ? M_units : 1);               \
+    if (blocks > (int64_t)L.sm_count * 8) blocks = (int64_t)L.sm_count * 8;                      \
+    MlpCols cols{M_units, nb};                                                                   \
+    k_mlp3_fwd<T, NI, H1, H2, NO_><<<(int)blocks, MLP3_BS, 0, L.stream>>>(cfg, phi, xM, zetaP, cols, mu); \
+    HVI_LAUNCH_CHECK();                                                                          \
+    return cudaSuccess;                                                                          \
   }
   HVI_MLP3_CASES(X)
 #undef X
+  if (M_units > 0 || cfg.npc > 0) return cudaErrorInvalidConfiguration;  // pbm covariates need the tiled applicator
   const size_t smem = mlp_fwd_smem(cfg);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(k_mlp_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1414,26 +1544,41 @@ cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, con
   return cudaSuccess;
 }
 
+bool mlp_supports_pbm(const hvi_desc* d) {
+#define X(NI, H1, H2, NO_)                                                                                              \
+  if (d->n_layers == 3 && d->layers[0].n_in == NI && d->layers[0].n_out == H1 && d->layers[1].n_out == H2 &&            \
+      d->layers[2].n_out == NO_ && d->layers[0].act == HVI_ACT_TANH && d->layers[1].act == HVI_ACT_TANH &&              \
+      d->layers[2].act == HVI_ACT_LOGISTIC && d->layers[0].has_bias && d->layers[1].has_bias && !d->layers[2].has_bias) \
+    return true;
+  HVI_MLP3_CASES(X)
+#undef X
+  return false;
+}
+
 template <typename T>
 cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, const T* mubar, int64_t nb,
-                           double* part, int* nblk_out, int nblk_max) {
+                           double* part, int* nblk_out, int nblk_max, int M_units, const T* zetaP, double* part_x) {
 #define X(NI, H1, H2, NO_)                                                                                   \
   if (mlp3_match(cfg, NI, H1, H2, NO_)) {                                                                    \
     using N = Mlp3<T, NI, H1, H2, NO_>;                                                                      \
-    const size_t smem3 = sizeof(T) * (pad4(N::nW) + (size_t)MLP3_BS * N::ROW + (size_t)4 * N::TPL * 32 * 16); \
+    const size_t smem3 = sizeof(T) * (pad4(N::nW) + (size_t)MLP3_BS * N::ROW + (size_t)4 * N::TPL * 32 * 16) + \
+                         sizeof(double) * (size_t)(M_units > 0 ? M_units : 1) * cfg.npc + sizeof(T) * 4 * cfg.npc + 16; \
+    if (smem3 > 220 * 1024) return cudaErrorInvalidConfiguration;                                            \
     auto kern = k_mlp3_bwd<T, NI, H1, H2, NO_>;                                                              \
     cudaError_t e3 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);    \
     if (e3 != cudaSuccess) return e3;                                                                        \
-    const int64_t ntiles3 = (nb + MLP3_BS - 1) / MLP3_BS;                                                    \
+    const int64_t ntiles3 = ((nb + MLP3_BS - 1) / MLP3_BS) * (M_units > 0 ? M_units : 1);                    \
     int blocks3 = (int)(ntiles3 < (int64_t)nblk_max ? ntiles3 : (int64_t)nblk_max);                          \
     if (blocks3 < 1) blocks3 = 1;                                                                            \
-    kern<<<blocks3, MLP3_BS, smem3, L.stream>>>(cfg, phi, xM, mubar, nb, part);                              \
+    MlpCols cols{M_units, nb};                                                                               \
+    kern<<<blocks3, MLP3_BS, smem3, L.stream>>>(cfg, phi, xM, zetaP, mubar, cols, part, part_x);             \
     HVI_LAUNCH_CHECK();                                                                                      \
     *nblk_out = blocks3;                                                                                     \
     return cudaSuccess;                                                                                      \
   }
   HVI_MLP3_CASES(X)
 #undef X
+  if (M_units > 0 || cfg.npc > 0) return cudaErrorInvalidConfiguration;
   const size_t smem = mlp_bwd_smem(cfg);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(k_mlp_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1447,14 +1592,14 @@ cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, con
   return cudaSuccess;
 }
 
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB>
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM>
 static cudaError_t launch_stream_cfg(const Launch& L, const Cfg<T>& cfg, StreamArgs<T> a, int* nrows_out, int nrows_max) {
   constexpr int CH = 16 / sizeof(T), MC = 8 * CH, NWARP = STREAM_THREADS / 32;
   const size_t pd_bytes = (size_t)a.M * pd_stride(NP) * sizeof(T);
   a.pd_in_smem = (NP > 0 && pd_bytes <= 16 * 1024) ? 1 : 0;
   const size_t smem = (size_t)NWARP * 32 * NM * MC * sizeof(T) + (size_t)NWARP * nacc(NP, NM) * sizeof(double) +
                       (a.pd_in_smem ? pd_bytes : 0) + 16;
-  auto kern = k_stream<TR, T, NP, NM, NO, STREAM_THREADS, MINB>;
+  auto kern = k_stream<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -1484,15 +1629,19 @@ static int stream_variant() {
 template <class TR, typename T, int NP, int NM, int NO>
 static cudaError_t launch_stream_inst(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, int* nrows_out,
                                       int nrows_max) {
+  const bool pbm = a.MU != nullptr;
   if constexpr (sizeof(T) == 4) {
     if constexpr (TR::STATIC) {
-      if (stream_variant() == 1) return launch_stream_cfg<TR, T, NP, NM, NO, 128, 5>(L, cfg, a, nrows_out, nrows_max);
-      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2>(L, cfg, a, nrows_out, nrows_max);
+      if (pbm) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, true>(L, cfg, a, nrows_out, nrows_max);
+      if (stream_variant() == 1) return launch_stream_cfg<TR, T, NP, NM, NO, 128, 5, false>(L, cfg, a, nrows_out, nrows_max);
+      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, false>(L, cfg, a, nrows_out, nrows_max);
     } else {
-      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2>(L, cfg, a, nrows_out, nrows_max);
+      if (pbm) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, true>(L, cfg, a, nrows_out, nrows_max);
+      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, false>(L, cfg, a, nrows_out, nrows_max);
     }
   } else {
-    return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1>(L, cfg, a, nrows_out, nrows_max);
+    if (pbm) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1, true>(L, cfg, a, nrows_out, nrows_max);
+    return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1, false>(L, cfg, a, nrows_out, nrows_max);
   }
 }
 
@@ -1545,12 +1694,23 @@ cudaError_t launch_stream(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T
 template <typename T>
 cudaError_t launch_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, const T* pdraw,
                             const EvalConsts<T>* ec, const double* part_stream, int nrows, const double* part_mlp,
-                            int nblk, double const_nly, int64_t nb, int M, double* out, T* grad_T, double* red) {
+                            int nblk, double const_nly, int64_t nb, int M, double* out, T* grad_T, double* red,
+                            const double* part_xs, int nblk_xs, const double* part_xu, int nblk_xu, double* xred) {
   const int nbg = (cfg.nphig + 31) / 32;
   k_reduce<T><<<nbg + 1, RED_THREADS, 0, L.stream>>>(cfg.nphig, part_mlp, nblk, part_stream, nrows, nacc(cfg.nP, cfg.nM),
                                                      out, grad_T, red);
   HVI_LAUNCH_CHECK();
-  k_finalize<T><<<1, FIN_THREADS, 0, L.stream>>>(cfg, phi, zP, pdraw, ec, red, nbg + 1, const_nly, nb, M, out, grad_T);
+  double *xs = nullptr, *xu = nullptr;
+  if (cfg.npc > 0 && part_xs && part_xu) {
+    xs = xred;
+    xu = xred + cfg.npc;
+    k_colsum<<<(cfg.npc + 31) / 32, 256, 0, L.stream>>>(part_xs, nblk_xs, cfg.npc, xs);
+    HVI_LAUNCH_CHECK();
+    k_colsum<<<(M * cfg.npc + 31) / 32, 256, 0, L.stream>>>(part_xu, nblk_xu, M * cfg.npc, xu);
+    HVI_LAUNCH_CHECK();
+  }
+  k_finalize<T><<<1, FIN_THREADS, 0, L.stream>>>(cfg, phi, zP, pdraw, ec, red, nbg + 1, xs, xu, const_nly, nb, M, out,
+                                                grad_T);
   HVI_LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -1584,13 +1744,13 @@ cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const Strea
 #define HVI_INSTANTIATE(T)                                                                                              \
   template cudaError_t launch_preprocess<T>(const Launch&, int, int64_t, const T*, const T*, const T*, T*, double*, int*); \
   template cudaError_t launch_prologue<T>(const Launch&, const Cfg<T>&, const T*, const T*, int, EvalConsts<T>*, T*);    \
-  template cudaError_t launch_mlp_fwd<T>(const Launch&, const Cfg<T>&, const T*, const T*, int64_t, T*);                 \
+  template cudaError_t launch_mlp_fwd<T>(const Launch&, const Cfg<T>&, const T*, const T*, int64_t, T*, int, const T*);  \
   template cudaError_t launch_mlp_bwd<T>(const Launch&, const Cfg<T>&, const T*, const T*, const T*, int64_t, double*,   \
-                                         int*, int);                                                                     \
+                                         int*, int, int, const T*, double*);                                             \
   template cudaError_t launch_stream<T>(const Launch&, const Cfg<T>&, const StreamArgs<T>&, int*, int);                  \
   template cudaError_t launch_finalize<T>(const Launch&, const Cfg<T>&, const T*, const T*, const T*,                    \
                                           const EvalConsts<T>*, const double*, int, const double*, int, double, int64_t, \
-                                          int, double*, T*, double*);                                                             \
+                                          int, double*, T*, double*, const double*, int, const double*, int, double*);                                                             \
   template cudaError_t launch_gen_normal<T>(const Launch&, T*, int64_t, int, uint64_t, int64_t);                         \
   template cudaError_t launch_generate_zeta<T>(const Launch&, const Cfg<T>&, const StreamArgs<T>&, const T*, T*, T*, T*);
 HVI_INSTANTIATE(float)

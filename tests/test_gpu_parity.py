@@ -25,6 +25,10 @@ CASES = {
     "DoubleMM_transIdent": lambda dt: hvi_b200.DoubleMMCase(("transIdent",), dtype=dt),
     "DoubleMM_neglect_cor": lambda dt: hvi_b200.DoubleMMCase(("neglect_cor",), dtype=dt),
     "DoubleMM_rangescaling": lambda dt: hvi_b200.DoubleMMCase(("use_rangescaling",), dtype=dt),
+    # pbm covariates: g([xM; ζP_m[idx]]) per draw (src/elbo.jl:491-518; docs/src/tutorials/corr_site_global.md)
+    "DoubleMM_covarK2": lambda dt: hvi_b200.DoubleMMCase(("covarK2",), dtype=dt),
+    "C1_covarK2": lambda dt: hvi_b200.construct_problem_test_HybridProblem(("covarK2",), dtype=dt),
+    "DoubleMM_K1global_covarK1": lambda dt: hvi_b200.DoubleMMCase(("omit_r0", "K1global", "covarK2"), dtype=dt),
 }
 
 
@@ -82,6 +86,29 @@ def test_missing_drivers(dtype):
 def test_initial_parameters(dtype):
     """ϕ as initialised by the reference (logσ2 = −10, ρ = 0)."""
     check(hvi_b200.DoubleMMCase(dtype=dtype), nb=100, M=16, perturbed=False)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("nb,M", [(33, 8), (300, 12), (129, 5)])
+def test_pbm_covars_ragged(nb, M, dtype):
+    check(hvi_b200.DoubleMMCase(("covarK2",), dtype=dtype), nb=nb, M=M, nan_frac=0.2)
+
+
+def test_generate_zeta_with_pbm_covars():
+    import torch
+    prob = hvi_b200.DoubleMMCase(("covarK2",), dtype="f64")
+    nb, M = 40, 6
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb)
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
+    ϕ = prob.init_ϕ(perturbed=True)
+    plan = hvi_b200.NegElboPlan(prob)
+    plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    ζP, ζMs, σ = plan.generate_ζ(ϕ, zP, zMs)
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+    ζP_o, ζMs_o, σ_o = O.generate_zeta(oracle_spec(prob), t(ϕ), t(data["xM"]), t(zP), t(zMs))
+    np.testing.assert_allclose(ζP, ζP_o.numpy(), rtol=1e-12)
+    np.testing.assert_allclose(ζMs, ζMs_o.numpy(), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(σ, σ_o.numpy(), rtol=1e-12)
 
 
 def test_run_to_run_bit_reproducible():
