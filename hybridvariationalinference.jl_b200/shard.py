@@ -1,0 +1,32 @@
+"""Site sharding for multi-GPU jobs.  The reference is single-device; given ϕ
+the sites are independent, so rank r of R owns the contiguous site range
+[r·n/R, (r+1)·n/R) of (xM, xP, y_o, y_unc, zMs), ϕ and zP are replicated, the terms that exist
+once per evaluation (prior / log-Jacobian / entropy of the global block) are counted on rank 0
+only (`count_globals`), and ONE all-reduce(sum) of [∇ϕ ; 6 components ; nL ; non-finite count]
+(|ϕ| + 8 doubles) finishes the evaluation.  No other data-path collective.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+
+def site_range(n_site: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced site range of a rank (first `n_site % world` ranks get one more)."""
+    base, rem = divmod(n_site, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(data: dict, zMs, n_M: int, rank: int, world: int):
+    """Slice a batch and its draws zMs (n_MC × n_M·n_site, site-major columns) for one rank."""
+    n_site = data["xM"].shape[1]
+    lo, hi = site_range(n_site, rank, world)
+    d = {k: data[k][:, lo:hi] for k in ("xM", "xP", "y_o", "y_unc")}
+    return d, zMs[:, lo * n_M:hi * n_M], lo
+
+
+def allreduce_result(out, dist=None):
+    """Sum [∇ϕ ; components ; nL ; non-finite] over the ranks (torch tensor, in place)."""
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(out)
+    return out

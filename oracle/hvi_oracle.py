@@ -437,8 +437,8 @@ def value_and_grad(spec: Spec, phi, xM, xP, y_ob, y_unc, zP, zMs, dtype_name="f6
     comps = neg_elbo_gtf_components(spec, ph, t(xM), t(xP), t(y_ob), t(y_unc), t(zP), t(zMs), dtype_name)
     nL = comps["nLjoint"] - comps["entropy_zeta"] + comps["loss_penalty"]
     (g,) = torch.autograd.grad(nL, ph)
-    cv = np.array([float(comps[k]) for k in COMPONENTS])
-    return float(nL), cv, g.numpy().copy()
+    cv = np.array([float(comps[k].detach()) for k in COMPONENTS])
+    return float(nL.detach()), cv, g.numpy().copy()
 
 
 # --------------------------------------------------------------------------------------

@@ -173,3 +173,47 @@ def test_device_rng_mode_statistics():
     zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
     d = plan.neg_elbo_withgradient(ϕ, zP, zMs)
     assert abs(a[0] - d[0]) / abs(d[0]) < 0.2
+
+
+@pytest.mark.parametrize("case", ["DoubleMM_default", "DoubleMM_covarK2"])
+def test_site_shards_on_one_gpu_sum_to_the_whole(case):
+    """SURVEY 8(e) on the CUDA path: two plans own contiguous site ranges, only the first counts
+    the global-block terms; the sum of their [∇ϕ ; components] equals the unsharded evaluation
+    (what the NCCL all-reduce computes across ranks)."""
+    from hvi_b200.shard import shard_batch
+    prob = CASES[case]("f64")
+    nb, M = 90, 8
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb)
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
+    ϕ = prob.init_ϕ(perturbed=True)
+    full = hvi_b200.NegElboPlan(prob)
+    full.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    nL, comps, g = full.neg_elbo_withgradient(ϕ, zP, zMs)
+    tot_g, tot_c = np.zeros_like(g, dtype=np.float64), np.zeros(6)
+    for r in range(2):
+        d, z, lo = shard_batch(data, zMs, prob.n_M, r, 2)
+        plan = hvi_b200.NegElboPlan(prob, count_globals=(r == 0))
+        plan.set_data(d["xM"], d["xP"], d["y_o"], d["y_unc"])
+        _, c, gg = plan.neg_elbo_withgradient(ϕ, zP, z)
+        tot_g += gg
+        tot_c += np.array(c)
+    np.testing.assert_allclose(tot_c, np.array(comps), rtol=1e-11)
+    np.testing.assert_allclose(tot_g, g, rtol=1e-9, atol=1e-10 * np.abs(g).max())
+
+
+def test_device_rng_is_sharding_invariant():
+    """the device generator is keyed by the global site index: a shard with site_offset draws the
+    same ξ as the corresponding sites of the unsharded evaluation."""
+    prob = hvi_b200.DoubleMMCase(dtype="f64")
+    nb, M = 64, 8
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb)
+    ϕ = prob.init_ϕ(perturbed=True)
+    full = hvi_b200.NegElboPlan(prob)
+    full.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    nL, comps, g = full.neg_elbo_withgradient(ϕ, n_MC=M, seed=5)
+    tot = np.zeros(6)
+    for r, (lo, hi) in enumerate([(0, 24), (24, 64)]):
+        plan = hvi_b200.NegElboPlan(prob, count_globals=(r == 0))
+        plan.set_data(*(data[k][:, lo:hi] for k in ("xM", "xP", "y_o", "y_unc")))
+        tot += np.array(plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=5, site_offset=lo)[1])
+    np.testing.assert_allclose(tot, np.array(comps), rtol=1e-11)
