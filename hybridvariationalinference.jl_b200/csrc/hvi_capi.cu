@@ -37,6 +37,8 @@ struct hvi_plan {
   void* d_MUBAR; int64_t cap_MUBAR;  // and their cotangents
   double* d_part_x; int64_t cap_part_x;
   double* d_xred; int64_t cap_xred;
+  void* d_stage; int64_t cap_stage;   // staging of a host batch (xP, y_o, y_unc) for k_preprocess
+  double* h_pre;                      // pinned: preprocess partial sums
   double* d_part_stream; int max_rows;
   double* d_part_mlp; int max_blk;
   double* d_out;
@@ -211,6 +213,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   p->cap_zP = p->cap_zMs = p->cap_pdraw = 0;
   p->d_MU = p->d_MUBAR = nullptr; p->d_part_x = p->d_xred = nullptr;
   p->cap_MU = p->cap_MUBAR = p->cap_part_x = p->cap_xred = 0;
+  p->d_stage = nullptr; p->cap_stage = 0; p->h_pre = nullptr;
   p->d_part_stream = p->d_part_mlp = p->d_out = p->d_red = nullptr;
   p->d_grad = nullptr; p->h_out = nullptr; p->h_grad = nullptr;
   p->const_nly = 0; p->anomalies = 0;
@@ -243,6 +246,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   CRE(cudaMalloc(&p->d_grad, p->es * (size_t)nphi));
   CRE(cudaMallocHost(&p->h_out, sizeof(double) * (size_t)(nphi + 8)));
   CRE(cudaMallocHost(&p->h_grad, p->es * (size_t)nphi));
+  CRE(cudaMallocHost(&p->h_pre, sizeof(double) * (size_t)2 * p->sm_count * 8 * 8));
 #undef CRE
   *out = p;
   return HVI_OK;
@@ -253,10 +257,11 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   cudaSetDevice(p->desc.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   void* dev[] = {p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
-                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred};
+                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
   if (p->h_grad) cudaFreeHost(p->h_grad);
+  if (p->h_pre) cudaFreeHost(p->h_pre);
   for (auto& e_ : p->ev) if (e_) cudaEventDestroy(e_);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
@@ -324,6 +329,8 @@ static cudaError_t copy_in(void* dst, const void* src, size_t bytes, int mem_kin
   return cudaMemcpyAsync(dst, src, bytes, mem_kind == HVI_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
 }
 
+static int ensure(hvi_plan* p, void** buf, int64_t* cap, int64_t need_bytes);
+
 template <typename T>
 static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, const void* y_o, const void* y_unc,
                       int mem_kind) {
@@ -340,11 +347,11 @@ static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, c
   }
   CU(p, copy_in(p->d_xM, xM, sizeof(T) * (size_t)nC * nb, mem_kind, p->stream));
   const T *dxP = (const T*)xP, *dyo = (const T*)y_o, *dyu = (const T*)y_unc;
-  void* tmp = nullptr;
   if (mem_kind == HVI_MEM_HOST) {
     const size_t n1 = (size_t)2 * nO * nb, n2 = (size_t)nO * nb;
-    CU(p, cudaMalloc(&tmp, sizeof(T) * (n1 + 2 * n2)));
-    T* t = (T*)tmp;
+    int rc = ensure(p, &p->d_stage, &p->cap_stage, (int64_t)(sizeof(T) * (n1 + 2 * n2)));
+    if (rc) return rc;
+    T* t = (T*)p->d_stage;
     CU(p, copy_in(t, xP, sizeof(T) * n1, mem_kind, p->stream));
     CU(p, copy_in(t + n1, y_o, sizeof(T) * n2, mem_kind, p->stream));
     CU(p, copy_in(t + n1 + n2, y_unc, sizeof(T) * n2, mem_kind, p->stream));
@@ -356,12 +363,10 @@ static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, c
   const int NACC = nacc(p->cf.nP, p->cf.nM);
   if ((size_t)2 * p->sm_count * 8 * 8 > (size_t)p->max_rows * NACC) PLAN_FAIL(p, HVI_EINVAL, "internal: scratch too small");
   CU(p, launch_preprocess<T>(L, nO, nb, dxP, dyo, dyu, (T*)p->d_rec, p->d_part_stream, &nrows));
-  std::vector<double> h((size_t)2 * nrows);
-  CU(p, cudaMemcpyAsync(h.data(), p->d_part_stream, sizeof(double) * 2 * nrows, cudaMemcpyDeviceToHost, p->stream));
+  CU(p, cudaMemcpyAsync(p->h_pre, p->d_part_stream, sizeof(double) * 2 * nrows, cudaMemcpyDeviceToHost, p->stream));
   CU(p, cudaStreamSynchronize(p->stream));
-  if (tmp) cudaFree(tmp);
   double c = 0, an = 0;
-  for (int r = 0; r < nrows; r++) { c += h[2 * r]; an += h[2 * r + 1]; }
+  for (int r = 0; r < nrows; r++) { c += p->h_pre[2 * r]; an += p->h_pre[2 * r + 1]; }
   p->const_nly = c;
   p->anomalies = (int64_t)an;
   return HVI_OK;
@@ -393,7 +398,7 @@ template <> const Cfg<double>& cfg_of<double>(const hvi_plan* p) { return p->cd;
 // enqueue the whole evaluation on `s`; all pointers are device pointers
 template <typename T>
 static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* zMs, double* out, T* grad_T,
-                        cudaStream_t s) {
+                        cudaStream_t s, bool rng = false, uint64_t seed = 0, int64_t site_offset = 0) {
   const Cfg<T>& cfg = cfg_of<T>(p);
   int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)(sizeof(T) * pdraw_elems(cfg.nP, M)));
   if (rc) return rc;
@@ -426,7 +431,8 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   a.pd = pdraw + (((size_t)4 * (cfg.nP > 0 ? cfg.nP : 1) * M + 3) & ~(size_t)3); a.pd_in_smem = 0;
   a.ec = ec; a.mubar = (T*)p->d_mubar; a.partials = p->d_part_stream; a.nb = p->nb; a.M = M;
   a.MU = pbm ? (const T*)p->d_MU : nullptr; a.MUBAR = pbm ? (T*)p->d_MUBAR : nullptr;
-  a.staged = (M % (16 / (int)sizeof(T)) == 0) && (((uintptr_t)zMs & 15) == 0);
+  a.staged = !rng && (M % (16 / (int)sizeof(T)) == 0) && (((uintptr_t)zMs & 15) == 0);
+  a.rng = rng ? 1 : 0; a.seed = seed; a.col_offset = site_offset * cfg.nM;
   int nrows = 0, nblk = 0, nblk2 = 0;
   CU(p, launch_stream<T>(L, cfg, a, &nrows, p->max_rows));
   MARK();
@@ -462,21 +468,24 @@ static int eval_sync_t(hvi_plan* p, int M, const void* phi, const void* zP, cons
   if (use_rng || mem_kind == HVI_MEM_HOST) {
     int rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)sizeof(T) * nzP);
     if (rc) return rc;
-    rc = ensure(p, &p->d_zMs, &p->cap_zMs, (int64_t)sizeof(T) * nzM);
-    if (rc) return rc;
     if (use_rng) {
+      // global-block draws: columns keyed far above any site column; the site draws are generated
+      // inside the streaming kernel from the same (seed, column, draw) keys
       Launch L{s, p->sm_count, &p->launches};
-      // global-block draws: columns keyed far above any site column
       CU(p, launch_gen_normal<T>(L, (T*)p->d_zP, cfg.nP, M, seed, (int64_t)1 << 62));
-      CU(p, launch_gen_normal<T>(L, (T*)p->d_zMs, (int64_t)cfg.nM * p->nb, M, seed, site_offset * cfg.nM));
+      dzM = nullptr;
     } else {
+      rc = ensure(p, &p->d_zMs, &p->cap_zMs, (int64_t)sizeof(T) * nzM);
+      if (rc) return rc;
       if (cfg.nP > 0) CU(p, cudaMemcpyAsync(p->d_zP, zP, sizeof(T) * (size_t)M * cfg.nP, cudaMemcpyHostToDevice, s));
       CU(p, cudaMemcpyAsync(p->d_zMs, zMs, sizeof(T) * (size_t)nzM, cudaMemcpyHostToDevice, s));
+      dzM = (const T*)p->d_zMs;
     }
-    dzP = (const T*)p->d_zP; dzM = (const T*)p->d_zMs;
+    dzP = (const T*)p->d_zP;
   }
   const bool want_grad = grad != nullptr;
-  int rc = enqueue_eval<T>(p, M, dphi, dzP, dzM, p->d_out, want_grad ? (T*)p->d_grad : nullptr, s);
+  int rc = enqueue_eval<T>(p, M, dphi, dzP, dzM, p->d_out, want_grad ? (T*)p->d_grad : nullptr, s, use_rng, seed,
+                           site_offset);
   if (rc) return rc;
   CU(p, cudaMemcpyAsync(p->h_out + nphi, p->d_out + nphi, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
   if (want_grad) {
@@ -530,18 +539,16 @@ static int eval_async_t(hvi_plan* p, int M, const void* phi, const void* zP, con
                         int64_t site_offset, double* out, cudaStream_t s) {
   const Cfg<T>& cfg = cfg_of<T>(p);
   const T *dzP = (const T*)zP, *dzM = (const T*)zMs;
-  if (!zMs) {
-    const int64_t nzP = (int64_t)M * (cfg.nP > 0 ? cfg.nP : 1), nzM = (int64_t)M * cfg.nM * p->nb;
+  const bool rng = (zMs == nullptr);
+  if (rng) {
+    const int64_t nzP = (int64_t)M * (cfg.nP > 0 ? cfg.nP : 1);
     int rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)sizeof(T) * nzP);
-    if (rc) return rc;
-    rc = ensure(p, &p->d_zMs, &p->cap_zMs, (int64_t)sizeof(T) * nzM);
     if (rc) return rc;
     Launch L{s, p->sm_count, &p->launches};
     CU(p, launch_gen_normal<T>(L, (T*)p->d_zP, cfg.nP, M, seed, (int64_t)1 << 62));
-    CU(p, launch_gen_normal<T>(L, (T*)p->d_zMs, (int64_t)cfg.nM * p->nb, M, seed, site_offset * cfg.nM));
-    dzP = (const T*)p->d_zP; dzM = (const T*)p->d_zMs;
+    dzP = (const T*)p->d_zP;
   }
-  return enqueue_eval<T>(p, M, (const T*)phi, dzP, dzM, out, nullptr, s);
+  return enqueue_eval<T>(p, M, (const T*)phi, dzP, dzM, out, nullptr, s, rng, seed, site_offset);
 }
 
 extern "C" int hvi_neg_elbo_grad_async(hvi_plan* p, int32_t n_MC, const void* phi_dev, const void* zP_dev,
@@ -638,4 +645,29 @@ extern "C" int hvi_apply_g(hvi_plan* p, const void* phi, int mem_kind, void* mu_
   if (rc) return rc;
   if (!mu_zeta) PLAN_FAIL(p, HVI_EINVAL, "mu_zeta is NULL");
   return p->dtype == HVI_F32 ? apply_g_t<float>(p, phi, mem_kind, mu_zeta) : apply_g_t<double>(p, phi, mem_kind, mu_zeta);
+}
+
+template <typename T>
+static int randn_t(hvi_plan* p, int M, int64_t n_cols, uint64_t seed, int64_t col_offset, int mem_kind, void* out) {
+  cudaStream_t s = p->stream;
+  Launch L{s, p->sm_count, &p->launches};
+  const size_t bytes = sizeof(T) * (size_t)M * n_cols;
+  void* tmp = nullptr;
+  T* dst = (T*)out;
+  if (mem_kind == HVI_MEM_HOST) { CU(p, cudaMalloc(&tmp, bytes)); dst = (T*)tmp; }
+  cudaError_t e = launch_gen_normal<T>(L, dst, n_cols, M, seed, col_offset);
+  if (e == cudaSuccess && tmp) e = cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (tmp) cudaFree(tmp);
+  if (e != cudaSuccess) PLAN_FAIL(p, HVI_ECUDA, "hvi_randn: %s", cudaGetErrorString(e));
+  return HVI_OK;
+}
+
+extern "C" int hvi_randn(hvi_plan* p, int32_t n_MC, int64_t n_cols, uint64_t seed, int64_t col_offset, int mem_kind,
+                         void* out) {
+  if (!p) return HVI_EINVAL;
+  if (n_MC < 1 || n_cols < 1 || !out) PLAN_FAIL(p, HVI_EINVAL, "hvi_randn: bad arguments");
+  CU(p, cudaSetDevice(p->desc.device));
+  return p->dtype == HVI_F32 ? randn_t<float>(p, n_MC, n_cols, seed, col_offset, mem_kind, out)
+                             : randn_t<double>(p, n_MC, n_cols, seed, col_offset, mem_kind, out);
 }

@@ -67,6 +67,9 @@ struct StreamArgs {
   int64_t nb;
   int M;
   int pd_in_smem;    // 1: the kernel copies pd into shared memory (it fits)
+  int rng;           // 1: draw ξ inside the kernel from (seed, col_offset + site·n_θM + k, draw); zMs unused
+  uint64_t seed;
+  int64_t col_offset;
   int staged;        // 1: M % (16/sizeof(T)) == 0 and zMs 16-byte aligned → cp.async staging
 };
 

@@ -51,6 +51,36 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&o)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+
+// four standard normals of column gcol (= global site·n_θM + k), draws 4·m4 … 4·m4+3:
+// Philox4x32-10 keyed by the seed, Box-Muller on the MUFU pipe
+__device__ __forceinline__ void normal4(uint64_t seed, uint64_t gcol, int m4, float (&n4)[4]) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)gcol, (uint32_t)(gcol >> 32), (uint32_t)m4, 0x5eedu, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const float u1 = ((float)(r[2 * h] >> 8) + 1.0f) * 5.9604644775390625e-08f;   // (0, 1], 24 bits
+    const float u2 = (float)(r[2 * h + 1] >> 8) * 5.9604644775390625e-08f;        // [0, 1)
+    const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));                    // sqrt(−2 ln u1)
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &sn, &cs);             // argument in [−π, π)
+    n4[2 * h] = rad * cs; n4[2 * h + 1] = rad * sn;
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
@@ -948,7 +978,7 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, 
 
 constexpr int STREAM_THREADS_MAX = 256;
 
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM>
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool RNG>
 __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_constant__ Cfg<T> cfg,
                                                                  const __grid_constant__ StreamArgs<T> a) {
   constexpr int CH = 16 / sizeof(T);  // elements per 16-byte chunk
@@ -1021,13 +1051,16 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
     st.prior = st.lj = st.u2 = st.ljln = T(0);
     st.nly2 = mk2(T(0), T(0));
 
-    if (staged) {
-      // two half-row stages (MCS draws each) in flight: the next stage's cp.async is issued before
-      // the current one is consumed
+    // three sources of the draws ξ of this tile, one copy of the per-draw code:
+    //   mode 1: cp.async staging through shared memory (two half-row stages of MCS draws in flight)
+    //   mode 2: generated in registers (Philox + Box-Muller), no memory traffic at all
+    //   mode 0: direct global loads (n_MC not a multiple of the 16-byte chunk)
+    {
       constexpr int MCS = MC / 2, QS = 4;
+      const int mode = RNG ? 2 : (staged ? 1 : 0);
       const T* gz = a.zMs + (size_t)tile * 32 * NM * M;  // row r of the tile at gz + r*M
       const int rows_valid = (int)(a.nb - tile * 32 < 32 ? a.nb - tile * 32 : 32) * NM;
-      const int nst = (M + MCS - 1) / MCS;
+      const int nst = mode == 1 ? (M + MCS - 1) / MCS : 1;
       auto issue = [&](int st_) {
         const int m0 = st_ * MCS;
         const int nch = ((M - m0) < MCS ? (M - m0) : MCS) / CH;
@@ -1041,36 +1074,53 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
         }
         cp_async_commit();
       };
-      __syncwarp();
-      issue(0);
+      if (mode == 1) { __syncwarp(); issue(0); }
       for (int st_ = 0; st_ < nst; st_++) {
-        if (st_ + 1 < nst) { issue(st_ + 1); cp_async_wait_group<1>(); }
-        else cp_async_wait_group<0>();
-        __syncwarp();
-        const int m0 = st_ * MCS;
-        const int nch = ((M - m0) < MCS ? (M - m0) : MCS) / CH;
+        if (mode == 1) {
+          if (st_ + 1 < nst) { issue(st_ + 1); cp_async_wait_group<1>(); }
+          else cp_async_wait_group<0>();
+          __syncwarp();
+        }
+        const int m0 = mode == 1 ? st_ * MCS : 0;
+        const int nd = mode == 1 ? ((M - m0) < MCS ? (M - m0) : MCS) : M;   // draws of this stage
         const T* buf = ztile + (st_ & 1) * (32 * NM * MCS);
         if (active) {
-          for (int q = 0; q < nch; q++) {
+          const int nfull = nd / CH;
+          for (int q = 0; q < nfull; q++) {   // full chunks of CH draws, no guards
+            const int mq = m0 + q * CH;
             T zc[NM][CH];
+            if (mode == 1) {
 #pragma unroll
-            for (int k = 0; k < NM; k++) {
-              const T* src = buf + (lane * NM + k) * MCS + ((q + lane) & 3) * CH;
-              if constexpr (sizeof(T) == 4) {
-                const float4 v = *reinterpret_cast<const float4*>(src);
-                zc[k][0] = v.x; zc[k][1] = v.y; zc[k][2] = v.z; zc[k][3] = v.w;
-              } else {
-                const double2 v = *reinterpret_cast<const double2*>(src);
-                zc[k][0] = v.x; zc[k][1] = v.y;
+              for (int k = 0; k < NM; k++) {
+                const T* src = buf + (lane * NM + k) * MCS + ((q + lane) & 3) * CH;
+                if constexpr (sizeof(T) == 4) {
+                  const float4 v = *reinterpret_cast<const float4*>(src);
+                  zc[k][0] = v.x; zc[k][1] = v.y; zc[k][2] = v.z; zc[k][3] = v.w;
+                } else {
+                  const double2 v = *reinterpret_cast<const double2*>(src);
+                  zc[k][0] = v.x; zc[k][1] = v.y;
+                }
               }
+            } else if (mode == 2) {
+#pragma unroll
+              for (int k = 0; k < NM; k++) {
+                float n4[4];
+                normal4(a.seed, (uint64_t)(a.col_offset + site * NM + k), mq / 4, n4);
+#pragma unroll
+                for (int d = 0; d < CH; d++) zc[k][d] = (T)n4[(mq % 4) + d];
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < NM; k++)
+#pragma unroll
+                for (int d = 0; d < CH; d++) zc[k][d] = a.zMs[((size_t)site * NM + k) * M + mq + d];
             }
-            const T* pd = pdbase + (size_t)(m0 + q * CH) * PD;
+            const T* pd = pdbase + (size_t)mq * PD;
             T mud[CH][NM];
 #pragma unroll
             for (int d = 0; d < CH; d++)
 #pragma unroll
-              for (int k = 0; k < NM; k++)
-                mud[d][k] = PBM ? a.MU[((size_t)(m0 + q * CH + d) * NM + k) * a.nb + site] : st.mu[k];
+              for (int k = 0; k < NM; k++) mud[d][k] = PBM ? a.MU[((size_t)(mq + d) * NM + k) * a.nb + site] : st.mu[k];
 #pragma unroll
             for (int d = 0; d < CH; d++) {
               T z[NM], zb[NM];
@@ -1079,26 +1129,33 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
               do_draw<TR, T, NP, NM, NO>(cfg, st, z, pd + d * PD, mud[d], zb);
               if constexpr (PBM) {
 #pragma unroll
-                for (int k = 0; k < NM; k++) a.MUBAR[((size_t)(m0 + q * CH + d) * NM + k) * a.nb + site] = wM * zb[k];
+                for (int k = 0; k < NM; k++) a.MUBAR[((size_t)(mq + d) * NM + k) * a.nb + site] = wM * zb[k];
               }
             }
           }
-        }
-        __syncwarp();
-      }
-    } else if (active) {
-      for (int m = 0; m < M; m++) {
-        T z[NM], zb[NM], mud[NM];
+          // remaining draws (n_MC not a multiple of the chunk; never in mode 1), one at a time
+#pragma unroll 1
+          for (int m = m0 + nfull * CH; m < m0 + nd; m++) {
+            T z[NM], zb[NM], mud[NM];
 #pragma unroll
-        for (int k = 0; k < NM; k++) {
-          z[k] = a.zMs[((size_t)site * NM + k) * M + m];
-          mud[k] = PBM ? a.MU[((size_t)m * NM + k) * a.nb + site] : st.mu[k];
-        }
-        do_draw<TR, T, NP, NM, NO>(cfg, st, z, pdbase + (size_t)m * PD, mud, zb);
-        if constexpr (PBM) {
+            for (int k = 0; k < NM; k++) {
+              if (mode == 2) {
+                float n4[4];
+                normal4(a.seed, (uint64_t)(a.col_offset + site * NM + k), m / 4, n4);
+                z[k] = (T)(m % 4 == 0 ? n4[0] : m % 4 == 1 ? n4[1] : m % 4 == 2 ? n4[2] : n4[3]);
+              } else {
+                z[k] = a.zMs[((size_t)site * NM + k) * M + m];
+              }
+              mud[k] = PBM ? a.MU[((size_t)m * NM + k) * a.nb + site] : st.mu[k];
+            }
+            do_draw<TR, T, NP, NM, NO>(cfg, st, z, pdbase + (size_t)m * PD, mud, zb);
+            if constexpr (PBM) {
 #pragma unroll
-          for (int k = 0; k < NM; k++) a.MUBAR[((size_t)m * NM + k) * a.nb + site] = wM * zb[k];
+              for (int k = 0; k < NM; k++) a.MUBAR[((size_t)m * NM + k) * a.nb + site] = wM * zb[k];
+            }
+          }
         }
+        if (mode == 1) __syncwarp();
       }
     }
 
@@ -1401,19 +1458,6 @@ __global__ void k_cast_grad(int n, const double* __restrict__ out, T* __restrict
 // (seed; global column, draw/4): independent of the sharding.  Stands in for CUDA.randn
 // (ext/HybridVariationalInferenceCUDAExt.jl:82-86).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                                              uint32_t (&o)[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; r++) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256) k_gen_normal(T* __restrict__ z, int64_t n_cols, int M, uint64_t seed,
                                                     int64_t col_offset) {
@@ -1423,18 +1467,8 @@ __global__ void __launch_bounds__(256) k_gen_normal(T* __restrict__ z, int64_t n
     const int64_t col = e / M4;
     const int m4 = (int)(e % M4);
     const uint64_t gcol = (uint64_t)(col + col_offset);
-    uint32_t r[4];
-    philox4x32_10((uint32_t)gcol, (uint32_t)(gcol >> 32), (uint32_t)m4, 0x5eedu, (uint32_t)seed, (uint32_t)(seed >> 32), r);
     float n4[4];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const float u1 = ((float)r[2 * h] + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
-      const float u2 = (float)r[2 * h + 1] * 2.3283064365386963e-10f;
-      const float rad = sqrtf(-2.0f * logf(u1));
-      float sn, cs;
-      sincospif(2.0f * u2, &sn, &cs);
-      n4[2 * h] = rad * cs; n4[2 * h + 1] = rad * sn;
-    }
+    normal4(seed, gcol, m4, n4);
     for (int d = 0; d < 4; d++) {
       const int m = m4 * 4 + d;
       if (m < M) z[(size_t)col * M + m] = (T)n4[d];
@@ -1592,14 +1626,14 @@ cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, con
   return cudaSuccess;
 }
 
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM>
-static cudaError_t launch_stream_cfg(const Launch& L, const Cfg<T>& cfg, StreamArgs<T> a, int* nrows_out, int nrows_max) {
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool RNG>
+static cudaError_t launch_stream_cfg2(const Launch& L, const Cfg<T>& cfg, StreamArgs<T> a, int* nrows_out, int nrows_max) {
   constexpr int CH = 16 / sizeof(T), MC = 8 * CH, NWARP = STREAM_THREADS / 32;
   const size_t pd_bytes = (size_t)a.M * pd_stride(NP) * sizeof(T);
   a.pd_in_smem = (NP > 0 && pd_bytes <= 16 * 1024) ? 1 : 0;
   const size_t smem = (size_t)NWARP * 32 * NM * MC * sizeof(T) + (size_t)NWARP * nacc(NP, NM) * sizeof(double) +
                       (a.pd_in_smem ? pd_bytes : 0) + 16;
-  auto kern = k_stream<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM>;
+  auto kern = k_stream<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, RNG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -1615,6 +1649,12 @@ static cudaError_t launch_stream_cfg(const Launch& L, const Cfg<T>& cfg, StreamA
   HVI_LAUNCH_CHECK();
   *nrows_out = (int)blocks;
   return cudaSuccess;
+}
+
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM>
+static cudaError_t launch_stream_cfg(const Launch& L, const Cfg<T>& cfg, StreamArgs<T> a, int* nrows_out, int nrows_max) {
+  if (a.rng) return launch_stream_cfg2<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, true>(L, cfg, a, nrows_out, nrows_max);
+  return launch_stream_cfg2<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, false>(L, cfg, a, nrows_out, nrows_max);
 }
 
 // launch shape: Float32 runs 2 blocks of 256 threads per SM (128 registers), Float64 one block of

@@ -188,6 +188,13 @@ class NegElboPlan:
                                                _ptr(ζP), _ptr(ζMs), _ptr(σ)))
         return ζP, ζMs, σ
 
+    def randn(self, n_MC: int, n_cols: int, seed: int, col_offset: int = 0):
+        """The device generator's draws (n_MC × n_cols), column = global site·n_θM + k -- what
+        `neg_elbo_withgradient(seed=…)` uses (stand-in for CUDA.randn)."""
+        out = np.empty((n_MC, n_cols), dtype=self.dt, order="F")
+        self._check(self.lib.hvi_randn(self._h, n_MC, n_cols, seed, col_offset, A.HVI_MEM_HOST, _ptr(out)))
+        return out
+
     def apply_g(self, ϕ):
         """g(xM, ϕg) → μ_ζMs (n_θM × n_site) (src/ModelApplicator.jl:19-23,163-176)."""
         ϕ_ = np.ascontiguousarray(ϕ, dtype=self.dt)

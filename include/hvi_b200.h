@@ -160,6 +160,12 @@ int hvi_generate_zeta(hvi_plan* plan, int32_t n_MC, const void* phi, const void*
 /* g(xM, ϕg) alone (src/ModelApplicator.jl:19-23,163-176): mu_zeta (n_M x n_site). */
 int hvi_apply_g(hvi_plan* plan, const void* phi, int mem_kind, void* mu_zeta);
 
+/* The library's standard-normal generator on its own: out (n_MC x n_cols, column-major) filled with
+ * the draws of columns col_offset .. col_offset+n_cols (column = global site * n_M + k), exactly the
+ * values hvi_neg_elbo_grad_rng uses.  Stands in for CUDA.randn (ext/HybridVariationalInferenceCUDAExt.jl:82-86). */
+int hvi_randn(hvi_plan* plan, int32_t n_MC, int64_t n_cols, uint64_t seed, int64_t col_offset,
+              int mem_kind, void* out);
+
 /* number of kernels launched by this plan since creation (bench.py's gpu_launches) */
 int64_t hvi_launch_count(const hvi_plan* plan);
 
