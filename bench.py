@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--sites", type=int, default=10_000_000, help="sites per GPU")
     ap.add_argument("--n-mc", type=int, default=64)
     ap.add_argument("--scenario", default="", help="comma-separated DoubleMMCase scenario flags")
+    ap.add_argument("--nan-frac", type=float, default=0.0, help="fraction of sites with missing drivers (:driverNAN generalised)")
     ap.add_argument("--cpu-sample-sites", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -55,7 +56,7 @@ def parse():
 def workload_config(args, prob):
     return {"workload": f"DoubleMM (BASELINE config 4 shape) {args.sites:.0e} sites/GPU x n_MC={args.n_mc}, "
                         f"scenario=({args.scenario}), MLP {'-'.join(str(l[0]) for l in prob.layers)}-{prob.layers[-1][1]}",
-            "sites_per_gpu": args.sites, "n_MC": args.n_mc, "n_phi": prob.n_phi,
+            "sites_per_gpu": args.sites, "n_MC": args.n_mc, "n_phi": prob.n_phi, "nan_frac": args.nan_frac,
             "parallelism": f"site-sharded x{args.gpus}, allreduce of [grad; components]",
             "l2": "inputs (>= 600 B/site x sites) exceed the 126 MB L2; no flush needed"}
 
@@ -156,7 +157,7 @@ def main():
     prob = hvi_b200.DoubleMMCase(tuple(s for s in args.scenario.split(",") if s), dtype="f32")
     nb, M = args.sites, args.n_mc
     # synthetic batch of this rank's site shard (generator restates gen_hybridproblem_synthetic)
-    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=111 + rank)
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=111 + rank, driver_nan_frac=args.nan_frac)
     ϕ = prob.init_ϕ(perturbed=True)
     plan = hvi_b200.NegElboPlan(prob, device=local, count_globals=(rank == 0))
     pin = {k: torch.from_numpy(np.ascontiguousarray(data[k].T)).pin_memory() for k in ("xM", "xP", "y_o", "y_unc")}
@@ -216,7 +217,8 @@ def main():
     plan.set_profiling(False)
     kt = {k: float(np.mean(v)) for k, v in acc.items()}
     nO, nM = prob.n_obs, prob.n_M
-    alg_bytes = nb * (4 * 4 * nO + 2 * 4 * nM + 4 * nM * M)
+    # site records + μ_ζ/μ̄_ζ hand-off + ξ (+ per-draw means and their cotangents with pbm covariates)
+    alg_bytes = nb * (4 * 4 * nO + 2 * 4 * nM + 4 * nM * M + (2 * 4 * nM * M if prob.pbm_covars else 0))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -71,6 +71,7 @@ SYMBOLS = [
     ("hvi_neg_elbo_grad_rng", _INT, [_P, _I32, _P, _U64, _I64, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_async", _INT, [_P, _I32, _P, _P, _P, _U64, _I64, _P, _P]),
     ("hvi_generate_zeta", _INT, [_P, _I32, _P, _P, _P, _INT, _P, _P, _P]),
+    ("hvi_predict", _INT, [_P, _I32, _P, _P, _P, _U64, _I64, _INT, _P, _P, _P, _DP]),
     ("hvi_apply_g", _INT, [_P, _P, _INT, _P]),
     ("hvi_randn", _INT, [_P, _I32, _I64, _U64, _I64, _INT, _P]),
     ("hvi_launch_count", _I64, [_P]),

@@ -25,6 +25,8 @@ struct hvi_plan {
   // data
   int64_t nb;
   void *d_xM, *d_rec, *d_mu, *d_mubar;
+  void* d_xP;   // raw drivers (2 n_obs x nb), kept for the prediction path
+  int has_obs;
   double const_nly;
   int64_t anomalies;
   // per-evaluation scratch
@@ -208,7 +210,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   fill_cfg<float>(*desc, p->cf);
   fill_cfg<double>(*desc, p->cd);
   p->nb = 0; p->launches = 0;
-  p->d_xM = p->d_rec = p->d_mu = p->d_mubar = nullptr;
+  p->d_xM = p->d_rec = p->d_mu = p->d_mubar = nullptr; p->d_xP = nullptr; p->has_obs = 0;
   p->d_phi = p->d_zP = p->d_zMs = p->d_ec = p->d_pdraw = nullptr;
   p->cap_zP = p->cap_zMs = p->cap_pdraw = 0;
   p->d_MU = p->d_MUBAR = nullptr; p->d_part_x = p->d_xred = nullptr;
@@ -256,7 +258,7 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   if (!p) return HVI_OK;
   cudaSetDevice(p->desc.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
-  void* dev[] = {p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
+  void* dev[] = {p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
                  p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
@@ -336,26 +338,32 @@ static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, c
                       int mem_kind) {
   const int nO = p->desc.n_obs, nC = p->desc.n_covar, nM = p->desc.n_M;
   if (nb != p->nb) {
-    for (void** q : {&p->d_xM, &p->d_rec, &p->d_mu, &p->d_mubar}) { if (*q) cudaFree(*q); *q = nullptr; }
+    for (void** q : {&p->d_xM, &p->d_rec, &p->d_mu, &p->d_mubar, &p->d_xP}) { if (*q) cudaFree(*q); *q = nullptr; }
     p->nb = 0;
     const int64_t ntiles = (nb + 31) / 32;
     CU(p, cudaMalloc(&p->d_xM, sizeof(T) * (size_t)nC * nb));
     CU(p, cudaMalloc(&p->d_rec, sizeof(T) * (size_t)ntiles * 32 * 4 * nO));
     CU(p, cudaMalloc(&p->d_mu, sizeof(T) * (size_t)nM * nb));
     CU(p, cudaMalloc(&p->d_mubar, sizeof(T) * (size_t)nM * nb));
+    CU(p, cudaMalloc(&p->d_xP, sizeof(T) * (size_t)2 * nO * nb));
     p->nb = nb;
   }
   CU(p, copy_in(p->d_xM, xM, sizeof(T) * (size_t)nC * nb, mem_kind, p->stream));
   const T *dxP = (const T*)xP, *dyo = (const T*)y_o, *dyu = (const T*)y_unc;
-  if (mem_kind == HVI_MEM_HOST) {
+  {
     const size_t n1 = (size_t)2 * nO * nb, n2 = (size_t)nO * nb;
-    int rc = ensure(p, &p->d_stage, &p->cap_stage, (int64_t)(sizeof(T) * (n1 + 2 * n2)));
-    if (rc) return rc;
-    T* t = (T*)p->d_stage;
-    CU(p, copy_in(t, xP, sizeof(T) * n1, mem_kind, p->stream));
-    CU(p, copy_in(t + n1, y_o, sizeof(T) * n2, mem_kind, p->stream));
-    CU(p, copy_in(t + n1 + n2, y_unc, sizeof(T) * n2, mem_kind, p->stream));
-    dxP = t; dyo = t + n1; dyu = t + n1 + n2;
+    CU(p, copy_in(p->d_xP, xP, sizeof(T) * n1, mem_kind, p->stream));
+    dxP = (const T*)p->d_xP;
+    p->has_obs = (y_o && y_unc) ? 1 : 0;
+    if (mem_kind == HVI_MEM_HOST && p->has_obs) {
+      int rc = ensure(p, &p->d_stage, &p->cap_stage, (int64_t)(sizeof(T) * 2 * n2));
+      if (rc) return rc;
+      T* t = (T*)p->d_stage;
+      CU(p, copy_in(t, y_o, sizeof(T) * n2, mem_kind, p->stream));
+      CU(p, copy_in(t + n2, y_unc, sizeof(T) * n2, mem_kind, p->stream));
+      dyo = t; dyu = t + n2;
+    }
+    if (!p->has_obs) { dyo = nullptr; dyu = nullptr; }
   }
   Launch L{p->stream, p->sm_count, &p->launches};
   int nrows = 0;
@@ -375,7 +383,8 @@ static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, c
 extern "C" int hvi_plan_set_data(hvi_plan* p, int64_t n_site, const void* xM, const void* xP, const void* y_o,
                                  const void* y_unc, int mem_kind) {
   if (!p) return HVI_EINVAL;
-  if (n_site < 1 || !xM || !xP || !y_o || !y_unc) PLAN_FAIL(p, HVI_EINVAL, "set_data: n_site must be >= 1 and arrays non-NULL");
+  if (n_site < 1 || !xM || !xP) PLAN_FAIL(p, HVI_EINVAL, "set_data: n_site must be >= 1 and xM, xP non-NULL");
+  if ((y_o == nullptr) != (y_unc == nullptr)) PLAN_FAIL(p, HVI_EINVAL, "set_data: y_o and y_unc must both be given or both be NULL");
   if (mem_kind != HVI_MEM_HOST && mem_kind != HVI_MEM_DEVICE) PLAN_FAIL(p, HVI_EINVAL, "set_data: bad mem_kind");
   CU(p, cudaSetDevice(p->desc.device));
   return p->dtype == HVI_F32 ? set_data_t<float>(p, n_site, xM, xP, y_o, y_unc, mem_kind)
@@ -670,4 +679,94 @@ extern "C" int hvi_randn(hvi_plan* p, int32_t n_MC, int64_t n_cols, uint64_t see
   CU(p, cudaSetDevice(p->desc.device));
   return p->dtype == HVI_F32 ? randn_t<float>(p, n_MC, n_cols, seed, col_offset, mem_kind, out)
                              : randn_t<double>(p, n_MC, n_cols, seed, col_offset, mem_kind, out);
+}
+
+// predict_hvi (src/elbo.jl:320-352) = sample_posterior (:381-458) + the 3-D PBM applicator
+template <typename T>
+static int predict_t(hvi_plan* p, int M, const void* phi, const void* zP, const void* zMs, uint64_t seed,
+                     int64_t site_offset, int mem_kind, void* thetaP, void* thetaMs_tr, void* y, double* entropy) {
+  const Cfg<T>& cfg = cfg_of<T>(p);
+  cudaStream_t s = p->stream;
+  const int nphi = cfg.nphi, nP = cfg.nP, nM = cfg.nM, nO = cfg.nO;
+  const int64_t nb = p->nb;
+  const bool rng = (zMs == nullptr);
+  const size_t nzP = (size_t)M * (nP > 0 ? nP : 1), nzM = (size_t)M * nM * nb, ny = (size_t)nO * nb * M;
+  const T *dphi = (const T*)phi, *dzP = (const T*)zP, *dzM = (const T*)zMs;
+  Launch L{s, p->sm_count, &p->launches};
+  int rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)(sizeof(T) * nzP));
+  if (rc) return rc;
+  if (mem_kind == HVI_MEM_HOST) {
+    CU(p, cudaMemcpyAsync(p->d_phi, phi, sizeof(T) * nphi, cudaMemcpyHostToDevice, s));
+    dphi = (const T*)p->d_phi;
+  }
+  if (rng) {
+    CU(p, launch_gen_normal<T>(L, (T*)p->d_zP, nP, M, seed, (int64_t)1 << 62));
+    dzP = (const T*)p->d_zP;
+  } else if (mem_kind == HVI_MEM_HOST) {
+    rc = ensure(p, &p->d_zMs, &p->cap_zMs, (int64_t)(sizeof(T) * nzM));
+    if (rc) return rc;
+    if (nP > 0) CU(p, cudaMemcpyAsync(p->d_zP, zP, sizeof(T) * (size_t)M * nP, cudaMemcpyHostToDevice, s));
+    CU(p, cudaMemcpyAsync(p->d_zMs, zMs, sizeof(T) * nzM, cudaMemcpyHostToDevice, s));
+    dzP = (const T*)p->d_zP; dzM = (const T*)p->d_zMs;
+  }
+  rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)(sizeof(T) * pdraw_elems(nP, M)));
+  if (rc) return rc;
+  void *o1 = thetaP, *o2 = thetaMs_tr, *o3 = y, *tmp = nullptr;
+  if (mem_kind == HVI_MEM_HOST) {
+    CU(p, cudaMalloc(&tmp, sizeof(T) * ((size_t)nP * M + nzM + ny)));
+    o1 = tmp; o2 = (T*)tmp + (size_t)nP * M; o3 = (T*)o2 + nzM;
+  }
+  const int64_t nth = nb > (int64_t)nP * M ? nb : (int64_t)nP * M;
+  double* d_ls = nullptr;
+  const size_t nls = (size_t)((nth + 255) / 256) * 8;
+  cudaError_t e = cudaMalloc((void**)&d_ls, sizeof(double) * nls);
+  EvalConsts<T>* ec = (EvalConsts<T>*)p->d_ec;
+  T* pdraw = (T*)p->d_pdraw;
+  StreamArgs<T> a;
+  memset(&a, 0, sizeof a);
+  a.mu = (const T*)p->d_mu; a.zMs = dzM; a.ec = ec; a.nb = nb; a.M = M;
+  a.rng = rng ? 1 : 0; a.seed = seed; a.col_offset = site_offset * nM;
+  if (e == cudaSuccess && cfg.npc > 0) {
+    rc = ensure(p, &p->d_MU, &p->cap_MU, (int64_t)sizeof(T) * M * nM * nb);
+    if (rc) { if (tmp) cudaFree(tmp); cudaFree(d_ls); return rc; }
+    a.MU = (const T*)p->d_MU;
+  }
+  int nparts = 0;
+  if (e == cudaSuccess) e = launch_prologue<T>(L, cfg, dphi, dzP, M, ec, pdraw);
+  if (e == cudaSuccess) e = launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, nb, (T*)p->d_mu);
+  if (e == cudaSuccess && cfg.npc > 0)
+    e = launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, nb, (T*)p->d_MU, M, pdraw + (size_t)nP * M);
+  if (e == cudaSuccess) e = launch_predict<T>(L, cfg, a, pdraw, (const T*)p->d_xP, (T*)o1, (T*)o2, (T*)o3, d_ls, &nparts);
+  std::vector<double> hls(nparts > 0 ? nparts : 1);
+  std::vector<T> hq(nphi);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hls.data(), d_ls, sizeof(double) * nparts, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hq.data(), dphi, sizeof(T) * nphi, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && mem_kind == HVI_MEM_HOST) {
+    if (nP > 0) e = cudaMemcpyAsync(thetaP, o1, sizeof(T) * (size_t)nP * M, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(thetaMs_tr, o2, sizeof(T) * nzM, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(y, o3, sizeof(T) * ny, cudaMemcpyDeviceToHost, s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (tmp) cudaFree(tmp);
+  if (d_ls) cudaFree(d_ls);
+  if (e != cudaSuccess) PLAN_FAIL(p, HVI_ECUDA, "hvi_predict: %s", cudaGetErrorString(e));
+  if (entropy) {
+    // entropy_MvNormal(length(σ), 2 Σ log σ)  (src/elbo.jl:449-450, src/logden_normal.jl:74)
+    double logsig = 0;
+    for (int i = 0; i < nparts; i++) logsig += hls[i];
+    for (int j = 0; j < nP; j++) logsig += 0.5 * (double)hq[cfg.o_ls2P + j];
+    *entropy = 0.5 * ((double)nP + (double)nM * (double)nb) * 2.8378770664093454836 + logsig;
+  }
+  return HVI_OK;
+}
+
+extern "C" int hvi_predict(hvi_plan* p, int32_t n_sample, const void* phi, const void* zP, const void* zMs, uint64_t seed,
+                           int64_t site_offset, int mem_kind, void* thetaP, void* thetaMs_tr, void* y, double* entropy) {
+  int rc = check_eval_args(p, n_sample, phi, mem_kind);
+  if (rc) return rc;
+  if (!thetaMs_tr || !y || (p->desc.n_P > 0 && !thetaP)) PLAN_FAIL(p, HVI_EINVAL, "hvi_predict: NULL output");
+  if (zMs && p->desc.n_P > 0 && !zP) PLAN_FAIL(p, HVI_EINVAL, "hvi_predict: zP is NULL");
+  return p->dtype == HVI_F32
+             ? predict_t<float>(p, n_sample, phi, zP, zMs, seed, site_offset, mem_kind, thetaP, thetaMs_tr, y, entropy)
+             : predict_t<double>(p, n_sample, phi, zP, zMs, seed, site_offset, mem_kind, thetaP, thetaMs_tr, y, entropy);
 }

@@ -109,6 +109,9 @@ cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const Strea
                                  T* zetaMs_tr, T* sigma);
 __host__ __device__ constexpr int pd_stride(int nP) { return ((3 * nP + 3) / 4) * 4; }
 inline size_t pdraw_elems(int nP, int M) { return (size_t)4 * (nP > 0 ? nP : 1) * M + (size_t)M * pd_stride(nP) + 4; }
+template <typename T>
+cudaError_t launch_predict(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, const T* pdraw, const T* xP,
+                           T* thetaP, T* thetaMs_tr, T* y, double* part_logsig /*[sm_count*16*8]*/, int* nparts);
 int stream_max_rows(int sm_count);
 int mlp_bwd_max_blocks(int sm_count);
 bool stream_supported(int nP, int nM, int nO);

@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(256) k_preprocess(int nO, int64_t nb, const T*
       T s1 = T(1), s2 = T(1), yo = T(0), w = T(0);
       if (site < nb) {
         const T a = xP[site * 2 * nO + o], b = xP[site * 2 * nO + nO + o];
-        const T y = y_o[site * nO + o], u = y_unc[site * nO + o];
+        // prediction-only batches carry no observations (y_o == NULL): every entry counts as missing
+        const T y = y_o ? y_o[site * nO + o] : T(NAN), u = y_unc ? y_unc[site * nO + o] : T(0);
         const bool valid = isfinite(a) && isfinite(b);
         const bool obs = !isnan(y);
         if (valid) { s1 = a; s2 = b; }
@@ -1506,6 +1507,99 @@ __global__ void __launch_bounds__(256) k_generate_zeta(const __grid_constant__ C
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------
+// predict_hvi / sample_posterior forward path (src/elbo.jl:320-458; transform_ζs :815-835; 3-D PBM
+// applicator src/PBMApplicator.jl:51-57): for every posterior sample m and site i
+//   θsMs_tr[i,k,m] = T_k(ζMs[i,k,m]),  y[o,i,m] = f_doubleMM(θP_m, θMs_{i,m}, xP[:,i]),
+// no clamp (transform_ζs applies none), NaN where a driver is not finite.  One thread per site,
+// writes coalesced over sites; output-bandwidth bound (4·(n_θM + n_obs) bytes per site·sample).
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T transform_only(int tr, T zeta) {
+  if (tr == HVI_TR_EXP) return exp(zeta);
+  if (tr == HVI_TR_LOGISTIC) return T(1) / (T(1) + exp(-zeta));
+  return zeta;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_predict(const __grid_constant__ Cfg<T> cfg,
+                                                 const __grid_constant__ StreamArgs<T> a, const T* __restrict__ pdraw,
+                                                 const T* __restrict__ xP, T* __restrict__ thetaP,
+                                                 T* __restrict__ thetaMs_tr, T* __restrict__ y,
+                                                 double* __restrict__ part_logsig) {
+  const int nP = cfg.nP, nM = cfg.nM, nO = cfg.nO, M = a.M;
+  const EvalConsts<T>& ec = *a.ec;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const T* zetaP = pdraw + (size_t)nP * M;
+  if (gid < (int64_t)nP * M) {
+    const int j = (int)(gid / M), m = (int)(gid % M);
+    thetaP[j + (size_t)nP * m] = transform_only<T>(cfg.transP[j], zetaP[gid]);
+  }
+  double logsig = 0.0;
+  for (int64_t i = gid; i < a.nb; i += (int64_t)gridDim.x * blockDim.x) {
+    T mu[MAXP], sg[MAXP], S1[32], S2[32];
+    for (int k = 0; k < nM; k++) {
+      mu[k] = a.mu[i * nM + k];
+      const T ls = ec.coefA[k] + ec.coefB[k] * mu[k];
+      sg[k] = exp(T(0.5) * ls);
+      logsig += 0.5 * (double)ls;
+    }
+    for (int o = 0; o < nO; o++) { S1[o] = xP[i * 2 * nO + o]; S2[o] = xP[i * 2 * nO + nO + o]; }
+    for (int m = 0; m < M; m++) {
+      T th[MAXP], par[4];
+      for (int k = 0; k < nM; k++) {
+        T t = T(0);
+        for (int j = cfg.blkM_start[k]; j <= k; j++) {
+          T z;
+          if (a.rng) {
+            float n4[4];
+            normal4(a.seed, (uint64_t)(a.col_offset + i * nM + j), m / 4, n4);
+            z = (T)(m % 4 == 0 ? n4[0] : m % 4 == 1 ? n4[1] : m % 4 == 2 ? n4[2] : n4[3]);
+          } else {
+            z = a.zMs[((size_t)i * nM + j) * M + m];
+          }
+          t += ec.UM[j][k] * z;
+        }
+        const T mum = a.MU ? a.MU[((size_t)m * nM + k) * a.nb + i] : mu[k];
+        th[k] = transform_only<T>(cfg.transM[k], mum + sg[k] * t);
+        thetaMs_tr[i + a.nb * (k + (size_t)nM * m)] = th[k];
+      }
+      for (int s = 0; s < 4; s++) {
+        const int c = cfg.slot_code[s];
+        par[s] = c < 0 ? cfg.slot_fix[s] : c < nP ? transform_only<T>(cfg.transP[c], zetaP[(size_t)c * M + m]) : th[c - nP];
+      }
+      T* yo = y + (size_t)nO * (i + a.nb * (size_t)m);
+      for (int o = 0; o < nO; o++) {
+        // is_valid .* p: invalid drivers give NaN predictions (src/DoubleMM/f_doubleMM.jl:111-137)
+        const bool valid = isfinite(S1[o]) && isfinite(S2[o]);
+        yo[o] = valid ? par[0] + par[1] * S1[o] / (par[2] + S1[o]) * S2[o] / (par[3] + S2[o]) : T(NAN);
+      }
+    }
+  }
+  logsig = warp_sum(logsig);
+  if ((threadIdx.x & 31) == 0) part_logsig[gid >> 5] = logsig;
+}
+
+template <typename T>
+cudaError_t launch_predict(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, const T* pdraw, const T* xP,
+                           T* thetaP, T* thetaMs_tr, T* y, double* part_logsig, int* nparts) {
+  if (cfg.nO > 32) return cudaErrorInvalidConfiguration;
+  int64_t n = a.nb > (int64_t)cfg.nP * a.M ? a.nb : (int64_t)cfg.nP * a.M;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)L.sm_count * 16 && (int64_t)L.sm_count * 16 * 256 >= (int64_t)cfg.nP * a.M) blocks = (int64_t)L.sm_count * 16;
+  if (blocks < 1) blocks = 1;
+  k_predict<T><<<(int)blocks, 256, 0, L.stream>>>(cfg, a, pdraw, xP, thetaP, thetaMs_tr, y, part_logsig);
+  cudaError_t e_ = cudaGetLastError();
+  if (e_ != cudaSuccess) return e_;
+  if (L.counter) ++*L.counter;
+  *nparts = (int)blocks * 8;
+  return cudaSuccess;
+}
+template cudaError_t launch_predict<float>(const Launch&, const Cfg<float>&, const StreamArgs<float>&, const float*,
+                                           const float*, float*, float*, float*, double*, int*);
+template cudaError_t launch_predict<double>(const Launch&, const Cfg<double>&, const StreamArgs<double>&, const double*,
+                                            const double*, double*, double*, double*, double*, int*);
 
 // ---------------------------------------------------------------------------------------
 // launchers

@@ -116,7 +116,7 @@ class NegElboPlan:
         return dict(zip(("prologue", "mlp_fwd", "stream", "mlp_bwd", "finalize"), map(float, ms)))
 
     # -- data ----------------------------------------------------------------------------
-    def set_data(self, xM, xP, y_o, y_unc):
+    def set_data(self, xM, xP, y_o=None, y_unc=None):
         """Register one batch (xM, xP, y_o, y_unc) -- a DataLoader element of the reference
         (src/AbstractHybridProblem.jl:179-184).  numpy arrays (host) or CUDA tensors (device),
         column = site."""
@@ -125,11 +125,12 @@ class NegElboPlan:
             n_site = xM.shape[-1] if xM.dim() == 2 else xM.numel() // self.prob.n_covar
             args = (xM, xP, y_o, y_unc)
         else:
-            f = lambda a: np.asfortranarray(a, dtype=self.dt)
+            f = lambda a: None if a is None else np.asfortranarray(a, dtype=self.dt)
             args = tuple(map(f, (xM, xP, y_o, y_unc)))
             n_site = args[0].shape[1]
-            assert args[1].shape == (2 * self.prob.n_obs, n_site) and args[2].shape == (self.prob.n_obs, n_site)
-            assert args[3].shape == args[2].shape and args[0].shape[0] == self.prob.n_covar
+            assert args[1].shape == (2 * self.prob.n_obs, n_site) and args[0].shape[0] == self.prob.n_covar
+            if args[2] is not None:
+                assert args[2].shape == (self.prob.n_obs, n_site) and args[3].shape == args[2].shape
         self._keep = args
         self._check(self.lib.hvi_plan_set_data(self._h, n_site, *map(_ptr, args),
                                                A.HVI_MEM_DEVICE if dev else A.HVI_MEM_HOST))
@@ -187,6 +188,27 @@ class NegElboPlan:
         self._check(self.lib.hvi_generate_zeta(self._h, M, _ptr(ϕ_), _ptr(zP_), _ptr(zMs_), A.HVI_MEM_HOST,
                                                _ptr(ζP), _ptr(ζMs), _ptr(σ)))
         return ζP, ζMs, σ
+
+    def predict_hvi(self, ϕ, zP=None, zMs=None, *, n_sample_pred=200, seed=None, site_offset=0):
+        """predict_hvi (src/elbo.jl:320-352): returns (y, θsP, θsMs_tr, entropy_ζ) with
+        y (n_obs × n_site × n_sample), θsP (n_θP × n_sample), θsMs_tr (n_site × n_θM × n_sample)."""
+        ϕ_ = np.ascontiguousarray(ϕ, dtype=self.dt)
+        nP, nM, nb, nO = self.prob.n_P, self.prob.n_M, self.n_site, self.prob.n_obs
+        if zMs is not None:
+            zP_ = np.asfortranarray(zP, dtype=self.dt)
+            zMs_ = np.asfortranarray(zMs, dtype=self.dt)
+            M = zMs_.shape[0]
+        else:
+            assert seed is not None
+            zP_ = zMs_ = None
+            M = int(n_sample_pred)
+        θP = np.empty((nP, M), dtype=self.dt, order="F")
+        θMs = np.empty((nb, nM, M), dtype=self.dt, order="F")
+        y = np.empty((nO, nb, M), dtype=self.dt, order="F")
+        ent = C.c_double()
+        self._check(self.lib.hvi_predict(self._h, M, _ptr(ϕ_), _ptr(zP_), _ptr(zMs_), int(seed or 0), site_offset,
+                                         A.HVI_MEM_HOST, _ptr(θP), _ptr(θMs), _ptr(y), C.byref(ent)))
+        return y, θP, θMs, float(ent.value)
 
     def randn(self, n_MC: int, n_cols: int, seed: int, col_offset: int = 0):
         """The device generator's draws (n_MC × n_cols), column = global site·n_θM + k -- what

@@ -121,7 +121,8 @@ int64_t hvi_cor_count(const int32_t* cor_ends, int32_t n_cor_ends);
 /* ---- data --------------------------------------------------------------------------- */
 /* Register one batch (a DataLoader element (xM, xP, y_o, y_unc), src/AbstractHybridProblem.jl:
  * 179-184,206-207): xM (n_covar x n_site), xP (2 n_obs x n_site) rows S1;S2, y_o and y_unc
- * (n_obs x n_site).  The library copies and re-tiles the batch into its own HBM layout. */
+ * (n_obs x n_site).  The library copies and re-tiles the batch into its own HBM layout.
+ * y_o and y_unc may both be NULL (no observations: prediction only). */
 int hvi_plan_set_data(hvi_plan* plan, int64_t n_site, const void* xM, const void* xP,
                       const void* y_o, const void* y_unc, int mem_kind);
 
@@ -156,6 +157,15 @@ int hvi_neg_elbo_grad_async(hvi_plan* plan, int32_t n_MC, const void* phi_dev,
  * (n_site x n_M x n_MC), σ (n_P + n_M n_site).  Used by sample_posterior (:432-458). */
 int hvi_generate_zeta(hvi_plan* plan, int32_t n_MC, const void* phi, const void* zP,
                       const void* zMs, int mem_kind, void* zetaP, void* zetaMs_tr, void* sigma);
+
+/* predict_hvi (src/elbo.jl:320-352): sample_posterior (:381-458: generate_ζ with n_MC = n_sample,
+ * transform_ζs :815-835, no clamp) followed by the 3-D PBM applicator (src/PBMApplicator.jl:51-57) on
+ * the registered batch (set_data may be called with y_o = y_unc = NULL for prediction-only batches).
+ * thetaP (n_P x n_sample), thetaMs_tr (n_site x n_M x n_sample), y (n_obs x n_site x n_sample; NaN where a
+ * driver is not finite), *entropy = entropy_ζ.  zP/zMs NULL: draws from (seed, site_offset). */
+int hvi_predict(hvi_plan* plan, int32_t n_sample, const void* phi, const void* zP, const void* zMs,
+                uint64_t seed, int64_t site_offset, int mem_kind, void* thetaP, void* thetaMs_tr,
+                void* y, double* entropy);
 
 /* g(xM, ϕg) alone (src/ModelApplicator.jl:19-23,163-176): mu_zeta (n_M x n_site). */
 int hvi_apply_g(hvi_plan* plan, const void* phi, int mem_kind, void* mu_zeta);

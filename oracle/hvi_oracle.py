@@ -488,3 +488,24 @@ def normal_scaling_from_priors(priorsM, transM):
         mus.append((lo + hi) / 2)
         sgs.append((hi - lo) / (2 * Z95))
     return mus, sgs
+
+
+# --------------------------------------------------------------------------------------
+# prediction path (src/elbo.jl:320-458, 815-835; src/PBMApplicator.jl:51-57)
+# --------------------------------------------------------------------------------------
+def transform_zetas(spec: Spec, zsP, zsMs_tr):
+    """transform_ζs (src/elbo.jl:815-835): bijectors only, no clamp, no log-Jacobian."""
+    thP = _transform(spec.transP, zsP.T)[0].T if spec.nP > 0 else zsP
+    thMs = _transform(spec.transM, zsMs_tr.permute(0, 2, 1))[0].permute(0, 2, 1)
+    return thP, thMs
+
+
+def predict_hvi(spec: Spec, phi, xM, xP, zP, zMs):
+    """predict_hvi (src/elbo.jl:320-352) with the draws passed in: y (nO × nb × n_sample),
+    θsP (nP × n_sample), θsMs_tr (nb × nM × n_sample), entropy_ζ."""
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+    zsP, zsMs_tr, sigma = generate_zeta(spec, t(phi), t(xM), t(zP), t(zMs))
+    ent = entropy_MvNormal(sigma.numel(), 2 * torch.log(sigma).sum())
+    thP, thMs = transform_zetas(spec, zsP, zsMs_tr)
+    ys = [f_doubleMM_sites(spec, thP[:, m] if spec.nP > 0 else thP[:0, 0], thMs[:, :, m], t(xP)) for m in range(thMs.shape[2])]
+    return torch.stack(ys, dim=2).numpy(), thP.numpy(), thMs.numpy(), float(ent)

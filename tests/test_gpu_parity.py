@@ -225,3 +225,34 @@ def test_device_rng_is_sharding_invariant():
         plan.set_data(*(data[k][:, lo:hi] for k in ("xM", "xP", "y_o", "y_unc")))
         tot += np.array(plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=5, site_offset=lo)[1])
     np.testing.assert_allclose(tot, np.array(comps), rtol=1e-11)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("case", ["DoubleMM_default", "C1_test_HybridProblem", "DoubleMM_covarK2", "DoubleMM_no_globals"])
+def test_predict_hvi_matches_oracle(case, dtype):
+    """predict_hvi / sample_posterior forward path (src/elbo.jl:320-458): shapes as documented
+    (:305-313), values against the oracle, NaN predictions exactly where a driver is missing,
+    prediction-only batch (no observations)."""
+    prob = CASES[case](dtype)
+    nb, ns = 45, 9
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, driver_nan_frac=0.2)
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, ns)
+    ϕ = prob.init_ϕ(perturbed=True)
+    plan = hvi_b200.NegElboPlan(prob)
+    plan.set_data(data["xM"], data["xP"])          # no y_o / y_unc
+    y, θP, θMs, ent = plan.predict_hvi(ϕ, zP, zMs)
+    assert y.shape == (prob.n_obs, nb, ns) and θP.shape == (prob.n_P, ns) and θMs.shape == (nb, prob.n_M, ns)
+    f = (lambda a: np.asarray(a, dtype=np.float32)) if dtype == "f32" else (lambda a: a)
+    y_o, θP_o, θMs_o, ent_o = O.predict_hvi(oracle_spec(prob), f(ϕ), f(data["xM"]), f(data["xP"]), f(zP), f(zMs))
+    tol = {"f64": 1e-10, "f32": 2e-5}[dtype]
+    assert np.array_equal(np.isnan(y), np.isnan(y_o)) and np.isnan(y).any()
+    np.testing.assert_allclose(θP, θP_o, rtol=tol)
+    np.testing.assert_allclose(θMs, θMs_o, rtol=tol, atol=tol)
+    np.testing.assert_allclose(y, y_o, rtol=tol, atol=tol, equal_nan=True)
+    assert abs(ent - ent_o) <= 1e-6 * abs(ent_o) if dtype == "f32" else abs(ent - ent_o) <= 1e-11 * abs(ent_o)
+    # the device generator gives finite predictions of the same shape
+    y2, _, _, ent2 = plan.predict_hvi(ϕ, n_sample_pred=12, seed=3)
+    assert y2.shape == (prob.n_obs, nb, 12) and np.isfinite(y2[~np.isnan(y2)]).all() and abs(ent2 - ent) <= 1e-9 * abs(ent)
+    # without observations the ELBO of the batch has no likelihood term but still evaluates
+    nL, comps, g = plan.neg_elbo_withgradient(ϕ, zP, zMs)
+    assert comps.nLy == 0.0 and np.isfinite(nL)
