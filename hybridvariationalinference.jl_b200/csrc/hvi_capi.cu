@@ -39,6 +39,8 @@ struct hvi_plan {
   void* d_MUBAR; int64_t cap_MUBAR;  // and their cotangents
   double* d_part_x; int64_t cap_part_x;
   double* d_xred; int64_t cap_xred;
+  int wide;                           // wide applicator (forward paths only)
+  void* d_wide; int64_t cap_wide;
   void* d_stage; int64_t cap_stage;   // staging of a host batch (xP, y_o, y_unc) for k_preprocess
   double* h_pre;                      // pinned: preprocess partial sums
   double* d_part_stream; int max_rows;
@@ -143,6 +145,13 @@ static void fill_cfg(const hvi_desc& d, Cfg<T>& c) {
   c.npc = d.n_pbm_covar;
 }
 
+// a network with a layer wider than HVI_MAX_WIDTH runs on the wide (tensor-core) applicator: forward only
+static bool is_wide(const hvi_desc* d) {
+  for (int l = 0; l < d->n_layers; l++)
+    if (d->layers[l].n_in > HVI_MAX_WIDTH || d->layers[l].n_out > HVI_MAX_WIDTH) return true;
+  return false;
+}
+
 static const char* validate(const hvi_desc* d) {
   if (!d) return "desc is NULL";
   if (d->struct_size != (int32_t)sizeof(hvi_desc)) return "hvi_desc.struct_size mismatch (ABI)";
@@ -156,8 +165,7 @@ static const char* validate(const hvi_desc* d) {
   for (int l = 0; l < d->n_layers; l++) {
     if (d->layers[l].n_in < 1 || d->layers[l].n_out < 1) return "layer sizes must be positive";
     if (l > 0 && d->layers[l].n_in != d->layers[l - 1].n_out) return "layer sizes do not chain";
-    if (d->layers[l].n_in > HVI_MAX_WIDTH || d->layers[l].n_out > HVI_MAX_WIDTH)
-      return "layer wider than HVI_MAX_WIDTH: not supported by the CUDA-core applicator";
+    if (d->layers[l].n_in > 4096 || d->layers[l].n_out > 4096) return "layer wider than 4096";
   }
   if (d->layers[d->n_layers - 1].n_out < d->n_M) return "network has fewer outputs than n_M";
   if (d->n_cor_ends_P < 0 || d->n_cor_ends_P > MAXP || d->n_cor_ends_M < 0 || d->n_cor_ends_M > MAXP)
@@ -182,8 +190,8 @@ static const char* validate(const hvi_desc* d) {
     if (d->prior_M[i].kind && !(d->prior_M[i].b > 0)) return "prior_M scale must be positive";
   }
   if (!stream_supported(d->n_P, d->n_M, d->n_obs)) return "(n_P, n_M, n_obs) combination has no kernel instantiation";
-  if (d->n_pbm_covar > 0 && !mlp_supports_pbm(d))
-    return "pbm_covars need one of the register-tiled applicator shapes (5-20-20-2, 6-24-24-2)";
+  if (d->n_pbm_covar > 0 && !mlp_supports_pbm(d) && !is_wide(d))
+    return "pbm_covars need one of the register-tiled applicator shapes (5-20-20-2, 6-24-24-2) or a wide network";
   return nullptr;
 }
 
@@ -216,6 +224,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   p->d_MU = p->d_MUBAR = nullptr; p->d_part_x = p->d_xred = nullptr;
   p->cap_MU = p->cap_MUBAR = p->cap_part_x = p->cap_xred = 0;
   p->d_stage = nullptr; p->cap_stage = 0; p->h_pre = nullptr;
+  p->wide = is_wide(desc) ? 1 : 0; p->d_wide = nullptr; p->cap_wide = 0;
   p->d_part_stream = p->d_part_mlp = p->d_out = p->d_red = nullptr;
   p->d_grad = nullptr; p->h_out = nullptr; p->h_grad = nullptr;
   p->const_nly = 0; p->anomalies = 0;
@@ -242,7 +251,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   CRE(cudaMalloc(&p->d_phi, p->es * (size_t)nphi));
   CRE(cudaMalloc(&p->d_ec, sizeof(EvalConsts<double>)));
   CRE(cudaMalloc(&p->d_part_stream, sizeof(double) * (size_t)p->max_rows * nacc(p->cf.nP, p->cf.nM)));
-  CRE(cudaMalloc(&p->d_part_mlp, sizeof(double) * (size_t)2 * p->max_blk * p->cf.nphig));
+  if (!p->wide) CRE(cudaMalloc(&p->d_part_mlp, sizeof(double) * (size_t)2 * p->max_blk * p->cf.nphig));
   CRE(cudaMalloc(&p->d_out, sizeof(double) * (size_t)(nphi + 8)));
   CRE(cudaMalloc(&p->d_red, sizeof(double) * (size_t)(128 + (p->cf.nphig + 31) / 32 + 2)));
   CRE(cudaMalloc(&p->d_grad, p->es * (size_t)nphi));
@@ -259,7 +268,7 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   cudaSetDevice(p->desc.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   void* dev[] = {p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
-                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage};
+                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
   if (p->h_grad) cudaFreeHost(p->h_grad);
@@ -404,11 +413,27 @@ template <typename T> static const Cfg<T>& cfg_of(const hvi_plan* p);
 template <> const Cfg<float>& cfg_of<float>(const hvi_plan* p) { return p->cf; }
 template <> const Cfg<double>& cfg_of<double>(const hvi_plan* p) { return p->cd; }
 
+// g forward for all paths: register-tiled / generic CUDA-core kernels, or the wide tensor-core chain
+template <typename T>
+static int run_g_fwd(hvi_plan* p, const Launch& L, const Cfg<T>& cfg, const T* phi, T* out, int M_units, const T* zetaP) {
+  if (p->wide) {
+    int rc = ensure(p, &p->d_wide, &p->cap_wide, (int64_t)(sizeof(T) * wide_work_elems(cfg.max_width, cfg.nphig)));
+    if (rc) return rc;
+    CU(p, launch_mlp_fwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, out, M_units, zetaP, (T*)p->d_wide));
+    return HVI_OK;
+  }
+  CU(p, launch_mlp_fwd<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, out, M_units, zetaP));
+  return HVI_OK;
+}
+
 // enqueue the whole evaluation on `s`; all pointers are device pointers
 template <typename T>
 static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* zMs, double* out, T* grad_T,
                         cudaStream_t s, bool rng = false, uint64_t seed = 0, int64_t site_offset = 0) {
   const Cfg<T>& cfg = cfg_of<T>(p);
+  if (p->wide)
+    PLAN_FAIL(p, HVI_EINVAL, "the gradient of the wide applicator is not built yet: networks with a layer wider than %d "
+              "support hvi_apply_g, hvi_generate_zeta and hvi_predict only", HVI_MAX_WIDTH);
   int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)(sizeof(T) * pdraw_elems(cfg.nP, M)));
   if (rc) return rc;
   Launch L{s, p->sm_count, &p->launches};
@@ -608,9 +633,8 @@ static int generate_zeta_t(hvi_plan* p, int M, const void* phi, const void* zP, 
     a.MU = (const T*)p->d_MU;
   }
   cudaError_t e = launch_prologue<T>(L, cfg, dphi, dzP, M, ec, pdraw);
-  if (e == cudaSuccess) e = launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, nb, (T*)p->d_mu);
-  if (e == cudaSuccess && cfg.npc > 0)
-    e = launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, nb, (T*)p->d_MU, M, pdraw + (size_t)nP * M);
+  if (e == cudaSuccess && run_g_fwd<T>(p, L, cfg, dphi, (T*)p->d_mu, 0, nullptr)) e = cudaErrorUnknown;
+  if (e == cudaSuccess && cfg.npc > 0 && run_g_fwd<T>(p, L, cfg, dphi, (T*)p->d_MU, M, pdraw + (size_t)nP * M)) e = cudaErrorUnknown;
   if (e == cudaSuccess) e = launch_generate_zeta<T>(L, cfg, a, pdraw, (T*)o1, (T*)o2, (T*)o3);
   if (e == cudaSuccess && mem_kind == HVI_MEM_HOST) {
     if (nP > 0) e = cudaMemcpyAsync(zetaP, o1, sizeof(T) * (size_t)nP * M, cudaMemcpyDeviceToHost, s);
@@ -642,7 +666,8 @@ static int apply_g_t(hvi_plan* p, const void* phi, int mem_kind, void* mu) {
     dphi = (const T*)p->d_phi;
   }
   Launch L{s, p->sm_count, &p->launches};
-  CU(p, launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, p->nb, (T*)p->d_mu));
+  int rcg = run_g_fwd<T>(p, L, cfg, dphi, (T*)p->d_mu, 0, nullptr);
+  if (rcg) return rcg;
   CU(p, cudaMemcpyAsync(mu, p->d_mu, sizeof(T) * (size_t)cfg.nM * p->nb,
                         mem_kind == HVI_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
   CU(p, cudaStreamSynchronize(s));
@@ -733,9 +758,8 @@ static int predict_t(hvi_plan* p, int M, const void* phi, const void* zP, const 
   }
   int nparts = 0;
   if (e == cudaSuccess) e = launch_prologue<T>(L, cfg, dphi, dzP, M, ec, pdraw);
-  if (e == cudaSuccess) e = launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, nb, (T*)p->d_mu);
-  if (e == cudaSuccess && cfg.npc > 0)
-    e = launch_mlp_fwd<T>(L, cfg, dphi, (const T*)p->d_xM, nb, (T*)p->d_MU, M, pdraw + (size_t)nP * M);
+  if (e == cudaSuccess && run_g_fwd<T>(p, L, cfg, dphi, (T*)p->d_mu, 0, nullptr)) e = cudaErrorUnknown;
+  if (e == cudaSuccess && cfg.npc > 0 && run_g_fwd<T>(p, L, cfg, dphi, (T*)p->d_MU, M, pdraw + (size_t)nP * M)) e = cudaErrorUnknown;
   if (e == cudaSuccess) e = launch_predict<T>(L, cfg, a, pdraw, (const T*)p->d_xP, (T*)o1, (T*)o2, (T*)o3, d_ls, &nparts);
   std::vector<double> hls(nparts > 0 ? nparts : 1);
   std::vector<T> hq(nphi);
@@ -769,4 +793,33 @@ extern "C" int hvi_predict(hvi_plan* p, int32_t n_sample, const void* phi, const
   return p->dtype == HVI_F32
              ? predict_t<float>(p, n_sample, phi, zP, zMs, seed, site_offset, mem_kind, thetaP, thetaMs_tr, y, entropy)
              : predict_t<double>(p, n_sample, phi, zP, zMs, seed, site_offset, mem_kind, thetaP, thetaMs_tr, y, entropy);
+}
+
+namespace hvi {
+cudaError_t launch_dense_tc(cudaStream_t stream, const float* A, const float* W, const float* bias, float* C, int64_t Mc,
+                            int N, int K, int act);
+}
+
+// One dense layer on the tensor cores (tcgen05, 3xTF32): C (Mc x N, row-major) = act(A (Mc x K) W(N x K)^T + b).
+// Host pointers; building block of the wide applicator, exported for its parity test.
+extern "C" int hvi_dense_tc(int32_t device, int64_t Mc, int32_t N, int32_t K, const float* A, const float* W,
+                            const float* bias, int32_t act, float* C) {
+  if (!A || !W || !C || Mc < 1 || N < 1 || K < 1 || K % 32 != 0 || N % 128 != 0) { g_create_err = "hvi_dense_tc: bad arguments (K % 32 == 0, N % 128 == 0)"; return HVI_EINVAL; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_create_err = "hvi_dense_tc: no CUDA device (no CPU fallback)"; return HVI_ECUDA; }
+  cudaSetDevice(device);
+  float *dA = nullptr, *dW = nullptr, *db = nullptr, *dC = nullptr;
+  cudaError_t e = cudaMalloc((void**)&dA, sizeof(float) * (size_t)Mc * K);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dW, sizeof(float) * (size_t)N * K);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dC, sizeof(float) * (size_t)Mc * N);
+  if (e == cudaSuccess && bias) e = cudaMalloc((void**)&db, sizeof(float) * (size_t)N);
+  if (e == cudaSuccess) e = cudaMemcpy(dA, A, sizeof(float) * (size_t)Mc * K, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dW, W, sizeof(float) * (size_t)N * K, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && bias) e = cudaMemcpy(db, bias, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_dense_tc(nullptr, dA, dW, db, dC, Mc, N, K, act);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(C, dC, sizeof(float) * (size_t)Mc * N, cudaMemcpyDeviceToHost);
+  for (float* q : {dA, dW, db, dC}) if (q) cudaFree(q);
+  if (e != cudaSuccess) { g_create_err = std::string("hvi_dense_tc: ") + cudaGetErrorString(e); return HVI_ECUDA; }
+  return HVI_OK;
 }

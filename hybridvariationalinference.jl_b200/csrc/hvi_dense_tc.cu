@@ -1,0 +1,346 @@
+// hvi_dense_tc.cu -- tensor-core dense layer of the wide applicator (BASELINE config 5: 4x512 hidden):
+//   C[Mc x N] = act(A[Mc x K] * W[N x K]^T + b),  fp32 in / fp32 out, error-compensated 3xTF32
+// on the 5th-generation tensor cores: tcgen05.mma kind::tf32 issued by one thread, fp32 accumulators in
+// TMEM, operands in 128-byte-swizzled K-major shared-memory tiles, epilogue via tcgen05.ld.
+//
+// Every fp32 operand x is split on the way into shared memory into hi = tf32(x) and lo = x - hi
+// (exact), and each K step issues hi*hi + hi*lo + lo*hi into the same accumulator: relative error
+// ~1e-6 instead of tf32's 5e-4, which is what the 1e-4 gradient tolerance of the path needs
+// (SURVEY section 7 "Tolerance vs tensor cores").
+//
+// Reference: the dense layers of g (ext/HybridVariationalInferenceSimpleChainsExt.jl:43-52,
+// ext/HybridVariationalInferenceFluxExt.jl:26-31) -- cuBLAS/SimpleChains GEMMs there.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hvi_internal.cuh"
+
+namespace hvi {
+
+constexpr int TC_BM = 128;      // rows per CTA = TMEM lanes
+constexpr int TC_BN = 128;      // output columns per CTA = TMEM columns
+constexpr int TC_BK = 32;       // K per stage: 32 tf32 = one 128-byte swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 128;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;              // 16 KB per operand half
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;             // A hi, A lo, B hi, B lo
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start address >> 4 [0,14) | LBO (unused for swizzled K-major) = 1 [16,30) | SBO = 1024 B >> 4 [32,46)
+// | version = 1 [46,48) | layout type SWIZZLE_128B = 2 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+// instruction descriptor (InstrDescriptor): D = F32 [4,6)=1, A = TF32 [7,10)=2, B = TF32 [10,13)=2,
+// both K-major, N >> 3 [17,23), M >> 4 [24,29)
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate)
+      : "memory");
+}
+
+// round to nearest tf32 (10-bit mantissa), result as an fp32 bit pattern
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// split 4 fp32 values into tf32 hi / residual lo and store both as one 16-byte chunk each at the
+// swizzled position of (row, chunk) inside a [rows][32 floats] tile
+__device__ __forceinline__ void split_store(unsigned char* tile_hi, unsigned char* tile_lo, int row, int chunk, float4 v) {
+  float4 hi, lo;
+  hi.x = to_tf32(v.x); lo.x = v.x - hi.x;
+  hi.y = to_tf32(v.y); lo.y = v.y - hi.y;
+  hi.z = to_tf32(v.z); lo.z = v.z - hi.z;
+  hi.w = to_tf32(v.w); lo.w = v.w - hi.w;
+  const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
+  *reinterpret_cast<float4*>(tile_hi + off) = hi;
+  *reinterpret_cast<float4*>(tile_lo + off) = lo;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ C,
+           int64_t Mc, int N, int K, int act) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar_mma[TC_STAGES];   // "the MMAs that read stage s have completed"
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  unsigned char* tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
+  const int col0 = blockIdx.y * TC_BN;
+  if (t == 0) {
+    for (int s = 0; s < TC_STAGES; s++) mbar_init(&bar_mma[s], 1);
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TC_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+
+  const int KT = K / TC_BK;
+  // this thread's 8 + 8 float4 of a stage: element e = i*128 + t → row e/8, chunk e%8
+  for (int kt = 0; kt < KT; kt++) {
+    const int s = kt % TC_STAGES;
+    float4 va[8], vb[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int e = i * TC_THREADS + t, r = e >> 3, c = e & 7;
+      const int64_t gr = row0 + r;
+      va[i] = gr < Mc ? *reinterpret_cast<const float4*>(A + gr * K + (size_t)kt * TC_BK + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      vb[i] = *reinterpret_cast<const float4*>(W + (size_t)(col0 + r) * K + (size_t)kt * TC_BK + c * 4);
+    }
+    // the stage is free once the MMAs issued TC_STAGES iterations ago have completed
+    if (kt >= TC_STAGES) mbar_wait(&bar_mma[s], ((kt / TC_STAGES) - 1) & 1);
+    unsigned char* st = tiles + (size_t)s * TC_STAGE_BYTES;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int e = i * TC_THREADS + t, r = e >> 3, c = e & 7;
+      split_store(st, st + TC_TILE_BYTES, r, c, va[i]);
+      split_store(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, r, c, vb[i]);
+    }
+    // generic-proxy writes → visible to the tensor core's async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_TILE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
+#pragma unroll
+      for (int ks = 0; ks < TC_BK / 8; ks++) {   // UMMA_K = 8 for tf32: 32 bytes along the swizzled row
+        const uint32_t o = ks * 32;
+        mma_tf32(tmem_d, make_desc(a_hi + o), make_desc(b_hi + o), (kt > 0 || ks > 0) ? 1u : 0u);
+        mma_tf32(tmem_d, make_desc(a_hi + o), make_desc(b_lo + o), 1u);
+        mma_tf32(tmem_d, make_desc(a_lo + o), make_desc(b_hi + o), 1u);
+      }
+      // arrives on the barrier when all MMAs issued so far have completed (implies before_thread_sync)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma[s])) : "memory");
+      if (kt == KT - 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_done)) : "memory");
+    }
+  }
+  // epilogue: TMEM → registers → bias + activation → global.  Warp w owns TMEM lanes 32w … 32w+31.
+  mbar_wait(&bar_done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int64_t grow = row0 + warp * 32 + lane;
+#pragma unroll 1
+  for (int cb = 0; cb < TC_BN; cb += 32) {
+    uint32_t v[32];
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + cb;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (grow < Mc) {
+      float* out = C + grow * N + col0 + cb;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o;
+        float* po = &o.x;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          float z = __uint_as_float(v[j + c]) + (bias ? bias[col0 + cb + j + c] : 0.f);
+          if (act == HVI_ACT_TANH) z = tanhf(z);
+          else if (act == HVI_ACT_LOGISTIC) z = 1.f / (1.f + expf(-z));
+          po[c] = z;
+        }
+        *reinterpret_cast<float4*>(out + j) = o;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_BN));
+}
+
+// C = act(A·Wᵀ + b); device pointers; requires K % 32 == 0, N % 128 == 0, 16-byte aligned rows
+cudaError_t launch_dense_tc(cudaStream_t stream, const float* A, const float* W, const float* bias, float* C, int64_t Mc,
+                            int N, int K, int act) {
+  if (K % TC_BK != 0 || N % TC_BN != 0 || Mc < 1) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
+  cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)((Mc + TC_BM - 1) / TC_BM), (unsigned)(N / TC_BN));
+  k_dense_tc<<<grid, TC_THREADS, smem, stream>>>(A, W, bias, C, Mc, N, K, act);
+  return cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------------------
+// wide applicator, forward: g for networks with layers wider than HVI_MAX_WIDTH (BASELINE config 5:
+// 5-512-512-512-512-2).  Columns (sites, or draw x site with pbm covariates) are processed in chunks;
+// activations of a chunk live in two ping-pong HBM buffers [chunk x width]; hidden layers whose shape
+// fits (K % 32 == 0, N % 128 == 0, Float32) run on the tensor cores (k_dense_tc), the first layer
+// (K = n_covar) and the last (N = n_θM, fused logistic + Φ⁻¹ scaling) on CUDA cores.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T act_apply(int act, T z) {
+  if (act == HVI_ACT_TANH) return tanh(z);
+  if (act == HVI_ACT_LOGISTIC) return T(1) / (T(1) + exp(-z));
+  return z;
+}
+
+// W_ref: the reference's layout vec(W[out x in]) column-major = [in][out]; Wt: [out][in] row-major
+template <typename T>
+__global__ void k_transpose_w(const T* __restrict__ Wref, T* __restrict__ Wt, int n_in, int n_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n_in * n_out) { const int i = e / n_out, j = e % n_out; Wt[(size_t)j * n_in + i] = Wref[e]; }
+}
+
+// generic layer on CUDA cores: C[r][j] = act(Σ_i in(r,i)·W[i][j] + b[j]); one thread per (r, j), j fastest
+// first-layer mode (xM != NULL): in(r, i) = xM[site][i] for i < nC, else the pbm covariate value extra[i − nC]
+template <typename T>
+__global__ void __launch_bounds__(256) k_dense_simple(const T* __restrict__ A, const T* __restrict__ xM, int nC,
+                                                      const T* __restrict__ extra, int64_t site0,
+                                                      const T* __restrict__ Wref, const T* __restrict__ bias, int act,
+                                                      T* __restrict__ C, int64_t rows, int N, int K) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * N) return;
+  const int64_t r = e / N;
+  const int j = (int)(e % N);
+  T z = bias ? bias[j] : T(0);
+  for (int i = 0; i < K; i++) {
+    const T x = xM ? (i < nC ? xM[(site0 + r) * nC + i] : extra[i - nC]) : A[r * K + i];
+    z = fma(x, Wref[(size_t)i * N + j], z);
+  }
+  C[r * N + j] = act_apply<T>(act, z);
+}
+
+// last layer + output scaling: one warp per row, lanes over K, outputs n_out (≤ 8)
+template <typename T>
+__global__ void __launch_bounds__(256) k_wide_last(const Cfg<T> cfg, const T* __restrict__ A, const T* __restrict__ Wref,
+                                                   int act, int64_t rows, int K, int n_out, T* __restrict__ mu,
+                                                   int64_t site0, int m, int M_units, int64_t nb) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  T acc[MAXP];
+  for (int k = 0; k < n_out; k++) acc[k] = T(0);
+  for (int i = lane; i < K; i += 32) {
+    const T x = A[r * K + i];
+    for (int k = 0; k < n_out; k++) acc[k] = fma(x, Wref[(size_t)i * n_out + k], acc[k]);
+  }
+  for (int k = 0; k < n_out; k++) {
+    T s = acc[k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && k < cfg.nM) {
+      const T p = act_apply<T>(act, s);
+      const T v = (cfg.scale_kind == HVI_SCALE_RANGE) ? p * cfg.scale_b[k] + cfg.scale_a[k]
+                                                      : cfg.scale_a[k] + cfg.scale_b[k] * (T)normcdfinv((double)p);
+      const int64_t site = site0 + r;
+      if (M_units > 0) mu[((size_t)m * cfg.nM + k) * nb + site] = v;
+      else mu[site * cfg.nM + k] = v;
+    }
+  }
+}
+
+template <typename T>
+cudaError_t launch_mlp_fwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu,
+                                int M_units, const T* zetaP, T* work /*wide_work_elems(cfg)*/) {
+  if (cfg.l_bias[cfg.nL - 1] || cfg.l_out[cfg.nL - 1] > MAXP) return cudaErrorInvalidConfiguration;
+  const int64_t CHUNK = 65536;
+  const int maxw = cfg.max_width;
+  T* buf0 = work;
+  T* buf1 = work + (size_t)CHUNK * maxw;
+  T* wt = buf1 + (size_t)CHUNK * maxw;          // transposed hidden-layer weights, [out][in] each
+  T* extra_h = wt + (size_t)cfg.nphig;          // pbm covariate values of the current draw (device)
+  // transposed copies of the hidden-layer weights for the tensor-core layers
+  for (int l = 1; l < cfg.nL - 1; l++) {
+    const int n = cfg.l_in[l] * cfg.l_out[l];
+    k_transpose_w<T><<<(n + 255) / 256, 256, 0, L.stream>>>(phi + cfg.woff[l], wt + cfg.woff[l], cfg.l_in[l], cfg.l_out[l]);
+    if (L.counter) ++*L.counter;
+  }
+  const int nm = M_units > 0 ? M_units : 1;
+  for (int m = 0; m < nm; m++) {
+    // pbm covariates of this draw: ζP[idx, m] (unit mode) or μP[idx] (site mode)
+    for (int c = 0; c < cfg.npc; c++) {
+      const T* src = M_units > 0 ? zetaP + (size_t)cfg.pbm_covar_idx[c] * M_units + m : phi + cfg.o_muP + cfg.pbm_covar_idx[c];
+      cudaError_t e = cudaMemcpyAsync(extra_h + c, src, sizeof(T), cudaMemcpyDeviceToDevice, L.stream);
+      if (e != cudaSuccess) return e;
+    }
+    for (int64_t s0 = 0; s0 < nb; s0 += CHUNK) {
+      const int64_t rows = nb - s0 < CHUNK ? nb - s0 : CHUNK;
+      T *in = buf0, *out = buf1;
+      {  // first layer
+        const int N = cfg.l_out[0], K = cfg.l_in[0];
+        const int64_t n = rows * N;
+        k_dense_simple<T><<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(
+            nullptr, xM, cfg.nC, extra_h, s0, phi + cfg.woff[0], cfg.l_bias[0] ? phi + cfg.boff[0] : nullptr, cfg.l_act[0],
+            in, rows, N, K);
+        if (L.counter) ++*L.counter;
+      }
+      for (int l = 1; l < cfg.nL - 1; l++) {
+        const int N = cfg.l_out[l], K = cfg.l_in[l];
+        const T* b = cfg.l_bias[l] ? phi + cfg.boff[l] : nullptr;
+        bool tc = false;
+        if constexpr (sizeof(T) == 4) {
+          if (K % TC_BK == 0 && N % TC_BN == 0) {
+            cudaError_t e = launch_dense_tc(L.stream, (const float*)in, (const float*)(wt + cfg.woff[l]), (const float*)b,
+                                            (float*)out, rows, N, K, cfg.l_act[l]);
+            if (e != cudaSuccess) return e;
+            tc = true;
+          }
+        }
+        if (!tc) {
+          const int64_t n = rows * N;
+          k_dense_simple<T><<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(in, nullptr, 0, nullptr, 0, phi + cfg.woff[l], b,
+                                                                           cfg.l_act[l], out, rows, N, K);
+        }
+        if (L.counter) ++*L.counter;
+        T* tmp = in; in = out; out = tmp;
+      }
+      {  // last layer + scaling
+        const int l = cfg.nL - 1;
+        k_wide_last<T><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, L.stream>>>(cfg, in, phi + cfg.woff[l], cfg.l_act[l], rows,
+                                                                              cfg.l_in[l], cfg.l_out[l], mu, s0, m, M_units, nb);
+        if (L.counter) ++*L.counter;
+      }
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
+  }
+  return cudaSuccess;
+}
+
+size_t wide_work_elems(int max_width, int nphig) { return (size_t)2 * 65536 * max_width + (size_t)nphig + 16; }
+
+template cudaError_t launch_mlp_fwd_wide<float>(const Launch&, const Cfg<float>&, const float*, const float*, int64_t, float*,
+                                                int, const float*, float*);
+template cudaError_t launch_mlp_fwd_wide<double>(const Launch&, const Cfg<double>&, const double*, const double*, int64_t,
+                                                 double*, int, const double*, double*);
+
+}  // namespace hvi

@@ -112,6 +112,11 @@ inline size_t pdraw_elems(int nP, int M) { return (size_t)4 * (nP > 0 ? nP : 1) 
 template <typename T>
 cudaError_t launch_predict(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, const T* pdraw, const T* xP,
                            T* thetaP, T* thetaMs_tr, T* y, double* part_logsig /*[sm_count*16*8]*/, int* nparts);
+// wide applicator (any layer wider than HVI_MAX_WIDTH): forward only, tensor cores for the hidden layers
+template <typename T>
+cudaError_t launch_mlp_fwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu,
+                                int M_units, const T* zetaP, T* work);
+size_t wide_work_elems(int max_width, int nphig);
 int stream_max_rows(int sm_count);
 int mlp_bwd_max_blocks(int sm_count);
 bool stream_supported(int nP, int nM, int nO);

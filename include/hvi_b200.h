@@ -176,6 +176,13 @@ int hvi_apply_g(hvi_plan* plan, const void* phi, int mem_kind, void* mu_zeta);
 int hvi_randn(hvi_plan* plan, int32_t n_MC, int64_t n_cols, uint64_t seed, int64_t col_offset,
               int mem_kind, void* out);
 
+/* One dense layer of g on the tensor cores (tcgen05.mma kind::tf32 with 3xTF32 error compensation,
+ * accumulators in TMEM): C (Mc x N, row-major) = act(A (Mc x K, row-major) * W (N x K, row-major)^T + bias).
+ * Host pointers, K % 32 == 0, N % 128 == 0.  Building block of the wide applicator (layers of g wider
+ * than HVI_MAX_WIDTH; ext/HybridVariationalInferenceFluxExt.jl:26-31 uses cuBLAS there). */
+int hvi_dense_tc(int32_t device, int64_t Mc, int32_t N, int32_t K, const float* A, const float* W,
+                 const float* bias, int32_t act, float* C);
+
 /* number of kernels launched by this plan since creation (bench.py's gpu_launches) */
 int64_t hvi_launch_count(const hvi_plan* plan);
 
