@@ -108,17 +108,22 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
   const uint32_t tmem_d = tmem_base_s;
 
   const int KT = K / TC_BK;
-  // this thread's 8 + 8 float4 of a stage: element e = i*128 + t → row e/8, chunk e%8
-  for (int kt = 0; kt < KT; kt++) {
-    const int s = kt % TC_STAGES;
-    float4 va[8], vb[8];
+  // this thread's 8 + 8 float4 of a stage: element e = i*128 + t → row e/8, chunk e%8.  The global
+  // loads of tile kt+1 are issued right after tile kt has been handed to the tensor core, so their
+  // latency overlaps the MMAs.
+  float4 va[8], vb[8];
+  auto load_tile = [&](int kt_) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const int e = i * TC_THREADS + t, r = e >> 3, c = e & 7;
       const int64_t gr = row0 + r;
-      va[i] = gr < Mc ? *reinterpret_cast<const float4*>(A + gr * K + (size_t)kt * TC_BK + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      vb[i] = *reinterpret_cast<const float4*>(W + (size_t)(col0 + r) * K + (size_t)kt * TC_BK + c * 4);
+      va[i] = gr < Mc ? __ldg(reinterpret_cast<const float4*>(A + gr * K + (size_t)kt_ * TC_BK + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      vb[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)(col0 + r) * K + (size_t)kt_ * TC_BK + c * 4));
     }
+  };
+  load_tile(0);
+  for (int kt = 0; kt < KT; kt++) {
+    const int s = kt % TC_STAGES;
     // the stage is free once the MMAs issued TC_STAGES iterations ago have completed
     if (kt >= TC_STAGES) mbar_wait(&bar_mma[s], ((kt / TC_STAGES) - 1) & 1);
     unsigned char* st = tiles + (size_t)s * TC_STAGE_BYTES;
@@ -131,6 +136,7 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
     // generic-proxy writes → visible to the tensor core's async proxy
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    if (kt + 1 < KT) load_tile(kt + 1);
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_TILE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
@@ -221,23 +227,30 @@ __global__ void k_transpose_w(const T* __restrict__ Wref, T* __restrict__ Wt, in
   if (e < n_in * n_out) { const int i = e / n_out, j = e % n_out; Wt[(size_t)j * n_in + i] = Wref[e]; }
 }
 
-// generic layer on CUDA cores: C[r][j] = act(Σ_i in(r,i)·W[i][j] + b[j]); one thread per (r, j), j fastest
+// generic layer on CUDA cores: C[r][j] = act(Σ_i in(r,i)·W[i][j] + b[j]); one thread per (r, 4 consecutive j)
 // first-layer mode (xM != NULL): in(r, i) = xM[site][i] for i < nC, else the pbm covariate value extra[i − nC]
 template <typename T>
 __global__ void __launch_bounds__(256) k_dense_simple(const T* __restrict__ A, const T* __restrict__ xM, int nC,
                                                       const T* __restrict__ extra, int64_t site0,
                                                       const T* __restrict__ Wref, const T* __restrict__ bias, int act,
                                                       T* __restrict__ C, int64_t rows, int N, int K) {
+  const int N4 = (N + 3) / 4;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= rows * N) return;
-  const int64_t r = e / N;
-  const int j = (int)(e % N);
-  T z = bias ? bias[j] : T(0);
+  if (e >= rows * N4) return;
+  const int64_t r = e / N4;
+  const int j0 = (int)(e % N4) * 4;
+  T z[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) z[c] = (bias && j0 + c < N) ? bias[j0 + c] : T(0);
   for (int i = 0; i < K; i++) {
     const T x = xM ? (i < nC ? xM[(site0 + r) * nC + i] : extra[i - nC]) : A[r * K + i];
-    z = fma(x, Wref[(size_t)i * N + j], z);
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+      if (j0 + c < N) z[c] = fma(x, Wref[(size_t)i * N + j0 + c], z[c]);
   }
-  C[r * N + j] = act_apply<T>(act, z);
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+    if (j0 + c < N) C[r * N + j0 + c] = act_apply<T>(act, z[c]);
 }
 
 // last layer + output scaling: one warp per row, lanes over K, outputs n_out (≤ 8)
@@ -297,7 +310,7 @@ cudaError_t launch_mlp_fwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi
       T *in = buf0, *out = buf1;
       {  // first layer
         const int N = cfg.l_out[0], K = cfg.l_in[0];
-        const int64_t n = rows * N;
+        const int64_t n = rows * ((N + 3) / 4);
         k_dense_simple<T><<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(
             nullptr, xM, cfg.nC, extra_h, s0, phi + cfg.woff[0], cfg.l_bias[0] ? phi + cfg.boff[0] : nullptr, cfg.l_act[0],
             in, rows, N, K);
@@ -316,7 +329,7 @@ cudaError_t launch_mlp_fwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi
           }
         }
         if (!tc) {
-          const int64_t n = rows * N;
+          const int64_t n = rows * ((N + 3) / 4);
           k_dense_simple<T><<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(in, nullptr, 0, nullptr, 0, phi + cfg.woff[l], b,
                                                                            cfg.l_act[l], out, rows, N, K);
         }
