@@ -41,6 +41,8 @@ struct hvi_plan {
   double* d_xred; int64_t cap_xred;
   int wide;                           // wide applicator (forward paths only)
   void* d_wide; int64_t cap_wide;
+  void* d_wide_bwd; int64_t cap_wide_bwd;
+  double* d_gacc;                     // wide applicator: ∇ϕg accumulator [nphig] + x̄ accumulators
   void* d_stage; int64_t cap_stage;   // staging of a host batch (xP, y_o, y_unc) for k_preprocess
   double* h_pre;                      // pinned: preprocess partial sums
   double* d_part_stream; int max_rows;
@@ -225,6 +227,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   p->cap_MU = p->cap_MUBAR = p->cap_part_x = p->cap_xred = 0;
   p->d_stage = nullptr; p->cap_stage = 0; p->h_pre = nullptr;
   p->wide = is_wide(desc) ? 1 : 0; p->d_wide = nullptr; p->cap_wide = 0;
+  p->d_wide_bwd = nullptr; p->cap_wide_bwd = 0; p->d_gacc = nullptr;
   p->d_part_stream = p->d_part_mlp = p->d_out = p->d_red = nullptr;
   p->d_grad = nullptr; p->h_out = nullptr; p->h_grad = nullptr;
   p->const_nly = 0; p->anomalies = 0;
@@ -252,6 +255,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   CRE(cudaMalloc(&p->d_ec, sizeof(EvalConsts<double>)));
   CRE(cudaMalloc(&p->d_part_stream, sizeof(double) * (size_t)p->max_rows * nacc(p->cf.nP, p->cf.nM)));
   if (!p->wide) CRE(cudaMalloc(&p->d_part_mlp, sizeof(double) * (size_t)2 * p->max_blk * p->cf.nphig));
+  else CRE(cudaMalloc((void**)&p->d_gacc, sizeof(double) * (size_t)p->cf.nphig));
   CRE(cudaMalloc(&p->d_out, sizeof(double) * (size_t)(nphi + 8)));
   CRE(cudaMalloc(&p->d_red, sizeof(double) * (size_t)(128 + (p->cf.nphig + 31) / 32 + 2)));
   CRE(cudaMalloc(&p->d_grad, p->es * (size_t)nphi));
@@ -268,7 +272,7 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   cudaSetDevice(p->desc.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   void* dev[] = {p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
-                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide};
+                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide, p->d_wide_bwd, p->d_gacc};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
   if (p->h_grad) cudaFreeHost(p->h_grad);
@@ -431,9 +435,6 @@ template <typename T>
 static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* zMs, double* out, T* grad_T,
                         cudaStream_t s, bool rng = false, uint64_t seed = 0, int64_t site_offset = 0) {
   const Cfg<T>& cfg = cfg_of<T>(p);
-  if (p->wide)
-    PLAN_FAIL(p, HVI_EINVAL, "the gradient of the wide applicator is not built yet: networks with a layer wider than %d "
-              "support hvi_apply_g, hvi_generate_zeta and hvi_predict only", HVI_MAX_WIDTH);
   int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)(sizeof(T) * pdraw_elems(cfg.nP, M)));
   if (rc) return rc;
   Launch L{s, p->sm_count, &p->launches};
@@ -446,7 +447,8 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   MARK();
   const bool pbm = cfg.npc > 0;
   const T* zetaP = pdraw + (size_t)cfg.nP * M;
-  CU(p, launch_mlp_fwd<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (T*)p->d_mu));
+  rc = run_g_fwd<T>(p, L, cfg, phi, (T*)p->d_mu, 0, nullptr);
+  if (rc) return rc;
   if (pbm) {  // pass 2: g([xM; ζP_m[idx]]) for every draw (src/elbo.jl:508-515)
     const int64_t nmu = (int64_t)sizeof(T) * M * cfg.nM * p->nb;
     rc = ensure(p, &p->d_MU, &p->cap_MU, nmu);
@@ -457,7 +459,8 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
     if (rc) return rc;
     rc = ensure(p, (void**)&p->d_xred, &p->cap_xred, (int64_t)sizeof(double) * (M + 1) * cfg.npc);
     if (rc) return rc;
-    CU(p, launch_mlp_fwd<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (T*)p->d_MU, M, zetaP));
+    rc = run_g_fwd<T>(p, L, cfg, phi, (T*)p->d_MU, M, zetaP);
+    if (rc) return rc;
   }
   MARK();
   StreamArgs<T> a;
@@ -472,14 +475,30 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   MARK();
   double* part_xs = pbm ? p->d_part_x : nullptr;
   double* part_xu = pbm ? p->d_part_x + (size_t)p->max_blk * cfg.npc : nullptr;
-  CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_mubar, p->nb, p->d_part_mlp, &nblk, p->max_blk, 0,
-                          nullptr, part_xs));
-  if (pbm)
-    CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_MUBAR, p->nb,
-                            p->d_part_mlp + (size_t)nblk * cfg.nphig, &nblk2, p->max_blk, M, zetaP, part_xu));
+  const double* part_g = p->d_part_mlp;
+  if (p->wide) {
+    // wide applicator: tensor-core backward into one double accumulator (a single "partial row")
+    rc = ensure(p, &p->d_wide_bwd, &p->cap_wide_bwd, (int64_t)wide_bwd_work_bytes(cfg.nL, cfg.max_width, cfg.nphig));
+    if (rc) return rc;
+    CU(p, cudaMemsetAsync(p->d_gacc, 0, sizeof(double) * (size_t)cfg.nphig, s));
+    if (pbm) CU(p, cudaMemsetAsync(p->d_part_x, 0, sizeof(double) * (size_t)2 * p->max_blk * (M + 1) * cfg.npc, s));
+    CU(p, launch_mlp_bwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (const T*)p->d_mubar, 0, nullptr, p->d_wide_bwd,
+                                 p->d_gacc, part_xs));
+    if (pbm)
+      CU(p, launch_mlp_bwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (const T*)p->d_MUBAR, M, zetaP, p->d_wide_bwd,
+                                   p->d_gacc, part_xu));
+    part_g = p->d_gacc;
+    nblk = 1; nblk2 = 0;
+  } else {
+    CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_mubar, p->nb, p->d_part_mlp, &nblk, p->max_blk, 0,
+                            nullptr, part_xs));
+    if (pbm)
+      CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_MUBAR, p->nb,
+                              p->d_part_mlp + (size_t)nblk * cfg.nphig, &nblk2, p->max_blk, M, zetaP, part_xu));
+  }
   MARK();
-  CU(p, launch_finalize<T>(L, cfg, phi, zP, pdraw, ec, p->d_part_stream, nrows, p->d_part_mlp, nblk + nblk2, p->const_nly,
-                           p->nb, M, out, grad_T, p->d_red, part_xs, nblk, part_xu, nblk2, p->d_xred));
+  CU(p, launch_finalize<T>(L, cfg, phi, zP, pdraw, ec, p->d_part_stream, nrows, part_g, nblk + nblk2, p->const_nly,
+                           p->nb, M, out, grad_T, p->d_red, part_xs, p->wide ? 1 : nblk, part_xu, p->wide ? 1 : nblk2, p->d_xred));
   MARK();
 #undef MARK
   p->n_ev = iev;
@@ -797,7 +816,7 @@ extern "C" int hvi_predict(hvi_plan* p, int32_t n_sample, const void* phi, const
 
 namespace hvi {
 cudaError_t launch_dense_tc(cudaStream_t stream, const float* A, const float* W, const float* bias, float* C, int64_t Mc,
-                            int N, int K, int act);
+                            int N, int K, int act, const float* Hd);
 }
 
 // One dense layer on the tensor cores (tcgen05, 3xTF32): C (Mc x N, row-major) = act(A (Mc x K) W(N x K)^T + b).
@@ -816,7 +835,7 @@ extern "C" int hvi_dense_tc(int32_t device, int64_t Mc, int32_t N, int32_t K, co
   if (e == cudaSuccess) e = cudaMemcpy(dA, A, sizeof(float) * (size_t)Mc * K, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dW, W, sizeof(float) * (size_t)N * K, cudaMemcpyHostToDevice);
   if (e == cudaSuccess && bias) e = cudaMemcpy(db, bias, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = launch_dense_tc(nullptr, dA, dW, db, dC, Mc, N, K, act);
+  if (e == cudaSuccess) e = launch_dense_tc(nullptr, dA, dW, db, dC, Mc, N, K, act, nullptr);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(C, dC, sizeof(float) * (size_t)Mc * N, cudaMemcpyDeviceToHost);
   for (float* q : {dA, dW, db, dC}) if (q) cudaFree(q);

@@ -82,17 +82,39 @@ __device__ __forceinline__ void split_store(unsigned char* tile_hi, unsigned cha
   *reinterpret_cast<float4*>(tile_lo + off) = lo;
 }
 
+// scalar variant of split_store for the transposing loader of the weight-gradient GEMM: element
+// (row, col) of a [rows][32] K-major tile
+__device__ __forceinline__ void split_store1(unsigned char* tile_hi, unsigned char* tile_lo, int row, int col, float x) {
+  const float hi = to_tf32(x);
+  const int off = row * 128 + ((((col >> 2) ^ (row & 7))) << 4) + ((col & 3) << 2);
+  *reinterpret_cast<float*>(tile_hi + off) = hi;
+  *reinterpret_cast<float*>(tile_lo + off) = x - hi;
+}
+
+__device__ __forceinline__ float act_deriv_f(int act, float h) {
+  if (act == HVI_ACT_TANH) return 1.f - h * h;
+  if (act == HVI_ACT_LOGISTIC) return h * (1.f - h);
+  return 1.f;
+}
+
+// MODE 0 (layer / data gradient):  C[Mc x N] = epi(A[Mc x K] · W[N x K]ᵀ),
+//     epi(z) = act(z + bias)                        if Hd == NULL   (forward layer)
+//     epi(z) = z · act'(Hd[row][col])               otherwise       (δ_{l-1} = (δ_l W_l) ⊙ act'(H_{l-1}))
+// MODE 1 (weight gradient, split over the rows): P[split][Md x Nd] = Σ_{r in split} X[r][m]·Y[r][n]
+//     with A ≙ X (Mc x Md), W ≙ Y (Mc x Nd), N ≙ Nd, K ≙ Md; operands are transposed on the way into
+//     shared memory (lane ↔ row r, so the scalar stores of a warp hit 32 different banks)
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ C,
-           int64_t Mc, int N, int K, int act) {
+           int64_t Mc, int N, int K, int act, const float* __restrict__ Hd, int64_t rows_per_split) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar_mma[TC_STAGES];   // "the MMAs that read stage s have completed"
   __shared__ uint64_t bar_done;
   __shared__ uint32_t tmem_base_s;
   unsigned char* tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
-  const int col0 = blockIdx.y * TC_BN;
+  const int64_t row0 = (int64_t)blockIdx.x * TC_BM;   // MODE 0: first row of C;  MODE 1: first m
+  const int col0 = blockIdx.y * TC_BN;                 // first column of C / first n
   if (t == 0) {
     for (int s = 0; s < TC_STAGES; s++) mbar_init(&bar_mma[s], 1);
     mbar_init(&bar_done, 1);
@@ -107,31 +129,62 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
 
-  const int KT = K / TC_BK;
-  // this thread's 8 + 8 float4 of a stage: element e = i*128 + t → row e/8, chunk e%8.  The global
-  // loads of tile kt+1 are issued right after tile kt has been handed to the tensor core, so their
-  // latency overlaps the MMAs.
+  // MODE 1: this CTA's row range
+  int64_t r_begin = 0, r_end = 0;
+  if (MODE == 1) {
+    r_begin = (int64_t)blockIdx.z * rows_per_split;
+    r_end = r_begin + rows_per_split < Mc ? r_begin + rows_per_split : Mc;
+    if (r_end < r_begin) r_end = r_begin;
+  }
+  const int KT = MODE == 0 ? K / TC_BK : (int)((r_end - r_begin + TC_BK - 1) / TC_BK);
+  // 8 + 8 float4 per thread and stage.  The global loads of tile kt+1 are issued right after tile
+  // kt has been handed to the tensor core, so their latency overlaps the MMAs.
   float4 va[8], vb[8];
   auto load_tile = [&](int kt_) {
+    if (MODE == 0) {   // element e = i*128 + t → row e/8, 16-byte chunk e%8 of the K-major tile
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int e = i * TC_THREADS + t, r = e >> 3, c = e & 7;
-      const int64_t gr = row0 + r;
-      va[i] = gr < Mc ? __ldg(reinterpret_cast<const float4*>(A + gr * K + (size_t)kt_ * TC_BK + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      vb[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)(col0 + r) * K + (size_t)kt_ * TC_BK + c * 4));
+      for (int i = 0; i < 8; i++) {
+        const int e = i * TC_THREADS + t, r = e >> 3, c = e & 7;
+        const int64_t gr = row0 + r;
+        va[i] = gr < Mc ? __ldg(reinterpret_cast<const float4*>(A + gr * K + (size_t)kt_ * TC_BK + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)(col0 + r) * K + (size_t)kt_ * TC_BK + c * 4));
+      }
+    } else {           // lane ↔ row r of the step, warp w covers m (n) = 32w … 32w+31, four at a time
+      const int64_t gr = r_begin + (int64_t)kt_ * TC_BK + lane;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int m4 = warp * 8 + i;
+        va[i] = gr < r_end ? __ldg(reinterpret_cast<const float4*>(A + gr * K + row0 + 4 * m4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[i] = gr < r_end ? __ldg(reinterpret_cast<const float4*>(W + gr * N + col0 + 4 * m4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   };
-  load_tile(0);
+  if (KT > 0) load_tile(0);
   for (int kt = 0; kt < KT; kt++) {
     const int s = kt % TC_STAGES;
     // the stage is free once the MMAs issued TC_STAGES iterations ago have completed
     if (kt >= TC_STAGES) mbar_wait(&bar_mma[s], ((kt / TC_STAGES) - 1) & 1);
     unsigned char* st = tiles + (size_t)s * TC_STAGE_BYTES;
+    if (MODE == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int e = i * TC_THREADS + t, r = e >> 3, c = e & 7;
-      split_store(st, st + TC_TILE_BYTES, r, c, va[i]);
-      split_store(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, r, c, vb[i]);
+      for (int i = 0; i < 8; i++) {
+        const int e = i * TC_THREADS + t, r = e >> 3, c = e & 7;
+        split_store(st, st + TC_TILE_BYTES, r, c, va[i]);
+        split_store(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, r, c, vb[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int m = 4 * (warp * 8 + i);
+        split_store1(st, st + TC_TILE_BYTES, m + 0, lane, va[i].x);
+        split_store1(st, st + TC_TILE_BYTES, m + 1, lane, va[i].y);
+        split_store1(st, st + TC_TILE_BYTES, m + 2, lane, va[i].z);
+        split_store1(st, st + TC_TILE_BYTES, m + 3, lane, va[i].w);
+        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 0, lane, vb[i].x);
+        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 1, lane, vb[i].y);
+        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 2, lane, vb[i].z);
+        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 3, lane, vb[i].w);
+      }
     }
     // generic-proxy writes → visible to the tensor core's async proxy
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -153,35 +206,53 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_done)) : "memory");
     }
   }
-  // epilogue: TMEM → registers → bias + activation → global.  Warp w owns TMEM lanes 32w … 32w+31.
-  mbar_wait(&bar_done, 0);
+  // epilogue: TMEM → registers → global.  Warp w owns TMEM lanes 32w … 32w+31.
+  if (KT > 0) mbar_wait(&bar_done, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int64_t grow = row0 + warp * 32 + lane;
 #pragma unroll 1
   for (int cb = 0; cb < TC_BN; cb += 32) {
     uint32_t v[32];
-    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + cb;
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (grow < Mc) {
+    if (KT > 0) {
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + cb;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] = 0u;
+    }
+    if (MODE == 1) {
+      float* out = C + (size_t)blockIdx.z * (size_t)K * N + (size_t)grow * N + col0 + cb;   // K ≙ Md
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(out + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    } else if (grow < Mc) {
       float* out = C + grow * N + col0 + cb;
+      const float* hd = Hd ? Hd + grow * N + col0 + cb : nullptr;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 o;
         float* po = &o.x;
+        float4 h4 = hd ? *reinterpret_cast<const float4*>(hd + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* ph = &h4.x;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-          float z = __uint_as_float(v[j + c]) + (bias ? bias[col0 + cb + j + c] : 0.f);
-          if (act == HVI_ACT_TANH) z = tanhf(z);
-          else if (act == HVI_ACT_LOGISTIC) z = 1.f / (1.f + expf(-z));
+          float z = __uint_as_float(v[j + c]);
+          if (hd) z *= act_deriv_f(act, ph[c]);
+          else {
+            z += bias ? bias[col0 + cb + j + c] : 0.f;
+            if (act == HVI_ACT_TANH) z = tanhf(z);
+            else if (act == HVI_ACT_LOGISTIC) z = 1.f / (1.f + expf(-z));
+          }
           po[c] = z;
         }
         *reinterpret_cast<float4*>(out + j) = o;
@@ -193,18 +264,31 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_BN));
 }
 
-// C = act(A·Wᵀ + b); device pointers; requires K % 32 == 0, N % 128 == 0, 16-byte aligned rows
+// C = epi(A·Wᵀ); device pointers; requires K % 32 == 0, N % 128 == 0, 16-byte aligned rows
 cudaError_t launch_dense_tc(cudaStream_t stream, const float* A, const float* W, const float* bias, float* C, int64_t Mc,
-                            int N, int K, int act) {
+                            int N, int K, int act, const float* Hd = nullptr) {
   if (K % TC_BK != 0 || N % TC_BN != 0 || Mc < 1) return cudaErrorInvalidValue;
   const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
-  cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_dense_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)((Mc + TC_BM - 1) / TC_BM), (unsigned)(N / TC_BN));
-  k_dense_tc<<<grid, TC_THREADS, smem, stream>>>(A, W, bias, C, Mc, N, K, act);
+  k_dense_tc<0><<<grid, TC_THREADS, smem, stream>>>(A, W, bias, C, Mc, N, K, act, Hd, 0);
   return cudaGetLastError();
 }
 
+// weight gradient P[split][Md x Nd] = Σ_rows X[r][:]ᵀ Y[r][:] ; Md, Nd multiples of 128
+cudaError_t launch_wgrad_tc(cudaStream_t stream, const float* X, const float* Y, float* P, int64_t rows, int Md, int Nd,
+                            int nsplit) {
+  if (Md % TC_BM != 0 || Nd % TC_BN != 0 || rows < 1 || nsplit < 1) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
+  cudaError_t e = cudaFuncSetAttribute(k_dense_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int64_t per = (rows + nsplit - 1) / nsplit;
+  per = (per + TC_BK - 1) / TC_BK * TC_BK;
+  dim3 grid((unsigned)(Md / TC_BM), (unsigned)(Nd / TC_BN), (unsigned)nsplit);
+  k_dense_tc<1><<<grid, TC_THREADS, smem, stream>>>(X, Y, nullptr, P, rows, Nd, Md, 0, nullptr, per);
+  return cudaGetLastError();
+}
 
 // ---------------------------------------------------------------------------------------
 // wide applicator, forward: g for networks with layers wider than HVI_MAX_WIDTH (BASELINE config 5:
@@ -349,7 +433,317 @@ cudaError_t launch_mlp_fwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi
   return cudaSuccess;
 }
 
+// ---------------------------------------------------------------------------------------
+// wide applicator, backward: ∇ϕg (and the cotangent of the pbm covariate inputs) from μ̄_ζ.
+// Per chunk of columns: forward keeping every activation, δ of the last layer on CUDA cores, then per
+// hidden layer  δ_{l-1} = (δ_l W_l) ⊙ act'(H_{l-1})  (k_dense_tc<0>, W_l in the reference's own
+// [in][out] layout is already K-major for this product) and  ∇W_l = H_{l-1}ᵀ δ_l  (k_dense_tc<1>, split
+// over the rows, fp32 partial tiles summed in a fixed order into a double accumulator).  The first
+// layer (K = n_covar), the last (N = n_θM) and all biases use the "skinny" reduction kernels.
+// ---------------------------------------------------------------------------------------
+constexpr int64_t WIDE_CHUNK = 65536;
+constexpr int WIDE_SPLIT = 8;        // row splits of the weight-gradient GEMM
+constexpr int SKINNY_ROWS = 512;     // rows per block of the skinny reductions
+constexpr int XS_LD = 16;            // leading dimension of the small input matrix [x ; pbm covariates ; 1]
+
+template <typename T>
+__global__ void k_build_xs(const T* __restrict__ xM, int nC, const T* __restrict__ extra, int npc, int64_t site0,
+                           int64_t rows, T* __restrict__ Xs) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  for (int i = 0; i < XS_LD; i++) {
+    T v = T(0);
+    if (i < nC) v = xM[(site0 + r) * nC + i];
+    else if (i < nC + npc) v = extra[i - nC];
+    else if (i == nC + npc) v = T(1);
+    Xs[r * XS_LD + i] = v;
+  }
+}
+
+// G[s][b] = Σ_r S[r·ls + s]·B[r·lb + b] over this block's row slice; one thread per b
+template <typename T>
+__global__ void __launch_bounds__(256) k_skinny(const T* __restrict__ S, int ls, int ns, const T* __restrict__ B, int lb,
+                                                int nbig, int64_t rows, float* __restrict__ part) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * SKINNY_ROWS;
+  const int64_t r1 = r0 + SKINNY_ROWS < rows ? r0 + SKINNY_ROWS : rows;
+  if (b >= nbig) return;
+  float acc[8];
+  for (int s = 0; s < 8; s++) acc[s] = 0.f;
+  for (int64_t r = r0; r < r1; r++) {
+    const float y = (float)B[r * lb + b];
+    for (int s = 0; s < ns; s++) acc[s] = fmaf((float)S[r * ls + s], y, acc[s]);
+  }
+  for (int s = 0; s < ns; s++) part[((size_t)blockIdx.y * ns + s) * nbig + b] = acc[s];
+}
+template <>
+__global__ void __launch_bounds__(256) k_skinny<double>(const double* __restrict__ S, int ls, int ns, const double* __restrict__ B,
+                                                        int lb, int nbig, int64_t rows, float* __restrict__ part_f) {
+  double* part = reinterpret_cast<double*>(part_f);
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * SKINNY_ROWS;
+  const int64_t r1 = r0 + SKINNY_ROWS < rows ? r0 + SKINNY_ROWS : rows;
+  if (b >= nbig) return;
+  double acc[8];
+  for (int s = 0; s < 8; s++) acc[s] = 0.0;
+  for (int64_t r = r0; r < r1; r++) {
+    const double y = B[r * lb + b];
+    for (int s = 0; s < ns; s++) acc[s] = fma(S[r * ls + s], y, acc[s]);
+  }
+  for (int s = 0; s < ns; s++) part[((size_t)blockIdx.y * ns + s) * nbig + b] = acc[s];
+}
+
+// acc[off + s·stride_s + b·stride_b] += Σ_slices part[slice·slice_stride + s·nbig + b]  (fixed order);
+// optional copy of the sums; acc == NULL only fills chunk_sum
+template <typename PT>
+__global__ void k_accum(const PT* __restrict__ part, int nslice, size_t slice_stride, int ns, int nbig,
+                        double* __restrict__ acc, int off, int stride_s, int stride_b, double* __restrict__ chunk_sum) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ns * nbig) return;
+  const int s = e / nbig, b = e % nbig;
+  double t = 0.0;
+  for (int sl = 0; sl < nslice; sl++) t += (double)part[(size_t)sl * slice_stride + (size_t)s * nbig + b];
+  if (acc) acc[off + s * stride_s + b * stride_b] += t;
+  if (chunk_sum) chunk_sum[e] = t;
+}
+
+// last layer backward: one warp per row.  z_k = Σ_i H[r][i] W[i][k]; p = act(z); δ_L[k] = μ̄·scale'·act'(p);
+// writes δ_L (rows x 8) and δ_{L-1}[r][i] = (Σ_k W[i][k] δ_L[k])·act'_{L-1}(H[r][i])
+template <typename T>
+__global__ void __launch_bounds__(256) k_wide_last_bwd(const Cfg<T> cfg, const T* __restrict__ H, const T* __restrict__ Wref,
+                                                       int act, int act_prev, int64_t rows, int K, int n_out,
+                                                       const T* __restrict__ mubar, int64_t site0, int m, int M_units,
+                                                       int64_t nb, T* __restrict__ dlast, T* __restrict__ Dprev) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  T acc[MAXP], dl[MAXP];
+  for (int k = 0; k < n_out; k++) acc[k] = T(0);
+  for (int i = lane; i < K; i += 32) {
+    const T x = H[r * K + i];
+    for (int k = 0; k < n_out; k++) acc[k] = fma(x, Wref[(size_t)i * n_out + k], acc[k]);
+  }
+  const int64_t site = site0 + r;
+  for (int k = 0; k < n_out; k++) {
+    T s = acc[k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    T d = T(0);
+    if (k < cfg.nM) {
+      const T p = act_apply<T>(act, s);
+      const T mb = M_units > 0 ? mubar[((size_t)m * cfg.nM + k) * nb + site] : mubar[site * cfg.nM + k];
+      if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb * cfg.scale_b[k];
+      else { const T q = (T)normcdfinv((double)p); d = mb * cfg.scale_b[k] * T(2.50662827463100050242) * exp(T(0.5) * q * q); }
+      d *= (act == HVI_ACT_LOGISTIC) ? p * (T(1) - p) : (act == HVI_ACT_TANH) ? T(1) - p * p : T(1);
+    }
+    dl[k] = d;
+    if (lane == 0) dlast[r * 8 + k] = d;
+  }
+  if (lane == 0) for (int k = n_out; k < 8; k++) dlast[r * 8 + k] = T(0);
+  for (int i = lane; i < K; i += 32) {
+    T s = T(0);
+    for (int k = 0; k < n_out; k++) s = fma(Wref[(size_t)i * n_out + k], dl[k], s);
+    const T h = H[r * K + i];
+    const T dv = (act_prev == HVI_ACT_TANH) ? T(1) - h * h : (act_prev == HVI_ACT_LOGISTIC) ? h * (T(1) - h) : T(1);
+    Dprev[r * K + i] = s * dv;
+  }
+}
+
+// CUDA-core fallbacks (Float64, or shapes the tensor-core kernel does not take)
+template <typename T>
+__global__ void __launch_bounds__(256) k_dgrad_simple(const T* __restrict__ D, const T* __restrict__ Wref, const T* __restrict__ Hprev,
+                                                      int act_prev, T* __restrict__ C, int64_t rows, int n_in, int n_out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * n_in) return;
+  const int64_t r = e / n_in;
+  const int i = (int)(e % n_in);
+  T s = T(0);
+  for (int j = 0; j < n_out; j++) s = fma(D[r * n_out + j], Wref[(size_t)i * n_out + j], s);
+  const T h = Hprev[r * n_in + i];
+  const T dv = (act_prev == HVI_ACT_TANH) ? T(1) - h * h : (act_prev == HVI_ACT_LOGISTIC) ? h * (T(1) - h) : T(1);
+  C[r * n_in + i] = s * dv;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_wgrad_simple(const T* __restrict__ Hprev, const T* __restrict__ D, int64_t rows, int n_in,
+                                                      int n_out, double* __restrict__ acc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_in * n_out) return;
+  const int i = e / n_out, j = e % n_out;
+  double s = 0.0;
+  for (int64_t r = 0; r < rows; r++) s += (double)Hprev[r * n_in + i] * (double)D[r * n_out + j];
+  acc[e] += s;
+}
+
+// x̄[m][c] += Σ_j W_0[nC + c][j]·(Σ_r δ_0[r][j])  for this chunk
+template <typename T>
+__global__ void k_xbar(const T* __restrict__ W0, int nC, int npc, int N, const double* __restrict__ db0_chunk,
+                       double* __restrict__ xacc_m) {
+  const int c = threadIdx.x;
+  if (c >= npc) return;
+  double s = 0.0;
+  for (int j = 0; j < N; j++) s += (double)W0[(size_t)(nC + c) * N + j] * db0_chunk[j];
+  xacc_m[c] += s;
+}
+
 size_t wide_work_elems(int max_width, int nphig) { return (size_t)2 * 65536 * max_width + (size_t)nphig + 16; }
+// elements of T (treated as 8 bytes each for the double/float mix) of the backward work space
+size_t wide_bwd_work_bytes(int nL, int max_width, int nphig) {
+  const size_t cw = (size_t)WIDE_CHUNK * max_width;
+  return 8 * ((size_t)(nL + 1) * cw + (size_t)nphig + (size_t)WIDE_SPLIT * max_width * max_width +
+              (size_t)WIDE_CHUNK * (8 + XS_LD) + (size_t)(WIDE_CHUNK / SKINNY_ROWS) * 16 * max_width + 4 * (size_t)max_width + 1024);
+}
+
+template <typename T>
+cudaError_t launch_mlp_bwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, const T* mubar,
+                                int M_units, const T* zetaP, void* work, double* grad_acc, double* xacc) {
+  if (cfg.l_bias[cfg.nL - 1] || cfg.l_out[cfg.nL - 1] > 8 || cfg.nC + cfg.npc + 1 > 8) return cudaErrorInvalidConfiguration;
+  const int nL = cfg.nL, maxw = cfg.max_width;
+  const size_t cw = (size_t)WIDE_CHUNK * maxw;
+  // carve the work space
+  T* Hbuf = reinterpret_cast<T*>(work);                  // H_0 … H_{nL-2}: nL-1 buffers
+  T* D0 = Hbuf + (size_t)(nL - 1) * cw;
+  T* D1 = D0 + cw;
+  T* wt = D1 + cw;                                       // transposed hidden weights (forward GEMMs)
+  T* extra_h = wt + cfg.nphig;
+  T* Xs = extra_h + 16;                                  // [chunk][XS_LD]
+  T* dlast = Xs + (size_t)WIDE_CHUNK * XS_LD;            // [chunk][8]
+  float* P = reinterpret_cast<float*>(dlast + (size_t)WIDE_CHUNK * 8);   // wgrad partial tiles / skinny partials
+  double* db0 = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(P) +
+                                          8 * ((size_t)WIDE_SPLIT * maxw * maxw + (size_t)(WIDE_CHUNK / SKINNY_ROWS) * 16 * maxw));
+  auto count = [&]() { if (L.counter) ++*L.counter; };
+  for (int l = 1; l < nL - 1; l++) {
+    const int n = cfg.l_in[l] * cfg.l_out[l];
+    k_transpose_w<T><<<(n + 255) / 256, 256, 0, L.stream>>>(phi + cfg.woff[l], wt + cfg.woff[l], cfg.l_in[l], cfg.l_out[l]);
+    count();
+  }
+  const int nm = M_units > 0 ? M_units : 1;
+  for (int m = 0; m < nm; m++) {
+    for (int c = 0; c < cfg.npc; c++) {
+      const T* src = M_units > 0 ? zetaP + (size_t)cfg.pbm_covar_idx[c] * M_units + m : phi + cfg.o_muP + cfg.pbm_covar_idx[c];
+      cudaError_t e = cudaMemcpyAsync(extra_h + c, src, sizeof(T), cudaMemcpyDeviceToDevice, L.stream);
+      if (e != cudaSuccess) return e;
+    }
+    for (int64_t s0 = 0; s0 < nb; s0 += WIDE_CHUNK) {
+      const int64_t rows = nb - s0 < WIDE_CHUNK ? nb - s0 : WIDE_CHUNK;
+      const int nslice = (int)((rows + SKINNY_ROWS - 1) / SKINNY_ROWS);
+      auto H = [&](int l) { return Hbuf + (size_t)l * cw; };   // output of layer l
+      // ---- forward, keeping all activations
+      k_build_xs<T><<<(unsigned)((rows + 255) / 256), 256, 0, L.stream>>>(xM, cfg.nC, extra_h, cfg.npc, s0, rows, Xs);
+      count();
+      {
+        const int N = cfg.l_out[0], K = cfg.l_in[0];
+        const int64_t n = rows * ((N + 3) / 4);
+        k_dense_simple<T><<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(nullptr, xM, cfg.nC, extra_h, s0, phi + cfg.woff[0],
+                                                                         cfg.l_bias[0] ? phi + cfg.boff[0] : nullptr,
+                                                                         cfg.l_act[0], H(0), rows, N, K);
+        count();
+      }
+      for (int l = 1; l < nL - 1; l++) {
+        const int N = cfg.l_out[l], K = cfg.l_in[l];
+        const T* b = cfg.l_bias[l] ? phi + cfg.boff[l] : nullptr;
+        bool tc = false;
+        if constexpr (sizeof(T) == 4) {
+          if (K % TC_BK == 0 && N % TC_BN == 0) {
+            cudaError_t e = launch_dense_tc(L.stream, (const float*)H(l - 1), (const float*)(wt + cfg.woff[l]), (const float*)b,
+                                            (float*)H(l), rows, N, K, cfg.l_act[l]);
+            if (e != cudaSuccess) return e;
+            tc = true;
+          }
+        }
+        if (!tc) {
+          const int64_t n = rows * ((N + 3) / 4);
+          k_dense_simple<T><<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(H(l - 1), nullptr, 0, nullptr, 0, phi + cfg.woff[l], b,
+                                                                           cfg.l_act[l], H(l), rows, N, K);
+        }
+        count();
+      }
+      // ---- last layer: δ_L and δ_{L-1}, ∇W_L
+      T* Dcur = D0;   // δ of layer l's output, [rows][l_out[l]]
+      T* Dnxt = D1;
+      {
+        const int l = nL - 1, K = cfg.l_in[l], no = cfg.l_out[l];
+        k_wide_last_bwd<T><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, L.stream>>>(
+            cfg, H(l - 1), phi + cfg.woff[l], cfg.l_act[l], cfg.l_act[l - 1], rows, K, no, mubar, s0, m, M_units, nb, dlast, Dcur);
+        count();
+        k_skinny<T><<<dim3((K + 255) / 256, nslice), 256, 0, L.stream>>>(dlast, 8, no, H(l - 1), K, K, rows, P);
+        count();
+        if constexpr (sizeof(T) == 4)
+          k_accum<float><<<(no * K + 255) / 256, 256, 0, L.stream>>>(P, nslice, (size_t)no * K, no, K, grad_acc, cfg.woff[l], 1, no, nullptr);
+        else
+          k_accum<double><<<(no * K + 255) / 256, 256, 0, L.stream>>>((const double*)P, nslice, (size_t)no * K, no, K, grad_acc, cfg.woff[l], 1, no, nullptr);
+        count();
+      }
+      // ---- hidden layers l = nL-2 … 1: bias, weight gradient, then δ of the layer below
+      for (int l = nL - 2; l >= 1; l--) {
+        const int N = cfg.l_out[l], K = cfg.l_in[l];   // Dcur: [rows][N]
+        if (cfg.l_bias[l]) {
+          k_skinny<T><<<dim3((N + 255) / 256, nslice), 256, 0, L.stream>>>(Xs + cfg.nC + cfg.npc, XS_LD, 1, Dcur, N, N, rows, P);
+          count();
+          if constexpr (sizeof(T) == 4)
+            k_accum<float><<<(N + 255) / 256, 256, 0, L.stream>>>(P, nslice, (size_t)N, 1, N, grad_acc, cfg.boff[l], 0, 1, nullptr);
+          else
+            k_accum<double><<<(N + 255) / 256, 256, 0, L.stream>>>((const double*)P, nslice, (size_t)N, 1, N, grad_acc, cfg.boff[l], 0, 1, nullptr);
+          count();
+        }
+        bool tc = false;
+        if constexpr (sizeof(T) == 4) {
+          if (K % TC_BM == 0 && N % TC_BN == 0 && K % TC_BK == 0) {
+            // ∇W_l[in][out] = H_{l-1}ᵀ δ_l
+            cudaError_t e = launch_wgrad_tc(L.stream, (const float*)H(l - 1), (const float*)Dcur, P, rows, K, N, WIDE_SPLIT);
+            if (e != cudaSuccess) return e;
+            count();
+            k_accum<float><<<(K * N + 255) / 256, 256, 0, L.stream>>>(P, WIDE_SPLIT, (size_t)K * N, 1, K * N, grad_acc, cfg.woff[l], 0, 1, nullptr);
+            count();
+            // δ_{l-1} = (δ_l W_l) ⊙ act'(H_{l-1}):  A = δ_l [rows x N], "W" = W_l as [in][out] = [K x N] row-major
+            e = launch_dense_tc(L.stream, (const float*)Dcur, (const float*)(phi + cfg.woff[l]), nullptr, (float*)Dnxt, rows, K, N,
+                                cfg.l_act[l - 1], (const float*)H(l - 1));
+            if (e != cudaSuccess) return e;
+            count();
+            tc = true;
+          }
+        }
+        if (!tc) {
+          k_wgrad_simple<T><<<(K * N + 255) / 256, 256, 0, L.stream>>>(H(l - 1), Dcur, rows, K, N, grad_acc + cfg.woff[l]);
+          count();
+          const int64_t n = rows * K;
+          k_dgrad_simple<T><<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(Dcur, phi + cfg.woff[l], H(l - 1), cfg.l_act[l - 1], Dnxt,
+                                                                           rows, K, N);
+          count();
+        }
+        T* tmp = Dcur; Dcur = Dnxt; Dnxt = tmp;
+      }
+      // ---- first layer: ∇b_0, ∇W_0 = [x; covariates]ᵀ δ_0, and the cotangent of the covariate inputs
+      {
+        const int N = cfg.l_out[0], K = cfg.l_in[0];
+        const int ns = K + 1;   // inputs + the constant 1
+        k_skinny<T><<<dim3((N + 255) / 256, nslice), 256, 0, L.stream>>>(Xs, XS_LD, ns, Dcur, N, N, rows, P);
+        count();
+        // the skinny partial is [slice][K+1][N]: rows 0..K-1 → W_0[i][j]; row K → b_0[j] (its chunk sum Σ_r δ_0 is kept for x̄)
+        const size_t sst = (size_t)ns * N;
+        double* acc_b = cfg.l_bias[0] ? grad_acc : nullptr;
+        if constexpr (sizeof(T) == 4) {
+          k_accum<float><<<(K * N + 255) / 256, 256, 0, L.stream>>>(P, nslice, sst, K, N, grad_acc, cfg.woff[0], N, 1, nullptr);
+          k_accum<float><<<(N + 255) / 256, 256, 0, L.stream>>>(P + (size_t)K * N, nslice, sst, 1, N, acc_b, cfg.boff[0], 0, 1, db0);
+        } else {
+          k_accum<double><<<(K * N + 255) / 256, 256, 0, L.stream>>>((const double*)P, nslice, sst, K, N, grad_acc, cfg.woff[0], N, 1, nullptr);
+          k_accum<double><<<(N + 255) / 256, 256, 0, L.stream>>>((const double*)P + (size_t)K * N, nslice, sst, 1, N, acc_b, cfg.boff[0], 0, 1, db0);
+        }
+        count(); count();
+        if (cfg.npc > 0 && xacc) {
+          k_xbar<T><<<1, 32, 0, L.stream>>>(phi + cfg.woff[0], cfg.nC, cfg.npc, N, db0, xacc + (size_t)(M_units > 0 ? m : 0) * cfg.npc);
+          count();
+        }
+      }
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
+  }
+  return cudaSuccess;
+}
+
+template cudaError_t launch_mlp_bwd_wide<float>(const Launch&, const Cfg<float>&, const float*, const float*, int64_t, const float*,
+                                                int, const float*, void*, double*, double*);
+template cudaError_t launch_mlp_bwd_wide<double>(const Launch&, const Cfg<double>&, const double*, const double*, int64_t,
+                                                 const double*, int, const double*, void*, double*, double*);
 
 template cudaError_t launch_mlp_fwd_wide<float>(const Launch&, const Cfg<float>&, const float*, const float*, int64_t, float*,
                                                 int, const float*, float*);

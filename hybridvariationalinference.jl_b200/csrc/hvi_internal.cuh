@@ -117,6 +117,11 @@ template <typename T>
 cudaError_t launch_mlp_fwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu,
                                 int M_units, const T* zetaP, T* work);
 size_t wide_work_elems(int max_width, int nphig);
+template <typename T>
+cudaError_t launch_mlp_bwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, const T* mubar,
+                                int M_units, const T* zetaP, void* work, double* grad_acc /*[nphig], zeroed*/,
+                                double* xacc /*[max(M_units,1)*npc], zeroed*/);
+size_t wide_bwd_work_bytes(int nL, int max_width, int nphig);
 int stream_max_rows(int sm_count);
 int mlp_bwd_max_blocks(int sm_count);
 bool stream_supported(int nP, int nM, int nO);

@@ -33,8 +33,7 @@ def test_dense_tc_matches_float64(Mc, N, K, act):
                                                ("f32", (512, 512), ("covarK2",)), ("f64", (96, 160), ())])
 def test_wide_applicator_forward(dtype, hidden, scen):
     """g for networks wider than HVI_MAX_WIDTH (BASELINE config 5 shape 5-512-512-512-512-2): hidden
-    layers on the tensor cores (Float32) -- forward paths against the oracle; the ELBO gradient of
-    the wide applicator is not built yet and must say so."""
+    layers on the tensor cores (Float32) -- forward paths and the ELBO gradient against the oracle."""
     import torch
     from helpers import O, oracle_spec
     prob = hvi_b200.DoubleMMCase(scen, dtype=dtype, hidden=hidden)
@@ -55,5 +54,13 @@ def test_wide_applicator_forward(dtype, hidden, scen):
     y_o, θP_o, θMs_o, ent_o = O.predict_hvi(spec, ϕ, data["xM"], data["xP"], zP, zMs)
     np.testing.assert_allclose(θMs, θMs_o, rtol=5 * tol, atol=tol)
     np.testing.assert_allclose(y, y_o, rtol=5 * tol, atol=tol)
-    with pytest.raises(hvi_b200.HVIError, match="wide applicator"):
-        plan.neg_elbo_withgradient(ϕ, zP, zMs)
+    # the ELBO and its gradient through the wide applicator: tensor-core forward, data-gradient and
+    # weight-gradient GEMMs (Float32), CUDA-core fallbacks (Float64)
+    nL, comps, g = plan.neg_elbo_withgradient(ϕ, zP, zMs)
+    nL_o, comps_o, g_o = O.value_and_grad(spec, ϕ, data["xM"], data["xP"], data["y_o"], data["y_unc"], zP, zMs, dtype)
+    gtol = 1e-9 if dtype == "f64" else 1e-4
+    assert abs(nL - nL_o) <= gtol * abs(nL_o), (nL, nL_o)
+    for name, r in prob.positions().items():
+        if len(r):
+            err = np.max(np.abs(g[r].astype(np.float64) - g_o[r]))
+            assert err <= gtol * np.max(np.abs(g_o[r])), (name, err, np.max(np.abs(g_o[r])))
