@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--sites", type=int, default=10_000_000, help="sites per GPU")
     ap.add_argument("--n-mc", type=int, default=64)
     ap.add_argument("--scenario", default="", help="comma-separated DoubleMMCase scenario flags")
+    ap.add_argument("--hidden", default="", help="comma-separated hidden widths of g (BASELINE config 5: 512,512,512,512)")
     ap.add_argument("--nan-frac", type=float, default=0.0, help="fraction of sites with missing drivers (:driverNAN generalised)")
     ap.add_argument("--cpu-sample-sites", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -154,7 +155,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    prob = hvi_b200.DoubleMMCase(tuple(s for s in args.scenario.split(",") if s), dtype="f32")
+    hidden = tuple(int(w) for w in args.hidden.split(",") if w) or None
+    prob = hvi_b200.DoubleMMCase(tuple(s for s in args.scenario.split(",") if s), dtype="f32", hidden=hidden)
     nb, M = args.sites, args.n_mc
     # synthetic batch of this rank's site shard (generator restates gen_hybridproblem_synthetic)
     data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=111 + rank, driver_nan_frac=args.nan_frac)
