@@ -21,7 +21,8 @@ constexpr int TC_BM = 128;      // rows per CTA = TMEM lanes
 constexpr int TC_BN = 128;      // output columns per CTA = TMEM columns
 constexpr int TC_BK = 32;       // K per stage: 32 tf32 = one 128-byte swizzle row
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;     // 8 warps: two per scheduler for the split/store phase; warps 0-3 and 4-7 share the epilogue
+constexpr int TC_LD = 1024 / TC_THREADS;   // float4 per thread, operand and stage (= 4)
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;              // 16 KB per operand half
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;             // A hi, A lo, B hi, B lo
 
@@ -63,10 +64,9 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
 }
 
 // round to nearest tf32 (10-bit mantissa), result as an fp32 bit pattern
+// (integer add + mask on the ALU pipe: the cvt.rna.tf32 instruction runs at the 16/clk conversion rate)
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // split 4 fp32 values into tf32 hi / residual lo and store both as one 16-byte chunk each at the
@@ -113,8 +113,10 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
   __shared__ uint32_t tmem_base_s;
   unsigned char* tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * TC_BM;   // MODE 0: first row of C;  MODE 1: first m
-  const int col0 = blockIdx.y * TC_BN;                 // first column of C / first n
+  // MODE 0: blockIdx.x = column tile (fastest: the CTAs that share a row tile of A run together and
+  // re-read it from L2), blockIdx.y = row tile.  MODE 1: blockIdx.x = m tile, blockIdx.y = n tile.
+  const int64_t row0 = (int64_t)(MODE == 0 ? blockIdx.y : blockIdx.x) * TC_BM;
+  const int col0 = (MODE == 0 ? blockIdx.x : blockIdx.y) * TC_BN;
   if (t == 0) {
     for (int s = 0; s < TC_STAGES; s++) mbar_init(&bar_mma[s], 1);
     mbar_init(&bar_done, 1);
@@ -139,57 +141,65 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
   const int KT = MODE == 0 ? K / TC_BK : (int)((r_end - r_begin + TC_BK - 1) / TC_BK);
   // 8 + 8 float4 per thread and stage.  The global loads of tile kt+1 are issued right after tile
   // kt has been handed to the tensor core, so their latency overlaps the MMAs.
-  float4 va[8], vb[8];
-  auto load_tile = [&](int kt_) {
-    if (MODE == 0) {   // element e = i*128 + t → row e/8, 16-byte chunk e%8 of the K-major tile
+  // two register sets: the global loads of tile kt+1 are issued before tile kt is split and stored,
+  // so a full iteration (stores, barrier, MMA issue) hides their latency
+  float4 va[2][TC_LD], vb[2][TC_LD];
+  auto load_tile = [&](int kt_, float4 (&xa)[TC_LD], float4 (&xb)[TC_LD]) {
+    if (MODE == 0) {   // element e = i*TC_THREADS + t → row e/8, 16-byte chunk e%8 of the K-major tile
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
+      for (int i = 0; i < TC_LD; i++) {
         const int e = i * TC_THREADS + t, r = e >> 3, c = e & 7;
         const int64_t gr = row0 + r;
-        va[i] = gr < Mc ? __ldg(reinterpret_cast<const float4*>(A + gr * K + (size_t)kt_ * TC_BK + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        vb[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)(col0 + r) * K + (size_t)kt_ * TC_BK + c * 4));
+        xa[i] = gr < Mc ? __ldg(reinterpret_cast<const float4*>(A + gr * K + (size_t)kt_ * TC_BK + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xb[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)(col0 + r) * K + (size_t)kt_ * TC_BK + c * 4));
       }
-    } else {           // lane ↔ row r of the step, warp w covers m (n) = 32w … 32w+31, four at a time
+    } else {           // lane ↔ row r of the step, warp w covers m (n) = 16w … 16w+15, four at a time
       const int64_t gr = r_begin + (int64_t)kt_ * TC_BK + lane;
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int m4 = warp * 8 + i;
-        va[i] = gr < r_end ? __ldg(reinterpret_cast<const float4*>(A + gr * K + row0 + 4 * m4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        vb[i] = gr < r_end ? __ldg(reinterpret_cast<const float4*>(W + gr * N + col0 + 4 * m4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < TC_LD; i++) {
+        const int m4 = warp * TC_LD + i;
+        xa[i] = gr < r_end ? __ldg(reinterpret_cast<const float4*>(A + gr * K + row0 + 4 * m4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xb[i] = gr < r_end ? __ldg(reinterpret_cast<const float4*>(W + gr * N + col0 + 4 * m4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   };
-  if (KT > 0) load_tile(0);
-  for (int kt = 0; kt < KT; kt++) {
-    const int s = kt % TC_STAGES;
-    // the stage is free once the MMAs issued TC_STAGES iterations ago have completed
-    if (kt >= TC_STAGES) mbar_wait(&bar_mma[s], ((kt / TC_STAGES) - 1) & 1);
-    unsigned char* st = tiles + (size_t)s * TC_STAGE_BYTES;
+  auto store_tile = [&](unsigned char* st, const float4 (&xa)[TC_LD], const float4 (&xb)[TC_LD]) {
     if (MODE == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
+      for (int i = 0; i < TC_LD; i++) {
         const int e = i * TC_THREADS + t, r = e >> 3, c = e & 7;
-        split_store(st, st + TC_TILE_BYTES, r, c, va[i]);
-        split_store(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, r, c, vb[i]);
+        split_store(st, st + TC_TILE_BYTES, r, c, xa[i]);
+        split_store(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, r, c, xb[i]);
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int m = 4 * (warp * 8 + i);
-        split_store1(st, st + TC_TILE_BYTES, m + 0, lane, va[i].x);
-        split_store1(st, st + TC_TILE_BYTES, m + 1, lane, va[i].y);
-        split_store1(st, st + TC_TILE_BYTES, m + 2, lane, va[i].z);
-        split_store1(st, st + TC_TILE_BYTES, m + 3, lane, va[i].w);
-        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 0, lane, vb[i].x);
-        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 1, lane, vb[i].y);
-        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 2, lane, vb[i].z);
-        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 3, lane, vb[i].w);
+      for (int i = 0; i < TC_LD; i++) {
+        const int m = 4 * (warp * TC_LD + i);
+        split_store1(st, st + TC_TILE_BYTES, m + 0, lane, xa[i].x);
+        split_store1(st, st + TC_TILE_BYTES, m + 1, lane, xa[i].y);
+        split_store1(st, st + TC_TILE_BYTES, m + 2, lane, xa[i].z);
+        split_store1(st, st + TC_TILE_BYTES, m + 3, lane, xa[i].w);
+        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 0, lane, xb[i].x);
+        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 1, lane, xb[i].y);
+        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 2, lane, xb[i].z);
+        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 3, lane, xb[i].w);
       }
     }
+  };
+  if (KT > 0) load_tile(0, va[0], vb[0]);
+#pragma unroll 2
+  for (int kt = 0; kt < KT; kt++) {
+    const int s = kt % TC_STAGES;
+    if (kt + 1 < KT) {
+      if (kt & 1) load_tile(kt + 1, va[0], vb[0]); else load_tile(kt + 1, va[1], vb[1]);
+    }
+    // the stage is free once the MMAs issued TC_STAGES iterations ago have completed
+    if (kt >= TC_STAGES) mbar_wait(&bar_mma[s], ((kt / TC_STAGES) - 1) & 1);
+    unsigned char* st = tiles + (size_t)s * TC_STAGE_BYTES;
+    if (kt & 1) store_tile(st, va[1], vb[1]); else store_tile(st, va[0], vb[0]);
     // generic-proxy writes → visible to the tensor core's async proxy
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (kt + 1 < KT) load_tile(kt + 1);
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_TILE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
@@ -209,12 +219,14 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
   // epilogue: TMEM → registers → global.  Warp w owns TMEM lanes 32w … 32w+31.
   if (KT > 0) mbar_wait(&bar_done, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int64_t grow = row0 + warp * 32 + lane;
+  // warp w may only touch TMEM lanes 32·(w mod 4) …; warps 0-3 take the first half of the columns, 4-7 the second
+  const int wq = warp & 3;
+  const int64_t grow = row0 + wq * 32 + lane;
 #pragma unroll 1
-  for (int cb = 0; cb < TC_BN; cb += 32) {
+  for (int cb = (warp >> 2) * (TC_BN / 2); cb < ((warp >> 2) + 1) * (TC_BN / 2); cb += 32) {
     uint32_t v[32];
     if (KT > 0) {
-      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + cb;
+      const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + cb;
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -271,7 +283,7 @@ cudaError_t launch_dense_tc(cudaStream_t stream, const float* A, const float* W,
   const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
   cudaError_t e = cudaFuncSetAttribute(k_dense_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  dim3 grid((unsigned)((Mc + TC_BM - 1) / TC_BM), (unsigned)(N / TC_BN));
+  dim3 grid((unsigned)(N / TC_BN), (unsigned)((Mc + TC_BM - 1) / TC_BM));
   k_dense_tc<0><<<grid, TC_THREADS, smem, stream>>>(A, W, bias, C, Mc, N, K, act, Hd, 0);
   return cudaGetLastError();
 }
@@ -443,7 +455,7 @@ cudaError_t launch_mlp_fwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi
 // ---------------------------------------------------------------------------------------
 constexpr int64_t WIDE_CHUNK = 65536;
 constexpr int WIDE_SPLIT = 8;        // row splits of the weight-gradient GEMM
-constexpr int SKINNY_ROWS = 512;     // rows per block of the skinny reductions
+constexpr int SKINNY_ROWS = 128;     // rows per block of the skinny reductions (many blocks: the kernel is latency bound)
 constexpr int XS_LD = 16;            // leading dimension of the small input matrix [x ; pbm covariates ; 1]
 
 template <typename T>
@@ -470,7 +482,18 @@ __global__ void __launch_bounds__(256) k_skinny(const T* __restrict__ S, int ls,
   if (b >= nbig) return;
   float acc[8];
   for (int s = 0; s < 8; s++) acc[s] = 0.f;
-  for (int64_t r = r0; r < r1; r++) {
+  int64_t r = r0;
+  for (; r + 4 <= r1; r += 4) {   // four independent loads in flight per thread
+    const float y0 = (float)B[r * lb + b], y1 = (float)B[(r + 1) * lb + b], y2 = (float)B[(r + 2) * lb + b],
+                y3 = (float)B[(r + 3) * lb + b];
+    for (int s = 0; s < ns; s++) {
+      acc[s] = fmaf((float)S[r * ls + s], y0, acc[s]);
+      acc[s] = fmaf((float)S[(r + 1) * ls + s], y1, acc[s]);
+      acc[s] = fmaf((float)S[(r + 2) * ls + s], y2, acc[s]);
+      acc[s] = fmaf((float)S[(r + 3) * ls + s], y3, acc[s]);
+    }
+  }
+  for (; r < r1; r++) {
     const float y = (float)B[r * lb + b];
     for (int s = 0; s < ns; s++) acc[s] = fmaf((float)S[r * ls + s], y, acc[s]);
   }
