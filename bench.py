@@ -186,19 +186,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
     l0 = plan.launch_count
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     barrier()
-    sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
     launches = plan.launch_count - l0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -217,6 +216,7 @@ def main():
         for k, v in plan.kernel_times_ms().items():
             acc.setdefault(k, []).append(v)
     plan.set_profiling(False)
+    sampler.stop_flag = True
     kt = {k: float(np.mean(v)) for k, v in acc.items()}
     nO, nM = prob.n_obs, prob.n_M
     # site records + μ_ζ/μ̄_ζ hand-off + ξ (+ per-draw means and their cotangents with pbm covariates)
@@ -228,8 +228,17 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (kt["stream"] * 1e-3) / 1e9
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    # workload (profiles/traffic.json, written from the capture by profiles/summarize_ncu.py); null if
+    # this workload has no capture
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(f"k_stream:{args.scenario}:{nb}x{M}", {}).get("dram_bytes")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_stream<float,2,2,8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kt}
 
