@@ -20,6 +20,7 @@ HVI_SRC_P, HVI_SRC_M, HVI_SRC_FIX = 0, 1, 2
 HVI_ACT_IDENTITY, HVI_ACT_TANH, HVI_ACT_LOGISTIC = 0, 1, 2
 HVI_SCALE_NORMAL, HVI_SCALE_RANGE = 0, 1
 HVI_FLAG_OMIT_PRIORS = 1
+HVI_APPROX_MEAN, HVI_APPROX_MEANVAR_SEP = 0, 1
 
 
 class hvi_layer(C.Structure):
@@ -45,6 +46,8 @@ class hvi_desc(C.Structure):
         ("slot_src", C.c_int32 * 4), ("slot_idx", C.c_int32 * 4), ("slot_fix", C.c_double * 4),
         ("n_pbm_covar", C.c_int32), ("pbm_covar_idx", C.c_int32 * HVI_MAX_PAR),
         ("count_globals", C.c_int32),
+        ("approx", C.c_int32),
+        ("n_site_total", C.c_int64),
     ]
 
 
@@ -67,6 +70,7 @@ SYMBOLS = [
     ("hvi_utri2vec_pos", _I64, [_I64, _I64]),
     ("hvi_cor_count", _I64, [C.POINTER(_I32), _I32]),
     ("hvi_plan_set_data", _INT, [_P, _I64, _P, _P, _P, _P, _INT]),
+    ("hvi_plan_set_sites", _INT, [_P, C.POINTER(_I64), _I64]),
     ("hvi_neg_elbo_grad", _INT, [_P, _I32, _P, _P, _P, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_rng", _INT, [_P, _I32, _P, _U64, _I64, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_async", _INT, [_P, _I32, _P, _P, _P, _U64, _I64, _P, _P]),

@@ -26,6 +26,7 @@ struct hvi_plan {
   int64_t nb;
   void *d_xM, *d_rec, *d_mu, *d_mubar;
   void* d_xP;   // raw drivers (2 n_obs x nb), kept for the prediction path
+  int64_t* d_isites;   // MeanVarSep: global site index of every site of the batch (NULL: identity)
   int has_obs;
   double const_nly;
   int64_t anomalies;
@@ -138,7 +139,9 @@ static void fill_cfg(const hvi_desc& d, Cfg<T>& c) {
   c.sum_width += d.layers[d.n_layers - 1].n_out;
   c.nphig = p;
   c.o_ls2P = p; p += c.nP;
-  c.o_coef = p; p += 2 * c.nM;
+  c.sepvar = d.approx == HVI_APPROX_MEANVAR_SEP ? 1 : 0;
+  c.n_site_total = (int)d.n_site_total;
+  c.o_coef = p; p += c.sepvar ? c.nM * c.n_site_total : 2 * c.nM;
   c.o_rhoP = p; p += block_maps(d.cor_ends_P, d.n_cor_ends_P, c.nP, c.blkP_start, c.rhoP_off);
   c.o_rhoM = p; p += block_maps(d.cor_ends_M, d.n_cor_ends_M, c.nM, c.blkM_start, c.rhoM_off);
   c.o_muP = p; p += c.nP;
@@ -191,6 +194,9 @@ static const char* validate(const hvi_desc* d) {
     if (d->prior_M[i].kind < 0 || d->prior_M[i].kind > 2) return "prior_M kind invalid";
     if (d->prior_M[i].kind && !(d->prior_M[i].b > 0)) return "prior_M scale must be positive";
   }
+  if (d->approx != HVI_APPROX_MEAN && d->approx != HVI_APPROX_MEANVAR_SEP) return "approx invalid";
+  if (d->approx == HVI_APPROX_MEANVAR_SEP && (d->n_site_total < 1 || d->n_site_total * d->n_M > 1000000000LL))
+    return "MeanVarSep needs 1 <= n_site_total (and n_M*n_site_total <= 1e9)";
   if (!stream_supported(d->n_P, d->n_M, d->n_obs)) return "(n_P, n_M, n_obs) combination has no kernel instantiation";
   if (d->n_pbm_covar > 0 && !mlp_supports_pbm(d) && !is_wide(d))
     return "pbm_covars need one of the register-tiled applicator shapes (5-20-20-2, 6-24-24-2) or a wide network";
@@ -220,7 +226,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   fill_cfg<float>(*desc, p->cf);
   fill_cfg<double>(*desc, p->cd);
   p->nb = 0; p->launches = 0;
-  p->d_xM = p->d_rec = p->d_mu = p->d_mubar = nullptr; p->d_xP = nullptr; p->has_obs = 0;
+  p->d_xM = p->d_rec = p->d_mu = p->d_mubar = nullptr; p->d_xP = nullptr; p->has_obs = 0; p->d_isites = nullptr;
   p->d_phi = p->d_zP = p->d_zMs = p->d_ec = p->d_pdraw = nullptr;
   p->cap_zP = p->cap_zMs = p->cap_pdraw = 0;
   p->d_MU = p->d_MUBAR = nullptr; p->d_part_x = p->d_xred = nullptr;
@@ -271,7 +277,7 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   if (!p) return HVI_OK;
   cudaSetDevice(p->desc.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
-  void* dev[] = {p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
+  void* dev[] = {p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
                  p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide, p->d_wide_bwd, p->d_gacc};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
@@ -321,6 +327,19 @@ extern "C" int64_t hvi_cor_count(const int32_t* cor_ends, int32_t n) {
 }
 
 extern "C" int64_t hvi_launch_count(const hvi_plan* p) { return p ? p->launches : -1; }
+
+extern "C" int hvi_plan_set_sites(hvi_plan* p, const int64_t* i_sites, int64_t n) {
+  if (!p) return HVI_EINVAL;
+  if (p->nb <= 0) PLAN_FAIL(p, HVI_ENODATA, "hvi_plan_set_data has not been called");
+  if (!i_sites || n != p->nb) PLAN_FAIL(p, HVI_EINVAL, "set_sites: need one index per site of the registered batch");
+  if (p->cf.sepvar)
+    for (int64_t i = 0; i < n; i++)
+      if (i_sites[i] < 0 || i_sites[i] >= p->cf.n_site_total) PLAN_FAIL(p, HVI_EINVAL, "set_sites: index out of range");
+  CU(p, cudaSetDevice(p->desc.device));
+  if (!p->d_isites) CU(p, cudaMalloc((void**)&p->d_isites, sizeof(int64_t) * (size_t)n));
+  CU(p, cudaMemcpy(p->d_isites, i_sites, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice));
+  return HVI_OK;
+}
 
 extern "C" int hvi_plan_set_profiling(hvi_plan* p, int on) {
   if (!p) return HVI_EINVAL;
@@ -400,6 +419,8 @@ extern "C" int hvi_plan_set_data(hvi_plan* p, int64_t n_site, const void* xM, co
   if ((y_o == nullptr) != (y_unc == nullptr)) PLAN_FAIL(p, HVI_EINVAL, "set_data: y_o and y_unc must both be given or both be NULL");
   if (mem_kind != HVI_MEM_HOST && mem_kind != HVI_MEM_DEVICE) PLAN_FAIL(p, HVI_EINVAL, "set_data: bad mem_kind");
   CU(p, cudaSetDevice(p->desc.device));
+  if (p->cf.sepvar && n_site > p->cf.n_site_total) PLAN_FAIL(p, HVI_EINVAL, "set_data: batch has more sites than n_site_total");
+  if (p->d_isites) { cudaFree(p->d_isites); p->d_isites = nullptr; }   // back to the identity map
   return p->dtype == HVI_F32 ? set_data_t<float>(p, n_site, xM, xP, y_o, y_unc, mem_kind)
                              : set_data_t<double>(p, n_site, xM, xP, y_o, y_unc, mem_kind);
 }
@@ -470,6 +491,12 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   a.MU = pbm ? (const T*)p->d_MU : nullptr; a.MUBAR = pbm ? (T*)p->d_MUBAR : nullptr;
   a.staged = !rng && (M % (16 / (int)sizeof(T)) == 0) && (((uintptr_t)zMs & 15) == 0);
   a.rng = rng ? 1 : 0; a.seed = seed; a.col_offset = site_offset * cfg.nM;
+  a.phi = phi; a.i_sites = p->d_isites; a.out = out; a.grad_T = grad_T;
+  if (cfg.sepvar) {   // sites outside the batch have zero gradient
+    const size_t big = (size_t)cfg.nM * cfg.n_site_total;
+    CU(p, cudaMemsetAsync(out + cfg.o_coef, 0, sizeof(double) * big, s));
+    if (grad_T) CU(p, cudaMemsetAsync(grad_T + cfg.o_coef, 0, sizeof(T) * big, s));
+  }
   int nrows = 0, nblk = 0, nblk2 = 0;
   CU(p, launch_stream<T>(L, cfg, a, &nrows, p->max_rows));
   MARK();
@@ -646,6 +673,7 @@ static int generate_zeta_t(hvi_plan* p, int M, const void* phi, const void* zP, 
   StreamArgs<T> a;
   memset(&a, 0, sizeof a);
   a.mu = (const T*)p->d_mu; a.zMs = dzM; a.ec = ec; a.nb = nb; a.M = M;
+  a.phi = dphi; a.i_sites = p->d_isites;
   if (cfg.npc > 0) {
     rc = ensure(p, &p->d_MU, &p->cap_MU, (int64_t)sizeof(T) * M * nM * nb);
     if (rc) { if (tmp) cudaFree(tmp); return rc; }
@@ -770,6 +798,7 @@ static int predict_t(hvi_plan* p, int M, const void* phi, const void* zP, const 
   memset(&a, 0, sizeof a);
   a.mu = (const T*)p->d_mu; a.zMs = dzM; a.ec = ec; a.nb = nb; a.M = M;
   a.rng = rng ? 1 : 0; a.seed = seed; a.col_offset = site_offset * nM;
+  a.phi = dphi; a.i_sites = p->d_isites;
   if (e == cudaSuccess && cfg.npc > 0) {
     rc = ensure(p, &p->d_MU, &p->cap_MU, (int64_t)sizeof(T) * M * nM * nb);
     if (rc) { if (tmp) cudaFree(tmp); cudaFree(d_ls); return rc; }

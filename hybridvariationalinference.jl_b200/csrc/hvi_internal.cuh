@@ -36,6 +36,8 @@ struct Cfg {
   int scale_kind;
   T scale_a[MAXP], scale_b[MAXP];
   int npc, pbm_covar_idx[MAXP];
+  // MeanVarSepHVIApproximation (src/elbo_sepvec.jl): o_coef is then the offset of logσ2_ζMs (nM × n_site_total)
+  int sepvar, n_site_total;
 };
 
 // Per-evaluation constants derived from ϕq by the prologue kernel.
@@ -67,6 +69,10 @@ struct StreamArgs {
   int64_t nb;
   int M;
   int pd_in_smem;    // 1: the kernel copies pd into shared memory (it fits)
+  const T* phi;      // MeanVarSep: ϕ (per-site log-variances are read from it) …
+  const int64_t* i_sites;   // … at the batch's global site indices (NULL: 0..nb-1)
+  double* out;       // … and their gradient goes straight into the result vector
+  T* grad_T;
   int rng;           // 1: draw ξ inside the kernel from (seed, col_offset + site·n_θM + k, draw); zMs unused
   uint64_t seed;
   int64_t col_offset;

@@ -223,7 +223,10 @@ __global__ void k_prologue(const __grid_constant__ Cfg<T> cfg, const T* __restri
   if (threadIdx.x == 0) {
     build_U<T>(nP, cfg.blkP_start, cfg.rhoP_off, phi + cfg.o_rhoP, s.UP, s.nrmP);
     build_U<T>(nM, cfg.blkM_start, cfg.rhoM_off, phi + cfg.o_rhoM, s.UM, s.nrmM);
-    for (int k = 0; k < nM; k++) { s.coefA[k] = phi[cfg.o_coef + 2 * k]; s.coefB[k] = phi[cfg.o_coef + 2 * k + 1]; }
+    for (int k = 0; k < nM; k++) {   // intercept and slope of log σ² (src/elbo.jl:652-653); MeanVarSep has neither
+      s.coefA[k] = cfg.sepvar ? T(0) : phi[cfg.o_coef + 2 * k];
+      s.coefB[k] = cfg.sepvar ? T(0) : phi[cfg.o_coef + 2 * k + 1];
+    }
     for (int j = 0; j < nP; j++) { s.sigP[j] = exp_t(phi[cfg.o_ls2P + j] / T(2)); s.muP[j] = phi[cfg.o_muP + j]; }
     *ec = s;
   }
@@ -1019,6 +1022,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
   for (int64_t tile = (int64_t)blockIdx.x * NWARP + warp; tile < ntiles; tile += (int64_t)gridDim.x * NWARP) {
     const int64_t site = tile * 32 + lane;
     const bool active = site < a.nb;
+    const int64_t isite = (cfg.sepvar && active && a.i_sites) ? a.i_sites[site] : site;   // global site index
     {
       const T* r = a.rec + (tile * 4 * NO) * 32 + lane;
       constexpr int NOP = SiteState<T, NP, NM, NO>::NOP;
@@ -1037,7 +1041,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
 #pragma unroll
     for (int k = 0; k < NM; k++) {
       st.mu[k] = active ? a.mu[site * NM + k] : T(0);
-      ls[k] = fma(cB[k], st.mu[k], cA[k]);
+      // log σ²: intercept + slope·μ_ζ (src/elbo.jl:652-653) or the site's own parameter (src/elbo_sepvec.jl:23)
+      ls[k] = (cfg.sepvar && active) ? a.phi[cfg.o_coef + isite * NM + k] : fma(cB[k], st.mu[k], cA[k]);
       sig[k] = exp_t(T(0.5) * ls[k]);
       st.smu[k] = T(0);
 #pragma unroll
@@ -1174,10 +1179,20 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
         for (int j = 0; j <= k; j++) sr = fma(st.sU[ut(j, k)], st.sz[ut(j, k)], sr);
         const T lsb = T(0.5) * wM * sr - T(0.5);          // −½ from the entropy
         acc[ACC_LOGSIG] += T(0.5) * ls[k];
-        acc[ACC_FIRST_VEC + k] = lsb;
-        acc[ACC_FIRST_VEC + NM + k] = lsb * st.mu[k];
-        // with pbm covariates the pass-1 mean feeds σ only (src/elbo.jl:491-495)
-        a.mubar[site * NM + k] = PBM ? lsb * cB[k] : fma(wM, st.smu[k], lsb * cB[k]);
+        if (cfg.sepvar) {
+          // the gradient w.r.t. this site's own log-variance goes straight to its slot of ∇ϕ; the
+          // slot of ā counts non-finite entries instead
+          const int64_t o = (int64_t)cfg.o_coef + isite * NM + k;
+          a.out[o] = (double)lsb;
+          if (a.grad_T) a.grad_T[o] = lsb;
+          acc[ACC_FIRST_VEC + k] = isfinite(lsb) ? T(0) : T(1);
+          a.mubar[site * NM + k] = PBM ? T(0) : wM * st.smu[k];
+        } else {
+          acc[ACC_FIRST_VEC + k] = lsb;
+          acc[ACC_FIRST_VEC + NM + k] = lsb * st.mu[k];
+          // with pbm covariates the pass-1 mean feeds σ only (src/elbo.jl:491-495)
+          a.mubar[site * NM + k] = PBM ? lsb * cB[k] : fma(wM, st.smu[k], lsb * cB[k]);
+        }
 #pragma unroll
         for (int j = 0; j <= k; j++) acc[ACC_FIRST_VEC + 2 * NM + ut(j, k)] = sig[k] * st.sz[ut(j, k)];
       }
@@ -1332,7 +1347,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
   const int t = threadIdx.x;
   const int nP = cfg.nP, nM = cfg.nM;
   const int NACC = nacc(nP, nM);
-  const int nq = cfg.nphi - cfg.nphig;
+  // MeanVarSep: the block logσ2_ζMs (nM × n_site_total) is written by the streaming kernel; everything
+  // here works on ∇ϕq with that block cut out
+  const int big = cfg.sepvar ? nM * cfg.n_site_total : 0;
+  const int nq = cfg.nphi - cfg.nphig - big;
   double bad = 0.0;
   for (int e = t; e < nred_blocks; e += FIN_THREADS) bad += red[128 + e];
   for (int e = t; e < NACC; e += FIN_THREADS) sacc[e] = red[e];
@@ -1387,7 +1405,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
     const double* cU = bbar + nM;
     const double* aPs = cU + NUM;
     const double* cPs = aPs + nP;
-    double* G = sq - cfg.nphig;   // G[o] for o >= nphig
+    // G(o): slot of ϕ position o (≥ nphig, outside the logσ2_ζMs block) in the compressed vector
+    auto Gp = [&](int o) -> double* { return sq + (o - cfg.nphig - ((cfg.sepvar && o >= cfg.o_coef + big) ? big : 0)); };
     double nLy = 0.5 * w * sacc[ACC_NLY] + const_nly;
     double nlp = w * sacc[ACC_PRIOR];
     double lj = w * sacc[ACC_LJ];
@@ -1395,12 +1414,13 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
     if (!cfg.omit_priors)
       for (int k = 0; k < nM; k++) nlp += (double)nb * cfg.prM_c0[k];
     // coefficients of log σ²
-    for (int k = 0; k < nM; k++) { G[cfg.o_coef + 2 * k] = abar[k]; G[cfg.o_coef + 2 * k + 1] = bbar[k]; }
+    if (!cfg.sepvar)
+      for (int k = 0; k < nM; k++) { *Gp(cfg.o_coef + 2 * k) = abar[k]; *Gp(cfg.o_coef + 2 * k + 1) = bbar[k]; }
     // M block: Ū = w·cU (columns restricted to their block) → ρ̄sM
     double Ubar[MAXP][MAXP];
     for (int k = 0; k < nM; k++)
       for (int j = 0; j <= k; j++) Ubar[j][k] = w * cU[k * (k + 1) / 2 + j];
-    build_U_adj<T>(nM, cfg.blkM_start, cfg.rhoM_off, ec.UM, ec.nrmM, Ubar, G + cfg.o_rhoM);
+    build_U_adj<T>(nM, cfg.blkM_start, cfg.rhoM_off, ec.UM, ec.nrmM, Ubar, Gp(cfg.o_rhoM));
     // global block
     double CP[MAXP][MAXP];
     for (int j = 0; j < nP; j++) {
@@ -1417,18 +1437,18 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
         aP += sPx[j][0];
         for (int jj = 0; jj <= j; jj++) CP[jj][j] += sPx[j][1 + jj];
       }
-      G[cfg.o_muP + j] += aP;
+      *Gp(cfg.o_muP + j) += aP;
       // Σ_m ζ̄P[j,m]·rP[j,m] = σP[j] Σ_{jj} UP[jj][j]·CP[jj][j]
       double sr = 0;
       for (int jj = cfg.blkP_start[j]; jj <= j; jj++) sr += (double)ec.UP[jj][j] * CP[jj][j];
       sr *= (double)ec.sigP[j];
-      G[cfg.o_ls2P + j] = 0.5 * sr - (cfg.count_globals ? 0.5 : 0.0);
+      *Gp(cfg.o_ls2P + j) = 0.5 * sr - (cfg.count_globals ? 0.5 : 0.0);
       for (int jj = 0; jj <= j; jj++) Ubar[jj][j] = (double)ec.sigP[j] * CP[jj][j];
     }
-    build_U_adj<T>(nP, cfg.blkP_start, cfg.rhoP_off, ec.UP, ec.nrmP, Ubar, G + cfg.o_rhoP);
+    build_U_adj<T>(nP, cfg.blkP_start, cfg.rhoP_off, ec.UP, ec.nrmP, Ubar, Gp(cfg.o_rhoP));
     // pass 1 of g took μP[idx] as input (src/elbo.jl:491)
     if (xs)
-      for (int c = 0; c < cfg.npc; c++) G[cfg.o_muP + cfg.pbm_covar_idx[c]] += xs[c];
+      for (int c = 0; c < cfg.npc; c++) *Gp(cfg.o_muP + cfg.pbm_covar_idx[c]) += xs[c];
     const double Kdim = (double)nM * (double)nb + (cfg.count_globals ? nP : 0);
     const double ent = 0.5 * Kdim * 2.8378770664093454836 + logsig;   // (K·log(2πe) + 2Σlog σ)/2, logden_normal.jl:74
     const double nlj = -lj;
@@ -1439,10 +1459,13 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
   __syncthreads();
   for (int e = t; e < nq + 7; e += FIN_THREADS) {
     const double v = sq[e];
-    out[cfg.nphig + e] = v;
-    if (grad_T && e < nq) grad_T[cfg.nphig + e] = (T)v;
+    const int o = cfg.nphig + e + ((cfg.sepvar && cfg.nphig + e >= cfg.o_coef) ? big : 0);   // back to ϕ positions
+    out[o] = v;
+    if (grad_T && e < nq) grad_T[o] = (T)v;
     bad += isfinite(v) ? 0.0 : 1.0;
   }
+  if (cfg.sepvar && t == 0)
+    for (int k = 0; k < nM; k++) bad += sacc[ACC_FIRST_VEC + k];
   bad = block_sum_fixed(bad, sred);
   if (t == 0) out[cfg.nphi + 7] = bad;
 }
@@ -1497,7 +1520,8 @@ __global__ void __launch_bounds__(256) k_generate_zeta(const __grid_constant__ C
     const int64_t i = e / nM;
     const int k = (int)(e % nM);
     const T mu = a.mu[i * nM + k];
-    const T sg = exp_t(T(0.5) * (ec.coefA[k] + ec.coefB[k] * mu));
+    const T sg = exp_t(T(0.5) * (cfg.sepvar ? a.phi[cfg.o_coef + (a.i_sites ? a.i_sites[i] : i) * nM + k]
+                                            : ec.coefA[k] + ec.coefB[k] * mu));
     sigma[nP + i * nM + k] = sg;
     for (int m = 0; m < M; m++) {
       T t = T(0);
@@ -1541,7 +1565,7 @@ __global__ void __launch_bounds__(256) k_predict(const __grid_constant__ Cfg<T> 
     T mu[MAXP], sg[MAXP], S1[32], S2[32];
     for (int k = 0; k < nM; k++) {
       mu[k] = a.mu[i * nM + k];
-      const T ls = ec.coefA[k] + ec.coefB[k] * mu[k];
+      const T ls = cfg.sepvar ? a.phi[cfg.o_coef + (a.i_sites ? a.i_sites[i] : i) * nM + k] : ec.coefA[k] + ec.coefB[k] * mu[k];
       sg[k] = exp(T(0.5) * ls);
       logsig += 0.5 * (double)ls;
     }

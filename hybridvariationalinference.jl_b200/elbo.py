@@ -99,7 +99,7 @@ class NegElboPlan:
         off = (C.c_int64 * 6)()
         ln = (C.c_int64 * 6)()
         self._check(self.lib.hvi_phi_positions(self._h, off, ln))
-        names = ("ϕg", "logσ2_ζP", "coef_logσ2_ζMs", "ρsP", "ρsM", "μP")
+        names = ("ϕg", "logσ2_ζP", "logσ2_ζMs" if self.prob.is_sepvar else "coef_logσ2_ζMs", "ρsP", "ρsM", "μP")
         return {n: range(off[i], off[i] + ln[i]) for i, n in enumerate(names)}
 
     @property
@@ -116,7 +116,7 @@ class NegElboPlan:
         return dict(zip(("prologue", "mlp_fwd", "stream", "mlp_bwd", "finalize"), map(float, ms)))
 
     # -- data ----------------------------------------------------------------------------
-    def set_data(self, xM, xP, y_o=None, y_unc=None):
+    def set_data(self, xM, xP, y_o=None, y_unc=None, i_sites=None):
         """Register one batch (xM, xP, y_o, y_unc) -- a DataLoader element of the reference
         (src/AbstractHybridProblem.jl:179-184).  numpy arrays (host) or CUDA tensors (device),
         column = site."""
@@ -135,6 +135,10 @@ class NegElboPlan:
         self._check(self.lib.hvi_plan_set_data(self._h, n_site, *map(_ptr, args),
                                                A.HVI_MEM_DEVICE if dev else A.HVI_MEM_HOST))
         self.n_site = n_site
+        if i_sites is not None:
+            # the batch's site indices, 0-based (the `i_sites` of loss_elbo; used by MeanVarSep, src/elbo_sepvec.jl:23)
+            idx = np.ascontiguousarray(i_sites, dtype=np.int64)
+            self._check(self.lib.hvi_plan_set_sites(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
 
     # -- the hot path ----------------------------------------------------------------------
     def neg_elbo_withgradient(self, ϕ, zP=None, zMs=None, *, n_MC=None, seed=None, site_offset=0,

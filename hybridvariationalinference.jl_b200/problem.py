@@ -100,6 +100,7 @@ class HybridProblem:
     scale_kind: int = A.HVI_SCALE_NORMAL
     n_site: int = 800
     n_batch: int = 20
+    approx: str = "MeanHVIApproximationMat"   # or "MeanVarSepHVIApproximation" (src/HVIApproximation.jl:7-24)
 
     # ---- sizes and the ϕ layout (src/init_hybrid_params.jl:25-33,119-124; HybridProblem.jl:101-104)
     @property
@@ -114,12 +115,16 @@ class HybridProblem:
     def n_rhoM(self): return sum(get_cor_counts(self.cor_ends["M"]))
     @property
     def np_dtype(self): return np.float32 if self.dtype == "f32" else np.float64
+    @property
+    def is_sepvar(self): return self.approx == "MeanVarSepHVIApproximation"
 
     def positions(self) -> Dict[str, range]:
         """0-based ranges of the components of ϕ -- `get_positions` of the interpreters
         `int_ϕg_ϕq` / `int_ϕq` (src/ComponentArrayInterpreter.jl:281-288)."""
         out, p = {}, 0
-        for name, ln in (("ϕg", self.n_phig), ("logσ2_ζP", self.n_P), ("coef_logσ2_ζMs", 2 * self.n_M),
+        # MeanVarSep: logσ2_ζMs (n_θM × n_site) replaces the coefficients (src/init_hybrid_params.jl:147-152)
+        third = ("logσ2_ζMs", self.n_M * self.n_site) if self.is_sepvar else ("coef_logσ2_ζMs", 2 * self.n_M)
+        for name, ln in (("ϕg", self.n_phig), ("logσ2_ζP", self.n_P), third,
                          ("ρsP", self.n_rhoP), ("ρsM", self.n_rhoM), ("μP", self.n_P)):
             out[name] = range(p, p + ln)
             p += ln
@@ -183,6 +188,8 @@ class HybridProblem:
         for i, v in enumerate(idx):
             d.pbm_covar_idx[i] = v
         d.count_globals = int(count_globals)
+        d.approx = A.HVI_APPROX_MEANVAR_SEP if self.is_sepvar else A.HVI_APPROX_MEAN
+        d.n_site_total = self.n_site if self.is_sepvar else 0
         return d
 
     def as_plain_dict(self) -> dict:
@@ -194,15 +201,24 @@ class HybridProblem:
                     cor_ends_P=list(self.cor_ends["P"]), cor_ends_M=list(self.cor_ends["M"]),
                     slots=[(s, (i if s != A.HVI_SRC_FIX else f)) for s, i, f in self.slots()],
                     pbm_covar_idx=self.pbm_covar_indices(), omit_priors=self.is_omit_priors,
-                    scale_kind="range" if self.scale_kind == A.HVI_SCALE_RANGE else "normal")
+                    scale_kind="range" if self.scale_kind == A.HVI_SCALE_RANGE else "normal",
+                    approx="sepvar" if self.is_sepvar else "mean", n_site_total=self.n_site if self.is_sepvar else 0)
 
     # ---- initial parameters -------------------------------------------------------------
     def init_ϕq(self, ρ0: float = 0.0) -> np.ndarray:
         """init_hybrid_ϕunc + update_μP_by_θP (src/init_hybrid_params.jl:105-125,
         src/HybridProblem.jl:101-104): logσ2_ζP=-10, coef=[-10,0] per column, ρ=ρ0, μP=T⁻¹(θP)."""
         q = [-10.0] * self.n_P
-        for _ in range(self.n_M):
-            q += [-10.0, 0.0]
+        if self.is_sepvar:
+            # init_hybrid_ϕunc(::AbstractMeanVarSepHVIApproximation) (src/init_hybrid_params.jl:127-153):
+            # σ = relative error 0.01 of the template, per transform (compute_σ_unconstrained :155-168)
+            rel = 0.01
+            ls = [2 * math.log(math.sqrt(math.log(rel * rel + 1))) if t == A.HVI_TR_EXP else 2 * math.log(rel * v)
+                  for t, v in zip(self.transM, self.θM.values())]
+            q += ls * self.n_site
+        else:
+            for _ in range(self.n_M):
+                q += [-10.0, 0.0]
         q += [ρ0] * (self.n_rhoP + self.n_rhoM)
         q += [inverse_transform(t, v) for t, v in zip(self.transP, self.θP.values())]
         return np.asarray(q, dtype=self.np_dtype)
@@ -231,9 +247,13 @@ class HybridProblem:
             ϕ[pos["ρsP"]] = np.linspace(1.33, -0.4, len(pos["ρsP"])) if len(pos["ρsP"]) else 0
             cf = np.array([[math.log(0.1 ** 2), -0.3], [math.log(2.0 ** 2) - 8.0, 0.2],
                            [-6.0, 0.1], [-7.0, -0.15]])
-            for k in range(self.n_M):
-                ϕ[pos["coef_logσ2_ζMs"][2 * k]] = cf[k % 4, 0] - 2.0
-                ϕ[pos["coef_logσ2_ζMs"][2 * k + 1]] = cf[k % 4, 1]
+            if self.is_sepvar:
+                r = pos["logσ2_ζMs"]
+                ϕ[r] = -7.0 + np.random.Generator(np.random.PCG64(seed + 1)).standard_normal(len(r))
+            else:
+                for k in range(self.n_M):
+                    ϕ[pos["coef_logσ2_ζMs"][2 * k]] = cf[k % 4, 0] - 2.0
+                    ϕ[pos["coef_logσ2_ζMs"][2 * k + 1]] = cf[k % 4, 1]
             ϕ[pos["logσ2_ζP"]] = np.linspace(-6.0, -5.0, self.n_P) if self.n_P else 0
         return ϕ
 
@@ -295,7 +315,8 @@ def DoubleMMCase(scenario: Sequence[str] = (), dtype: str = "f32", hidden=None) 
         mu, sg = lo, [2 * Z95 * s for s in sg]
         scale_kind = A.HVI_SCALE_RANGE
     n_site = 100 if "few_sites" in scen else 20 if "sites20" in scen else 800        # :315-325
-    return HybridProblem(θP=θP, θM=θM, θFix=θFix, transP=transP, transM=transM, priors=priors,
+    approx = "MeanVarSepHVIApproximation" if "sepvar" in scen else "MeanHVIApproximationMat"   # :408
+    return HybridProblem(approx=approx, θP=θP, θM=θM, θFix=θFix, transP=transP, transM=transM, priors=priors,
                          cor_ends=cor_ends, layers=_three_layer(n_covar + len(pbm_covars), len(θM), hidden),
                          scale_mu=mu, scale_sigma=sg, pbm_covars=pbm_covars, n_obs=8, n_covar=n_covar,
                          dtype=dtype, scale_kind=scale_kind, n_site=n_site, n_batch=20)

@@ -49,6 +49,10 @@ enum { HVI_ACT_IDENTITY = 0, HVI_ACT_TANH = 1, HVI_ACT_LOGISTIC = 2 };
  * RangeScalingModelApplicator (:191-194) */
 enum { HVI_SCALE_NORMAL = 0, HVI_SCALE_RANGE = 1 };
 enum { HVI_FLAG_OMIT_PRIORS = 1 };  /* is_omit_priors = Val(true), src/elbo.jl:203-206 */
+/* posterior approximation (src/HVIApproximation.jl:7-24): MeanHVIApproximationMat (src/elbo.jl:633-678; the
+ * per-block MeanHVIApproximation of src/elbo2.jl is the same mathematics) or MeanVarSepHVIApproximation
+ * (src/elbo_sepvec.jl:3-48: one log-variance per site and parameter instead of intercept + slope) */
+enum { HVI_APPROX_MEAN = 0, HVI_APPROX_MEANVAR_SEP = 1 };
 
 typedef struct hvi_layer {
   int32_t n_in, n_out, act, has_bias; /* params per layer: vec(W[out x in]) col-major, then b */
@@ -91,6 +95,9 @@ typedef struct hvi_desc {
   /* site sharding: exactly one plan of a job adds the terms that exist once per
    * evaluation (prior and log-Jacobian of θP, entropy of the P block). */
   int32_t count_globals;
+  int32_t approx;        /* HVI_APPROX_* */
+  int64_t n_site_total;  /* MeanVarSep only: number of sites of the problem, ϕq holds logσ2_ζMs (n_M x n_site_total)
+                          * in place of coef_logσ2_ζMs (src/init_hybrid_params.jl:127-153) */
 } hvi_desc;
 
 typedef struct hvi_plan hvi_plan;
@@ -108,7 +115,7 @@ int hvi_plan_destroy(hvi_plan* plan);
 /* ---- integer index maps (bit-exact contract) ---------------------------------------- */
 /* length of ϕ = [ϕg ; ϕq] (src/init_hybrid_params.jl:25-33) */
 int64_t hvi_phi_len(const hvi_plan* plan);
-/* 0-based offsets/lengths of (ϕg, logσ2_ζP, coef_logσ2_ζMs, ρsP, ρsM, μP) inside ϕ --
+/* 0-based offsets/lengths of (ϕg, logσ2_ζP, coef_logσ2_ζMs | logσ2_ζMs, ρsP, ρsM, μP) inside ϕ --
  * what ComponentArrayInterpreter/get_positions yields
  * (src/ComponentArrayInterpreter.jl:281-288; layout src/init_hybrid_params.jl:119-124,
  * src/HybridProblem.jl:101-104) */
@@ -125,6 +132,11 @@ int64_t hvi_cor_count(const int32_t* cor_ends, int32_t n_cor_ends);
  * y_o and y_unc may both be NULL (no observations: prediction only). */
 int hvi_plan_set_data(hvi_plan* plan, int64_t n_site, const void* xM, const void* xP,
                       const void* y_o, const void* y_unc, int mem_kind);
+
+/* MeanVarSep only: the 0-based indices (into 0..n_site_total) of the registered batch's sites -- the
+ * `i_sites` argument of loss_elbo (src/HybridSolver.jl:312-322, src/elbo_sepvec.jl:23).  Host array of
+ * length n_site; default after set_data is 0..n_site-1. */
+int hvi_plan_set_sites(hvi_plan* plan, const int64_t* i_sites, int64_t n);
 
 /* ---- the hot path -------------------------------------------------------------------- */
 /* neg_elbo_gtf_components + gradient (src/elbo.jl:30-88 under Zygote, src/HybridSolver.jl:

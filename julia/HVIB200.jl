@@ -46,6 +46,8 @@ struct hvi_desc
     slot_src::NTuple{4,Int32}; slot_idx::NTuple{4,Int32}; slot_fix::NTuple{4,Float64}
     n_pbm_covar::Int32; pbm_covar_idx::NTuple{HVI_MAX_PAR,Int32}
     count_globals::Int32
+    approx::Int32
+    n_site_total::Int64
 end
 
 pad(v, n, z) = ntuple(i -> i <= length(v) ? v[i] : z, n)
@@ -102,7 +104,9 @@ function make_desc(prob::AbstractHybridProblem; scenario=Val(()), device=0, coun
         length(cor_ends.P), pad(Int32.(cor_ends.P), HVI_MAX_PAR, Int32(0)),
         length(cor_ends.M), pad(Int32.(cor_ends.M), HVI_MAX_PAR, Int32(0)),
         map(first, slots), map(s -> s[2], slots), map(last, slots),
-        length(idx), pad(idx, HVI_MAX_PAR, Int32(0)), count_globals ? 1 : 0)
+        length(idx), pad(idx, HVI_MAX_PAR, Int32(0)), count_globals ? 1 : 0,
+        prob.approx isa HVI.AbstractMeanVarSepHVIApproximation ? 1 : 0,
+        first(HVI.get_hybridproblem_n_site_and_batch(prob; scenario)))
 end
 
 mutable struct Plan

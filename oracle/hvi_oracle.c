@@ -83,6 +83,7 @@ typedef struct {
   int blk_start_M[HVI_MAX_PAR], rho_off_M[HVI_MAX_PAR];
   int slot_code[4];
   double clamp_lo, clamp_hi;
+  int sepvar;   /* MeanVarSepHVIApproximation: o_coef is the offset of logσ2_ζMs (nM x n_site_total) */
 } layout_t;
 
 static int cor_count_n(int n) { return (n - 1) * n / 2; }
@@ -119,7 +120,8 @@ static void make_layout(const hvi_desc* d, layout_t* L) {
   }
   L->nphig = p; L->n_in = d->layers[0].n_in;
   L->o_ls2P = p; p += L->nP;
-  L->o_coef = p; p += 2 * L->nM;
+  L->sepvar = d->approx == HVI_APPROX_MEANVAR_SEP;
+  L->o_coef = p; p += L->sepvar ? L->nM * (int)d->n_site_total : 2 * L->nM;
   L->o_rhoP = p; p += block_maps(d->cor_ends_P, d->n_cor_ends_P, L->nP, L->blk_start_P, L->rho_off_P);
   L->o_rhoM = p; p += block_maps(d->cor_ends_M, d->n_cor_ends_M, L->nM, L->blk_start_M, L->rho_off_M);
   L->o_muP = p; p += L->nP;
@@ -297,7 +299,7 @@ static void draw_eval(const hvi_desc* d, const layout_t* L, const real* thP, con
  * zP (M×nP), zMs (M×nM·nb), all column-major `real`.  grad may be NULL. */
 int FN(hvi_oracle_neg_elbo_grad)(const hvi_desc* d, int64_t nb, int M, const real* phi, const real* xM, const real* xP,
                                  const real* y_o, const real* y_unc, const real* zP, const real* zMs, double comps[6],
-                                 double* nL_out, real* grad, int nthreads) {
+                                 double* nL_out, real* grad, int nthreads, const int64_t* i_sites) {
   layout_t L;
   real UP[HVI_MAX_PAR][HVI_MAX_PAR], UM[HVI_MAX_PAR][HVI_MAX_PAR], nrmP[HVI_MAX_PAR], nrmM[HVI_MAX_PAR];
   real sigP[HVI_MAX_PAR];
@@ -359,8 +361,9 @@ int FN(hvi_oracle_neg_elbo_grad)(const hvi_desc* d, int64_t nb, int M, const rea
       for (c = 0; c < nC; c++) x[c] = xM[(int64_t)nC * i + c];
       for (c = 0; c < npc; c++) x[nC + c] = phi[L.o_muP + d->pbm_covar_idx[c]];
       g_forward(d, &L, phi, x, acts, mu, q);       /* pass 1: μ_ζMs0 (src/elbo.jl:491-492) */
+      const int64_t isite = i_sites ? i_sites[i] : i;   /* src/elbo_sepvec.jl:23 */
       for (k = 0; k < nM; k++) {
-        ls[k] = phi[L.o_coef + 2 * k] + phi[L.o_coef + 2 * k + 1] * mu[k];
+        ls[k] = L.sepvar ? phi[L.o_coef + isite * nM + k] : phi[L.o_coef + 2 * k] + phi[L.o_coef + 2 * k + 1] * mu[k];
         sig[k] = (real)exp((double)ls[k] / 2);
         t_ls += (double)ls[k] / 2;
         lsbar[k] = 0; mubar_sum[k] = 0;
@@ -399,9 +402,14 @@ int FN(hvi_oracle_neg_elbo_grad)(const hvi_desc* d, int64_t nb, int M, const rea
       }
       for (k = 0; k < nM; k++) {
         lsbar[k] -= 0.5; /* entropy: −Σ log σ = −Σ ls/2 */
-        Gt[L.o_coef + 2 * k] += lsbar[k];
-        Gt[L.o_coef + 2 * k + 1] += lsbar[k] * (double)mu[k];
-        mu_bar0[k] = (real)(lsbar[k] * (double)phi[L.o_coef + 2 * k + 1] + (npc > 0 ? 0.0 : mubar_sum[k]));
+        if (L.sepvar) {
+          Gt[L.o_coef + isite * nM + k] += lsbar[k];
+          mu_bar0[k] = (real)(npc > 0 ? 0.0 : mubar_sum[k]);
+        } else {
+          Gt[L.o_coef + 2 * k] += lsbar[k];
+          Gt[L.o_coef + 2 * k + 1] += lsbar[k] * (double)mu[k];
+          mu_bar0[k] = (real)(lsbar[k] * (double)phi[L.o_coef + 2 * k + 1] + (npc > 0 ? 0.0 : mubar_sum[k]));
+        }
       }
       if (npc > 0) { /* redo pass 1 to have its activations for the backward */
         for (c = 0; c < npc; c++) x[nC + c] = phi[L.o_muP + d->pbm_covar_idx[c]];

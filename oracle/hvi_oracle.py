@@ -184,6 +184,10 @@ class Spec:
     pbm_covar_idx: Sequence[int] = field(default_factory=list)  # 0-based positions in θP
     omit_priors: bool = False
     scale_kind: str = "normal"  # or "range" (offset=scale_mu, width=scale_sigma)
+    # "mean": MeanHVIApproximationMat (src/elbo.jl:633-678); "sepvar": MeanVarSepHVIApproximation
+    # (src/elbo_sepvec.jl:3-48), ϕq then holds logσ2_ζMs (nM × n_site_total) instead of the coefficients
+    approx: str = "mean"
+    n_site_total: int = 0
 
     @property
     def n_phig(self):
@@ -202,7 +206,8 @@ class Spec:
         (src/init_hybrid_params.jl:26,119-124; src/HybridProblem.jl:101-104)."""
         o = {}
         p = 0
-        for name, ln in (("phig", self.n_phig), ("logsigma2_P", self.nP), ("coef", 2 * self.nM),
+        n_coef = self.nM * self.n_site_total if self.approx == "sepvar" else 2 * self.nM
+        for name, ln in (("phig", self.n_phig), ("logsigma2_P", self.nP), ("coef", n_coef),
                          ("rhoP", self.n_rhoP), ("rhoM", self.n_rhoM), ("muP", self.nP)):
             o[name] = (p, ln)
             p += ln
@@ -258,7 +263,7 @@ def _append_each_covars(xM, zP_covar):
     return torch.cat([xM, rep], dim=0)
 
 
-def sample_zeta_resid_norm(spec: Spec, zP, zMs, mu_zMs, phiq):
+def sample_zeta_resid_norm(spec: Spec, zP, zMs, mu_zMs, phiq, i_sites=None):
     """MeanHVIApproximationMat method, src/elbo.jl:633-678 with _compute_choleskyfactor
     :721-743.  zP (n_MC×nP), zMs (n_MC × nM·nb) column index (i·nM + k);
     mu_zMs (nM × nb).  Returns ζP_resids (nP×M), ζMs_parfirst_resids (nM×nb×M), σ."""
@@ -269,8 +274,13 @@ def sample_zeta_resid_norm(spec: Spec, zP, zMs, mu_zMs, phiq):
     rhoM = phiq[o["rhoM"][0]:o["rhoM"][0] + o["rhoM"][1]]
     UP = transformU_block_cholesky1(rhoP, spec.cor_ends_P) if spec.nP > 0 else torch.zeros((0, 0), dtype=F64)
     UM = transformU_block_cholesky1(rhoM, spec.cor_ends_M)
-    cf = phiq[o["coef"][0]:o["coef"][0] + 2 * nM].reshape(nM, 2).T  # (2 × nM) col-major
-    logs2M = cf[0, :].reshape(-1, 1) + cf[1, :].reshape(-1, 1) * mu_zMs
+    if spec.approx == "sepvar":   # src/elbo_sepvec.jl:23: logσ2_ζMs[:, i_sites]
+        blk = phiq[o["coef"][0]:o["coef"][0] + o["coef"][1]].reshape(spec.n_site_total, nM).T
+        idx = torch.arange(nb) if i_sites is None else torch.as_tensor(np.asarray(i_sites), dtype=torch.long)
+        logs2M = blk[:, idx]
+    else:
+        cf = phiq[o["coef"][0]:o["coef"][0] + 2 * nM].reshape(nM, 2).T  # (2 × nM) col-major
+        logs2M = cf[0, :].reshape(-1, 1) + cf[1, :].reshape(-1, 1) * mu_zMs
     logs2P = phiq[o["logsigma2_P"][0]:o["logsigma2_P"][0] + spec.nP]
     sigM = torch.exp(logs2M / 2)
     sigP = torch.exp(logs2P / 2)
@@ -289,7 +299,7 @@ def _phiq_offsets(spec: Spec):
     return {k: (v[0] - base, v[1]) for k, v in o.items() if k not in ("phig", "_len")}
 
 
-def generate_zeta(spec: Spec, phi, xM, zP, zMs):
+def generate_zeta(spec: Spec, phi, xM, zP, zMs, i_sites=None):
     """src/elbo.jl:472-521.  Returns ζsP (nP×M), ζsMs_tr (nb×nM×M), σ."""
     o = spec.offsets()
     phig = phi[o["phig"][0]:o["phig"][0] + o["phig"][1]]
@@ -298,7 +308,7 @@ def generate_zeta(spec: Spec, phi, xM, zP, zMs):
     idx = list(spec.pbm_covar_idx)
     xMP0 = _append_each_covars(xM, mu_zP[idx] if idx else mu_zP[:0])
     mu_zMs0 = apply_g(spec, xMP0, phig)
-    rP, rM, sigma = sample_zeta_resid_norm(spec, zP, zMs, mu_zMs0, phiq)
+    rP, rM, sigma = sample_zeta_resid_norm(spec, zP, zMs, mu_zMs0, phiq, i_sites)
     zsP = mu_zP.reshape(-1, 1) + rP if spec.nP > 0 else rP
     M = zP.shape[0]
     if not idx:
@@ -416,9 +426,9 @@ def neg_elbo_zeta_tf(spec: Spec, zsP, zsMs_tr, sigma, xP, y_ob, y_unc, dtype_nam
 COMPONENTS = ("nLjoint", "entropy_zeta", "loss_penalty", "nLy", "neg_log_prior", "neg_log_jac")
 
 
-def neg_elbo_gtf_components(spec: Spec, phi, xM, xP, y_ob, y_unc, zP, zMs, dtype_name="f64"):
+def neg_elbo_gtf_components(spec: Spec, phi, xM, xP, y_ob, y_unc, zP, zMs, dtype_name="f64", i_sites=None):
     """src/elbo.jl:46-88 (n_MC_cap == n_MC; priors_θ_mean empty)."""
-    zsP, zsMs_tr, sigma = generate_zeta(spec, phi, xM, zP, zMs)
+    zsP, zsMs_tr, sigma = generate_zeta(spec, phi, xM, zP, zMs, i_sites)
     return neg_elbo_zeta_tf(spec, zsP, zsMs_tr, sigma, xP, y_ob, y_unc, dtype_name)
 
 
@@ -428,13 +438,13 @@ def neg_elbo_gtf(spec: Spec, phi, xM, xP, y_ob, y_unc, zP, zMs, dtype_name="f64"
     return c["nLjoint"] - c["entropy_zeta"] + c["loss_penalty"]
 
 
-def value_and_grad(spec: Spec, phi, xM, xP, y_ob, y_unc, zP, zMs, dtype_name="f64"):
+def value_and_grad(spec: Spec, phi, xM, xP, y_ob, y_unc, zP, zMs, dtype_name="f64", i_sites=None):
     """Scalar, six components and ∇ϕ by torch reverse-mode autograd in float64 (stands in
     for Zygote.withgradient, src/HybridSolver.jl:256-258).  Inputs: numpy arrays in the
     reference's shapes; they are converted (exactly) to float64."""
     t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
     ph = t(phi).clone().requires_grad_(True)
-    comps = neg_elbo_gtf_components(spec, ph, t(xM), t(xP), t(y_ob), t(y_unc), t(zP), t(zMs), dtype_name)
+    comps = neg_elbo_gtf_components(spec, ph, t(xM), t(xP), t(y_ob), t(y_unc), t(zP), t(zMs), dtype_name, i_sites)
     nL = comps["nLjoint"] - comps["entropy_zeta"] + comps["loss_penalty"]
     (g,) = torch.autograd.grad(nL, ph)
     cv = np.array([float(comps[k].detach()) for k in COMPONENTS])
@@ -500,11 +510,11 @@ def transform_zetas(spec: Spec, zsP, zsMs_tr):
     return thP, thMs
 
 
-def predict_hvi(spec: Spec, phi, xM, xP, zP, zMs):
+def predict_hvi(spec: Spec, phi, xM, xP, zP, zMs, i_sites=None):
     """predict_hvi (src/elbo.jl:320-352) with the draws passed in: y (nO × nb × n_sample),
     θsP (nP × n_sample), θsMs_tr (nb × nM × n_sample), entropy_ζ."""
     t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
-    zsP, zsMs_tr, sigma = generate_zeta(spec, t(phi), t(xM), t(zP), t(zMs))
+    zsP, zsMs_tr, sigma = generate_zeta(spec, t(phi), t(xM), t(zP), t(zMs), i_sites)
     ent = entropy_MvNormal(sigma.numel(), 2 * torch.log(sigma).sum())
     thP, thMs = transform_zetas(spec, zsP, zsMs_tr)
     ys = [f_doubleMM_sites(spec, thP[:, m] if spec.nP > 0 else thP[:0, 0], thMs[:, :, m], t(xP)) for m in range(thMs.shape[2])]

@@ -33,7 +33,7 @@ def c_oracle_lib():
     return _clib
 
 
-def c_oracle_value_and_grad(prob, phi, data, zP, zMs, nthreads=1, count_globals=True, want_grad=True):
+def c_oracle_value_and_grad(prob, phi, data, zP, zMs, nthreads=1, count_globals=True, want_grad=True, i_sites=None):
     lib = c_oracle_lib()
     ft = prob.np_dtype
     fn = getattr(lib, "hvi_oracle_neg_elbo_grad_" + prob.dtype)
@@ -47,8 +47,10 @@ def c_oracle_value_and_grad(prob, phi, data, zP, zMs, nthreads=1, count_globals=
     grad = np.zeros(phi_.shape, dtype=ft)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     fn.restype = C.c_int
-    fn.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    isp = None if i_sites is None else np.ascontiguousarray(i_sites, dtype=np.int64)
     rc = fn(C.byref(desc), nb, M, p(phi_), p(xM), p(xP), p(yo), p(yu), p(zP_), p(zMs_),
-            C.cast(comps, C.c_void_p), C.cast(C.byref(nL), C.c_void_p), p(grad) if want_grad else None, nthreads)
+            C.cast(comps, C.c_void_p), C.cast(C.byref(nL), C.c_void_p), p(grad) if want_grad else None, nthreads,
+            None if isp is None else p(isp))
     assert rc == 0, rc
     return nL.value, np.array(list(comps)), grad

@@ -35,13 +35,14 @@ def test_desc_layout_matches_c():
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "s.c")
         open(src, "w").write('#include <stdio.h>\n#include <stddef.h>\n#include "hvi_b200.h"\n'
-                             'int main(){printf("%zu %zu %zu %zu %zu", sizeof(hvi_desc), offsetof(hvi_desc, scale_a),'
-                             'offsetof(hvi_desc, prior_M), offsetof(hvi_desc, slot_fix), offsetof(hvi_desc, count_globals));return 0;}')
+                             'int main(){printf("%zu %zu %zu %zu %zu %zu", sizeof(hvi_desc), offsetof(hvi_desc, scale_a),'
+                             'offsetof(hvi_desc, prior_M), offsetof(hvi_desc, slot_fix), offsetof(hvi_desc, count_globals), offsetof(hvi_desc, n_site_total));return 0;}')
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         out = list(map(int, subprocess.check_output([exe]).split()))
     D = A.hvi_desc
-    assert out == [C.sizeof(D), D.scale_a.offset, D.prior_M.offset, D.slot_fix.offset, D.count_globals.offset]
+    assert out == [C.sizeof(D), D.scale_a.offset, D.prior_M.offset, D.slot_fix.offset, D.count_globals.offset,
+                   D.n_site_total.offset]
 
 
 def test_index_maps_known_answers():

@@ -256,3 +256,37 @@ def test_predict_hvi_matches_oracle(case, dtype):
     # without observations the ELBO of the batch has no likelihood term but still evaluates
     nL, comps, g = plan.neg_elbo_withgradient(ϕ, zP, zMs)
     assert comps.nLy == 0.0 and np.isfinite(nL)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("scen", [("sepvar", "few_sites"), ("sepvar", "few_sites", "covarK2")])
+def test_meanvarsep_approximation(scen, dtype):
+    """MeanVarSepHVIApproximation (src/elbo_sepvec.jl:3-48): per-site log-variances read at the
+    batch's i_sites; their gradient is owner-local, zero for sites outside the batch."""
+    prob = hvi_b200.DoubleMMCase(scen, dtype=dtype)
+    nb, M = 20, 4
+    i_sites = np.arange(60, 80)[::-1].copy()       # any order
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb)
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
+    ϕ = prob.init_ϕ(perturbed=True)
+    plan = hvi_b200.NegElboPlan(prob)
+    assert {k: (r.start, r.stop) for k, r in plan.positions().items()} == \
+           {k: (r.start, r.stop) for k, r in prob.positions().items()}
+    plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"], i_sites=i_sites)
+    nL, comps, g = plan.neg_elbo_withgradient(ϕ, zP, zMs)
+    nL_o, comps_o, g_o = O.value_and_grad(oracle_spec(prob), ϕ, data["xM"], data["xP"], data["y_o"], data["y_unc"],
+                                          zP, zMs, dtype, i_sites=i_sites)
+    tol = TOL[dtype]
+    assert abs(nL - nL_o) <= tol * abs(nL_o)
+    assert np.max(np.abs(np.array(comps) - comps_o)) <= tol * np.max(np.abs(comps_o))
+    for name, r in prob.positions().items():
+        if len(r):
+            assert np.max(np.abs(g[r] - g_o[r])) <= tol * np.max(np.abs(g_o[r])), name
+    r = prob.positions()["logσ2_ζMs"]
+    outside = np.ones(len(r), bool)
+    outside[(i_sites[:, None] * 2 + np.arange(2)).ravel()] = False
+    assert np.all(g[r][outside] == 0)
+    y, θP, θMs, ent = plan.predict_hvi(ϕ, zP, zMs)
+    y_o, θP_o, θMs_o, ent_o = O.predict_hvi(oracle_spec(prob), ϕ, data["xM"], data["xP"], zP, zMs, i_sites=i_sites)
+    np.testing.assert_allclose(θMs, θMs_o, rtol=max(tol, 2e-5), atol=tol)
+    assert abs(ent - ent_o) <= 1e-6 * abs(ent_o)

@@ -71,3 +71,23 @@ def test_site_shards_sum_to_the_whole():
         tot_c += c
     assert np.allclose(tot_c, full[1], rtol=1e-12)
     assert np.allclose(tot_g, full[2], rtol=1e-10, atol=1e-10 * np.abs(full[2]).max())
+
+
+def test_meanvarsep_c_restatement_matches_autograd():
+    """MeanVarSepHVIApproximation (src/elbo_sepvec.jl:3-48): per-site log-variances gathered by i_sites."""
+    prob = hvi_b200.DoubleMMCase(("sepvar", "few_sites"), dtype="f64")
+    assert prob.n_phi == prob.n_phig + 2 + 2 * 100 + 1 + 1 + 2     # init_hybrid_params.jl:147-152
+    nb, M = 20, 3
+    i_sites = np.arange(40, 60)          # the third minibatch of a DataLoader with batchsize 20
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb)
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
+    ϕ = prob.init_ϕ(perturbed=True)
+    nL, comps, g = O.value_and_grad(oracle_spec(prob), ϕ, data["xM"], data["xP"], data["y_o"], data["y_unc"], zP, zMs,
+                                    i_sites=i_sites)
+    nLc, compsc, gc = c_oracle_value_and_grad(prob, ϕ, data, zP, zMs, i_sites=i_sites)
+    assert nLc == pytest.approx(nL, rel=1e-12)
+    np.testing.assert_allclose(gc, g, rtol=1e-10, atol=1e-11 * np.abs(g).max())
+    r = prob.positions()["logσ2_ζMs"]
+    touched = np.zeros(len(r), bool)
+    touched[(i_sites[:, None] * 2 + np.arange(2)).ravel()] = True
+    assert np.all(g[r][~touched] == 0) and np.all(g[r][touched] != 0)
