@@ -608,15 +608,15 @@ __global__ void __launch_bounds__(MLP3_BS, 3) k_mlp3_bwd(const __grid_constant__
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sW = reinterpret_cast<T*>(smem_raw);
   T* rows = sW + pad4(N::nW);                       // [MLP3_BS][ROW]
-  T* sacc = rows + (size_t)MLP3_BS * N::ROW;        // [4 warps][TPL*32 tiles][16]: gradient tiles between site tiles
+  T* sacc = rows + (size_t)MLP3_BS * N::ROW;        // [4 warps][NT tiles][16]: gradient tiles between site tiles
   // cotangent of the pbm covariate inputs, summed over the sites: [max(M_units,1)][npc] doubles
-  double* xacc = reinterpret_cast<double*>(sacc + (size_t)4 * N::TPL * 32 * 16);
+  double* xacc = reinterpret_cast<double*>(sacc + (size_t)4 * N::NT * 16);
   T* xred = reinterpret_cast<T*>(xacc + (size_t)(cols.M_units > 0 ? cols.M_units : 1) * cfg.npc);  // [4 warps][npc]
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int64_t nb = cols.nb;
   const int nxa = (cols.M_units > 0 ? cols.M_units : 1) * cfg.npc;
   N::load_weights(cfg, phi, sW, t, MLP3_BS);
-  for (int e = t; e < 4 * N::TPL * 32 * 16; e += MLP3_BS) sacc[e] = T(0);
+  for (int e = t; e < 4 * N::NT * 16; e += MLP3_BS) sacc[e] = T(0);
   for (int e = t; e < nxa; e += MLP3_BS) xacc[e] = 0.0;
   // this lane's gradient tiles: offsets of the δ quad and of the activation quad inside a site row
   int doff[N::TPL], aoff[N::TPL];
@@ -731,7 +731,8 @@ __global__ void __launch_bounds__(MLP3_BS, 3) k_mlp3_bwd(const __grid_constant__
       T acc[N::TPL][16];
 #pragma unroll
       for (int q = 0; q < N::TPL; q++) {
-        const T* sa = sacc + ((size_t)(warp * N::TPL + q) * 32 + lane) * 16;
+        const int tl = lane + 32 * q;
+        const T* sa = sacc + ((size_t)warp * N::NT + (tl < N::NT ? tl : 0)) * 16;
 #pragma unroll
         for (int e4 = 0; e4 < 4; e4++) {
           const V4<T> v = ld4(sa + 4 * e4);
@@ -751,11 +752,15 @@ __global__ void __launch_bounds__(MLP3_BS, 3) k_mlp3_bwd(const __grid_constant__
             for (int ii = 0; ii < 4; ii++) acc[q][4 * jj + ii] = fma(d.v[jj], a.v[ii], acc[q][4 * jj + ii]);
         }
       }
+      __syncwarp();   // idle slots read tile 0 above: all reads before any write
 #pragma unroll
       for (int q = 0; q < N::TPL; q++) {
-        T* sa = sacc + ((size_t)(warp * N::TPL + q) * 32 + lane) * 16;
+        const int tl = lane + 32 * q;
+        if (tl < N::NT) {
+          T* sa = sacc + ((size_t)warp * N::NT + tl) * 16;
 #pragma unroll
-        for (int e4 = 0; e4 < 4; e4++) st4(sa + 4 * e4, acc[q][4 * e4], acc[q][4 * e4 + 1], acc[q][4 * e4 + 2], acc[q][4 * e4 + 3]);
+          for (int e4 = 0; e4 < 4; e4++) st4(sa + 4 * e4, acc[q][4 * e4], acc[q][4 * e4 + 1], acc[q][4 * e4 + 2], acc[q][4 * e4 + 3]);
+        }
       }
     }
     __syncthreads();
@@ -766,7 +771,7 @@ __global__ void __launch_bounds__(MLP3_BS, 3) k_mlp3_bwd(const __grid_constant__
     const int tl = e / 16, jj = (e % 16) / 4, ii = e % 4;
     double s = 0;
     for (int w = 0; w < MLP3_BS / 32; w++)
-      s += (double)sacc[((size_t)(w * N::TPL + tl / 32) * 32 + (tl % 32)) * 16 + (e % 16)];
+      s += (double)sacc[((size_t)w * N::NT + tl) * 16 + (e % 16)];
     int l, j, i, nin, nout;
     if (tl < N::NT1) { l = 0; j = 4 * (tl % N::T1j) + jj; i = 4 * (tl / N::T1j) + ii; nin = NI; nout = H1; }
     else if (tl < N::NT1 + N::NT2) { const int u = tl - N::NT1; l = 1; j = 4 * (u % N::T2j) + jj; i = 4 * (u / N::T2j) + ii; nin = H1; nout = H2; }
@@ -1636,7 +1641,7 @@ template cudaError_t launch_predict<double>(const Launch&, const Cfg<double>&, c
   } while (0)
 
 int stream_max_rows(int sm_count) { return sm_count * 8 * (STREAM_THREADS_MAX / 32); }
-int mlp_bwd_max_blocks(int sm_count) { return sm_count * 2; }
+int mlp_bwd_max_blocks(int sm_count) { return sm_count * 3; }
 
 template <typename T>
 cudaError_t launch_preprocess(const Launch& L, int nO, int64_t nb, const T* xP, const T* y_o, const T* y_unc, T* rec,
@@ -1713,7 +1718,7 @@ cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, con
 #define X(NI, H1, H2, NO_)                                                                                   \
   if (mlp3_match(cfg, NI, H1, H2, NO_)) {                                                                    \
     using N = Mlp3<T, NI, H1, H2, NO_>;                                                                      \
-    const size_t smem3 = sizeof(T) * (pad4(N::nW) + (size_t)MLP3_BS * N::ROW + (size_t)4 * N::TPL * 32 * 16) + \
+    const size_t smem3 = sizeof(T) * (pad4(N::nW) + (size_t)MLP3_BS * N::ROW + (size_t)4 * N::NT * 16) + \
                          sizeof(double) * (size_t)(M_units > 0 ? M_units : 1) * cfg.npc + sizeof(T) * 4 * cfg.npc + 16; \
     if (smem3 > 220 * 1024) return cudaErrorInvalidConfiguration;                                            \
     auto kern = k_mlp3_bwd<T, NI, H1, H2, NO_>;                                                              \

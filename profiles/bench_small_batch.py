@@ -1,0 +1,26 @@
+"""Latency of one neg-ELBO + gradient evaluation at the batch sizes the reference itself runs
+(n_batch = 20 of 800 sites, n_MC = 3 … 12; test/test_HybridProblem.jl:252, src/HybridSolver.jl:147):
+host ϕ in, (nL, ∇ϕ) out, draws on the device.  Usage: python profiles/bench_small_batch.py"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import hvi_b200
+
+for dtype in ("f32", "f64"):
+    for nb, M in ((20, 3), (20, 12), (800, 12), (10_000, 32), (100_000, 32)):
+        prob = hvi_b200.DoubleMMCase(dtype=dtype)
+        data = hvi_b200.gen_hybridproblem_synthetic(prob, nb)
+        ϕ = prob.init_ϕ(perturbed=True)
+        plan = hvi_b200.NegElboPlan(prob)
+        plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+        for _ in range(20):
+            plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=1)
+        n = 200
+        t0 = time.perf_counter()
+        for i in range(n):
+            plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=i)
+        dt = (time.perf_counter() - t0) / n
+        print(f"{dtype} n_batch={nb:6d} n_MC={M:3d}: {dt * 1e6:8.1f} us per evaluation  ({nb * M / dt:.3e} units/s)", flush=True)
