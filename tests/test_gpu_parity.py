@@ -290,3 +290,29 @@ def test_meanvarsep_approximation(scen, dtype):
     y_o, θP_o, θMs_o, ent_o = O.predict_hvi(oracle_spec(prob), ϕ, data["xM"], data["xP"], zP, zMs, i_sites=i_sites)
     np.testing.assert_allclose(θMs, θMs_o, rtol=max(tol, 2e-5), atol=tol)
     assert abs(ent - ent_o) <= 1e-6 * abs(ent_o)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_many_draws_global_pd_path(dtype):
+    """n_MC = 700: the per-draw records of the global block no longer fit the 16 KB shared-memory
+    budget and are read from global memory (n_sample_pred-sized evaluations)."""
+    check(hvi_b200.DoubleMMCase(dtype=dtype), nb=40, M=700)
+
+
+@pytest.mark.parametrize("M", [5, 6, 64])
+def test_device_rng_equals_explicit_draws_any_n_mc(M):
+    """in-kernel draws, including n_MC not a multiple of 4 (tail draws) and Float64 (chunks of 2)."""
+    for dtype in ("f32", "f64"):
+        prob = hvi_b200.DoubleMMCase(dtype=dtype)
+        nb = 70
+        data = hvi_b200.gen_hybridproblem_synthetic(prob, nb)
+        ϕ = prob.init_ϕ(perturbed=True)
+        plan = hvi_b200.NegElboPlan(prob)
+        plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+        a = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=11)
+        z = plan.randn(M, prob.n_M * nb, seed=11)
+        zP = plan.randn(M, prob.n_P, seed=11, col_offset=1 << 62)
+        d = plan.neg_elbo_withgradient(ϕ, zP, z)
+        tol = 1e-5 if dtype == "f32" else 1e-12
+        assert abs(a[0] - d[0]) <= tol * abs(d[0]), (dtype, M)
+        np.testing.assert_allclose(a[2], d[2], rtol=100 * tol, atol=10 * tol * np.abs(d[2]).max())
