@@ -985,7 +985,7 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, 
   }
 }
 
-constexpr int STREAM_THREADS_MAX = 256;
+constexpr int STREAM_THREADS_MAX = 384;
 
 template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool RNG>
 __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_constant__ Cfg<T> cfg,
@@ -1780,9 +1780,12 @@ static cudaError_t launch_stream_cfg(const Launch& L, const Cfg<T>& cfg, StreamA
   return launch_stream_cfg2<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, false>(L, cfg, a, nrows_out, nrows_max);
 }
 
-// launch shape: Float32 runs 2 blocks of 256 threads per SM (128 registers), Float64 one block of
-// 256.  HVI_STREAM_VARIANT=1 selects 5 blocks of 128 threads (96 registers, spills; measured
-// 1.15 ms vs 0.88 ms at 2e6 sites x 64 draws) for experiments.
+// launch shape (measured at 2e6 sites x 64 draws, Float32, compile-time traits): one block of 256
+// threads per SM with up to 255 registers 0.84 ms; two blocks of 256 (128 registers) 0.90 ms; one block
+// of 384 (168 registers) 0.90 ms; five blocks of 128 (96 registers, spills) 1.15 ms.  The kernel is bound
+// by the FP32 pipe and by instruction latency, and registers buy the compiler room to interleave the
+// four unrolled draws -- that is worth more than resident warps.  HVI_STREAM_VARIANT = 1, 2, 3 selects
+// the other shapes for experiments.
 static int stream_variant() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("HVI_STREAM_VARIANT"); v = e ? atoi(e) : 0; }
@@ -1797,10 +1800,12 @@ static cudaError_t launch_stream_inst(const Launch& L, const Cfg<T>& cfg, const 
     if constexpr (TR::STATIC) {
       if (pbm) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, true>(L, cfg, a, nrows_out, nrows_max);
       if (stream_variant() == 1) return launch_stream_cfg<TR, T, NP, NM, NO, 128, 5, false>(L, cfg, a, nrows_out, nrows_max);
-      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, false>(L, cfg, a, nrows_out, nrows_max);
+      if (stream_variant() == 2) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, false>(L, cfg, a, nrows_out, nrows_max);
+      if (stream_variant() == 3) return launch_stream_cfg<TR, T, NP, NM, NO, 384, 1, false>(L, cfg, a, nrows_out, nrows_max);
+      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1, false>(L, cfg, a, nrows_out, nrows_max);
     } else {
       if (pbm) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, true>(L, cfg, a, nrows_out, nrows_max);
-      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, false>(L, cfg, a, nrows_out, nrows_max);
+      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, false>(L, cfg, a, nrows_out, nrows_max);   // run-time traits: 1.41 ms vs 1.55 ms with 256 x 1
     }
   } else {
     if (pbm) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1, true>(L, cfg, a, nrows_out, nrows_max);
