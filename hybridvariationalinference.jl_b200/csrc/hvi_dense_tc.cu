@@ -10,8 +10,10 @@
 //
 // Reference: the dense layers of g (ext/HybridVariationalInferenceSimpleChainsExt.jl:43-52,
 // ext/HybridVariationalInferenceFluxExt.jl:26-31) -- cuBLAS/SimpleChains GEMMs there.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "hvi_internal.cuh"
 
@@ -23,6 +25,7 @@ constexpr int TC_BK = 32;       // K per stage: 32 tf32 = one 128-byte swizzle r
 constexpr int TC_STAGES = 3;
 constexpr int TC_THREADS = 256;     // 8 warps: two per scheduler for the split/store phase; warps 0-3 and 4-7 share the epilogue
 constexpr int TC_LD = 1024 / TC_THREADS;   // float4 per thread, operand and stage (= 4)
+constexpr int TC_BLOCK = TC_THREADS + 32;   // 8 producer/epilogue warps + 1 warp whose lane 0 issues the MMAs
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;              // 16 KB per operand half
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;             // A hi, A lo, B hi, B lo
 
@@ -30,6 +33,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -53,6 +59,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // instruction descriptor (InstrDescriptor): D = F32 [4,6)=1, A = TF32 [7,10)=2, B = TF32 [10,13)=2,
 // both K-major, N >> 3 [17,23), M >> 4 [24,29)
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+// the same with A = B = BF16 (format 1) for kind::f16
+constexpr uint32_t TC_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(TC_IDESC_BF16), "r"(accumulate)
+      : "memory");
+}
 
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
   asm volatile(
@@ -91,6 +109,34 @@ __device__ __forceinline__ void split_store1(unsigned char* tile_hi, unsigned ch
   *reinterpret_cast<float*>(tile_lo + off) = x - hi;
 }
 
+// bf16 variant of the split: x ≈ hi + lo with hi = bf16(x), lo = bf16(x − hi) (16 mantissa bits together);
+// three products hi·hi + hi·lo + lo·hi at twice the tf32 rate and half the shared-memory bytes
+__device__ __forceinline__ void bf16_split(float x, unsigned short& hi, unsigned short& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(l);
+}
+// eight consecutive K values (two float4) → one 16-byte chunk of bf16 hi and one of lo at (row, chunk)
+__device__ __forceinline__ void split_store_bf16(unsigned char* tile_hi, unsigned char* tile_lo, int row, int chunk, float4 v0, float4 v1) {
+  unsigned short h[8], l[8];
+  bf16_split(v0.x, h[0], l[0]); bf16_split(v0.y, h[1], l[1]); bf16_split(v0.z, h[2], l[2]); bf16_split(v0.w, h[3], l[3]);
+  bf16_split(v1.x, h[4], l[4]); bf16_split(v1.y, h[5], l[5]); bf16_split(v1.z, h[6], l[6]); bf16_split(v1.w, h[7], l[7]);
+  const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
+  *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16),
+                                                        h[4] | ((uint32_t)h[5] << 16), h[6] | ((uint32_t)h[7] << 16));
+  *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16),
+                                                        l[4] | ((uint32_t)l[5] << 16), l[6] | ((uint32_t)l[7] << 16));
+}
+// element (row, col) of a [rows][64 bf16] K-major tile
+__device__ __forceinline__ void split_store1_bf16(unsigned char* tile_hi, unsigned char* tile_lo, int row, int col, float x) {
+  unsigned short h, l;
+  bf16_split(x, h, l);
+  const int off = row * 128 + ((((col >> 3) ^ (row & 7))) << 4) + ((col & 7) << 1);
+  *reinterpret_cast<unsigned short*>(tile_hi + off) = h;
+  *reinterpret_cast<unsigned short*>(tile_lo + off) = l;
+}
+
 __device__ __forceinline__ float act_deriv_f(int act, float h) {
   if (act == HVI_ACT_TANH) return 1.f - h * h;
   if (act == HVI_ACT_LOGISTIC) return h * (1.f - h);
@@ -103,12 +149,14 @@ __device__ __forceinline__ float act_deriv_f(int act, float h) {
 // MODE 1 (weight gradient, split over the rows): P[split][Md x Nd] = Σ_{r in split} X[r][m]·Y[r][n]
 //     with A ≙ X (Mc x Md), W ≙ Y (Mc x Nd), N ≙ Nd, K ≙ Md; operands are transposed on the way into
 //     shared memory (lane ↔ row r, so the scalar stores of a warp hit 32 different banks)
-template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// PREC 0: 3xTF32 (K = 32 per stage);  PREC 1: 3xBF16 (K = 64 per stage)
+template <int MODE, int PREC>
+__global__ void __launch_bounds__(TC_BLOCK, 1)
 k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ C,
            int64_t Mc, int N, int K, int act, const float* __restrict__ Hd, int64_t rows_per_split) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t bar_mma[TC_STAGES];   // "the MMAs that read stage s have completed"
+  __shared__ uint64_t bar_full[TC_STAGES];  // "all 8 producer warps have stored stage s" (count 8)
+  __shared__ uint64_t bar_mma[TC_STAGES];   // "the MMAs that read stage s have completed" (tcgen05.commit)
   __shared__ uint64_t bar_done;
   __shared__ uint32_t tmem_base_s;
   unsigned char* tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
@@ -118,7 +166,7 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
   const int64_t row0 = (int64_t)(MODE == 0 ? blockIdx.y : blockIdx.x) * TC_BM;
   const int col0 = (MODE == 0 ? blockIdx.x : blockIdx.y) * TC_BN;
   if (t == 0) {
-    for (int s = 0; s < TC_STAGES; s++) mbar_init(&bar_mma[s], 1);
+    for (int s = 0; s < TC_STAGES; s++) { mbar_init(&bar_mma[s], 1); mbar_init(&bar_full[s], TC_THREADS / 32); }
     mbar_init(&bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -138,77 +186,120 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
     r_end = r_begin + rows_per_split < Mc ? r_begin + rows_per_split : Mc;
     if (r_end < r_begin) r_end = r_begin;
   }
-  const int KT = MODE == 0 ? K / TC_BK : (int)((r_end - r_begin + TC_BK - 1) / TC_BK);
-  // 8 + 8 float4 per thread and stage.  The global loads of tile kt+1 are issued right after tile
-  // kt has been handed to the tensor core, so their latency overlaps the MMAs.
+  constexpr int BKV = PREC == 0 ? TC_BK : 2 * TC_BK;       // K values per stage
+  constexpr int NV = PREC == 0 ? TC_LD : 2 * TC_LD;        // float4 per thread, operand and stage
+  const int KT = MODE == 0 ? K / BKV : (int)((r_end - r_begin + BKV - 1) / BKV);
   // two register sets: the global loads of tile kt+1 are issued before tile kt is split and stored,
   // so a full iteration (stores, barrier, MMA issue) hides their latency
-  float4 va[2][TC_LD], vb[2][TC_LD];
-  auto load_tile = [&](int kt_, float4 (&xa)[TC_LD], float4 (&xb)[TC_LD]) {
+  float4 va[2][NV], vb[2][NV];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_tile = [&](int kt_, float4 (&xa)[NV], float4 (&xb)[NV]) {
     if (MODE == 0) {   // element e = i*TC_THREADS + t → row e/8, 16-byte chunk e%8 of the K-major tile
 #pragma unroll
       for (int i = 0; i < TC_LD; i++) {
         const int e = i * TC_THREADS + t, r = e >> 3, c = e & 7;
         const int64_t gr = row0 + r;
-        xa[i] = gr < Mc ? __ldg(reinterpret_cast<const float4*>(A + gr * K + (size_t)kt_ * TC_BK + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xb[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)(col0 + r) * K + (size_t)kt_ * TC_BK + c * 4));
+        if (PREC == 0) {
+          xa[i] = gr < Mc ? __ldg(reinterpret_cast<const float4*>(A + gr * K + (size_t)kt_ * BKV + c * 4)) : zero4;
+          xb[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)(col0 + r) * K + (size_t)kt_ * BKV + c * 4));
+        } else {       // a chunk holds 8 bf16 = 8 K values = two float4
+          const float4* pa = reinterpret_cast<const float4*>(A + gr * K + (size_t)kt_ * BKV + c * 8);
+          const float4* pb = reinterpret_cast<const float4*>(W + (size_t)(col0 + r) * K + (size_t)kt_ * BKV + c * 8);
+          xa[2 * i] = gr < Mc ? __ldg(pa) : zero4;
+          xa[2 * i + 1] = gr < Mc ? __ldg(pa + 1) : zero4;
+          xb[2 * i] = __ldg(pb);
+          xb[2 * i + 1] = __ldg(pb + 1);
+        }
       }
     } else {           // lane ↔ row r of the step, warp w covers m (n) = 16w … 16w+15, four at a time
-      const int64_t gr = r_begin + (int64_t)kt_ * TC_BK + lane;
 #pragma unroll
-      for (int i = 0; i < TC_LD; i++) {
-        const int m4 = warp * TC_LD + i;
-        xa[i] = gr < r_end ? __ldg(reinterpret_cast<const float4*>(A + gr * K + row0 + 4 * m4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xb[i] = gr < r_end ? __ldg(reinterpret_cast<const float4*>(W + gr * N + col0 + 4 * m4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int h = 0; h < (PREC == 0 ? 1 : 2); h++) {
+        const int64_t gr = r_begin + (int64_t)kt_ * BKV + h * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < TC_LD; i++) {
+          const int m4 = warp * TC_LD + i;
+          xa[h * TC_LD + i] = gr < r_end ? __ldg(reinterpret_cast<const float4*>(A + gr * K + row0 + 4 * m4)) : zero4;
+          xb[h * TC_LD + i] = gr < r_end ? __ldg(reinterpret_cast<const float4*>(W + gr * N + col0 + 4 * m4)) : zero4;
+        }
       }
     }
   };
-  auto store_tile = [&](unsigned char* st, const float4 (&xa)[TC_LD], const float4 (&xb)[TC_LD]) {
+  auto store_tile = [&](unsigned char* st, const float4 (&xa)[NV], const float4 (&xb)[NV]) {
+    unsigned char *ahi = st, *alo = st + TC_TILE_BYTES, *bhi = st + 2 * TC_TILE_BYTES, *blo = st + 3 * TC_TILE_BYTES;
     if (MODE == 0) {
 #pragma unroll
       for (int i = 0; i < TC_LD; i++) {
         const int e = i * TC_THREADS + t, r = e >> 3, c = e & 7;
-        split_store(st, st + TC_TILE_BYTES, r, c, xa[i]);
-        split_store(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, r, c, xb[i]);
+        if (PREC == 0) {
+          split_store(ahi, alo, r, c, xa[i]);
+          split_store(bhi, blo, r, c, xb[i]);
+        } else {
+          split_store_bf16(ahi, alo, r, c, xa[2 * i], xa[2 * i + 1]);
+          split_store_bf16(bhi, blo, r, c, xb[2 * i], xb[2 * i + 1]);
+        }
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < TC_LD; i++) {
-        const int m = 4 * (warp * TC_LD + i);
-        split_store1(st, st + TC_TILE_BYTES, m + 0, lane, xa[i].x);
-        split_store1(st, st + TC_TILE_BYTES, m + 1, lane, xa[i].y);
-        split_store1(st, st + TC_TILE_BYTES, m + 2, lane, xa[i].z);
-        split_store1(st, st + TC_TILE_BYTES, m + 3, lane, xa[i].w);
-        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 0, lane, xb[i].x);
-        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 1, lane, xb[i].y);
-        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 2, lane, xb[i].z);
-        split_store1(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, m + 3, lane, xb[i].w);
+      for (int h = 0; h < (PREC == 0 ? 1 : 2); h++) {
+        const int col = h * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < TC_LD; i++) {
+          const int m = 4 * (warp * TC_LD + i);
+          const float4 a4 = xa[h * TC_LD + i], b4 = xb[h * TC_LD + i];
+          if (PREC == 0) {
+            split_store1(ahi, alo, m + 0, col, a4.x); split_store1(ahi, alo, m + 1, col, a4.y);
+            split_store1(ahi, alo, m + 2, col, a4.z); split_store1(ahi, alo, m + 3, col, a4.w);
+            split_store1(bhi, blo, m + 0, col, b4.x); split_store1(bhi, blo, m + 1, col, b4.y);
+            split_store1(bhi, blo, m + 2, col, b4.z); split_store1(bhi, blo, m + 3, col, b4.w);
+          } else {
+            split_store1_bf16(ahi, alo, m + 0, col, a4.x); split_store1_bf16(ahi, alo, m + 1, col, a4.y);
+            split_store1_bf16(ahi, alo, m + 2, col, a4.z); split_store1_bf16(ahi, alo, m + 3, col, a4.w);
+            split_store1_bf16(bhi, blo, m + 0, col, b4.x); split_store1_bf16(bhi, blo, m + 1, col, b4.y);
+            split_store1_bf16(bhi, blo, m + 2, col, b4.z); split_store1_bf16(bhi, blo, m + 3, col, b4.w);
+          }
+        }
       }
     }
   };
-  if (KT > 0) load_tile(0, va[0], vb[0]);
+  // warp-specialised main loop, no block-wide barrier: warps 0-7 produce stages (global → registers →
+  // tf32/bf16 split → swizzled shared memory) and arrive on bar_full; lane 0 of warp 8 waits for a full
+  // stage, issues its MMAs and lets tcgen05.commit release the stage (bar_mma) when they have completed
+  if (warp < TC_THREADS / 32) {
+    if (KT > 0) load_tile(0, va[0], vb[0]);
 #pragma unroll 2
-  for (int kt = 0; kt < KT; kt++) {
-    const int s = kt % TC_STAGES;
-    if (kt + 1 < KT) {
-      if (kt & 1) load_tile(kt + 1, va[0], vb[0]); else load_tile(kt + 1, va[1], vb[1]);
+    for (int kt = 0; kt < KT; kt++) {
+      const int s = kt % TC_STAGES;
+      if (kt + 1 < KT) {
+        if (kt & 1) load_tile(kt + 1, va[0], vb[0]); else load_tile(kt + 1, va[1], vb[1]);
+      }
+      // the stage is free once the MMAs issued TC_STAGES iterations ago have completed
+      if (kt >= TC_STAGES) mbar_wait(&bar_mma[s], ((kt / TC_STAGES) - 1) & 1);
+      unsigned char* st = tiles + (size_t)s * TC_STAGE_BYTES;
+      if (kt & 1) store_tile(st, va[1], vb[1]); else store_tile(st, va[0], vb[0]);
+      // generic-proxy writes → visible to the tensor core's async proxy, then one arrival per warp
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[s]);
     }
-    // the stage is free once the MMAs issued TC_STAGES iterations ago have completed
-    if (kt >= TC_STAGES) mbar_wait(&bar_mma[s], ((kt / TC_STAGES) - 1) & 1);
-    unsigned char* st = tiles + (size_t)s * TC_STAGE_BYTES;
-    if (kt & 1) store_tile(st, va[1], vb[1]); else store_tile(st, va[0], vb[0]);
-    // generic-proxy writes → visible to the tensor core's async proxy
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (t == 0) {
+  } else if (lane == 0) {
+    for (int kt = 0; kt < KT; kt++) {
+      const int s = kt % TC_STAGES;
+      mbar_wait(&bar_full[s], (kt / TC_STAGES) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_TILE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
+      const uint32_t a_hi = smem_u32(tiles + (size_t)s * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES,
+                     b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
 #pragma unroll
-      for (int ks = 0; ks < TC_BK / 8; ks++) {   // UMMA_K = 8 for tf32: 32 bytes along the swizzled row
+      for (int ks = 0; ks < 4; ks++) {   // UMMA_K = 8 tf32 or 16 bf16: 32 bytes along the swizzled 128-byte row
         const uint32_t o = ks * 32;
-        mma_tf32(tmem_d, make_desc(a_hi + o), make_desc(b_hi + o), (kt > 0 || ks > 0) ? 1u : 0u);
-        mma_tf32(tmem_d, make_desc(a_hi + o), make_desc(b_lo + o), 1u);
-        mma_tf32(tmem_d, make_desc(a_lo + o), make_desc(b_hi + o), 1u);
+        if (PREC == 0) {
+          mma_tf32(tmem_d, make_desc(a_hi + o), make_desc(b_hi + o), (kt > 0 || ks > 0) ? 1u : 0u);
+          mma_tf32(tmem_d, make_desc(a_hi + o), make_desc(b_lo + o), 1u);
+          mma_tf32(tmem_d, make_desc(a_lo + o), make_desc(b_hi + o), 1u);
+        } else {
+          mma_bf16(tmem_d, make_desc(a_hi + o), make_desc(b_hi + o), (kt > 0 || ks > 0) ? 1u : 0u);
+          mma_bf16(tmem_d, make_desc(a_hi + o), make_desc(b_lo + o), 1u);
+          mma_bf16(tmem_d, make_desc(a_lo + o), make_desc(b_hi + o), 1u);
+        }
       }
       // arrives on the barrier when all MMAs issued so far have completed (implies before_thread_sync)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma[s])) : "memory");
@@ -217,13 +308,13 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
     }
   }
   // epilogue: TMEM → registers → global.  Warp w owns TMEM lanes 32w … 32w+31.
-  if (KT > 0) mbar_wait(&bar_done, 0);
+  if (KT > 0 && warp < TC_THREADS / 32) mbar_wait(&bar_done, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   // warp w may only touch TMEM lanes 32·(w mod 4) …; warps 0-3 take the first half of the columns, 4-7 the second
   const int wq = warp & 3;
   const int64_t grow = row0 + wq * 32 + lane;
 #pragma unroll 1
-  for (int cb = (warp >> 2) * (TC_BN / 2); cb < ((warp >> 2) + 1) * (TC_BN / 2); cb += 32) {
+  for (int cb = (warp >> 2) * (TC_BN / 2); cb < ((warp >> 2) + 1) * (TC_BN / 2) && warp < TC_THREADS / 32; cb += 32) {
     uint32_t v[32];
     if (KT > 0) {
       const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + cb;
@@ -276,15 +367,24 @@ k_dense_tc(const float* __restrict__ A, const float* __restrict__ W, const float
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_BN));
 }
 
-// C = epi(A·Wᵀ); device pointers; requires K % 32 == 0, N % 128 == 0, 16-byte aligned rows
+// operand precision of the tensor-core GEMMs: HVI_TC_PREC=0 → 3xTF32, 1 → 3xBF16 (default)
+static int tc_prec() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HVI_TC_PREC"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+// C = epi(A·Wᵀ); device pointers; requires K % 64 == 0 (32 with TF32), N % 128 == 0, 16-byte aligned rows
 cudaError_t launch_dense_tc(cudaStream_t stream, const float* A, const float* W, const float* bias, float* C, int64_t Mc,
                             int N, int K, int act, const float* Hd = nullptr) {
   if (K % TC_BK != 0 || N % TC_BN != 0 || Mc < 1) return cudaErrorInvalidValue;
+  const bool bf = tc_prec() == 1 && K % (2 * TC_BK) == 0;
   const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
-  cudaError_t e = cudaFuncSetAttribute(k_dense_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = bf ? k_dense_tc<0, 1> : k_dense_tc<0, 0>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)(N / TC_BN), (unsigned)((Mc + TC_BM - 1) / TC_BM));
-  k_dense_tc<0><<<grid, TC_THREADS, smem, stream>>>(A, W, bias, C, Mc, N, K, act, Hd, 0);
+  kern<<<grid, TC_BLOCK, smem, stream>>>(A, W, bias, C, Mc, N, K, act, Hd, 0);
   return cudaGetLastError();
 }
 
@@ -292,13 +392,16 @@ cudaError_t launch_dense_tc(cudaStream_t stream, const float* A, const float* W,
 cudaError_t launch_wgrad_tc(cudaStream_t stream, const float* X, const float* Y, float* P, int64_t rows, int Md, int Nd,
                             int nsplit) {
   if (Md % TC_BM != 0 || Nd % TC_BN != 0 || rows < 1 || nsplit < 1) return cudaErrorInvalidValue;
+  const bool bf = tc_prec() == 1;
+  const int bkv = bf ? 2 * TC_BK : TC_BK;
   const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
-  cudaError_t e = cudaFuncSetAttribute(k_dense_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = bf ? k_dense_tc<1, 1> : k_dense_tc<1, 0>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int64_t per = (rows + nsplit - 1) / nsplit;
-  per = (per + TC_BK - 1) / TC_BK * TC_BK;
+  per = (per + bkv - 1) / bkv * bkv;
   dim3 grid((unsigned)(Md / TC_BM), (unsigned)(Nd / TC_BN), (unsigned)nsplit);
-  k_dense_tc<1><<<grid, TC_THREADS, smem, stream>>>(X, Y, nullptr, P, rows, Nd, Md, 0, nullptr, per);
+  kern<<<grid, TC_BLOCK, smem, stream>>>(X, Y, nullptr, P, rows, Nd, Md, 0, nullptr, per);
   return cudaGetLastError();
 }
 
