@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "hvi_internal.cuh"
+#include "hvi_tc_common.cuh"
 
 namespace hvi {
 
@@ -28,33 +29,6 @@ constexpr int TC_LD = 1024 / TC_THREADS;   // float4 per thread, operand and sta
 constexpr int TC_BLOCK = TC_THREADS + 32;   // 8 producer/epilogue warps + 1 warp whose lane 0 issues the MMAs
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;              // 16 KB per operand half
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;             // A hi, A lo, B hi, B lo
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-// start address >> 4 [0,14) | LBO (unused for swizzled K-major) = 1 [16,30) | SBO = 1024 B >> 4 [32,46)
-// | version = 1 [46,48) | layout type SWIZZLE_128B = 2 [61,64)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
 
 // instruction descriptor (InstrDescriptor): D = F32 [4,6)=1, A = TF32 [7,10)=2, B = TF32 [10,13)=2,
 // both K-major, N >> 3 [17,23), M >> 4 [24,29)
@@ -109,14 +83,6 @@ __device__ __forceinline__ void split_store1(unsigned char* tile_hi, unsigned ch
   *reinterpret_cast<float*>(tile_lo + off) = x - hi;
 }
 
-// bf16 variant of the split: x ≈ hi + lo with hi = bf16(x), lo = bf16(x − hi) (16 mantissa bits together);
-// three products hi·hi + hi·lo + lo·hi at twice the tf32 rate and half the shared-memory bytes
-__device__ __forceinline__ void bf16_split(float x, unsigned short& hi, unsigned short& lo) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(x);
-  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-  hi = __bfloat16_as_ushort(h);
-  lo = __bfloat16_as_ushort(l);
-}
 // eight consecutive K values (two float4) → one 16-byte chunk of bf16 hi and one of lo at (row, chunk)
 __device__ __forceinline__ void split_store_bf16(unsigned char* tile_hi, unsigned char* tile_lo, int row, int chunk, float4 v0, float4 v1) {
   unsigned short h[8], l[8];
@@ -135,12 +101,6 @@ __device__ __forceinline__ void split_store1_bf16(unsigned char* tile_hi, unsign
   const int off = row * 128 + ((((col >> 3) ^ (row & 7))) << 4) + ((col & 7) << 1);
   *reinterpret_cast<unsigned short*>(tile_hi + off) = h;
   *reinterpret_cast<unsigned short*>(tile_lo + off) = l;
-}
-
-__device__ __forceinline__ float act_deriv_f(int act, float h) {
-  if (act == HVI_ACT_TANH) return 1.f - h * h;
-  if (act == HVI_ACT_LOGISTIC) return h * (1.f - h);
-  return 1.f;
 }
 
 // MODE 0 (layer / data gradient):  C[Mc x N] = epi(A[Mc x K] · W[N x K]ᵀ),
@@ -412,13 +372,6 @@ cudaError_t launch_wgrad_tc(cudaStream_t stream, const float* X, const float* Y,
 // fits (K % 32 == 0, N % 128 == 0, Float32) run on the tensor cores (k_dense_tc), the first layer
 // (K = n_covar) and the last (N = n_θM, fused logistic + Φ⁻¹ scaling) on CUDA cores.
 // ---------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ T act_apply(int act, T z) {
-  if (act == HVI_ACT_TANH) return tanh(z);
-  if (act == HVI_ACT_LOGISTIC) return T(1) / (T(1) + exp(-z));
-  return z;
-}
-
 // W_ref: the reference's layout vec(W[out x in]) column-major = [in][out]; Wt: [out][in] row-major
 template <typename T>
 __global__ void k_transpose_w(const T* __restrict__ Wref, T* __restrict__ Wt, int n_in, int n_out) {
@@ -484,6 +437,9 @@ template <typename T>
 cudaError_t launch_mlp_fwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu,
                                 int M_units, const T* zetaP, T* work /*wide_work_elems(cfg)*/) {
   if (cfg.l_bias[cfg.nL - 1] || cfg.l_out[cfg.nL - 1] > MAXP) return cudaErrorInvalidConfiguration;
+  if constexpr (sizeof(T) == 4) {   // TMA-fed 3xBF16 chain (hvi_dense_tma.cu) when every hidden width is a multiple of 128
+    if (bf3_eligible(cfg)) return launch_mlp_fwd_bf3(L, cfg, phi, xM, nb, mu, M_units, zetaP, work);
+  }
   const int64_t CHUNK = 65536;
   const int maxw = cfg.max_width;
   T* buf0 = work;
@@ -556,26 +512,6 @@ cudaError_t launch_mlp_fwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi
 // over the rows, fp32 partial tiles summed in a fixed order into a double accumulator).  The first
 // layer (K = n_covar), the last (N = n_θM) and all biases use the "skinny" reduction kernels.
 // ---------------------------------------------------------------------------------------
-constexpr int64_t WIDE_CHUNK = 65536;
-constexpr int WIDE_SPLIT = 8;        // row splits of the weight-gradient GEMM
-constexpr int SKINNY_ROWS = 128;     // rows per block of the skinny reductions (many blocks: the kernel is latency bound)
-constexpr int XS_LD = 16;            // leading dimension of the small input matrix [x ; pbm covariates ; 1]
-
-template <typename T>
-__global__ void k_build_xs(const T* __restrict__ xM, int nC, const T* __restrict__ extra, int npc, int64_t site0,
-                           int64_t rows, T* __restrict__ Xs) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  for (int i = 0; i < XS_LD; i++) {
-    T v = T(0);
-    if (i < nC) v = xM[(site0 + r) * nC + i];
-    else if (i < nC + npc) v = extra[i - nC];
-    else if (i == nC + npc) v = T(1);
-    Xs[r * XS_LD + i] = v;
-  }
-}
-
-// G[s][b] = Σ_r S[r·ls + s]·B[r·lb + b] over this block's row slice; one thread per b
 template <typename T>
 __global__ void __launch_bounds__(256) k_skinny(const T* __restrict__ S, int ls, int ns, const T* __restrict__ B, int lb,
                                                 int nbig, int64_t rows, float* __restrict__ part) {
@@ -617,20 +553,6 @@ __global__ void __launch_bounds__(256) k_skinny<double>(const double* __restrict
     for (int s = 0; s < ns; s++) acc[s] = fma(S[r * ls + s], y, acc[s]);
   }
   for (int s = 0; s < ns; s++) part[((size_t)blockIdx.y * ns + s) * nbig + b] = acc[s];
-}
-
-// acc[off + s·stride_s + b·stride_b] += Σ_slices part[slice·slice_stride + s·nbig + b]  (fixed order);
-// optional copy of the sums; acc == NULL only fills chunk_sum
-template <typename PT>
-__global__ void k_accum(const PT* __restrict__ part, int nslice, size_t slice_stride, int ns, int nbig,
-                        double* __restrict__ acc, int off, int stride_s, int stride_b, double* __restrict__ chunk_sum) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ns * nbig) return;
-  const int s = e / nbig, b = e % nbig;
-  double t = 0.0;
-  for (int sl = 0; sl < nslice; sl++) t += (double)part[(size_t)sl * slice_stride + (size_t)s * nbig + b];
-  if (acc) acc[off + s * stride_s + b * stride_b] += t;
-  if (chunk_sum) chunk_sum[e] = t;
 }
 
 // last layer backward: one warp per row.  z_k = Σ_i H[r][i] W[i][k]; p = act(z); δ_L[k] = μ̄·scale'·act'(p);
@@ -699,29 +621,26 @@ __global__ void __launch_bounds__(256) k_wgrad_simple(const T* __restrict__ Hpre
   acc[e] += s;
 }
 
-// x̄[m][c] += Σ_j W_0[nC + c][j]·(Σ_r δ_0[r][j])  for this chunk
-template <typename T>
-__global__ void k_xbar(const T* __restrict__ W0, int nC, int npc, int N, const double* __restrict__ db0_chunk,
-                       double* __restrict__ xacc_m) {
-  const int c = threadIdx.x;
-  if (c >= npc) return;
-  double s = 0.0;
-  for (int j = 0; j < N; j++) s += (double)W0[(size_t)(nC + c) * N + j] * db0_chunk[j];
-  xacc_m[c] += s;
+size_t wide_work_elems(int max_width, int nphig) {
+  const size_t a = (size_t)2 * 65536 * max_width + (size_t)nphig + 16, b = (bf3_fwd_work_bytes(max_width, nphig) + 3) / 4;
+  return a > b ? a : b;
 }
-
-size_t wide_work_elems(int max_width, int nphig) { return (size_t)2 * 65536 * max_width + (size_t)nphig + 16; }
 // elements of T (treated as 8 bytes each for the double/float mix) of the backward work space
 size_t wide_bwd_work_bytes(int nL, int max_width, int nphig) {
   const size_t cw = (size_t)WIDE_CHUNK * max_width;
-  return 8 * ((size_t)(nL + 1) * cw + (size_t)nphig + (size_t)WIDE_SPLIT * max_width * max_width +
-              (size_t)WIDE_CHUNK * (8 + XS_LD) + (size_t)(WIDE_CHUNK / SKINNY_ROWS) * 16 * max_width + 4 * (size_t)max_width + 1024);
+  const size_t a = 8 * ((size_t)(nL + 1) * cw + (size_t)nphig + (size_t)WIDE_SPLIT * max_width * max_width +
+                        (size_t)WIDE_CHUNK * (8 + XS_LD) + (size_t)(WIDE_CHUNK / SKINNY_ROWS) * 16 * max_width + 4 * (size_t)max_width + 1024);
+  const size_t b = bf3_bwd_work_bytes(nL, max_width, nphig);
+  return a > b ? a : b;
 }
 
 template <typename T>
 cudaError_t launch_mlp_bwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, const T* mubar,
                                 int M_units, const T* zetaP, void* work, double* grad_acc, double* xacc) {
   if (cfg.l_bias[cfg.nL - 1] || cfg.l_out[cfg.nL - 1] > 8 || cfg.nC + cfg.npc + 1 > 8) return cudaErrorInvalidConfiguration;
+  if constexpr (sizeof(T) == 4) {
+    if (bf3_eligible(cfg)) return launch_mlp_bwd_bf3(L, cfg, phi, xM, nb, mubar, M_units, zetaP, work, grad_acc, xacc);
+  }
   const int nL = cfg.nL, maxw = cfg.max_width;
   const size_t cw = (size_t)WIDE_CHUNK * maxw;
   // carve the work space

@@ -1,0 +1,848 @@
+// hvi_dense_tma.cu -- the wide applicator (BASELINE config 5: 4x512 hidden) as a chain of TMA-fed,
+// warp-specialised, persistent tcgen05 GEMMs with error-compensated bf16 operands ("3xBF16").
+//
+// Data layout in HBM.  Every activation H_l and every cotangent δ_l of a chunk of columns is kept as
+// two bf16 planes, hi = bf16(x) and lo = bf16(x − hi) (16 mantissa bits together, the footprint of one
+// fp32 array), in two orientations: [row][feature] (K-major operand of the layer / data-gradient
+// GEMMs) and [feature][row] (K-major operand of the weight-gradient GEMM, whose contraction runs over
+// the rows).  The epilogue that produces a tensor writes all planes it will be read in, so no GEMM
+// converts, splits or transposes anything on its way into shared memory: TMA (cp.async.bulk.tensor,
+// SWIZZLE_128B) drops the tiles where tcgen05.mma reads them.
+//
+// Kernel k_gemm_bf3<BN, MODE>:  D[M x N] = Σ_k A[m][k]·B[n][k]  with A ≈ A_hi + A_lo, B ≈ B_hi + B_lo and
+// three MMAs per K step (hi·hi + hi·lo + lo·hi) into one fp32 TMEM accumulator.
+//   warp 0 (one lane)  TMA producer: 4 tiles per stage (A hi/lo 128 x 64, B hi/lo BN x 64) → full barrier
+//   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN, K = 16;
+//                      tcgen05.commit frees the stage (empty barrier) and publishes the accumulator
+//   warps 2-5          epilogue: tcgen05.ld of one of the TWO accumulators (2·BN TMEM columns) while the
+//                      MMA warp fills the other one for the CTA's next tile (persistent, static schedule)
+//   MODE 0  H = act(D + bias)                          layer forward
+//   MODE 1  δ_{l-1} = D ⊙ act'(H_{l-1})                data gradient (D = δ_l W_l)
+//   MODE 2  P[split] = D over this split's K range     weight gradient, split over the rows
+//
+// Reference: the dense layers of g and their Zygote pullbacks
+// (ext/HybridVariationalInferenceSimpleChainsExt.jl:43-52, ext/HybridVariationalInferenceFluxExt.jl:26-31).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "hvi_internal.cuh"
+#include "hvi_tc_common.cuh"
+
+namespace hvi {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int G_BM = 128;            // rows per tile = TMEM lanes
+constexpr int G_BK = 64;             // K per stage: 64 bf16 = one 128-byte swizzle row
+constexpr int G_THREADS = 192;       // TMA warp, MMA warp, 4 epilogue warps
+
+template <int BN>
+struct GemmTile {
+  static constexpr int A_BYTES = G_BM * 128;                       // one plane of A per stage (16 KB)
+  static constexpr int B_BYTES = BN * 128;                         // one plane of B per stage
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);      // hi + lo of both
+  static constexpr int STAGES = BN == 256 ? 2 : 3;                 // 192 KB of shared memory either way
+  static constexpr int TMEM_COLS = 2 * BN;                         // two accumulators
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
+};
+
+// planes of one tensor: normal [rows][ld] and (optional) transposed [feature][ldT]
+struct Planes {
+  bf16 *hi, *lo;
+  int64_t ld;
+  bf16 *hiT, *loT;
+  int64_t ldT;
+};
+
+struct GemmShape {
+  int64_t M;             // rows of A (and of D)
+  int N;                 // rows of B = columns of D
+  int64_t K;             // contraction length
+  int nsplit;            // MODE 2: K is cut into nsplit ranges of k_per_split
+  int64_t k_per_split;
+};
+
+struct GemmEpi {
+  const float* bias;     // MODE 0 (nullable)
+  int act;               // MODE 0: activation; MODE 1: activation of the layer below
+  Planes out;            // MODE 0/1
+  const bf16 *h_hi, *h_lo;   // MODE 1: activation of the layer below, normal planes
+  int64_t ldh;
+  float* P;              // MODE 2: [split][M][N]
+};
+
+// ---- PTX ---------------------------------------------------------------------------------
+// bounded wait: a protocol error traps after ~2 s instead of hanging the device
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c_inner, int c_outer, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner), "r"(c_outer), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- plane helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// 32 consecutive features of one row (this lane's), fp32 → hi/lo planes in both orientations.
+// Normal planes: 64 contiguous bytes per lane and plane; transposed planes: the 32 lanes of the warp are
+// 32 consecutive rows, so every 2-byte store of the warp lands in one 64-byte segment.
+__device__ __forceinline__ void store_planes32(const Planes& o, int64_t row, int col0, const float (&x)[32], bool ok) {
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * j] - __low2float(hh), x[2 * j + 1] - __high2float(hh));
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  if (!ok) return;
+  uint4* ph = reinterpret_cast<uint4*>(o.hi + row * o.ld + col0);
+  uint4* pl = reinterpret_cast<uint4*>(o.lo + row * o.ld + col0);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    ph[q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    pl[q] = make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
+  }
+  if (o.hiT) {
+    unsigned short* th = reinterpret_cast<unsigned short*>(o.hiT) + (int64_t)col0 * o.ldT + row;
+    unsigned short* tl = reinterpret_cast<unsigned short*>(o.loT) + (int64_t)col0 * o.ldT + row;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      th[(int64_t)(2 * j) * o.ldT] = (unsigned short)(h[j] & 0xFFFFu);
+      th[(int64_t)(2 * j + 1) * o.ldT] = (unsigned short)(h[j] >> 16);
+      tl[(int64_t)(2 * j) * o.ldT] = (unsigned short)(l[j] & 0xFFFFu);
+      tl[(int64_t)(2 * j + 1) * o.ldT] = (unsigned short)(l[j] >> 16);
+    }
+  }
+}
+// 32 consecutive features of one row from the normal planes, recombined to fp32
+__device__ __forceinline__ void load_planes32(const bf16* hi, const bf16* lo, int64_t ld, int64_t row, int col0, float (&x)[32]) {
+  const uint4* ph = reinterpret_cast<const uint4*>(hi + row * ld + col0);
+  const uint4* pl = reinterpret_cast<const uint4*>(lo + row * ld + col0);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint4 a = __ldg(ph + q), b = __ldg(pl + q);
+    x[8 * q + 0] = bf_lo(a.x) + bf_lo(b.x); x[8 * q + 1] = bf_hi(a.x) + bf_hi(b.x);
+    x[8 * q + 2] = bf_lo(a.y) + bf_lo(b.y); x[8 * q + 3] = bf_hi(a.y) + bf_hi(b.y);
+    x[8 * q + 4] = bf_lo(a.z) + bf_lo(b.z); x[8 * q + 5] = bf_hi(a.z) + bf_hi(b.z);
+    x[8 * q + 6] = bf_lo(a.w) + bf_lo(b.w); x[8 * q + 7] = bf_hi(a.w) + bf_hi(b.w);
+  }
+}
+
+// ---- the GEMM ------------------------------------------------------------------------------
+template <int BN, int MODE>
+__global__ void __launch_bounds__(G_THREADS, 1)
+k_gemm_bf3(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+           const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, const GemmShape sh,
+           const GemmEpi ep) {
+  typedef GemmTile<BN> TL;
+  constexpr int S = TL::STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_full[S], bar_empty[S], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+  const int m_tiles = (int)((sh.M + G_BM - 1) / G_BM), n_tiles = sh.N / BN;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int total = mn_tiles * sh.nsplit;
+
+  if (t == 0) {
+    for (int s = 0; s < S; s++) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(TL::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int split = tile / mn_tiles, mn = tile % mn_tiles;
+        const int m0 = (mn / n_tiles) * G_BM, n0 = (mn % n_tiles) * BN;
+        const int64_t k0 = (int64_t)split * sh.k_per_split;
+        const int64_t k1 = k0 + sh.k_per_split < sh.K ? k0 + sh.k_per_split : sh.K;
+        const int nk = (int)((k1 - k0 + G_BK - 1) / G_BK);
+        for (int kb = 0; kb < nk; kb++, it++) {
+          const int s = it % S;
+          mbar_wait_b(&bar_empty[s], ((it / S) & 1) ^ 1);
+          mbar_expect_tx(&bar_full[s], TL::STAGE_BYTES);
+          const uint32_t base = smem_u32(tiles + (size_t)s * TL::STAGE_BYTES);
+          const int kc = (int)(k0 + (int64_t)kb * G_BK);
+          tma_load_2d(base, &mA_hi, kc, m0, &bar_full[s]);
+          tma_load_2d(base + TL::A_BYTES, &mA_lo, kc, m0, &bar_full[s]);
+          tma_load_2d(base + 2 * TL::A_BYTES, &mB_hi, kc, n0, &bar_full[s]);
+          tma_load_2d(base + 2 * TL::A_BYTES + TL::B_BYTES, &mB_lo, kc, n0, &bar_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t it = 0, tc = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, tc++) {
+        const int split = tile / mn_tiles;
+        const int64_t k0 = (int64_t)split * sh.k_per_split;
+        const int64_t k1 = k0 + sh.k_per_split < sh.K ? k0 + sh.k_per_split : sh.K;
+        const int nk = (int)((k1 - k0 + G_BK - 1) / G_BK);
+        const uint32_t acc = tc & 1;
+        mbar_wait_b(&bar_tempty[acc], ((tc >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem_base + acc * BN;
+        for (int kb = 0; kb < nk; kb++, it++) {
+          const int s = it % S;
+          mbar_wait_b(&bar_full[s], (it / S) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(tiles + (size_t)s * TL::STAGE_BYTES), a_lo = a_hi + TL::A_BYTES,
+                         b_hi = a_hi + 2 * TL::A_BYTES, b_lo = b_hi + TL::B_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < G_BK / 16; ks++) {   // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
+            const uint32_t o = ks * 32;
+            umma_bf16(d, make_desc(a_hi + o), make_desc(b_hi + o), TL::IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16(d, make_desc(a_hi + o), make_desc(b_lo + o), TL::IDESC, 1u);
+            umma_bf16(d, make_desc(a_lo + o), make_desc(b_hi + o), TL::IDESC, 1u);
+          }
+          umma_commit(&bar_empty[s]);               // stage free once these MMAs have read it
+        }
+        umma_commit(&bar_tfull[acc]);               // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue: warp w may only touch TMEM lanes 32·(w mod 4) … =====
+    const int q = warp & 3;
+    uint32_t tc = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, tc++) {
+      const int split = tile / mn_tiles, mn = tile % mn_tiles;
+      const int m0 = (mn / n_tiles) * G_BM, n0 = (mn % n_tiles) * BN;
+      const int64_t k0 = (int64_t)split * sh.k_per_split;
+      const bool empty_k = k0 >= sh.K;
+      const uint32_t acc = tc & 1;
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
+      const bool ok = row < sh.M;
+      mbar_wait_b(&bar_tfull[acc], (tc >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb, v);
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) x[j] = empty_k ? 0.f : __uint_as_float(v[j]);
+        const int col0 = n0 + cb;
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            float z = x[j] + (ep.bias ? __ldg(ep.bias + col0 + j) : 0.f);
+            if (ep.act == HVI_ACT_TANH) z = tanhf(z);
+            else if (ep.act == HVI_ACT_LOGISTIC) z = 1.f / (1.f + expf(-z));
+            x[j] = z;
+          }
+          store_planes32(ep.out, row, col0, x, ok);
+        } else if (MODE == 1) {
+          float h[32];
+          if (ok) load_planes32(ep.h_hi, ep.h_lo, ep.ldh, row, col0, h);
+#pragma unroll
+          for (int j = 0; j < 32; j++) x[j] *= ok ? act_deriv_f(ep.act, h[j]) : 0.f;
+          store_planes32(ep.out, row, col0, x, ok);
+        } else if (ok) {
+          float4* out = reinterpret_cast<float4*>(ep.P + ((size_t)split * sh.M + row) * sh.N + col0);
+#pragma unroll
+          for (int j = 0; j < 8; j++) out[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TL::TMEM_COLS));
+}
+
+// ---- host side: tensor maps and the launcher -------------------------------------------------
+static PFN_cuTensorMapEncodeTiled tma_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }
+  return fn;
+}
+// bf16 matrix [outer][ld] with `inner` valid elements per row, boxes of 64 x box_outer, 128-byte swizzle;
+// out-of-range elements read as zero
+static bool make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+  PFN_cuTensorMapEncodeTiled enc = tma_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)G_BK, box_outer};
+  const cuuint32_t es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int bf3_wgrad_splits(int Md, int Nd, int sm_count) {
+  const int bn = Nd % 256 == 0 ? 256 : 128;
+  const int tiles = (Md / G_BM) * (Nd / bn);
+  int ns = sm_count / (tiles > 0 ? tiles : 1);
+  return ns < 1 ? 1 : (ns > 24 ? 24 : ns);
+}
+
+// D = A·Bᵀ with A [M][lda] (K valid per row), B [N][ldb]; N % 128 == 0, lda/ldb % 8 == 0, 16-byte aligned bases
+template <int MODE>
+static cudaError_t launch_gemm_bf3(const Launch& L, const bf16* A_hi, const bf16* A_lo, int64_t lda, int64_t M, const bf16* B_hi,
+                                   const bf16* B_lo, int64_t ldb, int N, int64_t K, int nsplit, const GemmEpi& ep) {
+  if (N % 128 != 0 || lda % 8 != 0 || ldb % 8 != 0 || M < 1 || K < 1) return cudaErrorInvalidValue;
+  const int bn = N % 256 == 0 ? 256 : 128;
+  GemmShape sh;
+  sh.M = M; sh.N = N; sh.K = K;
+  int64_t per = (K + nsplit - 1) / nsplit;
+  per = (per + G_BK - 1) / G_BK * G_BK;
+  sh.k_per_split = per;
+  sh.nsplit = (int)((K + per - 1) / per);
+  CUtensorMap ma_h, ma_l, mb_h, mb_l;
+  if (!make_map(&ma_h, A_hi, (uint64_t)K, (uint64_t)M, (uint64_t)lda, G_BM) || !make_map(&ma_l, A_lo, (uint64_t)K, (uint64_t)M, (uint64_t)lda, G_BM) ||
+      !make_map(&mb_h, B_hi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)bn) ||
+      !make_map(&mb_l, B_lo, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)bn))
+    return cudaErrorInvalidValue;
+  const int m_tiles = (int)((M + G_BM - 1) / G_BM);
+  const int64_t total = (int64_t)m_tiles * (N / bn) * sh.nsplit;
+  const int sms = L.sm_count > 0 ? L.sm_count : 148;
+  const unsigned grid = (unsigned)(total < sms ? total : sms);
+  cudaError_t e;
+  if (bn == 256) {
+    const size_t smem = (size_t)GemmTile<256>::STAGES * GemmTile<256>::STAGE_BYTES + 1024;
+    auto kern = k_gemm_bf3<256, MODE>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, G_THREADS, smem, L.stream>>>(ma_h, ma_l, mb_h, mb_l, sh, ep);
+  } else {
+    const size_t smem = (size_t)GemmTile<128>::STAGES * GemmTile<128>::STAGE_BYTES + 1024;
+    auto kern = k_gemm_bf3<128, MODE>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, G_THREADS, smem, L.stream>>>(ma_h, ma_l, mb_h, mb_l, sh, ep);
+  }
+  if (L.counter) ++*L.counter;
+  return cudaGetLastError();
+}
+
+// ---- CUDA-core kernels around the GEMM chain -------------------------------------------------
+// weights of one layer, reference layout [in][out] fp32 → planes in the same layout (B operand of the
+// data-gradient GEMM: rows = in, K = out) and transposed [out][in] (B operand of the forward GEMM)
+__global__ void k_split_w(const float* __restrict__ W, int n_in, int n_out, bf16* __restrict__ n_hi, bf16* __restrict__ n_lo,
+                          bf16* __restrict__ t_hi, bf16* __restrict__ t_lo) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_in * n_out) return;
+  const int i = e / n_out, j = e % n_out;
+  unsigned short h, l;
+  bf16_split(W[e], h, l);
+  reinterpret_cast<unsigned short*>(n_hi)[e] = h;
+  reinterpret_cast<unsigned short*>(n_lo)[e] = l;
+  reinterpret_cast<unsigned short*>(t_hi)[(size_t)j * n_in + i] = h;
+  reinterpret_cast<unsigned short*>(t_lo)[(size_t)j * n_in + i] = l;
+}
+
+// fp32 [rows][W] → planes (tests, and the generic entry points); one warp per 32 rows x 32 features
+__global__ void __launch_bounds__(256) k_split_planes(const float* __restrict__ X, int64_t rows, int W, Planes o) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
+  const int col0 = blockIdx.y * 32;
+  const bool ok = row < rows;
+  float x[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) x[j] = ok ? X[row * W + col0 + j] : 0.f;
+  store_planes32(o, row, col0, x, ok);
+}
+// planes → fp32; transposed != 0 reads the [feature][row] planes instead
+__global__ void k_join_planes(Planes p, int64_t rows, int W, int transposed, float* __restrict__ X) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * W) return;
+  const int64_t r = e / W;
+  const int c = (int)(e % W);
+  const bf16* hi = transposed ? p.hiT + (int64_t)c * p.ldT + r : p.hi + r * p.ld + c;
+  const bf16* lo = transposed ? p.loT + (int64_t)c * p.ldT + r : p.lo + r * p.ld + c;
+  X[e] = __bfloat162float(*hi) + __bfloat162float(*lo);
+}
+
+// first layer (K = n_covar + pbm covariates ≤ 8) on CUDA cores: lane ↔ row, 64 features per warp
+__global__ void __launch_bounds__(256) k_first_bf3(const float* __restrict__ xM, int nC, const float* __restrict__ extra, int npc,
+                                                   int64_t site0, const float* __restrict__ W0, const float* __restrict__ b0, int act,
+                                                   int64_t rows, int N, Planes o) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
+  const bool ok = row < rows;
+  const int K = nC + npc;
+  float xin[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) xin[i] = (i < nC) ? (ok ? xM[(site0 + row) * nC + i] : 0.f) : (i < K ? extra[i - nC] : 0.f);
+#pragma unroll 1
+  for (int cb = blockIdx.y * 64; cb < blockIdx.y * 64 + 64; cb += 32) {
+    float z[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) z[j] = b0 ? __ldg(b0 + cb + j) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (i < K) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) z[j] = fmaf(xin[i], __ldg(W0 + (size_t)i * N + cb + j), z[j]);
+      }
+#pragma unroll
+    for (int j = 0; j < 32; j++) z[j] = act_apply<float>(act, z[j]);
+    store_planes32(o, row, cb, z, ok);
+  }
+}
+
+// last layer (N = n_θM ≤ 8): one warp per row, every lane 8 consecutive features per step.
+// BWD == 0: μ_ζ = scale(act(z));  BWD == 1: δ_L[k] = μ̄·scale'·act'  →  dlast[r][8]
+template <int BWD>
+__global__ void __launch_bounds__(256) k_last_bf3(const Cfg<float> cfg, const bf16* __restrict__ hi, const bf16* __restrict__ lo, int64_t ld,
+                                                  const float* __restrict__ Wref, int act, int64_t rows, int K, int n_out,
+                                                  float* __restrict__ mu, const float* __restrict__ mubar, int64_t site0, int m,
+                                                  int M_units, int64_t nb, float* __restrict__ dlast) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float acc[MAXP];
+#pragma unroll
+  for (int k = 0; k < MAXP; k++) acc[k] = 0.f;
+  for (int i0 = lane * 8; i0 < K; i0 += 256) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + r * ld + i0)), b = __ldg(reinterpret_cast<const uint4*>(lo + r * ld + i0));
+    const float x[8] = {bf_lo(a.x) + bf_lo(b.x), bf_hi(a.x) + bf_hi(b.x), bf_lo(a.y) + bf_lo(b.y), bf_hi(a.y) + bf_hi(b.y),
+                        bf_lo(a.z) + bf_lo(b.z), bf_hi(a.z) + bf_hi(b.z), bf_lo(a.w) + bf_lo(b.w), bf_hi(a.w) + bf_hi(b.w)};
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+      for (int k = 0; k < n_out; k++) acc[k] = fmaf(x[c], __ldg(Wref + (size_t)(i0 + c) * n_out + k), acc[k]);
+  }
+  const int64_t site = site0 + r;
+  for (int k = 0; k < n_out; k++) {
+    float s = acc[k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane != 0) continue;
+    const float p = act_apply<float>(act, s);
+    if (BWD == 0) {
+      if (k < cfg.nM) {
+        const float v = (cfg.scale_kind == HVI_SCALE_RANGE) ? p * cfg.scale_b[k] + cfg.scale_a[k]
+                                                           : cfg.scale_a[k] + cfg.scale_b[k] * (float)normcdfinv((double)p);
+        if (M_units > 0) mu[((size_t)m * cfg.nM + k) * nb + site] = v;
+        else mu[site * cfg.nM + k] = v;
+      }
+    } else {
+      float d = 0.f;
+      if (k < cfg.nM) {
+        const float mb = M_units > 0 ? mubar[((size_t)m * cfg.nM + k) * nb + site] : mubar[site * cfg.nM + k];
+        if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb * cfg.scale_b[k];
+        else { const float qn = (float)normcdfinv((double)p); d = mb * cfg.scale_b[k] * 2.50662827463100050242f * expf(0.5f * qn * qn); }
+        d *= (act == HVI_ACT_LOGISTIC) ? p * (1.f - p) : (act == HVI_ACT_TANH) ? 1.f - p * p : 1.f;
+      }
+      dlast[r * 8 + k] = d;
+    }
+  }
+  if (BWD == 1 && lane == 0) for (int k = n_out; k < 8; k++) dlast[r * 8 + k] = 0.f;
+}
+
+// δ_{L-1}[r][i] = (Σ_k W_L[i][k] δ_L[r][k]) · act'(H_{L-1}[r][i]); lane ↔ row, 64 features per warp
+__global__ void __launch_bounds__(256) k_thin_bwd_bf3(const float* __restrict__ dlast, const float* __restrict__ Wref, int n_out,
+                                                      const bf16* __restrict__ h_hi, const bf16* __restrict__ h_lo, int64_t ldh,
+                                                      int act_prev, int64_t rows, Planes o) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
+  const bool ok = row < rows;
+  float dl[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) dl[k] = ok ? dlast[row * 8 + k] : 0.f;
+#pragma unroll 1
+  for (int cb = blockIdx.y * 64; cb < blockIdx.y * 64 + 64; cb += 32) {
+    float h[32], z[32];
+    if (ok) load_planes32(h_hi, h_lo, ldh, row, cb, h);
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (k < n_out) s = fmaf(__ldg(Wref + (size_t)(cb + j) * n_out + k), dl[k], s);
+      z[j] = ok ? s * act_deriv_f(act_prev, h[j]) : 0.f;
+    }
+    store_planes32(o, row, cb, z, ok);
+  }
+}
+
+// G[s][b] = Σ_r S[r·ls + s]·B[r][b] over this block's row slice, B from normal planes; one thread per b
+__global__ void __launch_bounds__(256) k_skinny_bf3(const float* __restrict__ S, int ls, int ns, const bf16* __restrict__ b_hi,
+                                                    const bf16* __restrict__ b_lo, int64_t lb, int nbig, int64_t rows,
+                                                    float* __restrict__ part) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * SKINNY_ROWS;
+  const int64_t r1 = r0 + SKINNY_ROWS < rows ? r0 + SKINNY_ROWS : rows;
+  if (b >= nbig) return;
+  float acc[8];
+  for (int s = 0; s < 8; s++) acc[s] = 0.f;
+  int64_t r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    float y[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) y[u] = __bfloat162float(b_hi[(r + u) * lb + b]) + __bfloat162float(b_lo[(r + u) * lb + b]);
+    for (int s = 0; s < ns; s++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) acc[s] = fmaf(S[(r + u) * ls + s], y[u], acc[s]);
+    }
+  }
+  for (; r < r1; r++) {
+    const float y = __bfloat162float(b_hi[r * lb + b]) + __bfloat162float(b_lo[r * lb + b]);
+    for (int s = 0; s < ns; s++) acc[s] = fmaf(S[r * ls + s], y, acc[s]);
+  }
+  for (int s = 0; s < ns; s++) part[((size_t)blockIdx.y * ns + s) * nbig + b] = acc[s];
+}
+
+// ---- eligibility and work space ---------------------------------------------------------------
+bool bf3_eligible(const Cfg<float>& cfg) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("HVI_WIDE_IMPL"); off = (e && strcmp(e, "tf32") == 0) ? 1 : 0; }
+  if (off || !tma_encoder()) return false;
+  if (cfg.nL < 3 || cfg.l_bias[cfg.nL - 1] || cfg.l_out[cfg.nL - 1] > 8 || cfg.nC + cfg.npc + 1 > 8) return false;
+  for (int l = 0; l < cfg.nL - 1; l++)
+    if (cfg.l_out[l] % 128 != 0) return false;
+  return true;
+}
+
+struct Bf3Work {
+  Planes H[8];          // outputs of layers 0 … nL-2
+  Planes D[2];          // cotangent ping-pong
+  bf16 *wn_hi, *wn_lo, *wt_hi, *wt_lo;   // weight planes, indexed like ϕg
+  float* extra_h;       // pbm covariate values of the current draw
+  float* Xs;            // [chunk][XS_LD]
+  float* dlast;         // [chunk][8]
+  float* P;             // weight-gradient partial tiles / skinny partials
+  double* db0;
+};
+// carve the work space of launch_mlp_bwd_wide (wide_bwd_work_bytes) / launch_mlp_fwd_wide (wide_work_elems·4)
+static void carve(Bf3Work& w, void* work, int nL, int maxw, int nphig, bool bwd) {
+  const size_t cw = (size_t)WIDE_CHUNK * maxw;
+  bf16* p = reinterpret_cast<bf16*>(work);
+  auto planes = [&](Planes& pl, bool trans) {
+    pl.hi = p; p += cw; pl.lo = p; p += cw; pl.ld = 0;
+    if (trans) { pl.hiT = p; p += cw; pl.loT = p; p += cw; } else { pl.hiT = pl.loT = nullptr; }
+    pl.ldT = WIDE_CHUNK;
+  };
+  if (bwd) {
+    for (int l = 0; l < nL - 1; l++) planes(w.H[l], true);
+    planes(w.D[0], true); planes(w.D[1], true);
+  } else {
+    planes(w.H[0], false); planes(w.H[1], false);
+  }
+  w.wn_hi = p; p += nphig; w.wn_lo = p; p += nphig; w.wt_hi = p; p += nphig; w.wt_lo = p; p += nphig;
+  p += (8 - (4 * (size_t)nphig) % 8) % 8;      // keep 16-byte alignment
+  float* f = reinterpret_cast<float*>(p);
+  w.extra_h = f; f += 16;
+  if (bwd) {
+    w.Xs = f; f += (size_t)WIDE_CHUNK * XS_LD;
+    w.dlast = f; f += (size_t)WIDE_CHUNK * 8;
+    w.P = f;
+    const size_t pf = (size_t)24 * maxw * maxw, sk = (size_t)(WIDE_CHUNK / SKINNY_ROWS) * 8 * maxw;
+    f += (pf > sk ? pf : sk);
+    f += ((uintptr_t)f % 8) ? 1 : 0;
+    w.db0 = reinterpret_cast<double*>(f);
+  }
+}
+size_t bf3_fwd_work_bytes(int maxw, int nphig) { return (size_t)WIDE_CHUNK * maxw * 8 + (size_t)nphig * 8 + 256; }
+size_t bf3_bwd_work_bytes(int nL, int maxw, int nphig) {
+  const size_t cw = (size_t)WIDE_CHUNK * maxw;
+  const size_t pf = (size_t)24 * maxw * maxw, sk = (size_t)(WIDE_CHUNK / SKINNY_ROWS) * 8 * maxw;
+  return (size_t)(nL + 1) * cw * 8 + (size_t)nphig * 8 + 4 * ((size_t)WIDE_CHUNK * (XS_LD + 8) + (pf > sk ? pf : sk)) + 8 * (size_t)maxw + 1024;
+}
+
+static cudaError_t split_weights(const Launch& L, const Cfg<float>& cfg, const float* phi, Bf3Work& w) {
+  for (int l = 1; l < cfg.nL - 1; l++) {
+    const int n = cfg.l_in[l] * cfg.l_out[l];
+    const int o = cfg.woff[l];
+    k_split_w<<<(n + 255) / 256, 256, 0, L.stream>>>(phi + o, cfg.l_in[l], cfg.l_out[l], w.wn_hi + o, w.wn_lo + o, w.wt_hi + o, w.wt_lo + o);
+    if (L.counter) ++*L.counter;
+  }
+  return cudaGetLastError();
+}
+static cudaError_t set_extra(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* zetaP, int M_units, int m, float* extra_h) {
+  for (int c = 0; c < cfg.npc; c++) {
+    const float* src = M_units > 0 ? zetaP + (size_t)cfg.pbm_covar_idx[c] * M_units + m : phi + cfg.o_muP + cfg.pbm_covar_idx[c];
+    cudaError_t e = cudaMemcpyAsync(extra_h + c, src, sizeof(float), cudaMemcpyDeviceToDevice, L.stream);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+// forward chain of one chunk: first layer on CUDA cores, hidden layers on the tensor cores; H[l] = output of layer l
+static cudaError_t chain_fwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t s0, int64_t rows,
+                             Bf3Work& w, Planes* outs /*nL-1 entries*/) {
+  {
+    const int N = cfg.l_out[0];
+    Planes o = outs[0]; o.ld = N;
+    k_first_bf3<<<dim3((unsigned)((rows + 255) / 256), N / 64), 256, 0, L.stream>>>(
+        xM, cfg.nC, w.extra_h, cfg.npc, s0, phi + cfg.woff[0], cfg.l_bias[0] ? phi + cfg.boff[0] : nullptr, cfg.l_act[0], rows, N, o);
+    if (L.counter) ++*L.counter;
+    outs[0].ld = N;
+  }
+  for (int l = 1; l < cfg.nL - 1; l++) {
+    const int N = cfg.l_out[l], K = cfg.l_in[l];
+    GemmEpi ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.bias = cfg.l_bias[l] ? phi + cfg.boff[l] : nullptr;
+    ep.act = cfg.l_act[l];
+    outs[l].ld = N;
+    ep.out = outs[l];
+    cudaError_t e = launch_gemm_bf3<0>(L, outs[l - 1].hi, outs[l - 1].lo, K, rows, w.wt_hi + cfg.woff[l], w.wt_lo + cfg.woff[l], K, N, K, 1, ep);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mlp_fwd_bf3(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb, float* mu,
+                               int M_units, const float* zetaP, void* work) {
+  Bf3Work w;
+  carve(w, work, cfg.nL, cfg.max_width, cfg.nphig, false);
+  cudaError_t e = split_weights(L, cfg, phi, w);
+  if (e != cudaSuccess) return e;
+  const int nm = M_units > 0 ? M_units : 1;
+  const int nL = cfg.nL;
+  for (int m = 0; m < nm; m++) {
+    e = set_extra(L, cfg, phi, zetaP, M_units, m, w.extra_h);
+    if (e != cudaSuccess) return e;
+    for (int64_t s0 = 0; s0 < nb; s0 += WIDE_CHUNK) {
+      const int64_t rows = nb - s0 < WIDE_CHUNK ? nb - s0 : WIDE_CHUNK;
+      Planes outs[8];
+      for (int l = 0; l < nL - 1; l++) outs[l] = w.H[l & 1];      // ping-pong
+      e = chain_fwd(L, cfg, phi, xM, s0, rows, w, outs);
+      if (e != cudaSuccess) return e;
+      const int l = nL - 1;
+      k_last_bf3<0><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, L.stream>>>(cfg, outs[l - 1].hi, outs[l - 1].lo, cfg.l_in[l],
+                                                                            phi + cfg.woff[l], cfg.l_act[l], rows, cfg.l_in[l],
+                                                                            cfg.l_out[l], mu, nullptr, s0, m, M_units, nb, nullptr);
+      if (L.counter) ++*L.counter;
+    }
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb, const float* mubar,
+                               int M_units, const float* zetaP, void* work, double* grad_acc, double* xacc) {
+  Bf3Work w;
+  const int nL = cfg.nL;
+  carve(w, work, nL, cfg.max_width, cfg.nphig, true);
+  auto count = [&]() { if (L.counter) ++*L.counter; };
+  cudaError_t e = split_weights(L, cfg, phi, w);
+  if (e != cudaSuccess) return e;
+  const int sms = L.sm_count > 0 ? L.sm_count : 148;
+  const int nm = M_units > 0 ? M_units : 1;
+  for (int m = 0; m < nm; m++) {
+    e = set_extra(L, cfg, phi, zetaP, M_units, m, w.extra_h);
+    if (e != cudaSuccess) return e;
+    for (int64_t s0 = 0; s0 < nb; s0 += WIDE_CHUNK) {
+      const int64_t rows = nb - s0 < WIDE_CHUNK ? nb - s0 : WIDE_CHUNK;
+      const int nslice = (int)((rows + SKINNY_ROWS - 1) / SKINNY_ROWS);
+      // ---- forward, keeping all activations (transposed planes where a weight gradient reads them)
+      k_build_xs<float><<<(unsigned)((rows + 255) / 256), 256, 0, L.stream>>>(xM, cfg.nC, w.extra_h, cfg.npc, s0, rows, w.Xs);
+      count();
+      Planes H[8];
+      for (int l = 0; l < nL - 1; l++) { H[l] = w.H[l]; if (l == nL - 2) H[l].hiT = H[l].loT = nullptr; }
+      e = chain_fwd(L, cfg, phi, xM, s0, rows, w, H);
+      if (e != cudaSuccess) return e;
+      // ---- last layer: δ_L, ∇W_L, δ_{L-1}
+      Planes Dcur = w.D[0], Dnxt = w.D[1];
+      {
+        const int l = nL - 1, K = cfg.l_in[l], no = cfg.l_out[l];
+        k_last_bf3<1><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, L.stream>>>(cfg, H[l - 1].hi, H[l - 1].lo, K, phi + cfg.woff[l],
+                                                                              cfg.l_act[l], rows, K, no, nullptr, mubar, s0, m,
+                                                                              M_units, nb, w.dlast);
+        count();
+        Dcur.ld = K;
+        Planes o = Dcur;
+        if (nL - 2 < 1) o.hiT = o.loT = nullptr;
+        k_thin_bwd_bf3<<<dim3((unsigned)((rows + 255) / 256), K / 64), 256, 0, L.stream>>>(w.dlast, phi + cfg.woff[l], no, H[l - 1].hi,
+                                                                                        H[l - 1].lo, K, cfg.l_act[l - 1], rows, o);
+        count();
+        k_skinny_bf3<<<dim3((K + 255) / 256, nslice), 256, 0, L.stream>>>(w.dlast, 8, no, H[l - 1].hi, H[l - 1].lo, K, K, rows, w.P);
+        count();
+        k_accum<float><<<(no * K + 255) / 256, 256, 0, L.stream>>>(w.P, nslice, (size_t)no * K, no, K, grad_acc, cfg.woff[l], 1, no, nullptr);
+        count();
+      }
+      // ---- hidden layers l = nL-2 … 1: bias, weight gradient, δ of the layer below
+      for (int l = nL - 2; l >= 1; l--) {
+        const int N = cfg.l_out[l], K = cfg.l_in[l];   // Dcur: [rows][N]
+        if (cfg.l_bias[l]) {
+          k_skinny_bf3<<<dim3((N + 255) / 256, nslice), 256, 0, L.stream>>>(w.Xs + cfg.nC + cfg.npc, XS_LD, 1, Dcur.hi, Dcur.lo, N, N, rows, w.P);
+          count();
+          k_accum<float><<<(N + 255) / 256, 256, 0, L.stream>>>(w.P, nslice, (size_t)N, 1, N, grad_acc, cfg.boff[l], 0, 1, nullptr);
+          count();
+        }
+        {  // ∇W_l[in][out] = H_{l-1}ᵀ δ_l: both operands from the transposed planes, contraction over the rows
+          GemmEpi ep;
+          memset(&ep, 0, sizeof(ep));
+          ep.P = w.P;
+          const int ns = bf3_wgrad_splits(K, N, sms);
+          e = launch_gemm_bf3<2>(L, H[l - 1].hiT, H[l - 1].loT, WIDE_CHUNK, K, Dcur.hiT, Dcur.loT, WIDE_CHUNK, N, rows, ns, ep);
+          if (e != cudaSuccess) return e;
+          int64_t per = (rows + ns - 1) / ns;
+          per = (per + G_BK - 1) / G_BK * G_BK;
+          const int ns_eff = (int)((rows + per - 1) / per);
+          k_accum<float><<<(K * N + 255) / 256, 256, 0, L.stream>>>(w.P, ns_eff, (size_t)K * N, 1, K * N, grad_acc, cfg.woff[l], 0, 1, nullptr);
+          count();
+        }
+        {  // δ_{l-1} = (δ_l W_l) ⊙ act'(H_{l-1}): A = δ_l [rows x N], B = W_l in its own [in][out] layout
+          GemmEpi ep;
+          memset(&ep, 0, sizeof(ep));
+          ep.act = cfg.l_act[l - 1];
+          ep.h_hi = H[l - 1].hi; ep.h_lo = H[l - 1].lo; ep.ldh = K;
+          Dnxt.ld = K;
+          ep.out = Dnxt;
+          if (l == 1) ep.out.hiT = ep.out.loT = nullptr;   // δ_0 feeds only the first layer's skinny reduction
+          e = launch_gemm_bf3<1>(L, Dcur.hi, Dcur.lo, N, rows, w.wn_hi + cfg.woff[l], w.wn_lo + cfg.woff[l], N, K, N, 1, ep);
+          if (e != cudaSuccess) return e;
+        }
+        Planes tmp = Dcur; Dcur = Dnxt; Dnxt = tmp;
+      }
+      // ---- first layer: ∇b_0, ∇W_0 = [x; covariates]ᵀ δ_0, and the cotangent of the covariate inputs
+      {
+        const int N = cfg.l_out[0], K = cfg.l_in[0];
+        const int ns = K + 1;
+        k_skinny_bf3<<<dim3((N + 255) / 256, nslice), 256, 0, L.stream>>>(w.Xs, XS_LD, ns, Dcur.hi, Dcur.lo, N, N, rows, w.P);
+        count();
+        const size_t sst = (size_t)ns * N;
+        double* acc_b = cfg.l_bias[0] ? grad_acc : nullptr;
+        k_accum<float><<<(K * N + 255) / 256, 256, 0, L.stream>>>(w.P, nslice, sst, K, N, grad_acc, cfg.woff[0], N, 1, nullptr);
+        k_accum<float><<<(N + 255) / 256, 256, 0, L.stream>>>(w.P + (size_t)K * N, nslice, sst, 1, N, acc_b, cfg.boff[0], 0, 1, w.db0);
+        count(); count();
+        if (cfg.npc > 0 && xacc) {
+          k_xbar<float><<<1, 32, 0, L.stream>>>(phi + cfg.woff[0], cfg.nC, cfg.npc, N, w.db0, xacc + (size_t)(M_units > 0 ? m : 0) * cfg.npc);
+          count();
+        }
+      }
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
+  }
+  return cudaSuccess;
+}
+
+// ---- test harness: one GEMM on device fp32 arrays (split → GEMM → join) ----------------------
+// mode 0: C = act(A·Bᵀ + bias); mode 1: C = (A·Bᵀ) ⊙ act'(Hd); mode 2: C = A·Bᵀ through the split-K path.
+// A [M][K], B [N][K], C [M][N], Ct [N][M] (nullable; transposed planes of the result, modes 0/1)
+cudaError_t gemm_bf3_device(cudaStream_t stream, int sm_count, int mode, int64_t M, int N, int64_t K, const float* A, const float* B,
+                            const float* bias, int act, const float* Hd, float* C, float* Ct) {
+  if (K % 32 != 0 || N % 128 != 0 || !tma_encoder()) return cudaErrorInvalidValue;
+  Launch L{stream, sm_count, nullptr};
+  const int64_t Mp = (M + 31) / 32 * 32;      // transposed leading dimension
+  bf16* buf = nullptr;
+  const size_t nA = (size_t)M * K, nB = (size_t)N * K, nC = (size_t)N * Mp;
+  const int ns = mode == 2 ? bf3_wgrad_splits((int)M, N, sm_count) : 1;
+  cudaError_t e = cudaMalloc((void**)&buf, 2 * (2 * nA + 2 * nB + 4 * nC + 2 * nC) + sizeof(float) * (size_t)ns * M * N + 64);
+  if (e != cudaSuccess) return e;
+  Planes pa{buf, buf + nA, K, nullptr, nullptr, 0};
+  Planes pb{buf + 2 * nA, buf + 2 * nA + nB, K, nullptr, nullptr, 0};
+  bf16* q = buf + 2 * nA + 2 * nB;
+  Planes pc{q, q + nC, N, Ct ? q + 2 * nC : nullptr, Ct ? q + 3 * nC : nullptr, Mp};
+  Planes ph{q + 4 * nC, q + 5 * nC, N, nullptr, nullptr, 0};
+  float* P = reinterpret_cast<float*>(q + 6 * nC);
+  k_split_planes<<<dim3((unsigned)((M + 255) / 256), (unsigned)(K / 32)), 256, 0, stream>>>(A, M, (int)K, pa);
+  k_split_planes<<<dim3((unsigned)((N + 255) / 256), (unsigned)(K / 32)), 256, 0, stream>>>(B, N, (int)K, pb);
+  GemmEpi ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = bias; ep.act = act; ep.out = pc; ep.P = P;
+  if (mode == 1) {
+    k_split_planes<<<dim3((unsigned)((M + 255) / 256), (unsigned)(N / 32)), 256, 0, stream>>>(Hd, M, N, ph);
+    ep.h_hi = ph.hi; ep.h_lo = ph.lo; ep.ldh = N;
+  }
+  if (mode == 0) e = launch_gemm_bf3<0>(L, pa.hi, pa.lo, K, M, pb.hi, pb.lo, K, N, K, 1, ep);
+  else if (mode == 1) e = launch_gemm_bf3<1>(L, pa.hi, pa.lo, K, M, pb.hi, pb.lo, K, N, K, 1, ep);
+  else e = launch_gemm_bf3<2>(L, pa.hi, pa.lo, K, M, pb.hi, pb.lo, K, N, K, ns, ep);
+  if (e == cudaSuccess) {
+    const int64_t n = M * N;
+    if (mode == 2) {
+      int64_t per = (K + ns - 1) / ns;
+      per = (per + G_BK - 1) / G_BK * G_BK;
+      const int ns_eff = (int)((K + per - 1) / per);
+      double* acc = nullptr;
+      e = cudaMalloc((void**)&acc, sizeof(double) * n);
+      if (e == cudaSuccess) {
+        cudaMemsetAsync(acc, 0, sizeof(double) * n, stream);
+        k_accum<float><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(P, ns_eff, (size_t)n, 1, (int)n, acc, 0, 0, 1, nullptr);
+        double* hacc = (double*)malloc(sizeof(double) * n);
+        e = cudaMemcpyAsync(hacc, acc, sizeof(double) * n, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        float* hc = (float*)malloc(sizeof(float) * n);
+        for (int64_t i = 0; i < n; i++) hc[i] = (float)hacc[i];
+        if (e == cudaSuccess) e = cudaMemcpy(C, hc, sizeof(float) * n, cudaMemcpyHostToDevice);
+        free(hacc); free(hc);
+        cudaFree(acc);
+      }
+    } else {
+      k_join_planes<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pc, M, N, 0, C);
+      if (Ct) {
+        // Ct [N][M]: element (c, r) = transposed planes at c·ldT + r  ⇒ join with rows ↔ features swapped
+        Planes pt{pc.hiT, pc.loT, Mp, nullptr, nullptr, 0};
+        k_join_planes<<<(unsigned)(((int64_t)N * Mp + 255) / 256), 256, 0, stream>>>(pt, N, (int)Mp, 0, Ct);
+      }
+      e = cudaGetLastError();
+    }
+  }
+  cudaError_t e2 = cudaStreamSynchronize(stream);
+  cudaFree(buf);
+  return e != cudaSuccess ? e : e2;
+}
+
+}  // namespace hvi

@@ -128,6 +128,16 @@ cudaError_t launch_mlp_bwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi
                                 int M_units, const T* zetaP, void* work, double* grad_acc /*[nphig], zeroed*/,
                                 double* xacc /*[max(M_units,1)*npc], zeroed*/);
 size_t wide_bwd_work_bytes(int nL, int max_width, int nphig);
+// TMA-fed 3xBF16 chain of the wide applicator (hvi_dense_tma.cu), Float32 and hidden widths % 128 == 0
+bool bf3_eligible(const Cfg<float>& cfg);
+size_t bf3_fwd_work_bytes(int maxw, int nphig);
+size_t bf3_bwd_work_bytes(int nL, int maxw, int nphig);
+cudaError_t launch_mlp_fwd_bf3(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb, float* mu,
+                               int M_units, const float* zetaP, void* work);
+cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb, const float* mubar,
+                               int M_units, const float* zetaP, void* work, double* grad_acc, double* xacc);
+cudaError_t gemm_bf3_device(cudaStream_t stream, int sm_count, int mode, int64_t M, int N, int64_t K, const float* A, const float* B,
+                            const float* bias, int act, const float* Hd, float* C, float* Ct);
 int stream_max_rows(int sm_count);
 int mlp_bwd_max_blocks(int sm_count);
 bool stream_supported(int nP, int nM, int nO);
