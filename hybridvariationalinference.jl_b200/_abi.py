@@ -79,7 +79,7 @@ SYMBOLS = [
     ("hvi_apply_g", _INT, [_P, _P, _INT, _P]),
     ("hvi_randn", _INT, [_P, _I32, _I64, _U64, _I64, _INT, _P]),
     ("hvi_dense_tc", _INT, [_I32, _I64, _I32, _I32, _P, _P, _P, _I32, _P]),
-    ("hvi_gemm_bf3", _INT, [_I32, _I32, _I64, _I32, _I64, _P, _P, _P, _I32, _P, _P, _P]),
+    ("hvi_gemm_bf3", _INT, [_I32, _I32, _I64, _I32, _I64, _P, _P, _P, _I32, _P, _P]),
     ("hvi_launch_count", _I64, [_P]),
     ("hvi_plan_set_profiling", _INT, [_P, _INT]),
     ("hvi_plan_kernel_times", _INT, [_P, C.POINTER(C.c_float)]),

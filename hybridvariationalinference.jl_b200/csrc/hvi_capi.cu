@@ -873,12 +873,13 @@ extern "C" int hvi_dense_tc(int32_t device, int64_t Mc, int32_t N, int32_t K, co
 }
 
 // One GEMM of the TMA-fed 3xBF16 chain (hvi_dense_tma.cu) on host arrays; exported for its parity test.
-//   mode 0: C = act(A·Bᵀ + bias);  mode 1: C = (A·Bᵀ) ⊙ act'(Hd);  mode 2: C = A·Bᵀ through the split-K path
-// A (M x K), B (N x K), Hd / C (M x N) row-major; Ct (N x M, nullable): the transposed planes of the result.
+//   mode 0: C = act(A·Bᵀ + bias), A (M x K), B (N x K);  mode 1: C = (A·Bᵀ) ⊙ act'(Hd);
+//   mode 2: C = AᵀB through the split-K, MN-major path, A (K x M), B (K x N).  Hd / C (M x N), all row-major.
 extern "C" int hvi_gemm_bf3(int32_t device, int32_t mode, int64_t M, int32_t N, int64_t K, const float* A, const float* B,
-                            const float* bias, int32_t act, const float* Hd, float* C, float* Ct) {
-  if (!A || !B || !C || M < 1 || N < 1 || K < 1 || K % 32 != 0 || N % 128 != 0 || mode < 0 || mode > 2 || (mode == 1 && !Hd)) {
-    g_create_err = "hvi_gemm_bf3: bad arguments (K % 32 == 0, N % 128 == 0)";
+                            const float* bias, int32_t act, const float* Hd, float* C) {
+  if (!A || !B || !C || M < 1 || N < 1 || K < 1 || N % 128 != 0 || mode < 0 || mode > 2 || (mode == 1 && !Hd) ||
+      (mode == 2 ? M % 32 != 0 : K % 32 != 0)) {
+    g_create_err = "hvi_gemm_bf3: bad arguments (N % 128 == 0; K % 32 == 0, or M % 32 == 0 in mode 2)";
     return HVI_EINVAL;
   }
   int ndev = 0;
@@ -886,25 +887,20 @@ extern "C" int hvi_gemm_bf3(int32_t device, int32_t mode, int64_t M, int32_t N, 
   cudaSetDevice(device);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
-  const int64_t Mp = (M + 31) / 32 * 32;
-  float *dA = nullptr, *dB = nullptr, *db = nullptr, *dH = nullptr, *dC = nullptr, *dCt = nullptr;
+  float *dA = nullptr, *dB = nullptr, *db = nullptr, *dH = nullptr, *dC = nullptr;
   cudaError_t e = cudaMalloc((void**)&dA, sizeof(float) * (size_t)M * K);
   if (e == cudaSuccess) e = cudaMalloc((void**)&dB, sizeof(float) * (size_t)N * K);
   if (e == cudaSuccess) e = cudaMalloc((void**)&dC, sizeof(float) * (size_t)M * N);
   if (e == cudaSuccess && bias) e = cudaMalloc((void**)&db, sizeof(float) * (size_t)N);
   if (e == cudaSuccess && Hd) e = cudaMalloc((void**)&dH, sizeof(float) * (size_t)M * N);
-  if (e == cudaSuccess && Ct) e = cudaMalloc((void**)&dCt, sizeof(float) * (size_t)N * Mp);
   if (e == cudaSuccess) e = cudaMemcpy(dA, A, sizeof(float) * (size_t)M * K, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dB, B, sizeof(float) * (size_t)N * K, cudaMemcpyHostToDevice);
   if (e == cudaSuccess && bias) e = cudaMemcpy(db, bias, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice);
   if (e == cudaSuccess && Hd) e = cudaMemcpy(dH, Hd, sizeof(float) * (size_t)M * N, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && dCt) e = cudaMemset(dCt, 0, sizeof(float) * (size_t)N * Mp);
-  if (e == cudaSuccess) e = gemm_bf3_device(nullptr, prop.multiProcessorCount, mode, M, N, K, dA, dB, db, act, dH, dC, dCt);
+  if (e == cudaSuccess) e = gemm_bf3_device(nullptr, prop.multiProcessorCount, mode, M, N, K, dA, dB, db, act, dH, dC);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(C, dC, sizeof(float) * (size_t)M * N, cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && Ct)
-    e = cudaMemcpy2D(Ct, sizeof(float) * (size_t)M, dCt, sizeof(float) * (size_t)Mp, sizeof(float) * (size_t)M, (size_t)N, cudaMemcpyDeviceToHost);
-  for (float* q : {dA, dB, db, dH, dC, dCt}) if (q) cudaFree(q);
+  for (float* q : {dA, dB, db, dH, dC}) if (q) cudaFree(q);
   if (e != cudaSuccess) { g_create_err = std::string("hvi_gemm_bf3: ") + cudaGetErrorString(e); return HVI_ECUDA; }
   return HVI_OK;
 }

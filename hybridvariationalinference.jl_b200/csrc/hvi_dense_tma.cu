@@ -2,20 +2,22 @@
 // warp-specialised, persistent tcgen05 GEMMs with error-compensated bf16 operands ("3xBF16").
 //
 // Data layout in HBM.  Every activation H_l and every cotangent δ_l of a chunk of columns is kept as
-// two bf16 planes, hi = bf16(x) and lo = bf16(x − hi) (16 mantissa bits together, the footprint of one
-// fp32 array), in two orientations: [row][feature] (K-major operand of the layer / data-gradient
-// GEMMs) and [feature][row] (K-major operand of the weight-gradient GEMM, whose contraction runs over
-// the rows).  The epilogue that produces a tensor writes all planes it will be read in, so no GEMM
-// converts, splits or transposes anything on its way into shared memory: TMA (cp.async.bulk.tensor,
-// SWIZZLE_128B) drops the tiles where tcgen05.mma reads them.
+// two bf16 planes [row][feature], hi = bf16(x) and lo = bf16(x − hi) (16 mantissa bits together, the
+// footprint of one fp32 array).  The epilogue that produces a tensor writes the planes, so no GEMM
+// converts or splits anything on its way into shared memory: TMA (cp.async.bulk.tensor, SWIZZLE_128B)
+// drops the tiles where tcgen05.mma reads them.  The layer and data-gradient GEMMs contract over the
+// features (operands K-major); the weight-gradient GEMM contracts over the rows and reads the SAME
+// planes as MN-major operands (64-feature x 8-row swizzle atoms, a_major = b_major = 1 in the
+// instruction descriptor), so nothing is ever transposed in memory.
 //
 // Kernel k_gemm_bf3<BN, MODE>:  D[M x N] = Σ_k A[m][k]·B[n][k]  with A ≈ A_hi + A_lo, B ≈ B_hi + B_lo and
 // three MMAs per K step (hi·hi + hi·lo + lo·hi) into one fp32 TMEM accumulator.
-//   warp 0 (one lane)  TMA producer: 4 tiles per stage (A hi/lo 128 x 64, B hi/lo BN x 64) → full barrier
+//   warp 0 (one lane)  TMA producer: A hi/lo (128 x 64) and B hi/lo (BN x 64) per stage → full barrier
 //   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN, K = 16;
 //                      tcgen05.commit frees the stage (empty barrier) and publishes the accumulator
-//   warps 2-5          epilogue: tcgen05.ld of one of the TWO accumulators (2·BN TMEM columns) while the
-//                      MMA warp fills the other one for the CTA's next tile (persistent, static schedule)
+//   warps 2-9          epilogue: tcgen05.ld of one of the TWO accumulators (2·BN TMEM columns) while the
+//                      MMA warp fills the other one for the CTA's next tile (persistent, static schedule);
+//                      two warps per TMEM lane quarter, each half of the columns
 //   MODE 0  H = act(D + bias)                          layer forward
 //   MODE 1  δ_{l-1} = D ⊙ act'(H_{l-1})                data gradient (D = δ_l W_l)
 //   MODE 2  P[split] = D over this split's K range     weight gradient, split over the rows
@@ -39,7 +41,8 @@ typedef __nv_bfloat16 bf16;
 
 constexpr int G_BM = 128;            // rows per tile = TMEM lanes
 constexpr int G_BK = 64;             // K per stage: 64 bf16 = one 128-byte swizzle row
-constexpr int G_THREADS = 192;       // TMA warp, MMA warp, 4 epilogue warps
+constexpr int G_EPI_WARPS = 8;
+constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;   // TMA warp, MMA warp, epilogue warps
 
 template <int BN>
 struct GemmTile {
@@ -48,21 +51,29 @@ struct GemmTile {
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);      // hi + lo of both
   static constexpr int STAGES = BN == 256 ? 2 : 3;                 // 192 KB of shared memory either way
   static constexpr int TMEM_COLS = 2 * BN;                         // two accumulators
+  // D = F32 [4,6) = 1, A = B = BF16 [7,10) = [10,13) = 1, a_major [15], b_major [16] (1 = MN-major), N >> 3 [17,23), M >> 4 [24,29)
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
+  static constexpr uint32_t IDESC_MN = IDESC | (1u << 15) | (1u << 16);
 };
+constexpr int G_MN_BOX = 64 * 128;   // bytes of one MN-major TMA box: 64 rows (K) x 64 features
 
-// planes of one tensor: normal [rows][ld] and (optional) transposed [feature][ldT]
+// MN-major SWIZZLE_128B descriptor: atoms of 64 features (128 B) x 8 rows; LBO = distance between 64-feature
+// chunks (one TMA box), SBO = distance between 8-row groups (1024 B)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(G_MN_BOX >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+// the two planes of one tensor, [rows][ld]
 struct Planes {
   bf16 *hi, *lo;
   int64_t ld;
-  bf16 *hiT, *loT;
-  int64_t ldT;
 };
 
 struct GemmShape {
-  int64_t M;             // rows of A (and of D)
-  int N;                 // rows of B = columns of D
-  int64_t K;             // contraction length
+  int64_t M;             // rows of D (MODE 0/1: rows of A; MODE 2: features of A)
+  int N;                 // columns of D (MODE 0/1: rows of B; MODE 2: features of B)
+  int64_t K;             // contraction length (MODE 2: the rows of both operands)
   int nsplit;            // MODE 2: K is cut into nsplit ranges of k_per_split
   int64_t k_per_split;
 };
@@ -131,9 +142,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-// 32 consecutive features of one row (this lane's), fp32 → hi/lo planes in both orientations.
-// Normal planes: 64 contiguous bytes per lane and plane; transposed planes: the 32 lanes of the warp are
-// 32 consecutive rows, so every 2-byte store of the warp lands in one 64-byte segment.
+// 32 consecutive features of one row (this lane's), fp32 → hi/lo planes: 64 contiguous bytes per lane and plane
 __device__ __forceinline__ void store_planes32(const Planes& o, int64_t row, int col0, const float (&x)[32], bool ok) {
   uint32_t h[16], l[16];
 #pragma unroll
@@ -151,17 +160,14 @@ __device__ __forceinline__ void store_planes32(const Planes& o, int64_t row, int
     ph[q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
     pl[q] = make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
   }
-  if (o.hiT) {
-    unsigned short* th = reinterpret_cast<unsigned short*>(o.hiT) + (int64_t)col0 * o.ldT + row;
-    unsigned short* tl = reinterpret_cast<unsigned short*>(o.loT) + (int64_t)col0 * o.ldT + row;
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-      th[(int64_t)(2 * j) * o.ldT] = (unsigned short)(h[j] & 0xFFFFu);
-      th[(int64_t)(2 * j + 1) * o.ldT] = (unsigned short)(h[j] >> 16);
-      tl[(int64_t)(2 * j) * o.ldT] = (unsigned short)(l[j] & 0xFFFFu);
-      tl[(int64_t)(2 * j + 1) * o.ldT] = (unsigned short)(l[j] >> 16);
-    }
-  }
+}
+// tanh to ~2e-7 absolute with two MUFU ops: 1 − 2/(1 + e^{2x})
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
 }
 // 32 consecutive features of one row from the normal planes, recombined to fp32
 __device__ __forceinline__ void load_planes32(const bf16* hi, const bf16* lo, int64_t ld, int64_t row, int col0, float (&x)[32]) {
@@ -197,7 +203,7 @@ k_gemm_bf3(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CU
 
   if (t == 0) {
     for (int s = 0; s < S; s++) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
+    for (int a = 0; a < 2; a++) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], G_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -225,10 +231,23 @@ k_gemm_bf3(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CU
           mbar_expect_tx(&bar_full[s], TL::STAGE_BYTES);
           const uint32_t base = smem_u32(tiles + (size_t)s * TL::STAGE_BYTES);
           const int kc = (int)(k0 + (int64_t)kb * G_BK);
-          tma_load_2d(base, &mA_hi, kc, m0, &bar_full[s]);
-          tma_load_2d(base + TL::A_BYTES, &mA_lo, kc, m0, &bar_full[s]);
-          tma_load_2d(base + 2 * TL::A_BYTES, &mB_hi, kc, n0, &bar_full[s]);
-          tma_load_2d(base + 2 * TL::A_BYTES + TL::B_BYTES, &mB_lo, kc, n0, &bar_full[s]);
+          if (MODE != 2) {      // K-major: one box per plane, [tile rows][64 K values]
+            tma_load_2d(base, &mA_hi, kc, m0, &bar_full[s]);
+            tma_load_2d(base + TL::A_BYTES, &mA_lo, kc, m0, &bar_full[s]);
+            tma_load_2d(base + 2 * TL::A_BYTES, &mB_hi, kc, n0, &bar_full[s]);
+            tma_load_2d(base + 2 * TL::A_BYTES + TL::B_BYTES, &mB_lo, kc, n0, &bar_full[s]);
+          } else {              // MN-major: boxes of [64 rows (K)][64 features], one per 64 features of the tile
+#pragma unroll
+            for (int b = 0; b < G_BM / 64; b++) {
+              tma_load_2d(base + b * G_MN_BOX, &mA_hi, m0 + 64 * b, kc, &bar_full[s]);
+              tma_load_2d(base + TL::A_BYTES + b * G_MN_BOX, &mA_lo, m0 + 64 * b, kc, &bar_full[s]);
+            }
+#pragma unroll
+            for (int b = 0; b < BN / 64; b++) {
+              tma_load_2d(base + 2 * TL::A_BYTES + b * G_MN_BOX, &mB_hi, n0 + 64 * b, kc, &bar_full[s]);
+              tma_load_2d(base + 2 * TL::A_BYTES + TL::B_BYTES + b * G_MN_BOX, &mB_lo, n0 + 64 * b, kc, &bar_full[s]);
+            }
+          }
         }
       }
     }
@@ -252,11 +271,19 @@ k_gemm_bf3(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CU
           const uint32_t a_hi = smem_u32(tiles + (size_t)s * TL::STAGE_BYTES), a_lo = a_hi + TL::A_BYTES,
                          b_hi = a_hi + 2 * TL::A_BYTES, b_lo = b_hi + TL::B_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < G_BK / 16; ks++) {   // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
-            const uint32_t o = ks * 32;
-            umma_bf16(d, make_desc(a_hi + o), make_desc(b_hi + o), TL::IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
-            umma_bf16(d, make_desc(a_hi + o), make_desc(b_lo + o), TL::IDESC, 1u);
-            umma_bf16(d, make_desc(a_lo + o), make_desc(b_hi + o), TL::IDESC, 1u);
+          for (int ks = 0; ks < G_BK / 16; ks++) {
+            const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
+            if (MODE != 2) {     // UMMA_K = 16 bf16 = 32 bytes along the swizzled 128-byte row
+              const uint32_t o = ks * 32;
+              umma_bf16(d, make_desc(a_hi + o), make_desc(b_hi + o), TL::IDESC, first);
+              umma_bf16(d, make_desc(a_hi + o), make_desc(b_lo + o), TL::IDESC, 1u);
+              umma_bf16(d, make_desc(a_lo + o), make_desc(b_hi + o), TL::IDESC, 1u);
+            } else {             // 16 rows = two 8-row groups of 1024 bytes
+              const uint32_t o = ks * 2048;
+              umma_bf16(d, make_desc_mn(a_hi + o), make_desc_mn(b_hi + o), TL::IDESC_MN, first);
+              umma_bf16(d, make_desc_mn(a_hi + o), make_desc_mn(b_lo + o), TL::IDESC_MN, 1u);
+              umma_bf16(d, make_desc_mn(a_lo + o), make_desc_mn(b_hi + o), TL::IDESC_MN, 1u);
+            }
           }
           umma_commit(&bar_empty[s]);               // stage free once these MMAs have read it
         }
@@ -264,8 +291,9 @@ k_gemm_bf3(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CU
       }
     }
   } else {
-    // ===== epilogue: warp w may only touch TMEM lanes 32·(w mod 4) … =====
+    // ===== epilogue: warp w may only touch TMEM lanes 32·(w mod 4) …; two warps per quarter split the columns =====
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     uint32_t tc = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, tc++) {
       const int split = tile / mn_tiles, mn = tile % mn_tiles;
@@ -278,7 +306,7 @@ k_gemm_bf3(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CU
       mbar_wait_b(&bar_tfull[acc], (tc >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cb = 0; cb < BN; cb += 32) {
+      for (int cb = chalf * (BN / 2); cb < (chalf + 1) * (BN / 2); cb += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb, v);
         float x[32];
@@ -289,7 +317,7 @@ k_gemm_bf3(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CU
 #pragma unroll
           for (int j = 0; j < 32; j++) {
             float z = x[j] + (ep.bias ? __ldg(ep.bias + col0 + j) : 0.f);
-            if (ep.act == HVI_ACT_TANH) z = tanhf(z);
+            if (ep.act == HVI_ACT_TANH) z = tanh_fast(z);
             else if (ep.act == HVI_ACT_LOGISTIC) z = 1.f / (1.f + expf(-z));
             x[j] = z;
           }
@@ -334,7 +362,7 @@ static bool make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t 
   if (!enc) return false;
   const cuuint64_t dims[2] = {inner, outer};
   const cuuint64_t strides[1] = {ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)G_BK, box_outer};
+  const cuuint32_t box[2] = {64, box_outer};
   const cuuint32_t es[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -342,12 +370,21 @@ static bool make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t 
 
 int bf3_wgrad_splits(int Md, int Nd, int sm_count) {
   const int bn = Nd % 256 == 0 ? 256 : 128;
-  const int tiles = (Md / G_BM) * (Nd / bn);
+  const int tiles = ((Md + G_BM - 1) / G_BM) * (Nd / bn);
   int ns = sm_count / (tiles > 0 ? tiles : 1);
   return ns < 1 ? 1 : (ns > 24 ? 24 : ns);
 }
+// the splits launch_gemm_bf3<2> really uses for a contraction of K rows (every split a multiple of 64, none empty)
+static int effective_splits(int64_t K, int nsplit, int64_t* per_out) {
+  int64_t per = (K + nsplit - 1) / nsplit;
+  per = (per + G_BK - 1) / G_BK * G_BK;
+  if (per_out) *per_out = per;
+  return (int)((K + per - 1) / per);
+}
 
-// D = A·Bᵀ with A [M][lda] (K valid per row), B [N][ldb]; N % 128 == 0, lda/ldb % 8 == 0, 16-byte aligned bases
+// MODE 0/1: D[M x N] = A·Bᵀ with A [M][lda], B [N][ldb], K features per row (K-major operands).
+// MODE 2:   D[M x N] = AᵀB  with A [K][lda] (M features per row), B [K][ldb] (N features per row): MN-major operands.
+// N % 128 == 0, lda/ldb % 8 == 0, 16-byte aligned bases.
 template <int MODE>
 static cudaError_t launch_gemm_bf3(const Launch& L, const bf16* A_hi, const bf16* A_lo, int64_t lda, int64_t M, const bf16* B_hi,
                                    const bf16* B_lo, int64_t ldb, int N, int64_t K, int nsplit, const GemmEpi& ep) {
@@ -355,15 +392,17 @@ static cudaError_t launch_gemm_bf3(const Launch& L, const bf16* A_hi, const bf16
   const int bn = N % 256 == 0 ? 256 : 128;
   GemmShape sh;
   sh.M = M; sh.N = N; sh.K = K;
-  int64_t per = (K + nsplit - 1) / nsplit;
-  per = (per + G_BK - 1) / G_BK * G_BK;
-  sh.k_per_split = per;
-  sh.nsplit = (int)((K + per - 1) / per);
+  sh.nsplit = effective_splits(K, nsplit < 1 ? 1 : nsplit, &sh.k_per_split);
   CUtensorMap ma_h, ma_l, mb_h, mb_l;
-  if (!make_map(&ma_h, A_hi, (uint64_t)K, (uint64_t)M, (uint64_t)lda, G_BM) || !make_map(&ma_l, A_lo, (uint64_t)K, (uint64_t)M, (uint64_t)lda, G_BM) ||
-      !make_map(&mb_h, B_hi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)bn) ||
-      !make_map(&mb_l, B_lo, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)bn))
-    return cudaErrorInvalidValue;
+  bool ok;
+  if (MODE != 2)
+    ok = make_map(&ma_h, A_hi, (uint64_t)K, (uint64_t)M, (uint64_t)lda, G_BM) && make_map(&ma_l, A_lo, (uint64_t)K, (uint64_t)M, (uint64_t)lda, G_BM) &&
+         make_map(&mb_h, B_hi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)bn) &&
+         make_map(&mb_l, B_lo, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)bn);
+  else
+    ok = make_map(&ma_h, A_hi, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64) && make_map(&ma_l, A_lo, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64) &&
+         make_map(&mb_h, B_hi, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64) && make_map(&mb_l, B_lo, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64);
+  if (!ok) return cudaErrorInvalidValue;
   const int m_tiles = (int)((M + G_BM - 1) / G_BM);
   const int64_t total = (int64_t)m_tiles * (N / bn) * sh.nsplit;
   const int sms = L.sm_count > 0 ? L.sm_count : 148;
@@ -402,7 +441,7 @@ __global__ void k_split_w(const float* __restrict__ W, int n_in, int n_out, bf16
   reinterpret_cast<unsigned short*>(t_lo)[(size_t)j * n_in + i] = l;
 }
 
-// fp32 [rows][W] → planes (tests, and the generic entry points); one warp per 32 rows x 32 features
+// fp32 [rows][W] → planes (test harness); one warp per 32 rows x 32 features
 __global__ void __launch_bounds__(256) k_split_planes(const float* __restrict__ X, int64_t rows, int W, Planes o) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
@@ -413,15 +452,13 @@ __global__ void __launch_bounds__(256) k_split_planes(const float* __restrict__ 
   for (int j = 0; j < 32; j++) x[j] = ok ? X[row * W + col0 + j] : 0.f;
   store_planes32(o, row, col0, x, ok);
 }
-// planes → fp32; transposed != 0 reads the [feature][row] planes instead
-__global__ void k_join_planes(Planes p, int64_t rows, int W, int transposed, float* __restrict__ X) {
+// planes → fp32 (test harness)
+__global__ void k_join_planes(Planes p, int64_t rows, int W, float* __restrict__ X) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows * W) return;
   const int64_t r = e / W;
   const int c = (int)(e % W);
-  const bf16* hi = transposed ? p.hiT + (int64_t)c * p.ldT + r : p.hi + r * p.ld + c;
-  const bf16* lo = transposed ? p.loT + (int64_t)c * p.ldT + r : p.lo + r * p.ld + c;
-  X[e] = __bfloat162float(*hi) + __bfloat162float(*lo);
+  X[e] = __bfloat162float(p.hi[r * p.ld + c]) + __bfloat162float(p.lo[r * p.ld + c]);
 }
 
 // first layer (K = n_covar + pbm covariates ≤ 8) on CUDA cores: lane ↔ row, 64 features per warp
@@ -447,7 +484,7 @@ __global__ void __launch_bounds__(256) k_first_bf3(const float* __restrict__ xM,
         for (int j = 0; j < 32; j++) z[j] = fmaf(xin[i], __ldg(W0 + (size_t)i * N + cb + j), z[j]);
       }
 #pragma unroll
-    for (int j = 0; j < 32; j++) z[j] = act_apply<float>(act, z[j]);
+    for (int j = 0; j < 32; j++) z[j] = (act == HVI_ACT_TANH) ? tanh_fast(z[j]) : act_apply<float>(act, z[j]);
     store_planes32(o, row, cb, z, ok);
   }
 }
@@ -526,31 +563,47 @@ __global__ void __launch_bounds__(256) k_thin_bwd_bf3(const float* __restrict__ 
   }
 }
 
-// G[s][b] = Σ_r S[r·ls + s]·B[r][b] over this block's row slice, B from normal planes; one thread per b
-__global__ void __launch_bounds__(256) k_skinny_bf3(const float* __restrict__ S, int ls, int ns, const bf16* __restrict__ b_hi,
+// G[s][b] = Σ_r S[r·ls + s]·B[r][b] over this block's row slice, B from the planes; one thread per TWO columns b
+__global__ void __launch_bounds__(128) k_skinny_bf3(const float* __restrict__ S, int ls, int ns, const bf16* __restrict__ b_hi,
                                                     const bf16* __restrict__ b_lo, int64_t lb, int nbig, int64_t rows,
                                                     float* __restrict__ part) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int64_t r0 = (int64_t)blockIdx.y * SKINNY_ROWS;
   const int64_t r1 = r0 + SKINNY_ROWS < rows ? r0 + SKINNY_ROWS : rows;
   if (b >= nbig) return;
-  float acc[8];
-  for (int s = 0; s < 8; s++) acc[s] = 0.f;
+  float acc0[8], acc1[8];
+  for (int s = 0; s < 8; s++) acc0[s] = acc1[s] = 0.f;
   int64_t r = r0;
   for (; r + 4 <= r1; r += 4) {
-    float y[4];
+    float y0[4], y1[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) y[u] = __bfloat162float(b_hi[(r + u) * lb + b]) + __bfloat162float(b_lo[(r + u) * lb + b]);
+    for (int u = 0; u < 4; u++) {
+      const uint32_t wh = __ldg(reinterpret_cast<const uint32_t*>(b_hi + (r + u) * lb + b)), wl = __ldg(reinterpret_cast<const uint32_t*>(b_lo + (r + u) * lb + b));
+      y0[u] = bf_lo(wh) + bf_lo(wl);
+      y1[u] = bf_hi(wh) + bf_hi(wl);
+    }
     for (int s = 0; s < ns; s++) {
 #pragma unroll
-      for (int u = 0; u < 4; u++) acc[s] = fmaf(S[(r + u) * ls + s], y[u], acc[s]);
+      for (int u = 0; u < 4; u++) {
+        const float sv = S[(r + u) * ls + s];
+        acc0[s] = fmaf(sv, y0[u], acc0[s]);
+        acc1[s] = fmaf(sv, y1[u], acc1[s]);
+      }
     }
   }
   for (; r < r1; r++) {
-    const float y = __bfloat162float(b_hi[r * lb + b]) + __bfloat162float(b_lo[r * lb + b]);
-    for (int s = 0; s < ns; s++) acc[s] = fmaf(S[r * ls + s], y, acc[s]);
+    const uint32_t wh = __ldg(reinterpret_cast<const uint32_t*>(b_hi + r * lb + b)), wl = __ldg(reinterpret_cast<const uint32_t*>(b_lo + r * lb + b));
+    const float y0 = bf_lo(wh) + bf_lo(wl), y1 = bf_hi(wh) + bf_hi(wl);
+    for (int s = 0; s < ns; s++) {
+      const float sv = S[r * ls + s];
+      acc0[s] = fmaf(sv, y0, acc0[s]);
+      acc1[s] = fmaf(sv, y1, acc1[s]);
+    }
   }
-  for (int s = 0; s < ns; s++) part[((size_t)blockIdx.y * ns + s) * nbig + b] = acc[s];
+  for (int s = 0; s < ns; s++) {
+    part[((size_t)blockIdx.y * ns + s) * nbig + b] = acc0[s];
+    part[((size_t)blockIdx.y * ns + s) * nbig + b + 1] = acc1[s];
+  }
 }
 
 // ---- eligibility and work space ---------------------------------------------------------------
@@ -574,20 +627,20 @@ struct Bf3Work {
   float* P;             // weight-gradient partial tiles / skinny partials
   double* db0;
 };
+static size_t bf3_partial_floats(int maxw) {
+  const size_t pf = (size_t)24 * maxw * maxw, sk = (size_t)(WIDE_CHUNK / SKINNY_ROWS) * 8 * maxw;
+  return pf > sk ? pf : sk;
+}
 // carve the work space of launch_mlp_bwd_wide (wide_bwd_work_bytes) / launch_mlp_fwd_wide (wide_work_elems·4)
 static void carve(Bf3Work& w, void* work, int nL, int maxw, int nphig, bool bwd) {
   const size_t cw = (size_t)WIDE_CHUNK * maxw;
   bf16* p = reinterpret_cast<bf16*>(work);
-  auto planes = [&](Planes& pl, bool trans) {
-    pl.hi = p; p += cw; pl.lo = p; p += cw; pl.ld = 0;
-    if (trans) { pl.hiT = p; p += cw; pl.loT = p; p += cw; } else { pl.hiT = pl.loT = nullptr; }
-    pl.ldT = WIDE_CHUNK;
-  };
+  auto planes = [&](Planes& pl) { pl.hi = p; p += cw; pl.lo = p; p += cw; pl.ld = 0; };
   if (bwd) {
-    for (int l = 0; l < nL - 1; l++) planes(w.H[l], true);
-    planes(w.D[0], true); planes(w.D[1], true);
+    for (int l = 0; l < nL - 1; l++) planes(w.H[l]);
+    planes(w.D[0]); planes(w.D[1]);
   } else {
-    planes(w.H[0], false); planes(w.H[1], false);
+    planes(w.H[0]); planes(w.H[1]);
   }
   w.wn_hi = p; p += nphig; w.wn_lo = p; p += nphig; w.wt_hi = p; p += nphig; w.wt_lo = p; p += nphig;
   p += (8 - (4 * (size_t)nphig) % 8) % 8;      // keep 16-byte alignment
@@ -597,8 +650,7 @@ static void carve(Bf3Work& w, void* work, int nL, int maxw, int nphig, bool bwd)
     w.Xs = f; f += (size_t)WIDE_CHUNK * XS_LD;
     w.dlast = f; f += (size_t)WIDE_CHUNK * 8;
     w.P = f;
-    const size_t pf = (size_t)24 * maxw * maxw, sk = (size_t)(WIDE_CHUNK / SKINNY_ROWS) * 8 * maxw;
-    f += (pf > sk ? pf : sk);
+    f += bf3_partial_floats(maxw);
     f += ((uintptr_t)f % 8) ? 1 : 0;
     w.db0 = reinterpret_cast<double*>(f);
   }
@@ -606,8 +658,7 @@ static void carve(Bf3Work& w, void* work, int nL, int maxw, int nphig, bool bwd)
 size_t bf3_fwd_work_bytes(int maxw, int nphig) { return (size_t)WIDE_CHUNK * maxw * 8 + (size_t)nphig * 8 + 256; }
 size_t bf3_bwd_work_bytes(int nL, int maxw, int nphig) {
   const size_t cw = (size_t)WIDE_CHUNK * maxw;
-  const size_t pf = (size_t)24 * maxw * maxw, sk = (size_t)(WIDE_CHUNK / SKINNY_ROWS) * 8 * maxw;
-  return (size_t)(nL + 1) * cw * 8 + (size_t)nphig * 8 + 4 * ((size_t)WIDE_CHUNK * (XS_LD + 8) + (pf > sk ? pf : sk)) + 8 * (size_t)maxw + 1024;
+  return (size_t)(nL + 1) * cw * 4 + (size_t)nphig * 8 + 4 * ((size_t)WIDE_CHUNK * (XS_LD + 8) + bf3_partial_floats(maxw)) + 8 * (size_t)maxw + 1024;
 }
 
 static cudaError_t split_weights(const Launch& L, const Cfg<float>& cfg, const float* phi, Bf3Work& w) {
@@ -627,16 +678,15 @@ static cudaError_t set_extra(const Launch& L, const Cfg<float>& cfg, const float
   }
   return cudaSuccess;
 }
-// forward chain of one chunk: first layer on CUDA cores, hidden layers on the tensor cores; H[l] = output of layer l
+// forward chain of one chunk: first layer on CUDA cores, hidden layers on the tensor cores; outs[l] = output of layer l
 static cudaError_t chain_fwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t s0, int64_t rows,
                              Bf3Work& w, Planes* outs /*nL-1 entries*/) {
   {
     const int N = cfg.l_out[0];
-    Planes o = outs[0]; o.ld = N;
-    k_first_bf3<<<dim3((unsigned)((rows + 255) / 256), N / 64), 256, 0, L.stream>>>(
-        xM, cfg.nC, w.extra_h, cfg.npc, s0, phi + cfg.woff[0], cfg.l_bias[0] ? phi + cfg.boff[0] : nullptr, cfg.l_act[0], rows, N, o);
-    if (L.counter) ++*L.counter;
     outs[0].ld = N;
+    k_first_bf3<<<dim3((unsigned)((rows + 255) / 256), N / 64), 256, 0, L.stream>>>(
+        xM, cfg.nC, w.extra_h, cfg.npc, s0, phi + cfg.woff[0], cfg.l_bias[0] ? phi + cfg.boff[0] : nullptr, cfg.l_act[0], rows, N, outs[0]);
+    if (L.counter) ++*L.counter;
   }
   for (int l = 1; l < cfg.nL - 1; l++) {
     const int N = cfg.l_out[l], K = cfg.l_in[l];
@@ -695,11 +745,10 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
     for (int64_t s0 = 0; s0 < nb; s0 += WIDE_CHUNK) {
       const int64_t rows = nb - s0 < WIDE_CHUNK ? nb - s0 : WIDE_CHUNK;
       const int nslice = (int)((rows + SKINNY_ROWS - 1) / SKINNY_ROWS);
-      // ---- forward, keeping all activations (transposed planes where a weight gradient reads them)
+      // ---- forward, keeping all activations
       k_build_xs<float><<<(unsigned)((rows + 255) / 256), 256, 0, L.stream>>>(xM, cfg.nC, w.extra_h, cfg.npc, s0, rows, w.Xs);
       count();
-      Planes H[8];
-      for (int l = 0; l < nL - 1; l++) { H[l] = w.H[l]; if (l == nL - 2) H[l].hiT = H[l].loT = nullptr; }
+      Planes* H = w.H;
       e = chain_fwd(L, cfg, phi, xM, s0, rows, w, H);
       if (e != cudaSuccess) return e;
       // ---- last layer: δ_L, ∇W_L, δ_{L-1}
@@ -711,12 +760,10 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
                                                                               M_units, nb, w.dlast);
         count();
         Dcur.ld = K;
-        Planes o = Dcur;
-        if (nL - 2 < 1) o.hiT = o.loT = nullptr;
         k_thin_bwd_bf3<<<dim3((unsigned)((rows + 255) / 256), K / 64), 256, 0, L.stream>>>(w.dlast, phi + cfg.woff[l], no, H[l - 1].hi,
-                                                                                        H[l - 1].lo, K, cfg.l_act[l - 1], rows, o);
+                                                                                        H[l - 1].lo, K, cfg.l_act[l - 1], rows, Dcur);
         count();
-        k_skinny_bf3<<<dim3((K + 255) / 256, nslice), 256, 0, L.stream>>>(w.dlast, 8, no, H[l - 1].hi, H[l - 1].lo, K, K, rows, w.P);
+        k_skinny_bf3<<<dim3((K / 2 + 127) / 128, nslice), 128, 0, L.stream>>>(w.dlast, 8, no, H[l - 1].hi, H[l - 1].lo, K, K, rows, w.P);
         count();
         k_accum<float><<<(no * K + 255) / 256, 256, 0, L.stream>>>(w.P, nslice, (size_t)no * K, no, K, grad_acc, cfg.woff[l], 1, no, nullptr);
         count();
@@ -725,21 +772,19 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
       for (int l = nL - 2; l >= 1; l--) {
         const int N = cfg.l_out[l], K = cfg.l_in[l];   // Dcur: [rows][N]
         if (cfg.l_bias[l]) {
-          k_skinny_bf3<<<dim3((N + 255) / 256, nslice), 256, 0, L.stream>>>(w.Xs + cfg.nC + cfg.npc, XS_LD, 1, Dcur.hi, Dcur.lo, N, N, rows, w.P);
+          k_skinny_bf3<<<dim3((N / 2 + 127) / 128, nslice), 128, 0, L.stream>>>(w.Xs + cfg.nC + cfg.npc, XS_LD, 1, Dcur.hi, Dcur.lo, N, N, rows, w.P);
           count();
           k_accum<float><<<(N + 255) / 256, 256, 0, L.stream>>>(w.P, nslice, (size_t)N, 1, N, grad_acc, cfg.boff[l], 0, 1, nullptr);
           count();
         }
-        {  // ∇W_l[in][out] = H_{l-1}ᵀ δ_l: both operands from the transposed planes, contraction over the rows
+        {  // ∇W_l[in][out] = H_{l-1}ᵀ δ_l: the same planes as MN-major operands, contraction over the rows
           GemmEpi ep;
           memset(&ep, 0, sizeof(ep));
           ep.P = w.P;
           const int ns = bf3_wgrad_splits(K, N, sms);
-          e = launch_gemm_bf3<2>(L, H[l - 1].hiT, H[l - 1].loT, WIDE_CHUNK, K, Dcur.hiT, Dcur.loT, WIDE_CHUNK, N, rows, ns, ep);
+          e = launch_gemm_bf3<2>(L, H[l - 1].hi, H[l - 1].lo, K, K, Dcur.hi, Dcur.lo, N, N, rows, ns, ep);
           if (e != cudaSuccess) return e;
-          int64_t per = (rows + ns - 1) / ns;
-          per = (per + G_BK - 1) / G_BK * G_BK;
-          const int ns_eff = (int)((rows + per - 1) / per);
+          const int ns_eff = effective_splits(rows, ns, nullptr);
           k_accum<float><<<(K * N + 255) / 256, 256, 0, L.stream>>>(w.P, ns_eff, (size_t)K * N, 1, K * N, grad_acc, cfg.woff[l], 0, 1, nullptr);
           count();
         }
@@ -750,7 +795,6 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
           ep.h_hi = H[l - 1].hi; ep.h_lo = H[l - 1].lo; ep.ldh = K;
           Dnxt.ld = K;
           ep.out = Dnxt;
-          if (l == 1) ep.out.hiT = ep.out.loT = nullptr;   // δ_0 feeds only the first layer's skinny reduction
           e = launch_gemm_bf3<1>(L, Dcur.hi, Dcur.lo, N, rows, w.wn_hi + cfg.woff[l], w.wn_lo + cfg.woff[l], N, K, N, 1, ep);
           if (e != cudaSuccess) return e;
         }
@@ -760,7 +804,7 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
       {
         const int N = cfg.l_out[0], K = cfg.l_in[0];
         const int ns = K + 1;
-        k_skinny_bf3<<<dim3((N + 255) / 256, nslice), 256, 0, L.stream>>>(w.Xs, XS_LD, ns, Dcur.hi, Dcur.lo, N, N, rows, w.P);
+        k_skinny_bf3<<<dim3((N / 2 + 127) / 128, nslice), 128, 0, L.stream>>>(w.Xs, XS_LD, ns, Dcur.hi, Dcur.lo, N, N, rows, w.P);
         count();
         const size_t sst = (size_t)ns * N;
         double* acc_b = cfg.l_bias[0] ? grad_acc : nullptr;
@@ -780,26 +824,27 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
 }
 
 // ---- test harness: one GEMM on device fp32 arrays (split → GEMM → join) ----------------------
-// mode 0: C = act(A·Bᵀ + bias); mode 1: C = (A·Bᵀ) ⊙ act'(Hd); mode 2: C = A·Bᵀ through the split-K path.
-// A [M][K], B [N][K], C [M][N], Ct [N][M] (nullable; transposed planes of the result, modes 0/1)
+// mode 0: C = act(A·Bᵀ + bias), A [M][K], B [N][K];  mode 1: C = (A·Bᵀ) ⊙ act'(Hd);
+// mode 2: C = AᵀB through the split-K path, A [K][M], B [K][N] (the weight-gradient orientation).  C [M][N].
 cudaError_t gemm_bf3_device(cudaStream_t stream, int sm_count, int mode, int64_t M, int N, int64_t K, const float* A, const float* B,
-                            const float* bias, int act, const float* Hd, float* C, float* Ct) {
-  if (K % 32 != 0 || N % 128 != 0 || !tma_encoder()) return cudaErrorInvalidValue;
+                            const float* bias, int act, const float* Hd, float* C) {
+  if (N % 128 != 0 || !tma_encoder()) return cudaErrorInvalidValue;
+  if (mode == 2 ? (M % 32 != 0) : (K % 32 != 0)) return cudaErrorInvalidValue;
   Launch L{stream, sm_count, nullptr};
-  const int64_t Mp = (M + 31) / 32 * 32;      // transposed leading dimension
   bf16* buf = nullptr;
-  const size_t nA = (size_t)M * K, nB = (size_t)N * K, nC = (size_t)N * Mp;
+  const size_t nA = (size_t)M * K, nB = (size_t)N * K, nC = (size_t)M * N;
   const int ns = mode == 2 ? bf3_wgrad_splits((int)M, N, sm_count) : 1;
-  cudaError_t e = cudaMalloc((void**)&buf, 2 * (2 * nA + 2 * nB + 4 * nC + 2 * nC) + sizeof(float) * (size_t)ns * M * N + 64);
+  cudaError_t e = cudaMalloc((void**)&buf, 2 * (2 * nA + 2 * nB + 4 * nC) + sizeof(float) * (size_t)ns * M * N + 64);
   if (e != cudaSuccess) return e;
-  Planes pa{buf, buf + nA, K, nullptr, nullptr, 0};
-  Planes pb{buf + 2 * nA, buf + 2 * nA + nB, K, nullptr, nullptr, 0};
+  const int64_t a_rows = mode == 2 ? K : M, a_w = mode == 2 ? M : K, b_rows = mode == 2 ? K : N, b_w = mode == 2 ? N : K;
+  Planes pa{buf, buf + nA, a_w};
+  Planes pb{buf + 2 * nA, buf + 2 * nA + nB, b_w};
   bf16* q = buf + 2 * nA + 2 * nB;
-  Planes pc{q, q + nC, N, Ct ? q + 2 * nC : nullptr, Ct ? q + 3 * nC : nullptr, Mp};
-  Planes ph{q + 4 * nC, q + 5 * nC, N, nullptr, nullptr, 0};
-  float* P = reinterpret_cast<float*>(q + 6 * nC);
-  k_split_planes<<<dim3((unsigned)((M + 255) / 256), (unsigned)(K / 32)), 256, 0, stream>>>(A, M, (int)K, pa);
-  k_split_planes<<<dim3((unsigned)((N + 255) / 256), (unsigned)(K / 32)), 256, 0, stream>>>(B, N, (int)K, pb);
+  Planes pc{q, q + nC, N};
+  Planes ph{q + 2 * nC, q + 3 * nC, N};
+  float* P = reinterpret_cast<float*>(q + 4 * nC);
+  k_split_planes<<<dim3((unsigned)((a_rows + 255) / 256), (unsigned)(a_w / 32)), 256, 0, stream>>>(A, a_rows, (int)a_w, pa);
+  k_split_planes<<<dim3((unsigned)((b_rows + 255) / 256), (unsigned)(b_w / 32)), 256, 0, stream>>>(B, b_rows, (int)b_w, pb);
   GemmEpi ep;
   memset(&ep, 0, sizeof(ep));
   ep.bias = bias; ep.act = act; ep.out = pc; ep.P = P;
@@ -809,13 +854,11 @@ cudaError_t gemm_bf3_device(cudaStream_t stream, int sm_count, int mode, int64_t
   }
   if (mode == 0) e = launch_gemm_bf3<0>(L, pa.hi, pa.lo, K, M, pb.hi, pb.lo, K, N, K, 1, ep);
   else if (mode == 1) e = launch_gemm_bf3<1>(L, pa.hi, pa.lo, K, M, pb.hi, pb.lo, K, N, K, 1, ep);
-  else e = launch_gemm_bf3<2>(L, pa.hi, pa.lo, K, M, pb.hi, pb.lo, K, N, K, ns, ep);
+  else e = launch_gemm_bf3<2>(L, pa.hi, pa.lo, M, M, pb.hi, pb.lo, N, N, K, ns, ep);
   if (e == cudaSuccess) {
     const int64_t n = M * N;
     if (mode == 2) {
-      int64_t per = (K + ns - 1) / ns;
-      per = (per + G_BK - 1) / G_BK * G_BK;
-      const int ns_eff = (int)((K + per - 1) / per);
+      const int ns_eff = effective_splits(K, ns, nullptr);
       double* acc = nullptr;
       e = cudaMalloc((void**)&acc, sizeof(double) * n);
       if (e == cudaSuccess) {
@@ -831,12 +874,7 @@ cudaError_t gemm_bf3_device(cudaStream_t stream, int sm_count, int mode, int64_t
         cudaFree(acc);
       }
     } else {
-      k_join_planes<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pc, M, N, 0, C);
-      if (Ct) {
-        // Ct [N][M]: element (c, r) = transposed planes at c·ldT + r  ⇒ join with rows ↔ features swapped
-        Planes pt{pc.hiT, pc.loT, Mp, nullptr, nullptr, 0};
-        k_join_planes<<<(unsigned)(((int64_t)N * Mp + 255) / 256), 256, 0, stream>>>(pt, N, (int)Mp, 0, Ct);
-      }
+      k_join_planes<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pc, M, N, C);
       e = cudaGetLastError();
     }
   }

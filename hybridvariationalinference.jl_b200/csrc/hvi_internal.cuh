@@ -137,7 +137,7 @@ cudaError_t launch_mlp_fwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
 cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb, const float* mubar,
                                int M_units, const float* zetaP, void* work, double* grad_acc, double* xacc);
 cudaError_t gemm_bf3_device(cudaStream_t stream, int sm_count, int mode, int64_t M, int N, int64_t K, const float* A, const float* B,
-                            const float* bias, int act, const float* Hd, float* C, float* Ct);
+                            const float* bias, int act, const float* Hd, float* C);
 int stream_max_rows(int sm_count);
 int mlp_bwd_max_blocks(int sm_count);
 bool stream_supported(int nP, int nM, int nO);

@@ -197,12 +197,13 @@ int hvi_dense_tc(int32_t device, int64_t Mc, int32_t N, int32_t K, const float* 
 
 /* One GEMM of the TMA-fed chain the wide applicator runs on (cp.async.bulk.tensor → tcgen05.mma kind::f16
  * with bf16 hi/lo operand planes, three MMAs per K step, two TMEM accumulators, persistent CTAs):
- *   mode 0: C = act(A B^T + bias)   mode 1: C = (A B^T) .* act'(Hd)   mode 2: C = A B^T via the split-K path
- * A (M x K), B (N x K), Hd and C (M x N) row-major host arrays; Ct (N x M, nullable) returns the transposed
- * planes the epilogue writes for the weight-gradient GEMM.  K % 32 == 0, N % 128 == 0.  The pullbacks of the
- * dense layers (Zygote over ext/HybridVariationalInferenceFluxExt.jl:26-31) are modes 1 and 2. */
+ *   mode 0: C = act(A B^T + bias), A (M x K), B (N x K)     (layer forward)
+ *   mode 1: C = (A B^T) .* act'(Hd)                          (data gradient)
+ *   mode 2: C = A^T B, A (K x M), B (K x N), split over K     (weight gradient; MN-major operands)
+ * Hd and C are (M x N); row-major host arrays.  N % 128 == 0; K % 32 == 0 (mode 2: M % 32 == 0).  Modes 1
+ * and 2 are the pullbacks of the dense layers (Zygote over ext/HybridVariationalInferenceFluxExt.jl:26-31). */
 int hvi_gemm_bf3(int32_t device, int32_t mode, int64_t M, int32_t N, int64_t K, const float* A, const float* B,
-                 const float* bias, int32_t act, const float* Hd, float* C, float* Ct);
+                 const float* bias, int32_t act, const float* Hd, float* C);
 
 /* number of kernels launched by this plan since creation (bench.py's gpu_launches) */
 int64_t hvi_launch_count(const hvi_plan* plan);
