@@ -29,6 +29,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -76,6 +77,7 @@ struct GemmShape {
   int64_t K;             // contraction length (MODE 2: the rows of both operands)
   int nsplit;            // MODE 2: K is cut into nsplit ranges of k_per_split
   int64_t k_per_split;
+  int dbg;               // experiments (HVI_GEMM_DBG): 1 no stores, 2 no bias loads, 4 no TMEM loads
 };
 
 struct GemmEpi {
@@ -139,6 +141,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // ---- plane helpers -------------------------------------------------------------------------
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane and instruction
+__device__ __forceinline__ void stg256(void* p, const uint32_t* a) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]),
+               "r"(a[5]), "r"(a[6]), "r"(a[7])
+               : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* a) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+               : "l"(p));
+}
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
@@ -153,13 +166,10 @@ __device__ __forceinline__ void store_planes32(const Planes& o, int64_t row, int
     l[j] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   if (!ok) return;
-  uint4* ph = reinterpret_cast<uint4*>(o.hi + row * o.ld + col0);
-  uint4* pl = reinterpret_cast<uint4*>(o.lo + row * o.ld + col0);
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    ph[q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
-    pl[q] = make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
-  }
+  bf16* ph = o.hi + row * o.ld + col0;
+  bf16* pl = o.lo + row * o.ld + col0;
+  stg256(ph, h); stg256(ph + 16, h + 8);
+  stg256(pl, l); stg256(pl + 16, l + 8);
 }
 // tanh to ~2e-7 absolute with two MUFU ops: 1 − 2/(1 + e^{2x})
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -169,17 +179,21 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
   return fmaf(-2.f, r, 1.f);
 }
+// raw hi/lo words of 32 consecutive features of one row (issue early, combine later)
+__device__ __forceinline__ void load_planes32_raw(const bf16* hi, const bf16* lo, int64_t ld, int64_t row, int col0, uint32_t (&a)[16],
+                                                  uint32_t (&b)[16]) {
+  ldg256(hi + row * ld + col0, a); ldg256(hi + row * ld + col0 + 16, a + 8);
+  ldg256(lo + row * ld + col0, b); ldg256(lo + row * ld + col0 + 16, b + 8);
+}
 // 32 consecutive features of one row from the normal planes, recombined to fp32
 __device__ __forceinline__ void load_planes32(const bf16* hi, const bf16* lo, int64_t ld, int64_t row, int col0, float (&x)[32]) {
-  const uint4* ph = reinterpret_cast<const uint4*>(hi + row * ld + col0);
-  const uint4* pl = reinterpret_cast<const uint4*>(lo + row * ld + col0);
+  uint32_t a[16], b[16];
+  ldg256(hi + row * ld + col0, a); ldg256(hi + row * ld + col0 + 16, a + 8);
+  ldg256(lo + row * ld + col0, b); ldg256(lo + row * ld + col0 + 16, b + 8);
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const uint4 a = __ldg(ph + q), b = __ldg(pl + q);
-    x[8 * q + 0] = bf_lo(a.x) + bf_lo(b.x); x[8 * q + 1] = bf_hi(a.x) + bf_hi(b.x);
-    x[8 * q + 2] = bf_lo(a.y) + bf_lo(b.y); x[8 * q + 3] = bf_hi(a.y) + bf_hi(b.y);
-    x[8 * q + 4] = bf_lo(a.z) + bf_lo(b.z); x[8 * q + 5] = bf_hi(a.z) + bf_hi(b.z);
-    x[8 * q + 6] = bf_lo(a.w) + bf_lo(b.w); x[8 * q + 7] = bf_hi(a.w) + bf_hi(b.w);
+  for (int j = 0; j < 16; j++) {
+    x[2 * j] = bf_lo(a[j]) + bf_lo(b[j]);
+    x[2 * j + 1] = bf_hi(a[j]) + bf_hi(b[j]);
   }
 }
 
@@ -303,30 +317,48 @@ k_gemm_bf3(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CU
       const uint32_t acc = tc & 1;
       const int64_t row = (int64_t)m0 + q * 32 + lane;
       const bool ok = row < sh.M;
+      // MODE 1: the activation planes of the first block are requested before the accumulator is awaited,
+      // those of block b+1 while block b is converted and stored
+      uint32_t ha[16], hb[16];
+      if (MODE == 1 && ok) load_planes32_raw(ep.h_hi, ep.h_lo, ep.ldh, row, n0 + chalf * (BN / 2), ha, hb);
       mbar_wait_b(&bar_tfull[acc], (tc >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (int cb = chalf * (BN / 2); cb < (chalf + 1) * (BN / 2); cb += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb, v);
+        if (!(sh.dbg & 4)) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb, v);
+        else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = j + lane;
+        }
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) x[j] = empty_k ? 0.f : __uint_as_float(v[j]);
         const int col0 = n0 + cb;
         if (MODE == 0) {
+          uint32_t bb[32];     // the 32 biases of this block: four 256-bit loads, same address in every lane
+          if (ep.bias && !(sh.dbg & 2)) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) ldg256(ep.bias + col0 + 8 * g, bb + 8 * g);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) bb[j] = 0u;
+          }
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            float z = x[j] + (ep.bias ? __ldg(ep.bias + col0 + j) : 0.f);
+            float z = x[j] + __uint_as_float(bb[j]);
             if (ep.act == HVI_ACT_TANH) z = tanh_fast(z);
             else if (ep.act == HVI_ACT_LOGISTIC) z = 1.f / (1.f + expf(-z));
             x[j] = z;
           }
-          store_planes32(ep.out, row, col0, x, ok);
+          store_planes32(ep.out, row, col0, x, ok && (!(sh.dbg & 1) || x[3] == 1234.5f));
         } else if (MODE == 1) {
-          float h[32];
-          if (ok) load_planes32(ep.h_hi, ep.h_lo, ep.ldh, row, col0, h);
 #pragma unroll
-          for (int j = 0; j < 32; j++) x[j] *= ok ? act_deriv_f(ep.act, h[j]) : 0.f;
+          for (int j = 0; j < 16; j++) {
+            x[2 * j] *= ok ? act_deriv_f(ep.act, bf_lo(ha[j]) + bf_lo(hb[j])) : 0.f;
+            x[2 * j + 1] *= ok ? act_deriv_f(ep.act, bf_hi(ha[j]) + bf_hi(hb[j])) : 0.f;
+          }
+          if (ok && cb + 32 < (chalf + 1) * (BN / 2)) load_planes32_raw(ep.h_hi, ep.h_lo, ep.ldh, row, col0 + 32, ha, hb);
           store_planes32(ep.out, row, col0, x, ok);
         } else if (ok) {
           float4* out = reinterpret_cast<float4*>(ep.P + ((size_t)split * sh.M + row) * sh.N + col0);
@@ -389,10 +421,12 @@ template <int MODE>
 static cudaError_t launch_gemm_bf3(const Launch& L, const bf16* A_hi, const bf16* A_lo, int64_t lda, int64_t M, const bf16* B_hi,
                                    const bf16* B_lo, int64_t ldb, int N, int64_t K, int nsplit, const GemmEpi& ep) {
   if (N % 128 != 0 || lda % 8 != 0 || ldb % 8 != 0 || M < 1 || K < 1) return cudaErrorInvalidValue;
+  if (MODE == 0 && ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) & 31)) return cudaErrorInvalidValue;   // 256-bit bias loads
   const int bn = N % 256 == 0 ? 256 : 128;
   GemmShape sh;
   sh.M = M; sh.N = N; sh.K = K;
   sh.nsplit = effective_splits(K, nsplit < 1 ? 1 : nsplit, &sh.k_per_split);
+  { const char* d = getenv("HVI_GEMM_DBG"); sh.dbg = d ? atoi(d) : 0; }
   CUtensorMap ma_h, ma_l, mb_h, mb_l;
   bool ok;
   if (MODE != 2)
@@ -852,9 +886,27 @@ cudaError_t gemm_bf3_device(cudaStream_t stream, int sm_count, int mode, int64_t
     k_split_planes<<<dim3((unsigned)((M + 255) / 256), (unsigned)(N / 32)), 256, 0, stream>>>(Hd, M, N, ph);
     ep.h_hi = ph.hi; ep.h_lo = ph.lo; ep.ldh = N;
   }
-  if (mode == 0) e = launch_gemm_bf3<0>(L, pa.hi, pa.lo, K, M, pb.hi, pb.lo, K, N, K, 1, ep);
-  else if (mode == 1) e = launch_gemm_bf3<1>(L, pa.hi, pa.lo, K, M, pb.hi, pb.lo, K, N, K, 1, ep);
-  else e = launch_gemm_bf3<2>(L, pa.hi, pa.lo, M, M, pb.hi, pb.lo, N, N, K, ns, ep);
+  auto run = [&]() {
+    if (mode == 0) return launch_gemm_bf3<0>(L, pa.hi, pa.lo, K, M, pb.hi, pb.lo, K, N, K, 1, ep);
+    if (mode == 1) return launch_gemm_bf3<1>(L, pa.hi, pa.lo, K, M, pb.hi, pb.lo, K, N, K, 1, ep);
+    return launch_gemm_bf3<2>(L, pa.hi, pa.lo, M, M, pb.hi, pb.lo, N, N, K, ns, ep);
+  };
+  e = run();
+  if (e == cudaSuccess && getenv("HVI_GEMM_TIME")) {   // device time of the GEMM alone (profiles/bench_gemm_bf3.py)
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int reps = 20;
+    cudaEventRecord(e0, stream);
+    for (int i = 0; i < reps && e == cudaSuccess; i++) e = run();
+    cudaEventRecord(e1, stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double us = 1e3 * ms / reps, flop = 2.0 * (double)M * N * (double)K;
+    fprintf(stderr, "hvi_gemm_bf3 mode %d M=%lld N=%d K=%lld: %.1f us/launch, %.1f TFLOP/s fp32-equivalent (x3 bf16 MMA work)\n", mode,
+            (long long)M, N, (long long)K, us, flop / us * 1e-6);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   if (e == cudaSuccess) {
     const int64_t n = M * N;
     if (mode == 2) {
