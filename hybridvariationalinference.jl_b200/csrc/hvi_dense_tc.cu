@@ -774,7 +774,7 @@ cudaError_t launch_mlp_bwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi
         }
         count(); count();
         if (cfg.npc > 0 && xacc) {
-          k_xbar<T><<<1, 32, 0, L.stream>>>(phi + cfg.woff[0], cfg.nC, cfg.npc, N, db0, xacc + (size_t)(M_units > 0 ? m : 0) * cfg.npc);
+          k_xbar<T><<<1, 32 * (cfg.npc > 0 ? cfg.npc : 1), 0, L.stream>>>(phi + cfg.woff[0], cfg.nC, cfg.npc, N, db0, xacc + (size_t)(M_units > 0 ? m : 0) * cfg.npc);
           count();
         }
       }

@@ -400,11 +400,14 @@ static bool make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t 
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// row splits of a weight-gradient GEMM: one CTA per (tile, split); at most 24 full tiles of partials
+// (the work space holds 24·maxw² floats), any number when the left operand is skinny (Md ≤ S_LD)
 int bf3_wgrad_splits(int Md, int Nd, int sm_count) {
   const int bn = Nd % 256 == 0 ? 256 : 128;
   const int tiles = ((Md + G_BM - 1) / G_BM) * (Nd / bn);
   int ns = sm_count / (tiles > 0 ? tiles : 1);
-  return ns < 1 ? 1 : (ns > 24 ? 24 : ns);
+  const int cap = Md <= 64 ? 148 : 24;
+  return ns < 1 ? 1 : (ns > cap ? cap : ns);
 }
 // the splits launch_gemm_bf3<2> really uses for a contraction of K rows (every split a multiple of 64, none empty)
 static int effective_splits(int64_t K, int nsplit, int64_t* per_out) {
@@ -495,7 +498,34 @@ __global__ void k_join_planes(Planes p, int64_t rows, int W, float* __restrict__
   X[e] = __bfloat162float(p.hi[r * p.ld + c]) + __bfloat162float(p.lo[r * p.ld + c]);
 }
 
-// first layer (K = n_covar + pbm covariates ≤ 8) on CUDA cores: lane ↔ row, 64 features per warp
+// [x ; pbm covariates ; 1 ; 0 …] of every row of the chunk as hi/lo planes [rows][S_LD]: the skinny left operand
+// of the first layer's weight gradient (rows 0 … K-1 → ∇W_0, row K → ∇b_0) and, through its ones column,
+// of the hidden layers' bias gradients
+constexpr int S_LD = 64;
+__global__ void k_build_sx(const float* __restrict__ xM, int nC, const float* __restrict__ extra, int npc, int64_t site0, int64_t rows,
+                           bf16* __restrict__ s_hi, bf16* __restrict__ s_lo) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  uint32_t h[S_LD / 2], l[S_LD / 2];
+#pragma unroll
+  for (int j = 0; j < S_LD / 2; j++) {
+    float v[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int i = 2 * j + u;
+      v[u] = i < nC ? xM[(site0 + r) * nC + i] : i < nC + npc ? extra[i - nC] : i == nC + npc ? 1.f : 0.f;
+    }
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[0], v[1]);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[0] - __low2float(hh), v[1] - __high2float(hh));
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+#pragma unroll
+  for (int g = 0; g < S_LD / 16; g++) { stg256(s_hi + r * S_LD + 16 * g, h + 8 * g); stg256(s_lo + r * S_LD + 16 * g, l + 8 * g); }
+}
+
+// first layer (K = n_covar + pbm covariates ≤ 8) on CUDA cores: lane ↔ row, 64 features per warp;
+// weights and biases come in as 256-bit loads of one address per warp
 __global__ void __launch_bounds__(256) k_first_bf3(const float* __restrict__ xM, int nC, const float* __restrict__ extra, int npc,
                                                    int64_t site0, const float* __restrict__ W0, const float* __restrict__ b0, int act,
                                                    int64_t rows, int N, Planes o) {
@@ -509,13 +539,23 @@ __global__ void __launch_bounds__(256) k_first_bf3(const float* __restrict__ xM,
 #pragma unroll 1
   for (int cb = blockIdx.y * 64; cb < blockIdx.y * 64 + 64; cb += 32) {
     float z[32];
+    uint32_t wv[32];
+    if (b0) {
 #pragma unroll
-    for (int j = 0; j < 32; j++) z[j] = b0 ? __ldg(b0 + cb + j) : 0.f;
+      for (int g = 0; g < 4; g++) ldg256(b0 + cb + 8 * g, wv + 8 * g);
+#pragma unroll
+      for (int j = 0; j < 32; j++) z[j] = __uint_as_float(wv[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j++) z[j] = 0.f;
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++)
       if (i < K) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) z[j] = fmaf(xin[i], __ldg(W0 + (size_t)i * N + cb + j), z[j]);
+        for (int g = 0; g < 4; g++) ldg256(W0 + (size_t)i * N + cb + 8 * g, wv + 8 * g);
+#pragma unroll
+        for (int j = 0; j < 32; j++) z[j] = fmaf(xin[i], __uint_as_float(wv[j]), z[j]);
       }
 #pragma unroll
     for (int j = 0; j < 32; j++) z[j] = (act == HVI_ACT_TANH) ? tanh_fast(z[j]) : act_apply<float>(act, z[j]);
@@ -523,56 +563,119 @@ __global__ void __launch_bounds__(256) k_first_bf3(const float* __restrict__ xM,
   }
 }
 
-// last layer (N = n_θM ≤ 8): one warp per row, every lane 8 consecutive features per step.
-// BWD == 0: μ_ζ = scale(act(z));  BWD == 1: δ_L[k] = μ̄·scale'·act'  →  dlast[r][8]
-template <int BWD>
+// last layer (N = n_θM ≤ 8): a warp takes 32 rows; per row the lanes share the features (8 consecutive ones per
+// lane and step) and a butterfly leaves the sums in lane (row mod 32), so that the output scaling (Φ⁻¹ in double)
+// runs with all lanes busy.
+// BWD == 0: μ_ζ = scale(act(z));  BWD == 1: δ_L[k] = μ̄·scale'·act' → dlast[r][8] and the planes [r][S_LD]
+template <int BWD, int NOUT>
 __global__ void __launch_bounds__(256) k_last_bf3(const Cfg<float> cfg, const bf16* __restrict__ hi, const bf16* __restrict__ lo, int64_t ld,
-                                                  const float* __restrict__ Wref, int act, int64_t rows, int K, int n_out,
+                                                  const float* __restrict__ Wref, int act, int64_t rows, int K,
                                                   float* __restrict__ mu, const float* __restrict__ mubar, int64_t site0, int m,
-                                                  int M_units, int64_t nb, float* __restrict__ dlast) {
-  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                                  int M_units, int64_t nb, float* __restrict__ dlast, bf16* __restrict__ d_hi,
+                                                  bf16* __restrict__ d_lo) {
   const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  float acc[MAXP];
+  const int64_t r0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  if (r0 >= rows) return;
+  float mine[NOUT];
 #pragma unroll
-  for (int k = 0; k < MAXP; k++) acc[k] = 0.f;
-  for (int i0 = lane * 8; i0 < K; i0 += 256) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + r * ld + i0)), b = __ldg(reinterpret_cast<const uint4*>(lo + r * ld + i0));
-    const float x[8] = {bf_lo(a.x) + bf_lo(b.x), bf_hi(a.x) + bf_hi(b.x), bf_lo(a.y) + bf_lo(b.y), bf_hi(a.y) + bf_hi(b.y),
-                        bf_lo(a.z) + bf_lo(b.z), bf_hi(a.z) + bf_hi(b.z), bf_lo(a.w) + bf_lo(b.w), bf_hi(a.w) + bf_hi(b.w)};
+  for (int k = 0; k < NOUT; k++) mine[k] = 0.f;
+  const int nr = rows - r0 < 32 ? (int)(rows - r0) : 32;
+  // this lane's slice of W_L (features lane·8 … +7 of every 256): 8·NOUT consecutive floats per step, kept in
+  // registers across the rows when the layer is at most 512 wide
+  constexpr int WSTEPS = 2;
+  uint32_t wv[WSTEPS][8 * NOUT];
+  const bool wreg = K <= 256 * WSTEPS;
+  if (wreg) {
 #pragma unroll
-    for (int c = 0; c < 8; c++)
-      for (int k = 0; k < n_out; k++) acc[k] = fmaf(x[c], __ldg(Wref + (size_t)(i0 + c) * n_out + k), acc[k]);
+    for (int st = 0; st < WSTEPS; st++)
+      if (lane * 8 + 256 * st < K) {
+#pragma unroll
+        for (int g = 0; g < NOUT; g++) ldg256(Wref + (size_t)(lane * 8 + 256 * st) * NOUT + 8 * g, wv[st] + 8 * g);
+      }
   }
-  const int64_t site = site0 + r;
-  for (int k = 0; k < n_out; k++) {
-    float s = acc[k];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane != 0) continue;
-    const float p = act_apply<float>(act, s);
-    if (BWD == 0) {
-      if (k < cfg.nM) {
-        const float v = (cfg.scale_kind == HVI_SCALE_RANGE) ? p * cfg.scale_b[k] + cfg.scale_a[k]
-                                                           : cfg.scale_a[k] + cfg.scale_b[k] * (float)normcdfinv((double)p);
-        if (M_units > 0) mu[((size_t)m * cfg.nM + k) * nb + site] = v;
-        else mu[site * cfg.nM + k] = v;
+  for (int i = 0; i < nr; i++) {
+    const int64_t r = r0 + i;
+    float acc[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) acc[k] = 0.f;
+    if (wreg) {
+#pragma unroll
+      for (int st = 0; st < WSTEPS; st++) {
+        const int i0 = lane * 8 + 256 * st;
+        if (i0 < K) {
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + r * ld + i0)), b = __ldg(reinterpret_cast<const uint4*>(lo + r * ld + i0));
+          const float x[8] = {bf_lo(a.x) + bf_lo(b.x), bf_hi(a.x) + bf_hi(b.x), bf_lo(a.y) + bf_lo(b.y), bf_hi(a.y) + bf_hi(b.y),
+                              bf_lo(a.z) + bf_lo(b.z), bf_hi(a.z) + bf_hi(b.z), bf_lo(a.w) + bf_lo(b.w), bf_hi(a.w) + bf_hi(b.w)};
+#pragma unroll
+          for (int c = 0; c < 8; c++)
+#pragma unroll
+            for (int k = 0; k < NOUT; k++) acc[k] = fmaf(x[c], __uint_as_float(wv[st][c * NOUT + k]), acc[k]);
+        }
       }
     } else {
-      float d = 0.f;
-      if (k < cfg.nM) {
-        const float mb = M_units > 0 ? mubar[((size_t)m * cfg.nM + k) * nb + site] : mubar[site * cfg.nM + k];
-        if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb * cfg.scale_b[k];
-        else { const float qn = (float)normcdfinv((double)p); d = mb * cfg.scale_b[k] * 2.50662827463100050242f * expf(0.5f * qn * qn); }
-        d *= (act == HVI_ACT_LOGISTIC) ? p * (1.f - p) : (act == HVI_ACT_TANH) ? 1.f - p * p : 1.f;
+      for (int i0 = lane * 8; i0 < K; i0 += 256) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + r * ld + i0)), b = __ldg(reinterpret_cast<const uint4*>(lo + r * ld + i0));
+        const float x[8] = {bf_lo(a.x) + bf_lo(b.x), bf_hi(a.x) + bf_hi(b.x), bf_lo(a.y) + bf_lo(b.y), bf_hi(a.y) + bf_hi(b.y),
+                            bf_lo(a.z) + bf_lo(b.z), bf_hi(a.z) + bf_hi(b.z), bf_lo(a.w) + bf_lo(b.w), bf_hi(a.w) + bf_hi(b.w)};
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+#pragma unroll
+          for (int k = 0; k < NOUT; k++) acc[k] = fmaf(x[c], __ldg(Wref + (size_t)(i0 + c) * NOUT + k), acc[k]);
       }
-      dlast[r * 8 + k] = d;
+    }
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) {
+      float s = acc[k];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == i) mine[k] = s;
     }
   }
-  if (BWD == 1 && lane == 0) for (int k = n_out; k < 8; k++) dlast[r * 8 + k] = 0.f;
+  if (lane >= nr) return;
+  const int64_t r = r0 + lane, site = site0 + r;
+  float d[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) d[k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) {
+    if (k >= cfg.nM) continue;
+    const float p = act_apply<float>(act, mine[k]);
+    if (BWD == 0) {
+      const float v = (cfg.scale_kind == HVI_SCALE_RANGE) ? p * cfg.scale_b[k] + cfg.scale_a[k]
+                                                         : cfg.scale_a[k] + cfg.scale_b[k] * (float)normcdfinv((double)p);
+      if (M_units > 0) mu[((size_t)m * cfg.nM + k) * nb + site] = v;
+      else mu[site * cfg.nM + k] = v;
+    } else {
+      const float mb = M_units > 0 ? mubar[((size_t)m * cfg.nM + k) * nb + site] : mubar[site * cfg.nM + k];
+      float dv;
+      if (cfg.scale_kind == HVI_SCALE_RANGE) dv = mb * cfg.scale_b[k];
+      else { const float qn = (float)normcdfinv((double)p); dv = mb * cfg.scale_b[k] * 2.50662827463100050242f * expf(0.5f * qn * qn); }
+      dv *= (act == HVI_ACT_LOGISTIC) ? p * (1.f - p) : (act == HVI_ACT_TANH) ? 1.f - p * p : 1.f;
+      if (k < 8) d[k] = dv;
+    }
+  }
+  if (BWD == 1) {
+    float4* dl = reinterpret_cast<float4*>(dlast + r * 8);
+    dl[0] = make_float4(d[0], d[1], d[2], d[3]);
+    dl[1] = make_float4(d[4], d[5], d[6], d[7]);
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(d[2 * j], d[2 * j + 1]);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(d[2 * j] - __low2float(hh), d[2 * j + 1] - __high2float(hh));
+      h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+      l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+      h[4 + j] = l[4 + j] = 0u;
+    }
+    const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    stg256(d_hi + r * S_LD, h); stg256(d_lo + r * S_LD, l);
+#pragma unroll
+    for (int g = 1; g < S_LD / 16; g++) { stg256(d_hi + r * S_LD + 16 * g, zero); stg256(d_lo + r * S_LD + 16 * g, zero); }
+  }
 }
 
 // δ_{L-1}[r][i] = (Σ_k W_L[i][k] δ_L[r][k]) · act'(H_{L-1}[r][i]); lane ↔ row, 64 features per warp
-__global__ void __launch_bounds__(256) k_thin_bwd_bf3(const float* __restrict__ dlast, const float* __restrict__ Wref, int n_out,
+template <int NOUT>
+__global__ void __launch_bounds__(256) k_thin_bwd_bf3(const float* __restrict__ dlast, const float* __restrict__ Wref,
                                                       const bf16* __restrict__ h_hi, const bf16* __restrict__ h_lo, int64_t ldh,
                                                       int act_prev, int64_t rows, Planes o) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -586,59 +689,33 @@ __global__ void __launch_bounds__(256) k_thin_bwd_bf3(const float* __restrict__ 
     float h[32], z[32];
     if (ok) load_planes32(h_hi, h_lo, ldh, row, cb, h);
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-      float s = 0.f;
+    for (int j0 = 0; j0 < 32; j0 += 8) {      // W_L[(cb+j)·n_out + k], 8 features at a time: n_out 256-bit loads, one address per warp
+      uint32_t wv[8 * NOUT];
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-        if (k < n_out) s = fmaf(__ldg(Wref + (size_t)(cb + j) * n_out + k), dl[k], s);
-      z[j] = ok ? s * act_deriv_f(act_prev, h[j]) : 0.f;
+      for (int g = 0; g < NOUT; g++) ldg256(Wref + (size_t)(cb + j0) * NOUT + 8 * g, wv + 8 * g);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NOUT; k++) s = fmaf(__uint_as_float(wv[j * NOUT + k]), dl[k], s);
+        z[j0 + j] = ok ? s * act_deriv_f(act_prev, h[j0 + j]) : 0.f;
+      }
     }
     store_planes32(o, row, cb, z, ok);
   }
 }
 
-// G[s][b] = Σ_r S[r·ls + s]·B[r][b] over this block's row slice, B from the planes; one thread per TWO columns b
-__global__ void __launch_bounds__(128) k_skinny_bf3(const float* __restrict__ S, int ls, int ns, const bf16* __restrict__ b_hi,
-                                                    const bf16* __restrict__ b_lo, int64_t lb, int nbig, int64_t rows,
-                                                    float* __restrict__ part) {
-  const int b = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int64_t r0 = (int64_t)blockIdx.y * SKINNY_ROWS;
-  const int64_t r1 = r0 + SKINNY_ROWS < rows ? r0 + SKINNY_ROWS : rows;
-  if (b >= nbig) return;
-  float acc0[8], acc1[8];
-  for (int s = 0; s < 8; s++) acc0[s] = acc1[s] = 0.f;
-  int64_t r = r0;
-  for (; r + 4 <= r1; r += 4) {
-    float y0[4], y1[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const uint32_t wh = __ldg(reinterpret_cast<const uint32_t*>(b_hi + (r + u) * lb + b)), wl = __ldg(reinterpret_cast<const uint32_t*>(b_lo + (r + u) * lb + b));
-      y0[u] = bf_lo(wh) + bf_lo(wl);
-      y1[u] = bf_hi(wh) + bf_hi(wl);
-    }
-    for (int s = 0; s < ns; s++) {
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const float sv = S[(r + u) * ls + s];
-        acc0[s] = fmaf(sv, y0[u], acc0[s]);
-        acc1[s] = fmaf(sv, y1[u], acc1[s]);
-      }
-    }
+#define HVI_NOUT_SWITCH(n, CALL)                                                               \
+  switch (n) {                                                                                 \
+    case 1: { constexpr int NOUT = 1; CALL; } break;                                           \
+    case 2: { constexpr int NOUT = 2; CALL; } break;                                           \
+    case 3: { constexpr int NOUT = 3; CALL; } break;                                           \
+    case 4: { constexpr int NOUT = 4; CALL; } break;                                           \
+    case 5: { constexpr int NOUT = 5; CALL; } break;                                           \
+    case 6: { constexpr int NOUT = 6; CALL; } break;                                           \
+    case 7: { constexpr int NOUT = 7; CALL; } break;                                           \
+    default: { constexpr int NOUT = 8; CALL; } break;                                          \
   }
-  for (; r < r1; r++) {
-    const uint32_t wh = __ldg(reinterpret_cast<const uint32_t*>(b_hi + r * lb + b)), wl = __ldg(reinterpret_cast<const uint32_t*>(b_lo + r * lb + b));
-    const float y0 = bf_lo(wh) + bf_lo(wl), y1 = bf_hi(wh) + bf_hi(wl);
-    for (int s = 0; s < ns; s++) {
-      const float sv = S[r * ls + s];
-      acc0[s] = fmaf(sv, y0, acc0[s]);
-      acc1[s] = fmaf(sv, y1, acc1[s]);
-    }
-  }
-  for (int s = 0; s < ns; s++) {
-    part[((size_t)blockIdx.y * ns + s) * nbig + b] = acc0[s];
-    part[((size_t)blockIdx.y * ns + s) * nbig + b + 1] = acc1[s];
-  }
-}
 
 // ---- eligibility and work space ---------------------------------------------------------------
 bool bf3_eligible(const Cfg<float>& cfg) {
@@ -656,13 +733,15 @@ struct Bf3Work {
   Planes D[2];          // cotangent ping-pong
   bf16 *wn_hi, *wn_lo, *wt_hi, *wt_lo;   // weight planes, indexed like ϕg
   float* extra_h;       // pbm covariate values of the current draw
-  float* Xs;            // [chunk][XS_LD]
-  float* dlast;         // [chunk][8]
+  Planes Sx;            // [chunk][S_LD]: inputs, pbm covariates, 1 (k_build_sx)
+  Planes Sd;            // [chunk][S_LD]: δ of the last layer
+  float* dlast;         // [chunk][8], the same in fp32
   float* P;             // weight-gradient partial tiles / skinny partials
   double* db0;
 };
+// partial tiles of the split-K GEMMs: 24 splits of a full weight gradient, or 148 splits of a skinny one
 static size_t bf3_partial_floats(int maxw) {
-  const size_t pf = (size_t)24 * maxw * maxw, sk = (size_t)(WIDE_CHUNK / SKINNY_ROWS) * 8 * maxw;
+  const size_t pf = (size_t)24 * maxw * maxw, sk = (size_t)148 * 64 * maxw;
   return pf > sk ? pf : sk;
 }
 // carve the work space of launch_mlp_bwd_wide (wide_bwd_work_bytes) / launch_mlp_fwd_wide (wide_work_elems·4)
@@ -681,7 +760,11 @@ static void carve(Bf3Work& w, void* work, int nL, int maxw, int nphig, bool bwd)
   float* f = reinterpret_cast<float*>(p);
   w.extra_h = f; f += 16;
   if (bwd) {
-    w.Xs = f; f += (size_t)WIDE_CHUNK * XS_LD;
+    bf16* sp = reinterpret_cast<bf16*>(f);
+    const size_t sn = (size_t)WIDE_CHUNK * S_LD;
+    w.Sx = Planes{sp, sp + sn, S_LD};
+    w.Sd = Planes{sp + 2 * sn, sp + 3 * sn, S_LD};
+    f += 2 * sn;          // 4 planes of sn bf16
     w.dlast = f; f += (size_t)WIDE_CHUNK * 8;
     w.P = f;
     f += bf3_partial_floats(maxw);
@@ -692,7 +775,7 @@ static void carve(Bf3Work& w, void* work, int nL, int maxw, int nphig, bool bwd)
 size_t bf3_fwd_work_bytes(int maxw, int nphig) { return (size_t)WIDE_CHUNK * maxw * 8 + (size_t)nphig * 8 + 256; }
 size_t bf3_bwd_work_bytes(int nL, int maxw, int nphig) {
   const size_t cw = (size_t)WIDE_CHUNK * maxw;
-  return (size_t)(nL + 1) * cw * 4 + (size_t)nphig * 8 + 4 * ((size_t)WIDE_CHUNK * (XS_LD + 8) + bf3_partial_floats(maxw)) + 8 * (size_t)maxw + 1024;
+  return (size_t)(nL + 1) * cw * 4 + (size_t)nphig * 8 + 4 * ((size_t)WIDE_CHUNK * (2 * S_LD + 8) + bf3_partial_floats(maxw)) + 8 * (size_t)maxw + 1024;
 }
 
 static cudaError_t split_weights(const Launch& L, const Cfg<float>& cfg, const float* phi, Bf3Work& w) {
@@ -754,9 +837,9 @@ cudaError_t launch_mlp_fwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
       e = chain_fwd(L, cfg, phi, xM, s0, rows, w, outs);
       if (e != cudaSuccess) return e;
       const int l = nL - 1;
-      k_last_bf3<0><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, L.stream>>>(cfg, outs[l - 1].hi, outs[l - 1].lo, cfg.l_in[l],
-                                                                            phi + cfg.woff[l], cfg.l_act[l], rows, cfg.l_in[l],
-                                                                            cfg.l_out[l], mu, nullptr, s0, m, M_units, nb, nullptr);
+      HVI_NOUT_SWITCH(cfg.l_out[l], (k_last_bf3<0, NOUT><<<(unsigned)((rows + 255) / 256), 256, 0, L.stream>>>(
+                                        cfg, outs[l - 1].hi, outs[l - 1].lo, cfg.l_in[l], phi + cfg.woff[l], cfg.l_act[l], rows, cfg.l_in[l], mu,
+                                        nullptr, s0, m, M_units, nb, nullptr, nullptr, nullptr)));
       if (L.counter) ++*L.counter;
     }
   }
@@ -773,14 +856,25 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
   if (e != cudaSuccess) return e;
   const int sms = L.sm_count > 0 ? L.sm_count : 148;
   const int nm = M_units > 0 ? M_units : 1;
+  // skinny product G[S_w x N] = Sᵀ·B over the rows of the chunk on the tensor cores (S: planes [rows][S_LD], only the
+  // first S_w features used; B: planes [rows][N]); returns the number of partial slices in w.P ([slice][S_w][N])
+  auto skinny = [&](const Planes& S, int S_w, const Planes& B, int N, int64_t rows, int* nslice) -> cudaError_t {
+    GemmEpi ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.P = w.P;
+    const int ns = bf3_wgrad_splits(S_w, N, sms);
+    *nslice = effective_splits(rows, ns, nullptr);
+    return launch_gemm_bf3<2>(L, S.hi, S.lo, S_LD, S_w, B.hi, B.lo, N, N, rows, ns, ep);
+  };
   for (int m = 0; m < nm; m++) {
     e = set_extra(L, cfg, phi, zetaP, M_units, m, w.extra_h);
     if (e != cudaSuccess) return e;
     for (int64_t s0 = 0; s0 < nb; s0 += WIDE_CHUNK) {
       const int64_t rows = nb - s0 < WIDE_CHUNK ? nb - s0 : WIDE_CHUNK;
-      const int nslice = (int)((rows + SKINNY_ROWS - 1) / SKINNY_ROWS);
+      const int K0 = cfg.l_in[0];          // inputs of the first layer; Sx column K0 is the constant 1
+      int nslice = 0;
       // ---- forward, keeping all activations
-      k_build_xs<float><<<(unsigned)((rows + 255) / 256), 256, 0, L.stream>>>(xM, cfg.nC, w.extra_h, cfg.npc, s0, rows, w.Xs);
+      k_build_sx<<<(unsigned)((rows + 127) / 128), 128, 0, L.stream>>>(xM, cfg.nC, w.extra_h, cfg.npc, s0, rows, w.Sx.hi, w.Sx.lo);
       count();
       Planes* H = w.H;
       e = chain_fwd(L, cfg, phi, xM, s0, rows, w, H);
@@ -789,26 +883,26 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
       Planes Dcur = w.D[0], Dnxt = w.D[1];
       {
         const int l = nL - 1, K = cfg.l_in[l], no = cfg.l_out[l];
-        k_last_bf3<1><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, L.stream>>>(cfg, H[l - 1].hi, H[l - 1].lo, K, phi + cfg.woff[l],
-                                                                              cfg.l_act[l], rows, K, no, nullptr, mubar, s0, m,
-                                                                              M_units, nb, w.dlast);
+        HVI_NOUT_SWITCH(no, (k_last_bf3<1, NOUT><<<(unsigned)((rows + 255) / 256), 256, 0, L.stream>>>(
+                                cfg, H[l - 1].hi, H[l - 1].lo, K, phi + cfg.woff[l], cfg.l_act[l], rows, K, nullptr, mubar, s0, m, M_units, nb,
+                                w.dlast, w.Sd.hi, w.Sd.lo)));
         count();
         Dcur.ld = K;
-        k_thin_bwd_bf3<<<dim3((unsigned)((rows + 255) / 256), K / 64), 256, 0, L.stream>>>(w.dlast, phi + cfg.woff[l], no, H[l - 1].hi,
-                                                                                        H[l - 1].lo, K, cfg.l_act[l - 1], rows, Dcur);
+        HVI_NOUT_SWITCH(no, (k_thin_bwd_bf3<NOUT><<<dim3((unsigned)((rows + 255) / 256), K / 64), 256, 0, L.stream>>>(
+                                w.dlast, phi + cfg.woff[l], H[l - 1].hi, H[l - 1].lo, K, cfg.l_act[l - 1], rows, Dcur)));
         count();
-        k_skinny_bf3<<<dim3((K / 2 + 127) / 128, nslice), 128, 0, L.stream>>>(w.dlast, 8, no, H[l - 1].hi, H[l - 1].lo, K, K, rows, w.P);
-        count();
+        e = skinny(w.Sd, no, H[l - 1], K, rows, &nslice);      // ∇W_L[i][k] = Σ_r δ_L[r][k] H_{L-1}[r][i]
+        if (e != cudaSuccess) return e;
         k_accum<float><<<(no * K + 255) / 256, 256, 0, L.stream>>>(w.P, nslice, (size_t)no * K, no, K, grad_acc, cfg.woff[l], 1, no, nullptr);
         count();
       }
       // ---- hidden layers l = nL-2 … 1: bias, weight gradient, δ of the layer below
       for (int l = nL - 2; l >= 1; l--) {
         const int N = cfg.l_out[l], K = cfg.l_in[l];   // Dcur: [rows][N]
-        if (cfg.l_bias[l]) {
-          k_skinny_bf3<<<dim3((N / 2 + 127) / 128, nslice), 128, 0, L.stream>>>(w.Xs + cfg.nC + cfg.npc, XS_LD, 1, Dcur.hi, Dcur.lo, N, N, rows, w.P);
-          count();
-          k_accum<float><<<(N + 255) / 256, 256, 0, L.stream>>>(w.P, nslice, (size_t)N, 1, N, grad_acc, cfg.boff[l], 0, 1, nullptr);
+        if (cfg.l_bias[l]) {                           // ∇b_l = 1ᵀ δ_l: row K0 of Sxᵀ δ_l
+          e = skinny(w.Sx, K0 + 1, Dcur, N, rows, &nslice);
+          if (e != cudaSuccess) return e;
+          k_accum<float><<<(N + 255) / 256, 256, 0, L.stream>>>(w.P + (size_t)K0 * N, nslice, (size_t)(K0 + 1) * N, 1, N, grad_acc, cfg.boff[l], 0, 1, nullptr);
           count();
         }
         {  // ∇W_l[in][out] = H_{l-1}ᵀ δ_l: the same planes as MN-major operands, contraction over the rows
@@ -834,19 +928,18 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
         }
         Planes tmp = Dcur; Dcur = Dnxt; Dnxt = tmp;
       }
-      // ---- first layer: ∇b_0, ∇W_0 = [x; covariates]ᵀ δ_0, and the cotangent of the covariate inputs
+      // ---- first layer: ∇W_0 = [x; covariates]ᵀ δ_0 (rows 0 … K0-1), ∇b_0 (row K0), and the cotangent of the covariate inputs
       {
-        const int N = cfg.l_out[0], K = cfg.l_in[0];
-        const int ns = K + 1;
-        k_skinny_bf3<<<dim3((N / 2 + 127) / 128, nslice), 128, 0, L.stream>>>(w.Xs, XS_LD, ns, Dcur.hi, Dcur.lo, N, N, rows, w.P);
-        count();
+        const int N = cfg.l_out[0], ns = K0 + 1;
+        e = skinny(w.Sx, ns, Dcur, N, rows, &nslice);
+        if (e != cudaSuccess) return e;
         const size_t sst = (size_t)ns * N;
         double* acc_b = cfg.l_bias[0] ? grad_acc : nullptr;
-        k_accum<float><<<(K * N + 255) / 256, 256, 0, L.stream>>>(w.P, nslice, sst, K, N, grad_acc, cfg.woff[0], N, 1, nullptr);
-        k_accum<float><<<(N + 255) / 256, 256, 0, L.stream>>>(w.P + (size_t)K * N, nslice, sst, 1, N, acc_b, cfg.boff[0], 0, 1, w.db0);
+        k_accum<float><<<(K0 * N + 255) / 256, 256, 0, L.stream>>>(w.P, nslice, sst, K0, N, grad_acc, cfg.woff[0], N, 1, nullptr);
+        k_accum<float><<<(N + 255) / 256, 256, 0, L.stream>>>(w.P + (size_t)K0 * N, nslice, sst, 1, N, acc_b, cfg.boff[0], 0, 1, w.db0);
         count(); count();
         if (cfg.npc > 0 && xacc) {
-          k_xbar<float><<<1, 32, 0, L.stream>>>(phi + cfg.woff[0], cfg.nC, cfg.npc, N, w.db0, xacc + (size_t)(M_units > 0 ? m : 0) * cfg.npc);
+          k_xbar<float><<<1, 32 * cfg.npc, 0, L.stream>>>(phi + cfg.woff[0], cfg.nC, cfg.npc, N, w.db0, xacc + (size_t)(M_units > 0 ? m : 0) * cfg.npc);
           count();
         }
       }

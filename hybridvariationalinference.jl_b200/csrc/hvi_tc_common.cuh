@@ -97,11 +97,13 @@ __global__ void k_accum(const PT* __restrict__ part, int nslice, size_t slice_st
 template <typename T>
 __global__ void k_xbar(const T* __restrict__ W0, int nC, int npc, int N, const double* __restrict__ db0_chunk,
                        double* __restrict__ xacc_m) {
-  const int c = threadIdx.x;
+  // one warp per covariate, lanes stride over the features, fixed-order butterfly
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (c >= npc) return;
   double s = 0.0;
-  for (int j = 0; j < N; j++) s += (double)W0[(size_t)(nC + c) * N + j] * db0_chunk[j];
-  xacc_m[c] += s;
+  for (int j = lane; j < N; j += 32) s += (double)W0[(size_t)(nC + c) * N + j] * db0_chunk[j];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) xacc_m[c] += s;
 }
 
 
