@@ -43,6 +43,7 @@ struct hvi_plan {
   int wide;                           // wide applicator (forward paths only)
   void* d_wide; int64_t cap_wide;
   void* d_wide_bwd; int64_t cap_wide_bwd;
+  void* d_wide_cache; int64_t cap_wide_cache;   // activations kept between g forward and backward (bf3 chain)
   double* d_gacc;                     // wide applicator: ∇ϕg accumulator [nphig] + x̄ accumulators
   void* d_stage; int64_t cap_stage;   // staging of a host batch (xP, y_o, y_unc) for k_preprocess
   double* h_pre;                      // pinned: preprocess partial sums
@@ -234,6 +235,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   p->d_stage = nullptr; p->cap_stage = 0; p->h_pre = nullptr;
   p->wide = is_wide(desc) ? 1 : 0; p->d_wide = nullptr; p->cap_wide = 0;
   p->d_wide_bwd = nullptr; p->cap_wide_bwd = 0; p->d_gacc = nullptr;
+  p->d_wide_cache = nullptr; p->cap_wide_cache = 0;
   p->d_part_stream = p->d_part_mlp = p->d_out = p->d_red = nullptr;
   p->d_grad = nullptr; p->h_out = nullptr; p->h_grad = nullptr;
   p->const_nly = 0; p->anomalies = 0;
@@ -278,7 +280,7 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   cudaSetDevice(p->desc.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   void* dev[] = {p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
-                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide, p->d_wide_bwd, p->d_gacc};
+                 p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide, p->d_wide_bwd, p->d_gacc, p->d_wide_cache};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
   if (p->h_grad) cudaFreeHost(p->h_grad);
@@ -440,11 +442,12 @@ template <> const Cfg<double>& cfg_of<double>(const hvi_plan* p) { return p->cd;
 
 // g forward for all paths: register-tiled / generic CUDA-core kernels, or the wide tensor-core chain
 template <typename T>
-static int run_g_fwd(hvi_plan* p, const Launch& L, const Cfg<T>& cfg, const T* phi, T* out, int M_units, const T* zetaP) {
+static int run_g_fwd(hvi_plan* p, const Launch& L, const Cfg<T>& cfg, const T* phi, T* out, int M_units, const T* zetaP,
+                     WideCache cache = WideCache{nullptr, 0, 0}) {
   if (p->wide) {
     int rc = ensure(p, &p->d_wide, &p->cap_wide, (int64_t)(sizeof(T) * wide_work_elems(cfg.max_width, cfg.nphig)));
     if (rc) return rc;
-    CU(p, launch_mlp_fwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, out, M_units, zetaP, (T*)p->d_wide));
+    CU(p, launch_mlp_fwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, out, M_units, zetaP, (T*)p->d_wide, cache));
     return HVI_OK;
   }
   CU(p, launch_mlp_fwd<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, out, M_units, zetaP));
@@ -468,7 +471,28 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   MARK();
   const bool pbm = cfg.npc > 0;
   const T* zetaP = pdraw + (size_t)cfg.nP * M;
-  rc = run_g_fwd<T>(p, L, cfg, phi, (T*)p->d_mu, 0, nullptr);
+  // wide Float32 applicator: keep the activations of as many chunks as half of the free memory holds
+  WideCache cache_s{nullptr, 0, 0}, cache_u{nullptr, 0, 0};
+  if constexpr (sizeof(T) == 4) {
+    if (p->wide && bf3_eligible(cfg)) {
+      const int64_t nch = bf3_chunks(p->nb), need = nch * (1 + (pbm ? M : 0));
+      const int64_t slot = (int64_t)bf3_cache_slot_bytes(cfg.nL, cfg.max_width);
+      if (p->cap_wide_cache < need * slot) {
+        size_t fr = 0, tot = 0;
+        CU(p, cudaMemGetInfo(&fr, &tot));
+        int64_t can = ((int64_t)fr + p->cap_wide_cache) / 2 / slot;
+        if (can > need) can = need;
+        if (can * slot > p->cap_wide_cache) {
+          rc = ensure(p, &p->d_wide_cache, &p->cap_wide_cache, can * slot);
+          if (rc) return rc;
+        }
+      }
+      const int64_t have = p->cap_wide_cache / slot;
+      cache_s = WideCache{p->d_wide_cache, have, 0};
+      cache_u = WideCache{p->d_wide_cache, have, nch};
+    }
+  }
+  rc = run_g_fwd<T>(p, L, cfg, phi, (T*)p->d_mu, 0, nullptr, cache_s);
   if (rc) return rc;
   if (pbm) {  // pass 2: g([xM; ζP_m[idx]]) for every draw (src/elbo.jl:508-515)
     const int64_t nmu = (int64_t)sizeof(T) * M * cfg.nM * p->nb;
@@ -480,7 +504,7 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
     if (rc) return rc;
     rc = ensure(p, (void**)&p->d_xred, &p->cap_xred, (int64_t)sizeof(double) * (M + 1) * cfg.npc);
     if (rc) return rc;
-    rc = run_g_fwd<T>(p, L, cfg, phi, (T*)p->d_MU, M, zetaP);
+    rc = run_g_fwd<T>(p, L, cfg, phi, (T*)p->d_MU, M, zetaP, cache_u);
     if (rc) return rc;
   }
   MARK();
@@ -510,10 +534,10 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
     CU(p, cudaMemsetAsync(p->d_gacc, 0, sizeof(double) * (size_t)cfg.nphig, s));
     if (pbm) CU(p, cudaMemsetAsync(p->d_part_x, 0, sizeof(double) * (size_t)2 * p->max_blk * (M + 1) * cfg.npc, s));
     CU(p, launch_mlp_bwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (const T*)p->d_mubar, 0, nullptr, p->d_wide_bwd,
-                                 p->d_gacc, part_xs));
+                                 p->d_gacc, part_xs, cache_s));
     if (pbm)
       CU(p, launch_mlp_bwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (const T*)p->d_MUBAR, M, zetaP, p->d_wide_bwd,
-                                   p->d_gacc, part_xu));
+                                   p->d_gacc, part_xu, cache_u));
     part_g = p->d_gacc;
     nblk = 1; nblk2 = 0;
   } else {

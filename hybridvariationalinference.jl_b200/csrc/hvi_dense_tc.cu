@@ -435,10 +435,10 @@ __global__ void __launch_bounds__(256) k_wide_last(const Cfg<T> cfg, const T* __
 
 template <typename T>
 cudaError_t launch_mlp_fwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu,
-                                int M_units, const T* zetaP, T* work /*wide_work_elems(cfg)*/) {
+                                int M_units, const T* zetaP, T* work /*wide_work_elems(cfg)*/, WideCache cache) {
   if (cfg.l_bias[cfg.nL - 1] || cfg.l_out[cfg.nL - 1] > MAXP) return cudaErrorInvalidConfiguration;
   if constexpr (sizeof(T) == 4) {   // TMA-fed 3xBF16 chain (hvi_dense_tma.cu) when every hidden width is a multiple of 128
-    if (bf3_eligible(cfg)) return launch_mlp_fwd_bf3(L, cfg, phi, xM, nb, mu, M_units, zetaP, work);
+    if (bf3_eligible(cfg)) return launch_mlp_fwd_bf3(L, cfg, phi, xM, nb, mu, M_units, zetaP, work, cache);
   }
   const int64_t CHUNK = 65536;
   const int maxw = cfg.max_width;
@@ -636,10 +636,10 @@ size_t wide_bwd_work_bytes(int nL, int max_width, int nphig) {
 
 template <typename T>
 cudaError_t launch_mlp_bwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, const T* mubar,
-                                int M_units, const T* zetaP, void* work, double* grad_acc, double* xacc) {
+                                int M_units, const T* zetaP, void* work, double* grad_acc, double* xacc, WideCache cache) {
   if (cfg.l_bias[cfg.nL - 1] || cfg.l_out[cfg.nL - 1] > 8 || cfg.nC + cfg.npc + 1 > 8) return cudaErrorInvalidConfiguration;
   if constexpr (sizeof(T) == 4) {
-    if (bf3_eligible(cfg)) return launch_mlp_bwd_bf3(L, cfg, phi, xM, nb, mubar, M_units, zetaP, work, grad_acc, xacc);
+    if (bf3_eligible(cfg)) return launch_mlp_bwd_bf3(L, cfg, phi, xM, nb, mubar, M_units, zetaP, work, grad_acc, xacc, cache);
   }
   const int nL = cfg.nL, maxw = cfg.max_width;
   const size_t cw = (size_t)WIDE_CHUNK * maxw;
@@ -786,13 +786,13 @@ cudaError_t launch_mlp_bwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi
 }
 
 template cudaError_t launch_mlp_bwd_wide<float>(const Launch&, const Cfg<float>&, const float*, const float*, int64_t, const float*,
-                                                int, const float*, void*, double*, double*);
+                                                int, const float*, void*, double*, double*, WideCache);
 template cudaError_t launch_mlp_bwd_wide<double>(const Launch&, const Cfg<double>&, const double*, const double*, int64_t,
-                                                 const double*, int, const double*, void*, double*, double*);
+                                                 const double*, int, const double*, void*, double*, double*, WideCache);
 
 template cudaError_t launch_mlp_fwd_wide<float>(const Launch&, const Cfg<float>&, const float*, const float*, int64_t, float*,
-                                                int, const float*, float*);
+                                                int, const float*, float*, WideCache);
 template cudaError_t launch_mlp_fwd_wide<double>(const Launch&, const Cfg<double>&, const double*, const double*, int64_t,
-                                                 double*, int, const double*, double*);
+                                                 double*, int, const double*, double*, WideCache);
 
 }  // namespace hvi

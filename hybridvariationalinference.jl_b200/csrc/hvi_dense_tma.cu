@@ -772,6 +772,16 @@ static void carve(Bf3Work& w, void* work, int nL, int maxw, int nphig, bool bwd)
     w.db0 = reinterpret_cast<double*>(f);
   }
 }
+size_t bf3_cache_slot_bytes(int nL, int maxw) { return (size_t)(nL - 1) * WIDE_CHUNK * maxw * 4; }
+int64_t bf3_chunks(int64_t nb) { return (nb + WIDE_CHUNK - 1) / WIDE_CHUNK; }
+// the planes of slot `slot` of the activation cache, or false when the slot does not exist
+static bool cache_planes(const WideCache& c, int64_t slot, int nL, int maxw, Planes* H) {
+  if (!c.base || slot < 0 || slot >= c.n_slots) return false;
+  const size_t cw = (size_t)WIDE_CHUNK * maxw;
+  bf16* p = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(c.base) + (size_t)slot * bf3_cache_slot_bytes(nL, maxw));
+  for (int l = 0; l < nL - 1; l++) { H[l].hi = p; p += cw; H[l].lo = p; p += cw; H[l].ld = 0; }
+  return true;
+}
 size_t bf3_fwd_work_bytes(int maxw, int nphig) { return (size_t)WIDE_CHUNK * maxw * 8 + (size_t)nphig * 8 + 256; }
 size_t bf3_bwd_work_bytes(int nL, int maxw, int nphig) {
   const size_t cw = (size_t)WIDE_CHUNK * maxw;
@@ -820,7 +830,7 @@ static cudaError_t chain_fwd(const Launch& L, const Cfg<float>& cfg, const float
 }
 
 cudaError_t launch_mlp_fwd_bf3(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb, float* mu,
-                               int M_units, const float* zetaP, void* work) {
+                               int M_units, const float* zetaP, void* work, WideCache cache) {
   Bf3Work w;
   carve(w, work, cfg.nL, cfg.max_width, cfg.nphig, false);
   cudaError_t e = split_weights(L, cfg, phi, w);
@@ -833,7 +843,8 @@ cudaError_t launch_mlp_fwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
     for (int64_t s0 = 0; s0 < nb; s0 += WIDE_CHUNK) {
       const int64_t rows = nb - s0 < WIDE_CHUNK ? nb - s0 : WIDE_CHUNK;
       Planes outs[8];
-      for (int l = 0; l < nL - 1; l++) outs[l] = w.H[l & 1];      // ping-pong
+      if (!cache_planes(cache, cache.slot0 + (int64_t)m * bf3_chunks(nb) + s0 / WIDE_CHUNK, nL, cfg.max_width, outs))
+        for (int l = 0; l < nL - 1; l++) outs[l] = w.H[l & 1];    // not kept: ping-pong
       e = chain_fwd(L, cfg, phi, xM, s0, rows, w, outs);
       if (e != cudaSuccess) return e;
       const int l = nL - 1;
@@ -847,7 +858,7 @@ cudaError_t launch_mlp_fwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
 }
 
 cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb, const float* mubar,
-                               int M_units, const float* zetaP, void* work, double* grad_acc, double* xacc) {
+                               int M_units, const float* zetaP, void* work, double* grad_acc, double* xacc, WideCache cache) {
   Bf3Work w;
   const int nL = cfg.nL;
   carve(w, work, nL, cfg.max_width, cfg.nphig, true);
@@ -873,12 +884,17 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
       const int64_t rows = nb - s0 < WIDE_CHUNK ? nb - s0 : WIDE_CHUNK;
       const int K0 = cfg.l_in[0];          // inputs of the first layer; Sx column K0 is the constant 1
       int nslice = 0;
-      // ---- forward, keeping all activations
+      // ---- activations of the chunk: kept by the forward pass, or recomputed
       k_build_sx<<<(unsigned)((rows + 127) / 128), 128, 0, L.stream>>>(xM, cfg.nC, w.extra_h, cfg.npc, s0, rows, w.Sx.hi, w.Sx.lo);
       count();
-      Planes* H = w.H;
-      e = chain_fwd(L, cfg, phi, xM, s0, rows, w, H);
-      if (e != cudaSuccess) return e;
+      Planes H[8];
+      if (cache_planes(cache, cache.slot0 + (int64_t)m * bf3_chunks(nb) + s0 / WIDE_CHUNK, nL, cfg.max_width, H)) {
+        for (int l = 0; l < nL - 1; l++) H[l].ld = cfg.l_out[l];    // kept by the forward pass of this evaluation
+      } else {
+        for (int l = 0; l < nL - 1; l++) H[l] = w.H[l];
+        e = chain_fwd(L, cfg, phi, xM, s0, rows, w, H);
+        if (e != cudaSuccess) return e;
+      }
       // ---- last layer: δ_L, ∇W_L, δ_{L-1}
       Planes Dcur = w.D[0], Dnxt = w.D[1];
       {

@@ -85,6 +85,15 @@ struct Launch {
   int64_t* counter;
 };
 
+// activations of the wide applicator kept from the forward pass for the backward pass of the same evaluation:
+// slot (slot0 + m·n_chunks + chunk) holds every layer output of one chunk of columns; chunks beyond n_slots
+// are recomputed in the backward pass
+struct WideCache {
+  void* base;
+  int64_t n_slots;
+  int64_t slot0;
+};
+
 // ---- kernel launchers (hvi_kernels.cu) -------------------------------------------------
 template <typename T>
 cudaError_t launch_preprocess(const Launch& L, int nO, int64_t nb, const T* xP, const T* y_o, const T* y_unc, T* rec,
@@ -121,21 +130,23 @@ cudaError_t launch_predict(const Launch& L, const Cfg<T>& cfg, const StreamArgs<
 // wide applicator (any layer wider than HVI_MAX_WIDTH): forward only, tensor cores for the hidden layers
 template <typename T>
 cudaError_t launch_mlp_fwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu,
-                                int M_units, const T* zetaP, T* work);
+                                int M_units, const T* zetaP, T* work, WideCache cache = WideCache{nullptr, 0, 0});
 size_t wide_work_elems(int max_width, int nphig);
 template <typename T>
 cudaError_t launch_mlp_bwd_wide(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, const T* mubar,
                                 int M_units, const T* zetaP, void* work, double* grad_acc /*[nphig], zeroed*/,
-                                double* xacc /*[max(M_units,1)*npc], zeroed*/);
+                                double* xacc /*[max(M_units,1)*npc], zeroed*/, WideCache cache = WideCache{nullptr, 0, 0});
 size_t wide_bwd_work_bytes(int nL, int max_width, int nphig);
 // TMA-fed 3xBF16 chain of the wide applicator (hvi_dense_tma.cu), Float32 and hidden widths % 128 == 0
 bool bf3_eligible(const Cfg<float>& cfg);
 size_t bf3_fwd_work_bytes(int maxw, int nphig);
 size_t bf3_bwd_work_bytes(int nL, int maxw, int nphig);
+size_t bf3_cache_slot_bytes(int nL, int maxw);
+int64_t bf3_chunks(int64_t nb);
 cudaError_t launch_mlp_fwd_bf3(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb, float* mu,
-                               int M_units, const float* zetaP, void* work);
+                               int M_units, const float* zetaP, void* work, WideCache cache);
 cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb, const float* mubar,
-                               int M_units, const float* zetaP, void* work, double* grad_acc, double* xacc);
+                               int M_units, const float* zetaP, void* work, double* grad_acc, double* xacc, WideCache cache);
 cudaError_t gemm_bf3_device(cudaStream_t stream, int sm_count, int mode, int64_t M, int N, int64_t K, const float* A, const float* B,
                             const float* bias, int act, const float* Hd, float* C);
 int stream_max_rows(int sm_count);
