@@ -56,6 +56,7 @@ struct GemmTile {
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
   static constexpr uint32_t IDESC_MN = IDESC | (1u << 15) | (1u << 16);
 };
+constexpr int S_LD = 64;             // width of the skinny operand planes (inputs + ones, δ of the last layer)
 constexpr int G_MN_BOX = 64 * 128;   // bytes of one MN-major TMA box: 64 rows (K) x 64 features
 
 // MN-major SWIZZLE_128B descriptor: atoms of 64 features (128 B) x 8 rows; LBO = distance between 64-feature
@@ -333,30 +334,44 @@ k_gemm_bf3(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CU
         }
         float x[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) x[j] = empty_k ? 0.f : __uint_as_float(v[j]);
+        for (int j = 0; j < 32; j++) x[j] = __uint_as_float(v[j]);
+        if (empty_k) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) x[j] = 0.f;
+        }
         const int col0 = n0 + cb;
         if (MODE == 0) {
-          uint32_t bb[32];     // the 32 biases of this block: four 256-bit loads, same address in every lane
-          if (ep.bias && !(sh.dbg & 2)) {
+          if (ep.bias && !(sh.dbg & 2)) {   // the 32 biases of this block: four 256-bit loads, same address in every lane
+            uint32_t bb[32];
 #pragma unroll
             for (int g = 0; g < 4; g++) ldg256(ep.bias + col0 + 8 * g, bb + 8 * g);
-          } else {
 #pragma unroll
-            for (int j = 0; j < 32; j++) bb[j] = 0u;
+            for (int j = 0; j < 32; j++) x[j] += __uint_as_float(bb[j]);
           }
+          // the activation is chosen once per block, not per element
+          if (ep.act == HVI_ACT_TANH) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            float z = x[j] + __uint_as_float(bb[j]);
-            if (ep.act == HVI_ACT_TANH) z = tanh_fast(z);
-            else if (ep.act == HVI_ACT_LOGISTIC) z = 1.f / (1.f + expf(-z));
-            x[j] = z;
+            for (int j = 0; j < 32; j++) x[j] = tanh_fast(x[j]);
+          } else if (ep.act == HVI_ACT_LOGISTIC) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) x[j] = __fdividef(1.f, 1.f + __expf(-x[j]));
           }
           store_planes32(ep.out, row, col0, x, ok && (!(sh.dbg & 1) || x[3] == 1234.5f));
         } else if (MODE == 1) {
+          if (ep.act == HVI_ACT_TANH) {
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            x[2 * j] *= ok ? act_deriv_f(ep.act, bf_lo(ha[j]) + bf_lo(hb[j])) : 0.f;
-            x[2 * j + 1] *= ok ? act_deriv_f(ep.act, bf_hi(ha[j]) + bf_hi(hb[j])) : 0.f;
+            for (int j = 0; j < 16; j++) {
+              const float h0 = bf_lo(ha[j]) + bf_lo(hb[j]), h1 = bf_hi(ha[j]) + bf_hi(hb[j]);
+              x[2 * j] *= fmaf(-h0, h0, 1.f);
+              x[2 * j + 1] *= fmaf(-h1, h1, 1.f);
+            }
+          } else if (ep.act == HVI_ACT_LOGISTIC) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const float h0 = bf_lo(ha[j]) + bf_lo(hb[j]), h1 = bf_hi(ha[j]) + bf_hi(hb[j]);
+              x[2 * j] *= h0 * (1.f - h0);
+              x[2 * j + 1] *= h1 * (1.f - h1);
+            }
           }
           if (ok && cb + 32 < (chalf + 1) * (BN / 2)) load_planes32_raw(ep.h_hi, ep.h_lo, ep.ldh, row, col0 + 32, ha, hb);
           store_planes32(ep.out, row, col0, x, ok);
@@ -478,6 +493,20 @@ __global__ void k_split_w(const float* __restrict__ W, int n_in, int n_out, bf16
   reinterpret_cast<unsigned short*>(t_lo)[(size_t)j * n_in + i] = l;
 }
 
+// first layer as a GEMM over the S_LD-wide input planes: B[j][i] = W_0[i][j] (i < K0), b_0[j] (i = K0, the ones
+// column of Sx), 0 otherwise
+__global__ void k_split_w0(const float* __restrict__ W0, const float* __restrict__ b0, int K0, int N, bf16* __restrict__ hi,
+                           bf16* __restrict__ lo) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * S_LD) return;
+  const int j = e / S_LD, i = e % S_LD;
+  const float v = i < K0 ? W0[(size_t)i * N + j] : (i == K0 && b0) ? b0[j] : 0.f;
+  unsigned short h, l;
+  bf16_split(v, h, l);
+  reinterpret_cast<unsigned short*>(hi)[e] = h;
+  reinterpret_cast<unsigned short*>(lo)[e] = l;
+}
+
 // fp32 [rows][W] → planes (test harness); one warp per 32 rows x 32 features
 __global__ void __launch_bounds__(256) k_split_planes(const float* __restrict__ X, int64_t rows, int W, Planes o) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -501,7 +530,6 @@ __global__ void k_join_planes(Planes p, int64_t rows, int W, float* __restrict__
 // [x ; pbm covariates ; 1 ; 0 …] of every row of the chunk as hi/lo planes [rows][S_LD]: the skinny left operand
 // of the first layer's weight gradient (rows 0 … K-1 → ∇W_0, row K → ∇b_0) and, through its ones column,
 // of the hidden layers' bias gradients
-constexpr int S_LD = 64;
 __global__ void k_build_sx(const float* __restrict__ xM, int nC, const float* __restrict__ extra, int npc, int64_t site0, int64_t rows,
                            bf16* __restrict__ s_hi, bf16* __restrict__ s_lo) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -522,45 +550,6 @@ __global__ void k_build_sx(const float* __restrict__ xM, int nC, const float* __
   }
 #pragma unroll
   for (int g = 0; g < S_LD / 16; g++) { stg256(s_hi + r * S_LD + 16 * g, h + 8 * g); stg256(s_lo + r * S_LD + 16 * g, l + 8 * g); }
-}
-
-// first layer (K = n_covar + pbm covariates ≤ 8) on CUDA cores: lane ↔ row, 64 features per warp;
-// weights and biases come in as 256-bit loads of one address per warp
-__global__ void __launch_bounds__(256) k_first_bf3(const float* __restrict__ xM, int nC, const float* __restrict__ extra, int npc,
-                                                   int64_t site0, const float* __restrict__ W0, const float* __restrict__ b0, int act,
-                                                   int64_t rows, int N, Planes o) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
-  const bool ok = row < rows;
-  const int K = nC + npc;
-  float xin[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) xin[i] = (i < nC) ? (ok ? xM[(site0 + row) * nC + i] : 0.f) : (i < K ? extra[i - nC] : 0.f);
-#pragma unroll 1
-  for (int cb = blockIdx.y * 64; cb < blockIdx.y * 64 + 64; cb += 32) {
-    float z[32];
-    uint32_t wv[32];
-    if (b0) {
-#pragma unroll
-      for (int g = 0; g < 4; g++) ldg256(b0 + cb + 8 * g, wv + 8 * g);
-#pragma unroll
-      for (int j = 0; j < 32; j++) z[j] = __uint_as_float(wv[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; j++) z[j] = 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-      if (i < K) {
-#pragma unroll
-        for (int g = 0; g < 4; g++) ldg256(W0 + (size_t)i * N + cb + 8 * g, wv + 8 * g);
-#pragma unroll
-        for (int j = 0; j < 32; j++) z[j] = fmaf(xin[i], __uint_as_float(wv[j]), z[j]);
-      }
-#pragma unroll
-    for (int j = 0; j < 32; j++) z[j] = (act == HVI_ACT_TANH) ? tanh_fast(z[j]) : act_apply<float>(act, z[j]);
-    store_planes32(o, row, cb, z, ok);
-  }
 }
 
 // last layer (N = n_θM ≤ 8): a warp takes 32 rows; per row the lanes share the features (8 consecutive ones per
@@ -732,6 +721,7 @@ struct Bf3Work {
   Planes H[8];          // outputs of layers 0 … nL-2
   Planes D[2];          // cotangent ping-pong
   bf16 *wn_hi, *wn_lo, *wt_hi, *wt_lo;   // weight planes, indexed like ϕg
+  bf16 *w0_hi, *w0_lo;                   // first layer [N][S_LD] incl. the bias column
   float* extra_h;       // pbm covariate values of the current draw
   Planes Sx;            // [chunk][S_LD]: inputs, pbm covariates, 1 (k_build_sx)
   Planes Sd;            // [chunk][S_LD]: δ of the last layer
@@ -756,15 +746,16 @@ static void carve(Bf3Work& w, void* work, int nL, int maxw, int nphig, bool bwd)
     planes(w.H[0]); planes(w.H[1]);
   }
   w.wn_hi = p; p += nphig; w.wn_lo = p; p += nphig; w.wt_hi = p; p += nphig; w.wt_lo = p; p += nphig;
-  p += (8 - (4 * (size_t)nphig) % 8) % 8;      // keep 16-byte alignment
+  p += (16 - (4 * (size_t)nphig) % 16) % 16;   // keep 32-byte alignment
+  w.w0_hi = p; p += (size_t)maxw * S_LD; w.w0_lo = p; p += (size_t)maxw * S_LD;
+  const size_t sn = (size_t)WIDE_CHUNK * S_LD;
+  w.Sx = Planes{p, p + sn, S_LD}; p += 2 * sn;
   float* f = reinterpret_cast<float*>(p);
   w.extra_h = f; f += 16;
   if (bwd) {
     bf16* sp = reinterpret_cast<bf16*>(f);
-    const size_t sn = (size_t)WIDE_CHUNK * S_LD;
-    w.Sx = Planes{sp, sp + sn, S_LD};
-    w.Sd = Planes{sp + 2 * sn, sp + 3 * sn, S_LD};
-    f += 2 * sn;          // 4 planes of sn bf16
+    w.Sd = Planes{sp, sp + sn, S_LD};
+    f += sn;              // 2 planes of sn bf16
     w.dlast = f; f += (size_t)WIDE_CHUNK * 8;
     w.P = f;
     f += bf3_partial_floats(maxw);
@@ -782,10 +773,13 @@ static bool cache_planes(const WideCache& c, int64_t slot, int nL, int maxw, Pla
   for (int l = 0; l < nL - 1; l++) { H[l].hi = p; p += cw; H[l].lo = p; p += cw; H[l].ld = 0; }
   return true;
 }
-size_t bf3_fwd_work_bytes(int maxw, int nphig) { return (size_t)WIDE_CHUNK * maxw * 8 + (size_t)nphig * 8 + 256; }
+size_t bf3_fwd_work_bytes(int maxw, int nphig) {
+  return (size_t)WIDE_CHUNK * maxw * 8 + (size_t)nphig * 8 + 4 * (size_t)S_LD * (maxw + WIDE_CHUNK) + 512;
+}
 size_t bf3_bwd_work_bytes(int nL, int maxw, int nphig) {
   const size_t cw = (size_t)WIDE_CHUNK * maxw;
-  return (size_t)(nL + 1) * cw * 4 + (size_t)nphig * 8 + 4 * ((size_t)WIDE_CHUNK * (2 * S_LD + 8) + bf3_partial_floats(maxw)) + 8 * (size_t)maxw + 1024;
+  return (size_t)(nL + 1) * cw * 4 + (size_t)nphig * 8 + 4 * (size_t)S_LD * maxw +
+         4 * ((size_t)WIDE_CHUNK * (2 * S_LD + 8) + bf3_partial_floats(maxw)) + 8 * (size_t)maxw + 1024;
 }
 
 static cudaError_t split_weights(const Launch& L, const Cfg<float>& cfg, const float* phi, Bf3Work& w) {
@@ -793,6 +787,12 @@ static cudaError_t split_weights(const Launch& L, const Cfg<float>& cfg, const f
     const int n = cfg.l_in[l] * cfg.l_out[l];
     const int o = cfg.woff[l];
     k_split_w<<<(n + 255) / 256, 256, 0, L.stream>>>(phi + o, cfg.l_in[l], cfg.l_out[l], w.wn_hi + o, w.wn_lo + o, w.wt_hi + o, w.wt_lo + o);
+    if (L.counter) ++*L.counter;
+  }
+  {
+    const int N = cfg.l_out[0];
+    k_split_w0<<<(N * S_LD + 255) / 256, 256, 0, L.stream>>>(phi + cfg.woff[0], cfg.l_bias[0] ? phi + cfg.boff[0] : nullptr, cfg.l_in[0], N,
+                                                             w.w0_hi, w.w0_lo);
     if (L.counter) ++*L.counter;
   }
   return cudaGetLastError();
@@ -808,12 +808,17 @@ static cudaError_t set_extra(const Launch& L, const Cfg<float>& cfg, const float
 // forward chain of one chunk: first layer on CUDA cores, hidden layers on the tensor cores; outs[l] = output of layer l
 static cudaError_t chain_fwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t s0, int64_t rows,
                              Bf3Work& w, Planes* outs /*nL-1 entries*/) {
-  {
+  {  // first layer: [x ; covariates ; 1] (Sx planes, K = S_LD) against [W_0 ; b_0]ᵀ on the tensor cores
     const int N = cfg.l_out[0];
     outs[0].ld = N;
-    k_first_bf3<<<dim3((unsigned)((rows + 255) / 256), N / 64), 256, 0, L.stream>>>(
-        xM, cfg.nC, w.extra_h, cfg.npc, s0, phi + cfg.woff[0], cfg.l_bias[0] ? phi + cfg.boff[0] : nullptr, cfg.l_act[0], rows, N, outs[0]);
+    k_build_sx<<<(unsigned)((rows + 127) / 128), 128, 0, L.stream>>>(xM, cfg.nC, w.extra_h, cfg.npc, s0, rows, w.Sx.hi, w.Sx.lo);
     if (L.counter) ++*L.counter;
+    GemmEpi ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.act = cfg.l_act[0];
+    ep.out = outs[0];
+    cudaError_t e = launch_gemm_bf3<0>(L, w.Sx.hi, w.Sx.lo, S_LD, rows, w.w0_hi, w.w0_lo, S_LD, N, S_LD, 1, ep);
+    if (e != cudaSuccess) return e;
   }
   for (int l = 1; l < cfg.nL - 1; l++) {
     const int N = cfg.l_out[l], K = cfg.l_in[l];
@@ -884,12 +889,12 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
       const int64_t rows = nb - s0 < WIDE_CHUNK ? nb - s0 : WIDE_CHUNK;
       const int K0 = cfg.l_in[0];          // inputs of the first layer; Sx column K0 is the constant 1
       int nslice = 0;
-      // ---- activations of the chunk: kept by the forward pass, or recomputed
-      k_build_sx<<<(unsigned)((rows + 127) / 128), 128, 0, L.stream>>>(xM, cfg.nC, w.extra_h, cfg.npc, s0, rows, w.Sx.hi, w.Sx.lo);
-      count();
+      // ---- activations of the chunk: kept by the forward pass, or recomputed (which also builds Sx)
       Planes H[8];
       if (cache_planes(cache, cache.slot0 + (int64_t)m * bf3_chunks(nb) + s0 / WIDE_CHUNK, nL, cfg.max_width, H)) {
         for (int l = 0; l < nL - 1; l++) H[l].ld = cfg.l_out[l];    // kept by the forward pass of this evaluation
+        k_build_sx<<<(unsigned)((rows + 127) / 128), 128, 0, L.stream>>>(xM, cfg.nC, w.extra_h, cfg.npc, s0, rows, w.Sx.hi, w.Sx.lo);
+        count();
       } else {
         for (int l = 0; l < nL - 1; l++) H[l] = w.H[l];
         e = chain_fwd(L, cfg, phi, xM, s0, rows, w, H);
