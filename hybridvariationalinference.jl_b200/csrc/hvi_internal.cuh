@@ -149,6 +149,12 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
                                int M_units, const float* zetaP, void* work, double* grad_acc, double* xacc, WideCache cache);
 cudaError_t gemm_bf3_device(cudaStream_t stream, int sm_count, int mode, int64_t M, int N, int64_t K, const float* A, const float* B,
                             const float* bias, int act, const float* Hd, float* C);
+// tensor-core (mma.sync, 3xBF16) small applicator, Float32 (hvi_mlp_mma.cu); cudaErrorNotSupported: not one of its shapes
+cudaError_t launch_mlp3_mma_fwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb,
+                                float* mu, int M_units, const float* zetaP);
+cudaError_t launch_mlp3_mma_bwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM,
+                                const float* mubar, int64_t nb, double* part, int* nblk_out, int nblk_max, int M_units,
+                                const float* zetaP, double* part_x);
 int stream_max_rows(int sm_count);
 int mlp_bwd_max_blocks(int sm_count);
 bool stream_supported(int nP, int nM, int nO);

@@ -1677,6 +1677,10 @@ static size_t mlp_bwd_smem(const Cfg<T>& cfg) {
 template <typename T>
 cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu, int M_units,
                            const T* zetaP) {
+  if constexpr (sizeof(T) == 4) {   // Float32: the named shapes run on the tensor cores
+    const cudaError_t em = launch_mlp3_mma_fwd(L, cfg, phi, xM, nb, mu, M_units, zetaP);
+    if (em != cudaErrorNotSupported) return em;
+  }
 #define X(NI, H1, H2, NO_)                                                                       \
   if (mlp3_match(cfg, NI, H1, H2, NO_)) {                                                        \
     int64_t blocks = ((nb + MLP3_BS - 1) / MLP3_BS) * (M_units > 0 ? M_units : 1);               \
@@ -1715,6 +1719,10 @@ bool mlp_supports_pbm(const hvi_desc* d) {
 template <typename T>
 cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, const T* mubar, int64_t nb,
                            double* part, int* nblk_out, int nblk_max, int M_units, const T* zetaP, double* part_x) {
+  if constexpr (sizeof(T) == 4) {
+    const cudaError_t em = launch_mlp3_mma_bwd(L, cfg, phi, xM, mubar, nb, part, nblk_out, nblk_max, M_units, zetaP, part_x);
+    if (em != cudaErrorNotSupported) return em;
+  }
 #define X(NI, H1, H2, NO_)                                                                                   \
   if (mlp3_match(cfg, NI, H1, H2, NO_)) {                                                                    \
     using N = Mlp3<T, NI, H1, H2, NO_>;                                                                      \
