@@ -70,6 +70,8 @@ SYMBOLS = [
     ("hvi_utri2vec_pos", _I64, [_I64, _I64]),
     ("hvi_cor_count", _I64, [C.POINTER(_I32), _I32]),
     ("hvi_plan_set_data", _INT, [_P, _I64, _P, _P, _P, _P, _INT]),
+    ("hvi_plan_prefetch_data", _INT, [_P, _I64, _P, _P, _P, _P]),
+    ("hvi_plan_commit_data", _INT, [_P]),
     ("hvi_plan_set_sites", _INT, [_P, C.POINTER(_I64), _I64]),
     ("hvi_neg_elbo_grad", _INT, [_P, _I32, _P, _P, _P, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_rng", _INT, [_P, _I32, _P, _U64, _I64, _INT, _DP, _DP, _P]),

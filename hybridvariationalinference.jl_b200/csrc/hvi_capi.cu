@@ -6,6 +6,7 @@
 
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "hvi_internal.cuh"
@@ -28,6 +29,13 @@ struct hvi_plan {
   void* d_xP;   // raw drivers (2 n_obs x nb), kept for the prediction path
   int64_t* d_isites;   // MeanVarSep: global site index of every site of the batch (NULL: identity)
   int has_obs;
+  // next batch being uploaded by hvi_plan_prefetch_data while the current one is evaluated
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_copied;
+  void *d_xM_next, *d_xP_next;
+  int64_t cap_cur, cap_next;   // capacity in sites of (d_xM, d_xP) and of their _next twins
+  int64_t nb_next;             // > 0: a prefetched batch is pending
+  int has_obs_next;
   double const_nly;
   int64_t anomalies;
   // per-evaluation scratch
@@ -227,6 +235,8 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   fill_cfg<float>(*desc, p->cf);
   fill_cfg<double>(*desc, p->cd);
   p->nb = 0; p->launches = 0;
+  p->copy_stream = nullptr; p->ev_copied = nullptr; p->d_xM_next = p->d_xP_next = nullptr;
+  p->cap_cur = p->cap_next = p->nb_next = 0; p->has_obs_next = 0;
   p->d_xM = p->d_rec = p->d_mu = p->d_mubar = nullptr; p->d_xP = nullptr; p->has_obs = 0; p->d_isites = nullptr;
   p->d_phi = p->d_zP = p->d_zMs = p->d_ec = p->d_pdraw = nullptr;
   p->cap_zP = p->cap_zMs = p->cap_pdraw = 0;
@@ -279,7 +289,9 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   if (!p) return HVI_OK;
   cudaSetDevice(p->desc.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
-  void* dev[] = {p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
+  if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
+  if (p->ev_copied) cudaEventDestroy(p->ev_copied);
+  void* dev[] = {p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
                  p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide, p->d_wide_bwd, p->d_gacc, p->d_wide_cache};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
@@ -367,38 +379,32 @@ static cudaError_t copy_in(void* dst, const void* src, size_t bytes, int mem_kin
 
 static int ensure(hvi_plan* p, void** buf, int64_t* cap, int64_t need_bytes);
 
+// (re)allocate the per-batch buffers for nb sites; keep_raw: d_xM/d_xP already hold the batch (commit of a prefetch)
 template <typename T>
-static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, const void* y_o, const void* y_unc,
-                      int mem_kind) {
+static int alloc_batch(hvi_plan* p, int64_t nb, bool keep_raw) {
   const int nO = p->desc.n_obs, nC = p->desc.n_covar, nM = p->desc.n_M;
-  if (nb != p->nb) {
-    for (void** q : {&p->d_xM, &p->d_rec, &p->d_mu, &p->d_mubar, &p->d_xP}) { if (*q) cudaFree(*q); *q = nullptr; }
-    p->nb = 0;
-    const int64_t ntiles = (nb + 31) / 32;
+  if (nb == p->nb && (keep_raw || p->cap_cur >= nb)) return HVI_OK;
+  for (void** q : {&p->d_rec, &p->d_mu, &p->d_mubar}) { if (*q) cudaFree(*q); *q = nullptr; }
+  p->nb = 0;
+  const int64_t ntiles = (nb + 31) / 32;
+  if (!keep_raw) {
+    for (void** q : {&p->d_xM, &p->d_xP}) { if (*q) cudaFree(*q); *q = nullptr; }
+    p->cap_cur = 0;
     CU(p, cudaMalloc(&p->d_xM, sizeof(T) * (size_t)nC * nb));
-    CU(p, cudaMalloc(&p->d_rec, sizeof(T) * (size_t)ntiles * 32 * 4 * nO));
-    CU(p, cudaMalloc(&p->d_mu, sizeof(T) * (size_t)nM * nb));
-    CU(p, cudaMalloc(&p->d_mubar, sizeof(T) * (size_t)nM * nb));
     CU(p, cudaMalloc(&p->d_xP, sizeof(T) * (size_t)2 * nO * nb));
-    p->nb = nb;
+    p->cap_cur = nb;
   }
-  CU(p, copy_in(p->d_xM, xM, sizeof(T) * (size_t)nC * nb, mem_kind, p->stream));
-  const T *dxP = (const T*)xP, *dyo = (const T*)y_o, *dyu = (const T*)y_unc;
-  {
-    const size_t n1 = (size_t)2 * nO * nb, n2 = (size_t)nO * nb;
-    CU(p, copy_in(p->d_xP, xP, sizeof(T) * n1, mem_kind, p->stream));
-    dxP = (const T*)p->d_xP;
-    p->has_obs = (y_o && y_unc) ? 1 : 0;
-    if (mem_kind == HVI_MEM_HOST && p->has_obs) {
-      int rc = ensure(p, &p->d_stage, &p->cap_stage, (int64_t)(sizeof(T) * 2 * n2));
-      if (rc) return rc;
-      T* t = (T*)p->d_stage;
-      CU(p, copy_in(t, y_o, sizeof(T) * n2, mem_kind, p->stream));
-      CU(p, copy_in(t + n2, y_unc, sizeof(T) * n2, mem_kind, p->stream));
-      dyo = t; dyu = t + n2;
-    }
-    if (!p->has_obs) { dyo = nullptr; dyu = nullptr; }
-  }
+  CU(p, cudaMalloc(&p->d_rec, sizeof(T) * (size_t)ntiles * 32 * 4 * nO));
+  CU(p, cudaMalloc(&p->d_mu, sizeof(T) * (size_t)nM * nb));
+  CU(p, cudaMalloc(&p->d_mubar, sizeof(T) * (size_t)nM * nb));
+  p->nb = nb;
+  return HVI_OK;
+}
+
+// re-tile the raw batch on the device (k_preprocess) and fetch the two batch constants
+template <typename T>
+static int finish_batch(hvi_plan* p, int64_t nb, const T* dxP, const T* dyo, const T* dyu) {
+  const int nO = p->desc.n_obs;
   Launch L{p->stream, p->sm_count, &p->launches};
   int nrows = 0;
   // the stream partial buffer doubles as scratch for the 2·nwarps preprocess partials
@@ -414,6 +420,86 @@ static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, c
   return HVI_OK;
 }
 
+template <typename T>
+static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, const void* y_o, const void* y_unc,
+                      int mem_kind) {
+  const int nO = p->desc.n_obs, nC = p->desc.n_covar;
+  if (p->nb_next > 0) {   // a pending prefetch shares the staging buffer: drop it
+    CU(p, cudaStreamSynchronize(p->copy_stream));
+    p->nb_next = 0;
+  }
+  int rc = alloc_batch<T>(p, nb, false);
+  if (rc) return rc;
+  CU(p, copy_in(p->d_xM, xM, sizeof(T) * (size_t)nC * nb, mem_kind, p->stream));
+  const T *dxP = (const T*)xP, *dyo = (const T*)y_o, *dyu = (const T*)y_unc;
+  {
+    const size_t n1 = (size_t)2 * nO * nb, n2 = (size_t)nO * nb;
+    CU(p, copy_in(p->d_xP, xP, sizeof(T) * n1, mem_kind, p->stream));
+    dxP = (const T*)p->d_xP;
+    p->has_obs = (y_o && y_unc) ? 1 : 0;
+    if (mem_kind == HVI_MEM_HOST && p->has_obs) {
+      rc = ensure(p, &p->d_stage, &p->cap_stage, (int64_t)(sizeof(T) * 2 * n2));
+      if (rc) return rc;
+      T* t = (T*)p->d_stage;
+      CU(p, copy_in(t, y_o, sizeof(T) * n2, mem_kind, p->stream));
+      CU(p, copy_in(t + n2, y_unc, sizeof(T) * n2, mem_kind, p->stream));
+      dyo = t; dyu = t + n2;
+    }
+    if (!p->has_obs) { dyo = nullptr; dyu = nullptr; }
+  }
+  return finish_batch<T>(p, nb, dxP, dyo, dyu);
+}
+
+// upload of the NEXT batch on the plan's copy stream; nothing of the current batch is touched
+template <typename T>
+static int prefetch_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, const void* y_o, const void* y_unc) {
+  const int nO = p->desc.n_obs, nC = p->desc.n_covar;
+  if (!p->copy_stream) CU(p, cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+  if (!p->ev_copied) CU(p, cudaEventCreateWithFlags(&p->ev_copied, cudaEventDisableTiming));
+  if (p->nb_next > 0) CU(p, cudaStreamSynchronize(p->copy_stream));   // replaces a batch that was never committed
+  p->nb_next = 0;
+  if (p->cap_next < nb) {
+    for (void** q : {&p->d_xM_next, &p->d_xP_next}) { if (*q) cudaFree(*q); *q = nullptr; }
+    p->cap_next = 0;
+    CU(p, cudaMalloc(&p->d_xM_next, sizeof(T) * (size_t)nC * nb));
+    CU(p, cudaMalloc(&p->d_xP_next, sizeof(T) * (size_t)2 * nO * nb));
+    p->cap_next = nb;
+  }
+  const size_t n1 = (size_t)2 * nO * nb, n2 = (size_t)nO * nb;
+  p->has_obs_next = (y_o && y_unc) ? 1 : 0;
+  cudaStream_t cs = p->copy_stream;
+  CU(p, cudaMemcpyAsync(p->d_xM_next, xM, sizeof(T) * (size_t)nC * nb, cudaMemcpyHostToDevice, cs));
+  CU(p, cudaMemcpyAsync(p->d_xP_next, xP, sizeof(T) * n1, cudaMemcpyHostToDevice, cs));
+  if (p->has_obs_next) {
+    // the staging buffer is free: every k_preprocess that read it has completed (set_data / commit_data synchronise)
+    int rc = ensure(p, &p->d_stage, &p->cap_stage, (int64_t)(sizeof(T) * 2 * n2));
+    if (rc) return rc;
+    T* t = (T*)p->d_stage;
+    CU(p, cudaMemcpyAsync(t, y_o, sizeof(T) * n2, cudaMemcpyHostToDevice, cs));
+    CU(p, cudaMemcpyAsync(t + n2, y_unc, sizeof(T) * n2, cudaMemcpyHostToDevice, cs));
+  }
+  CU(p, cudaEventRecord(p->ev_copied, cs));
+  p->nb_next = nb;
+  return HVI_OK;
+}
+
+template <typename T>
+static int commit_t(hvi_plan* p) {
+  const int nO = p->desc.n_obs;
+  const int64_t nb = p->nb_next;
+  CU(p, cudaStreamWaitEvent(p->stream, p->ev_copied, 0));
+  std::swap(p->d_xM, p->d_xM_next);
+  std::swap(p->d_xP, p->d_xP_next);
+  std::swap(p->cap_cur, p->cap_next);
+  p->nb_next = 0;
+  int rc = alloc_batch<T>(p, nb, true);
+  if (rc) return rc;
+  p->has_obs = p->has_obs_next;
+  const T* t = (const T*)p->d_stage;
+  const size_t n2 = (size_t)nO * nb;
+  return finish_batch<T>(p, nb, (const T*)p->d_xP, p->has_obs ? t : nullptr, p->has_obs ? t + n2 : nullptr);
+}
+
 extern "C" int hvi_plan_set_data(hvi_plan* p, int64_t n_site, const void* xM, const void* xP, const void* y_o,
                                  const void* y_unc, int mem_kind) {
   if (!p) return HVI_EINVAL;
@@ -425,6 +511,24 @@ extern "C" int hvi_plan_set_data(hvi_plan* p, int64_t n_site, const void* xM, co
   if (p->d_isites) { cudaFree(p->d_isites); p->d_isites = nullptr; }   // back to the identity map
   return p->dtype == HVI_F32 ? set_data_t<float>(p, n_site, xM, xP, y_o, y_unc, mem_kind)
                              : set_data_t<double>(p, n_site, xM, xP, y_o, y_unc, mem_kind);
+}
+
+extern "C" int hvi_plan_prefetch_data(hvi_plan* p, int64_t n_site, const void* xM, const void* xP, const void* y_o,
+                                      const void* y_unc) {
+  if (!p) return HVI_EINVAL;
+  if (n_site < 1 || !xM || !xP) PLAN_FAIL(p, HVI_EINVAL, "prefetch_data: n_site must be >= 1 and xM, xP non-NULL");
+  if ((y_o == nullptr) != (y_unc == nullptr)) PLAN_FAIL(p, HVI_EINVAL, "prefetch_data: y_o and y_unc must both be given or both be NULL");
+  CU(p, cudaSetDevice(p->desc.device));
+  if (p->cf.sepvar && n_site > p->cf.n_site_total) PLAN_FAIL(p, HVI_EINVAL, "prefetch_data: batch has more sites than n_site_total");
+  return p->dtype == HVI_F32 ? prefetch_t<float>(p, n_site, xM, xP, y_o, y_unc) : prefetch_t<double>(p, n_site, xM, xP, y_o, y_unc);
+}
+
+extern "C" int hvi_plan_commit_data(hvi_plan* p) {
+  if (!p) return HVI_EINVAL;
+  if (p->nb_next <= 0) PLAN_FAIL(p, HVI_ENODATA, "commit_data: no prefetched batch (call hvi_plan_prefetch_data first)");
+  CU(p, cudaSetDevice(p->desc.device));
+  if (p->d_isites) { cudaFree(p->d_isites); p->d_isites = nullptr; }   // back to the identity map
+  return p->dtype == HVI_F32 ? commit_t<float>(p) : commit_t<double>(p);
 }
 
 static int ensure(hvi_plan* p, void** buf, int64_t* cap, int64_t need_bytes) {

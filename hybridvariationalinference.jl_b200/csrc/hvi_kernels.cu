@@ -1641,7 +1641,7 @@ template cudaError_t launch_predict<double>(const Launch&, const Cfg<double>&, c
   } while (0)
 
 int stream_max_rows(int sm_count) { return sm_count * 8 * (STREAM_THREADS_MAX / 32); }
-int mlp_bwd_max_blocks(int sm_count) { return sm_count * 3; }
+int mlp_bwd_max_blocks(int sm_count) { return sm_count * 4; }
 
 template <typename T>
 cudaError_t launch_preprocess(const Launch& L, int nO, int64_t nb, const T* xP, const T* y_o, const T* y_unc, T* rec,

@@ -367,7 +367,7 @@ __device__ __forceinline__ float gather_out(const float (&z3)[4], int lane) {
 }
 
 template <int NI, int H1, int H2, int NOUT>
-__global__ void __launch_bounds__(MMA_BS, 3) k_mlp3_mma_fwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ phi,
+__global__ void __launch_bounds__(MMA_BS, 4) k_mlp3_mma_fwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ phi,
                                                              const float* __restrict__ xM, const float* __restrict__ zetaP,
                                                              int M_units, int64_t nb, float* __restrict__ mu) {
   using N = MlpMma<NI, H1, H2, NOUT>;
@@ -653,7 +653,7 @@ cudaError_t launch_mlp3_mma_fwd(const Launch& L, const Cfg<float>& cfg, const fl
   if (mma_match(cfg, NI, H1, H2, NO_)) {                                                                    \
     const int64_t ntot = ((nb + 15) / 16) * (M_units > 0 ? M_units : 1);                                    \
     int64_t blocks = (ntot + MMA_NW - 1) / MMA_NW;                                                          \
-    if (blocks > (int64_t)L.sm_count * 3) blocks = (int64_t)L.sm_count * 3;                                 \
+    if (blocks > (int64_t)L.sm_count * 4) blocks = (int64_t)L.sm_count * 4;                                 \
     k_mlp3_mma_fwd<NI, H1, H2, NO_><<<(int)blocks, MMA_BS, 0, L.stream>>>(cfg, phi, xM, zetaP, M_units, nb, mu); \
     HVI_MMA_CHECK();                                                                                        \
     return cudaSuccess;                                                                                     \

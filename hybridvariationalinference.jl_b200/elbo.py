@@ -140,6 +140,26 @@ class NegElboPlan:
             idx = np.ascontiguousarray(i_sites, dtype=np.int64)
             self._check(self.lib.hvi_plan_set_sites(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
 
+    def prefetch_data(self, xM, xP, y_o=None, y_unc=None):
+        """Start the upload of the NEXT batch (host arrays, ideally page-locked) while the current one is
+        evaluated -- the DataLoader iteration of `solve` (src/HybridSolver.jl:240-260) double-buffered.
+        `commit_data()` makes it the current batch.  The arrays must stay unchanged until then."""
+        f = lambda a: None if a is None else np.asfortranarray(a, dtype=self.dt)
+        args = tuple(map(f, (xM, xP, y_o, y_unc)))
+        n_site = args[0].shape[1]
+        assert args[1].shape == (2 * self.prob.n_obs, n_site) and args[0].shape[0] == self.prob.n_covar
+        if args[2] is not None:
+            assert args[2].shape == (self.prob.n_obs, n_site) and args[3].shape == args[2].shape
+        self._keep_next = (args, n_site)
+        self._check(self.lib.hvi_plan_prefetch_data(self._h, n_site, *map(_ptr, args)))
+
+    def commit_data(self, i_sites=None):
+        self._check(self.lib.hvi_plan_commit_data(self._h))
+        self._keep, self.n_site = self._keep_next
+        if i_sites is not None:
+            idx = np.ascontiguousarray(i_sites, dtype=np.int64)
+            self._check(self.lib.hvi_plan_set_sites(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
+
     # -- the hot path ----------------------------------------------------------------------
     def neg_elbo_withgradient(self, ϕ, zP=None, zMs=None, *, n_MC=None, seed=None, site_offset=0,
                               want_grad=True, allow_nonfinite=False):

@@ -133,6 +133,16 @@ int64_t hvi_cor_count(const int32_t* cor_ends, int32_t n_cor_ends);
 int hvi_plan_set_data(hvi_plan* plan, int64_t n_site, const void* xM, const void* xP,
                       const void* y_o, const void* y_unc, int mem_kind);
 
+/* Double-buffered registration for a minibatch loop (the DataLoader iteration of src/HybridSolver.jl:240-260):
+ * hvi_plan_prefetch_data starts the upload of the NEXT batch from HOST memory on the plan's copy stream and returns
+ * at once, so the transfer runs while the current batch is evaluated; hvi_plan_commit_data makes it the current
+ * batch (waits for the upload, re-tiles it).  The host arrays must stay valid and unchanged until commit_data
+ * returns; page-locked memory is needed for the copy to be asynchronous.  Evaluations between the two calls still
+ * use the current batch.  A plain hvi_plan_set_data drops a pending prefetch. */
+int hvi_plan_prefetch_data(hvi_plan* plan, int64_t n_site, const void* xM, const void* xP,
+                           const void* y_o, const void* y_unc);
+int hvi_plan_commit_data(hvi_plan* plan);
+
 /* MeanVarSep only: the 0-based indices (into 0..n_site_total) of the registered batch's sites -- the
  * `i_sites` argument of loss_elbo (src/HybridSolver.jl:312-322, src/elbo_sepvec.jl:23).  Host array of
  * length n_site; default after set_data is 0..n_site-1. */
