@@ -338,7 +338,7 @@ int FN(hvi_oracle_neg_elbo_grad)(const hvi_desc* d, int64_t nb, int M, const rea
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
-#pragma omp parallel
+#pragma omp parallel private(m, k, j, jj)
   {
     double* Gt = (double*)calloc((size_t)L.nphi, sizeof(double));
     double* zPb = (double*)calloc((size_t)((nP + 1) * M), sizeof(double));

@@ -91,3 +91,17 @@ def test_meanvarsep_c_restatement_matches_autograd():
     touched = np.zeros(len(r), bool)
     touched[(i_sites[:, None] * 2 + np.arange(2)).ravel()] = True
     assert np.all(g[r][~touched] == 0) and np.all(g[r][touched] != 0)
+
+
+def test_threads_agree():
+    """the OpenMP site loop must give the single-thread result (loop counters private, per-thread accumulators)"""
+    for scen in ((), ("covarK2",)):
+        prob = hvi_b200.DoubleMMCase(scen, dtype="f64")
+        n, M = 1500, 8
+        data = hvi_b200.gen_hybridproblem_synthetic(prob, n, seed=5)
+        zP, zMs = hvi_b200.draw_ξ(prob, n, M)
+        ϕ = prob.init_ϕ(perturbed=True)
+        nL1, c1, g1 = c_oracle_value_and_grad(prob, ϕ, data, zP, zMs, nthreads=1)
+        nL4, c4, g4 = c_oracle_value_and_grad(prob, ϕ, data, zP, zMs, nthreads=4)
+        assert abs(nL1 - nL4) <= 1e-12 * abs(nL1)
+        assert np.max(np.abs(g1 - g4)) <= 1e-12 * np.max(np.abs(g1))
