@@ -113,11 +113,12 @@ mutable struct Plan
     h::Ptr{Cvoid}
     n_phi::Int
     FT::DataType
+    next_batch::Any   # host arrays of a prefetched batch, kept alive until commit_data!
     function Plan(desc::hvi_desc)
         ref = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:hvi_plan_create, libhvi), Cint, (Ref{hvi_desc}, Ref{Ptr{Cvoid}}), desc, ref)
         rc == 0 || error("hvi_plan_create: " * unsafe_string(ccall((:hvi_last_error, libhvi), Cstring, (Ptr{Cvoid},), C_NULL)))
-        p = new(ref[], ccall((:hvi_phi_len, libhvi), Int64, (Ptr{Cvoid},), ref[]), desc.dtype == 0 ? Float32 : Float64)
+        p = new(ref[], ccall((:hvi_phi_len, libhvi), Int64, (Ptr{Cvoid},), ref[]), desc.dtype == 0 ? Float32 : Float64, nothing)
         finalizer(q -> ccall((:hvi_plan_destroy, libhvi), Cint, (Ptr{Cvoid},), q.h), p)
     end
 end
@@ -132,6 +133,15 @@ function set_data!(p::Plan, xM::Matrix{T}, xP::Matrix{T}, y_o::Matrix{T}, y_unc:
 end
 
 "value, six components and gradient; ξ drawn on the device from `seed` (cf. ext/…CUDAExt.jl:82-86)"
+# double-buffered registration: upload the next DataLoader element while the current one is evaluated
+function prefetch_data!(p::Plan, xM::Matrix{T}, xP::Matrix{T}, y_o::Matrix{T}, y_unc::Matrix{T}) where {T}
+    p.next_batch = (xM, xP, y_o, y_unc)   # keep the host arrays alive and untouched until commit_data!
+    check(p, ccall((:hvi_plan_prefetch_data, libhvi), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{T}),
+        p.h, size(xM, 2), xM, xP, y_o, y_unc))
+end
+commit_data!(p::Plan) = check(p, ccall((:hvi_plan_commit_data, libhvi), Cint, (Ptr{Cvoid},), p.h))
+
 function neg_elbo_withgradient(p::Plan, ϕ::Vector{T}, n_MC::Integer, seed::Integer) where {T}
     comps = zeros(Float64, 6); nL = Ref(0.0); grad = similar(ϕ)
     check(p, ccall((:hvi_neg_elbo_grad_rng, libhvi), Cint,
