@@ -76,6 +76,11 @@ SYMBOLS = [
     ("hvi_neg_elbo_grad", _INT, [_P, _I32, _P, _P, _P, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_rng", _INT, [_P, _I32, _P, _U64, _I64, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_async", _INT, [_P, _I32, _P, _P, _P, _U64, _I64, _P, _P]),
+    ("hvi_adam_init", _INT, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double]),
+    ("hvi_adam_run", _INT, [_P, _I32, _I32, _U64, _I64, _DP]),
+    ("hvi_adam_apply_dev", _INT, [_P, _P, _P]),
+    ("hvi_adam_phi_dev", _INT, [_P, C.POINTER(_P)]),
+    ("hvi_adam_get_phi", _INT, [_P, _P]),
     ("hvi_generate_zeta", _INT, [_P, _I32, _P, _P, _P, _INT, _P, _P, _P]),
     ("hvi_predict", _INT, [_P, _I32, _P, _P, _P, _U64, _I64, _INT, _P, _P, _P, _DP]),
     ("hvi_apply_g", _INT, [_P, _P, _INT, _P]),

@@ -62,6 +62,9 @@ struct hvi_plan {
   void* d_grad;
   double* h_out;  // pinned
   void* h_grad;   // pinned
+  // device-resident Adam state (hvi_adam_*): ϕ in the working type, moments in double
+  void* d_phi_opt; double *d_adam_m, *d_adam_v, *d_trace; int64_t cap_trace;
+  double adam_eta, adam_b1, adam_b2, adam_eps; int64_t adam_t;
   // optional per-kernel timing (CUDA events on the launching stream)
   int profiling;
   cudaEvent_t ev[8];
@@ -235,6 +238,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   fill_cfg<float>(*desc, p->cf);
   fill_cfg<double>(*desc, p->cd);
   p->nb = 0; p->launches = 0;
+  p->d_phi_opt = nullptr; p->d_adam_m = p->d_adam_v = p->d_trace = nullptr; p->cap_trace = 0; p->adam_t = 0;
   p->copy_stream = nullptr; p->ev_copied = nullptr; p->d_xM_next = p->d_xP_next = nullptr;
   p->cap_cur = p->cap_next = p->nb_next = 0; p->has_obs_next = 0;
   p->d_xM = p->d_rec = p->d_mu = p->d_mubar = nullptr; p->d_xP = nullptr; p->has_obs = 0; p->d_isites = nullptr;
@@ -291,7 +295,7 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->ev_copied) cudaEventDestroy(p->ev_copied);
-  void* dev[] = {p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
+  void* dev[] = {p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->d_trace, p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
                  p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide, p->d_wide_bwd, p->d_gacc, p->d_wide_cache};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
@@ -1030,5 +1034,123 @@ extern "C" int hvi_gemm_bf3(int32_t device, int32_t mode, int64_t M, int32_t N, 
   if (e == cudaSuccess) e = cudaMemcpy(C, dC, sizeof(float) * (size_t)M * N, cudaMemcpyDeviceToHost);
   for (float* q : {dA, dB, db, dH, dC}) if (q) cudaFree(q);
   if (e != cudaSuccess) { g_create_err = std::string("hvi_gemm_bf3: ") + cudaGetErrorString(e); return HVI_ECUDA; }
+  return HVI_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Device-resident optimiser steps: Optimization.solve(optprob, Adam(η); …) of
+// src/HybridSolver.jl:259-260 without the host round trip per iteration.  The update is the
+// Optimisers.jl Adam rule: m ← β1 m + (1−β1) g, v ← β2 v + (1−β2) g², ϕ ← ϕ − η·m̂/(√v̂ + ε).
+// An iteration whose value or gradient is not finite leaves ϕ, m, v untouched (the reference
+// raises there) and is visible as a non-finite entry of the loss trace.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_adam(int64_t n, const double* __restrict__ out, T* __restrict__ phi,
+                                              double* __restrict__ m, double* __restrict__ v, double eta, double b1,
+                                              double b2, double eps, double c1, double c2, double* __restrict__ trace,
+                                              int64_t it) {
+  const bool bad = out[n + 7] != 0.0 || !isfinite(out[n + 6]);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && trace) trace[it] = bad ? nan("") : out[n + 6];
+  if (bad) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double g = out[i];
+    const double mi = b1 * m[i] + (1.0 - b1) * g, vi = b2 * v[i] + (1.0 - b2) * g * g;
+    m[i] = mi; v[i] = vi;
+    phi[i] = (T)((double)phi[i] - eta * (mi * c1) / (sqrt(vi * c2) + eps));
+  }
+}
+
+template <typename T>
+static int adam_apply_t(hvi_plan* p, const double* out_dev, cudaStream_t s, int64_t it_in_trace, bool trace) {
+  const int64_t n = cfg_of<T>(p).nphi;
+  p->adam_t += 1;
+  const double c1 = 1.0 / (1.0 - pow(p->adam_b1, (double)p->adam_t)), c2 = 1.0 / (1.0 - pow(p->adam_b2, (double)p->adam_t));
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > p->sm_count * 8) blocks = p->sm_count * 8;
+  k_adam<T><<<blocks, 256, 0, s>>>(n, out_dev, (T*)p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->adam_eta, p->adam_b1, p->adam_b2,
+                                  p->adam_eps, c1, c2, trace ? p->d_trace : nullptr, it_in_trace);
+  CU(p, cudaGetLastError());
+  ++p->launches;
+  return HVI_OK;
+}
+
+extern "C" int hvi_adam_init(hvi_plan* p, const void* phi0, double eta, double beta1, double beta2, double eps) {
+  if (!p) return HVI_EINVAL;
+  if (!phi0 || !(eta > 0) || !(beta1 >= 0 && beta1 < 1) || !(beta2 >= 0 && beta2 < 1) || !(eps > 0))
+    PLAN_FAIL(p, HVI_EINVAL, "adam_init: need phi0, eta > 0, 0 <= beta < 1, eps > 0");
+  CU(p, cudaSetDevice(p->desc.device));
+  const size_t n = (size_t)p->cf.nphi;
+  if (!p->d_phi_opt) {
+    CU(p, cudaMalloc(&p->d_phi_opt, p->es * n));
+    CU(p, cudaMalloc((void**)&p->d_adam_m, sizeof(double) * n));
+    CU(p, cudaMalloc((void**)&p->d_adam_v, sizeof(double) * n));
+  }
+  CU(p, cudaMemcpyAsync(p->d_phi_opt, phi0, p->es * n, cudaMemcpyHostToDevice, p->stream));
+  CU(p, cudaMemsetAsync(p->d_adam_m, 0, sizeof(double) * n, p->stream));
+  CU(p, cudaMemsetAsync(p->d_adam_v, 0, sizeof(double) * n, p->stream));
+  CU(p, cudaStreamSynchronize(p->stream));
+  p->adam_eta = eta; p->adam_b1 = beta1; p->adam_b2 = beta2; p->adam_eps = eps; p->adam_t = 0;
+  return HVI_OK;
+}
+
+template <typename T>
+static int adam_run_t(hvi_plan* p, int n_iter, int M, uint64_t seed0, int64_t site_offset, double* trace_host) {
+  const Cfg<T>& cfg = cfg_of<T>(p);
+  cudaStream_t s = p->stream;
+  int rc = ensure(p, (void**)&p->d_trace, &p->cap_trace, (int64_t)sizeof(double) * n_iter);
+  if (rc) return rc;
+  const int64_t nzP = (int64_t)M * (cfg.nP > 0 ? cfg.nP : 1);
+  rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)sizeof(T) * nzP);
+  if (rc) return rc;
+  Launch L{s, p->sm_count, &p->launches};
+  for (int it = 0; it < n_iter; it++) {
+    const uint64_t seed = seed0 + (uint64_t)it;
+    CU(p, launch_gen_normal<T>(L, (T*)p->d_zP, cfg.nP, M, seed, (int64_t)1 << 62));
+    rc = enqueue_eval<T>(p, M, (const T*)p->d_phi_opt, (const T*)p->d_zP, nullptr, p->d_out, nullptr, s, true, seed, site_offset);
+    if (rc) return rc;
+    rc = adam_apply_t<T>(p, p->d_out, s, it, true);
+    if (rc) return rc;
+  }
+  if (trace_host) {
+    CU(p, cudaMemcpyAsync(trace_host, p->d_trace, sizeof(double) * n_iter, cudaMemcpyDeviceToHost, s));
+    CU(p, cudaStreamSynchronize(s));
+  }
+  return HVI_OK;
+}
+
+extern "C" int hvi_adam_run(hvi_plan* p, int32_t n_iter, int32_t n_MC, uint64_t seed0, int64_t site_offset,
+                            double* nL_trace) {
+  if (!p) return HVI_EINVAL;
+  if (!p->d_phi_opt) PLAN_FAIL(p, HVI_EINVAL, "adam_run: call hvi_adam_init first");
+  if (p->nb <= 0) PLAN_FAIL(p, HVI_ENODATA, "hvi_plan_set_data has not been called");
+  if (n_iter < 1 || n_MC < 1) PLAN_FAIL(p, HVI_EINVAL, "adam_run: n_iter and n_MC must be >= 1");
+  CU(p, cudaSetDevice(p->desc.device));
+  return p->dtype == HVI_F32 ? adam_run_t<float>(p, n_iter, n_MC, seed0, site_offset, nL_trace)
+                             : adam_run_t<double>(p, n_iter, n_MC, seed0, site_offset, nL_trace);
+}
+
+extern "C" int hvi_adam_apply_dev(hvi_plan* p, const double* out_dev, void* cuda_stream) {
+  if (!p) return HVI_EINVAL;
+  if (!p->d_phi_opt) PLAN_FAIL(p, HVI_EINVAL, "adam_apply_dev: call hvi_adam_init first");
+  if (!out_dev) PLAN_FAIL(p, HVI_EINVAL, "adam_apply_dev: out_dev is NULL");
+  CU(p, cudaSetDevice(p->desc.device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  return p->dtype == HVI_F32 ? adam_apply_t<float>(p, out_dev, s, 0, false) : adam_apply_t<double>(p, out_dev, s, 0, false);
+}
+
+extern "C" int hvi_adam_phi_dev(hvi_plan* p, void** phi_dev) {
+  if (!p || !phi_dev) return HVI_EINVAL;
+  if (!p->d_phi_opt) PLAN_FAIL(p, HVI_EINVAL, "adam_phi_dev: call hvi_adam_init first");
+  *phi_dev = p->d_phi_opt;
+  return HVI_OK;
+}
+
+extern "C" int hvi_adam_get_phi(hvi_plan* p, void* phi_host) {
+  if (!p || !phi_host) return HVI_EINVAL;
+  if (!p->d_phi_opt) PLAN_FAIL(p, HVI_EINVAL, "adam_get_phi: call hvi_adam_init first");
+  CU(p, cudaSetDevice(p->desc.device));
+  CU(p, cudaMemcpyAsync(phi_host, p->d_phi_opt, p->es * (size_t)p->cf.nphi, cudaMemcpyDeviceToHost, p->stream));
+  CU(p, cudaStreamSynchronize(p->stream));
   return HVI_OK;
 }

@@ -160,6 +160,26 @@ class NegElboPlan:
             idx = np.ascontiguousarray(i_sites, dtype=np.int64)
             self._check(self.lib.hvi_plan_set_sites(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
 
+    # -- optimiser steps on the device -------------------------------------------------------
+    def adam_init(self, ϕ0, eta=0.02, betas=(0.9, 0.999), eps=1e-8):
+        """Device-resident `Adam(eta)` state for `adam_run` (Optimization.solve of src/HybridSolver.jl:259-260)."""
+        ϕ0 = np.ascontiguousarray(ϕ0, dtype=self.dt)
+        assert ϕ0.size == self.prob.n_phi
+        self._check(self.lib.hvi_adam_init(self._h, _ptr(ϕ0), eta, betas[0], betas[1], eps))
+
+    def adam_run(self, n_iter, n_MC, seed0=0, site_offset=0, trace=True):
+        """n_iter iterations of (neg-ELBO gradient with device draws seeded seed0+i, Adam update) on the registered
+        batch without leaving the GPU; returns the loss of every iteration (or None: nothing is synchronised)."""
+        tr = np.empty(n_iter, dtype=np.float64) if trace else None
+        self._check(self.lib.hvi_adam_run(self._h, n_iter, n_MC, seed0, site_offset,
+                                          tr.ctypes.data_as(C.POINTER(C.c_double)) if trace else None))
+        return tr
+
+    def adam_phi(self):
+        ϕ = np.empty(self.prob.n_phi, dtype=self.dt)
+        self._check(self.lib.hvi_adam_get_phi(self._h, _ptr(ϕ)))
+        return ϕ
+
     # -- the hot path ----------------------------------------------------------------------
     def neg_elbo_withgradient(self, ϕ, zP=None, zMs=None, *, n_MC=None, seed=None, site_offset=0,
                               want_grad=True, allow_nonfinite=False):

@@ -175,6 +175,22 @@ int hvi_neg_elbo_grad_async(hvi_plan* plan, int32_t n_MC, const void* phi_dev,
                             const void* zP_dev, const void* zMs_dev, uint64_t seed,
                             int64_t site_offset, double* out_dev, void* cuda_stream);
 
+/* ---- optimiser steps on the device -------------------------------------- */
+/* Optimization.solve(optprob, Adam(η); …) of src/HybridSolver.jl:259-260 without the host round trip per
+ * iteration: ϕ, the Adam moments and the gradient stay in HBM; the update is the Optimisers.jl Adam rule.
+ * hvi_adam_init uploads ϕ0 (host) and resets the moments.  hvi_adam_run enqueues n_iter iterations on the
+ * registered batch back to back -- iteration i draws with seed0 + i -- and, if nL_trace (host, n_iter doubles)
+ * is given, returns the loss of every iteration (NaN marks an iteration that was skipped because its value or
+ * gradient was not finite); with nL_trace = NULL nothing is synchronised.  hvi_adam_get_phi downloads ϕ.
+ * Multi-GPU: evaluate with hvi_neg_elbo_grad_async on phi = *hvi_adam_phi_dev, all-reduce out_dev, then
+ * hvi_adam_apply_dev(out_dev) on every rank (identical updates, ϕ stays replicated). */
+int hvi_adam_init(hvi_plan* plan, const void* phi0, double eta, double beta1, double beta2, double eps);
+int hvi_adam_run(hvi_plan* plan, int32_t n_iter, int32_t n_MC, uint64_t seed0, int64_t site_offset,
+                 double* nL_trace);
+int hvi_adam_apply_dev(hvi_plan* plan, const double* out_dev, void* cuda_stream);
+int hvi_adam_phi_dev(hvi_plan* plan, void** phi_dev);
+int hvi_adam_get_phi(hvi_plan* plan, void* phi_host);
+
 /* generate_ζ (src/elbo.jl:472-521) forward only: ζsP (n_P x n_MC), ζsMs_tr
  * (n_site x n_M x n_MC), σ (n_P + n_M n_site).  Used by sample_posterior (:432-458). */
 int hvi_generate_zeta(hvi_plan* plan, int32_t n_MC, const void* phi, const void* zP,

@@ -168,6 +168,18 @@ y_unc, i_sites; is_testmode)` with the same signature; its `rrule` hands Zygote 
 computed by the library, so `OptimizationFunction(..., AutoZygote())` (src/HybridSolver.jl:256-258)
 works unchanged.
 """
+"n_iter Adam iterations on the registered batch without leaving the GPU (Optimization.solve with Adam, src/HybridSolver.jl:259-260)"
+function adam_solve!(p::Plan, ϕ0::Vector{T}, n_iter::Integer, n_MC::Integer; eta=0.02, betas=(0.9, 0.999), eps=1e-8, seed0=0) where {T}
+    check(p, ccall((:hvi_adam_init, libhvi), Cint, (Ptr{Cvoid}, Ptr{T}, Cdouble, Cdouble, Cdouble, Cdouble),
+        p.h, ϕ0, eta, betas[1], betas[2], eps))
+    trace = Vector{Float64}(undef, n_iter)
+    check(p, ccall((:hvi_adam_run, libhvi), Cint, (Ptr{Cvoid}, Int32, Int32, UInt64, Int64, Ptr{Float64}),
+        p.h, n_iter, n_MC, seed0, 0, trace))
+    ϕ = similar(ϕ0)
+    check(p, ccall((:hvi_adam_get_phi, libhvi), Cint, (Ptr{Cvoid}, Ptr{T}), p.h, ϕ))
+    ϕ, trace
+end
+
 function get_loss_elbo_b200(prob; scenario=Val(()), n_MC=12, device=0)
     plan = Plan(make_desc(prob; scenario, device))
     last_batch = Ref{Any}(nothing)
