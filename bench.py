@@ -141,6 +141,22 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def bind_to_gpu_numa_node(gpu):
+    """Run this rank on the CPUs next to its GPU, so that the pinned batch buffers are allocated on that NUMA node and the
+    host -> device uploads of the ranks do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(gpu), (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -150,6 +166,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dist = None
     if world > 1:

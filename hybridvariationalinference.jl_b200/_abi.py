@@ -76,6 +76,7 @@ SYMBOLS = [
     ("hvi_neg_elbo_grad", _INT, [_P, _I32, _P, _P, _P, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_rng", _INT, [_P, _I32, _P, _U64, _I64, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_async", _INT, [_P, _I32, _P, _P, _P, _U64, _I64, _P, _P]),
+    ("hvi_loss_gf_grad", _INT, [_P, _P, _INT, _DP, _P]),
     ("hvi_adam_init", _INT, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double]),
     ("hvi_adam_run", _INT, [_P, _I32, _I32, _U64, _I64, _DP]),
     ("hvi_adam_apply_dev", _INT, [_P, _P, _P]),

@@ -1039,6 +1039,64 @@ extern "C" int hvi_gemm_bf3(int32_t device, int32_t mode, int64_t M, int32_t N, 
 
 
 // ---------------------------------------------------------------------------------------
+// Point-solver loss loss_gf (src/gf.jl:227-295) and its gradient w.r.t. ϕ = [ϕg; ϕP]
+// ---------------------------------------------------------------------------------------
+template <typename T>
+static int loss_gf_t(hvi_plan* p, const void* phi_gf, int mem_kind, double comps[3], void* grad) {
+  const Cfg<T>& cfg = cfg_of<T>(p);
+  if (p->wide) PLAN_FAIL(p, HVI_EINVAL, "loss_gf: not available with the wide applicator");
+  if (!p->has_obs) PLAN_FAIL(p, HVI_ENODATA, "loss_gf: the registered batch has no observations");
+  cudaStream_t s = p->stream;
+  const int ng = cfg.nphig, nP = cfg.nP;
+  const cudaMemcpyKind kind = mem_kind == HVI_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  // full-layout ϕ: ϕg in place, ϕP in the μP slot (what g's pbm covariates and θP = transP(ϕP) read), the rest zero
+  T* dphi = (T*)p->d_phi;
+  CU(p, cudaMemsetAsync(dphi, 0, sizeof(T) * (size_t)cfg.nphi, s));
+  CU(p, cudaMemcpyAsync(dphi, phi_gf, sizeof(T) * (size_t)ng, kind, s));
+  if (nP > 0) CU(p, cudaMemcpyAsync(dphi + cfg.o_muP, (const T*)phi_gf + ng, sizeof(T) * (size_t)nP, kind, s));
+  Launch L{s, p->sm_count, &p->launches};
+  int rc = run_g_fwd<T>(p, L, cfg, dphi, (T*)p->d_mu, 0, nullptr);
+  if (rc) return rc;
+  if ((size_t)point_max_rows(p->sm_count) * point_row_len() > (size_t)p->max_rows * nacc(p->cf.nP, p->cf.nM))
+    PLAN_FAIL(p, HVI_EINVAL, "internal: scratch too small");
+  int nrows = 0, nblk = 0;
+  CU(p, launch_point<T>(L, cfg, dphi, (const T*)p->d_rec, (const T*)p->d_mu, (T*)p->d_mubar, p->nb, p->d_part_stream, &nrows));
+  double* part_xs = nullptr;
+  if (cfg.npc > 0) {
+    rc = ensure(p, (void**)&p->d_part_x, &p->cap_part_x, (int64_t)sizeof(double) * 2 * p->max_blk * cfg.npc);
+    if (rc) return rc;
+    part_xs = p->d_part_x;
+  }
+  CU(p, launch_mlp_bwd<T>(L, cfg, dphi, (const T*)p->d_xM, (const T*)p->d_mubar, p->nb, p->d_part_mlp, &nblk, p->max_blk, 0,
+                          nullptr, part_xs));
+  const bool want_grad = grad != nullptr;
+  CU(p, launch_point_finalize<T>(L, cfg, dphi, p->d_part_stream, nrows, p->d_part_mlp, nblk, part_xs, p->const_nly, p->d_out,
+                                 want_grad ? (T*)p->d_grad : nullptr));
+  CU(p, cudaMemcpyAsync(p->h_out, p->d_out + ng + nP, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+  if (want_grad) {
+    if (mem_kind == HVI_MEM_HOST) CU(p, cudaMemcpyAsync(p->h_grad, p->d_grad, sizeof(T) * (size_t)(ng + nP), cudaMemcpyDeviceToHost, s));
+    else CU(p, cudaMemcpyAsync(grad, p->d_grad, sizeof(T) * (size_t)(ng + nP), cudaMemcpyDeviceToDevice, s));
+  }
+  CU(p, cudaStreamSynchronize(s));
+  if (want_grad && mem_kind == HVI_MEM_HOST) memcpy(grad, p->h_grad, sizeof(T) * (size_t)(ng + nP));
+  if (comps) for (int i = 0; i < 3; i++) comps[i] = p->h_out[i];
+  if (p->anomalies > 0)
+    PLAN_FAIL(p, HVI_ENONFINITE, "%lld observation(s) are finite where a driver is not: the reference returns NaN here",
+              (long long)p->anomalies);
+  if (p->h_out[3] != 0.0) PLAN_FAIL(p, HVI_ENONFINITE, "non-finite value or gradient (%g entries)", p->h_out[3]);
+  return HVI_OK;
+}
+
+extern "C" int hvi_loss_gf_grad(hvi_plan* p, const void* phi_gf, int mem_kind, double comps[3], void* grad) {
+  if (!p) return HVI_EINVAL;
+  if (p->nb <= 0) PLAN_FAIL(p, HVI_ENODATA, "hvi_plan_set_data has not been called");
+  if (!phi_gf) PLAN_FAIL(p, HVI_EINVAL, "phi_gf is NULL");
+  if (mem_kind != HVI_MEM_HOST && mem_kind != HVI_MEM_DEVICE) PLAN_FAIL(p, HVI_EINVAL, "bad mem_kind");
+  CU(p, cudaSetDevice(p->desc.device));
+  return p->dtype == HVI_F32 ? loss_gf_t<float>(p, phi_gf, mem_kind, comps, grad) : loss_gf_t<double>(p, phi_gf, mem_kind, comps, grad);
+}
+
+// ---------------------------------------------------------------------------------------
 // Device-resident optimiser steps: Optimization.solve(optprob, Adam(η); …) of
 // src/HybridSolver.jl:259-260 without the host round trip per iteration.  The update is the
 // Optimisers.jl Adam rule: m ← β1 m + (1−β1) g, v ← β2 v + (1−β2) g², ϕ ← ϕ − η·m̂/(√v̂ + ε).

@@ -155,6 +155,16 @@ cudaError_t launch_mlp3_mma_fwd(const Launch& L, const Cfg<float>& cfg, const fl
 cudaError_t launch_mlp3_mma_bwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM,
                                 const float* mubar, int64_t nb, double* part, int* nblk_out, int nblk_max, int M_units,
                                 const float* zetaP, double* part_x);
+// point-solver loss (hvi_point.cu)
+template <typename T>
+cudaError_t launch_point(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* rec, const T* mu, T* mubar, int64_t nb,
+                         double* part /*[point_max_rows][point_row_len]*/, int* nrows_out);
+template <typename T>
+cudaError_t launch_point_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, const double* part, int nrows,
+                                  const double* part_mlp, int nblk, const double* part_x, double const_nly, double* out,
+                                  T* grad_T);
+int point_max_rows(int sm_count);
+int point_row_len();
 int stream_max_rows(int sm_count);
 int mlp_bwd_max_blocks(int sm_count);
 bool stream_supported(int nP, int nM, int nO);

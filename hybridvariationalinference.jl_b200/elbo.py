@@ -160,6 +160,17 @@ class NegElboPlan:
             idx = np.ascontiguousarray(i_sites, dtype=np.int64)
             self._check(self.lib.hvi_plan_set_sites(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
 
+    # -- point solver ---------------------------------------------------------------------------
+    def loss_gf_withgradient(self, ϕ_gf, want_grad=True):
+        """(nLjoint_pen, (nLjoint_pen, nLy, neg_log_prior), ∇ϕ) of `loss_gf` (src/gf.jl:227-295) for ϕ = [ϕg; ϕP] --
+        the cost function of `solve(prob, HybridPointSolver)` (src/HybridSolver.jl:9-140) on the registered batch."""
+        ϕ_gf = np.ascontiguousarray(ϕ_gf, dtype=self.dt)
+        assert ϕ_gf.size == self.prob.n_phig + self.prob.n_P
+        comps = (C.c_double * 3)()
+        grad = np.empty_like(ϕ_gf) if want_grad else None
+        self._check(self.lib.hvi_loss_gf_grad(self._h, _ptr(ϕ_gf), A.HVI_MEM_HOST, comps, _ptr(grad) if want_grad else None))
+        return comps[0], np.array(list(comps)), grad
+
     # -- optimiser steps on the device -------------------------------------------------------
     def adam_init(self, ϕ0, eta=0.02, betas=(0.9, 0.999), eps=1e-8):
         """Device-resident `Adam(eta)` state for `adam_run` (Optimization.solve of src/HybridSolver.jl:259-260)."""

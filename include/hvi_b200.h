@@ -175,6 +175,13 @@ int hvi_neg_elbo_grad_async(hvi_plan* plan, int32_t n_MC, const void* phi_dev,
                             const void* zP_dev, const void* zMs_dev, uint64_t seed,
                             int64_t site_offset, double* out_dev, void* cuda_stream);
 
+/* ---- point solver ------------------------------------------------------- */
+/* loss_gf of get_loss_gf (src/gf.jl:227-295; used by solve(prob, HybridPointSolver), src/HybridSolver.jl:9-140) and
+ * its gradient: phi_gf = [ϕg ; ϕP] (ComponentVector(ϕg, ϕP), src/HybridSolver.jl:26), θMs = transM(g([xM; ϕP[covars]], ϕg)'),
+ * θP = transP(ϕP), no draws, no clamp.  comps[3] = (nLjoint_pen, nLy, neg_log_prior); grad has the layout of phi_gf
+ * (NULL = value only). */
+int hvi_loss_gf_grad(hvi_plan* plan, const void* phi_gf, int mem_kind, double comps[3], void* grad);
+
 /* ---- optimiser steps on the device -------------------------------------- */
 /* Optimization.solve(optprob, Adam(η); …) of src/HybridSolver.jl:259-260 without the host round trip per
  * iteration: ϕ, the Adam moments and the gradient stay in HBM; the update is the Optimisers.jl Adam rule.

@@ -168,6 +168,13 @@ y_unc, i_sites; is_testmode)` with the same signature; its `rrule` hands Zygote 
 computed by the library, so `OptimizationFunction(..., AutoZygote())` (src/HybridSolver.jl:256-258)
 works unchanged.
 """
+"loss_gf and its gradient for ϕ = [ϕg; ϕP] (src/gf.jl:227-295), the point solver's cost function"
+function loss_gf_withgradient(p::Plan, ϕ::Vector{T}) where {T}
+    comps = zeros(Float64, 3); grad = similar(ϕ)
+    check(p, ccall((:hvi_loss_gf_grad, libhvi), Cint, (Ptr{Cvoid}, Ptr{T}, Cint, Ptr{Float64}, Ptr{T}), p.h, ϕ, 0, comps, grad))
+    (; nLjoint_pen = comps[1], nLy = comps[2], neg_log_prior = comps[3]), grad
+end
+
 "n_iter Adam iterations on the registered batch without leaving the GPU (Optimization.solve with Adam, src/HybridSolver.jl:259-260)"
 function adam_solve!(p::Plan, ϕ0::Vector{T}, n_iter::Integer, n_MC::Integer; eta=0.02, betas=(0.9, 0.999), eps=1e-8, seed0=0) where {T}
     check(p, ccall((:hvi_adam_init, libhvi), Cint, (Ptr{Cvoid}, Ptr{T}, Cdouble, Cdouble, Cdouble, Cdouble),

@@ -452,6 +452,37 @@ def value_and_grad(spec: Spec, phi, xM, xP, y_ob, y_unc, zP, zMs, dtype_name="f6
 
 
 # --------------------------------------------------------------------------------------
+# src/gf.jl: the point-solver loss
+# --------------------------------------------------------------------------------------
+def loss_gf_components(spec: Spec, phi_gf, xM, xP, y_ob, y_unc):
+    """loss_gf (src/gf.jl:227-295) with gf (:153-177) and gtrans (:183-199): ϕ = [ϕg; ϕP];
+    θMs = transMs(g([xM; ϕP[covars]], ϕg)'), θP = transP(ϕP) -- no clamp on this path; nLy = py(y_o, y_pred, y_unc)
+    (src/logden_normal.jl:16-43); neg_log_prior (src/elbo.jl:203-260); floss_penalty = zero."""
+    n_g = spec.n_phig
+    phig, zP = phi_gf[:n_g], phi_gf[n_g:n_g + spec.nP]
+    idx = list(spec.pbm_covar_idx)
+    xMP = _append_each_covars(xM, zP[idx] if idx else zP[:0])
+    zMs_tr = apply_g(spec, xMP, phig).T
+    thM, _ = _transform(spec.transM, zMs_tr)
+    thP, _ = _transform(spec.transP, zP) if spec.nP > 0 else (zP, None)
+    y_pred = f_doubleMM_sites(spec, thP, thM, xP)
+    nLy = neg_logden_indep_normal(y_ob, y_pred, y_unc)
+    nlp = compute_priors_logdensity(spec, thP, thM)
+    return dict(nLjoint_pen=nLy + nlp, nLy=nLy, neg_log_prior=nlp)
+
+
+def loss_gf_value_and_grad(spec: Spec, phi_gf, xM, xP, y_ob, y_unc):
+    """value, (nLjoint_pen, nLy, neg_log_prior) and ∇ϕ by float64 autograd (stands in for the AutoZygote gradient of
+    src/HybridSolver.jl:95-100)."""
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+    ph = t(phi_gf).clone().requires_grad_(True)
+    c = loss_gf_components(spec, ph, t(xM), t(xP), t(y_ob), t(y_unc))
+    (g,) = torch.autograd.grad(c["nLjoint_pen"], ph)
+    return float(c["nLjoint_pen"].detach()), np.array([float(c[k].detach()) for k in ("nLjoint_pen", "nLy", "neg_log_prior")]), \
+        g.numpy().copy()
+
+
+# --------------------------------------------------------------------------------------
 # prior / scaling fits done by DistributionFits in the reference (inputs to the boundary)
 # --------------------------------------------------------------------------------------
 Z95 = 1.6448536269514722   # quantile(Normal(), 0.95)
