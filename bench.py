@@ -259,6 +259,18 @@ def main():
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kt}
+    # the kernel's real limiter is the FP32 pipe: 56 packed + 35 scalar FP32 instructions per site·draw
+    # for DoubleMM with 8 observations = 147 pipe slots (SASS count of the hot loop, profiles/README.md), against
+    # 128 lanes x SMs x clock; reported next to the HBM roofline the contract asks for
+    try:
+        import torch
+        sm = torch.cuda.get_device_properties(local).multi_processor_count
+        clk_hz = float(sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+        if nO == 8 and nM == 2 and not prob.pbm_covars:
+            roofline["fp32_pipe"] = {"slots_per_unit": 147, "peak_lane_slots_per_s": sm * 128 * clk_hz,
+                                     "frac": 147.0 * nb * M / (kt["stream"] * 1e-3) / (sm * 128 * clk_hz)}
+    except Exception:
+        pass
 
     # ---- end to end through the public host API ------------------------------------------------
     e2e = None
