@@ -28,6 +28,44 @@ __global__ void __launch_bounds__(256) k(float* out, float a, float b) {
       if (KIND == 8) { x[i] = fmaf(x[i], a, b); asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[(i + 1) % ILP])); }  // 1 FFMA + 1 MUFU
       if (KIND == 9) { v[i] = __ffma2_rn(v[i], aa, bb); x[i] = fmaf(x[i], a, b); }   // FFMA2 + FFMA mix
     }
+    if (KIND == 10) {   // the same mix in runs of 8: all packed, then all scalar
+#pragma unroll
+      for (int i = 0; i < ILP; i++) v[i] = __ffma2_rn(v[i], aa, bb);
+#pragma unroll
+      for (int i = 0; i < ILP; i++) x[i] = fmaf(x[i], a, b);
+    }
+    if (KIND == 11) {   // 2 packed : 1 scalar, interleaved (the ratio of the streaming kernel's hot loop is 56 : 35)
+#pragma unroll
+      for (int i = 0; i < ILP; i++) { v[i] = __ffma2_rn(v[i], aa, bb); if (i & 1) x[i] = fmaf(x[i], a, b); }
+    }
+    if (KIND == 12) {   // FFMA2 with three distinct register operands each
+#pragma unroll
+      for (int i = 0; i < ILP; i++) v[i] = __ffma2_rn(v[i], v[(i + 3) % ILP], v[(i + 5) % ILP]);
+    }
+    if (KIND == 14) {   // scalar FFMA with three distinct register operands
+#pragma unroll
+      for (int i = 0; i < ILP; i++) x[i] = fmaf(x[i], x[(i + 3) % ILP], x[(i + 5) % ILP]);
+    }
+    if (KIND == 15) {   // FADD2 / FMUL2 with two distinct register operands
+#pragma unroll
+      for (int i = 0; i < ILP; i++) v[i] = __fadd2_rn(v[i], v[(i + 3) % ILP]);
+    }
+    if (KIND == 16) {
+#pragma unroll
+      for (int i = 0; i < ILP; i++) v[i] = __fmul2_rn(v[i], v[(i + 3) % ILP]);
+    }
+    if (KIND == 17) {   // FFMA2 with two distinct operands + one reused
+#pragma unroll
+      for (int i = 0; i < ILP; i++) v[i] = __ffma2_rn(v[i], v[(i + 3) % ILP], bb);
+    }
+    if (KIND == 18) {   // two scalar FFMA doing the work of one distinct-operand FFMA2
+#pragma unroll
+      for (int i = 0; i < ILP; i++) { v[i].x = fmaf(v[i].x, v[(i + 3) % ILP].x, v[(i + 5) % ILP].x); v[i].y = fmaf(v[i].y, v[(i + 3) % ILP].y, v[(i + 5) % ILP].y); }
+    }
+    if (KIND == 13) {   // FFMA2 + FMNMX (ALU pipe) interleaved
+#pragma unroll
+      for (int i = 0; i < ILP; i++) { v[i] = __ffma2_rn(v[i], aa, bb); x[i] = fmaxf(x[i], a); }
+    }
   }
   float s = 0;
 #pragma unroll
@@ -36,7 +74,7 @@ __global__ void __launch_bounds__(256) k(float* out, float a, float b) {
 }
 
 template <int KIND>
-void run(const char* name, int per_iter) {
+void run(const char* name, double per_iter) {
   int dev = 0, sms = 0, clk = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);
@@ -70,5 +108,14 @@ int main() {
   run<7>("FMNMX", 1);
   run<8>("FFMA+RCP", 2);
   run<9>("FFMA2+FFMA", 2);
+  run<10>("FFMA2 x8 then FFMA x8", 2);
+  run<11>("FFMA2 + FFMA 2:1", 1.5);
+  run<12>("FFMA2 distinct operands", 1);
+  run<13>("FFMA2 + FMNMX", 2);
+  run<14>("FFMA distinct operands", 1);
+  run<15>("FADD2 distinct operands", 1);
+  run<16>("FMUL2 distinct operands", 1);
+  run<17>("FFMA2 2 distinct + 1 reused", 1);
+  run<18>("2 x FFMA distinct (= 1 FFMA2)", 2);
   return 0;
 }
