@@ -4,22 +4,25 @@
 // ext/HybridVariationalInferenceSimpleChainsExt.jl:43-52) for the 3-layer shapes of DoubleMM
 // (5-20-20-2 and, with one pbm covariate, 6-24-24-2).  One warp owns a tile of 16 columns (sites, or
 // (draw, site) units in pass 2 of generate_ζ, src/elbo.jl:508-515) and keeps the whole layer chain in
-// registers: every product is a warp-level mma.sync.m16n8k16 (bf16 inputs, fp32 accumulate) with both
-// operands split into bf16 hi + bf16 lo and three MMAs per product (hi·hi + hi·lo + lo·hi, ≈2^-17
-// relative), so the results stay inside the 1e-4 Float32 tolerance of the path.  The accumulator
-// fragment of one layer (row = site, columns 2t, 2t+1) is, after tanh and packing, exactly the A
-// fragment of the next layer, so nothing goes through shared memory between layers.
+// registers: the two hidden layers are warp-level mma.sync instructions whose operands are split hi + lo
+// and multiplied three times (hi·hi + hi·lo + lo·hi).  The accumulator fragment of one layer (row =
+// site, columns 2t, 2t+1) is, after tanh, the A fragment of the next layer -- directly for m16n8k16 (bf16),
+// through a permutation of the K index for m16n8k8 (tf32) -- so nothing goes through shared memory between
+// layers.  The last layer (2 outputs) runs on the CUDA cores in exact fp32.
 //
-// Backward (hand adjoint): recompute forward, δ3 from μ̄_ζ through logistic and Φ⁻¹, δ2 = (δ3 W3ᵀ)⊙(1−h2²),
-// δ1 = (δ2 W2ᵀ)⊙(1−h1²) as MMAs against pre-split transposed weight fragments, and the weight gradients
-// ∇W_l = [a_{l-1}; 1]ᵀ δ_l as MMAs whose K dimension is the tile's 16 sites: both operands are the
-// packed register fragments transposed in place with movmatrix (no shared memory).  The bias gradient
-// rides along as the row of the constant 1 appended to each activation.  Accumulators stay in fp32
-// registers over the warp's tiles and are reduced over warps in a fixed order into one row of double
-// partial sums per block (same hand-off as k_mlp3_bwd: k_reduce sums the rows).
+// Forward kernel: 3xTF32 (operands carry ≈21 bits): μ_ζ feeds the streaming kernel, whose σ- and ρ-gradients
+// amplify its rounding (a 3xBF16 forward missed the 1e-4 tolerance on ρsM).
+// Backward kernel (hand adjoint): recompute forward in 3xBF16 (≈2^-17), δ3 from μ̄_ζ through logistic and Φ⁻¹,
+// ∇W3 and δ2 = (δ3 W3ᵀ)⊙(1−h2²) on the CUDA cores, δ1 = (δ2 W2ᵀ)⊙(1−h1²) as MMAs against pre-split transposed
+// weight fragments, and the weight gradients ∇W_l = [a_{l-1}; 1]ᵀ δ_l (l = 1, 2) as MMAs whose K dimension is the
+// tile's 16 sites: both operands are the packed register fragments transposed in place with movmatrix (no
+// shared memory).  The bias gradient rides along as the row of the constant 1 appended to each activation.
+// Accumulators stay in fp32 registers over the warp's tiles and are reduced over warps in a fixed order into one
+// row of double partial sums per block (same hand-off as k_mlp3_bwd: k_reduce sums the rows).
 //
-// Measured pipe rates on B200 (profiles/microbench/mma_pipes.cu): HMMA.16816 0.457 warp-inst/clk/SM,
-// overlapping with FP32/MUFU work of other warps.
+// Measured on B200 (profiles/microbench/mma_pipes.cu): HMMA.16816 / HMMA.1688 issue at 0.457 warp-inst/clk/SM and
+// FP32 instructions of the same scheduler do not overlap them, so the cost of a tile is ≈ 8.75 clk x HMMA + the
+// other instructions; that is why the thin last layer is cheaper on the CUDA cores.
 #include <math.h>
 #include <stdlib.h>
 
@@ -90,18 +93,18 @@ struct MlpMma {
   static_assert(H1 <= 24 && H2 <= 24 && H1 % 2 == 0 && H2 % 2 == 0, "hidden widths up to 24 (two k-steps incl. the bias one)");
   static_assert(NOUT <= 2, "epilogue redistributes 16 sites × 2 outputs over the 32 lanes");
   // computed n-tiles of each hidden layer and tiles including the column of the constant 1
-  static constexpr int NTH1 = cdiv(H1, 8), NTH2 = cdiv(H2, 8), NT1 = H1 / 8 + 1, NT2 = H2 / 8 + 1;
+  static constexpr int NTH1 = cdiv(H1, 8), NTH2 = cdiv(H2, 8), NT1 = H1 / 8 + 1;
   // weight fragment tables, one uint4 {b0 hi, b1 hi, b0 lo, b1 lo} per lane: index (ks·ntiles + nt)
   static constexpr int F_W1 = 0;                    // B[k=i][n=j] = W1[i][j], 1 k-step × NTH1
   static constexpr int F_W2 = F_W1 + NTH1;          // W2, 2 × NTH2
-  static constexpr int F_W3 = F_W2 + 2 * NTH2;      // W3, 2 × 1
-  static constexpr int F_W3T = F_W3 + 2;            // B[k=j][n=i] = W3[i][j], 1 × NTH2
-  static constexpr int F_W2T = F_W3T + NTH2;        // B[k=j][n=i] = W2[i][j], 2 × NTH1
+  static constexpr int F_W2T = F_W2 + 2 * NTH2;     // B[k=j][n=i] = W2[i][j], 2 × NTH1
   static constexpr int F_W1T = F_W2T + 2 * NTH1;    // B[k=j][n=i] = W1[i][j], 2 × 1 (cotangent of the inputs)
   static constexpr int NFRAG = F_W1T + 2;
   static constexpr int NB = 8 * (NTH1 + NTH2);      // padded biases b1 | b2
-  // gradient accumulators (fp32 C fragments): ∇W1 1×NTH1 tiles, ∇W2 2×NTH2, ∇W3 2×1
-  static constexpr int A_W1 = 0, A_W2 = A_W1 + NTH1, A_W3 = A_W2 + 2 * NTH2, NACCT = A_W3 + 2;
+  // gradient accumulators: fp32 C fragments ∇W1 (1×NTH1 tiles) and ∇W2 (2×NTH2), then this lane's partial sums of
+  // ∇W3 (rows 8nt+2t+c of W3, both outputs), NRED floats per lane in all
+  static constexpr int A_W1 = 0, A_W2 = A_W1 + NTH1, NACCT = A_W2 + 2 * NTH2, NACC3 = NTH2 * 2 * NOUT,
+                       NRED = NACCT * 4 + NACC3;
 
   __device__ static float wfetch(const Cfg<float>& cfg, const float* __restrict__ phi, int l, int nin, int nout, int i, int j) {
     return (i < nin && j < nout) ? phi[cfg.woff[l] + i * nout + j] : 0.0f;
@@ -114,9 +117,7 @@ struct MlpMma {
       int l, nin, nout, ks, nt;
       bool tr;
       if (f < F_W2) { l = 0; nin = NI; nout = H1; tr = false; ks = 0; nt = f - F_W1; }
-      else if (f < F_W3) { l = 1; nin = H1; nout = H2; tr = false; ks = (f - F_W2) / NTH2; nt = (f - F_W2) % NTH2; }
-      else if (f < F_W3T) { l = 2; nin = H2; nout = NOUT; tr = false; ks = f - F_W3; nt = 0; }
-      else if (f < F_W2T) { l = 2; nin = H2; nout = NOUT; tr = true; ks = 0; nt = f - F_W3T; }
+      else if (f < F_W2T) { l = 1; nin = H1; nout = H2; tr = false; ks = (f - F_W2) / NTH2; nt = (f - F_W2) % NTH2; }
       else if (f < F_W1T) { l = 1; nin = H1; nout = H2; tr = true; ks = (f - F_W2T) / NTH1; nt = (f - F_W2T) % NTH1; }
       else { l = 0; nin = NI; nout = H1; tr = true; ks = f - F_W1T; nt = 0; }
       float v[4];
@@ -241,11 +242,10 @@ struct MlpMma {
     else { m = 0; site0 = tile * 16; }
   }
 
-  // forward of one tile up to the pre-activation of the last layer
-  __device__ __forceinline__ static void forward(const uint4* __restrict__ wf, const float* __restrict__ sb, int lane, int t,
-                                                 const uint32_t (&xh)[1][2], const uint32_t (&xl)[1][2], float (&h1)[NTH1][4],
-                                                 uint32_t (&h1h)[NT1][2], uint32_t (&h1l)[NT1][2], float (&h2)[NTH2][4],
-                                                 uint32_t (&h2h)[NT2][2], uint32_t (&h2l)[NT2][2], float (&z3)[1][4]) {
+  // forward of one tile up to the activations of the second hidden layer (3xBF16; h1 stays packed for ∇W2)
+  __device__ __forceinline__ static void forward_h2(const uint4* __restrict__ wf, const float* __restrict__ sb, int lane, int t,
+                                                    const uint32_t (&xh)[1][2], const uint32_t (&xl)[1][2], float (&h1)[NTH1][4],
+                                                    uint32_t (&h1h)[NT1][2], uint32_t (&h1l)[NT1][2], float (&h2)[NTH2][4]) {
 #pragma unroll
     for (int nt = 0; nt < NTH1; nt++) {
       const float2 b = *reinterpret_cast<const float2*>(sb + 8 * nt + 2 * t);
@@ -259,16 +259,53 @@ struct MlpMma {
       h2[nt][0] = h2[nt][2] = b.x; h2[nt][1] = h2[nt][3] = b.y;
     }
     dense<NT1, 2, NTH2>(wf + F_W2 * 32, lane, h1h, h1l, h2);
-    activate<H2, NTH2, NT2>(h2, t, h2h, h2l);
-    z3[0][0] = z3[0][1] = z3[0][2] = z3[0][3] = 0.0f;
-    dense<NT2, 2, 1>(wf + F_W3 * 32, lane, h2h, h2l, z3);
+#pragma unroll
+    for (int nt = 0; nt < NTH2; nt++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) h2[nt][r] = tanh5(h2[nt][r]);
+  }
+
+  // The last layer has NOUT <= 2 outputs: an MMA tile would spend 8 columns (and, on this path, issue slots the
+  // FP32 pipe cannot use meanwhile) on them, so it runs on the CUDA cores in exact fp32.  This lane's rows of W3:
+  // w3[nt][c][k] = W3[8nt + 2t + c][k].
+  __device__ __forceinline__ static void load_w3(const Cfg<float>& cfg, const float* __restrict__ phi, int t,
+                                                 float (&w3)[NTH2][2][NOUT]) {
+#pragma unroll
+    for (int nt = 0; nt < NTH2; nt++)
+#pragma unroll
+      for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int k = 0; k < NOUT; k++) w3[nt][c][k] = wfetch(cfg, phi, 2, H2, NOUT, 8 * nt + 2 * t + c, k);
+  }
+  // z3 of rows g (pz[0]) and g+8 (pz[1]); after the two butterfly steps every lane of a quad holds all of them
+  __device__ __forceinline__ static void last_layer(const float (&h2)[NTH2][4], const float (&w3)[NTH2][2][NOUT],
+                                                    float (&pz)[2][NOUT]) {
+#pragma unroll
+    for (int hb = 0; hb < 2; hb++)
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) {
+        float s = 0.0f;
+#pragma unroll
+        for (int nt = 0; nt < NTH2; nt++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) s = fmaf(h2[nt][2 * hb + c], w3[nt][c][k], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        pz[hb][k] = s;
+      }
+  }
+  // lane (g, t) of the epilogue owns row g + 8·(t >> 1), output t & 1
+  __device__ __forceinline__ static float pick(const float (&pz)[2][NOUT], int t) {
+    const float a = (t & 1) && NOUT > 1 ? pz[0][NOUT > 1 ? 1 : 0] : pz[0][0];
+    const float b = (t & 1) && NOUT > 1 ? pz[1][NOUT > 1 ? 1 : 0] : pz[1][0];
+    return (t >> 1) ? b : a;
   }
 
   // ---- forward-only variant in 3xTF32 (m16n8k8; operands carry 22 bits): μ_ζ feeds the whole streaming
   // kernel, whose σ- and ρ-gradients amplify its rounding, so the value path gets the tighter split.
   // The A fragment of m16n8k8 wants columns t and t+4 while the accumulator holds 2t and 2t+1: the K index
   // is permuted (logical k = t ↔ column 2t, k = t+4 ↔ column 2t+1) and the weight rows with it.
-  static constexpr int G_W1 = 0, G_W2 = G_W1 + NTH1, G_W3 = G_W2 + NTH1 * NTH2, NFRAG32 = G_W3 + NTH2;
+  static constexpr int G_W1 = 0, G_W2 = G_W1 + NTH1, NFRAG32 = G_W2 + NTH1 * NTH2;
 
   __device__ static void build_frags32(const Cfg<float>& cfg, const float* __restrict__ phi, uint4* __restrict__ wf,
                                        float* __restrict__ sb, int tid, int nthr) {
@@ -276,8 +313,7 @@ struct MlpMma {
       const int f = e >> 5, lane = e & 31, g = lane >> 2, t = lane & 3;
       int l, nin, nout, ks, nt;
       if (f < G_W2) { l = 0; nin = NI; nout = H1; ks = 0; nt = f - G_W1; }
-      else if (f < G_W3) { l = 1; nin = H1; nout = H2; ks = (f - G_W2) / NTH2; nt = (f - G_W2) % NTH2; }
-      else { l = 2; nin = H2; nout = NOUT; ks = f - G_W3; nt = 0; }
+      else { l = 1; nin = H1; nout = H2; ks = (f - G_W2) / NTH2; nt = (f - G_W2) % NTH2; }
       uint4 w;
       split_tf32(wfetch(cfg, phi, l, nin, nout, 8 * ks + 2 * t, 8 * nt + g), w.x, w.z);
       split_tf32(wfetch(cfg, phi, l, nin, nout, 8 * ks + 2 * t + 1, 8 * nt + g), w.y, w.w);
@@ -294,7 +330,6 @@ struct MlpMma {
   template <int NK, int NTN>
   __device__ __forceinline__ static void dense32(const uint4* __restrict__ wf, int lane, const float (&a)[NK][4],
                                                  float (&acc)[NTN][4]) {
-    float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ks = 0; ks < NK; ks++) {
       uint32_t ah[4], al[4];
@@ -302,34 +337,24 @@ struct MlpMma {
       split_tf32(a[ks][2], ah[1], al[1]);   // (row g+8, column 2t)
       split_tf32(a[ks][1], ah[2], al[2]);   // (row g,   column 2t+1)
       split_tf32(a[ks][3], ah[3], al[3]);   // (row g+8, column 2t+1)
-      // consecutive MMAs go to different accumulators (the three n-tiles; for a single n-tile, one accumulator
-      // per term), so the dependent-issue latency of HMMA is not serialised inside a warp
+      // consecutive MMAs go to different accumulators (the n-tiles), so the dependent-issue latency of HMMA is not
+      // serialised inside a warp
       uint4 w[NTN];
 #pragma unroll
       for (int nt = 0; nt < NTN; nt++) w[nt] = wf[(ks * NTN + nt) * 32 + lane];
-      if constexpr (NTN == 1) {
-        mma1688(t1, al, w[0].x, w[0].y);
-        mma1688(t2, ah, w[0].z, w[0].w);
-        mma1688(acc[0], ah, w[0].x, w[0].y);
-      } else {
 #pragma unroll
-        for (int nt = 0; nt < NTN; nt++) mma1688(acc[nt], al, w[nt].x, w[nt].y);
+      for (int nt = 0; nt < NTN; nt++) mma1688(acc[nt], al, w[nt].x, w[nt].y);
 #pragma unroll
-        for (int nt = 0; nt < NTN; nt++) mma1688(acc[nt], ah, w[nt].z, w[nt].w);
+      for (int nt = 0; nt < NTN; nt++) mma1688(acc[nt], ah, w[nt].z, w[nt].w);
 #pragma unroll
-        for (int nt = 0; nt < NTN; nt++) mma1688(acc[nt], ah, w[nt].x, w[nt].y);
-      }
-    }
-    if constexpr (NTN == 1) {
-#pragma unroll
-      for (int r = 0; r < 4; r++) acc[0][r] += t1[r] + t2[r];
+      for (int nt = 0; nt < NTN; nt++) mma1688(acc[nt], ah, w[nt].x, w[nt].y);
     }
   }
 
   __device__ __forceinline__ static void forward32(const uint4* __restrict__ wf, const float* __restrict__ sb, int lane, int t,
-                                                   const float (&xv)[4], float (&z3)[1][4]) {
+                                                   const float (&xv)[4], float (&h2)[NTH2][4]) {
     float x[1][4] = {{xv[0], xv[1], xv[2], xv[3]}};
-    float h1[NTH1][4], h2[NTH2][4];
+    float h1[NTH1][4];
 #pragma unroll
     for (int nt = 0; nt < NTH1; nt++) {
       const float2 b = *reinterpret_cast<const float2*>(sb + 8 * nt + 2 * t);
@@ -350,21 +375,11 @@ struct MlpMma {
     for (int nt = 0; nt < NTH2; nt++)
 #pragma unroll
       for (int r = 0; r < 4; r++) h2[nt][r] = tanh5(h2[nt][r]);
-    z3[0][0] = z3[0][1] = z3[0][2] = z3[0][3] = 0.0f;
-    dense32<NTH2, 1>(wf + G_W3 * 32, lane, h2, z3);
   }
 };
 
 constexpr int MMA_BS = 256, MMA_NW = MMA_BS / 32;      // forward: 3 blocks per SM
 constexpr int MMA_BSB = 128, MMA_NWB = MMA_BSB / 32;   // backward (168 registers): 3 blocks per SM
-
-// lane L of the epilogue owns column s = L & 15 of the tile and output k = L >> 4
-__device__ __forceinline__ float gather_out(const float (&z3)[4], int lane) {
-  const int s = lane & 15, k = lane >> 4, src = 4 * (s & 7);
-  const float v0 = __shfl_sync(0xffffffffu, z3[0], src), v1 = __shfl_sync(0xffffffffu, z3[1], src);
-  const float v2 = __shfl_sync(0xffffffffu, z3[2], src), v3 = __shfl_sync(0xffffffffu, z3[3], src);
-  return (s & 8) ? (k ? v3 : v2) : (k ? v1 : v0);
-}
 
 template <int NI, int H1, int H2, int NOUT>
 __global__ void __launch_bounds__(MMA_BS, 4) k_mlp3_mma_fwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ phi,
@@ -381,6 +396,8 @@ __global__ void __launch_bounds__(MMA_BS, 4) k_mlp3_mma_fwd(const __grid_constan
   const int64_t stride = (int64_t)gridDim.x * MMA_NW;
   int64_t tile = (int64_t)blockIdx.x * MMA_NW + warp;
   const typename N::XCols xcols = N::x_cols(cfg, t);
+  float w3[N::NTH2][2][NOUT];
+  N::load_w3(cfg, phi, t, w3);
   float xv[4];
   int m = 0, m_next = 0;
   int64_t site0 = 0, site0_next = 0;
@@ -396,11 +413,12 @@ __global__ void __launch_bounds__(MMA_BS, 4) k_mlp3_mma_fwd(const __grid_constan
       N::tile_pos(tile + stride, ntiles, M_units, m_next, site0_next);
       N::load_x(cfg, xcols, phi, xM, zetaP, M_units, m_next, site0_next, nb, g, xv);
     }
-    float z3[1][4];
-    N::forward32(wf, sb, lane, t, xc, z3);
-    const float z = gather_out(z3[0], lane);
-    const int k = lane >> 4;
-    const int64_t site = site0 + (lane & 15);
+    float h2[N::NTH2][4], pz[2][NOUT];
+    N::forward32(wf, sb, lane, t, xc, h2);
+    N::last_layer(h2, w3, pz);
+    const float z = N::pick(pz, t);
+    const int k = t & 1;
+    const int64_t site = site0 + g + 8 * (t >> 1);
     if (k < NOUT && k < cfg.nM && site < nb) {
       const float p = logisticf_(z);
       const float v = (cfg.scale_kind == HVI_SCALE_RANGE) ? p * cfg.scale_b[k] + cfg.scale_a[k]
@@ -420,8 +438,8 @@ __global__ void __launch_bounds__(MMA_BSB, 3) k_mlp3_mma_bwd(const __grid_consta
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint4* wf = reinterpret_cast<uint4*>(smem_raw);                                   // [NFRAG][32]
   float* sb = reinterpret_cast<float*>(wf + N::NFRAG * 32);                         // [NB]
-  float* red = sb + ((N::NB + 3) & ~3);                                             // [MMA_NWB][NACCT·4][32]
-  double* xw = reinterpret_cast<double*>(red + (size_t)MMA_NWB * N::NACCT * 4 * 32); // [MMA_NWB][nxa]
+  float* red = sb + ((N::NB + 3) & ~3);                                             // [MMA_NWB][NRED][32]
+  double* xw = reinterpret_cast<double*>(red + (size_t)MMA_NWB * N::NRED * 32);      // [MMA_NWB][nxa]
   const int nxa = (M_units > 0 ? M_units : 1) * cfg.npc;
   N::build_frags(cfg, phi, wf, sb, N::NFRAG, threadIdx.x, MMA_BSB);
   for (int e = threadIdx.x; e < MMA_NWB * nxa; e += MMA_BSB) xw[e] = 0.0;
@@ -440,11 +458,19 @@ __global__ void __launch_bounds__(MMA_BSB, 3) k_mlp3_mma_bwd(const __grid_consta
   float xv[4];
   int m = 0, m_next = 0;
   int64_t site0 = 0, site0_next = 0;
-  // cotangent of this lane's epilogue element (column lane & 15 of the tile, output lane >> 4), clamped address
-  const int ke = lane >> 4;
+  float w3[N::NTH2][2][NOUT], acc3[N::NTH2][2][NOUT];
+  N::load_w3(cfg, phi, t, w3);
+#pragma unroll
+  for (int nt = 0; nt < N::NTH2; nt++)
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) acc3[nt][c][k] = 0.0f;
+  // cotangent of this lane's epilogue element (row g + 8·(t >> 1) of the tile, output t & 1), clamped address
+  const int ke = t & 1, re = g + 8 * (t >> 1);
   const bool k_ok = ke < NOUT && ke < cfg.nM;
   auto load_mb = [&](int mm, int64_t s0) -> float {
-    int64_t se = s0 + (lane & 15);
+    int64_t se = s0 + re;
     if (se >= nb) se = nb - 1;
     const int kk = k_ok ? ke : 0;
     return M_units > 0 ? mubar[((size_t)mm * cfg.nM + kk) * nb + se] : mubar[se * cfg.nM + kk];
@@ -457,7 +483,7 @@ __global__ void __launch_bounds__(MMA_BSB, 3) k_mlp3_mma_bwd(const __grid_consta
   }
   for (; tile < ntot; tile += stride) {
     m = m_next; site0 = site0_next;
-    const int64_t site_e = site0 + (lane & 15);
+    const int64_t site_e = site0 + re;
     const bool act_e = k_ok && site_e < nb;
     const float mb = mb_next;
 
@@ -473,63 +499,48 @@ __global__ void __launch_bounds__(MMA_BSB, 3) k_mlp3_mma_bwd(const __grid_consta
       N::load_x(cfg, xcols, phi, xM, zetaP, M_units, m_next, site0_next, nb, g, xv);
       mb_next = load_mb(m_next, site0_next);
     }
-    float h1[N::NTH1][4], h2[N::NTH2][4], z3[1][4];
-    uint32_t h1h[N::NT1][2], h1l[N::NT1][2], h2h[N::NT2][2], h2l[N::NT2][2];
-    N::forward(wf, sb, lane, t, xh, xl, h1, h1h, h1l, h2, h2h, h2l, z3);
+    float h1[N::NTH1][4], h2[N::NTH2][4], pz[2][NOUT];
+    uint32_t h1h[N::NT1][2], h1l[N::NT1][2];
+    N::forward_h2(wf, sb, lane, t, xh, xl, h1, h1h, h1l, h2);
+    N::last_layer(h2, w3, pz);
 
     // δ3 = μ̄ · dμ/dp · p(1−p)   (NormalScaling: dμ/dp = σ·√(2π)·exp(q²/2), q = Φ⁻¹(p); src/ModelApplicator.jl:168)
     float d = 0.0f;
-    {
-      const float z = gather_out(z3[0], lane);
-      if (act_e) {
-        const float pk = logisticf_(z);
-        if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb * cfg.scale_b[ke];
-        else {
-          const float q = normcdfinvf(pk);
-          d = mb * cfg.scale_b[ke] * 2.50662827463100050242f * ex2f_(0.72134752044448170368f * q * q);
-        }
-        d *= pk * (1.0f - pk);
+    if (act_e) {
+      const float pk = logisticf_(N::pick(pz, t));
+      if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb * cfg.scale_b[ke];
+      else {
+        const float q = normcdfinvf(pk);
+        d = mb * cfg.scale_b[ke] * 2.50662827463100050242f * ex2f_(0.72134752044448170368f * q * q);
       }
+      d *= pk * (1.0f - pk);
     }
-    // back to the accumulator layout: lanes t == 0 hold (site g, out 0), (g, 1), (g+8, 0), (g+8, 1)
-    uint32_t d3h[1][2], d3l[1][2];
-    {
-      float c0 = __shfl_sync(0xffffffffu, d, g), c1 = __shfl_sync(0xffffffffu, d, 16 + g);
-      float c2 = __shfl_sync(0xffffffffu, d, 8 + g), c3 = __shfl_sync(0xffffffffu, d, 24 + g);
-      if (t != 0) c0 = c1 = c2 = c3 = 0.0f;
-      split2(c0, c1, d3h[0][0], d3l[0][0]);
-      split2(c2, c3, d3h[0][1], d3l[0][1]);
-    }
-    // transposed δ as the B operand of a weight-gradient product (K = the tile's 16 sites)
-    // and transposed [a; 1] as its A operand (M = features)
-    {  // ∇W3 += [h2; 1]ᵀ δ3
-      const uint32_t bh0 = tr8(d3h[0][0]), bh1 = tr8(d3h[0][1]), bl0 = tr8(d3l[0][0]), bl1 = tr8(d3l[0][1]);
+    // every lane of the quad needs δ3 of rows g and g+8, both outputs: dq[hb][k] sits in lane 2·hb + k of the quad
+    float dq[2][NOUT];
 #pragma unroll
-      for (int mt = 0; mt < 2; mt++) {
-        if (2 * mt >= N::NT2) break;
-        uint32_t ah[4], al[4];
-        ah[0] = tr8(h2h[2 * mt][0]); ah[2] = tr8(h2h[2 * mt][1]); al[0] = tr8(h2l[2 * mt][0]); al[2] = tr8(h2l[2 * mt][1]);
-        if (2 * mt + 1 < N::NT2) {
-          ah[1] = tr8(h2h[2 * mt + 1][0]); ah[3] = tr8(h2h[2 * mt + 1][1]);
-          al[1] = tr8(h2l[2 * mt + 1][0]); al[3] = tr8(h2l[2 * mt + 1][1]);
-        } else { ah[1] = ah[3] = al[1] = al[3] = 0u; }
-        mma3(acc[N::A_W3 + mt], ah, al, bh0, bh1, bl0, bl1);
-      }
-    }
-    // δ2 = (δ3 W3ᵀ) ⊙ (1 − h2²)
+    for (int hb = 0; hb < 2; hb++)
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) dq[hb][k] = __shfl_sync(0xffffffffu, d, (lane & ~3) + 2 * hb + k);
+    // ∇W3 += h2ᵀ δ3 (this lane's rows of W3) and δ2 = (δ3 W3ᵀ) ⊙ (1 − h2²), both on the CUDA cores
     uint32_t d2h[N::NTH2][2], d2l[N::NTH2][2];
-    {
-      float p[N::NTH2][4];
 #pragma unroll
-      for (int nt = 0; nt < N::NTH2; nt++) p[nt][0] = p[nt][1] = p[nt][2] = p[nt][3] = 0.0f;
-      N::template dense<1, 1, N::NTH2>(wf + N::F_W3T * 32, lane, d3h, d3l, p);
+    for (int nt = 0; nt < N::NTH2; nt++) {
+      float p[4];
 #pragma unroll
-      for (int nt = 0; nt < N::NTH2; nt++) {
+      for (int c = 0; c < 2; c++) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) p[nt][r] *= fmaf(-h2[nt][r], h2[nt][r], 1.0f);
-        split2(p[nt][0], p[nt][1], d2h[nt][0], d2l[nt][0]);
-        split2(p[nt][2], p[nt][3], d2h[nt][1], d2l[nt][1]);
+        for (int k = 0; k < NOUT; k++)
+          acc3[nt][c][k] = fmaf(h2[nt][c], dq[0][k], fmaf(h2[nt][2 + c], dq[1][k], acc3[nt][c][k]));
+#pragma unroll
+        for (int hb = 0; hb < 2; hb++) {
+          float v = 0.0f;
+#pragma unroll
+          for (int k = 0; k < NOUT; k++) v = fmaf(dq[hb][k], w3[nt][c][k], v);
+          p[2 * hb + c] = v * fmaf(-h2[nt][2 * hb + c], h2[nt][2 * hb + c], 1.0f);
+        }
       }
+      split2(p[0], p[1], d2h[nt][0], d2l[nt][0]);
+      split2(p[2], p[3], d2h[nt][1], d2l[nt][1]);
     }
     {  // ∇W2 += [h1; 1]ᵀ δ2
       uint32_t bh[N::NTH2][2], bl[N::NTH2][2];
@@ -596,22 +607,37 @@ __global__ void __launch_bounds__(MMA_BSB, 3) k_mlp3_mma_bwd(const __grid_consta
 #pragma unroll
   for (int a = 0; a < N::NACCT; a++)
 #pragma unroll
-    for (int r = 0; r < 4; r++) red[((size_t)warp * N::NACCT * 4 + a * 4 + r) * 32 + lane] = acc[a][r];
+    for (int r = 0; r < 4; r++) red[((size_t)warp * N::NRED + a * 4 + r) * 32 + lane] = acc[a][r];
+#pragma unroll
+  for (int nt = 0; nt < N::NTH2; nt++)
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+      for (int k = 0; k < NOUT; k++)
+        red[((size_t)warp * N::NRED + N::NACCT * 4 + (nt * 2 + c) * NOUT + k) * 32 + lane] = acc3[nt][c][k];
   __syncthreads();
   double* out = part + (size_t)blockIdx.x * cfg.nphig;
   for (int e = threadIdx.x; e < N::NACCT * 4 * 32; e += MMA_BSB) {
     const int ln = e & 31, r = (e >> 5) & 3, a = e >> 7, gg = ln >> 2, tt = ln & 3;
     double s = 0.0;
-    for (int w = 0; w < MMA_NWB; w++) s += (double)red[((size_t)w * N::NACCT * 4 + a * 4 + r) * 32 + ln];
+    for (int w = 0; w < MMA_NWB; w++) s += (double)red[((size_t)w * N::NRED + a * 4 + r) * 32 + ln];
     int l, nin, nout, mt, nt;
     if (a < N::A_W2) { l = 0; nin = NI; nout = H1; mt = 0; nt = a - N::A_W1; }
-    else if (a < N::A_W3) { l = 1; nin = H1; nout = H2; mt = (a - N::A_W2) / N::NTH2; nt = (a - N::A_W2) % N::NTH2; }
-    else { l = 2; nin = H2; nout = NOUT; mt = a - N::A_W3; nt = 0; }
+    else { l = 1; nin = H1; nout = H2; mt = (a - N::A_W2) / N::NTH2; nt = (a - N::A_W2) % N::NTH2; }
     const int i = 16 * mt + gg + (r >> 1) * 8, j = 8 * nt + 2 * tt + (r & 1);
     if (j < nout) {
       if (i < nin) out[cfg.woff[l] + i * nout + j] = s;
       else if (i == nin && cfg.l_bias[l]) out[cfg.boff[l] + j] = s;
     }
+  }
+  // ∇W3[i][k]: the lanes with the same t hold partial sums over their rows (8 values of g per warp)
+  for (int e = threadIdx.x; e < H2 * NOUT; e += MMA_BSB) {
+    const int i = e / NOUT, k = e % NOUT, nt = i >> 3, tt = (i & 7) >> 1, c = i & 1;
+    double s = 0.0;
+    for (int w = 0; w < MMA_NWB; w++)
+      for (int gg = 0; gg < 8; gg++)
+        s += (double)red[((size_t)w * N::NRED + N::NACCT * 4 + (nt * 2 + c) * NOUT + k) * 32 + 4 * gg + tt];
+    out[cfg.woff[2] + i * NOUT + k] = s;
   }
   if (part_x)
     for (int e = threadIdx.x; e < nxa; e += MMA_BSB) {
@@ -672,7 +698,7 @@ cudaError_t launch_mlp3_mma_bwd(const Launch& L, const Cfg<float>& cfg, const fl
     using N = MlpMma<NI, H1, H2, NO_>;                                                                      \
     const size_t nxa = (size_t)(M_units > 0 ? M_units : 1) * cfg.npc;                                       \
     const size_t smem = sizeof(uint4) * N::NFRAG * 32 + sizeof(float) * ((N::NB + 3) & ~3) +                \
-                        sizeof(float) * (size_t)MMA_NWB * N::NACCT * 4 * 32 + sizeof(double) * MMA_NWB * nxa + 16; \
+                        sizeof(float) * (size_t)MMA_NWB * N::NRED * 32 + sizeof(double) * MMA_NWB * nxa + 16;    \
     if (smem > 200 * 1024) return cudaErrorNotSupported;                                                    \
     auto kern = k_mlp3_mma_bwd<NI, H1, H2, NO_>;                                                            \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
