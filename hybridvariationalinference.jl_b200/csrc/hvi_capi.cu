@@ -62,6 +62,7 @@ struct hvi_plan {
   void* d_grad;
   double* h_out;  // pinned
   void* h_grad;   // pinned
+  double* d_ls; int64_t cap_ls;       // per-warp Σ log σ partials of hvi_predict
   // device-resident Adam state (hvi_adam_*): ϕ in the working type, moments in double
   void* d_phi_opt; double *d_adam_m, *d_adam_v, *d_trace; int64_t cap_trace;
   double adam_eta, adam_b1, adam_b2, adam_eps; int64_t adam_t;
@@ -238,6 +239,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   fill_cfg<float>(*desc, p->cf);
   fill_cfg<double>(*desc, p->cd);
   p->nb = 0; p->launches = 0;
+  p->d_ls = nullptr; p->cap_ls = 0;
   p->d_phi_opt = nullptr; p->d_adam_m = p->d_adam_v = p->d_trace = nullptr; p->cap_trace = 0; p->adam_t = 0;
   p->copy_stream = nullptr; p->ev_copied = nullptr; p->d_xM_next = p->d_xP_next = nullptr;
   p->cap_cur = p->cap_next = p->nb_next = 0; p->has_obs_next = 0;
@@ -295,7 +297,7 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->ev_copied) cudaEventDestroy(p->ev_copied);
-  void* dev[] = {p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->d_trace, p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
+  void* dev[] = {p->d_ls, p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->d_trace, p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
                  p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide, p->d_wide_bwd, p->d_gacc, p->d_wide_cache};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
@@ -921,9 +923,11 @@ static int predict_t(hvi_plan* p, int M, const void* phi, const void* zP, const 
     o1 = tmp; o2 = (T*)tmp + (size_t)nP * M; o3 = (T*)o2 + nzM;
   }
   const int64_t nth = nb > (int64_t)nP * M ? nb : (int64_t)nP * M;
-  double* d_ls = nullptr;
   const size_t nls = (size_t)((nth + 255) / 256) * 8;
-  cudaError_t e = cudaMalloc((void**)&d_ls, sizeof(double) * nls);
+  rc = ensure(p, (void**)&p->d_ls, &p->cap_ls, (int64_t)(sizeof(double) * nls));
+  if (rc) { if (tmp) cudaFree(tmp); return rc; }
+  double* d_ls = p->d_ls;
+  cudaError_t e = cudaSuccess;
   EvalConsts<T>* ec = (EvalConsts<T>*)p->d_ec;
   T* pdraw = (T*)p->d_pdraw;
   StreamArgs<T> a;
@@ -933,7 +937,7 @@ static int predict_t(hvi_plan* p, int M, const void* phi, const void* zP, const 
   a.phi = dphi; a.i_sites = p->d_isites;
   if (e == cudaSuccess && cfg.npc > 0) {
     rc = ensure(p, &p->d_MU, &p->cap_MU, (int64_t)sizeof(T) * M * nM * nb);
-    if (rc) { if (tmp) cudaFree(tmp); cudaFree(d_ls); return rc; }
+    if (rc) { if (tmp) cudaFree(tmp); return rc; }
     a.MU = (const T*)p->d_MU;
   }
   int nparts = 0;
@@ -952,7 +956,6 @@ static int predict_t(hvi_plan* p, int M, const void* phi, const void* zP, const 
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (tmp) cudaFree(tmp);
-  if (d_ls) cudaFree(d_ls);
   if (e != cudaSuccess) PLAN_FAIL(p, HVI_ECUDA, "hvi_predict: %s", cudaGetErrorString(e));
   if (entropy) {
     // entropy_MvNormal(length(σ), 2 Σ log σ)  (src/elbo.jl:449-450, src/logden_normal.jl:74)

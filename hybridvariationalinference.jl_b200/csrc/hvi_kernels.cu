@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "hvi_internal.cuh"
+#include "hvi_rng.cuh"
 
 namespace hvi {
 
@@ -50,36 +51,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                                              uint32_t (&o)[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; r++) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
-}
-
-
-// four standard normals of column gcol (= global site·n_θM + k), draws 4·m4 … 4·m4+3:
-// Philox4x32-10 keyed by the seed, Box-Muller on the MUFU pipe
-__device__ __forceinline__ void normal4(uint64_t seed, uint64_t gcol, int m4, float (&n4)[4]) {
-  uint32_t r[4];
-  philox4x32_10((uint32_t)gcol, (uint32_t)(gcol >> 32), (uint32_t)m4, 0x5eedu, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const float u1 = ((float)(r[2 * h] >> 8) + 1.0f) * 5.9604644775390625e-08f;   // (0, 1], 24 bits
-    const float u2 = (float)(r[2 * h + 1] >> 8) * 5.9604644775390625e-08f;        // [0, 1)
-    const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));                    // sqrt(−2 ln u1)
-    float sn, cs;
-    __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &sn, &cs);             // argument in [−π, π)
-    n4[2 * h] = rad * cs; n4[2 * h + 1] = rad * sn;
-  }
-}
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
@@ -1536,99 +1507,6 @@ __global__ void __launch_bounds__(256) k_generate_zeta(const __grid_constant__ C
     }
   }
 }
-
-// ---------------------------------------------------------------------------------------
-// predict_hvi / sample_posterior forward path (src/elbo.jl:320-458; transform_ζs :815-835; 3-D PBM
-// applicator src/PBMApplicator.jl:51-57): for every posterior sample m and site i
-//   θsMs_tr[i,k,m] = T_k(ζMs[i,k,m]),  y[o,i,m] = f_doubleMM(θP_m, θMs_{i,m}, xP[:,i]),
-// no clamp (transform_ζs applies none), NaN where a driver is not finite.  One thread per site,
-// writes coalesced over sites; output-bandwidth bound (4·(n_θM + n_obs) bytes per site·sample).
-// ---------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ T transform_only(int tr, T zeta) {
-  if (tr == HVI_TR_EXP) return exp(zeta);
-  if (tr == HVI_TR_LOGISTIC) return T(1) / (T(1) + exp(-zeta));
-  return zeta;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) k_predict(const __grid_constant__ Cfg<T> cfg,
-                                                 const __grid_constant__ StreamArgs<T> a, const T* __restrict__ pdraw,
-                                                 const T* __restrict__ xP, T* __restrict__ thetaP,
-                                                 T* __restrict__ thetaMs_tr, T* __restrict__ y,
-                                                 double* __restrict__ part_logsig) {
-  const int nP = cfg.nP, nM = cfg.nM, nO = cfg.nO, M = a.M;
-  const EvalConsts<T>& ec = *a.ec;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const T* zetaP = pdraw + (size_t)nP * M;
-  if (gid < (int64_t)nP * M) {
-    const int j = (int)(gid / M), m = (int)(gid % M);
-    thetaP[j + (size_t)nP * m] = transform_only<T>(cfg.transP[j], zetaP[gid]);
-  }
-  double logsig = 0.0;
-  for (int64_t i = gid; i < a.nb; i += (int64_t)gridDim.x * blockDim.x) {
-    T mu[MAXP], sg[MAXP], S1[32], S2[32];
-    for (int k = 0; k < nM; k++) {
-      mu[k] = a.mu[i * nM + k];
-      const T ls = cfg.sepvar ? a.phi[cfg.o_coef + (a.i_sites ? a.i_sites[i] : i) * nM + k] : ec.coefA[k] + ec.coefB[k] * mu[k];
-      sg[k] = exp(T(0.5) * ls);
-      logsig += 0.5 * (double)ls;
-    }
-    for (int o = 0; o < nO; o++) { S1[o] = xP[i * 2 * nO + o]; S2[o] = xP[i * 2 * nO + nO + o]; }
-    for (int m = 0; m < M; m++) {
-      T th[MAXP], par[4];
-      for (int k = 0; k < nM; k++) {
-        T t = T(0);
-        for (int j = cfg.blkM_start[k]; j <= k; j++) {
-          T z;
-          if (a.rng) {
-            float n4[4];
-            normal4(a.seed, (uint64_t)(a.col_offset + i * nM + j), m / 4, n4);
-            z = (T)(m % 4 == 0 ? n4[0] : m % 4 == 1 ? n4[1] : m % 4 == 2 ? n4[2] : n4[3]);
-          } else {
-            z = a.zMs[((size_t)i * nM + j) * M + m];
-          }
-          t += ec.UM[j][k] * z;
-        }
-        const T mum = a.MU ? a.MU[((size_t)m * nM + k) * a.nb + i] : mu[k];
-        th[k] = transform_only<T>(cfg.transM[k], mum + sg[k] * t);
-        thetaMs_tr[i + a.nb * (k + (size_t)nM * m)] = th[k];
-      }
-      for (int s = 0; s < 4; s++) {
-        const int c = cfg.slot_code[s];
-        par[s] = c < 0 ? cfg.slot_fix[s] : c < nP ? transform_only<T>(cfg.transP[c], zetaP[(size_t)c * M + m]) : th[c - nP];
-      }
-      T* yo = y + (size_t)nO * (i + a.nb * (size_t)m);
-      for (int o = 0; o < nO; o++) {
-        // is_valid .* p: invalid drivers give NaN predictions (src/DoubleMM/f_doubleMM.jl:111-137)
-        const bool valid = isfinite(S1[o]) && isfinite(S2[o]);
-        yo[o] = valid ? par[0] + par[1] * S1[o] / (par[2] + S1[o]) * S2[o] / (par[3] + S2[o]) : T(NAN);
-      }
-    }
-  }
-  logsig = warp_sum(logsig);
-  if ((threadIdx.x & 31) == 0) part_logsig[gid >> 5] = logsig;
-}
-
-template <typename T>
-cudaError_t launch_predict(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, const T* pdraw, const T* xP,
-                           T* thetaP, T* thetaMs_tr, T* y, double* part_logsig, int* nparts) {
-  if (cfg.nO > 32) return cudaErrorInvalidConfiguration;
-  int64_t n = a.nb > (int64_t)cfg.nP * a.M ? a.nb : (int64_t)cfg.nP * a.M;
-  int64_t blocks = (n + 255) / 256;
-  if (blocks > (int64_t)L.sm_count * 16 && (int64_t)L.sm_count * 16 * 256 >= (int64_t)cfg.nP * a.M) blocks = (int64_t)L.sm_count * 16;
-  if (blocks < 1) blocks = 1;
-  k_predict<T><<<(int)blocks, 256, 0, L.stream>>>(cfg, a, pdraw, xP, thetaP, thetaMs_tr, y, part_logsig);
-  cudaError_t e_ = cudaGetLastError();
-  if (e_ != cudaSuccess) return e_;
-  if (L.counter) ++*L.counter;
-  *nparts = (int)blocks * 8;
-  return cudaSuccess;
-}
-template cudaError_t launch_predict<float>(const Launch&, const Cfg<float>&, const StreamArgs<float>&, const float*,
-                                           const float*, float*, float*, float*, double*, int*);
-template cudaError_t launch_predict<double>(const Launch&, const Cfg<double>&, const StreamArgs<double>&, const double*,
-                                            const double*, double*, double*, double*, double*, int*);
 
 // ---------------------------------------------------------------------------------------
 // launchers
