@@ -186,6 +186,16 @@ class NegElboPlan:
                                           tr.ctypes.data_as(C.POINTER(C.c_double)) if trace else None))
         return tr
 
+    def adam_phi_dev(self) -> int:
+        """Device address of the optimiser's ϕ (the `phi_dev` of `neg_elbo_async` in sharded jobs)."""
+        ptr = C.c_void_p()
+        self._check(self.lib.hvi_adam_phi_dev(self._h, C.byref(ptr)))
+        return ptr.value
+
+    def adam_apply_dev(self, out_dev, stream_ptr=0):
+        """One Adam update from an (all-reduced) device result vector [∇ϕ; components; nL; non-finite] of doubles."""
+        self._check(self.lib.hvi_adam_apply_dev(self._h, _ptr(out_dev), C.c_void_p(stream_ptr)))
+
     def adam_phi(self):
         ϕ = np.empty(self.prob.n_phi, dtype=self.dt)
         self._check(self.lib.hvi_adam_get_phi(self._h, _ptr(ϕ)))

@@ -30,3 +30,15 @@ def allreduce_result(out, dist=None):
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(out)
     return out
+
+
+def adam_step_sharded(plan, out_dev, n_MC: int, seed: int, site_offset: int, dist=None, stream_ptr: int = 0):
+    """One optimiser iteration of a site-sharded job without a host round trip: every rank evaluates its shard with
+    the replicated device ϕ of its plan (`adam_init` first), the result vectors are summed over the ranks and every rank
+    applies the same Adam update (`hvi_adam_apply_dev`), so ϕ stays replicated.  `out_dev`: float64 CUDA tensor of
+    n_phi + 8 elements; afterwards out_dev[n_phi + 6] is the job's loss of this iteration."""
+    plan.neg_elbo_async(plan.adam_phi_dev(), None, None, out_dev, n_MC, stream_ptr, seed=seed, site_offset=site_offset)
+    allreduce_result(out_dev, dist)
+    plan.adam_apply_dev(out_dev, stream_ptr)
+    return out_dev
+

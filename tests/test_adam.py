@@ -51,3 +51,44 @@ def test_adam_lowers_the_loss_and_needs_init():
     assert np.mean(tr[-20:]) < 0.5 * np.mean(tr[:20])
     assert plan.adam_run(5, 12, seed0=400, trace=False) is None     # nothing synchronised
     assert np.all(np.isfinite(plan.adam_phi()))
+
+
+def test_sharded_adam_steps_equal_unsharded():
+    """two site shards (two plans on one device stand in for two ranks; their result vectors are added where NCCL
+    would all-reduce them) walk the same trajectory as one plan over all sites"""
+    import torch
+    from hvi_b200.shard import adam_step_sharded, site_range
+    prob = hvi_b200.DoubleMMCase(dtype="f64")
+    nb, M, steps = 301, 4, 6
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=8)
+    ϕ0 = prob.init_ϕ(perturbed=True)
+    whole = hvi_b200.NegElboPlan(prob, device=0)
+    whole.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    whole.adam_init(ϕ0, eta=0.01)
+    want_trace = whole.adam_run(steps, M, seed0=21)
+    want = whole.adam_phi()
+    dev = torch.device("cuda", 0)
+    plans, offs, outs = [], [], []
+    for r in range(2):
+        lo, hi = site_range(nb, r, 2)
+        p = hvi_b200.NegElboPlan(prob, device=0, count_globals=(r == 0))
+        p.set_data(*(data[k][:, lo:hi] for k in ("xM", "xP", "y_o", "y_unc")))
+        p.adam_init(ϕ0, eta=0.01)
+        plans.append(p); offs.append(lo)
+        outs.append(torch.zeros(prob.n_phi + 8, dtype=torch.float64, device=dev))
+
+    trace = []
+    for it in range(steps):
+        for p, lo, o in zip(plans, offs, outs):
+            p.neg_elbo_async(p.adam_phi_dev(), None, None, o, M, 0, seed=21 + it, site_offset=lo)
+        torch.cuda.synchronize()
+        total = outs[0] + outs[1]
+        for p in plans:
+            p.adam_apply_dev(total)
+        torch.cuda.synchronize()
+        trace.append(float(total[prob.n_phi + 6]))
+    for p in plans:
+        got = p.adam_phi()
+        assert np.max(np.abs(got - want)) <= 1e-10 * max(1.0, np.max(np.abs(want)))
+    assert np.max(np.abs(np.array(trace) - want_trace)) <= 1e-10 * np.max(np.abs(want_trace))
+    assert callable(adam_step_sharded)
