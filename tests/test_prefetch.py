@@ -37,3 +37,23 @@ def test_prefetch_commit_equals_set_data(dtype):
     assert nL == want[0][0]
     with pytest.raises(Exception):
         plan.commit_data()
+
+
+def test_prefetch_commit_with_site_indices():
+    """MeanVarSep batches carry their global site indices: commit_data(i_sites) must behave like set_data(i_sites)"""
+    prob = hvi_b200.DoubleMMCase(("sepvar", "few_sites"), dtype="f64")
+    nb, M = 20, 4
+    ϕ = prob.init_ϕ(perturbed=True)
+    b1 = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=1)
+    b2 = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=2)
+    i1, i2 = np.arange(0, 20), np.arange(60, 80)[::-1].copy()
+    ref = hvi_b200.NegElboPlan(prob, device=0)
+    ref.set_data(b2["xM"], b2["xP"], b2["y_o"], b2["y_unc"], i_sites=i2)
+    want = ref.neg_elbo_withgradient(ϕ, n_MC=M, seed=3)
+    plan = hvi_b200.NegElboPlan(prob, device=0)
+    plan.set_data(b1["xM"], b1["xP"], b1["y_o"], b1["y_unc"], i_sites=i1)
+    plan.prefetch_data(b2["xM"], b2["xP"], b2["y_o"], b2["y_unc"])
+    plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=3)
+    plan.commit_data(i_sites=i2)
+    got = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=3)
+    assert got[0] == want[0] and np.array_equal(got[2], want[2])
