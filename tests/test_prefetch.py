@@ -57,3 +57,24 @@ def test_prefetch_commit_with_site_indices():
     plan.commit_data(i_sites=i2)
     got = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=3)
     assert got[0] == want[0] and np.array_equal(got[2], want[2])
+
+
+def test_prefetch_on_a_fresh_plan():
+    prob = hvi_b200.DoubleMMCase(dtype="f32")
+    b = hvi_b200.gen_hybridproblem_synthetic(prob, 97, seed=5)
+    ϕ = prob.init_ϕ(perturbed=True)
+    ref = hvi_b200.NegElboPlan(prob, device=0)
+    ref.set_data(b["xM"], b["xP"], b["y_o"], b["y_unc"])
+    want = ref.neg_elbo_withgradient(ϕ, n_MC=8, seed=2)
+    plan = hvi_b200.NegElboPlan(prob, device=0)
+    plan.prefetch_data(b["xM"], b["xP"], b["y_o"], b["y_unc"])
+    plan.commit_data()
+    got = plan.neg_elbo_withgradient(ϕ, n_MC=8, seed=2)
+    assert got[0] == want[0] and np.array_equal(got[2], want[2])
+    # prediction-only batch through the same route
+    plan.prefetch_data(b["xM"], b["xP"])
+    plan.commit_data()
+    y, θP, θMs, ent = plan.predict_hvi(ϕ, n_sample_pred=8, seed=3)
+    ref.set_data(b["xM"], b["xP"])
+    y2, _, θMs2, ent2 = ref.predict_hvi(ϕ, n_sample_pred=8, seed=3)
+    assert np.array_equal(y, y2) and np.array_equal(θMs, θMs2) and ent == ent2
