@@ -1217,6 +1217,21 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* sred) {
   return r;
 }
 
+// the same tree for n values per thread at once (one pass of barriers instead of n): sums[i] = Σ_threads v[i],
+// bit-identical to n separate calls; sred holds n·FIN_THREADS doubles, sums is shared memory
+__device__ __forceinline__ void block_sum_fixed_n(const double* v, int n, double* sred, double* sums) {
+  const int t = threadIdx.x;
+  for (int i = 0; i < n; i++) sred[i * FIN_THREADS + t] = v[i];
+  __syncthreads();
+  for (int s = FIN_THREADS / 2; s > 0; s >>= 1) {
+    if (t < s)
+      for (int i = 0; i < n; i++) sred[i * FIN_THREADS + t] += sred[i * FIN_THREADS + t + s];
+    __syncthreads();
+  }
+  if (t < n) sums[t] = sred[t * FIN_THREADS];
+  __syncthreads();
+}
+
 template <typename T>
 __device__ void build_U_adj(int n, const int* blk_start, const int* rho_off, const T (*U)[MAXP], const T* nrm,
                             const double (*Ubar)[MAXP], double* rho_bar) {
@@ -1252,6 +1267,23 @@ __global__ void __launch_bounds__(256) k_colsum(const double* __restrict__ part,
 // red[0..NACC) = column sums; red[128 + b] = number of non-finite entries seen by block b
 constexpr int RED_THREADS = 256;
 
+// Σ_{r = g, g+8, g+16, …} col[r·ld] in a fixed order with eight loads in flight (the reduction is latency bound:
+// a thread that adds one row after the other waits a DRAM/L2 round trip per row)
+__device__ __forceinline__ double strided_sum8(const double* __restrict__ col, int ld, int g, int nrows) {
+  double s[8];
+#pragma unroll
+  for (int u = 0; u < 8; u++) s[u] = 0.0;
+  int r = g;
+  for (; r + 56 < nrows; r += 64) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) s[u] += col[(size_t)(r + 8 * u) * ld];
+  }
+#pragma unroll
+  for (int u = 0; u < 8; u++)
+    if (r + 8 * u < nrows) s[u] += col[(size_t)(r + 8 * u) * ld];
+  return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS) k_reduce(int nphig, const double* __restrict__ part_mlp, int nblk,
                                                         const double* __restrict__ part_stream, int nrows, int NACC,
@@ -1263,12 +1295,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce(int nphig, const double*
     const int e = blockIdx.x * 32 + c;
     double s0 = 0, s1 = 0;
     if (e < nphig) {
-      int r = g;
-      for (; r + 8 < nblk; r += 16) {
-        s0 += part_mlp[(size_t)r * nphig + e];
-        s1 += part_mlp[(size_t)(r + 8) * nphig + e];
-      }
-      if (r < nblk) s0 += part_mlp[(size_t)r * nphig + e];
+      s0 = strided_sum8(part_mlp + e, nphig, g, nblk);
     }
     sm[g][c] = s0 + s1;
     __syncthreads();
@@ -1288,12 +1315,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce(int nphig, const double*
       const int a = a0 + c;
       double s0 = 0, s1 = 0;
       if (a < NACC) {
-        int r = g;
-        for (; r + 8 < nrows; r += 16) {
-          s0 += part_stream[(size_t)r * NACC + a];
-          s1 += part_stream[(size_t)(r + 8) * NACC + a];
-        }
-        if (r < nrows) s0 += part_stream[(size_t)r * NACC + a];
+        s0 = strided_sum8(part_stream + a, NACC, g, nrows);
       }
       sm[g][c] = s0 + s1;
       __syncthreads();
@@ -1317,7 +1339,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
                                                           const double* __restrict__ xs, const double* __restrict__ xu,
                                                           double const_nly, int64_t nb, int M,
                                                           double* __restrict__ out, T* __restrict__ grad_T) {
-  __shared__ double sred[FIN_THREADS];
+  __shared__ double sred[(3 + MAXP) * FIN_THREADS];
   __shared__ double sacc[128];
   __shared__ double sq[8 * MAXP + 2 * MAXP * MAXP + 16];   // ∇ϕq then the 8 trailing scalars
   const int t = threadIdx.x;
@@ -1327,6 +1349,16 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
   // here works on ∇ϕq with that block cut out
   const int big = cfg.sepvar ? nM * cfg.n_site_total : 0;
   const int nq = cfg.nphi - cfg.nphig - big;
+  // the serial section below reads the evaluation constants and a few entries of ϕ: fetch them with one parallel
+  // round trip instead of one dependent global load after the other
+  __shared__ EvalConsts<T> sec;
+  __shared__ T sls2P[MAXP];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(ecp);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sec);
+    for (int e = t; e < (int)(sizeof(EvalConsts<T>) / 4); e += FIN_THREADS) dst[e] = src[e];
+    if (t < nP) sls2P[t] = phi[cfg.o_ls2P + t];
+  }
   double bad = 0.0;
   for (int e = t; e < nred_blocks; e += FIN_THREADS) bad += red[128 + e];
   for (int e = t; e < NACC; e += FIN_THREADS) sacc[e] = red[e];
@@ -1349,10 +1381,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
           for (int jj = 0; jj <= j; jj++) v[3 + jj] += (double)dz * (double)zP[m + (size_t)M * jj];
         }
       }
-      for (int i = 0; i < 3 + j + 1; i++) {
-        const double r = block_sum_fixed(v[i], sred);
-        if (t == 0) sPg[j][i] = r;
-      }
+      block_sum_fixed_n(v, 3 + j + 1, sred, sPg[j]);
       // cotangent that reaches ζP[j, m] through the pbm covariate inputs of g (already scaled by 1/n_MC)
       if (xu) {
         for (int i = 0; i < 1 + MAXP; i++) v[i] = 0.0;
@@ -1364,16 +1393,13 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
             for (int jj = 0; jj <= j; jj++) v[1 + jj] += x * (double)zP[m + (size_t)M * jj];
           }
         }
-        for (int i = 0; i < 1 + j + 1; i++) {
-          const double r = block_sum_fixed(v[i], sred);
-          if (t == 0) sPx[j][i] = r;
-        }
+        block_sum_fixed_n(v, 1 + j + 1, sred, sPx[j]);
       }
     }
   }
   __syncthreads();
   if (t == 0) {
-    const EvalConsts<T>& ec = *ecp;
+    const EvalConsts<T>& ec = sec;
     const double w = 1.0 / (double)M;
     const int NUM = tri(nM);
     const double* abar = sacc + ACC_FIRST_VEC;
@@ -1407,7 +1433,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
         for (int jj = 0; jj <= j; jj++) CP[jj][j] += w * sPg[j][3 + jj];
         nlp += w * sPg[j][0] + (cfg.omit_priors ? 0.0 : cfg.prP_c0[j]);
         lj += w * sPg[j][1];
-        logsig += 0.5 * (double)phi[cfg.o_ls2P + j];
+        logsig += 0.5 * (double)sls2P[j];
       }
       if (xu) {
         aP += sPx[j][0];
