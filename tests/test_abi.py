@@ -85,3 +85,22 @@ def test_plan_create_validates_and_fails_loudly_without_gpu():
 def test_missing_library_raises():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         A.load_library(os.path.join(ROOT, "does_not_exist.so"))
+
+
+def test_entry_points_reject_a_null_plan():
+    """every plan-taking entry point returns HVI_EINVAL for plan == NULL instead of touching the device"""
+    lib = A.load_library()
+    n = None
+    assert lib.hvi_plan_set_data(n, 1, n, n, n, n, A.HVI_MEM_HOST) == A.HVI_EINVAL
+    assert lib.hvi_plan_prefetch_data(n, 1, n, n, n, n) == A.HVI_EINVAL
+    assert lib.hvi_plan_commit_data(n) == A.HVI_EINVAL
+    assert lib.hvi_plan_set_sites(n, None, 0) == A.HVI_EINVAL
+    assert lib.hvi_neg_elbo_grad(n, 1, n, n, n, A.HVI_MEM_HOST, None, None, n) == A.HVI_EINVAL
+    assert lib.hvi_neg_elbo_grad_rng(n, 1, n, 0, 0, A.HVI_MEM_HOST, None, None, n) == A.HVI_EINVAL
+    assert lib.hvi_loss_gf_grad(n, n, A.HVI_MEM_HOST, None, n) == A.HVI_EINVAL
+    assert lib.hvi_adam_init(n, n, 0.02, 0.9, 0.999, 1e-8) == A.HVI_EINVAL
+    assert lib.hvi_adam_run(n, 1, 1, 0, 0, None) == A.HVI_EINVAL
+    assert lib.hvi_adam_apply_dev(n, n, n) == A.HVI_EINVAL
+    assert lib.hvi_adam_get_phi(n, n) == A.HVI_EINVAL
+    assert lib.hvi_plan_destroy(n) == A.HVI_OK
+    assert lib.hvi_phi_len(n) == -1 and lib.hvi_launch_count(n) == -1
