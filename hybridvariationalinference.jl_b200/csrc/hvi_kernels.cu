@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) k_preprocess(int nO, int64_t nb, const T*
 // pdraw = 4 arrays [nP][M]: rP, ζP, θP, gP = dθP/dζP.
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__device__ void build_U(int n, const int* blk_start, const int* rho_off, const T* rho, T (*U)[MAXP], T* nrm) {
+__device__ __noinline__ void build_U(int n, const int* blk_start, const int* rho_off, const T* rho, T (*U)[MAXP], T* nrm) {
   for (int k = 0; k < n; k++) {
     T ss = T(1);
     for (int i = 0; i < n; i++) U[i][k] = T(0);
@@ -194,11 +194,11 @@ __global__ void k_prologue(const __grid_constant__ Cfg<T> cfg, const T* __restri
   if (threadIdx.x == 0) {
     build_U<T>(nP, cfg.blkP_start, cfg.rhoP_off, phi + cfg.o_rhoP, s.UP, s.nrmP);
     build_U<T>(nM, cfg.blkM_start, cfg.rhoM_off, phi + cfg.o_rhoM, s.UM, s.nrmM);
-    for (int k = 0; k < nM; k++) {   // intercept and slope of log σ² (src/elbo.jl:652-653); MeanVarSep has neither
+    _Pragma("unroll 1") for (int k = 0; k < nM; k++) {   // intercept and slope of log σ² (src/elbo.jl:652-653); MeanVarSep has neither
       s.coefA[k] = cfg.sepvar ? T(0) : phi[cfg.o_coef + 2 * k];
       s.coefB[k] = cfg.sepvar ? T(0) : phi[cfg.o_coef + 2 * k + 1];
     }
-    for (int j = 0; j < nP; j++) { s.sigP[j] = exp_t(phi[cfg.o_ls2P + j] / T(2)); s.muP[j] = phi[cfg.o_muP + j]; }
+    _Pragma("unroll 1") for (int j = 0; j < nP; j++) { s.sigP[j] = exp_t(phi[cfg.o_ls2P + j] / T(2)); s.muP[j] = phi[cfg.o_muP + j]; }
     *ec = s;
   }
   __syncthreads();
@@ -206,10 +206,10 @@ __global__ void k_prologue(const __grid_constant__ Cfg<T> cfg, const T* __restri
   T* zetaP = pdraw + (size_t)nP * M;
   T* thP = pdraw + (size_t)2 * nP * M;
   T* gP = pdraw + (size_t)3 * nP * M;
-  for (int e = threadIdx.x; e < nP * M; e += blockDim.x) {
+  _Pragma("unroll 1") for (int e = threadIdx.x; e < nP * M; e += blockDim.x) {
     const int j = e / M, m = e % M;
     T t = T(0);
-    for (int jj = cfg.blkP_start[j]; jj <= j; jj++) t += s.UP[jj][j] * zP[m + (size_t)M * jj];
+    _Pragma("unroll 1") for (int jj = cfg.blkP_start[j]; jj <= j; jj++) t += s.UP[jj][j] * zP[m + (size_t)M * jj];
     const T r = s.sigP[j] * t;
     const T zeta = s.muP[j] + r;
     T th, dth, pv, dz, lj;
@@ -1203,7 +1203,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
 // ---------------------------------------------------------------------------------------
 constexpr int FIN_THREADS = 256;
 
-__device__ __forceinline__ double block_sum_fixed(double v, double* sred) {
+__device__ __noinline__ double block_sum_fixed(double v, double* sred) {
   // fixed-shape tree: deterministic run to run
   const int t = threadIdx.x;
   sred[t] = v;
@@ -1219,7 +1219,7 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* sred) {
 
 // the same tree for n values per thread at once (one pass of barriers instead of n): sums[i] = Σ_threads v[i],
 // bit-identical to n separate calls; sred holds n·FIN_THREADS doubles, sums is shared memory
-__device__ __forceinline__ void block_sum_fixed_n(const double* v, int n, double* sred, double* sums) {
+__device__ __noinline__ void block_sum_fixed_n(const double* v, int n, double* sred, double* sums) {
   const int t = threadIdx.x;
   for (int i = 0; i < n; i++) sred[i * FIN_THREADS + t] = v[i];
   __syncthreads();
@@ -1233,7 +1233,7 @@ __device__ __forceinline__ void block_sum_fixed_n(const double* v, int n, double
 }
 
 template <typename T>
-__device__ void build_U_adj(int n, const int* blk_start, const int* rho_off, const T (*U)[MAXP], const T* nrm,
+__device__ __noinline__ void build_U_adj(int n, const int* blk_start, const int* rho_off, const T (*U)[MAXP], const T* nrm,
                             const double (*Ubar)[MAXP], double* rho_bar) {
   for (int k = 0; k < n; k++) {
     double dot = 0;
@@ -1330,6 +1330,8 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce(int nphig, const double*
   }
 }
 
+// k_finalize executes a few thousand instructions once; with a cold instruction cache (after a large streaming kernel)
+// its run time is instruction fetch, so loops are not unrolled and helpers are not inlined (4888 -> 2128 instructions)
 template <typename T>
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant__ Cfg<T> cfg,
                                                           const T* __restrict__ phi, const T* __restrict__ zP,
@@ -1356,41 +1358,41 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(ecp);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sec);
-    for (int e = t; e < (int)(sizeof(EvalConsts<T>) / 4); e += FIN_THREADS) dst[e] = src[e];
+    _Pragma("unroll 1") for (int e = t; e < (int)(sizeof(EvalConsts<T>) / 4); e += FIN_THREADS) dst[e] = src[e];
     if (t < nP) sls2P[t] = phi[cfg.o_ls2P + t];
   }
   double bad = 0.0;
-  for (int e = t; e < nred_blocks; e += FIN_THREADS) bad += red[128 + e];
-  for (int e = t; e < NACC; e += FIN_THREADS) sacc[e] = red[e];
-  for (int e = t; e < nq + 8; e += FIN_THREADS) sq[e] = 0.0;
+  _Pragma("unroll 1") for (int e = t; e < nred_blocks; e += FIN_THREADS) bad += red[128 + e];
+  _Pragma("unroll 1") for (int e = t; e < NACC; e += FIN_THREADS) sacc[e] = red[e];
+  _Pragma("unroll 1") for (int e = t; e < nq + 8; e += FIN_THREADS) sq[e] = 0.0;
   // prior and log-Jacobian of θP and their cotangents, once per evaluation: the
   // draws are spread over the threads, each sum is a fixed-shape tree
   __shared__ double sPg[MAXP][3 + MAXP];   // per j: Σ pv, Σ lj, Σ zb, Σ zb·zP[m, jj]
   __shared__ double sPx[MAXP][1 + MAXP];   // per j: Σ x̄, Σ x̄·zP[m, jj]  (pbm covariates)
   {
     const T* zetaP_ = pdraw + (size_t)nP * M;
-    for (int j = 0; j < nP; j++) {
+    _Pragma("unroll 1") for (int j = 0; j < nP; j++) {
       double v[3 + MAXP];
-      for (int i = 0; i < 3 + MAXP; i++) v[i] = 0.0;
+      _Pragma("unroll 1") for (int i = 0; i < 3 + MAXP; i++) v[i] = 0.0;
       if (cfg.count_globals) {
-        for (int m = t; m < M; m += FIN_THREADS) {
+        _Pragma("unroll 1") for (int m = t; m < M; m += FIN_THREADS) {
           T th, dth, pv, dz, ljm;
           transform_prior<T>(cfg.transP[j], cfg.omit_priors ? HVI_PR_NONE : cfg.prP_kind[j], cfg.prP_a[j],
                              cfg.prP_ib[j], cfg.clamp_lo, cfg.clamp_hi, zetaP_[(size_t)j * M + m], th, dth, pv, dz, ljm);
           v[0] += (double)pv; v[1] += (double)ljm; v[2] += (double)dz;
-          for (int jj = 0; jj <= j; jj++) v[3 + jj] += (double)dz * (double)zP[m + (size_t)M * jj];
+          _Pragma("unroll 1") for (int jj = 0; jj <= j; jj++) v[3 + jj] += (double)dz * (double)zP[m + (size_t)M * jj];
         }
       }
       block_sum_fixed_n(v, 3 + j + 1, sred, sPg[j]);
       // cotangent that reaches ζP[j, m] through the pbm covariate inputs of g (already scaled by 1/n_MC)
       if (xu) {
-        for (int i = 0; i < 1 + MAXP; i++) v[i] = 0.0;
-        for (int c = 0; c < cfg.npc; c++) {
+        _Pragma("unroll 1") for (int i = 0; i < 1 + MAXP; i++) v[i] = 0.0;
+        _Pragma("unroll 1") for (int c = 0; c < cfg.npc; c++) {
           if (cfg.pbm_covar_idx[c] != j) continue;
-          for (int m = t; m < M; m += FIN_THREADS) {
+          _Pragma("unroll 1") for (int m = t; m < M; m += FIN_THREADS) {
             const double x = xu[(size_t)m * cfg.npc + c];
             v[0] += x;
-            for (int jj = 0; jj <= j; jj++) v[1 + jj] += x * (double)zP[m + (size_t)M * jj];
+            _Pragma("unroll 1") for (int jj = 0; jj <= j; jj++) v[1 + jj] += x * (double)zP[m + (size_t)M * jj];
           }
         }
         block_sum_fixed_n(v, 1 + j + 1, sred, sPx[j]);
@@ -1414,43 +1416,43 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
     double lj = w * sacc[ACC_LJ];
     double logsig = sacc[ACC_LOGSIG];
     if (!cfg.omit_priors)
-      for (int k = 0; k < nM; k++) nlp += (double)nb * cfg.prM_c0[k];
+      _Pragma("unroll 1") for (int k = 0; k < nM; k++) nlp += (double)nb * cfg.prM_c0[k];
     // coefficients of log σ²
     if (!cfg.sepvar)
-      for (int k = 0; k < nM; k++) { *Gp(cfg.o_coef + 2 * k) = abar[k]; *Gp(cfg.o_coef + 2 * k + 1) = bbar[k]; }
+      _Pragma("unroll 1") for (int k = 0; k < nM; k++) { *Gp(cfg.o_coef + 2 * k) = abar[k]; *Gp(cfg.o_coef + 2 * k + 1) = bbar[k]; }
     // M block: Ū = w·cU (columns restricted to their block) → ρ̄sM
     double Ubar[MAXP][MAXP];
-    for (int k = 0; k < nM; k++)
-      for (int j = 0; j <= k; j++) Ubar[j][k] = w * cU[k * (k + 1) / 2 + j];
+    _Pragma("unroll 1") for (int k = 0; k < nM; k++)
+      _Pragma("unroll 1") for (int j = 0; j <= k; j++) Ubar[j][k] = w * cU[k * (k + 1) / 2 + j];
     build_U_adj<T>(nM, cfg.blkM_start, cfg.rhoM_off, ec.UM, ec.nrmM, Ubar, Gp(cfg.o_rhoM));
     // global block
     double CP[MAXP][MAXP];
-    for (int j = 0; j < nP; j++) {
+    _Pragma("unroll 1") for (int j = 0; j < nP; j++) {
       double aP = w * aPs[j];
-      for (int jj = 0; jj <= j; jj++) CP[jj][j] = w * cPs[j * (j + 1) / 2 + jj];
+      _Pragma("unroll 1") for (int jj = 0; jj <= j; jj++) CP[jj][j] = w * cPs[j * (j + 1) / 2 + jj];
       if (cfg.count_globals) {
         aP += w * sPg[j][2];
-        for (int jj = 0; jj <= j; jj++) CP[jj][j] += w * sPg[j][3 + jj];
+        _Pragma("unroll 1") for (int jj = 0; jj <= j; jj++) CP[jj][j] += w * sPg[j][3 + jj];
         nlp += w * sPg[j][0] + (cfg.omit_priors ? 0.0 : cfg.prP_c0[j]);
         lj += w * sPg[j][1];
         logsig += 0.5 * (double)sls2P[j];
       }
       if (xu) {
         aP += sPx[j][0];
-        for (int jj = 0; jj <= j; jj++) CP[jj][j] += sPx[j][1 + jj];
+        _Pragma("unroll 1") for (int jj = 0; jj <= j; jj++) CP[jj][j] += sPx[j][1 + jj];
       }
       *Gp(cfg.o_muP + j) += aP;
       // Σ_m ζ̄P[j,m]·rP[j,m] = σP[j] Σ_{jj} UP[jj][j]·CP[jj][j]
       double sr = 0;
-      for (int jj = cfg.blkP_start[j]; jj <= j; jj++) sr += (double)ec.UP[jj][j] * CP[jj][j];
+      _Pragma("unroll 1") for (int jj = cfg.blkP_start[j]; jj <= j; jj++) sr += (double)ec.UP[jj][j] * CP[jj][j];
       sr *= (double)ec.sigP[j];
       *Gp(cfg.o_ls2P + j) = 0.5 * sr - (cfg.count_globals ? 0.5 : 0.0);
-      for (int jj = 0; jj <= j; jj++) Ubar[jj][j] = (double)ec.sigP[j] * CP[jj][j];
+      _Pragma("unroll 1") for (int jj = 0; jj <= j; jj++) Ubar[jj][j] = (double)ec.sigP[j] * CP[jj][j];
     }
     build_U_adj<T>(nP, cfg.blkP_start, cfg.rhoP_off, ec.UP, ec.nrmP, Ubar, Gp(cfg.o_rhoP));
     // pass 1 of g took μP[idx] as input (src/elbo.jl:491)
     if (xs)
-      for (int c = 0; c < cfg.npc; c++) *Gp(cfg.o_muP + cfg.pbm_covar_idx[c]) += xs[c];
+      _Pragma("unroll 1") for (int c = 0; c < cfg.npc; c++) *Gp(cfg.o_muP + cfg.pbm_covar_idx[c]) += xs[c];
     const double Kdim = (double)nM * (double)nb + (cfg.count_globals ? nP : 0);
     const double ent = 0.5 * Kdim * 2.8378770664093454836 + logsig;   // (K·log(2πe) + 2Σlog σ)/2, logden_normal.jl:74
     const double nlj = -lj;
@@ -1459,7 +1461,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
     C[6] = C[0] - C[1] + C[2];
   }
   __syncthreads();
-  for (int e = t; e < nq + 7; e += FIN_THREADS) {
+  _Pragma("unroll 1") for (int e = t; e < nq + 7; e += FIN_THREADS) {
     const double v = sq[e];
     const int o = cfg.nphig + e + ((cfg.sepvar && cfg.nphig + e >= cfg.o_coef) ? big : 0);   // back to ϕ positions
     out[o] = v;
@@ -1467,7 +1469,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
     bad += isfinite(v) ? 0.0 : 1.0;
   }
   if (cfg.sepvar && t == 0)
-    for (int k = 0; k < nM; k++) bad += sacc[ACC_FIRST_VEC + k];
+    _Pragma("unroll 1") for (int k = 0; k < nM; k++) bad += sacc[ACC_FIRST_VEC + k];
   bad = block_sum_fixed(bad, sred);
   if (t == 0) out[cfg.nphi + 7] = bad;
 }
