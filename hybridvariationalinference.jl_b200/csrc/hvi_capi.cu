@@ -919,8 +919,11 @@ static int predict_t(hvi_plan* p, int M, const void* phi, const void* zP, const 
   if (rc) return rc;
   void *o1 = thetaP, *o2 = thetaMs_tr, *o3 = y, *tmp = nullptr;
   if (mem_kind == HVI_MEM_HOST) {
-    CU(p, cudaMalloc(&tmp, sizeof(T) * ((size_t)nP * M + nzM + ny)));
-    o1 = tmp; o2 = (T*)tmp + (size_t)nP * M; o3 = (T*)o2 + nzM;
+    // the three result arrays in one allocation, each starting on a 256-byte boundary (the prediction kernel
+    // writes y with 256-bit stores)
+    const size_t oM = (((size_t)nP * M + 63) / 64) * 64, oY = oM + ((nzM + 63) / 64) * 64;
+    CU(p, cudaMalloc(&tmp, sizeof(T) * (oY + ny)));
+    o1 = tmp; o2 = (T*)tmp + oM; o3 = (T*)tmp + oY;
   }
   const int64_t nth = nb > (int64_t)nP * M ? nb : (int64_t)nP * M;
   const size_t nls = (size_t)((nth + 255) / 256) * 8;
