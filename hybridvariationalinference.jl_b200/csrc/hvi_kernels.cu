@@ -1808,9 +1808,84 @@ cudaError_t launch_gen_normal(const Launch& L, T* z, int64_t n_cols, int M, uint
   return cudaSuccess;
 }
 
+// generate_ζ sized for its traffic (it reads ξ once and writes ζ once, n_θM values per site·draw each way): one thread
+// per site handles all its parameters, so that for a fixed (k, draw) the warp writes 32 consecutive sites of one row
+// of ζMs_tr (the kernel above alternates k between neighbouring threads and half-fills every sector); four draws per
+// step, the draws of a column are read as one 16-byte load when the layout allows it.
+template <typename T, int NM>
+__global__ void __launch_bounds__(256) k_generate_zeta_fast(const __grid_constant__ Cfg<T> cfg,
+                                                            const __grid_constant__ StreamArgs<T> a,
+                                                            const T* __restrict__ pdraw, T* __restrict__ zetaP,
+                                                            T* __restrict__ zetaMs_tr, T* __restrict__ sigma) {
+  const int nP = cfg.nP, M = a.M;
+  const EvalConsts<T>& ec = *a.ec;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t e = gid; e < (int64_t)nP * M; e += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e / M), m = (int)(e % M);
+    zetaP[j + (size_t)nP * m] = pdraw[(size_t)nP * M + e];  // ζP array of pdraw
+  }
+  if (gid < nP) sigma[gid] = ec.sigP[gid];
+  constexpr int CH = 16 / (int)sizeof(T);
+  const bool vec = (M % CH == 0) && (((uintptr_t)a.zMs & 15) == 0);
+  for (int64_t i = gid; i < a.nb; i += (int64_t)gridDim.x * blockDim.x) {
+    T mu[NM], U[NM][NM];
+#pragma unroll
+    for (int k = 0; k < NM; k++) {
+      mu[k] = a.mu[i * NM + k];
+      const T sg = exp_t(T(0.5) * (cfg.sepvar ? a.phi[cfg.o_coef + (a.i_sites ? a.i_sites[i] : i) * NM + k]
+                                              : ec.coefA[k] + ec.coefB[k] * mu[k]));
+      sigma[nP + i * NM + k] = sg;
+#pragma unroll
+      for (int j = 0; j < NM; j++) U[j][k] = (j >= cfg.blkM_start[k] && j <= k) ? ec.UM[j][k] * sg : T(0);
+    }
+    const T* zrow = a.zMs + (size_t)i * NM * M;
+    T* out = zetaMs_tr + i;
+    for (int m0 = 0; m0 < M; m0 += CH) {
+      T z[NM][CH];
+#pragma unroll
+      for (int j = 0; j < NM; j++) {
+        if (vec) {
+          if constexpr (sizeof(T) == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(zrow + (size_t)j * M + m0);
+            z[j][0] = v.x; z[j][1] = v.y; z[j][2] = v.z; z[j][3] = v.w;
+          } else {
+            const double2 v = *reinterpret_cast<const double2*>(zrow + (size_t)j * M + m0);
+            z[j][0] = v.x; z[j][1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < CH; d++) z[j][d] = m0 + d < M ? zrow[(size_t)j * M + m0 + d] : T(0);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < CH; d++) {
+        const int m = m0 + d;
+        if (m >= M) break;
+#pragma unroll
+        for (int k = 0; k < NM; k++) {
+          T r = a.MU ? a.MU[((size_t)m * NM + k) * a.nb + i] : mu[k];   // pass-2 mean with pbm covariates
+#pragma unroll
+          for (int j = 0; j <= k; j++) r = fma(U[j][k], z[j][d], r);
+          __stcs(out + a.nb * (k + (size_t)NM * m), r);
+        }
+      }
+    }
+  }
+}
+
 template <typename T>
 cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, const T* pdraw, T* zetaP,
                                  T* zetaMs_tr, T* sigma) {
+  if (cfg.nM >= 1 && cfg.nM <= 3) {
+    int64_t blocks = (a.nb + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > (int64_t)L.sm_count * 16) blocks = (int64_t)L.sm_count * 16;
+    if (cfg.nM == 1) k_generate_zeta_fast<T, 1><<<(int)blocks, 256, 0, L.stream>>>(cfg, a, pdraw, zetaP, zetaMs_tr, sigma);
+    else if (cfg.nM == 2) k_generate_zeta_fast<T, 2><<<(int)blocks, 256, 0, L.stream>>>(cfg, a, pdraw, zetaP, zetaMs_tr, sigma);
+    else k_generate_zeta_fast<T, 3><<<(int)blocks, 256, 0, L.stream>>>(cfg, a, pdraw, zetaP, zetaMs_tr, sigma);
+    HVI_LAUNCH_CHECK();
+    return cudaSuccess;
+  }
   int64_t n = a.nb * cfg.nM;
   if (n < (int64_t)cfg.nP * a.M) n = (int64_t)cfg.nP * a.M;
   int64_t blocks = (n + 255) / 256;
