@@ -73,6 +73,10 @@ SYMBOLS = [
     ("hvi_plan_prefetch_data", _INT, [_P, _I64, _P, _P, _P, _P]),
     ("hvi_plan_commit_data", _INT, [_P]),
     ("hvi_plan_set_sites", _INT, [_P, C.POINTER(_I64), _I64]),
+    ("hvi_plan_set_dataset", _INT, [_P, _I64, _P, _P, _P, _P, _INT]),
+    ("hvi_plan_select_range", _INT, [_P, _I64, _I64]),
+    ("hvi_plan_select_batch", _INT, [_P, _P, _I64, _INT]),
+    ("hvi_plan_set_stream", _INT, [_P, _P, _INT]),
     ("hvi_neg_elbo_grad", _INT, [_P, _I32, _P, _P, _P, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_rng", _INT, [_P, _I32, _P, _U64, _I64, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_async", _INT, [_P, _I32, _P, _P, _P, _U64, _I64, _P, _P]),
@@ -80,6 +84,8 @@ SYMBOLS = [
     ("hvi_adam_init", _INT, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double]),
     ("hvi_adam_run", _INT, [_P, _I32, _I32, _U64, _I64, _DP]),
     ("hvi_adam_apply_dev", _INT, [_P, _P, _P]),
+    ("hvi_adam_run_minibatches", _INT, [_P, _I32, _I32, _U64, _I64, _I64, _DP]),
+    ("hvi_plan_use_graphs", _INT, [_P, _INT]),
     ("hvi_adam_phi_dev", _INT, [_P, C.POINTER(_P)]),
     ("hvi_adam_get_phi", _INT, [_P, _P]),
     ("hvi_generate_zeta", _INT, [_P, _I32, _P, _P, _P, _INT, _P, _P, _P]),

@@ -1,14 +1,25 @@
 #!/bin/bash
 # Builds libhvi_b200.so (sm_100a only) in-tree.  Usage: ./build.sh [extra nvcc flags]
+# HVI_REBUILD=1 forces every object to be recompiled.  A failed compile fails the script (and never leaves a
+# stale object behind for the link step).
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --use_fast_math=false -Xcompiler -fPIC -Xcompiler -O2"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
-for f in hvi_kernels hvi_capi hvi_dense_tc hvi_dense_tma hvi_mlp_mma hvi_point hvi_predict; do
-  if [ ! -f $f.o ] || [ $f.cu -nt $f.o ] || [ hvi_internal.cuh -nt $f.o ] || [ hvi_tc_common.cuh -nt $f.o ] || [ hvi_rng.cuh -nt $f.o ] || [ ../../include/hvi_b200.h -nt $f.o ]; then
+SRCS="hvi_kernels hvi_capi hvi_dense_tc hvi_dense_tma hvi_mlp_mma hvi_point hvi_predict"
+HDRS="hvi_internal.cuh hvi_tc_common.cuh hvi_rng.cuh hvi_pbm.cuh ../../include/hvi_b200.h"
+pids=()
+for f in $SRCS; do
+  stale=0
+  if [ -n "$HVI_REBUILD" ] || [ ! -f $f.o ] || [ $f.cu -nt $f.o ]; then stale=1; fi
+  for h in $HDRS; do if [ -f $h ] && [ $h -nt $f.o ]; then stale=1; fi; done
+  if [ $stale = 1 ]; then
+    rm -f $f.o
     $NVCC $FLAGS "$@" -c $f.cu -o $f.o &
+    pids+=($!)
   fi
 done
-wait
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libhvi_b200.so hvi_kernels.o hvi_capi.o hvi_dense_tc.o hvi_dense_tma.o hvi_mlp_mma.o hvi_point.o hvi_predict.o
+for pid in "${pids[@]}"; do wait $pid || { echo "build.sh: a compile failed" >&2; exit 1; }; done
+OBJS=""
+for f in $SRCS; do OBJS="$OBJS $f.o"; done
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libhvi_b200.so $OBJS

@@ -13,13 +13,20 @@
 
 using namespace hvi;
 
+struct GraphKey { const void* ptrs[32]; int64_t v[8]; };
+
 struct hvi_plan {
   hvi_desc desc;
   int dtype;
   size_t es;  // element size
   Cfg<float> cf;
   Cfg<double> cd;
-  cudaStream_t stream;
+  cudaStream_t stream;       // the stream every call works on: own_stream, or the caller's (hvi_plan_set_stream)
+  cudaStream_t own_stream;
+  // ordering against caller streams: ev_user marks the last work an _async / _apply_dev call put on a caller's stream;
+  // every later call on `stream` waits for it first.  ev_plan orders a caller's stream behind the plan's own work.
+  cudaEvent_t ev_user, ev_plan;
+  int user_pending;
   int sm_count;
   int64_t launches;
   std::string err;
@@ -36,8 +43,14 @@ struct hvi_plan {
   int64_t cap_cur, cap_next;   // capacity in sites of (d_xM, d_xP) and of their _next twins
   int64_t nb_next;             // > 0: a prefetched batch is pending
   int has_obs_next;
-  double const_nly;
-  int64_t anomalies;
+  double* d_bconst;            // device: {½Σy_unc over the finite observations, anomaly count} of the current batch
+  double* h_bconst;            // pinned copy (fetched with the result of a synchronous evaluation)
+  int64_t anomalies;           // host copy of the anomaly count; -1: not fetched yet for this batch
+  // device-resident dataset (hvi_plan_set_dataset): raw arrays, column = site
+  int64_t ds_n; int ds_has_obs;
+  void *ds_xM, *ds_xP, *ds_yo, *ds_yu;
+  int64_t* d_idx; int64_t cap_idx;   // minibatch indices of hvi_plan_select_batch
+  int64_t n_isites;                  // length of d_isites
   // per-evaluation scratch
   void* d_phi;
   void* d_zP; int64_t cap_zP;
@@ -65,7 +78,12 @@ struct hvi_plan {
   double* d_ls; int64_t cap_ls;       // per-warp Σ log σ partials of hvi_predict
   // device-resident Adam state (hvi_adam_*): ϕ in the working type, moments in double
   void* d_phi_opt; double *d_adam_m, *d_adam_v, *d_trace; int64_t cap_trace;
-  double adam_eta, adam_b1, adam_b2, adam_eps; int64_t adam_t;
+  double adam_eta, adam_b1, adam_b2, adam_eps;
+  // device counters of the optimiser loop: [0] applied Adam steps, [1] iteration index inside the running hvi_adam_run,
+  // [2] seed of the current iteration, [3] block counter of k_adam
+  unsigned long long* d_ctr;
+  // one optimiser iteration captured as a CUDA graph (replayed by hvi_adam_run)
+  cudaGraphExec_t adam_graph; GraphKey graph_key; int graph_valid, graph_nodes, use_graphs;
   // optional per-kernel timing (CUDA events on the launching stream)
   int profiling;
   cudaEvent_t ev[8];
@@ -240,7 +258,11 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   fill_cfg<double>(*desc, p->cd);
   p->nb = 0; p->launches = 0;
   p->d_ls = nullptr; p->cap_ls = 0;
-  p->d_phi_opt = nullptr; p->d_adam_m = p->d_adam_v = p->d_trace = nullptr; p->cap_trace = 0; p->adam_t = 0;
+  p->d_phi_opt = nullptr; p->d_adam_m = p->d_adam_v = p->d_trace = nullptr; p->cap_trace = 0;
+  p->d_ctr = nullptr; p->adam_graph = nullptr; p->graph_valid = 0; p->graph_nodes = 0; p->use_graphs = 1;
+  p->own_stream = nullptr; p->ev_user = p->ev_plan = nullptr; p->user_pending = 0;
+  p->d_bconst = nullptr; p->h_bconst = nullptr;
+  p->ds_n = 0; p->ds_has_obs = 0; p->ds_xM = p->ds_xP = p->ds_yo = p->ds_yu = nullptr; p->d_idx = nullptr; p->cap_idx = 0; p->n_isites = 0;
   p->copy_stream = nullptr; p->ev_copied = nullptr; p->d_xM_next = p->d_xP_next = nullptr;
   p->cap_cur = p->cap_next = p->nb_next = 0; p->has_obs_next = 0;
   p->d_xM = p->d_rec = p->d_mu = p->d_mubar = nullptr; p->d_xP = nullptr; p->has_obs = 0; p->d_isites = nullptr;
@@ -254,7 +276,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   p->d_wide_cache = nullptr; p->cap_wide_cache = 0;
   p->d_part_stream = p->d_part_mlp = p->d_out = p->d_red = nullptr;
   p->d_grad = nullptr; p->h_out = nullptr; p->h_grad = nullptr;
-  p->const_nly = 0; p->anomalies = 0;
+  p->anomalies = 0;
   p->profiling = 0; p->n_ev = 0;
   for (auto& e_ : p->ev) e_ = nullptr;
 #define CRE(call)                                                                   \
@@ -271,7 +293,10 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   CRE(cudaGetDeviceProperties(&prop, desc->device));
   p->sm_count = prop.multiProcessorCount;
   p->stream = nullptr;
-  CRE(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  CRE(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+  p->stream = p->own_stream;
+  CRE(cudaEventCreateWithFlags(&p->ev_user, cudaEventDisableTiming));
+  CRE(cudaEventCreateWithFlags(&p->ev_plan, cudaEventDisableTiming));
   const int nphi = p->cf.nphi;
   p->max_rows = stream_max_rows(p->sm_count);
   p->max_blk = mlp_bwd_max_blocks(p->sm_count);
@@ -286,6 +311,10 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   CRE(cudaMallocHost(&p->h_out, sizeof(double) * (size_t)(nphi + 8)));
   CRE(cudaMallocHost(&p->h_grad, p->es * (size_t)nphi));
   CRE(cudaMallocHost(&p->h_pre, sizeof(double) * (size_t)2 * p->sm_count * 8 * 8));
+  CRE(cudaMalloc((void**)&p->d_bconst, sizeof(double) * 2));
+  CRE(cudaMallocHost((void**)&p->h_bconst, sizeof(double) * 2));
+  CRE(cudaMalloc((void**)&p->d_ctr, sizeof(unsigned long long) * 4));
+  CRE(cudaMemset(p->d_ctr, 0, sizeof(unsigned long long) * 4));
 #undef CRE
   *out = p;
   return HVI_OK;
@@ -295,16 +324,22 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   if (!p) return HVI_OK;
   cudaSetDevice(p->desc.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
+  if (p->own_stream && p->own_stream != p->stream) cudaStreamSynchronize(p->own_stream);
+  if (p->user_pending && p->ev_user) cudaEventSynchronize(p->ev_user);
+  if (p->adam_graph) cudaGraphExecDestroy(p->adam_graph);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->ev_copied) cudaEventDestroy(p->ev_copied);
-  void* dev[] = {p->d_ls, p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->d_trace, p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
+  void* dev[] = {p->d_bconst, p->d_ctr, p->ds_xM, p->ds_xP, p->ds_yo, p->ds_yu, p->d_idx, p->d_ls, p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->d_trace, p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
                  p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide, p->d_wide_bwd, p->d_gacc, p->d_wide_cache};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
   if (p->h_grad) cudaFreeHost(p->h_grad);
   if (p->h_pre) cudaFreeHost(p->h_pre);
+  if (p->h_bconst) cudaFreeHost(p->h_bconst);
   for (auto& e_ : p->ev) if (e_) cudaEventDestroy(e_);
-  if (p->stream) cudaStreamDestroy(p->stream);
+  if (p->ev_user) cudaEventDestroy(p->ev_user);
+  if (p->ev_plan) cudaEventDestroy(p->ev_plan);
+  if (p->own_stream) cudaStreamDestroy(p->own_stream);
   delete p;
   return HVI_OK;
 }
@@ -348,6 +383,47 @@ extern "C" int64_t hvi_cor_count(const int32_t* cor_ends, int32_t n) {
 
 extern "C" int64_t hvi_launch_count(const hvi_plan* p) { return p ? p->launches : -1; }
 
+// ---- stream ordering ---------------------------------------------------------------------
+// Work that an _async / _apply_dev call left on a caller's stream is awaited (on the device, not the host) before
+// anything else touches the plan's buffers on `stream`.
+static int join_user(hvi_plan* p) {
+  if (p->user_pending) {
+    CU(p, cudaStreamWaitEvent(p->stream, p->ev_user, 0));
+    p->user_pending = 0;
+  }
+  return HVI_OK;
+}
+// a caller's stream `s` is about to read/write plan buffers: order it behind everything queued on `stream`
+static int fork_to(hvi_plan* p, cudaStream_t s) {
+  if (s != p->stream) {
+    CU(p, cudaEventRecord(p->ev_plan, p->stream));
+    CU(p, cudaStreamWaitEvent(s, p->ev_plan, 0));
+  }
+  return HVI_OK;
+}
+static int mark_user(hvi_plan* p, cudaStream_t s) {
+  if (s != p->stream) {
+    CU(p, cudaEventRecord(p->ev_user, s));
+    p->user_pending = 1;
+  }
+  return HVI_OK;
+}
+
+extern "C" int hvi_plan_set_stream(hvi_plan* p, void* cuda_stream, int use_own) {
+  if (!p) return HVI_EINVAL;
+  CU(p, cudaSetDevice(p->desc.device));
+  cudaStream_t ns = use_own ? p->own_stream : (cudaStream_t)cuda_stream;
+  if (ns == p->stream) return HVI_OK;
+  int rc = join_user(p);
+  if (rc) return rc;
+  // the new stream continues after everything queued on the old one
+  CU(p, cudaEventRecord(p->ev_plan, p->stream));
+  CU(p, cudaStreamWaitEvent(ns, p->ev_plan, 0));
+  p->stream = ns;
+  p->graph_valid = 0;   // a captured optimiser iteration belongs to the stream it was captured on
+  return HVI_OK;
+}
+
 extern "C" int hvi_plan_set_sites(hvi_plan* p, const int64_t* i_sites, int64_t n) {
   if (!p) return HVI_EINVAL;
   if (p->nb <= 0) PLAN_FAIL(p, HVI_ENODATA, "hvi_plan_set_data has not been called");
@@ -356,8 +432,14 @@ extern "C" int hvi_plan_set_sites(hvi_plan* p, const int64_t* i_sites, int64_t n
     for (int64_t i = 0; i < n; i++)
       if (i_sites[i] < 0 || i_sites[i] >= p->cf.n_site_total) PLAN_FAIL(p, HVI_EINVAL, "set_sites: index out of range");
   CU(p, cudaSetDevice(p->desc.device));
-  if (!p->d_isites) CU(p, cudaMalloc((void**)&p->d_isites, sizeof(int64_t) * (size_t)n));
-  CU(p, cudaMemcpy(p->d_isites, i_sites, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice));
+  int rc = join_user(p);
+  if (rc) return rc;
+  CU(p, cudaStreamSynchronize(p->stream));   // nothing in flight reads the old index array
+  if (p->d_isites) { cudaFree(p->d_isites); p->d_isites = nullptr; p->n_isites = 0; }
+  CU(p, cudaMalloc((void**)&p->d_isites, sizeof(int64_t) * (size_t)n));
+  p->n_isites = n;
+  CU(p, cudaMemcpyAsync(p->d_isites, i_sites, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, p->stream));
+  CU(p, cudaStreamSynchronize(p->stream));
   return HVI_OK;
 }
 
@@ -407,6 +489,19 @@ static int alloc_batch(hvi_plan* p, int64_t nb, bool keep_raw) {
   return HVI_OK;
 }
 
+// after the partial sums of a (gather-)preprocess launch: reduce them into the device-resident batch constants
+static int finish_consts(hvi_plan* p, int nrows, bool sync_fetch) {
+  Launch L{p->stream, p->sm_count, &p->launches};
+  CU(p, launch_batch_consts(L, p->d_part_stream, nrows, p->d_bconst));
+  p->anomalies = -1;   // fetched with the next synchronous result (or here)
+  if (sync_fetch) {
+    CU(p, cudaMemcpyAsync(p->h_bconst, p->d_bconst, sizeof(double) * 2, cudaMemcpyDeviceToHost, p->stream));
+    CU(p, cudaStreamSynchronize(p->stream));
+    p->anomalies = (int64_t)p->h_bconst[1];
+  }
+  return HVI_OK;
+}
+
 // re-tile the raw batch on the device (k_preprocess) and fetch the two batch constants
 template <typename T>
 static int finish_batch(hvi_plan* p, int64_t nb, const T* dxP, const T* dyo, const T* dyu) {
@@ -417,13 +512,8 @@ static int finish_batch(hvi_plan* p, int64_t nb, const T* dxP, const T* dyo, con
   const int NACC = nacc(p->cf.nP, p->cf.nM);
   if ((size_t)2 * p->sm_count * 8 * 8 > (size_t)p->max_rows * NACC) PLAN_FAIL(p, HVI_EINVAL, "internal: scratch too small");
   CU(p, launch_preprocess<T>(L, nO, nb, dxP, dyo, dyu, (T*)p->d_rec, p->d_part_stream, &nrows));
-  CU(p, cudaMemcpyAsync(p->h_pre, p->d_part_stream, sizeof(double) * 2 * nrows, cudaMemcpyDeviceToHost, p->stream));
-  CU(p, cudaStreamSynchronize(p->stream));
-  double c = 0, an = 0;
-  for (int r = 0; r < nrows; r++) { c += p->h_pre[2 * r]; an += p->h_pre[2 * r + 1]; }
-  p->const_nly = c;
-  p->anomalies = (int64_t)an;
-  return HVI_OK;
+  // synchronous: the caller's host arrays are free again at return, and the anomaly count is known
+  return finish_consts(p, nrows, true);
 }
 
 template <typename T>
@@ -434,7 +524,10 @@ static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, c
     CU(p, cudaStreamSynchronize(p->copy_stream));
     p->nb_next = 0;
   }
-  int rc = alloc_batch<T>(p, nb, false);
+  int rc = join_user(p);
+  if (rc) return rc;
+  CU(p, cudaStreamSynchronize(p->stream));   // evaluations in flight still read the old batch
+  rc = alloc_batch<T>(p, nb, false);
   if (rc) return rc;
   CU(p, copy_in(p->d_xM, xM, sizeof(T) * (size_t)nC * nb, mem_kind, p->stream));
   const T *dxP = (const T*)xP, *dyo = (const T*)y_o, *dyu = (const T*)y_unc;
@@ -493,6 +586,9 @@ template <typename T>
 static int commit_t(hvi_plan* p) {
   const int nO = p->desc.n_obs;
   const int64_t nb = p->nb_next;
+  int rcj = join_user(p);
+  if (rcj) return rcj;
+  CU(p, cudaStreamSynchronize(p->stream));   // evaluations in flight still read the old batch
   CU(p, cudaStreamWaitEvent(p->stream, p->ev_copied, 0));
   std::swap(p->d_xM, p->d_xM_next);
   std::swap(p->d_xP, p->d_xP_next);
@@ -514,7 +610,7 @@ extern "C" int hvi_plan_set_data(hvi_plan* p, int64_t n_site, const void* xM, co
   if (mem_kind != HVI_MEM_HOST && mem_kind != HVI_MEM_DEVICE) PLAN_FAIL(p, HVI_EINVAL, "set_data: bad mem_kind");
   CU(p, cudaSetDevice(p->desc.device));
   if (p->cf.sepvar && n_site > p->cf.n_site_total) PLAN_FAIL(p, HVI_EINVAL, "set_data: batch has more sites than n_site_total");
-  if (p->d_isites) { cudaFree(p->d_isites); p->d_isites = nullptr; }   // back to the identity map
+  if (p->d_isites) { cudaStreamSynchronize(p->stream); cudaFree(p->d_isites); p->d_isites = nullptr; p->n_isites = 0; }   // back to the identity map
   return p->dtype == HVI_F32 ? set_data_t<float>(p, n_site, xM, xP, y_o, y_unc, mem_kind)
                              : set_data_t<double>(p, n_site, xM, xP, y_o, y_unc, mem_kind);
 }
@@ -533,8 +629,123 @@ extern "C" int hvi_plan_commit_data(hvi_plan* p) {
   if (!p) return HVI_EINVAL;
   if (p->nb_next <= 0) PLAN_FAIL(p, HVI_ENODATA, "commit_data: no prefetched batch (call hvi_plan_prefetch_data first)");
   CU(p, cudaSetDevice(p->desc.device));
-  if (p->d_isites) { cudaFree(p->d_isites); p->d_isites = nullptr; }   // back to the identity map
+  if (p->d_isites) { cudaStreamSynchronize(p->stream); cudaFree(p->d_isites); p->d_isites = nullptr; p->n_isites = 0; }   // back to the identity map
   return p->dtype == HVI_F32 ? commit_t<float>(p) : commit_t<double>(p);
+}
+
+// ---- device-resident dataset and minibatch selection -----------------------------------------
+// gdev_hybridproblem_dataloader (src/AbstractHybridProblem.jl:220-250) moves the whole training set to the device once;
+// solve walks its minibatches (src/HybridSolver.jl:259-260; consecutive column ranges, last partial batch dropped,
+// src/AbstractHybridProblem.jl:206-207).  set_dataset is the one upload; select_range / select_batch make a minibatch
+// the registered batch with one gather kernel and no host round trip.
+template <typename T>
+static int set_dataset_t(hvi_plan* p, int64_t N, const void* xM, const void* xP, const void* y_o, const void* y_unc,
+                         int mem_kind) {
+  const int nO = p->desc.n_obs, nC = p->desc.n_covar;
+  int rc = join_user(p);
+  if (rc) return rc;
+  CU(p, cudaStreamSynchronize(p->stream));
+  for (void** q : {&p->ds_xM, &p->ds_xP, &p->ds_yo, &p->ds_yu}) { if (*q) cudaFree(*q); *q = nullptr; }
+  p->ds_n = 0;
+  p->ds_has_obs = (y_o && y_unc) ? 1 : 0;
+  CU(p, cudaMalloc(&p->ds_xM, sizeof(T) * (size_t)nC * N));
+  CU(p, cudaMalloc(&p->ds_xP, sizeof(T) * (size_t)2 * nO * N));
+  CU(p, copy_in(p->ds_xM, xM, sizeof(T) * (size_t)nC * N, mem_kind, p->stream));
+  CU(p, copy_in(p->ds_xP, xP, sizeof(T) * (size_t)2 * nO * N, mem_kind, p->stream));
+  if (p->ds_has_obs) {
+    CU(p, cudaMalloc(&p->ds_yo, sizeof(T) * (size_t)nO * N));
+    CU(p, cudaMalloc(&p->ds_yu, sizeof(T) * (size_t)nO * N));
+    CU(p, copy_in(p->ds_yo, y_o, sizeof(T) * (size_t)nO * N, mem_kind, p->stream));
+    CU(p, copy_in(p->ds_yu, y_unc, sizeof(T) * (size_t)nO * N, mem_kind, p->stream));
+  }
+  CU(p, cudaStreamSynchronize(p->stream));   // the caller's arrays are free again at return
+  p->ds_n = N;
+  return HVI_OK;
+}
+
+// MeanVarSep reads its per-site parameters through d_isites: the gather kernel writes the selected sites there
+static int select_sites(hvi_plan* p, int64_t n);
+
+template <typename T>
+static int select_t(hvi_plan* p, const int64_t* idx_dev, int64_t first, int64_t n,
+                    const unsigned long long* ctr = nullptr, int64_t n_batches = 1) {
+  const int nO = p->desc.n_obs, nC = p->desc.n_covar;
+  if (p->nb_next > 0) { CU(p, cudaStreamSynchronize(p->copy_stream)); p->nb_next = 0; }
+  if (n != p->nb || p->cap_cur < n) {
+    CU(p, cudaStreamSynchronize(p->stream));   // buffers of the old size may still be in use
+    int rc = alloc_batch<T>(p, n, false);
+    if (rc) return rc;
+  }
+  int rc = select_sites(p, n);
+  if (rc) return rc;
+  p->has_obs = p->ds_has_obs;
+  Launch L{p->stream, p->sm_count, &p->launches};
+  int nrows = 0;
+  CU(p, launch_gather_preprocess<T>(L, nC, nO, n, idx_dev, first, (const T*)p->ds_xM, (const T*)p->ds_xP,
+                                    (const T*)p->ds_yo, (const T*)p->ds_yu, (T*)p->d_xM, (T*)p->d_xP, (T*)p->d_rec,
+                                    p->d_part_stream, &nrows, ctr, n_batches, p->d_isites));
+  return finish_consts(p, nrows, false);
+}
+
+extern "C" int hvi_plan_set_dataset(hvi_plan* p, int64_t n_site_total, const void* xM, const void* xP, const void* y_o,
+                                    const void* y_unc, int mem_kind) {
+  if (!p) return HVI_EINVAL;
+  if (n_site_total < 1 || !xM || !xP) PLAN_FAIL(p, HVI_EINVAL, "set_dataset: n_site_total must be >= 1 and xM, xP non-NULL");
+  if ((y_o == nullptr) != (y_unc == nullptr)) PLAN_FAIL(p, HVI_EINVAL, "set_dataset: y_o and y_unc must both be given or both be NULL");
+  if (mem_kind != HVI_MEM_HOST && mem_kind != HVI_MEM_DEVICE) PLAN_FAIL(p, HVI_EINVAL, "set_dataset: bad mem_kind");
+  if (p->cf.sepvar && n_site_total != p->cf.n_site_total)
+    PLAN_FAIL(p, HVI_EINVAL, "set_dataset: MeanVarSep needs the dataset to hold exactly n_site_total sites");
+  CU(p, cudaSetDevice(p->desc.device));
+  return p->dtype == HVI_F32 ? set_dataset_t<float>(p, n_site_total, xM, xP, y_o, y_unc, mem_kind)
+                             : set_dataset_t<double>(p, n_site_total, xM, xP, y_o, y_unc, mem_kind);
+}
+
+extern "C" int hvi_plan_select_range(hvi_plan* p, int64_t first, int64_t n) {
+  if (!p) return HVI_EINVAL;
+  if (p->ds_n <= 0) PLAN_FAIL(p, HVI_ENODATA, "select_range: hvi_plan_set_dataset has not been called");
+  if (first < 0 || n < 1 || first + n > p->ds_n) PLAN_FAIL(p, HVI_EINVAL, "select_range: [first, first + n) is not inside the dataset");
+  CU(p, cudaSetDevice(p->desc.device));
+  int rc = join_user(p);
+  if (rc) return rc;
+  return p->dtype == HVI_F32 ? select_t<float>(p, nullptr, first, n) : select_t<double>(p, nullptr, first, n);
+}
+
+extern "C" int hvi_plan_select_batch(hvi_plan* p, const int64_t* i_sites, int64_t n, int mem_kind) {
+  if (!p) return HVI_EINVAL;
+  if (p->ds_n <= 0) PLAN_FAIL(p, HVI_ENODATA, "select_batch: hvi_plan_set_dataset has not been called");
+  if (!i_sites || n < 1) PLAN_FAIL(p, HVI_EINVAL, "select_batch: need n >= 1 indices");
+  if (mem_kind != HVI_MEM_HOST && mem_kind != HVI_MEM_DEVICE) PLAN_FAIL(p, HVI_EINVAL, "select_batch: bad mem_kind");
+  if (mem_kind == HVI_MEM_HOST)
+    for (int64_t i = 0; i < n; i++)
+      if (i_sites[i] < 0 || i_sites[i] >= p->ds_n) PLAN_FAIL(p, HVI_EINVAL, "select_batch: index out of range");
+  CU(p, cudaSetDevice(p->desc.device));
+  int rc = join_user(p);
+  if (rc) return rc;
+  if (p->cap_idx < n) {
+    CU(p, cudaStreamSynchronize(p->stream));
+    if (p->d_idx) cudaFree(p->d_idx);
+    p->d_idx = nullptr; p->cap_idx = 0;
+    CU(p, cudaMalloc((void**)&p->d_idx, sizeof(int64_t) * (size_t)n));
+    p->cap_idx = n;
+  }
+  CU(p, copy_in(p->d_idx, i_sites, sizeof(int64_t) * (size_t)n, mem_kind, p->stream));
+  return p->dtype == HVI_F32 ? select_t<float>(p, p->d_idx, 0, n) : select_t<double>(p, p->d_idx, 0, n);
+}
+
+static int select_sites(hvi_plan* p, int64_t n) {
+  if (!p->cf.sepvar) {
+    if (p->d_isites) { CU(p, cudaStreamSynchronize(p->stream)); cudaFree(p->d_isites); p->d_isites = nullptr; p->n_isites = 0; }
+    return HVI_OK;
+  }
+  // (re)allocate only when the batch size changes: the array is rewritten in stream order by the gather kernel
+  if (!p->d_isites || n != p->n_isites) {
+    CU(p, cudaStreamSynchronize(p->stream));
+    if (p->d_isites) cudaFree(p->d_isites);
+    p->d_isites = nullptr; p->n_isites = 0;
+    CU(p, cudaMalloc((void**)&p->d_isites, sizeof(int64_t) * (size_t)n));
+    p->n_isites = n;
+  }
+  return HVI_OK;
 }
 
 static int ensure(hvi_plan* p, void** buf, int64_t* cap, int64_t need_bytes) {
@@ -567,7 +778,8 @@ static int run_g_fwd(hvi_plan* p, const Launch& L, const Cfg<T>& cfg, const T* p
 // enqueue the whole evaluation on `s`; all pointers are device pointers
 template <typename T>
 static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* zMs, double* out, T* grad_T,
-                        cudaStream_t s, bool rng = false, uint64_t seed = 0, int64_t site_offset = 0) {
+                        cudaStream_t s, bool rng = false, uint64_t seed = 0, int64_t site_offset = 0,
+                        const unsigned long long* seed_dev = nullptr) {
   const Cfg<T>& cfg = cfg_of<T>(p);
   int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)(sizeof(T) * pdraw_elems(cfg.nP, M)));
   if (rc) return rc;
@@ -624,7 +836,7 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   a.ec = ec; a.mubar = (T*)p->d_mubar; a.partials = p->d_part_stream; a.nb = p->nb; a.M = M;
   a.MU = pbm ? (const T*)p->d_MU : nullptr; a.MUBAR = pbm ? (T*)p->d_MUBAR : nullptr;
   a.staged = !rng && (M % (16 / (int)sizeof(T)) == 0) && (((uintptr_t)zMs & 15) == 0);
-  a.rng = rng ? 1 : 0; a.seed = seed; a.col_offset = site_offset * cfg.nM;
+  a.rng = rng ? 1 : 0; a.seed = seed; a.seed_dev = seed_dev; a.col_offset = site_offset * cfg.nM;
   a.phi = phi; a.i_sites = p->d_isites; a.out = out; a.grad_T = grad_T;
   if (cfg.sepvar) {   // sites outside the batch have zero gradient
     const size_t big = (size_t)cfg.nM * cfg.n_site_total;
@@ -658,7 +870,7 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
                               p->d_part_mlp + (size_t)nblk * cfg.nphig, &nblk2, p->max_blk, M, zetaP, part_xu));
   }
   MARK();
-  CU(p, launch_finalize<T>(L, cfg, phi, zP, pdraw, ec, p->d_part_stream, nrows, part_g, nblk + nblk2, p->const_nly,
+  CU(p, launch_finalize<T>(L, cfg, phi, zP, pdraw, ec, p->d_part_stream, nrows, part_g, nblk + nblk2, p->d_bconst,
                            p->nb, M, out, grad_T, p->d_red, part_xs, p->wide ? 1 : nblk, part_xu, p->wide ? 1 : nblk2, p->d_xred));
   MARK();
 #undef MARK
@@ -672,6 +884,8 @@ static int eval_sync_t(hvi_plan* p, int M, const void* phi, const void* zP, cons
   const Cfg<T>& cfg = cfg_of<T>(p);
   const int nphi = cfg.nphi;
   cudaStream_t s = p->stream;
+  int rcj = join_user(p);
+  if (rcj) return rcj;
   const T* dphi = (const T*)phi;
   if (mem_kind == HVI_MEM_HOST) {
     CU(p, cudaMemcpyAsync(p->d_phi, phi, sizeof(T) * nphi, cudaMemcpyHostToDevice, s));
@@ -702,11 +916,13 @@ static int eval_sync_t(hvi_plan* p, int M, const void* phi, const void* zP, cons
                            site_offset);
   if (rc) return rc;
   CU(p, cudaMemcpyAsync(p->h_out + nphi, p->d_out + nphi, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+  if (p->anomalies < 0) CU(p, cudaMemcpyAsync(p->h_bconst, p->d_bconst, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
   if (want_grad) {
     if (mem_kind == HVI_MEM_HOST) CU(p, cudaMemcpyAsync(p->h_grad, p->d_grad, sizeof(T) * nphi, cudaMemcpyDeviceToHost, s));
     else CU(p, cudaMemcpyAsync(grad, p->d_grad, sizeof(T) * nphi, cudaMemcpyDeviceToDevice, s));
   }
   CU(p, cudaStreamSynchronize(s));
+  if (p->anomalies < 0) p->anomalies = (int64_t)p->h_bconst[1];
   if (want_grad && mem_kind == HVI_MEM_HOST) memcpy(grad, p->h_grad, sizeof(T) * nphi);
   const double* C = p->h_out + nphi;
   if (comps) for (int i = 0; i < 6; i++) comps[i] = C[i];
@@ -720,6 +936,16 @@ static int eval_sync_t(hvi_plan* p, int M, const void* phi, const void* zP, cons
   return HVI_OK;
 }
 
+// the device-resident entry points cannot return the reference's NaN for a finite observation under a missing driver
+// (SURVEY Appendix C-2): refuse the batch up front when the count is known, and in any case the count is folded into
+// out[n_phi + 7] by k_finalize
+static int refuse_anomalies(hvi_plan* p) {
+  if (p->anomalies > 0)
+    PLAN_FAIL(p, HVI_ENONFINITE, "%lld observation(s) are finite where a driver is not: the reference returns NaN here",
+              (long long)p->anomalies);
+  return HVI_OK;
+}
+
 static int check_eval_args(hvi_plan* p, int32_t n_MC, const void* phi, int mem_kind) {
   if (!p) return HVI_EINVAL;
   if (p->nb <= 0) PLAN_FAIL(p, HVI_ENODATA, "hvi_plan_set_data has not been called");
@@ -727,7 +953,7 @@ static int check_eval_args(hvi_plan* p, int32_t n_MC, const void* phi, int mem_k
   if (!phi) PLAN_FAIL(p, HVI_EINVAL, "phi is NULL");
   if (mem_kind != HVI_MEM_HOST && mem_kind != HVI_MEM_DEVICE) PLAN_FAIL(p, HVI_EINVAL, "bad mem_kind");
   CU(p, cudaSetDevice(p->desc.device));
-  return HVI_OK;
+  return join_user(p);   // the plan's stream continues behind work left on a caller's stream
 }
 
 extern "C" int hvi_neg_elbo_grad(hvi_plan* p, int32_t n_MC, const void* phi, const void* zP, const void* zMs, int mem_kind,
@@ -754,15 +980,23 @@ static int eval_async_t(hvi_plan* p, int M, const void* phi, const void* zP, con
   const Cfg<T>& cfg = cfg_of<T>(p);
   const T *dzP = (const T*)zP, *dzM = (const T*)zMs;
   const bool rng = (zMs == nullptr);
+  int rc = refuse_anomalies(p);
+  if (rc) return rc;
+  // the caller's stream is ordered behind the plan's own work (batch registration, earlier calls) ...
+  rc = fork_to(p, s);
+  if (rc) return rc;
   if (rng) {
     const int64_t nzP = (int64_t)M * (cfg.nP > 0 ? cfg.nP : 1);
-    int rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)sizeof(T) * nzP);
+    rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)sizeof(T) * nzP);
     if (rc) return rc;
     Launch L{s, p->sm_count, &p->launches};
     CU(p, launch_gen_normal<T>(L, (T*)p->d_zP, cfg.nP, M, seed, (int64_t)1 << 62));
     dzP = (const T*)p->d_zP;
   }
-  return enqueue_eval<T>(p, M, (const T*)phi, dzP, dzM, out, nullptr, s, rng, seed, site_offset);
+  rc = enqueue_eval<T>(p, M, (const T*)phi, dzP, dzM, out, nullptr, s, rng, seed, site_offset);
+  if (rc) return rc;
+  // ... and later calls on the plan's stream are ordered behind this evaluation
+  return mark_user(p, s);
 }
 
 extern "C" int hvi_neg_elbo_grad_async(hvi_plan* p, int32_t n_MC, const void* phi_dev, const void* zP_dev,
@@ -1053,6 +1287,8 @@ static int loss_gf_t(hvi_plan* p, const void* phi_gf, int mem_kind, double comps
   if (p->wide) PLAN_FAIL(p, HVI_EINVAL, "loss_gf: not available with the wide applicator");
   if (!p->has_obs) PLAN_FAIL(p, HVI_ENODATA, "loss_gf: the registered batch has no observations");
   cudaStream_t s = p->stream;
+  int rcj = join_user(p);
+  if (rcj) return rcj;
   const int ng = cfg.nphig, nP = cfg.nP;
   const cudaMemcpyKind kind = mem_kind == HVI_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   // full-layout ϕ: ϕg in place, ϕP in the μP slot (what g's pbm covariates and θP = transP(ϕP) read), the rest zero
@@ -1076,14 +1312,16 @@ static int loss_gf_t(hvi_plan* p, const void* phi_gf, int mem_kind, double comps
   CU(p, launch_mlp_bwd<T>(L, cfg, dphi, (const T*)p->d_xM, (const T*)p->d_mubar, p->nb, p->d_part_mlp, &nblk, p->max_blk, 0,
                           nullptr, part_xs));
   const bool want_grad = grad != nullptr;
-  CU(p, launch_point_finalize<T>(L, cfg, dphi, p->d_part_stream, nrows, p->d_part_mlp, nblk, part_xs, p->const_nly, p->d_out,
+  CU(p, launch_point_finalize<T>(L, cfg, dphi, p->d_part_stream, nrows, p->d_part_mlp, nblk, part_xs, p->d_bconst, p->d_out,
                                  want_grad ? (T*)p->d_grad : nullptr));
   CU(p, cudaMemcpyAsync(p->h_out, p->d_out + ng + nP, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+  if (p->anomalies < 0) CU(p, cudaMemcpyAsync(p->h_bconst, p->d_bconst, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
   if (want_grad) {
     if (mem_kind == HVI_MEM_HOST) CU(p, cudaMemcpyAsync(p->h_grad, p->d_grad, sizeof(T) * (size_t)(ng + nP), cudaMemcpyDeviceToHost, s));
     else CU(p, cudaMemcpyAsync(grad, p->d_grad, sizeof(T) * (size_t)(ng + nP), cudaMemcpyDeviceToDevice, s));
   }
   CU(p, cudaStreamSynchronize(s));
+  if (p->anomalies < 0) p->anomalies = (int64_t)p->h_bconst[1];
   if (want_grad && mem_kind == HVI_MEM_HOST) memcpy(grad, p->h_grad, sizeof(T) * (size_t)(ng + nP));
   if (comps) for (int i = 0; i < 3; i++) comps[i] = p->h_out[i];
   if (p->anomalies > 0)
@@ -1109,31 +1347,52 @@ extern "C" int hvi_loss_gf_grad(hvi_plan* p, const void* phi_gf, int mem_kind, d
 // An iteration whose value or gradient is not finite leaves ϕ, m, v untouched (the reference
 // raises there) and is visible as a non-finite entry of the loss trace.
 // ---------------------------------------------------------------------------------------
+// Device-side counters (plan->d_ctr) make an iteration independent of host state, so that it can be captured once as
+// a CUDA graph and replayed: [0] Adam steps applied so far (advanced only when an update lands: the bias correction
+// never counts a skipped iteration), [1] iteration index (trace slot, minibatch choice), [2] seed of the iteration's
+// draws, [3] block counter.  All blocks read the counters before the last block to finish advances them.
 template <typename T>
 __global__ void __launch_bounds__(256) k_adam(int64_t n, const double* __restrict__ out, T* __restrict__ phi,
                                               double* __restrict__ m, double* __restrict__ v, double eta, double b1,
-                                              double b2, double eps, double c1, double c2, double* __restrict__ trace,
-                                              int64_t it) {
+                                              double b2, double eps, double* __restrict__ trace,
+                                              unsigned long long* __restrict__ ctr) {
+  const unsigned long long t_applied = ctr[0], it = ctr[1];
   const bool bad = out[n + 7] != 0.0 || !isfinite(out[n + 6]);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && trace) trace[it] = bad ? nan("") : out[n + 6];
-  if (bad) return;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double g = out[i];
-    const double mi = b1 * m[i] + (1.0 - b1) * g, vi = b2 * v[i] + (1.0 - b2) * g * g;
-    m[i] = mi; v[i] = vi;
-    phi[i] = (T)((double)phi[i] - eta * (mi * c1) / (sqrt(vi * c2) + eps));
+  if (!bad) {
+    const double t = (double)(t_applied + 1);
+    const double c1 = 1.0 / (1.0 - pow(b1, t)), c2 = 1.0 / (1.0 - pow(b2, t));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const double g = out[i];
+      const double mi = b1 * m[i] + (1.0 - b1) * g, vi = b2 * v[i] + (1.0 - b2) * g * g;
+      m[i] = mi; v[i] = vi;
+      phi[i] = (T)((double)phi[i] - eta * (mi * c1) / (sqrt(vi * c2) + eps));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && trace) trace[it] = bad ? nan("") : out[n + 6];
+    __threadfence();
+    if (atomicAdd(&ctr[3], 1ULL) == (unsigned long long)gridDim.x - 1) {
+      ctr[3] = 0;
+      if (!bad) ctr[0] = t_applied + 1;
+      ctr[1] = it + 1;
+      ctr[2] += 1;
+    }
   }
 }
 
+__global__ void k_set_ctr(unsigned long long* ctr, unsigned long long it0, unsigned long long seed0, int reset_steps) {
+  if (reset_steps) ctr[0] = 0;
+  ctr[1] = it0; ctr[2] = seed0; ctr[3] = 0;
+}
+
 template <typename T>
-static int adam_apply_t(hvi_plan* p, const double* out_dev, cudaStream_t s, int64_t it_in_trace, bool trace) {
+static int adam_apply_t(hvi_plan* p, const double* out_dev, cudaStream_t s, bool trace) {
   const int64_t n = cfg_of<T>(p).nphi;
-  p->adam_t += 1;
-  const double c1 = 1.0 / (1.0 - pow(p->adam_b1, (double)p->adam_t)), c2 = 1.0 / (1.0 - pow(p->adam_b2, (double)p->adam_t));
   int blocks = (int)((n + 255) / 256);
   if (blocks > p->sm_count * 8) blocks = p->sm_count * 8;
   k_adam<T><<<blocks, 256, 0, s>>>(n, out_dev, (T*)p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->adam_eta, p->adam_b1, p->adam_b2,
-                                  p->adam_eps, c1, c2, trace ? p->d_trace : nullptr, it_in_trace);
+                                  p->adam_eps, trace ? p->d_trace : nullptr, p->d_ctr);
   CU(p, cudaGetLastError());
   ++p->launches;
   return HVI_OK;
@@ -1144,6 +1403,8 @@ extern "C" int hvi_adam_init(hvi_plan* p, const void* phi0, double eta, double b
   if (!phi0 || !(eta > 0) || !(beta1 >= 0 && beta1 < 1) || !(beta2 >= 0 && beta2 < 1) || !(eps > 0))
     PLAN_FAIL(p, HVI_EINVAL, "adam_init: need phi0, eta > 0, 0 <= beta < 1, eps > 0");
   CU(p, cudaSetDevice(p->desc.device));
+  int rcj = join_user(p);
+  if (rcj) return rcj;
   const size_t n = (size_t)p->cf.nphi;
   if (!p->d_phi_opt) {
     CU(p, cudaMalloc(&p->d_phi_opt, p->es * n));
@@ -1153,28 +1414,102 @@ extern "C" int hvi_adam_init(hvi_plan* p, const void* phi0, double eta, double b
   CU(p, cudaMemcpyAsync(p->d_phi_opt, phi0, p->es * n, cudaMemcpyHostToDevice, p->stream));
   CU(p, cudaMemsetAsync(p->d_adam_m, 0, sizeof(double) * n, p->stream));
   CU(p, cudaMemsetAsync(p->d_adam_v, 0, sizeof(double) * n, p->stream));
+  CU(p, cudaMemsetAsync(p->d_ctr, 0, sizeof(unsigned long long) * 4, p->stream));
   CU(p, cudaStreamSynchronize(p->stream));
-  p->adam_eta = eta; p->adam_b1 = beta1; p->adam_b2 = beta2; p->adam_eps = eps; p->adam_t = 0;
+  p->adam_eta = eta; p->adam_b1 = beta1; p->adam_b2 = beta2; p->adam_eps = eps;
+  p->graph_valid = 0;   // the hyper-parameters are baked into a captured iteration
   return HVI_OK;
 }
 
+// one optimiser iteration on `s`: [minibatch selection] → draws of the global block → evaluation → Adam update.
+// Everything that varies between iterations (seed, minibatch, step count, trace slot) is read from p->d_ctr.
 template <typename T>
-static int adam_run_t(hvi_plan* p, int n_iter, int M, uint64_t seed0, int64_t site_offset, double* trace_host) {
+static int adam_iteration(hvi_plan* p, int M, int64_t site_offset, int64_t batch_size, int64_t first_batch, cudaStream_t s) {
+  const Cfg<T>& cfg = cfg_of<T>(p);
+  Launch L{s, p->sm_count, &p->launches};
+  if (batch_size > 0) {
+    const int64_t n_batches = p->ds_n / batch_size;   // partial = false (src/AbstractHybridProblem.jl:206-207)
+    int rc = select_t<T>(p, nullptr, first_batch, batch_size, p->d_ctr, n_batches);
+    if (rc) return rc;
+  }
+  CU(p, launch_gen_normal<T>(L, (T*)p->d_zP, cfg.nP, M, 0, (int64_t)1 << 62, p->d_ctr + 2));
+  int rc = enqueue_eval<T>(p, M, (const T*)p->d_phi_opt, (const T*)p->d_zP, nullptr, p->d_out, nullptr, s, true, 0, site_offset,
+                           p->d_ctr + 2);
+  if (rc) return rc;
+  return adam_apply_t<T>(p, p->d_out, s, true);
+}
+
+// every device pointer and size an iteration bakes into its kernel arguments; a captured graph is replayed only while
+// this is unchanged
+static void graph_key(const hvi_plan* p, int M, int64_t site_offset, int64_t batch_size, int64_t first_batch, GraphKey* k) {
+  memset(k, 0, sizeof *k);
+  const void* ptrs[] = {p->d_xM, p->d_xP, p->d_rec, p->d_mu, p->d_mubar, p->d_isites, p->d_phi_opt, p->d_adam_m, p->d_adam_v,
+                        p->d_trace, p->d_zP, p->d_pdraw, p->d_ec, p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_MU,
+                        p->d_MUBAR, p->d_part_x, p->d_xred, p->ds_xM, p->ds_xP, p->ds_yo, p->ds_yu, p->d_wide, p->d_wide_bwd,
+                        p->d_gacc, p->d_wide_cache, (const void*)p->stream};
+  static_assert(sizeof(ptrs) / sizeof(ptrs[0]) <= sizeof(k->ptrs) / sizeof(k->ptrs[0]), "GraphKey too small");
+  for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) k->ptrs[i] = ptrs[i];
+  k->v[0] = p->nb; k->v[1] = M; k->v[2] = site_offset; k->v[3] = batch_size; k->v[4] = first_batch; k->v[5] = p->ds_n;
+  k->v[6] = p->has_obs;
+}
+
+template <typename T>
+static int adam_run_t(hvi_plan* p, int n_iter, int M, uint64_t seed0, int64_t site_offset, int64_t batch_size,
+                      int64_t first_batch, double* trace_host) {
   const Cfg<T>& cfg = cfg_of<T>(p);
   cudaStream_t s = p->stream;
-  int rc = ensure(p, (void**)&p->d_trace, &p->cap_trace, (int64_t)sizeof(double) * n_iter);
+  int rc = join_user(p);
   if (rc) return rc;
+  if (p->cap_trace < (int64_t)sizeof(double) * n_iter) {
+    CU(p, cudaStreamSynchronize(s));
+    rc = ensure(p, (void**)&p->d_trace, &p->cap_trace, (int64_t)sizeof(double) * n_iter);
+    if (rc) return rc;
+  }
   const int64_t nzP = (int64_t)M * (cfg.nP > 0 ? cfg.nP : 1);
   rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)sizeof(T) * nzP);
   if (rc) return rc;
-  Launch L{s, p->sm_count, &p->launches};
-  for (int it = 0; it < n_iter; it++) {
-    const uint64_t seed = seed0 + (uint64_t)it;
-    CU(p, launch_gen_normal<T>(L, (T*)p->d_zP, cfg.nP, M, seed, (int64_t)1 << 62));
-    rc = enqueue_eval<T>(p, M, (const T*)p->d_phi_opt, (const T*)p->d_zP, nullptr, p->d_out, nullptr, s, true, seed, site_offset);
-    if (rc) return rc;
-    rc = adam_apply_t<T>(p, p->d_out, s, it, true);
-    if (rc) return rc;
+  k_set_ctr<<<1, 1, 0, s>>>(p->d_ctr, 0ULL, (unsigned long long)seed0, 0);
+  CU(p, cudaGetLastError());
+  ++p->launches;
+  // the first iteration runs eagerly (it sizes every scratch buffer); the rest replay one captured iteration.  The wide
+  // applicator issues thousands of launches per evaluation through its own chunk loop and is not captured.
+  int it = 0;
+  rc = adam_iteration<T>(p, M, site_offset, batch_size, first_batch, s);
+  if (rc) return rc;
+  it = 1;
+  const bool use_graph = !p->wide && !p->profiling && n_iter > 1 && p->use_graphs;
+  if (use_graph) {
+    GraphKey key;
+    graph_key(p, M, site_offset, batch_size, first_batch, &key);
+    if (!p->graph_valid || memcmp(&key, &p->graph_key, sizeof key) != 0) {
+      if (p->adam_graph) { cudaGraphExecDestroy(p->adam_graph); p->adam_graph = nullptr; }
+      p->graph_valid = 0;
+      cudaGraph_t g = nullptr;
+      const int64_t launches_before = p->launches;
+      CU(p, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      rc = adam_iteration<T>(p, M, site_offset, batch_size, first_batch, s);
+      cudaError_t e = cudaStreamEndCapture(s, &g);
+      p->launches = launches_before;   // nothing ran during the capture
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (e != cudaSuccess) PLAN_FAIL(p, HVI_ECUDA, "adam_run: graph capture failed: %s", cudaGetErrorString(e));
+      size_t nn = 0;
+      cudaGraphGetNodes(g, nullptr, &nn);
+      p->graph_nodes = (int)nn;
+      e = cudaGraphInstantiate(&p->adam_graph, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) PLAN_FAIL(p, HVI_ECUDA, "adam_run: graph instantiation failed: %s", cudaGetErrorString(e));
+      graph_key(p, M, site_offset, batch_size, first_batch, &p->graph_key);
+      p->graph_valid = 1;
+    }
+    for (; it < n_iter; it++) {
+      CU(p, cudaGraphLaunch(p->adam_graph, s));
+      p->launches += p->graph_nodes;
+    }
+  } else {
+    for (; it < n_iter; it++) {
+      rc = adam_iteration<T>(p, M, site_offset, batch_size, first_batch, s);
+      if (rc) return rc;
+    }
   }
   if (trace_host) {
     CU(p, cudaMemcpyAsync(trace_host, p->d_trace, sizeof(double) * n_iter, cudaMemcpyDeviceToHost, s));
@@ -1190,8 +1525,33 @@ extern "C" int hvi_adam_run(hvi_plan* p, int32_t n_iter, int32_t n_MC, uint64_t 
   if (p->nb <= 0) PLAN_FAIL(p, HVI_ENODATA, "hvi_plan_set_data has not been called");
   if (n_iter < 1 || n_MC < 1) PLAN_FAIL(p, HVI_EINVAL, "adam_run: n_iter and n_MC must be >= 1");
   CU(p, cudaSetDevice(p->desc.device));
-  return p->dtype == HVI_F32 ? adam_run_t<float>(p, n_iter, n_MC, seed0, site_offset, nL_trace)
-                             : adam_run_t<double>(p, n_iter, n_MC, seed0, site_offset, nL_trace);
+  int rc = refuse_anomalies(p);
+  if (rc) return rc;
+  return p->dtype == HVI_F32 ? adam_run_t<float>(p, n_iter, n_MC, seed0, site_offset, 0, 0, nL_trace)
+                             : adam_run_t<double>(p, n_iter, n_MC, seed0, site_offset, 0, 0, nL_trace);
+}
+
+// The minibatch loop of solve (src/HybridSolver.jl:259-260 over the DataLoader of src/AbstractHybridProblem.jl:206-207:
+// consecutive column ranges of the training set, last partial batch dropped, no shuffling) on the device-resident
+// dataset: iteration i evaluates minibatch (first_batch + i) mod n_batches and applies the Adam update.
+extern "C" int hvi_adam_run_minibatches(hvi_plan* p, int32_t n_iter, int32_t n_MC, uint64_t seed0, int64_t batch_size,
+                                        int64_t first_batch, double* nL_trace) {
+  if (!p) return HVI_EINVAL;
+  if (!p->d_phi_opt) PLAN_FAIL(p, HVI_EINVAL, "adam_run_minibatches: call hvi_adam_init first");
+  if (p->ds_n <= 0) PLAN_FAIL(p, HVI_ENODATA, "adam_run_minibatches: hvi_plan_set_dataset has not been called");
+  if (n_iter < 1 || n_MC < 1) PLAN_FAIL(p, HVI_EINVAL, "adam_run_minibatches: n_iter and n_MC must be >= 1");
+  if (batch_size < 1 || batch_size > p->ds_n) PLAN_FAIL(p, HVI_EINVAL, "adam_run_minibatches: batch_size must be in 1 .. n_site_total");
+  if (first_batch < 0 || first_batch >= p->ds_n / batch_size) PLAN_FAIL(p, HVI_EINVAL, "adam_run_minibatches: first_batch out of range");
+  if (!p->ds_has_obs) PLAN_FAIL(p, HVI_ENODATA, "adam_run_minibatches: the dataset has no observations");
+  CU(p, cudaSetDevice(p->desc.device));
+  return p->dtype == HVI_F32 ? adam_run_t<float>(p, n_iter, n_MC, seed0, 0, batch_size, first_batch, nL_trace)
+                             : adam_run_t<double>(p, n_iter, n_MC, seed0, 0, batch_size, first_batch, nL_trace);
+}
+
+extern "C" int hvi_plan_use_graphs(hvi_plan* p, int on) {
+  if (!p) return HVI_EINVAL;
+  p->use_graphs = on ? 1 : 0;
+  return HVI_OK;
 }
 
 extern "C" int hvi_adam_apply_dev(hvi_plan* p, const double* out_dev, void* cuda_stream) {
@@ -1200,7 +1560,11 @@ extern "C" int hvi_adam_apply_dev(hvi_plan* p, const double* out_dev, void* cuda
   if (!out_dev) PLAN_FAIL(p, HVI_EINVAL, "adam_apply_dev: out_dev is NULL");
   CU(p, cudaSetDevice(p->desc.device));
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  return p->dtype == HVI_F32 ? adam_apply_t<float>(p, out_dev, s, 0, false) : adam_apply_t<double>(p, out_dev, s, 0, false);
+  int rc = fork_to(p, s);
+  if (rc) return rc;
+  rc = p->dtype == HVI_F32 ? adam_apply_t<float>(p, out_dev, s, false) : adam_apply_t<double>(p, out_dev, s, false);
+  if (rc) return rc;
+  return mark_user(p, s);
 }
 
 extern "C" int hvi_adam_phi_dev(hvi_plan* p, void** phi_dev) {
@@ -1214,6 +1578,8 @@ extern "C" int hvi_adam_get_phi(hvi_plan* p, void* phi_host) {
   if (!p || !phi_host) return HVI_EINVAL;
   if (!p->d_phi_opt) PLAN_FAIL(p, HVI_EINVAL, "adam_get_phi: call hvi_adam_init first");
   CU(p, cudaSetDevice(p->desc.device));
+  int rcj = join_user(p);   // an update applied on a caller's stream (hvi_adam_apply_dev) lands first
+  if (rcj) return rcj;
   CU(p, cudaMemcpyAsync(phi_host, p->d_phi_opt, p->es * (size_t)p->cf.nphi, cudaMemcpyDeviceToHost, p->stream));
   CU(p, cudaStreamSynchronize(p->stream));
   return HVI_OK;

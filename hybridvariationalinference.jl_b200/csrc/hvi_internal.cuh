@@ -75,6 +75,7 @@ struct StreamArgs {
   T* grad_T;
   int rng;           // 1: draw ξ inside the kernel from (seed, col_offset + site·n_θM + k, draw); zMs unused
   uint64_t seed;
+  const unsigned long long* seed_dev;   // non-NULL: the seed is read from device memory (optimiser loops replayed as CUDA graphs)
   int64_t col_offset;
   int staged;        // 1: M % (16/sizeof(T)) == 0 and zMs 16-byte aligned → cp.async staging
 };
@@ -98,6 +99,18 @@ struct WideCache {
 template <typename T>
 cudaError_t launch_preprocess(const Launch& L, int nO, int64_t nb, const T* xP, const T* y_o, const T* y_unc, T* rec,
                               double* part /*[2*nwarps]*/, int* nrows_out);
+// select a minibatch of a device-resident dataset (hvi_plan_select_batch / _range): gather the sites idx[0..nb) (NULL:
+// first .. first+nb) of the raw dataset arrays into the batch arrays xM_b, xP_b and the tiled records; same partial sums.
+// ctr non-NULL: `first` counts minibatches and the device-side iteration counter ctr[1] advances it (modulo n_batches).
+// isites_out non-NULL: the dataset index of every batch site is written there (MeanVarSep)
+template <typename T>
+cudaError_t launch_gather_preprocess(const Launch& L, int nC, int nO, int64_t nb, const int64_t* idx, int64_t first,
+                                     const T* ds_xM, const T* ds_xP, const T* ds_yo, const T* ds_yu, T* xM_b, T* xP_b,
+                                     T* rec, double* part /*[2*nwarps]*/, int* nrows_out,
+                                     const unsigned long long* ctr = nullptr, int64_t n_batches = 1,
+                                     int64_t* isites_out = nullptr);
+// consts[0] = Σ part[2r] (the ϕ-independent ½Σy_unc of the batch), consts[1] = Σ part[2r+1] (anomalies); fixed order
+cudaError_t launch_batch_consts(const Launch& L, const double* part, int nrows, double* consts);
 template <typename T>
 cudaError_t launch_prologue(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, int M, EvalConsts<T>* ec,
                             T* pdraw /*4 arrays [nP][M]: rP, zetaP, thP, gP; then [M][pd_stride] records*/);
@@ -113,12 +126,14 @@ cudaError_t launch_stream(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T
 template <typename T>
 cudaError_t launch_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, const T* pdraw,
                             const EvalConsts<T>* ec, const double* part_stream, int nrows, const double* part_mlp,
-                            int nblk, double const_nly, int64_t nb, int M, double* out, T* grad_T,
+                            int nblk, const double* batch_consts /*device: ½Σy_unc, anomalies*/, int64_t nb, int M,
+                            double* out, T* grad_T,
                             double* red /*[128 + ceil(nphig/32) + 1] scratch*/, const double* part_xs = nullptr,
                             int nblk_xs = 0, const double* part_xu = nullptr, int nblk_xu = 0,
                             double* xred = nullptr /*[(1 + M)·npc] scratch*/);
 template <typename T>
-cudaError_t launch_gen_normal(const Launch& L, T* z, int64_t n_cols, int M, uint64_t seed, int64_t col_offset);
+cudaError_t launch_gen_normal(const Launch& L, T* z, int64_t n_cols, int M, uint64_t seed, int64_t col_offset,
+                              const unsigned long long* seed_dev = nullptr);
 template <typename T>
 cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, const T* pdraw, T* zetaP,
                                  T* zetaMs_tr, T* sigma);
@@ -161,7 +176,8 @@ cudaError_t launch_point(const Launch& L, const Cfg<T>& cfg, const T* phi, const
                          double* part /*[point_max_rows][point_row_len]*/, int* nrows_out);
 template <typename T>
 cudaError_t launch_point_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, const double* part, int nrows,
-                                  const double* part_mlp, int nblk, const double* part_x, double const_nly, double* out,
+                                  const double* part_mlp, int nblk, const double* part_x, const double* batch_consts,
+                                  double* out,
                                   T* grad_T);
 int point_max_rows(int sm_count);
 int point_row_len();

@@ -165,6 +165,75 @@ __global__ void __launch_bounds__(256) k_preprocess(int nO, int64_t nb, const T*
   if (lane == 0) { part[2 * gw] = cst; part[2 * gw + 1] = anomalies; }
 }
 
+// Minibatch of a device-resident dataset (gdev_hybridproblem_dataloader, src/AbstractHybridProblem.jl:220-250, walked
+// by the DataLoader of solve, src/HybridSolver.jl:259-260): batch site i is dataset site idx[i] (or first + i).  One
+// pass gathers the columns into the batch arrays (xM for g, raw xP for the prediction path) and builds the tiled
+// records exactly as k_preprocess does.  A site's columns are 4·nC … 8·nO contiguous bytes: every lane reads whole
+// sectors of its own site; the record stores are coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_preprocess(int nC, int nO, int64_t nb, const int64_t* __restrict__ idx,
+                                                           int64_t first, const T* __restrict__ ds_xM,
+                                                           const T* __restrict__ ds_xP, const T* __restrict__ ds_yo,
+                                                           const T* __restrict__ ds_yu, T* __restrict__ xM_b,
+                                                           T* __restrict__ xP_b, T* __restrict__ rec,
+                                                           double* __restrict__ part,
+                                                           const unsigned long long* __restrict__ ctr,
+                                                           int64_t n_batches, int64_t* __restrict__ isites_out) {
+  // optimiser loops replayed as CUDA graphs: the minibatch is chosen by the device-side iteration counter ctr[1]
+  if (ctr) first = (first + (int64_t)(ctr[1] % (unsigned long long)n_batches)) % n_batches * nb;
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t ntiles = (nb + 31) / 32;
+  double cst = 0.0, anomalies = 0.0;
+  for (int64_t tile = gw; tile < ntiles; tile += nw) {
+    const int64_t site = tile * 32 + lane;
+    const int64_t src = site < nb ? (idx ? idx[site] : first + site) : 0;
+    T* r = rec + (tile * 4 * nO) * 32 + lane;
+    if (site < nb) {
+      for (int c = 0; c < nC; c++) xM_b[site * nC + c] = ds_xM[src * nC + c];
+      if (isites_out) isites_out[site] = src;   // MeanVarSep reads its per-site parameters through this map
+    }
+    for (int o = 0; o < nO; o++) {
+      T s1 = T(1), s2 = T(1), yo = T(0), w = T(0);
+      if (site < nb) {
+        const T a = ds_xP[src * 2 * nO + o], b = ds_xP[src * 2 * nO + nO + o];
+        xP_b[site * 2 * nO + o] = a;
+        xP_b[site * 2 * nO + nO + o] = b;
+        const T y = ds_yo ? ds_yo[src * nO + o] : T(NAN), u = ds_yu ? ds_yu[src * nO + o] : T(0);
+        const bool valid = isfinite(a) && isfinite(b);
+        const bool obs = !isnan(y);
+        if (valid) { s1 = a; s2 = b; }
+        if (obs && valid) { yo = y; w = exp_t(-u); cst += 0.5 * (double)u; }
+        if (obs && !valid) anomalies += 1.0;
+      }
+      r[(0 * nO + o) * 32] = s1;
+      r[(1 * nO + o) * 32] = s2;
+      r[(2 * nO + o) * 32] = yo;
+      r[(3 * nO + o) * 32] = w;
+    }
+  }
+  cst = warp_sum(cst);
+  anomalies = warp_sum(anomalies);
+  if (lane == 0) { part[2 * gw] = cst; part[2 * gw + 1] = anomalies; }
+}
+
+// the two constants of a registered batch, summed in a fixed order (run-to-run bit-identical), left on the device so
+// that registering a batch needs no host round trip
+__global__ void __launch_bounds__(256) k_batch_consts(const double* __restrict__ part, int nrows, double* __restrict__ consts) {
+  __shared__ double sm[2][256];
+  const int t = threadIdx.x;
+  double c = 0.0, a = 0.0;
+  for (int r = t; r < nrows; r += 256) { c += part[2 * r]; a += part[2 * r + 1]; }
+  sm[0][t] = c; sm[1][t] = a;
+  __syncthreads();
+  for (int s_ = 128; s_ > 0; s_ >>= 1) {
+    if (t < s_) { sm[0][t] += sm[0][t + s_]; sm[1][t] += sm[1][t + s_]; }
+    __syncthreads();
+  }
+  if (t == 0) { consts[0] = sm[0][0]; consts[1] = sm[1][0]; }
+}
+
 // ---------------------------------------------------------------------------------------
 // prologue: one block.  thread 0 builds the Cholesky factors; all threads do the draws of
 // the global block (src/elbo.jl:647-657,664-670,496; src/cholesky.jl:156-174,262-313).
@@ -994,6 +1063,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
   }
   const T wM = T(1) / T(M);
   const bool staged = a.staged != 0;
+  const uint64_t seed = (RNG && a.seed_dev) ? (uint64_t)*a.seed_dev : a.seed;
   const int64_t ntiles = (a.nb + 31) / 32;
   for (int64_t tile = (int64_t)blockIdx.x * NWARP + warp; tile < ntiles; tile += (int64_t)gridDim.x * NWARP) {
     const int64_t site = tile * 32 + lane;
@@ -1087,7 +1157,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
 #pragma unroll
               for (int k = 0; k < NM; k++) {
                 float n4[4];
-                normal4(a.seed, (uint64_t)(a.col_offset + site * NM + k), mq / 4, n4);
+                normal4(seed, (uint64_t)(a.col_offset + site * NM + k), mq / 4, n4);
 #pragma unroll
                 for (int d = 0; d < CH; d++) zc[k][d] = (T)n4[(mq % 4) + d];
               }
@@ -1123,7 +1193,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
             for (int k = 0; k < NM; k++) {
               if (mode == 2) {
                 float n4[4];
-                normal4(a.seed, (uint64_t)(a.col_offset + site * NM + k), m / 4, n4);
+                normal4(seed, (uint64_t)(a.col_offset + site * NM + k), m / 4, n4);
                 z[k] = (T)(m % 4 == 0 ? n4[0] : m % 4 == 1 ? n4[1] : m % 4 == 2 ? n4[2] : n4[3]);
               } else {
                 z[k] = a.zMs[((size_t)site * NM + k) * M + m];
@@ -1339,7 +1409,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
                                                           const EvalConsts<T>* __restrict__ ecp,
                                                           const double* __restrict__ red, int nred_blocks,
                                                           const double* __restrict__ xs, const double* __restrict__ xu,
-                                                          double const_nly, int64_t nb, int M,
+                                                          const double* __restrict__ batch_consts, int64_t nb, int M,
                                                           double* __restrict__ out, T* __restrict__ grad_T) {
   __shared__ double sred[(3 + MAXP) * FIN_THREADS];
   __shared__ double sacc[128];
@@ -1411,7 +1481,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
     const double* cPs = aPs + nP;
     // G(o): slot of ϕ position o (≥ nphig, outside the logσ2_ζMs block) in the compressed vector
     auto Gp = [&](int o) -> double* { return sq + (o - cfg.nphig - ((cfg.sepvar && o >= cfg.o_coef + big) ? big : 0)); };
-    double nLy = 0.5 * w * sacc[ACC_NLY] + const_nly;
+    double nLy = 0.5 * w * sacc[ACC_NLY] + batch_consts[0];
     double nlp = w * sacc[ACC_PRIOR];
     double lj = w * sacc[ACC_LJ];
     double logsig = sacc[ACC_LOGSIG];
@@ -1470,6 +1540,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
   }
   if (cfg.sepvar && t == 0)
     _Pragma("unroll 1") for (int k = 0; k < nM; k++) bad += sacc[ACC_FIRST_VEC + k];
+  // an observation that is finite where a driver is not makes the reference's loss NaN: the masked
+  // value is evaluated, and the anomaly count joins the non-finite count so that no caller of the device-resident result
+  // (optimiser loop, all-reduce) takes the iteration for a clean one
+  if (t == 0) bad += batch_consts[1];
   bad = block_sum_fixed(bad, sred);
   if (t == 0) out[cfg.nphi + 7] = bad;
 }
@@ -1488,7 +1562,8 @@ __global__ void k_cast_grad(int n, const double* __restrict__ out, T* __restrict
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) k_gen_normal(T* __restrict__ z, int64_t n_cols, int M, uint64_t seed,
-                                                    int64_t col_offset) {
+                                                    int64_t col_offset, const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev) seed = *seed_dev;
   const int M4 = (M + 3) / 4;
   const int64_t n = n_cols * M4;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
@@ -1559,6 +1634,28 @@ cudaError_t launch_preprocess(const Launch& L, int nO, int64_t nb, const T* xP, 
   k_preprocess<T><<<blocks, 256, 0, L.stream>>>(nO, nb, xP, y_o, y_unc, rec, part);
   HVI_LAUNCH_CHECK();
   *nrows_out = blocks * 8;
+  return cudaSuccess;
+}
+
+template <typename T>
+cudaError_t launch_gather_preprocess(const Launch& L, int nC, int nO, int64_t nb, const int64_t* idx, int64_t first,
+                                     const T* ds_xM, const T* ds_xP, const T* ds_yo, const T* ds_yu, T* xM_b, T* xP_b,
+                                     T* rec, double* part, int* nrows_out, const unsigned long long* ctr,
+                                     int64_t n_batches, int64_t* isites_out) {
+  const int64_t ntiles = (nb + 31) / 32;
+  int blocks = (int)((ntiles + 7) / 8);
+  if (blocks > L.sm_count * 8) blocks = L.sm_count * 8;
+  if (blocks < 1) blocks = 1;
+  k_gather_preprocess<T><<<blocks, 256, 0, L.stream>>>(nC, nO, nb, idx, first, ds_xM, ds_xP, ds_yo, ds_yu, xM_b, xP_b, rec, part, ctr,
+                                                       n_batches, isites_out);
+  HVI_LAUNCH_CHECK();
+  *nrows_out = blocks * 8;
+  return cudaSuccess;
+}
+
+cudaError_t launch_batch_consts(const Launch& L, const double* part, int nrows, double* consts) {
+  k_batch_consts<<<1, 256, 0, L.stream>>>(part, nrows, consts);
+  HVI_LAUNCH_CHECK();
   return cudaSuccess;
 }
 
@@ -1776,7 +1873,7 @@ cudaError_t launch_stream(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T
 template <typename T>
 cudaError_t launch_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* zP, const T* pdraw,
                             const EvalConsts<T>* ec, const double* part_stream, int nrows, const double* part_mlp,
-                            int nblk, double const_nly, int64_t nb, int M, double* out, T* grad_T, double* red,
+                            int nblk, const double* batch_consts, int64_t nb, int M, double* out, T* grad_T, double* red,
                             const double* part_xs, int nblk_xs, const double* part_xu, int nblk_xu, double* xred) {
   const int nbg = (cfg.nphig + 31) / 32;
   k_reduce<T><<<nbg + 1, RED_THREADS, 0, L.stream>>>(cfg.nphig, part_mlp, nblk, part_stream, nrows, nacc(cfg.nP, cfg.nM),
@@ -1791,19 +1888,20 @@ cudaError_t launch_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, co
     k_colsum<<<(M * cfg.npc + 31) / 32, 256, 0, L.stream>>>(part_xu, nblk_xu, M * cfg.npc, xu);
     HVI_LAUNCH_CHECK();
   }
-  k_finalize<T><<<1, FIN_THREADS, 0, L.stream>>>(cfg, phi, zP, pdraw, ec, red, nbg + 1, xs, xu, const_nly, nb, M, out,
+  k_finalize<T><<<1, FIN_THREADS, 0, L.stream>>>(cfg, phi, zP, pdraw, ec, red, nbg + 1, xs, xu, batch_consts, nb, M, out,
                                                 grad_T);
   HVI_LAUNCH_CHECK();
   return cudaSuccess;
 }
 
 template <typename T>
-cudaError_t launch_gen_normal(const Launch& L, T* z, int64_t n_cols, int M, uint64_t seed, int64_t col_offset) {
+cudaError_t launch_gen_normal(const Launch& L, T* z, int64_t n_cols, int M, uint64_t seed, int64_t col_offset,
+                              const unsigned long long* seed_dev) {
   if (n_cols <= 0) return cudaSuccess;
   const int64_t n = n_cols * ((M + 3) / 4);
   int64_t blocks = (n + 255) / 256;
   if (blocks > (int64_t)L.sm_count * 16) blocks = (int64_t)L.sm_count * 16;
-  k_gen_normal<T><<<(int)blocks, 256, 0, L.stream>>>(z, n_cols, M, seed, col_offset);
+  k_gen_normal<T><<<(int)blocks, 256, 0, L.stream>>>(z, n_cols, M, seed, col_offset, seed_dev);
   HVI_LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -1901,14 +1999,17 @@ cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const Strea
 #define HVI_INSTANTIATE(T)                                                                                              \
   template cudaError_t launch_preprocess<T>(const Launch&, int, int64_t, const T*, const T*, const T*, T*, double*, int*); \
   template cudaError_t launch_prologue<T>(const Launch&, const Cfg<T>&, const T*, const T*, int, EvalConsts<T>*, T*);    \
+  template cudaError_t launch_gather_preprocess<T>(const Launch&, int, int, int64_t, const int64_t*, int64_t, const T*,  \
+                                                   const T*, const T*, const T*, T*, T*, T*, double*, int*,               \
+                                                   const unsigned long long*, int64_t, int64_t*);                         \
   template cudaError_t launch_mlp_fwd<T>(const Launch&, const Cfg<T>&, const T*, const T*, int64_t, T*, int, const T*);  \
   template cudaError_t launch_mlp_bwd<T>(const Launch&, const Cfg<T>&, const T*, const T*, const T*, int64_t, double*,   \
                                          int*, int, int, const T*, double*);                                             \
   template cudaError_t launch_stream<T>(const Launch&, const Cfg<T>&, const StreamArgs<T>&, int*, int);                  \
   template cudaError_t launch_finalize<T>(const Launch&, const Cfg<T>&, const T*, const T*, const T*,                    \
-                                          const EvalConsts<T>*, const double*, int, const double*, int, double, int64_t, \
+                                          const EvalConsts<T>*, const double*, int, const double*, int, const double*, int64_t, \
                                           int, double*, T*, double*, const double*, int, const double*, int, double*);                                                             \
-  template cudaError_t launch_gen_normal<T>(const Launch&, T*, int64_t, int, uint64_t, int64_t);                         \
+  template cudaError_t launch_gen_normal<T>(const Launch&, T*, int64_t, int, uint64_t, int64_t, const unsigned long long*); \
   template cudaError_t launch_generate_zeta<T>(const Launch&, const Cfg<T>&, const StreamArgs<T>&, const T*, T*, T*, T*);
 HVI_INSTANTIATE(float)
 HVI_INSTANTIATE(double)

@@ -120,7 +120,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_point_finalize(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi,
                                                          const double* __restrict__ part, int nrows,
                                                          const double* __restrict__ part_mlp, int nblk,
-                                                         const double* __restrict__ part_x, double const_nly,
+                                                         const double* __restrict__ part_x, const double* __restrict__ batch_consts,
                                                          double* __restrict__ out, T* __restrict__ grad_T) {
   __shared__ double tot[3 + MAXP];
   __shared__ double bad_g;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) k_point_finalize(const __grid_constant__ 
       if (grad_T) grad_T[ng + j] = (T)g;
       if (!isfinite(g)) nbad += 1.0;
     }
-    const double nLy = 0.5 * tot[0] + const_nly, nlp = tot[1] + nlpP;
+    const double nLy = 0.5 * tot[0] + batch_consts[0], nlp = tot[1] + nlpP;
     out[ng + nP] = nLy + nlp; out[ng + nP + 1] = nLy; out[ng + nP + 2] = nlp;
     if (!isfinite(nLy + nlp)) nbad += 1.0;
     out[ng + nP + 3] = nbad;
@@ -188,9 +188,9 @@ cudaError_t launch_point(const Launch& L, const Cfg<T>& cfg, const T* phi, const
 
 template <typename T>
 cudaError_t launch_point_finalize(const Launch& L, const Cfg<T>& cfg, const T* phi, const double* part, int nrows,
-                                  const double* part_mlp, int nblk, const double* part_x, double const_nly, double* out,
+                                  const double* part_mlp, int nblk, const double* part_x, const double* batch_consts, double* out,
                                   T* grad_T) {
-  k_point_finalize<T><<<1, 256, 0, L.stream>>>(cfg, phi, part, nrows, part_mlp, nblk, part_x, const_nly, out, grad_T);
+  k_point_finalize<T><<<1, 256, 0, L.stream>>>(cfg, phi, part, nrows, part_mlp, nblk, part_x, batch_consts, out, grad_T);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (L.counter) ++*L.counter;
@@ -202,8 +202,8 @@ template cudaError_t launch_point<float>(const Launch&, const Cfg<float>&, const
 template cudaError_t launch_point<double>(const Launch&, const Cfg<double>&, const double*, const double*, const double*,
                                           double*, int64_t, double*, int*);
 template cudaError_t launch_point_finalize<float>(const Launch&, const Cfg<float>&, const float*, const double*, int,
-                                                  const double*, int, const double*, double, double*, float*);
+                                                  const double*, int, const double*, const double*, double*, float*);
 template cudaError_t launch_point_finalize<double>(const Launch&, const Cfg<double>&, const double*, const double*, int,
-                                                   const double*, int, const double*, double, double*, double*);
+                                                   const double*, int, const double*, const double*, double*, double*);
 
 }  // namespace hvi

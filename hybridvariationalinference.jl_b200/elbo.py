@@ -57,6 +57,19 @@ def _is_device(a):
     return hasattr(a, "data_ptr") and a.is_cuda
 
 
+def _check_colmajor(tensors):
+    """Device tensors are read as the reference's column-major (rows x n_site) arrays: a 2-D tensor must have
+    stride (1, rows) -- e.g. `torch.empty(n_site, rows).T` -- a C-contiguous (rows, n_site) tensor is refused."""
+    for t in tensors:
+        if t is None:
+            continue
+        if t.dim() == 2 and t.shape[1] > 1 and t.shape[0] > 1 and not (t.stride(0) == 1 and t.stride(1) == t.shape[0]):
+            raise ValueError(f"device array of shape {tuple(t.shape)} has strides {t.stride()}: expected column-major "
+                             f"(1, {t.shape[0]})")
+        if t.dim() == 1 and not t.is_contiguous():
+            raise ValueError("1-D device array must be contiguous")
+
+
 class NegElboPlan:
     """One problem description bound to one GPU: owns the `hvi_plan`.  Stands in for the keyword
     set that `get_loss_elbo` captures (src/HybridSolver.jl:240-245)."""
@@ -122,6 +135,7 @@ class NegElboPlan:
         column = site."""
         dev = _is_device(xM)
         if dev:
+            _check_colmajor((xM, xP, y_o, y_unc))
             n_site = xM.shape[-1] if xM.dim() == 2 else xM.numel() // self.prob.n_covar
             args = (xM, xP, y_o, y_unc)
         else:
@@ -159,6 +173,57 @@ class NegElboPlan:
         if i_sites is not None:
             idx = np.ascontiguousarray(i_sites, dtype=np.int64)
             self._check(self.lib.hvi_plan_set_sites(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
+
+    # -- device-resident training set ------------------------------------------------------------
+    def set_dataset(self, xM, xP, y_o=None, y_unc=None):
+        """Upload the whole training set once (gdev_hybridproblem_dataloader, src/AbstractHybridProblem.jl:220-250);
+        minibatches are then chosen on the device by `select_range` / `select_batch` / `adam_run_minibatches`."""
+        dev = _is_device(xM)
+        if dev:
+            _check_colmajor((xM, xP, y_o, y_unc))
+            args = (xM, xP, y_o, y_unc)
+            n = xM.shape[-1]
+        else:
+            f = lambda a: None if a is None else np.asfortranarray(a, dtype=self.dt)
+            args = tuple(map(f, (xM, xP, y_o, y_unc)))
+            n = args[0].shape[1]
+            assert args[1].shape == (2 * self.prob.n_obs, n) and args[0].shape[0] == self.prob.n_covar
+        self._check(self.lib.hvi_plan_set_dataset(self._h, n, *map(_ptr, args),
+                                                  A.HVI_MEM_DEVICE if dev else A.HVI_MEM_HOST))
+        self.n_site_dataset = n
+
+    def select_range(self, first, n):
+        """Sites [first, first+n) of the dataset become the registered batch (one DataLoader element)."""
+        self._check(self.lib.hvi_plan_select_range(self._h, int(first), int(n)))
+        self.n_site = int(n)
+
+    def select_batch(self, i_sites):
+        """Sites i_sites (0-based; numpy or CUDA int64 tensor) of the dataset become the registered batch."""
+        if _is_device(i_sites):
+            assert i_sites.dtype.is_floating_point is False and i_sites.element_size() == 8 and i_sites.is_contiguous()
+            n = i_sites.numel()
+            self._check(self.lib.hvi_plan_select_batch(self._h, _ptr(i_sites), n, A.HVI_MEM_DEVICE))
+        else:
+            idx = np.ascontiguousarray(i_sites, dtype=np.int64)
+            n = idx.size
+            self._check(self.lib.hvi_plan_select_batch(self._h, _ptr(idx), n, A.HVI_MEM_HOST))
+        self.n_site = int(n)
+
+    def set_stream(self, stream_ptr=None):
+        """Make the plan work on the caller's CUDA stream (None: back to the plan's own)."""
+        self._check(self.lib.hvi_plan_set_stream(self._h, C.c_void_p(stream_ptr or 0), int(stream_ptr is None)))
+
+    def use_graphs(self, on: bool):
+        self._check(self.lib.hvi_plan_use_graphs(self._h, int(on)))
+
+    def adam_run_minibatches(self, n_iter, n_MC, batch_size, seed0=0, first_batch=0, trace=True):
+        """`solve`'s minibatch loop (src/HybridSolver.jl:259-260) on the device-resident dataset: iteration i takes
+        minibatch (first_batch + i) mod (n_site // batch_size), evaluates and applies Adam; CUDA-graph replayed."""
+        tr = np.empty(n_iter, dtype=np.float64) if trace else None
+        self._check(self.lib.hvi_adam_run_minibatches(self._h, n_iter, n_MC, seed0, int(batch_size), int(first_batch),
+                                                      tr.ctypes.data_as(C.POINTER(C.c_double)) if trace else None))
+        self.n_site = int(batch_size)
+        return tr
 
     # -- point solver ---------------------------------------------------------------------------
     def loss_gf_withgradient(self, ϕ_gf, want_grad=True):
@@ -303,16 +368,21 @@ def neg_elbo_gtf(plan: NegElboPlan, ϕ, zP, zMs) -> float:
 
 def get_loss_elbo(prob: HybridProblem, device: int = 0, n_MC: int = 12):
     """`get_loss_elbo` (src/HybridSolver.jl:293-324): returns
-    ``loss_elbo(ϕ, rng_seed, xM, xP, y_o, y_unc, i_sites) -> (nL, components, ∇ϕ)``; the batch is
-    re-registered only when it changes."""
-    plan = NegElboPlan(prob, device)
-    state = {"key": None}
+    ``loss_elbo(ϕ, rng_seed, xM, xP, y_o, y_unc, i_sites) -> (nL, components, ∇ϕ)``.
 
-    def loss_elbo(ϕ, rng_seed, xM, xP, y_o, y_unc, i_sites=None):
-        key = (id(xM), id(xP), id(y_o), id(y_unc))
-        if key != state["key"]:
-            plan.set_data(xM, xP, y_o, y_unc)
-            state["key"] = key
+    Every call registers its batch (set_data is a copy + one re-tile kernel): arrays refilled in place by a loader
+    are therefore always seen.  Pass ``batch_token`` (any hashable that changes when the batch does) to skip the
+    re-registration of an unchanged batch.  `i_sites` (0-based) is required with MeanVarSepHVIApproximation, whose
+    per-site log-variances are addressed through it (src/elbo_sepvec.jl:23)."""
+    plan = NegElboPlan(prob, device)
+    state = {"token": None}
+
+    def loss_elbo(ϕ, rng_seed, xM, xP, y_o, y_unc, i_sites=None, *, batch_token=None):
+        if prob.is_sepvar and i_sites is None:
+            raise ValueError("MeanVarSepHVIApproximation needs i_sites (src/elbo_sepvec.jl:23)")
+        if batch_token is None or batch_token != state["token"]:
+            plan.set_data(xM, xP, y_o, y_unc, i_sites=i_sites if prob.is_sepvar else None)
+            state["token"] = batch_token
         return plan.neg_elbo_withgradient(ϕ, n_MC=n_MC, seed=int(rng_seed))
 
     loss_elbo.plan = plan

@@ -8,7 +8,17 @@
  * Conventions: every function returns an `int` status (HVI_OK == 0); no exception crosses
  * the boundary; the caller owns every pointer it passes; a plan owns its device buffers;
  * one in-flight call per plan; calls are synchronous at return unless the name ends in
- * `_async`.  Arrays are column-major with the reference's shapes (site = column).
+ * `_async` (or the entry says otherwise).  Arrays are column-major with the reference's shapes
+ * (site = column).
+ *
+ * Stream contract.  A plan works on its own non-blocking stream (or the one given to
+ * hvi_plan_set_stream).  Work that an `_async` / `_apply_dev` call enqueues on a CALLER's stream is
+ * ordered on the device against the plan's stream in both directions: the caller's stream waits for the
+ * plan's earlier work (batch registration, earlier calls), and every later call on the plan waits for what
+ * was left on the caller's stream -- no host synchronisation is needed between calls.  What the library
+ * cannot see are the kernels that PRODUCE a HVI_MEM_DEVICE argument (phi, zP, zMs, xM, ... written by the
+ * caller's own kernels on the caller's own stream): either make the plan work on that stream
+ * (hvi_plan_set_stream) or synchronise that stream before the call.
  */
 #ifndef HVI_B200_H
 #define HVI_B200_H
@@ -143,6 +153,22 @@ int hvi_plan_prefetch_data(hvi_plan* plan, int64_t n_site, const void* xM, const
                            const void* y_o, const void* y_unc);
 int hvi_plan_commit_data(hvi_plan* plan);
 
+/* Device-resident training set with minibatch selection on the device -- gdev_hybridproblem_dataloader
+ * (src/AbstractHybridProblem.jl:220-250) moves the whole loader to the GPU once and solve walks its minibatches
+ * (src/HybridSolver.jl:259-260; MLUtils.DataLoader(...; batchsize, partial = false), src/AbstractHybridProblem.jl:
+ * 206-207).  hvi_plan_set_dataset is the one upload (arrays as in hvi_plan_set_data, n_site_total columns).
+ * hvi_plan_select_range makes sites [first, first + n) the registered batch, hvi_plan_select_batch the sites
+ * i_sites[0..n) (0-based; host or device array): one gather + re-tile kernel, stream-ordered, no host round trip, no
+ * synchronisation.  With MeanVarSep the selected indices also become the plan's `i_sites`. */
+int hvi_plan_set_dataset(hvi_plan* plan, int64_t n_site_total, const void* xM, const void* xP,
+                         const void* y_o, const void* y_unc, int mem_kind);
+int hvi_plan_select_range(hvi_plan* plan, int64_t first, int64_t n);
+int hvi_plan_select_batch(hvi_plan* plan, const int64_t* i_sites, int64_t n, int mem_kind);
+
+/* The plan's stream: cuda_stream (a cudaStream_t of the plan's device) replaces the plan's own stream for every
+ * later call; use_own != 0 switches back.  The new stream continues behind everything queued on the old one. */
+int hvi_plan_set_stream(hvi_plan* plan, void* cuda_stream, int use_own);
+
 /* MeanVarSep only: the 0-based indices (into 0..n_site_total) of the registered batch's sites -- the
  * `i_sites` argument of loss_elbo (src/HybridSolver.jl:312-322, src/elbo_sepvec.jl:23).  Host array of
  * length n_site; default after set_data is 0..n_site-1. */
@@ -188,13 +214,23 @@ int hvi_loss_gf_grad(hvi_plan* plan, const void* phi_gf, int mem_kind, double co
  * hvi_adam_init uploads ϕ0 (host) and resets the moments.  hvi_adam_run enqueues n_iter iterations on the
  * registered batch back to back -- iteration i draws with seed0 + i -- and, if nL_trace (host, n_iter doubles)
  * is given, returns the loss of every iteration (NaN marks an iteration that was skipped because its value or
- * gradient was not finite); with nL_trace = NULL nothing is synchronised.  hvi_adam_get_phi downloads ϕ.
+ * gradient was not finite, or because the batch holds a finite observation under a missing driver; a skipped
+ * iteration does not advance the Adam step count); with nL_trace = NULL nothing is synchronised.  hvi_adam_get_phi downloads ϕ.
  * Multi-GPU: evaluate with hvi_neg_elbo_grad_async on phi = *hvi_adam_phi_dev, all-reduce out_dev, then
  * hvi_adam_apply_dev(out_dev) on every rank (identical updates, ϕ stays replicated). */
 int hvi_adam_init(hvi_plan* plan, const void* phi0, double eta, double beta1, double beta2, double eps);
 int hvi_adam_run(hvi_plan* plan, int32_t n_iter, int32_t n_MC, uint64_t seed0, int64_t site_offset,
                  double* nL_trace);
 int hvi_adam_apply_dev(hvi_plan* plan, const double* out_dev, void* cuda_stream);
+/* The minibatch loop of solve on the device-resident dataset (hvi_plan_set_dataset): iteration i selects minibatch
+ * (first_batch + i) mod n_batches, n_batches = n_site_total / batch_size (consecutive column ranges, last partial
+ * batch dropped, no shuffling: src/AbstractHybridProblem.jl:206-207), evaluates value + gradient with draws seeded
+ * seed0 + i and applies the Adam update.  Iteration state (step count, minibatch index, seed) lives in device
+ * counters, so iterations 2..n replay ONE captured CUDA graph (hvi_plan_use_graphs(plan, 0) turns that off).
+ * hvi_adam_run does the same on the registered batch. */
+int hvi_adam_run_minibatches(hvi_plan* plan, int32_t n_iter, int32_t n_MC, uint64_t seed0, int64_t batch_size,
+                             int64_t first_batch, double* nL_trace);
+int hvi_plan_use_graphs(hvi_plan* plan, int on);
 int hvi_adam_phi_dev(hvi_plan* plan, void** phi_dev);
 int hvi_adam_get_phi(hvi_plan* plan, void* phi_host);
 
