@@ -41,3 +41,23 @@ for dtype in ("f32", "f64"):
         dt = (time.perf_counter() - t0) / n
         print(f"{dtype} n_batch={nb:6d} n_MC={M:3d}: {dt * 1e6:8.1f} us per iteration  ({nb * M / dt:.3e} units/s)  "
               f"loss {tr[0]:.4g} -> {tr[-1]:.4g}", flush=True)
+
+# the reference's training loop itself: 800 sites on the device, 20-site minibatches walked by hvi_adam_run_minibatches
+# (src/HybridSolver.jl:259-260); graph replay on / off
+print("minibatch loop on the device-resident dataset (hvi_adam_run_minibatches, 800 sites, 2000 iterations):")
+for dtype in ("f32", "f64"):
+    for bs, M in ((20, 3), (20, 12), (200, 12)):
+        for graphs in (True, False):
+            prob = hvi_b200.DoubleMMCase(dtype=dtype)
+            data = hvi_b200.gen_hybridproblem_synthetic(prob, 800)
+            plan = hvi_b200.NegElboPlan(prob)
+            plan.set_dataset(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+            plan.use_graphs(graphs)
+            plan.adam_init(prob.init_ϕ(), eta=0.02)
+            plan.adam_run_minibatches(50, M, bs, seed0=0)
+            n = 2000
+            t0 = time.perf_counter()
+            tr = plan.adam_run_minibatches(n, M, bs, seed0=100)
+            dt = (time.perf_counter() - t0) / n
+            print(f"{dtype} n_batch={bs:4d} n_MC={M:3d} graphs={graphs!s:5}: {dt * 1e6:8.1f} us per iteration  "
+                  f"loss {np.nanmean(tr[:40]):.4g} -> {np.nanmean(tr[-40:]):.4g}", flush=True)
