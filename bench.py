@@ -50,14 +50,27 @@ def parse():
     ap.add_argument("--nan-frac", type=float, default=0.0, help="fraction of sites with missing drivers (:driverNAN generalised)")
     ap.add_argument("--cpu-sample-sites", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --sites per GPU (default); strong: --sites in total, split over the GPUs (BASELINE config 4)")
+    ap.add_argument("--p2-sample-sites", type=int, default=100_000, help="sites of the torch-autograd (P2) CPU timing")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
+def sites_of_rank(args, rank, world):
+    """weak scaling: --sites on every GPU; strong scaling: --sites in total, contiguous balanced site ranges"""
+    if args.scaling == "weak":
+        return args.sites
+    base, rem = divmod(args.sites, world)
+    return base + (1 if rank < rem else 0)
+
+
 def workload_config(args, prob):
-    return {"workload": f"DoubleMM (BASELINE config 4 shape) {args.sites:.0e} sites/GPU x n_MC={args.n_mc}, "
+    per = "sites/GPU" if args.scaling == "weak" else f"sites in total over {args.gpus} GPU(s)"
+    return {"workload": f"DoubleMM (BASELINE config 4 shape) {args.sites:.0e} {per} x n_MC={args.n_mc}, "
                         f"scenario=({args.scenario}), MLP {'-'.join(str(l[0]) for l in prob.layers)}-{prob.layers[-1][1]}",
-            "sites_per_gpu": args.sites, "n_MC": args.n_mc, "n_phi": prob.n_phi, "nan_frac": args.nan_frac,
+            "sites_per_gpu": args.sites if args.scaling == "weak" else args.sites / max(args.gpus, 1),
+            "n_MC": args.n_mc, "n_phi": prob.n_phi, "nan_frac": args.nan_frac,
             "parallelism": f"site-sharded x{args.gpus}, allreduce of [grad; components]",
             "l2": "inputs (>= 600 B/site x sites) exceed the 126 MB L2; no flush needed"}
 
@@ -108,6 +121,28 @@ def cpu_baseline(prob, n_MC, sample_sites, nthreads):
     return sample_sites * n_MC / dt, dt
 
 
+def p2_baseline(prob, n_MC, sample_sites):
+    """P2 of BASELINE.md: the float32 torch-autograd oracle (taped reverse mode, structurally the closest thing to the
+    reference's Zygote path that can run here) on a bounded sample, all torch CPU threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import hvi_b200
+    from helpers import O, oracle_spec
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, sample_sites, seed=111)
+    zP, zMs = hvi_b200.draw_ξ(prob, sample_sites, n_MC)
+    ϕ = prob.init_ϕ(perturbed=True)
+    spec = oracle_spec(prob)
+    n0 = min(1000, sample_sites)
+    O.value_and_grad(spec, ϕ, data["xM"][:, :n0], data["xP"][:, :n0], data["y_o"][:, :n0], data["y_unc"][:, :n0], zP,
+                     zMs[:, :n0 * prob.n_M], "f32")
+    t0 = time.perf_counter()
+    O.value_and_grad(spec, ϕ, data["xM"], data["xP"], data["y_o"], data["y_unc"], zP, zMs, "f32")
+    dt = time.perf_counter() - t0
+    return {"value": sample_sites * n_MC / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_sites} sites x n_MC={n_MC}, one evaluation, {dt:.1f} s",
+            "note": "P2: oracle/hvi_oracle.py, float32 torch autograd on the CPU (Zygote-like proxy)"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation cannot run here (Julia absent), so
     the CPU restatement of it (oracle port) is timed with all host threads on the same config."""
@@ -133,12 +168,70 @@ def run_reference(args):
     sample_txt = f"{sample} sites x n_MC={args.n_mc} per step (bounded sample of the {args.sites:.0e}-site workload)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, prob),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_txt,
                          "note": "C restatement of the reference (oracle/hvi_oracle.c, OpenMP); the Julia reference "
                                  "itself cannot run in this image"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def dominant_roofline(args, prob, nb, M, kt, peaks, sampler, local):
+    """Roofline of the kernel (group) that dominates THIS run, from the library's own per-kernel CUDA events:
+    the fused streaming kernel against HBM, or the applicator g (forward + backward) against the tensor pipe."""
+    nO, nM = prob.n_obs, prob.n_M
+    g_ms = kt["mlp_fwd"] + kt["mlp_bwd"]
+    mac = sum(i * o for i, o, _, _ in prob.layers)
+    cols = nb * (M + 1) if prob.pbm_covars else nb
+    wide = max(max(i, o) for i, o, _, _ in prob.layers) > 64
+    traffic = None
+    if kt["stream"] >= g_ms:
+        # site records + μ_ζ/μ̄_ζ hand-off + ξ (+ per-draw means and their cotangents with pbm covariates)
+        alg_bytes = nb * (4 * 4 * nO + 2 * 4 * nM + 4 * nM * M + (2 * 4 * nM * M if prob.pbm_covars else 0))
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg_bytes / (kt["stream"] * 1e-3) / 1e9
+        kernel = "k_stream"
+        # DRAM bytes per launch from the committed `ncu --set full` capture of this workload and this kernel variant
+        # (profiles/traffic.json, written from the capture by profiles/summarize_ncu.py); null without a capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tj.get(f"k_stream:{args.scenario}:{nb}x{M}", {})
+            traffic = ent.get("dram_bytes")
+            kernel = ent.get("kernel", kernel)
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kt}
+        # the kernel's real limiter is the FP32 pipe (DESIGN.md §4): pipe slots per site·draw counted in the SASS of the
+        # hot loop (profiles/sass_summary.txt) against 128 lanes x SMs x clock
+        try:
+            import torch
+            sm = torch.cuda.get_device_properties(local).multi_processor_count
+            clk_hz = float(sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+            if nO == 8 and nM == 2 and not prob.pbm_covars:
+                slots = FP32_SLOTS_PER_UNIT
+                roofline["fp32_pipe"] = {"slots_per_unit": slots, "peak_lane_slots_per_s": sm * 128 * clk_hz,
+                                         "frac": slots * nb * M / (kt["stream"] * 1e-3) / (sm * 128 * clk_hz)}
+        except Exception:
+            pass
+        return roofline
+    # the applicator dominates: 2·Σ in·out flop per column forward, x3 with the backward pass (SURVEY 8(d)); the tensor
+    # work is 3 passes of that (3xBF16 / 3xTF32 error-compensated split) -- the algorithmic figure is the fp32-equivalent one
+    alg_flop = 3.0 * 2.0 * mac * cols
+    peak = float(peaks.get("bf16_tflops_sustained", 1384.0))
+    achieved = alg_flop / (g_ms * 1e-3) / 1e12
+    kernel = "k_gemm_bf3 chain (tcgen05 kind::f16, TMA)" if wide else "k_mlp3_mma_fwd + k_mlp3_mma_bwd (mma.sync)"
+    return {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)" if peaks
+                           else "fallback 1384 TFLOP/s",
+            "algorithmic_flop_per_step": alg_flop, "tensor_passes": 3, "columns": cols, "kernel_ms": kt}
+
+
+# FP32-pipe slots per site·draw of k_stream's hot loop (DoubleMM, 8 observations): packed instructions count twice
+FP32_SLOTS_PER_UNIT = 149
 
 
 def bind_to_gpu_numa_node(gpu):
@@ -175,7 +268,8 @@ def main():
     dev = torch.device("cuda", local)
     hidden = tuple(int(w) for w in args.hidden.split(",") if w) or None
     prob = hvi_b200.DoubleMMCase(tuple(s for s in args.scenario.split(",") if s), dtype="f32", hidden=hidden)
-    nb, M = args.sites, args.n_mc
+    nb, M = sites_of_rank(args, rank, world), args.n_mc
+    n_total = world * nb if args.scaling == "weak" else args.sites
     # synthetic batch of this rank's site shard (generator restates gen_hybridproblem_synthetic)
     data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=111 + rank, driver_nan_frac=args.nan_frac)
     ϕ = prob.init_ϕ(perturbed=True)
@@ -222,7 +316,7 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    value = world * nb * M / (ms_step * 1e-3)
+    value = n_total * M / (ms_step * 1e-3)
     res = out_dev.cpu().numpy()
 
     # ---- roofline of the dominant kernel, timed alone by the library's own events ----------
@@ -236,42 +330,12 @@ def main():
     plan.set_profiling(False)
     sampler.stop_flag = True
     kt = {k: float(np.mean(v)) for k, v in acc.items()}
-    nO, nM = prob.n_obs, prob.n_M
-    # site records + μ_ζ/μ̄_ζ hand-off + ξ (+ per-draw means and their cotangents with pbm covariates)
-    alg_bytes = nb * (4 * 4 * nO + 2 * 4 * nM + 4 * nM * M + (2 * 4 * nM * M if prob.pbm_covars else 0))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes / (kt["stream"] * 1e-3) / 1e9
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
-    # workload (profiles/traffic.json, written from the capture by profiles/summarize_ncu.py); null if
-    # this workload has no capture
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get(f"k_stream:{args.scenario}:{nb}x{M}", {}).get("dram_bytes")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "k_stream<float,2,2,8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kt}
-    # the kernel's real limiter is the FP32 pipe: 56 packed + 35 scalar FP32 instructions per site·draw
-    # for DoubleMM with 8 observations = 147 pipe slots (SASS count of the hot loop, profiles/README.md), against
-    # 128 lanes x SMs x clock; reported next to the HBM roofline the contract asks for
-    try:
-        import torch
-        sm = torch.cuda.get_device_properties(local).multi_processor_count
-        clk_hz = float(sampler.summary().get("sm_mhz") or 1965.0) * 1e6
-        if nO == 8 and nM == 2 and not prob.pbm_covars:
-            roofline["fp32_pipe"] = {"slots_per_unit": 147, "peak_lane_slots_per_s": sm * 128 * clk_hz,
-                                     "frac": 147.0 * nb * M / (kt["stream"] * 1e-3) / (sm * 128 * clk_hz)}
-    except Exception:
-        pass
-
+    roofline = dominant_roofline(args, prob, nb, M, kt, peaks, sampler, local)
     # ---- end to end through the public host API ------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -294,7 +358,7 @@ def main():
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        serial = world * nb * M / float(tt.item())
+        serial = n_total * M / float(tt.item())
         serial_ms = float(tt.item()) * 1e3
         # the minibatch loop as the library is meant to be driven: the upload of batch i+1 (prefetch_data, copy
         # stream) runs under the evaluation of batch i; every step still moves one whole batch host → device and
@@ -319,7 +383,7 @@ def main():
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * nb * M / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+        e2e = {"value": n_total * M / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": float(tt.item()) * 1e3,
                "what": "per step: commit_data + prefetch_data(next host batch, pinned) + neg_elbo_withgradient(host ϕ, "
                        "device-drawn ξ); the upload overlaps the evaluation; wall clock",
@@ -330,11 +394,43 @@ def main():
         for i in range(n_e2e):
             plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=2 + i)
         barrier()
-        e2e["resident_value"] = world * nb * M / ((time.perf_counter() - t0) / n_e2e)
+        e2e["resident_value"] = n_total * M / ((time.perf_counter() - t0) / n_e2e)
+        # the kernels of one such call (device draws: Philox + Box-Muller inside k_stream instead of ξ read from HBM)
+        plan.set_profiling(True)
+        plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=99)
+        e2e["resident_kernel_ms"] = plan.kernel_times_ms()
+        plan.set_profiling(False)
+        # training set resident on the device, the minibatch chosen there (hvi_plan_set_dataset + select_range --
+        # gdev_hybridproblem_dataloader, src/AbstractHybridProblem.jl:220-250): per step one gather kernel instead
+        # of an upload; ϕ host -> device and (nL, ∇ϕ) -> host stay inside the timed region
+        try:
+            plan.set_dataset(host["xM"], host["xP"], host["y_o"], host["y_unc"])
+            plan.select_range(0, nb)
+            plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=1)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(n_e2e):
+                plan.select_range(0, nb)
+                nL, comps, grad = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=2 + i)
+                if dist is not None:
+                    gt = torch.from_numpy(grad).to(dev)
+                    dist.all_reduce(gt)
+                    grad = gt.cpu().numpy()
+            barrier()
+            tt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e["device_dataset_value"] = n_total * M / float(tt.item())
+            e2e["device_dataset_ms_per_step"] = float(tt.item()) * 1e3
+            e2e["device_dataset_what"] = ("set_dataset once (outside the timed region); per step select_range (device "
+                                          "gather + re-tile) + neg_elbo_withgradient(host ϕ): h2d = 4·n_phi bytes")
+        except Exception as ex:   # e.g. not enough HBM for a second copy of a very large batch
+            e2e["device_dataset_value"] = None
+            e2e["device_dataset_what"] = f"skipped: {ex}"
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, prob),
                 "clocks": sampler.summary(), "gpu_launches": int(launches), "roofline": roofline,
                 "nL": float(res[n_phi + 6]), "nonfinite": float(res[n_phi + 7])}
@@ -345,6 +441,11 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{args.cpu_sample_sites} sites x n_MC={M}, one evaluation, {dt:.1f} s",
                                     "note": "oracle/hvi_oracle.c (C restatement of the Julia reference), f32, 1 thread"}
+            if args.p2_sample_sites > 0 and not prob.pbm_covars and hidden is None:
+                try:
+                    line["cpu_baseline"]["p2_torch_autograd"] = p2_baseline(prob, M, args.p2_sample_sites)
+                except Exception as ex:
+                    line["cpu_baseline"]["p2_torch_autograd"] = {"unavailable": str(ex)}
         print(json.dumps(line, ensure_ascii=False))
     if dist is not None:
         dist.destroy_process_group()
