@@ -9,9 +9,9 @@ from . import _abi
 from .problem import (HybridProblem, DoubleMMCase, construct_problem_test_HybridProblem,
                       gen_hybridproblem_synthetic, draw_ξ)
 from .elbo import (NegElboPlan, NegElboComponents, HVIError, neg_elbo_gtf, neg_elbo_gtf_components,
-                   get_loss_elbo, vec2utri_pos, utri2vec_pos, get_cor_count, COMPONENT_NAMES)
+                   get_loss_elbo, pbm_compile_check, vec2utri_pos, utri2vec_pos, get_cor_count, COMPONENT_NAMES)
 
 __all__ = ["_abi", "HybridProblem", "DoubleMMCase", "construct_problem_test_HybridProblem",
            "gen_hybridproblem_synthetic", "draw_ξ", "NegElboPlan", "NegElboComponents", "HVIError",
-           "neg_elbo_gtf", "neg_elbo_gtf_components", "get_loss_elbo", "vec2utri_pos", "utri2vec_pos",
+           "neg_elbo_gtf", "neg_elbo_gtf_components", "get_loss_elbo", "pbm_compile_check", "vec2utri_pos", "utri2vec_pos",
            "get_cor_count", "COMPONENT_NAMES"]

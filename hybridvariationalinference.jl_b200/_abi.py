@@ -77,6 +77,8 @@ SYMBOLS = [
     ("hvi_plan_select_range", _INT, [_P, _I64, _I64]),
     ("hvi_plan_select_batch", _INT, [_P, _P, _I64, _INT]),
     ("hvi_plan_set_stream", _INT, [_P, _P, _INT]),
+    ("hvi_plan_set_pbm", _INT, [_P, C.c_char_p, _I32, _I32, _DP]),
+    ("hvi_pbm_compile_check", _INT, [C.c_char_p, _I32, _I32, _I32, _I32, _I32, C.c_char_p, _I32]),
     ("hvi_neg_elbo_grad", _INT, [_P, _I32, _P, _P, _P, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_rng", _INT, [_P, _I32, _P, _U64, _I64, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_async", _INT, [_P, _I32, _P, _P, _P, _U64, _I64, _P, _P]),

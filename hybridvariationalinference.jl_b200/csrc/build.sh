@@ -6,8 +6,12 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
-SRCS="hvi_kernels hvi_capi hvi_dense_tc hvi_dense_tma hvi_mlp_mma hvi_point hvi_predict"
+SRCS="hvi_kernels hvi_capi hvi_dense_tc hvi_dense_tma hvi_mlp_mma hvi_point hvi_predict hvi_generic"
 HDRS="hvi_internal.cuh hvi_tc_common.cuh hvi_rng.cuh hvi_pbm.cuh ../../include/hvi_b200.h"
+# the text of hvi_pbm.cuh travels inside the library: NVRTC compiles it together with a user's process model
+if [ ! -f hvi_pbm_src.inc ] || [ hvi_pbm.cuh -nt hvi_pbm_src.inc ]; then
+  { printf 'static const char hvi_pbm_header[] = R"HVIPBMSRC('; cat hvi_pbm.cuh; printf ')HVIPBMSRC";\n'; } > hvi_pbm_src.inc
+fi
 pids=()
 for f in $SRCS; do
   stale=0
@@ -22,4 +26,4 @@ done
 for pid in "${pids[@]}"; do wait $pid || { echo "build.sh: a compile failed" >&2; exit 1; }; done
 OBJS=""
 for f in $SRCS; do OBJS="$OBJS $f.o"; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libhvi_b200.so $OBJS
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libhvi_b200.so $OBJS -ldl

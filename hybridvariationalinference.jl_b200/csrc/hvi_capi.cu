@@ -51,6 +51,8 @@ struct hvi_plan {
   void *ds_xM, *ds_xP, *ds_yo, *ds_yu;
   int64_t* d_idx; int64_t cap_idx;   // minibatch indices of hvi_plan_select_batch
   int64_t n_isites;                  // length of d_isites
+  // generic process-based model (hvi_plan_set_pbm): run-time compiled kernel, driver rows per site, raw observations
+  GenericPbm* gpbm; int n_x; void *d_yo, *d_yu; double* d_pen; double pbm_fix[MAXP]; std::string pbm_spec;
   // per-evaluation scratch
   void* d_phi;
   void* d_zP; int64_t cap_zP;
@@ -94,7 +96,7 @@ static thread_local std::string g_create_err;
 
 #define PLAN_FAIL(plan, code, ...)                    \
   do {                                                \
-    char buf_[512];                                   \
+    char buf_[2048];                                  \
     snprintf(buf_, sizeof buf_, __VA_ARGS__);         \
     (plan)->err = buf_;                               \
     return (code);                                    \
@@ -263,6 +265,8 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   p->own_stream = nullptr; p->ev_user = p->ev_plan = nullptr; p->user_pending = 0;
   p->d_bconst = nullptr; p->h_bconst = nullptr;
   p->ds_n = 0; p->ds_has_obs = 0; p->ds_xM = p->ds_xP = p->ds_yo = p->ds_yu = nullptr; p->d_idx = nullptr; p->cap_idx = 0; p->n_isites = 0;
+  p->gpbm = nullptr; p->n_x = 2 * desc->n_obs; p->d_yo = p->d_yu = nullptr; p->d_pen = nullptr;
+  for (double& v : p->pbm_fix) v = 0.0;
   p->copy_stream = nullptr; p->ev_copied = nullptr; p->d_xM_next = p->d_xP_next = nullptr;
   p->cap_cur = p->cap_next = p->nb_next = 0; p->has_obs_next = 0;
   p->d_xM = p->d_rec = p->d_mu = p->d_mubar = nullptr; p->d_xP = nullptr; p->has_obs = 0; p->d_isites = nullptr;
@@ -327,9 +331,10 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   if (p->own_stream && p->own_stream != p->stream) cudaStreamSynchronize(p->own_stream);
   if (p->user_pending && p->ev_user) cudaEventSynchronize(p->ev_user);
   if (p->adam_graph) cudaGraphExecDestroy(p->adam_graph);
+  if (p->gpbm) generic_pbm_destroy(p->gpbm);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->ev_copied) cudaEventDestroy(p->ev_copied);
-  void* dev[] = {p->d_bconst, p->d_ctr, p->ds_xM, p->ds_xP, p->ds_yo, p->ds_yu, p->d_idx, p->d_ls, p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->d_trace, p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
+  void* dev[] = {p->d_yo, p->d_yu, p->d_pen, p->d_bconst, p->d_ctr, p->ds_xM, p->ds_xP, p->ds_yo, p->ds_yu, p->d_idx, p->d_ls, p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->d_trace, p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
                  p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide, p->d_wide_bwd, p->d_gacc, p->d_wide_cache};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
@@ -424,6 +429,46 @@ extern "C" int hvi_plan_set_stream(hvi_plan* p, void* cuda_stream, int use_own) 
   return HVI_OK;
 }
 
+extern "C" int hvi_plan_set_pbm(hvi_plan* p, const char* pbm, int32_t n_x, int32_t n_fix, const double* fix) {
+  if (!p) return HVI_EINVAL;
+  if (!pbm) PLAN_FAIL(p, HVI_EINVAL, "set_pbm: pbm is NULL");
+  if (n_fix < 0 || n_fix > MAXP || (n_fix > 0 && !fix)) PLAN_FAIL(p, HVI_EINVAL, "set_pbm: 0 <= n_fix <= %d fixed parameters", MAXP);
+  CU(p, cudaSetDevice(p->desc.device));
+  int rc = join_user(p);
+  if (rc) return rc;
+  CU(p, cudaStreamSynchronize(p->stream));
+  // a different process model invalidates the registered batch (its layout depends on the model)
+  for (void** q : {&p->d_rec, &p->d_mu, &p->d_mubar, &p->d_yo, &p->d_yu, &p->d_xM, &p->d_xP}) { if (*q) cudaFree(*q); *q = nullptr; }
+  p->nb = 0; p->cap_cur = 0; p->graph_valid = 0;
+  if (p->gpbm) { generic_pbm_destroy(p->gpbm); p->gpbm = nullptr; }
+  for (int i = 0; i < MAXP; i++) p->pbm_fix[i] = i < n_fix ? fix[i] : 0.0;
+  p->pbm_spec = pbm;
+  if (p->pbm_spec == "doubleMM") {   // the hand-written kernel (default)
+    p->n_x = 2 * p->desc.n_obs;
+    return HVI_OK;
+  }
+  if (n_x < 1) PLAN_FAIL(p, HVI_EINVAL, "set_pbm: n_x (driver rows per site) must be >= 1");
+  if (p->wide) PLAN_FAIL(p, HVI_EINVAL, "set_pbm: a generic process model is not available with the wide applicator");
+  if (p->pbm_spec == "builtin:doubleMM")   // θFix of the slot map comes from the description
+    for (int s_ = 0; s_ < 4; s_++) p->pbm_fix[s_] = p->desc.slot_src[s_] == HVI_SRC_FIX ? p->desc.slot_fix[s_] : 0.0;
+  std::string err;
+  rc = generic_pbm_create(pbm, p->dtype, p->desc.n_P, p->desc.n_M, p->desc.n_obs, n_x, p->cf.npc > 0, err, &p->gpbm);
+  if (rc) PLAN_FAIL(p, rc, "%s", err.c_str());
+  p->n_x = n_x;
+  if (!p->d_pen) CU(p, cudaMalloc((void**)&p->d_pen, sizeof(double) * (size_t)p->max_rows));
+  return HVI_OK;
+}
+
+// NVRTC compilation of a process model for the given problem shape without touching a device (log: the compiler's
+// message on failure).  Lets a host check a model's source before a GPU is involved.
+extern "C" int hvi_pbm_compile_check(const char* pbm, int32_t dtype, int32_t n_P, int32_t n_M, int32_t n_obs, int32_t n_x,
+                                     char* log, int32_t log_len) {
+  std::string err;
+  const int rc = generic_pbm_compile_check(pbm, dtype, n_P, n_M, n_obs, n_x, err);
+  if (log && log_len > 0) { strncpy(log, err.c_str(), (size_t)log_len - 1); log[log_len - 1] = 0; }
+  return rc;
+}
+
 extern "C" int hvi_plan_set_sites(hvi_plan* p, const int64_t* i_sites, int64_t n) {
   if (!p) return HVI_EINVAL;
   if (p->nb <= 0) PLAN_FAIL(p, HVI_ENODATA, "hvi_plan_set_data has not been called");
@@ -472,15 +517,19 @@ template <typename T>
 static int alloc_batch(hvi_plan* p, int64_t nb, bool keep_raw) {
   const int nO = p->desc.n_obs, nC = p->desc.n_covar, nM = p->desc.n_M;
   if (nb == p->nb && (keep_raw || p->cap_cur >= nb)) return HVI_OK;
-  for (void** q : {&p->d_rec, &p->d_mu, &p->d_mubar}) { if (*q) cudaFree(*q); *q = nullptr; }
+  for (void** q : {&p->d_rec, &p->d_mu, &p->d_mubar, &p->d_yo, &p->d_yu}) { if (*q) cudaFree(*q); *q = nullptr; }
   p->nb = 0;
   const int64_t ntiles = (nb + 31) / 32;
   if (!keep_raw) {
     for (void** q : {&p->d_xM, &p->d_xP}) { if (*q) cudaFree(*q); *q = nullptr; }
     p->cap_cur = 0;
     CU(p, cudaMalloc(&p->d_xM, sizeof(T) * (size_t)nC * nb));
-    CU(p, cudaMalloc(&p->d_xP, sizeof(T) * (size_t)2 * nO * nb));
+    CU(p, cudaMalloc(&p->d_xP, sizeof(T) * (size_t)p->n_x * nb));
     p->cap_cur = nb;
+  }
+  if (p->gpbm) {   // the generic kernel reads the raw observations instead of DoubleMM records
+    CU(p, cudaMalloc(&p->d_yo, sizeof(T) * (size_t)nO * nb));
+    CU(p, cudaMalloc(&p->d_yu, sizeof(T) * (size_t)nO * nb));
   }
   CU(p, cudaMalloc(&p->d_rec, sizeof(T) * (size_t)ntiles * 32 * 4 * nO));
   CU(p, cudaMalloc(&p->d_mu, sizeof(T) * (size_t)nM * nb));
@@ -511,6 +560,14 @@ static int finish_batch(hvi_plan* p, int64_t nb, const T* dxP, const T* dyo, con
   // the stream partial buffer doubles as scratch for the 2·nwarps preprocess partials
   const int NACC = nacc(p->cf.nP, p->cf.nM);
   if ((size_t)2 * p->sm_count * 8 * 8 > (size_t)p->max_rows * NACC) PLAN_FAIL(p, HVI_EINVAL, "internal: scratch too small");
+  if (p->gpbm) {
+    if (!dyo || !dyu) PLAN_FAIL(p, HVI_ENODATA, "a generic process model needs observations (y_o, y_unc)");
+    const size_t n2 = (size_t)nO * nb;
+    CU(p, cudaMemcpyAsync(p->d_yo, dyo, sizeof(T) * n2, cudaMemcpyDeviceToDevice, p->stream));
+    CU(p, cudaMemcpyAsync(p->d_yu, dyu, sizeof(T) * n2, cudaMemcpyDeviceToDevice, p->stream));
+    CU(p, launch_preprocess_generic<T>(L, (int64_t)n2, (const T*)p->d_yo, (const T*)p->d_yu, p->d_part_stream, &nrows));
+    return finish_consts(p, nrows, true);
+  }
   CU(p, launch_preprocess<T>(L, nO, nb, dxP, dyo, dyu, (T*)p->d_rec, p->d_part_stream, &nrows));
   // synchronous: the caller's host arrays are free again at return, and the anomaly count is known
   return finish_consts(p, nrows, true);
@@ -532,7 +589,7 @@ static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, c
   CU(p, copy_in(p->d_xM, xM, sizeof(T) * (size_t)nC * nb, mem_kind, p->stream));
   const T *dxP = (const T*)xP, *dyo = (const T*)y_o, *dyu = (const T*)y_unc;
   {
-    const size_t n1 = (size_t)2 * nO * nb, n2 = (size_t)nO * nb;
+    const size_t n1 = (size_t)p->n_x * nb, n2 = (size_t)nO * nb;
     CU(p, copy_in(p->d_xP, xP, sizeof(T) * n1, mem_kind, p->stream));
     dxP = (const T*)p->d_xP;
     p->has_obs = (y_o && y_unc) ? 1 : 0;
@@ -620,6 +677,7 @@ extern "C" int hvi_plan_prefetch_data(hvi_plan* p, int64_t n_site, const void* x
   if (!p) return HVI_EINVAL;
   if (n_site < 1 || !xM || !xP) PLAN_FAIL(p, HVI_EINVAL, "prefetch_data: n_site must be >= 1 and xM, xP non-NULL");
   if ((y_o == nullptr) != (y_unc == nullptr)) PLAN_FAIL(p, HVI_EINVAL, "prefetch_data: y_o and y_unc must both be given or both be NULL");
+  if (p->gpbm) PLAN_FAIL(p, HVI_EINVAL, "prefetch_data: not available with a generic process model (use hvi_plan_set_data)");
   CU(p, cudaSetDevice(p->desc.device));
   if (p->cf.sepvar && n_site > p->cf.n_site_total) PLAN_FAIL(p, HVI_EINVAL, "prefetch_data: batch has more sites than n_site_total");
   return p->dtype == HVI_F32 ? prefetch_t<float>(p, n_site, xM, xP, y_o, y_unc) : prefetch_t<double>(p, n_site, xM, xP, y_o, y_unc);
@@ -693,6 +751,7 @@ extern "C" int hvi_plan_set_dataset(hvi_plan* p, int64_t n_site_total, const voi
   if (n_site_total < 1 || !xM || !xP) PLAN_FAIL(p, HVI_EINVAL, "set_dataset: n_site_total must be >= 1 and xM, xP non-NULL");
   if ((y_o == nullptr) != (y_unc == nullptr)) PLAN_FAIL(p, HVI_EINVAL, "set_dataset: y_o and y_unc must both be given or both be NULL");
   if (mem_kind != HVI_MEM_HOST && mem_kind != HVI_MEM_DEVICE) PLAN_FAIL(p, HVI_EINVAL, "set_dataset: bad mem_kind");
+  if (p->gpbm) PLAN_FAIL(p, HVI_EINVAL, "set_dataset: not available with a generic process model (use hvi_plan_set_data)");
   if (p->cf.sepvar && n_site_total != p->cf.n_site_total)
     PLAN_FAIL(p, HVI_EINVAL, "set_dataset: MeanVarSep needs the dataset to hold exactly n_site_total sites");
   CU(p, cudaSetDevice(p->desc.device));
@@ -844,7 +903,12 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
     if (grad_T) CU(p, cudaMemsetAsync(grad_T + cfg.o_coef, 0, sizeof(T) * big, s));
   }
   int nrows = 0, nblk = 0, nblk2 = 0;
-  CU(p, launch_stream<T>(L, cfg, a, &nrows, p->max_rows));
+  const bool penalty = generic_pbm_has_penalty(p->gpbm);
+  if (p->gpbm)
+    CU(p, launch_generic_stream<T>(L, p->gpbm, cfg, a, (const T*)p->d_xP, (const T*)p->d_yo, (const T*)p->d_yu, p->pbm_fix,
+                                   penalty ? p->d_pen : nullptr, &nrows, p->max_rows));
+  else
+    CU(p, launch_stream<T>(L, cfg, a, &nrows, p->max_rows));
   MARK();
   double* part_xs = pbm ? p->d_part_x : nullptr;
   double* part_xu = pbm ? p->d_part_x + (size_t)p->max_blk * cfg.npc : nullptr;
@@ -872,6 +936,7 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   MARK();
   CU(p, launch_finalize<T>(L, cfg, phi, zP, pdraw, ec, p->d_part_stream, nrows, part_g, nblk + nblk2, p->d_bconst,
                            p->nb, M, out, grad_T, p->d_red, part_xs, p->wide ? 1 : nblk, part_xu, p->wide ? 1 : nblk2, p->d_xred));
+  if (penalty) CU(p, launch_add_penalty(L, p->d_pen, nrows, M, cfg.nphi, out));
   MARK();
 #undef MARK
   p->n_ev = iev;
@@ -1209,6 +1274,7 @@ extern "C" int hvi_predict(hvi_plan* p, int32_t n_sample, const void* phi, const
   int rc = check_eval_args(p, n_sample, phi, mem_kind);
   if (rc) return rc;
   if (!thetaMs_tr || !y || (p->desc.n_P > 0 && !thetaP)) PLAN_FAIL(p, HVI_EINVAL, "hvi_predict: NULL output");
+  if (p->gpbm) PLAN_FAIL(p, HVI_EINVAL, "hvi_predict: not available with a generic process model");
   if (zMs && p->desc.n_P > 0 && !zP) PLAN_FAIL(p, HVI_EINVAL, "hvi_predict: zP is NULL");
   return p->dtype == HVI_F32
              ? predict_t<float>(p, n_sample, phi, zP, zMs, seed, site_offset, mem_kind, thetaP, thetaMs_tr, y, entropy)
@@ -1285,6 +1351,7 @@ template <typename T>
 static int loss_gf_t(hvi_plan* p, const void* phi_gf, int mem_kind, double comps[3], void* grad) {
   const Cfg<T>& cfg = cfg_of<T>(p);
   if (p->wide) PLAN_FAIL(p, HVI_EINVAL, "loss_gf: not available with the wide applicator");
+  if (p->gpbm) PLAN_FAIL(p, HVI_EINVAL, "loss_gf: not available with a generic process model");
   if (!p->has_obs) PLAN_FAIL(p, HVI_ENODATA, "loss_gf: the registered batch has no observations");
   cudaStream_t s = p->stream;
   int rcj = join_user(p);

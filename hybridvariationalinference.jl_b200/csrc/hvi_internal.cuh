@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 #include "../../include/hvi_b200.h"
 
 namespace hvi {
@@ -182,6 +184,19 @@ cudaError_t launch_point_finalize(const Launch& L, const Cfg<T>& cfg, const T* p
 int point_max_rows(int sm_count);
 int point_row_len();
 int stream_max_rows(int sm_count);
+// generic process-based-model seam (hvi_generic.cu, hvi_pbm.cuh)
+struct GenericPbm;
+int generic_pbm_create(const char* spec, int dtype, int NP, int NM, int NO, int NX, bool want_mu, std::string& err, GenericPbm** out);
+int generic_pbm_compile_check(const char* spec, int dtype, int NP, int NM, int NO, int NX, std::string& err);
+void generic_pbm_destroy(GenericPbm* g);
+bool generic_pbm_has_penalty(const GenericPbm* g);
+template <typename T>
+cudaError_t launch_generic_stream(const Launch& L, GenericPbm* g, const Cfg<T>& cfg, const StreamArgs<T>& s, const T* xP,
+                                  const T* y_o, const T* y_unc, const double* fix, double* pen_partials, int* nrows_out,
+                                  int nrows_max);
+template <typename T>
+cudaError_t launch_preprocess_generic(const Launch& L, int64_t n, const T* y_o, const T* y_unc, double* part, int* nrows_out);
+cudaError_t launch_add_penalty(const Launch& L, const double* pen, int nrows, int M, int nphi, double* out);
 int mlp_bwd_max_blocks(int sm_count);
 bool stream_supported(int nP, int nM, int nO);
 bool mlp_supports_pbm(const hvi_desc* d);

@@ -142,7 +142,7 @@ class NegElboPlan:
             f = lambda a: None if a is None else np.asfortranarray(a, dtype=self.dt)
             args = tuple(map(f, (xM, xP, y_o, y_unc)))
             n_site = args[0].shape[1]
-            assert args[1].shape == (2 * self.prob.n_obs, n_site) and args[0].shape[0] == self.prob.n_covar
+            assert args[1].shape == (getattr(self, "n_x", 2 * self.prob.n_obs), n_site) and args[0].shape[0] == self.prob.n_covar
             if args[2] is not None:
                 assert args[2].shape == (self.prob.n_obs, n_site) and args[3].shape == args[2].shape
         self._keep = args
@@ -173,6 +173,18 @@ class NegElboPlan:
         if i_sites is not None:
             idx = np.ascontiguousarray(i_sites, dtype=np.int64)
             self._check(self.lib.hvi_plan_set_sites(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
+
+    # -- generic process-based model --------------------------------------------------------------
+    def set_pbm(self, pbm: str, n_x: Optional[int] = None, fix=()):
+        """Replace the DoubleMM process model of this plan (AbstractPBMApplicator, src/PBMApplicator.jl:26-32) by
+        "builtin:doubleMM", "builtin:mm1" or CUDA C++ source defining `struct UserPbm` (include/hvi_b200.h).  `n_x`:
+        driver rows per site (xP is then n_x × n_site), `fix`: the fixed parameters θFix.  Call set_data afterwards."""
+        fx = np.ascontiguousarray(fix, dtype=np.float64)
+        nx = 2 * self.prob.n_obs if n_x is None else int(n_x)
+        self._check(self.lib.hvi_plan_set_pbm(self._h, pbm.encode(), nx, fx.size,
+                                              fx.ctypes.data_as(C.POINTER(C.c_double)) if fx.size else None))
+        self.n_x = nx
+        self.n_site = 0
 
     # -- device-resident training set ------------------------------------------------------------
     def set_dataset(self, xM, xP, y_o=None, y_unc=None):
@@ -356,6 +368,15 @@ class NegElboPlan:
 
 
 # ---- functional spellings that read like the reference's -----------------------------------
+def pbm_compile_check(pbm: str, prob: HybridProblem, n_x: Optional[int] = None):
+    """NVRTC-compile a process model for `prob`'s sizes without a device; returns (ok, compiler message)."""
+    lib = A.load_library()
+    log = C.create_string_buffer(4096)
+    rc = lib.hvi_pbm_compile_check(pbm.encode(), A.HVI_F32 if prob.dtype == "f32" else A.HVI_F64, prob.n_P, prob.n_M,
+                                   prob.n_obs, 2 * prob.n_obs if n_x is None else int(n_x), log, 4096)
+    return rc == A.HVI_OK, log.value.decode(errors="replace")
+
+
 def neg_elbo_gtf_components(plan: NegElboPlan, ϕ, zP, zMs) -> NegElboComponents:
     """src/elbo.jl:46-88"""
     return plan.neg_elbo_withgradient(ϕ, zP, zMs, want_grad=False)[1]

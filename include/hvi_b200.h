@@ -169,6 +169,41 @@ int hvi_plan_select_batch(hvi_plan* plan, const int64_t* i_sites, int64_t n, int
  * later call; use_own != 0 switches back.  The new stream continues behind everything queued on the old one. */
 int hvi_plan_set_stream(hvi_plan* plan, void* cuda_stream, int use_own);
 
+/* ---- generic process-based model --------------------------------------------- */
+/* The reference's process model is any AbstractPBMApplicator callable f(θP, θMs_tr, xP) (src/PBMApplicator.jl:26-32;
+ * per site: PBMSiteApplicator, :122-195), differentiated by Zygote.  hvi_plan_set_pbm replaces the built-in DoubleMM
+ * kernel of this plan by a process model given as CUDA C++ source:
+ *
+ *     struct UserPbm {
+ *       template <class S, class T>
+ *       __device__ static void f(const S* thP, const S* thM, const T* fix, const T* x, S* y) {
+ *         for (int o = 0; o < HVI_NO; o++) y[o] = thP[0] + thM[0] * x[o] / (thM[1] + x[o]);
+ *       }
+ *     };
+ *
+ * thP / thM: the constrained parameters of one draw (n_P, n_M values in the problem's order), fix: the n_fix fixed
+ * parameters (θFix), x: the site's column of xP (n_x driver rows -- xP is then (n_x x n_site)), y: the n_obs
+ * predictions.  S is the working type or a forward-mode dual number over it: the library obtains dy/dθ by
+ * instantiating f with duals, so no adjoint is written by hand (arithmetic + - * /, hexp, hlog, hsqrt, htanh; literals
+ * as T(2)).  The macros HVI_NP, HVI_NM, HVI_NO, HVI_NX and the type HVI_T are defined.  An optional
+ * `static constexpr bool HAS_PENALTY = true;` with `template <class S, class T> __device__ static S penalty(thP, thM,
+ * fix, x, y)` adds mean_draws(Σ_sites penalty) as the loss_penalty component (floss_penalty, src/elbo.jl:153,282-286).
+ * The source is compiled for this plan's sizes by NVRTC (libnvrtc.so.12 of the CUDA toolkit, loaded on demand); a
+ * compiler error is returned as HVI_EINVAL with the log in hvi_last_error.
+ *   pbm = "doubleMM"           the hand-written DoubleMM kernel (default)
+ *   pbm = "builtin:doubleMM"   f_doubleMM through the generic seam (x = [S1; S2], n_x = 2 n_obs)
+ *   pbm = "builtin:mm1"        y_o = θP[0] + θM[0] x_o / (θM[1] + x_o), n_x = n_obs
+ *   otherwise                  source text defining `struct UserPbm`
+ * An observation is used iff y_o is not NaN (src/logden_normal.jl:34); a non-finite prediction at a used observation
+ * makes the result non-finite (HVI_ENONFINITE), as in the reference.  Registers no batch: call hvi_plan_set_data
+ * afterwards.  With a generic model the plan evaluates value + gradient (all hvi_neg_elbo_grad* and hvi_adam_* entry
+ * points, hvi_generate_zeta, hvi_apply_g); hvi_predict, hvi_loss_gf_grad, prefetch and the device-resident dataset
+ * stay DoubleMM-only. */
+int hvi_plan_set_pbm(hvi_plan* plan, const char* pbm, int32_t n_x, int32_t n_fix, const double* fix);
+/* The same NVRTC compilation without a plan or a device: HVI_OK, or HVI_EINVAL with the compiler's message in log. */
+int hvi_pbm_compile_check(const char* pbm, int32_t dtype, int32_t n_P, int32_t n_M, int32_t n_obs, int32_t n_x,
+                          char* log, int32_t log_len);
+
 /* MeanVarSep only: the 0-based indices (into 0..n_site_total) of the registered batch's sites -- the
  * `i_sites` argument of loss_elbo (src/HybridSolver.jl:312-322, src/elbo_sepvec.jl:23).  Host array of
  * length n_site; default after set_data is 0..n_site-1. */

@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field
-from typing import List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -188,6 +188,10 @@ class Spec:
     # (src/elbo_sepvec.jl:3-48), ϕq then holds logσ2_ζMs (nM × n_site_total) instead of the coefficients
     approx: str = "mean"
     n_site_total: int = 0
+    # generic process-based model f(θP, θMs_tr, xP) -> y (n_obs × nb) (AbstractPBMApplicator, src/PBMApplicator.jl:26-32);
+    # None: f_doubleMM_sites.  penalty(θP, θMs_tr, xP, y_pred) -> scalar: floss_penalty (src/elbo.jl:153,282-286)
+    pbm: Optional[Callable] = None
+    penalty: Optional[Callable] = None
 
     @property
     def n_phig(self):
@@ -406,12 +410,14 @@ def compute_priors_logdensity(spec: Spec, thP, thMs_tr):
 def neg_elbo_zeta_tf(spec: Spec, zsP, zsMs_tr, sigma, xP, y_ob, y_unc, dtype_name):
     """src/elbo.jl:132-201"""
     M = zsMs_tr.shape[2]
-    nLy = nlp = nlj = torch.zeros((), dtype=F64)
+    nLy = nlp = nlj = pen = torch.zeros((), dtype=F64)
     for m in range(M):
         zP_m = zsP[:, m]
         thP, thM, lj = transform_and_logjac_zeta(spec, zP_m, zsMs_tr[:, :, m], dtype_name)
-        y_pred = f_doubleMM_sites(spec, thP, thM, xP)
+        y_pred = spec.pbm(thP, thM, xP) if spec.pbm is not None else f_doubleMM_sites(spec, thP, thM, xP)
         nLy = nLy + neg_logden_indep_normal(y_ob, y_pred, y_unc)
+        if spec.penalty is not None:
+            pen = pen + spec.penalty(thP, thM, xP, y_pred)
         nlp = nlp + compute_priors_logdensity(spec, thP, thM)
         nlj = nlj - lj
     nLy, nlp, nlj = nLy / M, nlp / M, nlj / M
@@ -419,7 +425,7 @@ def neg_elbo_zeta_tf(spec: Spec, zsP, zsMs_tr, sigma, xP, y_ob, y_unc, dtype_nam
     n_theta = spec.nP + zsMs_tr.shape[0] * zsMs_tr.shape[1]
     assert sigma.numel() == n_theta
     ent = entropy_MvNormal(n_theta, logdetS)
-    return dict(nLjoint=nLy + nlp + nlj, entropy_zeta=ent, loss_penalty=torch.zeros((), dtype=F64),
+    return dict(nLjoint=nLy + nlp + nlj, entropy_zeta=ent, loss_penalty=pen / M,
                 nLy=nLy, neg_log_prior=nlp, neg_log_jac=nlj)
 
 
