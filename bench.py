@@ -231,7 +231,7 @@ def dominant_roofline(args, prob, nb, M, kt, peaks, sampler, local):
 
 
 # FP32-pipe slots per site·draw of k_stream's hot loop (DoubleMM, 8 observations): packed instructions count twice
-FP32_SLOTS_PER_UNIT = 141
+FP32_SLOTS_PER_UNIT = 149
 
 
 def bind_to_gpu_numa_node(gpu):

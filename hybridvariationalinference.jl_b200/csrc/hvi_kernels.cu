@@ -34,8 +34,6 @@ __device__ __forceinline__ float exp_t(float x) {
   return r;
 }
 __device__ __forceinline__ double exp_t(double x) { return exp(x); }
-__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
-__device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
 __device__ __forceinline__ float log_t(float x) { return logf(x); }
 __device__ __forceinline__ double log_t(double x) { return log(x); }
 __device__ __forceinline__ float tanh_t(float x) { return tanhf(x); }
@@ -893,9 +891,7 @@ __host__ __device__ constexpr bool all_exp_ln() {
 template <typename T, int NP, int NM, int NO>
 struct SiteState {
   static constexpr int NOP = (NO + 1) / 2;   // observation pairs
-  // s = √w (w = mask·exp(−y_unc)): the residual is carried pre-scaled, res' = √w·(y − y_o), so that w·res² = res'² and
-  // w·res·ab = res'·(√w·ab) need no extra multiply.  S12 = √w·S1·S2, c = −√w·y_o
-  typename PairT<T>::type S1[NOP], S2[NOP], S12[NOP], c[NOP], s[NOP];
+  typename PairT<T>::type S1[NOP], S2[NOP], S12[NOP], nyo[NOP], w[NOP];   // nyo = −y_o
   typename PairT<T>::type nly2;  // Σ w·res² over the draws, two lanes
   T mu[NM];
   T sU[tri(NM)];                 // σ[k]·U[j,k]
@@ -908,8 +904,8 @@ struct SiteState {
 // f_doubleMM + logden_normal + adjoint w.r.t. (r0, r1, K1, K2), all observations of one site
 // and one draw:  y = r0 + r1·S1/(K1+S1)·S2/(K2+S2)   (src/DoubleMM/f_doubleMM.jl:137)
 // accumulates Σ w·res² into st.nly2; pbar = (Σ dy, Σ dy·ab, −r1 Σ dy·ab/d1, −r1 Σ dy·ab/d2),
-// dy = w·res.  With the residual pre-scaled by √w: 13 FP32 operations + 1 reciprocal per observation, two
-// observations per instruction.
+// dy = w·res.  14 FP32 operations + 1 reciprocal per observation, two observations per
+// instruction.
 template <typename T, int NP, int NM, int NO>
 __device__ __forceinline__ void obs_loop(SiteState<T, NP, NM, NO>& st, const T (&par)[4], T (&pbar)[4]) {
   using P = typename PairT<T>::type;
@@ -921,11 +917,13 @@ __device__ __forceinline__ void obs_loop(SiteState<T, NP, NM, NO>& st, const T (
     const P d1 = padd(k1, st.S1[o]), d2 = padd(k2, st.S2[o]);
     const P p = pmul(d1, d2);
     const P rp = mk2(rcp_fast(p.x), rcp_fast(p.y));
-    const P abw = pmul(st.S12[o], rp);                         // √w·ab
-    const P res = pfma(r1, abw, pfma(st.s[o], r0, st.c[o]));   // √w·(y − y_o)
-    st.nly2 = pfma(res, res, st.nly2);
-    g0 = pfma(st.s[o], res, g0);                               // Σ w·res
-    const P t = pmul(res, abw);                                // w·res·ab
+    const P ab = pmul(st.S12[o], rp);
+    const P y = pfma(r1, ab, r0);
+    const P res = padd(y, st.nyo[o]);
+    const P dy = pmul(res, st.w[o]);
+    st.nly2 = pfma(res, dy, st.nly2);
+    g0 = padd(g0, dy);
+    const P t = pmul(dy, ab);
     g1 = padd(g1, t);
     const P u = pmul(t, rp);
     gA = pfma(u, d2, gA);
@@ -1080,9 +1078,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
         const int o0 = 2 * o, o1 = two ? 2 * o + 1 : 2 * o;
         st.S1[o] = mk2(r[(0 * NO + o0) * 32], r[(0 * NO + o1) * 32]);
         st.S2[o] = mk2(r[(1 * NO + o0) * 32], r[(1 * NO + o1) * 32]);
-        st.s[o] = mk2(sqrt_t(r[(3 * NO + o0) * 32]), two ? sqrt_t(r[(3 * NO + o1) * 32]) : T(0));
-        st.c[o] = pmul(st.s[o], mk2(-r[(2 * NO + o0) * 32], -r[(2 * NO + o1) * 32]));
-        st.S12[o] = pmul(pmul(st.S1[o], st.S2[o]), st.s[o]);
+        st.nyo[o] = mk2(-r[(2 * NO + o0) * 32], -r[(2 * NO + o1) * 32]);
+        st.w[o] = mk2(r[(3 * NO + o0) * 32], two ? r[(3 * NO + o1) * 32] : T(0));
+        st.S12[o] = pmul(st.S1[o], st.S2[o]);
       }
     }
     T ls[NM], sig[NM];
