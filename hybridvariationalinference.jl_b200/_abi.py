@@ -88,6 +88,7 @@ SYMBOLS = [
     ("hvi_adam_apply_dev", _INT, [_P, _P, _P]),
     ("hvi_adam_run_minibatches", _INT, [_P, _I32, _I32, _U64, _I64, _I64, _DP]),
     ("hvi_plan_use_graphs", _INT, [_P, _INT]),
+    ("hvi_plan_use_fused", _INT, [_P, _INT]),
     ("hvi_adam_phi_dev", _INT, [_P, C.POINTER(_P)]),
     ("hvi_adam_get_phi", _INT, [_P, _P]),
     ("hvi_generate_zeta", _INT, [_P, _I32, _P, _P, _P, _INT, _P, _P, _P]),

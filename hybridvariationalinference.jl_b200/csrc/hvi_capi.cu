@@ -86,6 +86,7 @@ struct hvi_plan {
   unsigned long long* d_ctr;
   // one optimiser iteration captured as a CUDA graph (replayed by hvi_adam_run)
   cudaGraphExec_t adam_graph; GraphKey graph_key; int graph_valid, graph_nodes, use_graphs;
+  int use_fused;   // small batches: one launch per evaluation / optimiser iteration (k_small_iter)
   // optional per-kernel timing (CUDA events on the launching stream)
   int profiling;
   cudaEvent_t ev[8];
@@ -261,7 +262,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   p->nb = 0; p->launches = 0;
   p->d_ls = nullptr; p->cap_ls = 0;
   p->d_phi_opt = nullptr; p->d_adam_m = p->d_adam_v = p->d_trace = nullptr; p->cap_trace = 0;
-  p->d_ctr = nullptr; p->adam_graph = nullptr; p->graph_valid = 0; p->graph_nodes = 0; p->use_graphs = 1;
+  p->d_ctr = nullptr; p->adam_graph = nullptr; p->graph_valid = 0; p->graph_nodes = 0; p->use_graphs = 1; p->use_fused = 1;
   p->own_stream = nullptr; p->ev_user = p->ev_plan = nullptr; p->user_pending = 0;
   p->d_bconst = nullptr; p->h_bconst = nullptr;
   p->ds_n = 0; p->ds_has_obs = 0; p->ds_xM = p->ds_xP = p->ds_yo = p->ds_yu = nullptr; p->d_idx = nullptr; p->cap_idx = 0; p->n_isites = 0;
@@ -724,10 +725,9 @@ static int set_dataset_t(hvi_plan* p, int64_t N, const void* xM, const void* xP,
 // MeanVarSep reads its per-site parameters through d_isites: the gather kernel writes the selected sites there
 static int select_sites(hvi_plan* p, int64_t n);
 
+// buffers and bookkeeping of a minibatch of n sites of the device-resident dataset (no kernel)
 template <typename T>
-static int select_t(hvi_plan* p, const int64_t* idx_dev, int64_t first, int64_t n,
-                    const unsigned long long* ctr = nullptr, int64_t n_batches = 1) {
-  const int nO = p->desc.n_obs, nC = p->desc.n_covar;
+static int select_prepare(hvi_plan* p, int64_t n) {
   if (p->nb_next > 0) { CU(p, cudaStreamSynchronize(p->copy_stream)); p->nb_next = 0; }
   if (n != p->nb || p->cap_cur < n) {
     CU(p, cudaStreamSynchronize(p->stream));   // buffers of the old size may still be in use
@@ -737,6 +737,15 @@ static int select_t(hvi_plan* p, const int64_t* idx_dev, int64_t first, int64_t 
   int rc = select_sites(p, n);
   if (rc) return rc;
   p->has_obs = p->ds_has_obs;
+  return HVI_OK;
+}
+
+template <typename T>
+static int select_t(hvi_plan* p, const int64_t* idx_dev, int64_t first, int64_t n,
+                    const unsigned long long* ctr = nullptr, int64_t n_batches = 1) {
+  const int nO = p->desc.n_obs, nC = p->desc.n_covar;
+  int rc = select_prepare<T>(p, n);
+  if (rc) return rc;
   Launch L{p->stream, p->sm_count, &p->launches};
   int nrows = 0;
   CU(p, launch_gather_preprocess<T>(L, nC, nO, n, idx_dev, first, (const T*)p->ds_xM, (const T*)p->ds_xP,
@@ -943,6 +952,46 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   return HVI_OK;
 }
 
+// small batches with device draws: the whole evaluation (and optionally the minibatch gather before it and the Adam update
+// after it) as ONE launch of one block
+template <typename T>
+static bool fused_ok(const hvi_plan* p, int64_t nb, int M) {
+  return p->use_fused && !p->wide && !p->gpbm && !p->profiling && nb <= 1024 && nb * (int64_t)M <= 16384 &&
+         small_iter_supported<T>(cfg_of<T>(const_cast<hvi_plan*>(p)), nb, M);
+}
+
+template <typename T>
+static int enqueue_fused(hvi_plan* p, int M, T* phi, double* out, T* grad_T, cudaStream_t s, uint64_t seed, int64_t site_offset,
+                         bool adam, int64_t batch_size, int64_t first_batch) {
+  const Cfg<T>& cfg = cfg_of<T>(p);
+  int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)(sizeof(T) * pdraw_elems(cfg.nP, M)));
+  if (rc) return rc;
+  rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)sizeof(T) * M * (cfg.nP > 0 ? cfg.nP : 1));
+  if (rc) return rc;
+  SmallArgs<T> a;
+  memset(&a, 0, sizeof a);
+  T* pdraw = (T*)p->d_pdraw;
+  a.st.rec = (const T*)p->d_rec; a.st.mu = (const T*)p->d_mu; a.st.zMs = nullptr;
+  a.st.pd = pdraw + (((size_t)4 * (cfg.nP > 0 ? cfg.nP : 1) * M + 3) & ~(size_t)3);
+  a.st.ec = (const EvalConsts<T>*)p->d_ec; a.st.mubar = (T*)p->d_mubar; a.st.partials = p->d_part_stream;
+  a.st.nb = p->nb; a.st.M = M; a.st.rng = 1; a.st.seed = seed; a.st.col_offset = site_offset * cfg.nM;
+  a.st.phi = phi; a.st.i_sites = nullptr; a.st.out = out; a.st.grad_T = grad_T;
+  a.phi = phi; a.zP = (T*)p->d_zP; a.pdraw = pdraw; a.xM = (const T*)p->d_xM;
+  a.part_mlp = p->d_part_mlp; a.red = p->d_red; a.out = out; a.grad_T = grad_T; a.bconst = p->d_bconst;
+  if (batch_size > 0) {
+    a.ds_xM = (const T*)p->ds_xM; a.ds_xP = (const T*)p->ds_xP; a.ds_yo = (const T*)p->ds_yo; a.ds_yu = (const T*)p->ds_yu;
+    a.xM_b = (T*)p->d_xM; a.xP_b = (T*)p->d_xP; a.rec_w = (T*)p->d_rec;
+    a.first = first_batch; a.n_batches = p->ds_n / batch_size;
+  }
+  if (adam) {
+    a.adam_m = p->d_adam_m; a.adam_v = p->d_adam_v; a.trace = p->d_trace;
+    a.eta = p->adam_eta; a.b1 = p->adam_b1; a.b2 = p->adam_b2; a.eps = p->adam_eps; a.ctr = p->d_ctr;
+  }
+  Launch L{s, p->sm_count, &p->launches};
+  CU(p, launch_small_iter<T>(L, cfg, a));
+  return HVI_OK;
+}
+
 template <typename T>
 static int eval_sync_t(hvi_plan* p, int M, const void* phi, const void* zP, const void* zMs, bool use_rng, uint64_t seed,
                        int64_t site_offset, int mem_kind, double comps[6], double* nL, void* grad) {
@@ -958,6 +1007,7 @@ static int eval_sync_t(hvi_plan* p, int M, const void* phi, const void* zP, cons
   }
   const int64_t nzP = (int64_t)M * (cfg.nP > 0 ? cfg.nP : 1), nzM = (int64_t)M * cfg.nM * p->nb;
   const T *dzP = (const T*)zP, *dzM = (const T*)zMs;
+  const bool fused = use_rng && fused_ok<T>(p, p->nb, M);   // small batch, device draws: one launch
   if (use_rng || mem_kind == HVI_MEM_HOST) {
     int rc = ensure(p, &p->d_zP, &p->cap_zP, (int64_t)sizeof(T) * nzP);
     if (rc) return rc;
@@ -965,7 +1015,7 @@ static int eval_sync_t(hvi_plan* p, int M, const void* phi, const void* zP, cons
       // global-block draws: columns keyed far above any site column; the site draws are generated
       // inside the streaming kernel from the same (seed, column, draw) keys
       Launch L{s, p->sm_count, &p->launches};
-      CU(p, launch_gen_normal<T>(L, (T*)p->d_zP, cfg.nP, M, seed, (int64_t)1 << 62));
+      if (!fused) CU(p, launch_gen_normal<T>(L, (T*)p->d_zP, cfg.nP, M, seed, (int64_t)1 << 62));
       dzM = nullptr;
     } else {
       rc = ensure(p, &p->d_zMs, &p->cap_zMs, (int64_t)sizeof(T) * nzM);
@@ -977,8 +1027,10 @@ static int eval_sync_t(hvi_plan* p, int M, const void* phi, const void* zP, cons
     dzP = (const T*)p->d_zP;
   }
   const bool want_grad = grad != nullptr;
-  int rc = enqueue_eval<T>(p, M, dphi, dzP, dzM, p->d_out, want_grad ? (T*)p->d_grad : nullptr, s, use_rng, seed,
-                           site_offset);
+  int rc = fused ? enqueue_fused<T>(p, M, const_cast<T*>(dphi), p->d_out, want_grad ? (T*)p->d_grad : nullptr, s, seed,
+                                    site_offset, false, 0, 0)
+                 : enqueue_eval<T>(p, M, dphi, dzP, dzM, p->d_out, want_grad ? (T*)p->d_grad : nullptr, s, use_rng, seed,
+                                   site_offset);
   if (rc) return rc;
   CU(p, cudaMemcpyAsync(p->h_out + nphi, p->d_out + nphi, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
   if (p->anomalies < 0) CU(p, cudaMemcpyAsync(p->h_bconst, p->d_bconst, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
@@ -1494,6 +1546,14 @@ template <typename T>
 static int adam_iteration(hvi_plan* p, int M, int64_t site_offset, int64_t batch_size, int64_t first_batch, cudaStream_t s) {
   const Cfg<T>& cfg = cfg_of<T>(p);
   Launch L{s, p->sm_count, &p->launches};
+  if (fused_ok<T>(p, batch_size > 0 ? batch_size : p->nb, M)) {   // the reference's operating point: one launch per iteration
+    if (batch_size > 0) {
+      int rc = select_prepare<T>(p, batch_size);
+      if (rc) return rc;
+      p->anomalies = -1;
+    }
+    return enqueue_fused<T>(p, M, (T*)p->d_phi_opt, p->d_out, nullptr, s, 0, site_offset, true, batch_size, first_batch);
+  }
   if (batch_size > 0) {
     const int64_t n_batches = p->ds_n / batch_size;   // partial = false (src/AbstractHybridProblem.jl:206-207)
     int rc = select_t<T>(p, nullptr, first_batch, batch_size, p->d_ctr, n_batches);
@@ -1517,7 +1577,7 @@ static void graph_key(const hvi_plan* p, int M, int64_t site_offset, int64_t bat
   static_assert(sizeof(ptrs) / sizeof(ptrs[0]) <= sizeof(k->ptrs) / sizeof(k->ptrs[0]), "GraphKey too small");
   for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) k->ptrs[i] = ptrs[i];
   k->v[0] = p->nb; k->v[1] = M; k->v[2] = site_offset; k->v[3] = batch_size; k->v[4] = first_batch; k->v[5] = p->ds_n;
-  k->v[6] = p->has_obs;
+  k->v[6] = p->has_obs; k->v[7] = p->use_fused;
 }
 
 template <typename T>
@@ -1613,6 +1673,13 @@ extern "C" int hvi_adam_run_minibatches(hvi_plan* p, int32_t n_iter, int32_t n_M
   CU(p, cudaSetDevice(p->desc.device));
   return p->dtype == HVI_F32 ? adam_run_t<float>(p, n_iter, n_MC, seed0, 0, batch_size, first_batch, nL_trace)
                              : adam_run_t<double>(p, n_iter, n_MC, seed0, 0, batch_size, first_batch, nL_trace);
+}
+
+extern "C" int hvi_plan_use_fused(hvi_plan* p, int on) {
+  if (!p) return HVI_EINVAL;
+  p->use_fused = on ? 1 : 0;
+  p->graph_valid = 0;
+  return HVI_OK;
 }
 
 extern "C" int hvi_plan_use_graphs(hvi_plan* p, int on) {

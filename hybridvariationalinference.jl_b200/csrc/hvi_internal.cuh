@@ -82,6 +82,28 @@ struct StreamArgs {
   int staged;        // 1: M % (16/sizeof(T)) == 0 and zMs 16-byte aligned → cp.async staging
 };
 
+// arguments of the single-launch small-batch iteration (k_small_iter)
+template <typename T>
+struct SmallArgs {
+  StreamArgs<T> st;     // as for k_stream: rec, mu, pd, ec, mubar, partials, nb, M, seed, col_offset
+  T* phi;               // ϕ on the device (updated in place by the Adam phase)
+  T* zP;                // [n_P][M] draws of the global block
+  T* pdraw;
+  const T* xM;
+  double *part_mlp, *red, *out;
+  T* grad_T;
+  double* bconst;       // batch constants {½Σy_unc, anomalies}: read, and written by the gather phase
+  // minibatch of the device-resident dataset (ds_xM != NULL)
+  const T *ds_xM, *ds_xP, *ds_yo, *ds_yu;
+  T *xM_b, *xP_b, *rec_w;
+  int64_t first, n_batches;
+  int64_t* isites_out;
+  // Adam phase (adam_m != NULL) and the device-side iteration counters (k_adam)
+  double *adam_m, *adam_v, *trace;
+  double eta, b1, b2, eps;
+  unsigned long long* ctr;
+};
+
 struct Launch {
   cudaStream_t stream;
   int sm_count;
@@ -181,6 +203,10 @@ cudaError_t launch_point_finalize(const Launch& L, const Cfg<T>& cfg, const T* p
                                   const double* part_mlp, int nblk, const double* part_x, const double* batch_consts,
                                   double* out,
                                   T* grad_T);
+template <typename T>
+bool small_iter_supported(const Cfg<T>& cfg, int64_t nb, int M);
+template <typename T>
+cudaError_t launch_small_iter(const Launch& L, const Cfg<T>& cfg, SmallArgs<T> a);
 int point_max_rows(int sm_count);
 int point_row_len();
 int stream_max_rows(int sm_count);

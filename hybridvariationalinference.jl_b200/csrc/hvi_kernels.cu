@@ -171,19 +171,19 @@ __global__ void __launch_bounds__(256) k_preprocess(int nO, int64_t nb, const T*
 // records exactly as k_preprocess does.  A site's columns are 4·nC … 8·nO contiguous bytes: every lane reads whole
 // sectors of its own site; the record stores are coalesced.
 template <typename T>
-__global__ void __launch_bounds__(256) k_gather_preprocess(int nC, int nO, int64_t nb, const int64_t* __restrict__ idx,
-                                                           int64_t first, const T* __restrict__ ds_xM,
-                                                           const T* __restrict__ ds_xP, const T* __restrict__ ds_yo,
-                                                           const T* __restrict__ ds_yu, T* __restrict__ xM_b,
-                                                           T* __restrict__ xP_b, T* __restrict__ rec,
-                                                           double* __restrict__ part,
-                                                           const unsigned long long* __restrict__ ctr,
-                                                           int64_t n_batches, int64_t* __restrict__ isites_out) {
+__device__ __forceinline__ void gather_preprocess_body(int nC, int nO, int64_t nb, const int64_t* __restrict__ idx,
+                                                       int64_t first, const T* __restrict__ ds_xM,
+                                                       const T* __restrict__ ds_xP, const T* __restrict__ ds_yo,
+                                                       const T* __restrict__ ds_yu, T* __restrict__ xM_b,
+                                                       T* __restrict__ xP_b, T* __restrict__ rec,
+                                                       double* __restrict__ part,
+                                                       const unsigned long long* __restrict__ ctr,
+                                                       int64_t n_batches, int64_t* __restrict__ isites_out, int bid, int nblk) {
   // optimiser loops replayed as CUDA graphs: the minibatch is chosen by the device-side iteration counter ctr[1]
   if (ctr) first = (first + (int64_t)(ctr[1] % (unsigned long long)n_batches)) % n_batches * nb;
   const int lane = threadIdx.x & 31;
-  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t gw = ((int64_t)bid * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)nblk * blockDim.x) >> 5;
   const int64_t ntiles = (nb + 31) / 32;
   double cst = 0.0, anomalies = 0.0;
   for (int64_t tile = gw; tile < ntiles; tile += nw) {
@@ -216,6 +216,19 @@ __global__ void __launch_bounds__(256) k_gather_preprocess(int nC, int nO, int64
   cst = warp_sum(cst);
   anomalies = warp_sum(anomalies);
   if (lane == 0) { part[2 * gw] = cst; part[2 * gw + 1] = anomalies; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_preprocess(int nC, int nO, int64_t nb, const int64_t* __restrict__ idx,
+                                                           int64_t first, const T* __restrict__ ds_xM,
+                                                           const T* __restrict__ ds_xP, const T* __restrict__ ds_yo,
+                                                           const T* __restrict__ ds_yu, T* __restrict__ xM_b,
+                                                           T* __restrict__ xP_b, T* __restrict__ rec,
+                                                           double* __restrict__ part,
+                                                           const unsigned long long* __restrict__ ctr,
+                                                           int64_t n_batches, int64_t* __restrict__ isites_out) {
+  gather_preprocess_body<T>(nC, nO, nb, idx, first, ds_xM, ds_xP, ds_yo, ds_yu, xM_b, xP_b, rec, part, ctr, n_batches,
+                            isites_out, blockIdx.x, gridDim.x);
 }
 
 // the two constants of a registered batch, summed in a fixed order (run-to-run bit-identical), left on the device so
@@ -256,8 +269,8 @@ __device__ __noinline__ void build_U(int n, const int* blk_start, const int* rho
 }
 
 template <typename T>
-__global__ void k_prologue(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi, const T* __restrict__ zP,
-                           int M, EvalConsts<T>* __restrict__ ec, T* __restrict__ pdraw) {
+__device__ __forceinline__ void prologue_body(const Cfg<T>& cfg, const T* __restrict__ phi, const T* __restrict__ zP,
+                                              int M, EvalConsts<T>* __restrict__ ec, T* __restrict__ pdraw) {
   __shared__ EvalConsts<T> s;
   const int nP = cfg.nP, nM = cfg.nM;
   if (threadIdx.x == 0) {
@@ -290,6 +303,12 @@ __global__ void k_prologue(const __grid_constant__ Cfg<T> cfg, const T* __restri
   }
 }
 
+template <typename T>
+__global__ void k_prologue(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi, const T* __restrict__ zP,
+                           int M, EvalConsts<T>* __restrict__ ec, T* __restrict__ pdraw) {
+  prologue_body<T>(cfg, phi, zP, M, ec, pdraw);
+}
+
 // ---------------------------------------------------------------------------------------
 // g forward, CUDA-core version for narrow networks: one thread per site, weights and the
 // activation column of every thread in shared memory ([neuron][thread], conflict-free).
@@ -315,20 +334,20 @@ __device__ __forceinline__ void mlp_forward_block(const Cfg<T>& cfg, const T* __
   }
 }
 
+// body: any block of >= MLP_BS threads (the first MLP_BS own the sites of a tile); (bid, nblk) = the block's place in the grid
 template <typename T>
-__global__ void __launch_bounds__(MLP_BS) k_mlp_fwd(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi,
-                                                    const T* __restrict__ xM, int64_t nb, T* __restrict__ mu) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void mlp_fwd_body(const Cfg<T>& cfg, const T* __restrict__ phi, const T* __restrict__ xM,
+                                             int64_t nb, T* __restrict__ mu, unsigned char* smem_raw, int bid, int nblk) {
   T* sW = reinterpret_cast<T*>(smem_raw);
   T* acts = sW + ((cfg.nphig + 3) & ~3);
   const int t = threadIdx.x;
-  for (int e = t; e < cfg.nphig; e += MLP_BS) sW[e] = phi[e];
+  for (int e = t; e < cfg.nphig; e += blockDim.x) sW[e] = phi[e];
   __syncthreads();
   const int64_t ntiles = (nb + MLP_BS - 1) / MLP_BS;
   const int out_row = cfg.sum_width - cfg.l_out[cfg.nL - 1];
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int64_t tile = bid; tile < ntiles; tile += nblk) {
     const int64_t site = tile * MLP_BS + t;
-    if (site < nb) {
+    if (t < MLP_BS && site < nb) {
       for (int i = 0; i < cfg.nC; i++) acts[i * MLP_BS + t] = xM[site * cfg.nC + i];
       for (int c = 0; c < cfg.npc; c++) acts[(cfg.nC + c) * MLP_BS + t] = phi[cfg.o_muP + cfg.pbm_covar_idx[c]];
       mlp_forward_block<T>(cfg, sW, acts, t);
@@ -341,39 +360,47 @@ __global__ void __launch_bounds__(MLP_BS) k_mlp_fwd(const __grid_constant__ Cfg<
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(MLP_BS) k_mlp_fwd(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi,
+                                                    const T* __restrict__ xM, int64_t nb, T* __restrict__ mu) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  mlp_fwd_body<T>(cfg, phi, xM, nb, mu, smem_raw, blockIdx.x, gridDim.x);
+}
+
 // ---------------------------------------------------------------------------------------
 // g backward: recompute the forward per tile of 128 sites, back-propagate δ, then form the
 // weight gradient as (δ stack)·(activation stack)ᵀ over the tile with each thread owning
 // fixed gradient entries (deterministic; no atomics).  Per-block double partial sums.
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(MLP_BS) k_mlp_bwd(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi,
-                                                    const T* __restrict__ xM, const T* __restrict__ mubar, int64_t nb,
-                                                    double* __restrict__ part) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void mlp_bwd_body(const Cfg<T>& cfg, const T* __restrict__ phi, const T* __restrict__ xM,
+                                             const T* __restrict__ mubar, int64_t nb, double* __restrict__ part,
+                                             unsigned char* smem_raw, int bid, int nblk) {
+  const int NT = blockDim.x;
   double* gacc = reinterpret_cast<double*>(smem_raw);                 // [nphig]
   int2* tab = reinterpret_cast<int2*>(gacc + cfg.nphig);              // [nphig] (delta row, act row | -1)
   T* sW = reinterpret_cast<T*>(tab + cfg.nphig);                      // [nphig]
   T* acts = sW + ((cfg.nphig + 3) & ~3);                              // [sum_width][BS]
   T* dl = acts + (size_t)cfg.sum_width * MLP_BS;                      // [sum_out][BS]
   const int t = threadIdx.x;
-  for (int e = t; e < cfg.nphig; e += MLP_BS) { sW[e] = phi[e]; gacc[e] = 0.0; }
+  for (int e = t; e < cfg.nphig; e += NT) { sW[e] = phi[e]; gacc[e] = 0.0; }
   {  // gradient entry e ↔ (δ row, activation row)
     int row_in = 0, drow = 0;
     for (int l = 0; l < cfg.nL; l++) {
       const int ni = cfg.l_in[l], no = cfg.l_out[l];
-      for (int e = t; e < ni * no; e += MLP_BS) tab[cfg.woff[l] + e] = make_int2(drow + e % no, row_in + e / no);
+      for (int e = t; e < ni * no; e += NT) tab[cfg.woff[l] + e] = make_int2(drow + e % no, row_in + e / no);
       if (cfg.l_bias[l])
-        for (int e = t; e < no; e += MLP_BS) tab[cfg.boff[l] + e] = make_int2(drow + e, -1);
+        for (int e = t; e < no; e += NT) tab[cfg.boff[l] + e] = make_int2(drow + e, -1);
       row_in += ni; drow += no;
     }
   }
   __syncthreads();
   const int64_t ntiles = (nb + MLP_BS - 1) / MLP_BS;
   const int out_row = cfg.sum_width - cfg.l_out[cfg.nL - 1];
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int64_t tile = bid; tile < ntiles; tile += nblk) {
     const int64_t site = tile * MLP_BS + t;
     const bool active = site < nb;
+    if (t < MLP_BS) {
     // forward
     for (int i = 0; i < cfg.nC; i++) acts[i * MLP_BS + t] = active ? xM[site * cfg.nC + i] : T(0);
     for (int c = 0; c < cfg.npc; c++) acts[(cfg.nC + c) * MLP_BS + t] = phi[cfg.o_muP + cfg.pbm_covar_idx[c]];
@@ -405,10 +432,11 @@ __global__ void __launch_bounds__(MLP_BS) k_mlp_bwd(const __grid_constant__ Cfg<
       }
       row_out = row_in; drow = drow_prev;
     }
+    }
     __syncthreads();
     // weight gradient: entry e owned by thread e % BS; site index rotated per thread so that the
     // 32 lanes of a warp hit 32 different banks
-    for (int e = t; e < cfg.nphig; e += MLP_BS) {
+    for (int e = t; e < cfg.nphig; e += NT) {
       const int2 rc = tab[e];
       const T* dr = dl + (size_t)rc.x * MLP_BS;
       T acc = T(0);
@@ -422,7 +450,15 @@ __global__ void __launch_bounds__(MLP_BS) k_mlp_bwd(const __grid_constant__ Cfg<
     }
     __syncthreads();
   }
-  for (int e = t; e < cfg.nphig; e += MLP_BS) part[(size_t)blockIdx.x * cfg.nphig + e] = gacc[e];
+  for (int e = t; e < cfg.nphig; e += NT) part[(size_t)bid * cfg.nphig + e] = gacc[e];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MLP_BS) k_mlp_bwd(const __grid_constant__ Cfg<T> cfg, const T* __restrict__ phi,
+                                                    const T* __restrict__ xM, const T* __restrict__ mubar, int64_t nb,
+                                                    double* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  mlp_bwd_body<T>(cfg, phi, xM, mubar, nb, part, smem_raw, blockIdx.x, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1027,16 +1063,15 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, 
 
 constexpr int STREAM_THREADS_MAX = 384;
 
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool RNG>
-__global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_constant__ Cfg<T> cfg,
-                                                                 const __grid_constant__ StreamArgs<T> a) {
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, bool PBM, bool RNG>
+__device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<T>& a, unsigned char* smem_raw, int bid,
+                                            int nblk) {
   constexpr int CH = 16 / sizeof(T);  // elements per 16-byte chunk
   constexpr int MC = 8 * CH;          // draws per stage (one 128-byte row)
   constexpr int NUM = tri(NM), NUP = tri(NP);
   constexpr int NACC = nacc(NP, NM);
   constexpr int NWARP = STREAM_THREADS / 32;
   constexpr int PD = pd_stride(NP);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* ztile = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (32 * NM * MC);
   double* wacc = reinterpret_cast<double*>(smem_raw + (size_t)NWARP * 32 * NM * MC * sizeof(T)) + warp * NACC;
@@ -1065,7 +1100,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
   const bool staged = a.staged != 0;
   const uint64_t seed = (RNG && a.seed_dev) ? (uint64_t)*a.seed_dev : a.seed;
   const int64_t ntiles = (a.nb + 31) / 32;
-  for (int64_t tile = (int64_t)blockIdx.x * NWARP + warp; tile < ntiles; tile += (int64_t)gridDim.x * NWARP) {
+  for (int64_t tile = (int64_t)bid * NWARP + warp; tile < ntiles; tile += (int64_t)nblk * NWARP) {
     const int64_t site = tile * 32 + lane;
     const bool active = site < a.nb;
     const int64_t isite = (cfg.sepvar && active && a.i_sites) ? a.i_sites[site] : site;   // global site index
@@ -1260,9 +1295,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_co
     for (int i = threadIdx.x; i < NACC; i += STREAM_THREADS) {
       double s = 0.0;
       for (int w = 0; w < NWARP; w++) s += w0[w * NACC + i];
-      a.partials[(size_t)blockIdx.x * NACC + i] = s;
+      a.partials[(size_t)bid * NACC + i] = s;
     }
   }
+}
+
+
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool RNG>
+__global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_constant__ Cfg<T> cfg,
+                                                                 const __grid_constant__ StreamArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  stream_body<TR, T, NP, NM, NO, STREAM_THREADS, PBM, RNG>(cfg, a, smem_raw, blockIdx.x, gridDim.x);
 }
 
 
@@ -1354,15 +1397,17 @@ __device__ __forceinline__ double strided_sum8(const double* __restrict__ col, i
   return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
+// body for one (virtual) block `bid` of `ngrid` blocks of RED_THREADS threads; ends with a barrier so that a caller can
+// loop over the virtual blocks
 template <typename T>
-__global__ void __launch_bounds__(RED_THREADS) k_reduce(int nphig, const double* __restrict__ part_mlp, int nblk,
-                                                        const double* __restrict__ part_stream, int nrows, int NACC,
-                                                        double* __restrict__ out, T* __restrict__ grad_T,
-                                                        double* __restrict__ red) {
+__device__ __forceinline__ void reduce_body(int nphig, const double* __restrict__ part_mlp, int nblk,
+                                            const double* __restrict__ part_stream, int nrows, int NACC,
+                                            double* __restrict__ out, T* __restrict__ grad_T, double* __restrict__ red,
+                                            int bid, int ngrid) {
   __shared__ double sm[8][33];
   const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-  if ((int)blockIdx.x < (int)gridDim.x - 1) {
-    const int e = blockIdx.x * 32 + c;
+  if (bid < ngrid - 1) {
+    const int e = bid * 32 + c;
     double s0 = 0, s1 = 0;
     if (e < nphig) {
       s0 = strided_sum8(part_mlp + e, nphig, g, nblk);
@@ -1378,7 +1423,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce(int nphig, const double*
         bad = isfinite(s) ? 0.0 : 1.0;
       }
       bad = warp_sum(bad);
-      if (c == 0) red[128 + blockIdx.x] = bad;
+      if (c == 0) red[128 + bid] = bad;
     }
   } else {
     for (int a0 = 0; a0 < NACC; a0 += 32) {
@@ -1396,21 +1441,29 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce(int nphig, const double*
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) red[128 + blockIdx.x] = 0.0;
+    if (threadIdx.x == 0) red[128 + bid] = 0.0;
   }
+  __syncthreads();
 }
+
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) k_reduce(int nphig, const double* __restrict__ part_mlp, int nblk,
+                                                        const double* __restrict__ part_stream, int nrows, int NACC,
+                                                        double* __restrict__ out, T* __restrict__ grad_T,
+                                                        double* __restrict__ red) {
+  reduce_body<T>(nphig, part_mlp, nblk, part_stream, nrows, NACC, out, grad_T, red, blockIdx.x, gridDim.x);
+}
+
 
 // k_finalize executes a few thousand instructions once; with a cold instruction cache (after a large streaming kernel)
 // its run time is instruction fetch, so loops are not unrolled and helpers are not inlined (4888 -> 2128 instructions)
 template <typename T>
-__global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant__ Cfg<T> cfg,
-                                                          const T* __restrict__ phi, const T* __restrict__ zP,
-                                                          const T* __restrict__ pdraw,
-                                                          const EvalConsts<T>* __restrict__ ecp,
-                                                          const double* __restrict__ red, int nred_blocks,
-                                                          const double* __restrict__ xs, const double* __restrict__ xu,
-                                                          const double* __restrict__ batch_consts, int64_t nb, int M,
-                                                          double* __restrict__ out, T* __restrict__ grad_T) {
+__device__ __noinline__ void finalize_body(const Cfg<T>& cfg, const T* __restrict__ phi, const T* __restrict__ zP,
+                                           const T* __restrict__ pdraw, const EvalConsts<T>* __restrict__ ecp,
+                                           const double* __restrict__ red, int nred_blocks,
+                                           const double* __restrict__ xs, const double* __restrict__ xu,
+                                           const double* __restrict__ batch_consts, int64_t nb, int M,
+                                           double* __restrict__ out, T* __restrict__ grad_T) {
   __shared__ double sred[(3 + MAXP) * FIN_THREADS];
   __shared__ double sacc[128];
   __shared__ double sq[8 * MAXP + 2 * MAXP * MAXP + 16];   // ∇ϕq then the 8 trailing scalars
@@ -1546,6 +1599,18 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant_
   if (t == 0) bad += batch_consts[1];
   bad = block_sum_fixed(bad, sred);
   if (t == 0) out[cfg.nphi + 7] = bad;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize(const __grid_constant__ Cfg<T> cfg,
+                                                          const T* __restrict__ phi, const T* __restrict__ zP,
+                                                          const T* __restrict__ pdraw,
+                                                          const EvalConsts<T>* __restrict__ ecp,
+                                                          const double* __restrict__ red, int nred_blocks,
+                                                          const double* __restrict__ xs, const double* __restrict__ xu,
+                                                          const double* __restrict__ batch_consts, int64_t nb, int M,
+                                                          double* __restrict__ out, T* __restrict__ grad_T) {
+  finalize_body<T>(cfg, phi, zP, pdraw, ecp, red, nred_blocks, xs, xu, batch_consts, nb, M, out, grad_T);
 }
 
 // gradient entries of ϕg are written by many threads above; convert them after the block is done
@@ -1996,6 +2061,136 @@ cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const Strea
   return cudaSuccess;
 }
 
+// ---------------------------------------------------------------------------------------
+// The reference's own operating point -- n_batch = 20 sites of 800, n_MC = 3 … 12 (src/DoubleMM/f_doubleMM.jl:315-325,
+// src/HybridSolver.jl:147) -- is pure launch latency when it runs as eight kernels.  k_small_iter runs one whole
+// iteration of the optimiser loop (src/HybridSolver.jl:256-260) in ONE block of ONE launch: [minibatch gather from
+// the device-resident dataset] → draws of the global block → prologue → g forward → fused streaming phase (device
+// draws) → g backward → fixed-order reductions → finalize → [Adam update].  Every phase is the body of the kernel the
+// large-batch path launches (same arithmetic, same fixed reduction orders within a phase), separated by block
+// barriers instead of kernel boundaries.  For batches of a few hundred sites; g must be one of the CUDA-core shapes
+// without pbm covariates.
+// ---------------------------------------------------------------------------------------
+constexpr int SMALL_THREADS = 256;
+static_assert(SMALL_THREADS == FIN_THREADS && SMALL_THREADS == RED_THREADS && SMALL_THREADS >= MLP_BS, "block shapes of the fused phases");
+
+template <class TR, typename T, int NP, int NM, int NO>
+__global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_constant__ Cfg<T> cfg,
+                                                                 const __grid_constant__ SmallArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int t = threadIdx.x;
+  const int M = a.st.M;
+  const int64_t nb = a.st.nb;
+  const uint64_t seed = a.ctr ? (uint64_t)a.ctr[2] : a.st.seed;
+  // 0. minibatch of the device-resident dataset (hvi_adam_run_minibatches): gather + re-tile + batch constants
+  if (a.ds_xM) {
+    gather_preprocess_body<T>(cfg.nC, NO, nb, nullptr, a.first, a.ds_xM, a.ds_xP, a.ds_yo, a.ds_yu, a.xM_b, a.xP_b, a.rec_w,
+                              a.st.partials, a.ctr, a.n_batches, a.isites_out, 0, 1);
+    __syncthreads();
+    if (t == 0) {
+      double c = 0.0, an = 0.0;
+      for (int r = 0; r < SMALL_THREADS / 32; r++) { c += a.st.partials[2 * r]; an += a.st.partials[2 * r + 1]; }
+      a.bconst[0] = c; a.bconst[1] = an;
+    }
+    __syncthreads();
+  }
+  // 1. draws of the global block (k_gen_normal: columns keyed far above any site column)
+  {
+    const int M4 = (M + 3) / 4;
+    for (int e = t; e < NP * M4; e += SMALL_THREADS) {
+      const int col = e / M4, m4 = e % M4;
+      float n4[4];
+      normal4(seed, (uint64_t)((int64_t)col + ((int64_t)1 << 62)), m4, n4);
+      for (int d = 0; d < 4; d++)
+        if (m4 * 4 + d < M) a.zP[(size_t)col * M + m4 * 4 + d] = (T)n4[d];
+    }
+  }
+  __syncthreads();
+  // 2. ϕq → Cholesky factors, σP, per-draw θP
+  prologue_body<T>(cfg, a.phi, a.zP, M, const_cast<EvalConsts<T>*>(a.st.ec), a.pdraw);
+  __syncthreads();
+  // 3. μ_ζ = g(xM; ϕg)
+  mlp_fwd_body<T>(cfg, a.phi, a.xM, nb, const_cast<T*>(a.st.mu), smem_raw, 0, 1);
+  __syncthreads();
+  // 4. the fused streaming phase (draws generated in registers)
+  {
+    StreamArgs<T> sa = a.st;
+    sa.seed = seed; sa.seed_dev = nullptr; sa.rng = 1; sa.phi = a.phi;
+    stream_body<TR, T, NP, NM, NO, SMALL_THREADS, false, true>(cfg, sa, smem_raw, 0, 1);
+  }
+  __syncthreads();
+  // 5. μ̄_ζ → ∇ϕg (one row of partial sums)
+  mlp_bwd_body<T>(cfg, a.phi, a.xM, a.st.mubar, nb, a.part_mlp, smem_raw, 0, 1);
+  __syncthreads();
+  // 6. reductions in the fixed order of k_reduce, one virtual block after the other
+  const int nbg = (cfg.nphig + 31) / 32;
+  for (int b = 0; b <= nbg; b++)
+    reduce_body<T>(cfg.nphig, a.part_mlp, 1, a.st.partials, 1, nacc(NP, NM), a.out, a.grad_T, a.red, b, nbg + 1);
+  // 7. global-block terms, Cholesky adjoint, scatter into the layout of ϕ
+  finalize_body<T>(cfg, a.phi, a.zP, a.pdraw, a.st.ec, a.red, nbg + 1, nullptr, nullptr, a.bconst, nb, M, a.out, a.grad_T);
+  __syncthreads();
+  // 8. Adam (Optimisers.jl rule), as k_adam
+  if (a.adam_m) {
+    const int64_t n = cfg.nphi;
+    const unsigned long long t_applied = a.ctr[0], it = a.ctr[1];
+    const bool bad = a.out[n + 7] != 0.0 || !isfinite(a.out[n + 6]);
+    if (!bad) {
+      const double tt = (double)(t_applied + 1);
+      const double c1 = 1.0 / (1.0 - pow(a.b1, tt)), c2 = 1.0 / (1.0 - pow(a.b2, tt));
+      for (int64_t i = t; i < n; i += SMALL_THREADS) {
+        const double g = a.out[i];
+        const double mi = a.b1 * a.adam_m[i] + (1.0 - a.b1) * g, vi = a.b2 * a.adam_v[i] + (1.0 - a.b2) * g * g;
+        a.adam_m[i] = mi; a.adam_v[i] = vi;
+        a.phi[i] = (T)((double)a.phi[i] - a.eta * (mi * c1) / (sqrt(vi * c2) + a.eps));
+      }
+    }
+    __syncthreads();
+    if (t == 0) {
+      if (a.trace) a.trace[it] = bad ? nan("") : a.out[n + 6];
+      if (!bad) a.ctr[0] = t_applied + 1;
+      a.ctr[1] = it + 1;
+      a.ctr[2] += 1;
+    }
+  }
+}
+
+template <typename T>
+static size_t small_iter_smem(const Cfg<T>& cfg, int M) {
+  constexpr int CH = 16 / sizeof(T), MC = 8 * CH, NWARP = SMALL_THREADS / 32;
+  const size_t stream = (size_t)NWARP * 32 * cfg.nM * MC * sizeof(T) + (size_t)NWARP * nacc(cfg.nP, cfg.nM) * sizeof(double) +
+                        (size_t)M * pd_stride(cfg.nP) * sizeof(T) + 16;
+  const size_t mlp = mlp_bwd_smem(cfg);
+  return stream > mlp ? stream : mlp;
+}
+
+template <typename T>
+bool small_iter_supported(const Cfg<T>& cfg, int64_t nb, int M) {
+  if (cfg.npc > 0 || cfg.sepvar || nb < 1 || nb > 4096 || M < 1) return false;
+  if (!stream_supported(cfg.nP, cfg.nM, cfg.nO)) return false;
+  if (cfg.max_width > HVI_MAX_WIDTH) return false;
+  if ((size_t)M * pd_stride(cfg.nP) * sizeof(T) > 16 * 1024) return false;
+  return small_iter_smem(cfg, M) <= 200 * 1024;
+}
+
+template <typename T>
+cudaError_t launch_small_iter(const Launch& L, const Cfg<T>& cfg, SmallArgs<T> a) {
+  a.st.pd_in_smem = cfg.nP > 0 ? 1 : 0;
+  a.st.staged = 0; a.st.rng = 1;
+  const size_t smem = small_iter_smem(cfg, a.st.M);
+#define X(P, M_, O)                                                                              \
+  if (cfg.nP == P && cfg.nM == M_ && cfg.nO == O) {                                              \
+    auto kern = k_small_iter<DynTraits, T, P, M_, O>;                                            \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                              \
+    kern<<<1, SMALL_THREADS, smem, L.stream>>>(cfg, a);                                          \
+    HVI_LAUNCH_CHECK();                                                                          \
+    return cudaSuccess;                                                                          \
+  }
+  HVI_STREAM_CASES(X)
+#undef X
+  return cudaErrorInvalidConfiguration;
+}
+
 #define HVI_INSTANTIATE(T)                                                                                              \
   template cudaError_t launch_preprocess<T>(const Launch&, int, int64_t, const T*, const T*, const T*, T*, double*, int*); \
   template cudaError_t launch_prologue<T>(const Launch&, const Cfg<T>&, const T*, const T*, int, EvalConsts<T>*, T*);    \
@@ -2010,7 +2205,9 @@ cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const Strea
                                           const EvalConsts<T>*, const double*, int, const double*, int, const double*, int64_t, \
                                           int, double*, T*, double*, const double*, int, const double*, int, double*);                                                             \
   template cudaError_t launch_gen_normal<T>(const Launch&, T*, int64_t, int, uint64_t, int64_t, const unsigned long long*); \
-  template cudaError_t launch_generate_zeta<T>(const Launch&, const Cfg<T>&, const StreamArgs<T>&, const T*, T*, T*, T*);
+  template cudaError_t launch_generate_zeta<T>(const Launch&, const Cfg<T>&, const StreamArgs<T>&, const T*, T*, T*, T*); \
+  template bool small_iter_supported<T>(const Cfg<T>&, int64_t, int);                                                    \
+  template cudaError_t launch_small_iter<T>(const Launch&, const Cfg<T>&, SmallArgs<T>);
 HVI_INSTANTIATE(float)
 HVI_INSTANTIATE(double)
 

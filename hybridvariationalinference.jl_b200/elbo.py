@@ -228,6 +228,10 @@ class NegElboPlan:
     def use_graphs(self, on: bool):
         self._check(self.lib.hvi_plan_use_graphs(self._h, int(on)))
 
+    def use_fused(self, on: bool):
+        """Small batches with device draws run as one launch (k_small_iter); False forces the multi-kernel path."""
+        self._check(self.lib.hvi_plan_use_fused(self._h, int(on)))
+
     def adam_run_minibatches(self, n_iter, n_MC, batch_size, seed0=0, first_batch=0, trace=True):
         """`solve`'s minibatch loop (src/HybridSolver.jl:259-260) on the device-resident dataset: iteration i takes
         minibatch (first_batch + i) mod (n_site // batch_size), evaluates and applies Adam; CUDA-graph replayed."""

@@ -266,6 +266,13 @@ int hvi_adam_apply_dev(hvi_plan* plan, const double* out_dev, void* cuda_stream)
 int hvi_adam_run_minibatches(hvi_plan* plan, int32_t n_iter, int32_t n_MC, uint64_t seed0, int64_t batch_size,
                              int64_t first_batch, double* nL_trace);
 int hvi_plan_use_graphs(hvi_plan* plan, int on);
+/* Small batches (the reference's operating point: 20 sites of 800, n_MC = 3 … 12, src/DoubleMM/f_doubleMM.jl:315-325,
+ * src/HybridSolver.jl:147) with device draws run as ONE launch of one block per evaluation / optimiser iteration
+ * (minibatch gather → draws → prologue → g → fused streaming phase → g backward → reductions → finalize → Adam)
+ * instead of eight launches; hvi_plan_use_fused(plan, 0) forces the multi-kernel path (same results up to the
+ * summation order of the per-block partial sums).  Applies to n_site <= 1024, n_site x n_MC <= 16384, the CUDA-core
+ * applicator shapes, MeanHVIApproximationMat, no pbm covariates. */
+int hvi_plan_use_fused(hvi_plan* plan, int on);
 int hvi_adam_phi_dev(hvi_plan* plan, void** phi_dev);
 int hvi_adam_get_phi(hvi_plan* plan, void* phi_host);
 

@@ -92,3 +92,66 @@ def test_sharded_adam_steps_equal_unsharded():
         assert np.max(np.abs(got - want)) <= 1e-10 * max(1.0, np.max(np.abs(want)))
     assert np.max(np.abs(np.array(trace) - want_trace)) <= 1e-10 * np.max(np.abs(want_trace))
     assert callable(adam_step_sharded)
+
+
+CASES_FUSED = {
+    "DoubleMM_default": lambda dt: hvi_b200.DoubleMMCase(dtype=dt),
+    "C1_test_HybridProblem": lambda dt: hvi_b200.construct_problem_test_HybridProblem(dtype=dt),
+    "omit_r0": lambda dt: hvi_b200.DoubleMMCase(("omit_r0",), dtype=dt),
+    "no_globals": lambda dt: hvi_b200.DoubleMMCase(("no_globals",), dtype=dt),
+    "K1global": lambda dt: hvi_b200.DoubleMMCase(("omit_r0", "K1global"), dtype=dt),
+    "transIdent_rangescaling": lambda dt: hvi_b200.DoubleMMCase(("transIdent", "use_rangescaling"), dtype=dt),
+}
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-11), ("f32", 3e-5)])
+@pytest.mark.parametrize("case", list(CASES_FUSED))
+@pytest.mark.parametrize("nb,M", [(20, 3), (1, 1), (333, 12), (1000, 16)])
+def test_single_launch_evaluation_equals_the_multi_kernel_path(case, nb, M, dtype, tol):
+    """the reference's operating point (20 sites, n_MC = 3; src/DoubleMM/f_doubleMM.jl:315-325) runs as ONE launch
+    (k_small_iter): same value, components and gradient as the eight-kernel path on the same device draws, up to the
+    summation order of the partial sums"""
+    prob = CASES_FUSED[case](dtype)
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=12, driver_nan_frac=0.2 if nb > 20 else 0.0)
+    ϕ = prob.init_ϕ(perturbed=True)
+    plan = hvi_b200.NegElboPlan(prob)
+    plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    n0 = plan.launch_count
+    nL, comps, g = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=77)
+    assert plan.launch_count - n0 == 1
+    plan.use_fused(False)
+    n0 = plan.launch_count
+    nL2, comps2, g2 = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=77)
+    assert plan.launch_count - n0 >= 6
+    assert abs(nL - nL2) <= tol * abs(nL2)
+    assert np.max(np.abs(np.array(comps) - np.array(comps2))) <= tol * np.max(np.abs(comps2))
+    for name, r in prob.positions().items():
+        if len(r):
+            assert np.max(np.abs(g[r].astype(np.float64) - g2[r])) <= tol * np.max(np.abs(g2[r])), name
+    nL3, _, g3 = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=77, want_grad=False)
+    assert g3 is None and nL3 == nL2
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-10), ("f32", 3e-4)])
+def test_single_launch_optimiser_loop_equals_the_multi_kernel_loop(dtype, tol):
+    prob = hvi_b200.DoubleMMCase(dtype=dtype)
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, 800, seed=3)
+    ϕ0 = prob.init_ϕ()
+    res = []
+    for fused in (True, False):
+        plan = hvi_b200.NegElboPlan(prob)
+        plan.use_fused(fused)
+        plan.set_dataset(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+        plan.adam_init(ϕ0, eta=0.02)
+        n0 = plan.launch_count
+        tr = plan.adam_run_minibatches(45, 3, 20, seed0=5)           # 40 minibatches per epoch: wraps around
+        per_iter = (plan.launch_count - n0) / 45
+        plan.select_range(0, 20)
+        tr_b = plan.adam_run(10, 12, seed0=500)                        # the loop on one registered batch
+        res.append((tr, tr_b, plan.adam_phi().astype(np.float64), per_iter))
+    (tr, tr_b, ϕa, la), (tr2, tr2_b, ϕb, lb) = res
+    assert la < 2 and lb >= 8                                          # one launch (+ the counter reset) vs >= 8 per iteration
+    assert np.all(np.isfinite(tr)) and np.all(np.isfinite(tr_b))
+    assert np.max(np.abs(tr - tr2)) <= tol * np.max(np.abs(tr2))
+    assert np.max(np.abs(tr_b - tr2_b)) <= tol * np.max(np.abs(tr2_b))
+    assert np.max(np.abs(ϕa - ϕb)) <= tol * max(1.0, np.max(np.abs(ϕb)))
