@@ -70,6 +70,7 @@ SYMBOLS = [
     ("hvi_utri2vec_pos", _I64, [_I64, _I64]),
     ("hvi_cor_count", _I64, [C.POINTER(_I32), _I32]),
     ("hvi_plan_set_data", _INT, [_P, _I64, _P, _P, _P, _P, _INT]),
+    ("hvi_plan_set_data_bcast", _INT, [_P, _I64, _P, _P, _INT, _P, _P, _INT, _INT]),
     ("hvi_plan_prefetch_data", _INT, [_P, _I64, _P, _P, _P, _P]),
     ("hvi_plan_commit_data", _INT, [_P]),
     ("hvi_plan_set_sites", _INT, [_P, C.POINTER(_I64), _I64]),
@@ -89,6 +90,7 @@ SYMBOLS = [
     ("hvi_adam_run_minibatches", _INT, [_P, _I32, _I32, _U64, _I64, _I64, _DP]),
     ("hvi_plan_use_graphs", _INT, [_P, _INT]),
     ("hvi_plan_use_fused", _INT, [_P, _INT]),
+    ("hvi_plan_fused_phase_clocks", _INT, [_P, C.POINTER(_I64)]),
     ("hvi_adam_phi_dev", _INT, [_P, C.POINTER(_P)]),
     ("hvi_adam_get_phi", _INT, [_P, _P]),
     ("hvi_generate_zeta", _INT, [_P, _I32, _P, _P, _P, _INT, _P, _P, _P]),

@@ -87,6 +87,7 @@ struct hvi_plan {
   // one optimiser iteration captured as a CUDA graph (replayed by hvi_adam_run)
   cudaGraphExec_t adam_graph; GraphKey graph_key; int graph_valid, graph_nodes, use_graphs;
   int use_fused;   // small batches: one launch per evaluation / optimiser iteration (k_small_iter)
+  long long* d_clocks;   // phase time stamps of the last fused launch (hvi_plan_fused_phase_clocks)
   // optional per-kernel timing (CUDA events on the launching stream)
   int profiling;
   cudaEvent_t ev[8];
@@ -262,7 +263,7 @@ extern "C" int hvi_plan_create(const hvi_desc* desc, hvi_plan** out) {
   p->nb = 0; p->launches = 0;
   p->d_ls = nullptr; p->cap_ls = 0;
   p->d_phi_opt = nullptr; p->d_adam_m = p->d_adam_v = p->d_trace = nullptr; p->cap_trace = 0;
-  p->d_ctr = nullptr; p->adam_graph = nullptr; p->graph_valid = 0; p->graph_nodes = 0; p->use_graphs = 1; p->use_fused = 1;
+  p->d_ctr = nullptr; p->adam_graph = nullptr; p->graph_valid = 0; p->graph_nodes = 0; p->use_graphs = 1; p->use_fused = 1; p->d_clocks = nullptr;
   p->own_stream = nullptr; p->ev_user = p->ev_plan = nullptr; p->user_pending = 0;
   p->d_bconst = nullptr; p->h_bconst = nullptr;
   p->ds_n = 0; p->ds_has_obs = 0; p->ds_xM = p->ds_xP = p->ds_yo = p->ds_yu = nullptr; p->d_idx = nullptr; p->cap_idx = 0; p->n_isites = 0;
@@ -335,7 +336,7 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   if (p->gpbm) generic_pbm_destroy(p->gpbm);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->ev_copied) cudaEventDestroy(p->ev_copied);
-  void* dev[] = {p->d_yo, p->d_yu, p->d_pen, p->d_bconst, p->d_ctr, p->ds_xM, p->ds_xP, p->ds_yo, p->ds_yu, p->d_idx, p->d_ls, p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->d_trace, p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
+  void* dev[] = {p->d_clocks, p->d_yo, p->d_yu, p->d_pen, p->d_bconst, p->d_ctr, p->ds_xM, p->ds_xP, p->ds_yo, p->ds_yu, p->d_idx, p->d_ls, p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->d_trace, p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
                  p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide, p->d_wide_bwd, p->d_gacc, p->d_wide_cache};
   for (void* q : dev) if (q) cudaFree(q);
   if (p->h_out) cudaFreeHost(p->h_out);
@@ -607,6 +608,62 @@ static int set_data_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, c
   return finish_batch<T>(p, nb, dxP, dyo, dyu);
 }
 
+// dst (rows x nb, column-major) = the one column src (rows) repeated: arrays that are identical for every site are
+// uploaded once (PBMPopulationGlobalApplicator keeps shared drivers out of the per-site data, src/PBMApplicator.jl:305-375)
+template <typename T>
+__global__ void __launch_bounds__(256) k_expand_cols(T* __restrict__ dst, const T* __restrict__ src, int rows, int64_t nb) {
+  const int64_t n = (int64_t)rows * nb;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) dst[e] = src[e % rows];
+}
+
+template <typename T>
+static int expand_cols(hvi_plan* p, T* dst, const T* src_dev, int rows, int64_t nb) {
+  int64_t blocks = ((int64_t)rows * nb + 255) / 256;
+  if (blocks > (int64_t)p->sm_count * 16) blocks = (int64_t)p->sm_count * 16;
+  k_expand_cols<T><<<(int)blocks, 256, 0, p->stream>>>(dst, src_dev, rows, nb);
+  CU(p, cudaGetLastError());
+  ++p->launches;
+  return HVI_OK;
+}
+
+// set_data with arrays that are the same for every site given as ONE column
+template <typename T>
+static int set_data_bcast_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, int xP_shared, const void* y_o,
+                            const void* y_unc, int y_unc_shared, int mem_kind) {
+  const int nO = p->desc.n_obs, nC = p->desc.n_covar, nX = p->n_x;
+  if (p->nb_next > 0) { CU(p, cudaStreamSynchronize(p->copy_stream)); p->nb_next = 0; }
+  int rc = join_user(p);
+  if (rc) return rc;
+  CU(p, cudaStreamSynchronize(p->stream));
+  rc = alloc_batch<T>(p, nb, false);
+  if (rc) return rc;
+  const size_t n2 = (size_t)nO * nb;
+  // staging: y_o | y_unc | one column of xP | one column of y_unc
+  rc = ensure(p, &p->d_stage, &p->cap_stage, (int64_t)(sizeof(T) * (2 * n2 + nX + nO)));
+  if (rc) return rc;
+  T* t = (T*)p->d_stage;
+  T* col_x = t + 2 * n2;
+  T* col_u = col_x + nX;
+  CU(p, copy_in(p->d_xM, xM, sizeof(T) * (size_t)nC * nb, mem_kind, p->stream));
+  if (xP_shared) {
+    CU(p, copy_in(col_x, xP, sizeof(T) * (size_t)nX, mem_kind, p->stream));
+    rc = expand_cols<T>(p, (T*)p->d_xP, col_x, nX, nb);
+    if (rc) return rc;
+  } else {
+    CU(p, copy_in(p->d_xP, xP, sizeof(T) * (size_t)nX * nb, mem_kind, p->stream));
+  }
+  p->has_obs = 1;
+  CU(p, copy_in(t, y_o, sizeof(T) * n2, mem_kind, p->stream));
+  if (y_unc_shared) {
+    CU(p, copy_in(col_u, y_unc, sizeof(T) * (size_t)nO, mem_kind, p->stream));
+    rc = expand_cols<T>(p, t + n2, col_u, nO, nb);
+    if (rc) return rc;
+  } else {
+    CU(p, copy_in(t + n2, y_unc, sizeof(T) * n2, mem_kind, p->stream));
+  }
+  return finish_batch<T>(p, nb, (const T*)p->d_xP, t, t + n2);
+}
+
 // upload of the NEXT batch on the plan's copy stream; nothing of the current batch is touched
 template <typename T>
 static int prefetch_t(hvi_plan* p, int64_t nb, const void* xM, const void* xP, const void* y_o, const void* y_unc) {
@@ -671,6 +728,18 @@ extern "C" int hvi_plan_set_data(hvi_plan* p, int64_t n_site, const void* xM, co
   if (p->d_isites) { cudaStreamSynchronize(p->stream); cudaFree(p->d_isites); p->d_isites = nullptr; p->n_isites = 0; }   // back to the identity map
   return p->dtype == HVI_F32 ? set_data_t<float>(p, n_site, xM, xP, y_o, y_unc, mem_kind)
                              : set_data_t<double>(p, n_site, xM, xP, y_o, y_unc, mem_kind);
+}
+
+extern "C" int hvi_plan_set_data_bcast(hvi_plan* p, int64_t n_site, const void* xM, const void* xP, int xP_shared,
+                                       const void* y_o, const void* y_unc, int y_unc_shared, int mem_kind) {
+  if (!p) return HVI_EINVAL;
+  if (n_site < 1 || !xM || !xP || !y_o || !y_unc) PLAN_FAIL(p, HVI_EINVAL, "set_data_bcast: n_site must be >= 1 and all arrays non-NULL");
+  if (mem_kind != HVI_MEM_HOST && mem_kind != HVI_MEM_DEVICE) PLAN_FAIL(p, HVI_EINVAL, "set_data_bcast: bad mem_kind");
+  CU(p, cudaSetDevice(p->desc.device));
+  if (p->cf.sepvar && n_site > p->cf.n_site_total) PLAN_FAIL(p, HVI_EINVAL, "set_data_bcast: batch has more sites than n_site_total");
+  if (p->d_isites) { cudaStreamSynchronize(p->stream); cudaFree(p->d_isites); p->d_isites = nullptr; p->n_isites = 0; }
+  return p->dtype == HVI_F32 ? set_data_bcast_t<float>(p, n_site, xM, xP, xP_shared, y_o, y_unc, y_unc_shared, mem_kind)
+                             : set_data_bcast_t<double>(p, n_site, xM, xP, xP_shared, y_o, y_unc, y_unc_shared, mem_kind);
 }
 
 extern "C" int hvi_plan_prefetch_data(hvi_plan* p, int64_t n_site, const void* xM, const void* xP, const void* y_o,
@@ -987,6 +1056,7 @@ static int enqueue_fused(hvi_plan* p, int M, T* phi, double* out, T* grad_T, cud
     a.adam_m = p->d_adam_m; a.adam_v = p->d_adam_v; a.trace = p->d_trace;
     a.eta = p->adam_eta; a.b1 = p->adam_b1; a.b2 = p->adam_b2; a.eps = p->adam_eps; a.ctr = p->d_ctr;
   }
+  a.clocks = p->d_clocks;
   Launch L{s, p->sm_count, &p->launches};
   CU(p, launch_small_iter<T>(L, cfg, a));
   return HVI_OK;
@@ -1679,6 +1749,26 @@ extern "C" int hvi_plan_use_fused(hvi_plan* p, int on) {
   if (!p) return HVI_EINVAL;
   p->use_fused = on ? 1 : 0;
   p->graph_valid = 0;
+  return HVI_OK;
+}
+
+// Profiling aid of the single-launch path: from the next fused launch on, thread 0 stamps clock64() at the phase
+// boundaries; clocks[0..10] = start, after gather, zP draws, prologue, g forward, streaming phase, g backward, reduce,
+// finalize, Adam (SM clock ticks).  The reference has no tracing.
+extern "C" int hvi_plan_fused_phase_clocks(hvi_plan* p, int64_t clocks[10]) {
+  if (!p) return HVI_EINVAL;
+  CU(p, cudaSetDevice(p->desc.device));
+  if (!p->d_clocks) {
+    CU(p, cudaMalloc((void**)&p->d_clocks, sizeof(long long) * 16));
+    CU(p, cudaMemset(p->d_clocks, 0, sizeof(long long) * 16));
+    p->graph_valid = 0;
+  }
+  if (clocks) {
+    CU(p, cudaStreamSynchronize(p->stream));
+    long long h[16];
+    CU(p, cudaMemcpy(h, p->d_clocks, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 10; i++) clocks[i] = (int64_t)h[i];
+  }
   return HVI_OK;
 }
 

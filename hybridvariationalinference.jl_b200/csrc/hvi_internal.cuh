@@ -102,6 +102,7 @@ struct SmallArgs {
   double *adam_m, *adam_v, *trace;
   double eta, b1, b2, eps;
   unsigned long long* ctr;
+  long long* clocks;    // optional: clock64() at the phase boundaries (profiling aid), NULL otherwise
 };
 
 struct Launch {

@@ -2071,6 +2071,128 @@ cudaError_t launch_generate_zeta(const Launch& L, const Cfg<T>& cfg, const Strea
 // barriers instead of kernel boundaries.  For batches of a few hundred sites; g must be one of the CUDA-core shapes
 // without pbm covariates.
 // ---------------------------------------------------------------------------------------
+// g for a small batch inside one block: the work is spread over (site, neuron) pairs instead of one thread per site,
+// so that a 20-site minibatch keeps all threads busy and every dependent chain is one dot product long.  Same
+// shared-memory layout as k_mlp_fwd / k_mlp_bwd (weights, activation stack [row][MLP_BS], delta stack), same
+// accumulation order within a dot product as mlp_forward_block.  All threads of the block call these.
+template <typename T>
+__device__ __forceinline__ void small_mlp_forward_tile(const Cfg<T>& cfg, const T* __restrict__ sW, T* __restrict__ acts, int ns) {
+  const int t = threadIdx.x, NT = blockDim.x;
+  int row_in = 0;
+  for (int l = 0; l < cfg.nL; l++) {
+    const int ni = cfg.l_in[l], no = cfg.l_out[l], row_out = row_in + ni;
+    const T* W = sW + cfg.woff[l];
+    for (int task = t; task < ns * no; task += NT) {
+      const int site = task % ns, j = task / ns;
+      T z = cfg.l_bias[l] ? sW[cfg.boff[l] + j] : T(0);
+      for (int i = 0; i < ni; i++) z = fma(W[i * no + j], acts[(row_in + i) * MLP_BS + site], z);
+      acts[(row_out + j) * MLP_BS + site] = act_f<T>(cfg.l_act[l], z);
+    }
+    __syncthreads();
+    row_in = row_out;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void small_mlp_fwd(const Cfg<T>& cfg, const T* __restrict__ phi, const T* __restrict__ xM,
+                                              int64_t nb, T* __restrict__ mu, unsigned char* smem_raw) {
+  T* sW = reinterpret_cast<T*>(smem_raw);
+  T* acts = sW + ((cfg.nphig + 3) & ~3);
+  const int t = threadIdx.x, NT = blockDim.x;
+  for (int e = t; e < cfg.nphig; e += NT) sW[e] = phi[e];
+  const int out_row = cfg.sum_width - cfg.l_out[cfg.nL - 1];
+  for (int64_t s0 = 0; s0 < nb; s0 += MLP_BS) {
+    const int ns = (int)(nb - s0 < MLP_BS ? nb - s0 : MLP_BS);
+    for (int e = t; e < ns * cfg.nC; e += NT) acts[(e % cfg.nC) * MLP_BS + e / cfg.nC] = xM[s0 * cfg.nC + e];
+    __syncthreads();
+    small_mlp_forward_tile<T>(cfg, sW, acts, ns);
+    for (int e = t; e < ns * cfg.nM; e += NT) {
+      const int site = e / cfg.nM, k = e % cfg.nM;
+      const T p = acts[(out_row + k) * MLP_BS + site];
+      mu[(s0 + site) * cfg.nM + k] = (cfg.scale_kind == HVI_SCALE_RANGE) ? p * cfg.scale_b[k] + cfg.scale_a[k]
+                                                                        : cfg.scale_a[k] + cfg.scale_b[k] * ndtri_t(p);
+    }
+    __syncthreads();
+  }
+}
+
+// one row of ∇ϕg partial sums (part[0 .. nphig)), deterministic
+template <typename T>
+__device__ __forceinline__ void small_mlp_bwd(const Cfg<T>& cfg, const T* __restrict__ phi, const T* __restrict__ xM,
+                                              const T* __restrict__ mubar, int64_t nb, double* __restrict__ part,
+                                              unsigned char* smem_raw) {
+  double* gacc = reinterpret_cast<double*>(smem_raw);                 // [nphig]
+  int2* tab = reinterpret_cast<int2*>(gacc + cfg.nphig);              // [nphig] (delta row, act row | -1)
+  T* sW = reinterpret_cast<T*>(tab + cfg.nphig);                      // [nphig]
+  T* acts = sW + ((cfg.nphig + 3) & ~3);                              // [sum_width][BS]
+  T* dl = acts + (size_t)cfg.sum_width * MLP_BS;                      // [sum_out][BS]
+  const int t = threadIdx.x, NT = blockDim.x;
+  for (int e = t; e < cfg.nphig; e += NT) { sW[e] = phi[e]; gacc[e] = 0.0; }
+  {
+    int row_in = 0, drow = 0;
+    for (int l = 0; l < cfg.nL; l++) {
+      const int ni = cfg.l_in[l], no = cfg.l_out[l];
+      for (int e = t; e < ni * no; e += NT) tab[cfg.woff[l] + e] = make_int2(drow + e % no, row_in + e / no);
+      if (cfg.l_bias[l])
+        for (int e = t; e < no; e += NT) tab[cfg.boff[l] + e] = make_int2(drow + e, -1);
+      row_in += ni; drow += no;
+    }
+  }
+  const int out_row = cfg.sum_width - cfg.l_out[cfg.nL - 1];
+  const int nlast = cfg.l_out[cfg.nL - 1];
+  for (int64_t s0 = 0; s0 < nb; s0 += MLP_BS) {
+    const int ns = (int)(nb - s0 < MLP_BS ? nb - s0 : MLP_BS);
+    for (int e = t; e < ns * cfg.nC; e += NT) acts[(e % cfg.nC) * MLP_BS + e / cfg.nC] = xM[s0 * cfg.nC + e];
+    __syncthreads();
+    small_mlp_forward_tile<T>(cfg, sW, acts, ns);
+    // output delta: μ̄_ζ · σ_k · √(2π) e^{q²/2} · p(1−p)
+    int drow = cfg.sum_out - nlast;
+    for (int e = t; e < ns * nlast; e += NT) {
+      const int site = e / nlast, k = e % nlast;
+      T d = T(0);
+      if (k < cfg.nM) {
+        const T p = acts[(out_row + k) * MLP_BS + site];
+        const T mb = mubar[(s0 + site) * cfg.nM + k];
+        if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb * cfg.scale_b[k];
+        else { const T q = ndtri_t(p); d = mb * cfg.scale_b[k] * T(2.50662827463100050242) * exp_t(T(0.5) * q * q); }
+        d *= act_d<T>(cfg.l_act[cfg.nL - 1], p);
+      }
+      dl[(drow + k) * MLP_BS + site] = d;
+    }
+    __syncthreads();
+    // hidden deltas, one (site, neuron) pair per task
+    int row_out = out_row;
+    for (int l = cfg.nL - 1; l >= 1; l--) {
+      const int ni = cfg.l_in[l], no = cfg.l_out[l];
+      const int row_in = row_out - ni, drow_prev = drow - ni;
+      const T* W = sW + cfg.woff[l];
+      for (int task = t; task < ns * ni; task += NT) {
+        const int site = task % ns, i = task / ns;
+        T sacc = T(0);
+        for (int j = 0; j < no; j++) sacc = fma(W[i * no + j], dl[(drow + j) * MLP_BS + site], sacc);
+        dl[(drow_prev + i) * MLP_BS + site] = sacc * act_d<T>(cfg.l_act[l - 1], acts[(row_in + i) * MLP_BS + site]);
+      }
+      __syncthreads();
+      row_out = row_in; drow = drow_prev;
+    }
+    // weight gradient: entry e = Σ_sites δ·a over the sites of this tile
+    for (int e = t; e < cfg.nphig; e += NT) {
+      const int2 rc = tab[e];
+      const T* dr = dl + (size_t)rc.x * MLP_BS;
+      T acc = T(0);
+      if (rc.y >= 0) {
+        const T* ar = acts + (size_t)rc.y * MLP_BS;
+        for (int si = 0; si < ns; si++) acc = fma(dr[si], ar[si], acc);
+      } else {
+        for (int si = 0; si < ns; si++) acc += dr[si];
+      }
+      gacc[e] += (double)acc;
+    }
+    __syncthreads();
+  }
+  for (int e = t; e < cfg.nphig; e += NT) part[e] = gacc[e];
+}
+
 constexpr int SMALL_THREADS = 256;
 static_assert(SMALL_THREADS == FIN_THREADS && SMALL_THREADS == RED_THREADS && SMALL_THREADS >= MLP_BS, "block shapes of the fused phases");
 
@@ -2082,6 +2204,9 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
   const int M = a.st.M;
   const int64_t nb = a.st.nb;
   const uint64_t seed = a.ctr ? (uint64_t)a.ctr[2] : a.st.seed;
+  int stamp = 0;
+#define HVI_STAMP() do { if (a.clocks && t == 0) a.clocks[stamp] = clock64(); ++stamp; } while (0)
+  HVI_STAMP();
   // 0. minibatch of the device-resident dataset (hvi_adam_run_minibatches): gather + re-tile + batch constants
   if (a.ds_xM) {
     gather_preprocess_body<T>(cfg.nC, NO, nb, nullptr, a.first, a.ds_xM, a.ds_xP, a.ds_yo, a.ds_yu, a.xM_b, a.xP_b, a.rec_w,
@@ -2094,6 +2219,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
     }
     __syncthreads();
   }
+  HVI_STAMP();
   // 1. draws of the global block (k_gen_normal: columns keyed far above any site column)
   {
     const int M4 = (M + 3) / 4;
@@ -2106,12 +2232,15 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
     }
   }
   __syncthreads();
+  HVI_STAMP();
   // 2. ϕq → Cholesky factors, σP, per-draw θP
   prologue_body<T>(cfg, a.phi, a.zP, M, const_cast<EvalConsts<T>*>(a.st.ec), a.pdraw);
   __syncthreads();
+  HVI_STAMP();
   // 3. μ_ζ = g(xM; ϕg)
-  mlp_fwd_body<T>(cfg, a.phi, a.xM, nb, const_cast<T*>(a.st.mu), smem_raw, 0, 1);
+  small_mlp_fwd<T>(cfg, a.phi, a.xM, nb, const_cast<T*>(a.st.mu), smem_raw);
   __syncthreads();
+  HVI_STAMP();
   // 4. the fused streaming phase (draws generated in registers)
   {
     StreamArgs<T> sa = a.st;
@@ -2119,16 +2248,34 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
     stream_body<TR, T, NP, NM, NO, SMALL_THREADS, false, true>(cfg, sa, smem_raw, 0, 1);
   }
   __syncthreads();
+  HVI_STAMP();
   // 5. μ̄_ζ → ∇ϕg (one row of partial sums)
-  mlp_bwd_body<T>(cfg, a.phi, a.xM, a.st.mubar, nb, a.part_mlp, smem_raw, 0, 1);
+  small_mlp_bwd<T>(cfg, a.phi, a.xM, a.st.mubar, nb, a.part_mlp, smem_raw);
   __syncthreads();
-  // 6. reductions in the fixed order of k_reduce, one virtual block after the other
+  HVI_STAMP();
+  // 6. what k_reduce does for a single row of partial sums: ∇ϕg and its non-finite count per group of 32 entries, the
+  // streaming phase's accumulators
   const int nbg = (cfg.nphig + 31) / 32;
-  for (int b = 0; b <= nbg; b++)
-    reduce_body<T>(cfg.nphig, a.part_mlp, 1, a.st.partials, 1, nacc(NP, NM), a.out, a.grad_T, a.red, b, nbg + 1);
+  for (int e0 = 0; e0 < nbg * 32; e0 += SMALL_THREADS) {
+    const int e = e0 + t;
+    double bad = 0.0;
+    if (e < cfg.nphig) {
+      const double v = a.part_mlp[e];
+      a.out[e] = v;
+      if (a.grad_T) a.grad_T[e] = (T)v;
+      bad = isfinite(v) ? 0.0 : 1.0;
+    }
+    bad = warp_sum(bad);
+    if ((t & 31) == 0 && e < nbg * 32) a.red[128 + e / 32] = bad;
+  }
+  for (int i = t; i < nacc(NP, NM); i += SMALL_THREADS) a.red[i] = a.st.partials[i];
+  if (t == 0) a.red[128 + nbg] = 0.0;
+  __syncthreads();
+  HVI_STAMP();
   // 7. global-block terms, Cholesky adjoint, scatter into the layout of ϕ
   finalize_body<T>(cfg, a.phi, a.zP, a.pdraw, a.st.ec, a.red, nbg + 1, nullptr, nullptr, a.bconst, nb, M, a.out, a.grad_T);
   __syncthreads();
+  HVI_STAMP();
   // 8. Adam (Optimisers.jl rule), as k_adam
   if (a.adam_m) {
     const int64_t n = cfg.nphi;
@@ -2152,6 +2299,8 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
       a.ctr[2] += 1;
     }
   }
+  HVI_STAMP();
+#undef HVI_STAMP
 }
 
 template <typename T>

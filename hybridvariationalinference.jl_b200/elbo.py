@@ -154,6 +154,25 @@ class NegElboPlan:
             idx = np.ascontiguousarray(i_sites, dtype=np.int64)
             self._check(self.lib.hvi_plan_set_sites(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
 
+    def set_data_bcast(self, xM, xP, y_o, y_unc, i_sites=None):
+        """set_data where xP and / or y_unc may be ONE column shared by all sites (shape (rows, 1) or (rows,)): shared
+        drivers (PBMPopulationGlobalApplicator, src/PBMApplicator.jl:305-375) and a constant observation uncertainty
+        are uploaded once and expanded on the device.  Host arrays."""
+        f = lambda a: np.asfortranarray(np.asarray(a, dtype=self.dt).reshape(a.shape[0], -1))
+        xM_, xP_, yo_, yu_ = map(f, (xM, xP, y_o, y_unc))
+        n_site = xM_.shape[1]
+        nx = getattr(self, "n_x", 2 * self.prob.n_obs)
+        assert xP_.shape in ((nx, n_site), (nx, 1)) and yu_.shape in ((self.prob.n_obs, n_site), (self.prob.n_obs, 1))
+        assert yo_.shape == (self.prob.n_obs, n_site) and xM_.shape[0] == self.prob.n_covar
+        xs, us = int(xP_.shape[1] == 1 and n_site > 1), int(yu_.shape[1] == 1 and n_site > 1)
+        self._keep = (xM_, xP_, yo_, yu_)
+        self._check(self.lib.hvi_plan_set_data_bcast(self._h, n_site, _ptr(xM_), _ptr(xP_), xs, _ptr(yo_), _ptr(yu_), us,
+                                                     A.HVI_MEM_HOST))
+        self.n_site = n_site
+        if i_sites is not None:
+            idx = np.ascontiguousarray(i_sites, dtype=np.int64)
+            self._check(self.lib.hvi_plan_set_sites(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
+
     def prefetch_data(self, xM, xP, y_o=None, y_unc=None):
         """Start the upload of the NEXT batch (host arrays, ideally page-locked) while the current one is
         evaluated -- the DataLoader iteration of `solve` (src/HybridSolver.jl:240-260) double-buffered.
@@ -227,6 +246,16 @@ class NegElboPlan:
 
     def use_graphs(self, on: bool):
         self._check(self.lib.hvi_plan_use_graphs(self._h, int(on)))
+
+    def fused_phase_clocks(self, start_only=False):
+        """SM-clock stamps of the last single-launch evaluation at its phase boundaries (first call arms the stamping)."""
+        if start_only:
+            self._check(self.lib.hvi_plan_fused_phase_clocks(self._h, None))
+            return None
+        c = (C.c_int64 * 10)()
+        self._check(self.lib.hvi_plan_fused_phase_clocks(self._h, c))
+        names = ("gather", "zP_draws", "prologue", "g_fwd", "stream", "g_bwd", "reduce", "finalize", "adam")
+        return {n: int(c[i + 1] - c[i]) for i, n in enumerate(names)}
 
     def use_fused(self, on: bool):
         """Small batches with device draws run as one launch (k_small_iter); False forces the multi-kernel path."""

@@ -143,6 +143,15 @@ int64_t hvi_cor_count(const int32_t* cor_ends, int32_t n_cor_ends);
 int hvi_plan_set_data(hvi_plan* plan, int64_t n_site, const void* xM, const void* xP,
                       const void* y_o, const void* y_unc, int mem_kind);
 
+/* The same registration with arrays that are identical for every site passed as ONE column: xP_shared != 0: xP holds
+ * the 2 n_obs (or n_x) driver values shared by all sites (the reference keeps such drivers out of the per-site data with
+ * PBMPopulationGlobalApplicator, src/PBMApplicator.jl:305-375; the DoubleMM synthetic data are of this kind,
+ * src/DoubleMM/f_doubleMM.jl:12-13,375); y_unc_shared != 0: y_unc holds one column of n_obs log-variances.  The
+ * library expands them on the device, so a host batch costs 4·(n_covar + n_obs) instead of 4·(n_covar + 4 n_obs)
+ * bytes per site on the PCIe link (52 instead of 148 for DoubleMM). */
+int hvi_plan_set_data_bcast(hvi_plan* plan, int64_t n_site, const void* xM, const void* xP, int xP_shared,
+                            const void* y_o, const void* y_unc, int y_unc_shared, int mem_kind);
+
 /* Double-buffered registration for a minibatch loop (the DataLoader iteration of src/HybridSolver.jl:240-260):
  * hvi_plan_prefetch_data starts the upload of the NEXT batch from HOST memory on the plan's copy stream and returns
  * at once, so the transfer runs while the current batch is evaluated; hvi_plan_commit_data makes it the current
@@ -273,6 +282,10 @@ int hvi_plan_use_graphs(hvi_plan* plan, int on);
  * summation order of the per-block partial sums).  Applies to n_site <= 1024, n_site x n_MC <= 16384, the CUDA-core
  * applicator shapes, MeanHVIApproximationMat, no pbm covariates. */
 int hvi_plan_use_fused(hvi_plan* plan, int on);
+/* Profiling aid of that path: the first call (clocks may be NULL) switches the stamping on; later calls return the
+ * SM-clock stamps of the last single-launch evaluation at its phase boundaries: start, gather, global-block draws,
+ * prologue, g forward, streaming phase, g backward, reductions, finalize, Adam. */
+int hvi_plan_fused_phase_clocks(hvi_plan* plan, int64_t clocks[10]);
 int hvi_adam_phi_dev(hvi_plan* plan, void** phi_dev);
 int hvi_adam_get_phi(hvi_plan* plan, void* phi_host);
 

@@ -61,3 +61,16 @@ for dtype in ("f32", "f64"):
             dt = (time.perf_counter() - t0) / n
             print(f"{dtype} n_batch={bs:4d} n_MC={M:3d} graphs={graphs!s:5}: {dt * 1e6:8.1f} us per iteration  "
                   f"loss {np.nanmean(tr[:40]):.4g} -> {np.nanmean(tr[-40:]):.4g}", flush=True)
+
+# where the single launch spends its time: SM clocks between the phase boundaries of k_small_iter (thread 0)
+print("phase clocks of the single-launch iteration (SM cycles; 1965 MHz):")
+for dtype in ("f32", "f64"):
+    for bs, M in ((20, 3), (200, 12)):
+        prob = hvi_b200.DoubleMMCase(dtype=dtype)
+        data = hvi_b200.gen_hybridproblem_synthetic(prob, 800)
+        plan = hvi_b200.NegElboPlan(prob)
+        plan.set_dataset(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+        plan.adam_init(prob.init_ϕ(), eta=0.02)
+        plan.fused_phase_clocks(start_only=True)
+        plan.adam_run_minibatches(50, M, bs, seed0=0)
+        print(f"{dtype} n_batch={bs} n_MC={M}: {plan.fused_phase_clocks()}", flush=True)

@@ -78,3 +78,25 @@ def test_prefetch_on_a_fresh_plan():
     ref.set_data(b["xM"], b["xP"])
     y2, _, θMs2, ent2 = ref.predict_hvi(ϕ, n_sample_pred=8, seed=3)
     assert np.array_equal(y, y2) and np.array_equal(θMs, θMs2) and ent == ent2
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_broadcast_registration_equals_full_arrays(dtype):
+    """drivers and observation uncertainty shared by all sites given as one column (hvi_plan_set_data_bcast): identical
+    results to the full (rows x n_site) arrays, for the value + gradient and for the prediction path"""
+    prob = hvi_b200.DoubleMMCase(dtype=dtype)
+    nb, M = 1234, 8
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=6)         # DoubleMM: same drivers for every site
+    assert np.all(data["xP"] == data["xP"][:, :1]) and np.all(data["y_unc"] == data["y_unc"][:, :1])
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
+    ϕ = prob.init_ϕ(perturbed=True)
+    full = hvi_b200.NegElboPlan(prob)
+    full.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    ref = full.neg_elbo_withgradient(ϕ, zP, zMs)
+    for xs, us in ((True, True), (True, False), (False, True)):
+        plan = hvi_b200.NegElboPlan(prob)
+        plan.set_data_bcast(data["xM"], data["xP"][:, :1] if xs else data["xP"], data["y_o"],
+                            data["y_unc"][:, 0] if us else data["y_unc"])
+        got = plan.neg_elbo_withgradient(ϕ, zP, zMs)
+        assert got[0] == ref[0] and np.array_equal(got[2], ref[2])
+        assert np.array_equal(plan.predict_hvi(ϕ, zP, zMs)[0], full.predict_hvi(ϕ, zP, zMs)[0])
