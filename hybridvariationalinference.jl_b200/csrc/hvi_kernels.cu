@@ -15,112 +15,11 @@
 
 #include "hvi_internal.cuh"
 #include "hvi_rng.cuh"
+#include "hvi_dev.cuh"
+#include "hvi_stream.cuh"
 
 namespace hvi {
 
-// ---------------------------------------------------------------------------------------
-// small device helpers
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ float rcp_fast(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
-// ex2.approx of x·log2(e): relative error ≈ 2^-22 plus |x|·6e-8 from the argument rounding
-__device__ __forceinline__ float exp_t(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
-  return r;
-}
-__device__ __forceinline__ double exp_t(double x) { return exp(x); }
-__device__ __forceinline__ float log_t(float x) { return logf(x); }
-__device__ __forceinline__ double log_t(double x) { return log(x); }
-__device__ __forceinline__ float tanh_t(float x) { return tanhf(x); }
-__device__ __forceinline__ double tanh_t(double x) { return tanh(x); }
-__device__ __forceinline__ float ndtri_t(float p) { return normcdfinvf(p); }
-__device__ __forceinline__ double ndtri_t(double p) { return normcdfinv(p); }
-__device__ __forceinline__ float log1p_t(float x) { return log1pf(x); }
-__device__ __forceinline__ double log1p_t(double x) { return log1p(x); }
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <typename T>
-__device__ __forceinline__ T warp_sum(T v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// two-wide values: float2 maps to the packed FP32 instructions of sm_100 (FADD2/FMUL2/FFMA2 --
-// same FLOP rate as the scalar forms on B200, half the issue slots), double2 is plain pairs
-template <typename T> struct PairT;
-template <> struct PairT<float> { using type = float2; };
-template <> struct PairT<double> { using type = double2; };
-__device__ __forceinline__ float2 mk2(float x, float y) { return make_float2(x, y); }
-__device__ __forceinline__ double2 mk2(double x, double y) { return make_double2(x, y); }
-__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ double2 padd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 pmul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
-__device__ __forceinline__ double2 pfma(double2 a, double2 b, double2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
-
-template <typename T>
-__device__ __forceinline__ T act_f(int act, T z) {
-  if (act == HVI_ACT_TANH) return tanh_t(z);
-  if (act == HVI_ACT_LOGISTIC) return T(1) / (T(1) + exp_t(-z));
-  return z;
-}
-template <typename T>
-__device__ __forceinline__ T act_d(int act, T a) {
-  if (act == HVI_ACT_TANH) return T(1) - a * a;
-  if (act == HVI_ACT_LOGISTIC) return a * (T(1) - a);
-  return T(1);
-}
-
-// θ = T(ζ) with the reference's clamp (src/elbo.jl:783-808; bijectors_utils.jl:10-23,38-52) fused
-// with the prior on θ (src/elbo.jl:203-260).  Outputs: θ, dθ/dζ (0 when clamped), the variable part
-// of −logpdf(prior, θ) and its derivative w.r.t. ζ, the log-Jacobian term and its derivative.
-template <typename T>
-__device__ __forceinline__ void transform_prior(int tr, int pk, T a, T ib, T lo, T hi, T zeta, T& th, T& dth, T& pv,
-                                                T& dz, T& lj) {
-  T raw, d, dlj, dpz;
-  if (tr == HVI_TR_EXP) {
-    raw = exp_t(zeta); d = raw; lj = zeta; dlj = T(1);
-  } else if (tr == HVI_TR_LOGISTIC) {
-    raw = T(1) / (T(1) + exp_t(-zeta)); d = raw * (T(1) - raw);
-    lj = -(log1p_t(exp_t(-zeta)) + log1p_t(exp_t(zeta))); dlj = T(1) - T(2) * raw;
-  } else {
-    raw = zeta; d = T(1); lj = T(0); dlj = T(0);
-  }
-  th = fmin(hi, raw);
-  th = fmax(lo, th);
-  const bool uncl = (th == raw);
-  dth = uncl ? d : T(0);
-  if (pk == HVI_PR_LOGNORMAL) {
-    const T lt = (tr == HVI_TR_EXP && uncl) ? zeta : log_t(th);
-    const T u = (lt - a) * ib;
-    pv = lt + T(0.5) * u * u;
-    // d/dθ = (1 + u·ib)/θ ; times dθ/dζ
-    if (tr == HVI_TR_EXP) { dz = uncl ? u * ib : T(-1); return; }   // (1 + u·ib) − 1 when unclamped
-    dpz = (T(1) + u * ib) / th * dth;
-  } else if (pk == HVI_PR_NORMAL) {
-    const T u = (th - a) * ib;
-    pv = T(0.5) * u * u;
-    dpz = u * ib * dth;
-  } else {
-    pv = T(0); dpz = T(0);
-  }
-  dz = dpz - dlj;
-}
 
 // ---------------------------------------------------------------------------------------
 // set_data: re-tile one batch into site records and fold the ϕ-independent part of the
@@ -871,445 +770,6 @@ static bool mlp3_match(const Cfg<T>& c, int ni, int h1, int h2, int no) {
 }
 
 // ---------------------------------------------------------------------------------------
-// The fused streaming kernel.  One thread owns one site for all draws; a warp owns a tile of
-// 32 consecutive sites.  The tile's draws ξ (32·NM rows of M values, contiguous in HBM) are
-// staged through warp-private shared memory with coalesced 16-byte cp.async and read back
-// transposed; 16-byte chunks are rotated by the owning lane so that the transposed LDS.128 is
-// bank-conflict free.  Everything between μ_ζ and (μ̄_ζ, partial sums of the shared-parameter
-// cotangents) stays in registers.
-//
-// Traits: the PBM slot map, the bijector codes and the prior kinds are either read from the
-// constant bank at run time (DynTraits: any configuration) or baked in at compile time
-// (StaTraits: the named configurations below), which removes every select from the draw loop.
-// ---------------------------------------------------------------------------------------
-__host__ __device__ constexpr int ut(int j, int k) { return k * (k + 1) / 2 + j; }  // packed upper incl. diag
-
-struct DynTraits {
-  static constexpr bool STATIC = false;
-};
-// SLOTS: 4 nibbles (r0, r1, K1, K2), nibble = slot code + 1 (0 = fixed value);
-// TRM: 2 bits per θM column (bijector code); PRM: 2 bits per θM column (prior kind, 0 if omitted)
-template <uint32_t SLOTS, uint32_t TRM, uint32_t PRM>
-struct StaTraits {
-  static constexpr bool STATIC = true;
-  static constexpr uint32_t slots = SLOTS, trm = TRM, prm = PRM;
-};
-
-template <class TR, typename T>
-__device__ __forceinline__ int tr_slot(const Cfg<T>& cfg, int s) {
-  if constexpr (TR::STATIC) return (int)((TR::slots >> (4 * s)) & 15u) - 1;
-  else return cfg.slot_code[s];
-}
-template <class TR, typename T>
-__device__ __forceinline__ int tr_transM(const Cfg<T>& cfg, int k) {
-  if constexpr (TR::STATIC) return (int)((TR::trm >> (2 * k)) & 3u);
-  else return cfg.transM[k];
-}
-template <class TR, typename T>
-__device__ __forceinline__ int tr_priorM(const Cfg<T>& cfg, int k) {
-  if constexpr (TR::STATIC) return (int)((TR::prm >> (2 * k)) & 3u);
-  else return cfg.omit_priors ? HVI_PR_NONE : cfg.prM_kind[k];
-}
-
-// all θM columns are Exp-transformed with LogNormal priors (known at compile time)
-template <class TR, int NM>
-__host__ __device__ constexpr bool all_exp_ln() {
-  if constexpr (TR::STATIC) {
-    for (int k = 0; k < NM; k++)
-      if (((TR::trm >> (2 * k)) & 3u) != HVI_TR_EXP || ((TR::prm >> (2 * k)) & 3u) != HVI_PR_LOGNORMAL) return false;
-    return true;
-  } else {
-    return false;
-  }
-}
-
-// per-draw block of the global parameters, one record per draw: θP[NP], dθP/dζP[NP], zP[NP]
-template <typename T, int NP, int NM, int NO>
-struct SiteState {
-  static constexpr int NOP = (NO + 1) / 2;   // observation pairs
-  typename PairT<T>::type S1[NOP], S2[NOP], S12[NOP], nyo[NOP], w[NOP];   // nyo = −y_o
-  typename PairT<T>::type nly2;  // Σ w·res² over the draws, two lanes
-  T mu[NM];
-  T sU[tri(NM)];                 // σ[k]·U[j,k]
-  T smu[NM], sz[tri(NM)];        // Σ_m ζ̄[k],  Σ_m ζ̄[k]·z[j]
-  T aP[NP > 0 ? NP : 1], cP[NP > 0 ? tri(NP) : 1];
-  T prior, lj;                   // Σ of the generic prior terms / of all log-Jacobian terms
-  T u2, ljln;                    // Exp+LogNormal columns: Σ u² and Σ ζ  (prior = ζ + u²/2 when unclamped)
-};
-
-// f_doubleMM + logden_normal + adjoint w.r.t. (r0, r1, K1, K2), all observations of one site
-// and one draw:  y = r0 + r1·S1/(K1+S1)·S2/(K2+S2)   (src/DoubleMM/f_doubleMM.jl:137)
-// accumulates Σ w·res² into st.nly2; pbar = (Σ dy, Σ dy·ab, −r1 Σ dy·ab/d1, −r1 Σ dy·ab/d2),
-// dy = w·res.  14 FP32 operations + 1 reciprocal per observation, two observations per
-// instruction.
-template <typename T, int NP, int NM, int NO>
-__device__ __forceinline__ void obs_loop(SiteState<T, NP, NM, NO>& st, const T (&par)[4], T (&pbar)[4]) {
-  using P = typename PairT<T>::type;
-  const P r0 = mk2(par[0], par[0]), r1 = mk2(par[1], par[1]);
-  const P k1 = mk2(par[2], par[2]), k2 = mk2(par[3], par[3]);
-  P g0 = mk2(T(0), T(0)), g1 = g0, gA = g0, gB = g0;
-#pragma unroll
-  for (int o = 0; o < SiteState<T, NP, NM, NO>::NOP; o++) {
-    const P d1 = padd(k1, st.S1[o]), d2 = padd(k2, st.S2[o]);
-    const P p = pmul(d1, d2);
-    const P rp = mk2(rcp_fast(p.x), rcp_fast(p.y));
-    const P ab = pmul(st.S12[o], rp);
-    const P y = pfma(r1, ab, r0);
-    const P res = padd(y, st.nyo[o]);
-    const P dy = pmul(res, st.w[o]);
-    st.nly2 = pfma(res, dy, st.nly2);
-    g0 = padd(g0, dy);
-    const P t = pmul(dy, ab);
-    g1 = padd(g1, t);
-    const P u = pmul(t, rp);
-    gA = pfma(u, d2, gA);
-    gB = pfma(u, d1, gB);
-  }
-  pbar[0] = g0.x + g0.y;
-  pbar[1] = g1.x + g1.y;
-  pbar[2] = -par[1] * (gA.x + gA.y);
-  pbar[3] = -par[1] * (gB.x + gB.y);
-}
-
-// mud: the mean μ_ζ of this draw (st.mu without pbm covariates; g([xM; ζP_m]) with them,
-// src/elbo.jl:508-515); zbout: cotangent ζ̄M of this draw (unscaled by 1/n_MC)
-template <class TR, typename T, int NP, int NM, int NO>
-__device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, NO>& st, const T (&z)[NM],
-                                        const T* __restrict__ pd, const T (&mud)[NM], T (&zbout)[NM]) {
-  T th[NM], dth[NM], dz[NM];  // dz = d(prior − logjac)/dζ
-#pragma unroll
-  for (int k = 0; k < NM; k++) {
-    T zeta = mud[k];
-#pragma unroll
-    for (int j = 0; j <= k; j++) zeta = fma(st.sU[ut(j, k)], z[j], zeta);
-    const int trk = tr_transM<TR>(cfg, k), pkk = tr_priorM<TR>(cfg, k);
-    if (trk == HVI_TR_EXP && pkk == HVI_PR_LOGNORMAL) {
-      // θ = exp(ζ) with a LogNormal prior: −logpdf = ζ + ½u² + const, u = (ζ − μ)/σ; minus the
-      // log-Jacobian ζ the ζ's cancel in the gradient: d/dζ = u/σ
-      // the clamp θ ∈ [√floatmin, √floatmax] (src/elbo.jl:797-798) is applied to ζ before the
-      // exponential (same θ, no branch, no logarithm): ζc = clamp(ζ, ln lo, ln hi)
-      const T zc = fmax(cfg.ln_clamp_lo, fmin(cfg.ln_clamp_hi, zeta));
-      th[k] = exp_t(zc);
-      const bool uncl = (zc == zeta);
-      if (!uncl) st.prior += zc - zeta;   // log θ = ζc when clamped; predicated, almost never taken
-      const T u = fma(zc, cfg.prM_ib[k], cfg.prM_nab[k]);
-      st.u2 = fma(u, u, st.u2);
-      st.lj += zeta;
-      if constexpr (!all_exp_ln<TR, NM>()) st.ljln += zeta;
-      dth[k] = uncl ? th[k] : T(0);
-      dz[k] = uncl ? u * cfg.prM_ib[k] : T(-1);
-    } else {
-      T pv, lj;
-      transform_prior<T>(trk, pkk, cfg.prM_a[k], cfg.prM_ib[k], cfg.clamp_lo, cfg.clamp_hi, zeta, th[k], dth[k], pv,
-                         dz[k], lj);
-      st.prior += pv;
-      st.lj += lj;
-    }
-  }
-  T thp[NP > 0 ? NP : 1], gp[NP > 0 ? NP : 1], zp[NP > 0 ? NP : 1];
-  if constexpr (NP == 2 && sizeof(T) == 4) {
-    const float4 v = *reinterpret_cast<const float4*>(pd);
-    const float2 v2 = *reinterpret_cast<const float2*>(pd + 4);
-    thp[0] = v.x; thp[1] = v.y; gp[0] = v.z; gp[1] = v.w; zp[0] = v2.x; zp[1] = v2.y;
-  } else {
-#pragma unroll
-    for (int j = 0; j < NP; j++) { thp[j] = pd[j]; gp[j] = pd[NP + j]; zp[j] = pd[2 * NP + j]; }
-  }
-  // gather (r0, r1, K1, K2) by slot (src/PBMApplicator.jl:234-239,283-287)
-  T par[4];
-#pragma unroll
-  for (int s = 0; s < 4; s++) {
-    T v = cfg.slot_fix[s];
-    const int c = tr_slot<TR>(cfg, s);
-#pragma unroll
-    for (int j = 0; j < NP; j++) v = (c == j) ? thp[j] : v;
-#pragma unroll
-    for (int k = 0; k < NM; k++) v = (c == NP + k) ? th[k] : v;
-    par[s] = v;
-  }
-  T pbar[4];
-  obs_loop<T, NP, NM, NO>(st, par, pbar);
-  T thbar[NP + NM];
-#pragma unroll
-  for (int q = 0; q < NP + NM; q++) {
-    T v = T(0);
-    bool first = true;
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-      if constexpr (TR::STATIC) {
-        if (tr_slot<TR>(cfg, s) == q) { v = first ? pbar[s] : v + pbar[s]; first = false; }
-      } else {
-        v += (tr_slot<TR>(cfg, s) == q) ? pbar[s] : T(0);
-      }
-    }
-    thbar[q] = v;
-  }
-#pragma unroll
-  for (int k = 0; k < NM; k++) {
-    const T zb = fma(thbar[NP + k], dth[k], dz[k]);
-    zbout[k] = zb;
-    st.smu[k] += zb;
-#pragma unroll
-    for (int j = 0; j <= k; j++) st.sz[ut(j, k)] = fma(zb, z[j], st.sz[ut(j, k)]);
-  }
-#pragma unroll
-  for (int j = 0; j < NP; j++) {
-    const T zb = thbar[j] * gp[j];
-    st.aP[j] += zb;
-#pragma unroll
-    for (int jj = 0; jj <= j; jj++) st.cP[ut(jj, j)] = fma(zb, zp[jj], st.cP[ut(jj, j)]);
-  }
-}
-
-constexpr int STREAM_THREADS_MAX = 384;
-
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, bool PBM, bool RNG>
-__device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<T>& a, unsigned char* smem_raw, int bid,
-                                            int nblk) {
-  constexpr int CH = 16 / sizeof(T);  // elements per 16-byte chunk
-  constexpr int MC = 8 * CH;          // draws per stage (one 128-byte row)
-  constexpr int NUM = tri(NM), NUP = tri(NP);
-  constexpr int NACC = nacc(NP, NM);
-  constexpr int NWARP = STREAM_THREADS / 32;
-  constexpr int PD = pd_stride(NP);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T* ztile = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (32 * NM * MC);
-  double* wacc = reinterpret_cast<double*>(smem_raw + (size_t)NWARP * 32 * NM * MC * sizeof(T)) + warp * NACC;
-  T* spd = reinterpret_cast<T*>(smem_raw + (size_t)NWARP * 32 * NM * MC * sizeof(T) + (size_t)NWARP * NACC * sizeof(double));
-  const int M = a.M;
-  // per-draw global-parameter records: shared memory if they fit, else read from global
-  const T* pdbase = a.pd;
-  if (a.pd_in_smem) {
-    for (int e = threadIdx.x; e < M * PD; e += STREAM_THREADS) spd[e] = a.pd[e];
-    pdbase = spd;
-  }
-  if (lane == 0)
-    for (int i = 0; i < NACC; i++) wacc[i] = 0.0;
-  __syncthreads();
-
-  SiteState<T, NP, NM, NO> st;
-  T cA[NM], cB[NM], U[NUM];
-#pragma unroll
-  for (int k = 0; k < NM; k++) {
-    cA[k] = a.ec->coefA[k];
-    cB[k] = a.ec->coefB[k];
-#pragma unroll
-    for (int j = 0; j <= k; j++) U[ut(j, k)] = a.ec->UM[j][k];
-  }
-  const T wM = T(1) / T(M);
-  const bool staged = a.staged != 0;
-  const uint64_t seed = (RNG && a.seed_dev) ? (uint64_t)*a.seed_dev : a.seed;
-  const int64_t ntiles = (a.nb + 31) / 32;
-  for (int64_t tile = (int64_t)bid * NWARP + warp; tile < ntiles; tile += (int64_t)nblk * NWARP) {
-    const int64_t site = tile * 32 + lane;
-    const bool active = site < a.nb;
-    const int64_t isite = (cfg.sepvar && active && a.i_sites) ? a.i_sites[site] : site;   // global site index
-    {
-      const T* r = a.rec + (tile * 4 * NO) * 32 + lane;
-      constexpr int NOP = SiteState<T, NP, NM, NO>::NOP;
-#pragma unroll
-      for (int o = 0; o < NOP; o++) {
-        const bool two = (2 * o + 1 < NO);   // odd n_obs: the last pair is padded with weight 0
-        const int o0 = 2 * o, o1 = two ? 2 * o + 1 : 2 * o;
-        st.S1[o] = mk2(r[(0 * NO + o0) * 32], r[(0 * NO + o1) * 32]);
-        st.S2[o] = mk2(r[(1 * NO + o0) * 32], r[(1 * NO + o1) * 32]);
-        st.nyo[o] = mk2(-r[(2 * NO + o0) * 32], -r[(2 * NO + o1) * 32]);
-        st.w[o] = mk2(r[(3 * NO + o0) * 32], two ? r[(3 * NO + o1) * 32] : T(0));
-        st.S12[o] = pmul(st.S1[o], st.S2[o]);
-      }
-    }
-    T ls[NM], sig[NM];
-#pragma unroll
-    for (int k = 0; k < NM; k++) {
-      st.mu[k] = active ? a.mu[site * NM + k] : T(0);
-      // log σ²: intercept + slope·μ_ζ (src/elbo.jl:652-653) or the site's own parameter (src/elbo_sepvec.jl:23)
-      ls[k] = (cfg.sepvar && active) ? a.phi[cfg.o_coef + isite * NM + k] : fma(cB[k], st.mu[k], cA[k]);
-      sig[k] = exp_t(T(0.5) * ls[k]);
-      st.smu[k] = T(0);
-#pragma unroll
-      for (int j = 0; j <= k; j++) st.sU[ut(j, k)] = sig[k] * U[ut(j, k)];
-    }
-#pragma unroll
-    for (int i = 0; i < NUM; i++) st.sz[i] = T(0);
-#pragma unroll
-    for (int i = 0; i < (NP > 0 ? NP : 1); i++) st.aP[i] = T(0);
-#pragma unroll
-    for (int i = 0; i < (NP > 0 ? NUP : 1); i++) st.cP[i] = T(0);
-    st.prior = st.lj = st.u2 = st.ljln = T(0);
-    st.nly2 = mk2(T(0), T(0));
-
-    // three sources of the draws ξ of this tile, one copy of the per-draw code:
-    //   mode 1: cp.async staging through shared memory (two half-row stages of MCS draws in flight)
-    //   mode 2: generated in registers (Philox + Box-Muller), no memory traffic at all
-    //   mode 0: direct global loads (n_MC not a multiple of the 16-byte chunk)
-    {
-      constexpr int MCS = MC / 2, QS = 4;
-      const int mode = RNG ? 2 : (staged ? 1 : 0);
-      const T* gz = a.zMs + (size_t)tile * 32 * NM * M;  // row r of the tile at gz + r*M
-      const int rows_valid = (int)(a.nb - tile * 32 < 32 ? a.nb - tile * 32 : 32) * NM;
-      const int nst = mode == 1 ? (M + MCS - 1) / MCS : 1;
-      auto issue = [&](int st_) {
-        const int m0 = st_ * MCS;
-        const int nch = ((M - m0) < MCS ? (M - m0) : MCS) / CH;
-        T* buf = ztile + (st_ & 1) * (32 * NM * MCS);
-#pragma unroll
-        for (int e0 = 0; e0 < 32 * NM * QS; e0 += 32) {
-          const int e = e0 + lane;
-          const int row = e >> 2, q = e & 3, owner = row / NM;
-          if (q < nch && row < rows_valid)
-            cp_async16(buf + row * MCS + ((q + owner) & 3) * CH, gz + (size_t)row * M + m0 + q * CH);
-        }
-        cp_async_commit();
-      };
-      if (mode == 1) { __syncwarp(); issue(0); }
-      for (int st_ = 0; st_ < nst; st_++) {
-        if (mode == 1) {
-          if (st_ + 1 < nst) { issue(st_ + 1); cp_async_wait_group<1>(); }
-          else cp_async_wait_group<0>();
-          __syncwarp();
-        }
-        const int m0 = mode == 1 ? st_ * MCS : 0;
-        const int nd = mode == 1 ? ((M - m0) < MCS ? (M - m0) : MCS) : M;   // draws of this stage
-        const T* buf = ztile + (st_ & 1) * (32 * NM * MCS);
-        if (active) {
-          const int nfull = nd / CH;
-          for (int q = 0; q < nfull; q++) {   // full chunks of CH draws, no guards
-            const int mq = m0 + q * CH;
-            T zc[NM][CH];
-            if (mode == 1) {
-#pragma unroll
-              for (int k = 0; k < NM; k++) {
-                const T* src = buf + (lane * NM + k) * MCS + ((q + lane) & 3) * CH;
-                if constexpr (sizeof(T) == 4) {
-                  const float4 v = *reinterpret_cast<const float4*>(src);
-                  zc[k][0] = v.x; zc[k][1] = v.y; zc[k][2] = v.z; zc[k][3] = v.w;
-                } else {
-                  const double2 v = *reinterpret_cast<const double2*>(src);
-                  zc[k][0] = v.x; zc[k][1] = v.y;
-                }
-              }
-            } else if (mode == 2) {
-#pragma unroll
-              for (int k = 0; k < NM; k++) {
-                float n4[4];
-                normal4(seed, (uint64_t)(a.col_offset + site * NM + k), mq / 4, n4);
-#pragma unroll
-                for (int d = 0; d < CH; d++) zc[k][d] = (T)n4[(mq % 4) + d];
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < NM; k++)
-#pragma unroll
-                for (int d = 0; d < CH; d++) zc[k][d] = a.zMs[((size_t)site * NM + k) * M + mq + d];
-            }
-            const T* pd = pdbase + (size_t)mq * PD;
-            T mud[CH][NM];
-#pragma unroll
-            for (int d = 0; d < CH; d++)
-#pragma unroll
-              for (int k = 0; k < NM; k++) mud[d][k] = PBM ? a.MU[((size_t)(mq + d) * NM + k) * a.nb + site] : st.mu[k];
-#pragma unroll
-            for (int d = 0; d < CH; d++) {
-              T z[NM], zb[NM];
-#pragma unroll
-              for (int k = 0; k < NM; k++) z[k] = zc[k][d];
-              do_draw<TR, T, NP, NM, NO>(cfg, st, z, pd + d * PD, mud[d], zb);
-              if constexpr (PBM) {
-#pragma unroll
-                for (int k = 0; k < NM; k++) a.MUBAR[((size_t)(mq + d) * NM + k) * a.nb + site] = wM * zb[k];
-              }
-            }
-          }
-          // remaining draws (n_MC not a multiple of the chunk; never in mode 1), one at a time
-#pragma unroll 1
-          for (int m = m0 + nfull * CH; m < m0 + nd; m++) {
-            T z[NM], zb[NM], mud[NM];
-#pragma unroll
-            for (int k = 0; k < NM; k++) {
-              if (mode == 2) {
-                float n4[4];
-                normal4(seed, (uint64_t)(a.col_offset + site * NM + k), m / 4, n4);
-                z[k] = (T)(m % 4 == 0 ? n4[0] : m % 4 == 1 ? n4[1] : m % 4 == 2 ? n4[2] : n4[3]);
-              } else {
-                z[k] = a.zMs[((size_t)site * NM + k) * M + m];
-              }
-              mud[k] = PBM ? a.MU[((size_t)m * NM + k) * a.nb + site] : st.mu[k];
-            }
-            do_draw<TR, T, NP, NM, NO>(cfg, st, z, pdbase + (size_t)m * PD, mud, zb);
-            if constexpr (PBM) {
-#pragma unroll
-              for (int k = 0; k < NM; k++) a.MUBAR[((size_t)m * NM + k) * a.nb + site] = wM * zb[k];
-            }
-          }
-        }
-        if (mode == 1) __syncwarp();
-      }
-    }
-
-    // end of site: σ-path, entropy, μ̄_ζ  (SURVEY Appendix A adjoint)
-    T acc[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; i++) acc[i] = T(0);
-    if (active) {
-      acc[ACC_NLY] = st.nly2.x + st.nly2.y; acc[ACC_LJ] = st.lj;
-      acc[ACC_PRIOR] = st.prior + T(0.5) * st.u2 + (all_exp_ln<TR, NM>() ? st.lj : st.ljln);
-#pragma unroll
-      for (int k = 0; k < NM; k++) {
-        T sr = T(0);                                      // Σ_m ζ̄[k,m]·r[k,m]
-#pragma unroll
-        for (int j = 0; j <= k; j++) sr = fma(st.sU[ut(j, k)], st.sz[ut(j, k)], sr);
-        const T lsb = T(0.5) * wM * sr - T(0.5);          // −½ from the entropy
-        acc[ACC_LOGSIG] += T(0.5) * ls[k];
-        if (cfg.sepvar) {
-          // the gradient w.r.t. this site's own log-variance goes straight to its slot of ∇ϕ; the
-          // slot of ā counts non-finite entries instead
-          const int64_t o = (int64_t)cfg.o_coef + isite * NM + k;
-          a.out[o] = (double)lsb;
-          if (a.grad_T) a.grad_T[o] = lsb;
-          acc[ACC_FIRST_VEC + k] = isfinite(lsb) ? T(0) : T(1);
-          a.mubar[site * NM + k] = PBM ? T(0) : wM * st.smu[k];
-        } else {
-          acc[ACC_FIRST_VEC + k] = lsb;
-          acc[ACC_FIRST_VEC + NM + k] = lsb * st.mu[k];
-          // with pbm covariates the pass-1 mean feeds σ only (src/elbo.jl:491-495)
-          a.mubar[site * NM + k] = PBM ? lsb * cB[k] : fma(wM, st.smu[k], lsb * cB[k]);
-        }
-#pragma unroll
-        for (int j = 0; j <= k; j++) acc[ACC_FIRST_VEC + 2 * NM + ut(j, k)] = sig[k] * st.sz[ut(j, k)];
-      }
-#pragma unroll
-      for (int j = 0; j < NP; j++) acc[ACC_FIRST_VEC + 2 * NM + NUM + j] = st.aP[j];
-#pragma unroll
-      for (int i = 0; i < NUP; i++) acc[ACC_FIRST_VEC + 2 * NM + NUM + NP + i] = st.cP[i];
-    }
-#pragma unroll
-    for (int i = 0; i < NACC; i++) {
-      const T v = warp_sum(acc[i]);
-      if (lane == 0) wacc[i] += (double)v;
-    }
-  }
-  // one row of partial sums per block: the warps' double accumulators added in warp order
-  __syncthreads();
-  {
-    const double* w0 = reinterpret_cast<const double*>(smem_raw + (size_t)NWARP * 32 * NM * MC * sizeof(T));
-    for (int i = threadIdx.x; i < NACC; i += STREAM_THREADS) {
-      double s = 0.0;
-      for (int w = 0; w < NWARP; w++) s += w0[w * NACC + i];
-      a.partials[(size_t)bid * NACC + i] = s;
-    }
-  }
-}
-
-
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool RNG>
-__global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_constant__ Cfg<T> cfg,
-                                                                 const __grid_constant__ StreamArgs<T> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  stream_body<TR, T, NP, NM, NO, STREAM_THREADS, PBM, RNG>(cfg, a, smem_raw, blockIdx.x, gridDim.x);
-}
-
-
-// ---------------------------------------------------------------------------------------
 // finalize: one block.  Fixed-order reduction of all partial sums, global-block terms,
 // Cholesky adjoint, scatter into the layout of ϕ.
 // out[0..nphi) gradient, out[nphi..nphi+6) components, out[nphi+6] nL, out[nphi+7] non-finite count
@@ -1679,14 +1139,6 @@ __global__ void __launch_bounds__(256) k_generate_zeta(const __grid_constant__ C
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
-#define HVI_LAUNCH_CHECK()                         \
-  do {                                             \
-    cudaError_t e_ = cudaGetLastError();           \
-    if (e_ != cudaSuccess) return e_;              \
-    if (L.counter) ++*L.counter;                   \
-  } while (0)
-
-int stream_max_rows(int sm_count) { return sm_count * 8 * (STREAM_THREADS_MAX / 32); }
 int mlp_bwd_max_blocks(int sm_count) { return sm_count * 4; }
 
 template <typename T>
@@ -1823,116 +1275,6 @@ cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, con
   HVI_LAUNCH_CHECK();
   *nblk_out = blocks;
   return cudaSuccess;
-}
-
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool RNG>
-static cudaError_t launch_stream_cfg2(const Launch& L, const Cfg<T>& cfg, StreamArgs<T> a, int* nrows_out, int nrows_max) {
-  constexpr int CH = 16 / sizeof(T), MC = 8 * CH, NWARP = STREAM_THREADS / 32;
-  const size_t pd_bytes = (size_t)a.M * pd_stride(NP) * sizeof(T);
-  a.pd_in_smem = (NP > 0 && pd_bytes <= 16 * 1024) ? 1 : 0;
-  const size_t smem = (size_t)NWARP * 32 * NM * MC * sizeof(T) + (size_t)NWARP * nacc(NP, NM) * sizeof(double) +
-                      (a.pd_in_smem ? pd_bytes : 0) + 16;
-  auto kern = k_stream<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, RNG>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, STREAM_THREADS, smem);
-  if (e != cudaSuccess) return e;
-  if (occ < 1) occ = 1;
-  const int64_t ntiles = (a.nb + 31) / 32;
-  int64_t blocks = (ntiles + NWARP - 1) / NWARP;
-  if (blocks > (int64_t)L.sm_count * occ) blocks = (int64_t)L.sm_count * occ;
-  if (blocks > nrows_max) blocks = nrows_max;
-  if (blocks < 1) blocks = 1;
-  kern<<<(int)blocks, STREAM_THREADS, smem, L.stream>>>(cfg, a);
-  HVI_LAUNCH_CHECK();
-  *nrows_out = (int)blocks;
-  return cudaSuccess;
-}
-
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM>
-static cudaError_t launch_stream_cfg(const Launch& L, const Cfg<T>& cfg, StreamArgs<T> a, int* nrows_out, int nrows_max) {
-  if (a.rng) return launch_stream_cfg2<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, true>(L, cfg, a, nrows_out, nrows_max);
-  return launch_stream_cfg2<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, false>(L, cfg, a, nrows_out, nrows_max);
-}
-
-// launch shape (measured at 2e6 sites x 64 draws, Float32, compile-time traits): one block of 256
-// threads per SM with up to 255 registers 0.84 ms; two blocks of 256 (128 registers) 0.90 ms; one block
-// of 384 (168 registers) 0.90 ms; five blocks of 128 (96 registers, spills) 1.15 ms.  The kernel is bound
-// by the FP32 pipe and by instruction latency, and registers buy the compiler room to interleave the
-// four unrolled draws -- that is worth more than resident warps.  HVI_STREAM_VARIANT = 1, 2, 3 selects
-// the other shapes for experiments.
-static int stream_variant() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("HVI_STREAM_VARIANT"); v = e ? atoi(e) : 0; }
-  return v;
-}
-
-template <class TR, typename T, int NP, int NM, int NO>
-static cudaError_t launch_stream_inst(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, int* nrows_out,
-                                      int nrows_max) {
-  const bool pbm = a.MU != nullptr;
-  if constexpr (sizeof(T) == 4) {
-    if constexpr (TR::STATIC) {
-      if (pbm) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, true>(L, cfg, a, nrows_out, nrows_max);
-      if (stream_variant() == 1) return launch_stream_cfg<TR, T, NP, NM, NO, 128, 5, false>(L, cfg, a, nrows_out, nrows_max);
-      if (stream_variant() == 2) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, false>(L, cfg, a, nrows_out, nrows_max);
-      if (stream_variant() == 3) return launch_stream_cfg<TR, T, NP, NM, NO, 384, 1, false>(L, cfg, a, nrows_out, nrows_max);
-      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1, false>(L, cfg, a, nrows_out, nrows_max);
-    } else {
-      if (pbm) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, true>(L, cfg, a, nrows_out, nrows_max);
-      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, false>(L, cfg, a, nrows_out, nrows_max);   // run-time traits: 1.41 ms vs 1.55 ms with 256 x 1
-    }
-  } else {
-    if (pbm) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1, true>(L, cfg, a, nrows_out, nrows_max);
-    return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1, false>(L, cfg, a, nrows_out, nrows_max);
-  }
-}
-
-#define HVI_STREAM_CASES(X) \
-  X(0, 2, 8) X(1, 2, 8) X(2, 2, 8) X(0, 3, 8) X(1, 3, 8) X(2, 3, 8) X(3, 2, 8) X(2, 1, 8) X(2, 2, 4)
-
-bool stream_supported(int nP, int nM, int nO) {
-#define X(P, M_, O) if (nP == P && nM == M_ && nO == O) return true;
-  HVI_STREAM_CASES(X)
-#undef X
-  return false;
-}
-
-// compile-time specialisations: (slots, bijectors of θM, priors of θM) of the named problems
-//   DoubleMMCase default (src/DoubleMM/f_doubleMM.jl:161-243): θP=(r0,K2), θM=(r1,K1), Exp, LogNormal
-//   test/test_HybridProblem.jl:32-111: same slots, transM=(identity, Exp), priors (Normal, LogNormal)
-using TraitsDoubleMM = StaTraits<0x2431u, 0x5u, 0xAu>;
-using TraitsDoubleMMNoPrior = StaTraits<0x2431u, 0x5u, 0x0u>;
-using TraitsTestHybridProblem = StaTraits<0x2431u, 0x4u, 0x9u>;
-
-template <typename T>
-static void traits_key(const Cfg<T>& cfg, uint32_t& slots, uint32_t& trm, uint32_t& prm) {
-  slots = trm = prm = 0;
-  for (int s = 0; s < 4; s++) slots |= (uint32_t)(cfg.slot_code[s] + 1) << (4 * s);
-  for (int k = 0; k < cfg.nM; k++) {
-    trm |= (uint32_t)cfg.transM[k] << (2 * k);
-    prm |= (uint32_t)(cfg.omit_priors ? 0 : cfg.prM_kind[k]) << (2 * k);
-  }
-}
-
-template <typename T>
-cudaError_t launch_stream(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, int* nrows_out, int nrows_max) {
-  if (cfg.nP == 2 && cfg.nM == 2 && cfg.nO == 8) {
-    uint32_t slots, trm, prm;
-    traits_key(cfg, slots, trm, prm);
-#define Y(TRAITS) \
-    if (slots == TRAITS::slots && trm == TRAITS::trm && prm == TRAITS::prm) \
-      return launch_stream_inst<TRAITS, T, 2, 2, 8>(L, cfg, a, nrows_out, nrows_max);
-    Y(TraitsDoubleMM) Y(TraitsDoubleMMNoPrior) Y(TraitsTestHybridProblem)
-#undef Y
-  }
-#define X(P, M_, O) \
-  if (cfg.nP == P && cfg.nM == M_ && cfg.nO == O) \
-    return launch_stream_inst<DynTraits, T, P, M_, O>(L, cfg, a, nrows_out, nrows_max);
-  HVI_STREAM_CASES(X)
-#undef X
-  return cudaErrorInvalidConfiguration;
 }
 
 template <typename T>
@@ -2349,7 +1691,6 @@ cudaError_t launch_small_iter(const Launch& L, const Cfg<T>& cfg, SmallArgs<T> a
   template cudaError_t launch_mlp_fwd<T>(const Launch&, const Cfg<T>&, const T*, const T*, int64_t, T*, int, const T*);  \
   template cudaError_t launch_mlp_bwd<T>(const Launch&, const Cfg<T>&, const T*, const T*, const T*, int64_t, double*,   \
                                          int*, int, int, const T*, double*);                                             \
-  template cudaError_t launch_stream<T>(const Launch&, const Cfg<T>&, const StreamArgs<T>&, int*, int);                  \
   template cudaError_t launch_finalize<T>(const Launch&, const Cfg<T>&, const T*, const T*, const T*,                    \
                                           const EvalConsts<T>*, const double*, int, const double*, int, const double*, int64_t, \
                                           int, double*, T*, double*, const double*, int, const double*, int, double*);                                                             \
