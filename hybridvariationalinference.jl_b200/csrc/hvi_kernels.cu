@@ -1587,7 +1587,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
   {
     StreamArgs<T> sa = a.st;
     sa.seed = seed; sa.seed_dev = nullptr; sa.rng = 1; sa.phi = a.phi;
-    stream_body<TR, T, NP, NM, NO, SMALL_THREADS, false, true>(cfg, sa, smem_raw, 0, 1);
+    stream_body<TR, T, NP, NM, NO, SMALL_THREADS, false, true, (NP > 0), false, true>(cfg, sa, smem_raw, 0, 1);
   }
   __syncthreads();
   HVI_STAMP();
@@ -1647,9 +1647,8 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
 
 template <typename T>
 static size_t small_iter_smem(const Cfg<T>& cfg, int M) {
-  constexpr int CH = 16 / sizeof(T), MC = 8 * CH, NWARP = SMALL_THREADS / 32;
-  const size_t stream = (size_t)NWARP * 32 * cfg.nM * MC * sizeof(T) + (size_t)NWARP * nacc(cfg.nP, cfg.nM) * sizeof(double) +
-                        (size_t)M * pd_stride(cfg.nP) * sizeof(T) + 16;
+  const size_t stream = stream_smem_bytes(sizeof(T), SMALL_THREADS / 32, cfg.nP, cfg.nM, cfg.nO,
+                                          cfg.nP > 0 ? (size_t)M * pd_stride(cfg.nP) : 0, true);
   const size_t mlp = mlp_bwd_smem(cfg);
   return stream > mlp ? stream : mlp;
 }

@@ -5,24 +5,39 @@
 
 namespace hvi {
 
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool RNG>
+// site-record prefetch only where it does not cost a resident block (64 draws of per-draw records assumed)
+template <typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB>
+__host__ __device__ constexpr bool stream_spf() {
+  return (size_t)MINB * stream_smem_bytes(sizeof(T), STREAM_THREADS / 32, NP, NM, NO, (size_t)64 * pd_stride(NP), true) <= (size_t)227 * 1024;
+}
+
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool RNG, bool ILVP = true>
 __global__ void __launch_bounds__(STREAM_THREADS, MINB) k_stream(const __grid_constant__ Cfg<T> cfg,
                                                                  const __grid_constant__ StreamArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  stream_body<TR, T, NP, NM, NO, STREAM_THREADS, PBM, RNG>(cfg, a, smem_raw, blockIdx.x, gridDim.x);
+  // two draws per pass of the observation loop only where the register budget carries it (Float32, one block per SM)
+  constexpr bool ILV = ILVP && sizeof(T) == 4 && MINB == 1;
+  stream_body<TR, T, NP, NM, NO, STREAM_THREADS, PBM, RNG, (NP > 0), ILV, stream_spf<T, NP, NM, NO, STREAM_THREADS, MINB>()>(
+      cfg, a, smem_raw, blockIdx.x, gridDim.x);
 }
-
 
 int stream_max_rows(int sm_count) { return sm_count * 8 * (STREAM_THREADS_MAX / 32); }
 
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool RNG>
+// largest n_MC whose per-draw records of the global parameters fit into the shared memory of one block per SM
+int stream_max_draws(size_t szT, int nP, int nM, int nO) {
+  if (nP == 0) return 1 << 30;
+  const size_t fixed = stream_smem_bytes(szT, 8, nP, nM, nO, 0, true);
+  return (int)(((size_t)227 * 1024 - fixed) / (pd_stride(nP) * szT));
+}
+
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool RNG, bool ILVP = true>
 static cudaError_t launch_stream_cfg2(const Launch& L, const Cfg<T>& cfg, StreamArgs<T> a, int* nrows_out, int nrows_max) {
-  constexpr int CH = 16 / sizeof(T), MC = 8 * CH, NWARP = STREAM_THREADS / 32;
-  const size_t pd_bytes = (size_t)a.M * pd_stride(NP) * sizeof(T);
-  a.pd_in_smem = (NP > 0 && pd_bytes <= 16 * 1024) ? 1 : 0;
-  const size_t smem = (size_t)NWARP * 32 * NM * MC * sizeof(T) + (size_t)NWARP * nacc(NP, NM) * sizeof(double) +
-                      (a.pd_in_smem ? pd_bytes : 0) + 16;
-  auto kern = k_stream<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, RNG>;
+  constexpr int NWARP = STREAM_THREADS / 32;
+  constexpr bool SPF = stream_spf<T, NP, NM, NO, STREAM_THREADS, MINB>();
+  a.pd_in_smem = NP > 0 ? 1 : 0;
+  const size_t smem = stream_smem_bytes(sizeof(T), NWARP, NP, NM, NO, NP > 0 ? (size_t)a.M * pd_stride(NP) : 0, SPF);
+  if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;   // n_MC beyond stream_max_draws
+  auto kern = k_stream<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, RNG, ILVP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -40,18 +55,18 @@ static cudaError_t launch_stream_cfg2(const Launch& L, const Cfg<T>& cfg, Stream
   return cudaSuccess;
 }
 
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM>
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, int MINB, bool PBM, bool ILVP = true>
 static cudaError_t launch_stream_cfg(const Launch& L, const Cfg<T>& cfg, StreamArgs<T> a, int* nrows_out, int nrows_max) {
-  if (a.rng) return launch_stream_cfg2<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, true>(L, cfg, a, nrows_out, nrows_max);
-  return launch_stream_cfg2<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, false>(L, cfg, a, nrows_out, nrows_max);
+  if (a.rng) return launch_stream_cfg2<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, true, ILVP>(L, cfg, a, nrows_out, nrows_max);
+  return launch_stream_cfg2<TR, T, NP, NM, NO, STREAM_THREADS, MINB, PBM, false, ILVP>(L, cfg, a, nrows_out, nrows_max);
 }
 
-// launch shape (measured at 2e6 sites x 64 draws, Float32, compile-time traits): one block of 256
-// threads per SM with up to 255 registers 0.84 ms; two blocks of 256 (128 registers) 0.90 ms; one block
-// of 384 (168 registers) 0.90 ms; five blocks of 128 (96 registers, spills) 1.15 ms.  The kernel is bound
-// by the FP32 pipe and by instruction latency, and registers buy the compiler room to interleave the
-// four unrolled draws -- that is worth more than resident warps.  HVI_STREAM_VARIANT = 1, 2, 3 selects
-// the other shapes for experiments.
+// launch shape (Float32, compile-time traits, 1e7 sites x 64 draws): one block of 384 threads per SM (168 registers,
+// three warps per scheduler) 3.65 ms; one block of 512 (128 registers) 3.70 ms; two blocks of 256 (128 registers)
+// 3.87 ms; one block of 256 with up to 255 registers 3.99 ms, 3.91 ms with two draws per pass of the observation loop.
+// Until the per-tile and per-stage overheads were cut (cross-tile prefetch, one-pass accumulator reduction, unguarded
+// cp.async addresses) the order was the reverse: registers for interleaving draws were worth more than resident
+// warps.  HVI_STREAM_VARIANT = 2, 4, 5, 6, 7 selects the other shapes for experiments.
 static int stream_variant() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("HVI_STREAM_VARIANT"); v = e ? atoi(e) : 0; }
@@ -65,10 +80,12 @@ static cudaError_t launch_stream_inst(const Launch& L, const Cfg<T>& cfg, const 
   if constexpr (sizeof(T) == 4) {
     if constexpr (TR::STATIC) {
       if (pbm) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, true>(L, cfg, a, nrows_out, nrows_max);
-      if (stream_variant() == 1) return launch_stream_cfg<TR, T, NP, NM, NO, 128, 5, false>(L, cfg, a, nrows_out, nrows_max);
       if (stream_variant() == 2) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, false>(L, cfg, a, nrows_out, nrows_max);
-      if (stream_variant() == 3) return launch_stream_cfg<TR, T, NP, NM, NO, 384, 1, false>(L, cfg, a, nrows_out, nrows_max);
-      return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1, false>(L, cfg, a, nrows_out, nrows_max);
+      if (stream_variant() == 4) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1, false, false>(L, cfg, a, nrows_out, nrows_max);
+      if (stream_variant() == 5) return launch_stream_cfg<TR, T, NP, NM, NO, 384, 1, false, true>(L, cfg, a, nrows_out, nrows_max);
+      if (stream_variant() == 6) return launch_stream_cfg<TR, T, NP, NM, NO, 512, 1, false, false>(L, cfg, a, nrows_out, nrows_max);
+      if (stream_variant() == 7) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 1, false, true>(L, cfg, a, nrows_out, nrows_max);
+      return launch_stream_cfg<TR, T, NP, NM, NO, 384, 1, false, false>(L, cfg, a, nrows_out, nrows_max);
     } else {
       if (pbm) return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, true>(L, cfg, a, nrows_out, nrows_max);
       return launch_stream_cfg<TR, T, NP, NM, NO, 256, 2, false>(L, cfg, a, nrows_out, nrows_max);   // run-time traits: 1.41 ms vs 1.55 ms with 256 x 1

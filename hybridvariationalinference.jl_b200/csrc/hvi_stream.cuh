@@ -64,7 +64,9 @@ template <typename T, int NP, int NM, int NO>
 struct SiteState {
   static constexpr int NOP = (NO + 1) / 2;   // observation pairs
   typename PairT<T>::type S1[NOP], S2[NOP], S12[NOP], nyo[NOP], w[NOP];   // nyo = −y_o
-  typename PairT<T>::type nly2;  // Σ w·res² over the draws, two lanes
+  // Σ over the draws of res² per observation (the weight is applied once per site at the end: res·res reads two
+  // register pairs where res·(w·res) + acc reads three, and operand reads bound this kernel)
+  typename PairT<T>::type q[NOP];
   T mu[NM];
   T sU[tri(NM)];                 // σ[k]·U[j,k]
   T smu[NM], sz[tri(NM)];        // Σ_m ζ̄[k],  Σ_m ζ̄[k]·z[j]
@@ -75,7 +77,7 @@ struct SiteState {
 
 // f_doubleMM + logden_normal + adjoint w.r.t. (r0, r1, K1, K2), all observations of one site
 // and one draw:  y = r0 + r1·S1/(K1+S1)·S2/(K2+S2)   (src/DoubleMM/f_doubleMM.jl:137)
-// accumulates Σ w·res² into st.nly2; pbar = (Σ dy, Σ dy·ab, −r1 Σ dy·ab/d1, −r1 Σ dy·ab/d2),
+// accumulates res² per observation into st.q; pbar = (Σ dy, Σ dy·ab, −r1 Σ dy·ab/d1, −r1 Σ dy·ab/d2),
 // dy = w·res.  14 FP32 operations + 1 reciprocal per observation, two observations per
 // instruction.
 template <typename T, int NP, int NM, int NO>
@@ -93,7 +95,7 @@ __device__ __forceinline__ void obs_loop(SiteState<T, NP, NM, NO>& st, const T (
     const P y = pfma(r1, ab, r0);
     const P res = padd(y, st.nyo[o]);
     const P dy = pmul(res, st.w[o]);
-    st.nly2 = pfma(res, dy, st.nly2);
+    st.q[o] = pfma(res, res, st.q[o]);
     g0 = padd(g0, dy);
     const P t = pmul(dy, ab);
     g1 = padd(g1, t);
@@ -107,12 +109,54 @@ __device__ __forceinline__ void obs_loop(SiteState<T, NP, NM, NO>& st, const T (
   pbar[3] = -par[1] * (gB.x + gB.y);
 }
 
-// mud: the mean μ_ζ of this draw (st.mu without pbm covariates; g([xM; ζP_m]) with them,
-// src/elbo.jl:508-515); zbout: cotangent ζ̄M of this draw (unscaled by 1/n_MC)
+// the same for two draws at once: the statements of the two draws alternate in program order, which gives the
+// scheduler eight independent observation chains instead of four (two warps per scheduler do not cover the
+// dependent FMUL2 → MUFU.RCP → FMUL2 chain of a single draw)
+template <typename T, int NP, int NM, int NO>
+__device__ __forceinline__ void obs_loop2(SiteState<T, NP, NM, NO>& st, const T (&parA)[4], const T (&parB)[4],
+                                          T (&pbarA)[4], T (&pbarB)[4]) {
+  using P = typename PairT<T>::type;
+  const P r0A = mk2(parA[0], parA[0]), r1A = mk2(parA[1], parA[1]), k1A = mk2(parA[2], parA[2]), k2A = mk2(parA[3], parA[3]);
+  const P r0B = mk2(parB[0], parB[0]), r1B = mk2(parB[1], parB[1]), k1B = mk2(parB[2], parB[2]), k2B = mk2(parB[3], parB[3]);
+  P g0A = mk2(T(0), T(0)), g1A = g0A, gAA = g0A, gBA = g0A, g0B = g0A, g1B = g0A, gAB = g0A, gBB = g0A;
+#pragma unroll
+  for (int o = 0; o < SiteState<T, NP, NM, NO>::NOP; o++) {
+    const P d1A = padd(k1A, st.S1[o]), d1B = padd(k1B, st.S1[o]);
+    const P d2A = padd(k2A, st.S2[o]), d2B = padd(k2B, st.S2[o]);
+    const P pA = pmul(d1A, d2A), pB = pmul(d1B, d2B);
+    const P rpA = mk2(rcp_fast(pA.x), rcp_fast(pA.y)), rpB = mk2(rcp_fast(pB.x), rcp_fast(pB.y));
+    const P abA = pmul(st.S12[o], rpA), abB = pmul(st.S12[o], rpB);
+    const P yA = pfma(r1A, abA, r0A), yB = pfma(r1B, abB, r0B);
+    const P resA = padd(yA, st.nyo[o]), resB = padd(yB, st.nyo[o]);
+    const P dyA = pmul(resA, st.w[o]), dyB = pmul(resB, st.w[o]);
+    st.q[o] = pfma(resB, resB, pfma(resA, resA, st.q[o]));
+    g0A = padd(g0A, dyA); g0B = padd(g0B, dyB);
+    const P tA = pmul(dyA, abA), tB = pmul(dyB, abB);
+    g1A = padd(g1A, tA); g1B = padd(g1B, tB);
+    const P uA = pmul(tA, rpA), uB = pmul(tB, rpB);
+    gAA = pfma(uA, d2A, gAA); gAB = pfma(uB, d2B, gAB);
+    gBA = pfma(uA, d1A, gBA); gBB = pfma(uB, d1B, gBB);
+  }
+  pbarA[0] = g0A.x + g0A.y; pbarB[0] = g0B.x + g0B.y;
+  pbarA[1] = g1A.x + g1A.y; pbarB[1] = g1B.x + g1B.y;
+  pbarA[2] = -parA[1] * (gAA.x + gAA.y); pbarB[2] = -parB[1] * (gAB.x + gAB.y);
+  pbarA[3] = -parA[1] * (gBA.x + gBA.y); pbarB[3] = -parB[1] * (gBB.x + gBB.y);
+}
+
+// what one draw carries from the part before the observation loop to the part after it
+template <typename T, int NP, int NM>
+struct DrawTmp {
+  T dth[NM], dz[NM];                       // dθ/dζ, d(prior − logjac)/dζ of the site parameters
+  T gp[NP > 0 ? NP : 1], zp[NP > 0 ? NP : 1];   // dθP/dζP and zP of this draw
+  T par[4];                                // (r0, r1, K1, K2)
+};
+
+// before the observations: ζ = μ + σ(μ)·Uᵀz, θ = T(ζ) with clamp, priors, log-Jacobian, slot gather
+// mud: the mean μ_ζ of this draw (st.mu without pbm covariates; g([xM; ζP_m]) with them, src/elbo.jl:508-515)
 template <class TR, typename T, int NP, int NM, int NO>
-__device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, NO>& st, const T (&z)[NM],
-                                        const T* __restrict__ pd, const T (&mud)[NM], T (&zbout)[NM]) {
-  T th[NM], dth[NM], dz[NM];  // dz = d(prior − logjac)/dζ
+__device__ __forceinline__ void draw_pre(const Cfg<T>& cfg, SiteState<T, NP, NM, NO>& st, const T (&z)[NM],
+                                         const T* __restrict__ pd, const T (&mud)[NM], DrawTmp<T, NP, NM>& d) {
+  T th[NM];
 #pragma unroll
   for (int k = 0; k < NM; k++) {
     T zeta = mud[k];
@@ -132,27 +176,26 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, 
       st.u2 = fma(u, u, st.u2);
       st.lj += zeta;
       if constexpr (!all_exp_ln<TR, NM>()) st.ljln += zeta;
-      dth[k] = uncl ? th[k] : T(0);
-      dz[k] = uncl ? u * cfg.prM_ib[k] : T(-1);
+      d.dth[k] = uncl ? th[k] : T(0);
+      d.dz[k] = uncl ? u * cfg.prM_ib[k] : T(-1);
     } else {
       T pv, lj;
-      transform_prior<T>(trk, pkk, cfg.prM_a[k], cfg.prM_ib[k], cfg.clamp_lo, cfg.clamp_hi, zeta, th[k], dth[k], pv,
-                         dz[k], lj);
+      transform_prior<T>(trk, pkk, cfg.prM_a[k], cfg.prM_ib[k], cfg.clamp_lo, cfg.clamp_hi, zeta, th[k], d.dth[k], pv,
+                         d.dz[k], lj);
       st.prior += pv;
       st.lj += lj;
     }
   }
-  T thp[NP > 0 ? NP : 1], gp[NP > 0 ? NP : 1], zp[NP > 0 ? NP : 1];
+  T thp[NP > 0 ? NP : 1];
   if constexpr (NP == 2 && sizeof(T) == 4) {
     const float4 v = *reinterpret_cast<const float4*>(pd);
     const float2 v2 = *reinterpret_cast<const float2*>(pd + 4);
-    thp[0] = v.x; thp[1] = v.y; gp[0] = v.z; gp[1] = v.w; zp[0] = v2.x; zp[1] = v2.y;
+    thp[0] = v.x; thp[1] = v.y; d.gp[0] = v.z; d.gp[1] = v.w; d.zp[0] = v2.x; d.zp[1] = v2.y;
   } else {
 #pragma unroll
-    for (int j = 0; j < NP; j++) { thp[j] = pd[j]; gp[j] = pd[NP + j]; zp[j] = pd[2 * NP + j]; }
+    for (int j = 0; j < NP; j++) { thp[j] = pd[j]; d.gp[j] = pd[NP + j]; d.zp[j] = pd[2 * NP + j]; }
   }
   // gather (r0, r1, K1, K2) by slot (src/PBMApplicator.jl:234-239,283-287)
-  T par[4];
 #pragma unroll
   for (int s = 0; s < 4; s++) {
     T v = cfg.slot_fix[s];
@@ -161,10 +204,15 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, 
     for (int j = 0; j < NP; j++) v = (c == j) ? thp[j] : v;
 #pragma unroll
     for (int k = 0; k < NM; k++) v = (c == NP + k) ? th[k] : v;
-    par[s] = v;
+    d.par[s] = v;
   }
-  T pbar[4];
-  obs_loop<T, NP, NM, NO>(st, par, pbar);
+}
+
+// after the observations: cotangents of ζM and ζP of this draw into the per-site sums
+// zbout: cotangent ζ̄M of this draw (unscaled by 1/n_MC)
+template <class TR, typename T, int NP, int NM, int NO>
+__device__ __forceinline__ void draw_post(const Cfg<T>& cfg, SiteState<T, NP, NM, NO>& st, const T (&z)[NM],
+                                          const DrawTmp<T, NP, NM>& d, const T (&pbar)[4], T (&zbout)[NM]) {
   T thbar[NP + NM];
 #pragma unroll
   for (int q = 0; q < NP + NM; q++) {
@@ -182,7 +230,7 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, 
   }
 #pragma unroll
   for (int k = 0; k < NM; k++) {
-    const T zb = fma(thbar[NP + k], dth[k], dz[k]);
+    const T zb = fma(thbar[NP + k], d.dth[k], d.dz[k]);
     zbout[k] = zb;
     st.smu[k] += zb;
 #pragma unroll
@@ -190,16 +238,77 @@ __device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, 
   }
 #pragma unroll
   for (int j = 0; j < NP; j++) {
-    const T zb = thbar[j] * gp[j];
+    const T zb = thbar[j] * d.gp[j];
     st.aP[j] += zb;
 #pragma unroll
-    for (int jj = 0; jj <= j; jj++) st.cP[ut(jj, j)] = fma(zb, zp[jj], st.cP[ut(jj, j)]);
+    for (int jj = 0; jj <= j; jj++) st.cP[ut(jj, j)] = fma(zb, d.zp[jj], st.cP[ut(jj, j)]);
   }
 }
 
-constexpr int STREAM_THREADS_MAX = 384;
+template <class TR, typename T, int NP, int NM, int NO>
+__device__ __forceinline__ void do_draw(const Cfg<T>& cfg, SiteState<T, NP, NM, NO>& st, const T (&z)[NM],
+                                        const T* __restrict__ pd, const T (&mud)[NM], T (&zbout)[NM]) {
+  DrawTmp<T, NP, NM> d;
+  T pbar[4];
+  draw_pre<TR, T, NP, NM, NO>(cfg, st, z, pd, mud, d);
+  obs_loop<T, NP, NM, NO>(st, d.par, pbar);
+  draw_post<TR, T, NP, NM, NO>(cfg, st, z, d, pbar, zbout);
+}
 
-template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, bool PBM, bool RNG>
+constexpr int STREAM_THREADS_MAX = 512;
+
+// Σ over the 32 lanes of N ≤ 32 values per lane at once: at every level half of the values go to the partner lane and
+// the other half is kept, so the tree costs NPAD − 1 + (32/NPAD... ) shuffles instead of 5·N.  Returns, in lane l, the total of
+// value index warp_multi_index<NPAD>(l) (fixed order of additions: deterministic).
+template <int NPAD>
+__device__ __forceinline__ int warp_multi_index(int lane) {
+  // level with offset 16 keeps the upper half of the values in lanes with bit 4 set, and so on down the bits
+  int idx = 0, n = NPAD;
+#pragma unroll
+  for (int b = 4; b >= 0 && n > 1; b--) { n >>= 1; idx += ((lane >> b) & 1) * n; }
+  return idx;
+}
+template <typename T, int NPAD>
+__device__ __forceinline__ T warp_multi_sum(T (&v)[NPAD], int lane) {
+  static_assert(NPAD == 16 || NPAD == 32, "16 or 32 values");
+  int n = NPAD;
+#pragma unroll
+  for (int b = 4; b >= 0; b--) {
+    const int off = 1 << b;
+    if (n > 1) {
+      n >>= 1;
+      const bool up = (lane >> b) & 1;
+#pragma unroll
+      for (int i = 0; i < NPAD / 2; i++) {
+        if (i < n) {
+          const T send = up ? v[i] : v[i + n];
+          const T keep = up ? v[i + n] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    }
+  }
+  return v[0];
+}
+
+// dynamic shared memory of the streaming body: per warp the two half-row stages of ξ, one tile of site records
+// and means (prefetched one tile ahead), one row of double accumulators; per block the per-draw records of the
+// global parameters (pd_elems = n_MC·pd_stride(n_θP), or 0 when they stay in global memory)
+__host__ __device__ constexpr size_t stream_smem_z(size_t szT, int nwarp, int nM) { return (size_t)nwarp * 32 * nM * (8 * (16 / szT)) * szT; }
+__host__ __device__ constexpr size_t stream_smem_site(size_t szT, int nwarp, int nM, int nO) { return (size_t)nwarp * (4 * nO + nM) * 32 * szT; }
+__host__ __device__ constexpr size_t stream_smem_bytes(size_t szT, int nwarp, int nP, int nM, int nO, size_t pd_elems, bool spf = true) {
+  return stream_smem_z(szT, nwarp, nM) + (spf ? stream_smem_site(szT, nwarp, nM, nO) : 0) +
+         (size_t)nwarp * nacc(nP, nM) * sizeof(double) + pd_elems * szT + 16;
+}
+
+// PDS: the per-draw records are copied to shared memory (compile time, so that they are read with LDS, not with
+// generic loads); ILV: two draws share one pass of the observation loop
+// SPF: the site records and means of the next tile are prefetched into shared memory (costs (4·n_obs + n_θM)·128
+// bytes per warp; switched off by the launcher where that would cost a resident block)
+template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, bool PBM, bool RNG, bool PDS = true, bool ILV = true,
+          bool SPF = true>
 __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<T>& a, unsigned char* smem_raw, int bid,
                                             int nblk) {
   constexpr int CH = 16 / sizeof(T);  // elements per 16-byte chunk
@@ -208,17 +317,20 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
   constexpr int NACC = nacc(NP, NM);
   constexpr int NWARP = STREAM_THREADS / 32;
   constexpr int PD = pd_stride(NP);
+  constexpr int REC = 4 * NO * 32;     // elements of one tile of site records
+  constexpr size_t OFF_SITE = stream_smem_z(sizeof(T), NWARP, NM);
+  constexpr size_t OFF_ACC = OFF_SITE + (SPF ? stream_smem_site(sizeof(T), NWARP, NM, NO) : 0);
+  constexpr size_t OFF_PD = OFF_ACC + (size_t)NWARP * NACC * sizeof(double);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* ztile = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (32 * NM * MC);
-  double* wacc = reinterpret_cast<double*>(smem_raw + (size_t)NWARP * 32 * NM * MC * sizeof(T)) + warp * NACC;
-  T* spd = reinterpret_cast<T*>(smem_raw + (size_t)NWARP * 32 * NM * MC * sizeof(T) + (size_t)NWARP * NACC * sizeof(double));
+  T* srec = reinterpret_cast<T*>(smem_raw + OFF_SITE) + (size_t)warp * (REC + NM * 32);
+  T* smu = srec + REC;
+  double* wacc = reinterpret_cast<double*>(smem_raw + OFF_ACC) + warp * NACC;
+  T* spd = reinterpret_cast<T*>(smem_raw + OFF_PD);
   const int M = a.M;
   // per-draw global-parameter records: shared memory if they fit, else read from global
-  const T* pdbase = a.pd;
-  if (a.pd_in_smem) {
+  if constexpr (PDS)
     for (int e = threadIdx.x; e < M * PD; e += STREAM_THREADS) spd[e] = a.pd[e];
-    pdbase = spd;
-  }
   if (lane == 0)
     for (int i = 0; i < NACC; i++) wacc[i] = 0.0;
   __syncthreads();
@@ -236,12 +348,79 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
   const bool staged = a.staged != 0;
   const uint64_t seed = (RNG && a.seed_dev) ? (uint64_t)*a.seed_dev : a.seed;
   const int64_t ntiles = (a.nb + 31) / 32;
-  for (int64_t tile = (int64_t)bid * NWARP + warp; tile < ntiles; tile += (int64_t)nblk * NWARP) {
+  const bool mu_al = (reinterpret_cast<uintptr_t>(a.mu) & 15) == 0;
+  constexpr int MCS = MC / 2, QS = 4;
+  const int mode = RNG ? 2 : (staged ? 1 : 0);
+  const int nst = mode == 1 ? (M + MCS - 1) / MCS : 1;
+
+  // cp.async of one tile of site records and means into this warp's buffer (no commit)
+  auto issue_site = [&](int64_t tl) {
+    if constexpr (!SPF) return;
+    const T* r = a.rec + tl * REC;
+#pragma unroll
+    for (int c0 = 0; c0 < REC / CH; c0 += 32) cp_async16(srec + (c0 + lane) * CH, r + (size_t)(c0 + lane) * CH);
+    if (mu_al && tl * 32 + 32 <= a.nb) {
+      const T* m = a.mu + tl * 32 * NM;
+#pragma unroll
+      for (int c0 = 0; c0 < NM * 32 / CH; c0 += 32)
+        if (c0 + lane < NM * 32 / CH) cp_async16(smu + (c0 + lane) * CH, m + (size_t)(c0 + lane) * CH);
+    }
+  };
+  // cp.async of stage sg (MCS draws) of the draws ξ of tile tl into half-row buffer b (no commit); 16-byte chunks
+  // are rotated by the owning lane so that the transposed LDS.128 read-back is conflict free
+  auto issue_xi = [&](int64_t tl, int sg, int b) {
+    const T* gz = a.zMs + (size_t)tl * 32 * NM * M;  // row r of the tile at gz + r*M
+    const int rows_valid = (int)(a.nb - tl * 32 < 32 ? a.nb - tl * 32 : 32) * NM;
+    const int m0 = sg * MCS;
+    const int nch = ((M - m0) < MCS ? (M - m0) : MCS) / CH;
+    T* buf = ztile + b * (32 * NM * MCS);
+    const int q = lane & 3, r0 = lane >> 2;   // this lane's chunk of the row, and its first row (rows r0, r0 + 8, ...)
+    if (rows_valid == 32 * NM && nch == QS) {
+      // whole tile, whole stage: no guards, one pointer increment per copy
+      const T* src = gz + (size_t)r0 * M + m0 + q * CH;
+      const size_t step = (size_t)8 * M;
+#pragma unroll
+      for (int j = 0; j < 4 * NM; j++) {
+        const int row = r0 + 8 * j;
+        const int rot = NM == 2 ? ((q + (r0 >> 1)) & 3) : ((q + row / NM) & 3);   // (r0 + 8j)/2 = r0/2 + 4j
+        cp_async16(buf + row * MCS + rot * CH, src);
+        src += step;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4 * NM; j++) {
+        const int row = r0 + 8 * j, owner = row / NM;
+        if (q < nch && row < rows_valid)
+          cp_async16(buf + row * MCS + ((q + owner) & 3) * CH, gz + (size_t)row * M + m0 + q * CH);
+      }
+    }
+  };
+
+  const int64_t tstride = (int64_t)nblk * NWARP;
+  int64_t tile = (int64_t)bid * NWARP + warp;
+  // software pipeline over the warp's tiles: the records and means of tile t+1 and the first stage of its draws
+  // are in flight while tile t is computed, so that a tile starts without a round trip to HBM
+  if (tile < ntiles) {
+    issue_site(tile);
+    if (mode == 1) issue_xi(tile, 0, 0);
+    cp_async_commit();
+  }
+  int g = 0;            // running stage count of this warp: stage g lives in half-row buffer g & 1
+  bool first = true;
+  for (; tile < ntiles; tile += tstride) {
+    const int64_t tnext = tile + tstride;
+    const bool has_next = tnext < ntiles;
     const int64_t site = tile * 32 + lane;
     const bool active = site < a.nb;
+    const bool full = tile * 32 + 32 <= a.nb;
     const int64_t isite = (cfg.sepvar && active && a.i_sites) ? a.i_sites[site] : site;   // global site index
+    // the group that carried this tile's records is complete, except for the first tile, single-stage tiles and
+    // the modes without staged draws, where it is the most recent one
+    if (first || nst == 1 || mode != 1) cp_async_wait_group<0>();
+    __syncwarp();
+    first = false;
     {
-      const T* r = a.rec + (tile * 4 * NO) * 32 + lane;
+      const T* r = SPF ? srec + lane : a.rec + tile * REC + lane;
       constexpr int NOP = SiteState<T, NP, NM, NO>::NOP;
 #pragma unroll
       for (int o = 0; o < NOP; o++) {
@@ -257,7 +436,7 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
     T ls[NM], sig[NM];
 #pragma unroll
     for (int k = 0; k < NM; k++) {
-      st.mu[k] = active ? a.mu[site * NM + k] : T(0);
+      st.mu[k] = (SPF && mu_al && full) ? smu[lane * NM + k] : (active ? a.mu[site * NM + k] : T(0));
       // log σ²: intercept + slope·μ_ζ (src/elbo.jl:652-653) or the site's own parameter (src/elbo_sepvec.jl:23)
       ls[k] = (cfg.sepvar && active) ? a.phi[cfg.o_coef + isite * NM + k] : fma(cB[k], st.mu[k], cA[k]);
       sig[k] = exp_t(T(0.5) * ls[k]);
@@ -272,41 +451,31 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
 #pragma unroll
     for (int i = 0; i < (NP > 0 ? NUP : 1); i++) st.cP[i] = T(0);
     st.prior = st.lj = st.u2 = st.ljln = T(0);
-    st.nly2 = mk2(T(0), T(0));
+#pragma unroll
+    for (int o = 0; o < SiteState<T, NP, NM, NO>::NOP; o++) st.q[o] = mk2(T(0), T(0));
+    __syncwarp();   // every lane has taken its records: the buffer may be refilled
+    if (mode != 1) {
+      if (has_next) issue_site(tnext);
+      cp_async_commit();
+    }
 
     // three sources of the draws ξ of this tile, one copy of the per-draw code:
     //   mode 1: cp.async staging through shared memory (two half-row stages of MCS draws in flight)
     //   mode 2: generated in registers (Philox + Box-Muller), no memory traffic at all
     //   mode 0: direct global loads (n_MC not a multiple of the 16-byte chunk)
     {
-      constexpr int MCS = MC / 2, QS = 4;
-      const int mode = RNG ? 2 : (staged ? 1 : 0);
-      const T* gz = a.zMs + (size_t)tile * 32 * NM * M;  // row r of the tile at gz + r*M
-      const int rows_valid = (int)(a.nb - tile * 32 < 32 ? a.nb - tile * 32 : 32) * NM;
-      const int nst = mode == 1 ? (M + MCS - 1) / MCS : 1;
-      auto issue = [&](int st_) {
-        const int m0 = st_ * MCS;
-        const int nch = ((M - m0) < MCS ? (M - m0) : MCS) / CH;
-        T* buf = ztile + (st_ & 1) * (32 * NM * MCS);
-#pragma unroll
-        for (int e0 = 0; e0 < 32 * NM * QS; e0 += 32) {
-          const int e = e0 + lane;
-          const int row = e >> 2, q = e & 3, owner = row / NM;
-          if (q < nch && row < rows_valid)
-            cp_async16(buf + row * MCS + ((q + owner) & 3) * CH, gz + (size_t)row * M + m0 + q * CH);
-        }
-        cp_async_commit();
-      };
-      if (mode == 1) { __syncwarp(); issue(0); }
-      for (int st_ = 0; st_ < nst; st_++) {
+      for (int st_ = 0; st_ < nst; st_++, g++) {
         if (mode == 1) {
-          if (st_ + 1 < nst) { issue(st_ + 1); cp_async_wait_group<1>(); }
-          else cp_async_wait_group<0>();
+          if (st_ + 1 < nst) issue_xi(tile, st_ + 1, (g + 1) & 1);
+          else if (has_next) issue_xi(tnext, 0, (g + 1) & 1);
+          if (st_ == 0 && has_next) issue_site(tnext);
+          cp_async_commit();
+          cp_async_wait_group<1>();
           __syncwarp();
         }
         const int m0 = mode == 1 ? st_ * MCS : 0;
         const int nd = mode == 1 ? ((M - m0) < MCS ? (M - m0) : MCS) : M;   // draws of this stage
-        const T* buf = ztile + (st_ & 1) * (32 * NM * MCS);
+        const T* buf = ztile + (g & 1) * (32 * NM * MCS);
         if (active) {
           const int nfull = nd / CH;
           for (int q = 0; q < nfull; q++) {   // full chunks of CH draws, no guards
@@ -338,22 +507,38 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
 #pragma unroll
                 for (int d = 0; d < CH; d++) zc[k][d] = a.zMs[((size_t)site * NM + k) * M + mq + d];
             }
-            const T* pd = pdbase + (size_t)mq * PD;
-            T mud[CH][NM];
+            T mud[CH][NM], z[CH][NM], zb[CH][NM];
 #pragma unroll
             for (int d = 0; d < CH; d++)
 #pragma unroll
-              for (int k = 0; k < NM; k++) mud[d][k] = PBM ? a.MU[((size_t)(mq + d) * NM + k) * a.nb + site] : st.mu[k];
-#pragma unroll
-            for (int d = 0; d < CH; d++) {
-              T z[NM], zb[NM];
-#pragma unroll
-              for (int k = 0; k < NM; k++) z[k] = zc[k][d];
-              do_draw<TR, T, NP, NM, NO>(cfg, st, z, pd + d * PD, mud[d], zb);
-              if constexpr (PBM) {
-#pragma unroll
-                for (int k = 0; k < NM; k++) a.MUBAR[((size_t)(mq + d) * NM + k) * a.nb + site] = wM * zb[k];
+              for (int k = 0; k < NM; k++) {
+                mud[d][k] = PBM ? a.MU[((size_t)(mq + d) * NM + k) * a.nb + site] : st.mu[k];
+                z[d][k] = zc[k][d];
               }
+            if constexpr (ILV) {
+              DrawTmp<T, NP, NM> dt[CH];
+              T pbar[CH][4];
+#pragma unroll
+              for (int d = 0; d < CH; d++) {
+                const T* pd = PDS ? spd + (size_t)(mq + d) * PD : a.pd + (size_t)(mq + d) * PD;
+                draw_pre<TR, T, NP, NM, NO>(cfg, st, z[d], pd, mud[d], dt[d]);
+              }
+#pragma unroll
+              for (int d = 0; d < CH; d += 2) obs_loop2<T, NP, NM, NO>(st, dt[d].par, dt[d + 1].par, pbar[d], pbar[d + 1]);
+#pragma unroll
+              for (int d = 0; d < CH; d++) draw_post<TR, T, NP, NM, NO>(cfg, st, z[d], dt[d], pbar[d], zb[d]);
+            } else {
+#pragma unroll
+              for (int d = 0; d < CH; d++) {
+                const T* pd = PDS ? spd + (size_t)(mq + d) * PD : a.pd + (size_t)(mq + d) * PD;
+                do_draw<TR, T, NP, NM, NO>(cfg, st, z[d], pd, mud[d], zb[d]);
+              }
+            }
+            if constexpr (PBM) {
+#pragma unroll
+              for (int d = 0; d < CH; d++)
+#pragma unroll
+                for (int k = 0; k < NM; k++) a.MUBAR[((size_t)(mq + d) * NM + k) * a.nb + site] = wM * zb[d][k];
             }
           }
           // remaining draws (n_MC not a multiple of the chunk; never in mode 1), one at a time
@@ -371,7 +556,8 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
               }
               mud[k] = PBM ? a.MU[((size_t)m * NM + k) * a.nb + site] : st.mu[k];
             }
-            do_draw<TR, T, NP, NM, NO>(cfg, st, z, pdbase + (size_t)m * PD, mud, zb);
+            const T* pd = PDS ? spd + (size_t)m * PD : a.pd + (size_t)m * PD;
+            do_draw<TR, T, NP, NM, NO>(cfg, st, z, pd, mud, zb);
             if constexpr (PBM) {
 #pragma unroll
               for (int k = 0; k < NM; k++) a.MUBAR[((size_t)m * NM + k) * a.nb + site] = wM * zb[k];
@@ -383,11 +569,19 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
     }
 
     // end of site: σ-path, entropy, μ̄_ζ  (SURVEY Appendix A adjoint)
-    T acc[NACC];
+    constexpr int NPAD = NACC <= 16 ? 16 : 32;
+    static_assert(NACC <= 32, "at most 32 accumulators");
+    T acc[NPAD];
 #pragma unroll
-    for (int i = 0; i < NACC; i++) acc[i] = T(0);
+    for (int i = 0; i < NPAD; i++) acc[i] = T(0);
     if (active) {
-      acc[ACC_NLY] = st.nly2.x + st.nly2.y; acc[ACC_LJ] = st.lj;
+      {
+        typename PairT<T>::type s2 = mk2(T(0), T(0));
+#pragma unroll
+        for (int o = 0; o < SiteState<T, NP, NM, NO>::NOP; o++) s2 = pfma(st.w[o], st.q[o], s2);
+        acc[ACC_NLY] = s2.x + s2.y;
+      }
+      acc[ACC_LJ] = st.lj;
       acc[ACC_PRIOR] = st.prior + T(0.5) * st.u2 + (all_exp_ln<TR, NM>() ? st.lj : st.ljln);
 #pragma unroll
       for (int k = 0; k < NM; k++) {
@@ -418,16 +612,18 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
 #pragma unroll
       for (int i = 0; i < NUP; i++) acc[ACC_FIRST_VEC + 2 * NM + NUM + NP + i] = st.cP[i];
     }
-#pragma unroll
-    for (int i = 0; i < NACC; i++) {
-      const T v = warp_sum(acc[i]);
-      if (lane == 0) wacc[i] += (double)v;
+    {
+      // all accumulators at once: lane l ends up with the warp's total of accumulator warp_multi_index(l)
+      const T v = warp_multi_sum<T, NPAD>(acc, lane);
+      const int ia = warp_multi_index<NPAD>(lane);
+      if (ia < NACC && (NPAD == 32 || !(lane & 1))) wacc[ia] += (double)v;
     }
   }
+  cp_async_wait_group<0>();
   // one row of partial sums per block: the warps' double accumulators added in warp order
   __syncthreads();
   {
-    const double* w0 = reinterpret_cast<const double*>(smem_raw + (size_t)NWARP * 32 * NM * MC * sizeof(T));
+    const double* w0 = reinterpret_cast<const double*>(smem_raw + OFF_ACC);
     for (int i = threadIdx.x; i < NACC; i += STREAM_THREADS) {
       double s = 0.0;
       for (int w = 0; w < NWARP; w++) s += w0[w * NACC + i];
