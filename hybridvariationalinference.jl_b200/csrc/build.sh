@@ -6,7 +6,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
-SRCS="hvi_kernels hvi_stream hvi_capi hvi_dense_tc hvi_dense_tma hvi_mlp_mma hvi_point hvi_predict hvi_generic"
+SRCS="hvi_kernels hvi_stream hvi_capi hvi_dense_tc hvi_dense_tma hvi_mlp_mma hvi_mlp_tc hvi_point hvi_predict hvi_generic"
 HDRS="hvi_internal.cuh hvi_dev.cuh hvi_stream.cuh hvi_tc_common.cuh hvi_rng.cuh hvi_pbm.cuh ../../include/hvi_b200.h"
 # the text of hvi_pbm.cuh travels inside the library: NVRTC compiles it together with a user's process model
 if [ ! -f hvi_pbm_src.inc ] || [ hvi_pbm.cuh -nt hvi_pbm_src.inc ]; then

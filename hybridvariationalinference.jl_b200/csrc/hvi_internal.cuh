@@ -195,6 +195,12 @@ cudaError_t launch_mlp3_mma_fwd(const Launch& L, const Cfg<float>& cfg, const fl
 cudaError_t launch_mlp3_mma_bwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM,
                                 const float* mubar, int64_t nb, double* part, int* nblk_out, int nblk_max, int M_units,
                                 const float* zetaP, double* part_x);
+// tcgen05 small applicator, Float32 (hvi_mlp_tc.cu); cudaErrorNotSupported: not one of its shapes or HVI_MLP_TC=0
+cudaError_t launch_mlp3_tc_fwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb,
+                               float* mu, int M_units, const float* zetaP);
+cudaError_t launch_mlp3_tc_bwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM,
+                               const float* mubar, int64_t nb, double* part, int* nblk_out, int nblk_max, int M_units,
+                               const float* zetaP, double* part_x);
 // point-solver loss (hvi_point.cu)
 template <typename T>
 cudaError_t launch_point(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* rec, const T* mu, T* mubar, int64_t nb,

@@ -1198,6 +1198,8 @@ template <typename T>
 cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, int64_t nb, T* mu, int M_units,
                            const T* zetaP) {
   if constexpr (sizeof(T) == 4) {   // Float32: the named shapes run on the tensor cores
+    const cudaError_t et = launch_mlp3_tc_fwd(L, cfg, phi, xM, nb, mu, M_units, zetaP);
+    if (et != cudaErrorNotSupported) return et;
     const cudaError_t em = launch_mlp3_mma_fwd(L, cfg, phi, xM, nb, mu, M_units, zetaP);
     if (em != cudaErrorNotSupported) return em;
   }
@@ -1240,6 +1242,8 @@ template <typename T>
 cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, const T* mubar, int64_t nb,
                            double* part, int* nblk_out, int nblk_max, int M_units, const T* zetaP, double* part_x) {
   if constexpr (sizeof(T) == 4) {
+    const cudaError_t et = launch_mlp3_tc_bwd(L, cfg, phi, xM, mubar, nb, part, nblk_out, nblk_max, M_units, zetaP, part_x);
+    if (et != cudaErrorNotSupported) return et;
     const cudaError_t em = launch_mlp3_mma_bwd(L, cfg, phi, xM, mubar, nb, part, nblk_out, nblk_max, M_units, zetaP, part_x);
     if (em != cudaErrorNotSupported) return em;
   }
