@@ -4,17 +4,24 @@
 // ext/HybridVariationalInferenceSimpleChainsExt.jl:43-52) for the 3-layer shapes of DoubleMM (5-20-20-2 and, with one
 // pbm covariate, 6-24-24-2), evaluated on sites or -- pass 2 of generate_ζ, src/elbo.jl:508-515 -- on (draw, site) units.
 //
-// One CTA of 128 threads owns a tile of 128 columns: thread r = TMEM lane r = column r of the tile.
-//   * operands live in shared memory as K-major SWIZZLE_128B tiles [row][32 tf32], split hi = tf32(x), lo = x − hi;
-//     every product is issued three times (hi·hi + lo·hi + hi·lo, "3xTF32", ≈2^-21 relative) by ONE thread as
-//     tcgen05.mma.cta_group::1.kind::tf32, M = 128 (the columns), N = 32 (the features of the layer), K = 8 per instruction;
-//   * accumulators live in TMEM (two of 32 columns per CTA); the epilogue of a layer is thread-per-column:
-//     tcgen05.ld of the lane's row, bias + tanh (ex2 + rcp), split, and the row goes back to shared memory as the A
-//     operand of the next layer.  The layer-1 bias rides in the MMA as the weight row of a constant-1 input; the layer-2
-//     bias is folded into the argument scaling of ex2.  The 2-output last layer, logistic and Φ⁻¹ run on the CUDA cores.
-//   * the tensor work is asynchronous to the FP32/MUFU epilogues (unlike warp-level mma.sync, which blocks FP32 issue of
-//     its scheduler on B200: profiles/microbench/mma_pipes_b200.txt); several CTAs per SM interleave the phases.
-// The legacy mma.sync kernels (hvi_mlp_mma.cu) remain the fallback (HVI_MLP_TC=0) and the cross-check in the tests.
+// One CTA of 256 threads owns a tile of 128 columns.  Column r of the tile = TMEM lane r = row r of the operand tiles;
+// it is served by TWO threads (warps q and q + 4 share TMEM lane quarter q), each owning one half (12) of the padded
+// 24 features of a layer: half the registers and half the dependency chain per thread, twice the warps per SM to hide
+// the MUFU / TMEM / barrier latencies (the first, thread-per-column version issued 47 % of its cycles).
+//   * layer 1 (K = n_covar + pbm covariates) runs on the CUDA cores in exact fp32.  A CTA walks a contiguous range of
+//     units u = site_tile·n_MC + draw, so with pbm covariates the site part of the pre-activation (W1[:nC]ᵀ xM + b1) is
+//     computed once per site tile and each draw adds the rank-1 term of its covariates (only ζP[idx] changes between
+//     the draws of a site, src/elbo.jl:508-515).
+//   * layer 2 and every product of the backward pass are tcgen05.mma instructions issued by ONE thread, operands in
+//     shared memory as 128-byte-swizzled tiles split hi + lo, accumulators in TMEM, completion by tcgen05.commit →
+//     mbarrier; the epilogues read their TMEM lane with tcgen05.ld.  Tensor work is asynchronous to the FP32/MUFU
+//     epilogues (warp-level mma.sync blocks FP32 issue of its scheduler on B200: profiles/microbench/mma_pipes_b200.txt).
+//   * the 2-output last layer, logistic and Φ⁻¹ run on the CUDA cores; the two threads of a column exchange their
+//     partial sums through shared memory (named barrier of the 64 threads of a lane quarter).
+// Forward: 3xTF32 (hi = x truncated to tf32, lo = x − hi exactly, of which the tensor core reads the top 19 bits):
+// μ_ζ feeds the σ- and ρ-gradients of the streaming kernel, which amplify its rounding.
+// Backward: 3xBF16 like the mma.sync kernel it replaces; see the block comment above k_mlp3_tc_bwd.
+// The mma.sync kernels (hvi_mlp_mma.cu) remain the fallback (HVI_MLP_TC=0) and the cross-check in the tests.
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
@@ -25,14 +32,11 @@
 namespace hvi {
 namespace {
 
-constexpr int TCS_BM = 128;            // columns per tile = TMEM lanes = threads per CTA
-constexpr int TCS_N = 32;              // padded feature width of a hidden layer = N of the MMAs
-constexpr int TCS_ROW = 128;           // bytes per operand row: 32 tf32 = one swizzle row
-constexpr int TCS_A_BYTES = TCS_BM * TCS_ROW;   // one plane of an activation tile (16 KB)
-constexpr int TCS_W_BYTES = TCS_N * TCS_ROW;    // one plane of a weight tile (4 KB)
-
-// instruction descriptor: D = F32 [4,6) = 1, A = B = TF32 [7,10) = [10,13) = 2, K-major both, N >> 3 [17,23), M >> 4 [24,29)
-constexpr uint32_t TCS_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCS_N >> 3) << 17) | ((uint32_t)(TCS_BM >> 4) << 24);
+constexpr int TC_COLS = 128;           // columns per tile = TMEM lanes
+constexpr int TC_THREADS = 256;        // two threads per column
+constexpr int TC_HP = 24;              // padded hidden width
+constexpr int TC_HF = TC_HP / 2;       // features per thread
+constexpr int TC_PLANE = TC_COLS * 128;   // one plane of an operand tile: 128 rows of one swizzle row (16 KB)
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -42,10 +46,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16_(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+// MN-major SWIZZLE_128B descriptor: atoms of 64 bf16 features (128 B) x 8 rows; LBO = distance between 64-feature atoms,
+// SBO = distance between 8-row groups (1024 B)
+__device__ __forceinline__ uint64_t make_desc_mn_(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -53,7 +71,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 4; i++) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// this thread's 12 accumulator columns
+__device__ __forceinline__ void tmem_ld12(uint32_t taddr, float (&v)[TC_HF]) {
+  tmem_ld8(taddr, v);
+  tmem_ld4(taddr + 8, v + 8);
+  tmem_wait_ld();
+}
 
 __device__ __forceinline__ float rcpa(float x) {
   float r;
@@ -66,16 +98,20 @@ __device__ __forceinline__ float ex2a(float x) {
   return r;
 }
 constexpr float K2LOG2E = 2.885390081777927f;   // 2·log2(e): tanh(z) = 1 − 2/(1 + 2^(K2LOG2E·z))
+__device__ __forceinline__ float tanh_scaled(float a) { return fmaf(-2.0f, rcpa(ex2a(a) + 1.0f), 1.0f); }   // a = K2LOG2E·z
 
-// tf32 hi (round to nearest, integer add + mask) and exact residual lo
-__device__ __forceinline__ void split_tf(float x, float& hi, float& lo) {
-  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-  lo = x - hi;
-}
-// shared-memory accesses by 32-bit shared-window address (the tiles are carved out of an aligned-up dynamic buffer,
-// which would otherwise make the compiler fall back to generic LD/ST)
+// shared-memory accesses by 32-bit shared-window address (the tiles are carved out of an aligned-up dynamic buffer)
 __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64u(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
 __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ float lds32(uint32_t a) {
@@ -93,292 +129,41 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
-// four consecutive features (one 16-byte chunk) of row `row` of a K-major SWIZZLE_128B tile pair
-__device__ __forceinline__ void store_chunk(uint32_t hi_tile, uint32_t lo_tile, int row, int chunk, const float (&v)[4]) {
-  float4 h, l;
-  split_tf(v[0], h.x, l.x); split_tf(v[1], h.y, l.y); split_tf(v[2], h.z, l.z); split_tf(v[3], h.w, l.w);
-  const uint32_t off = row * TCS_ROW + ((chunk ^ (row & 7)) << 4);
+// barrier of the 64 threads that serve lane quarter q (warps q and q + 4); barrier 0 is the whole CTA.  Issued as PTX:
+// the two halves of the CTA run different instantiations of the loop body and meet at different program counters.
+__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// ---- tf32 tiles [row][32 floats]: four consecutive features (one 16-byte chunk); hi = trunc_tf32(x), lo = x − hi
+__device__ __forceinline__ float trunc_tf(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ void store4_tf(uint32_t hi_tile, uint32_t lo_tile, int row, int chunk, float a, float b, float c, float d) {
+  const uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
+  const float4 h = make_float4(trunc_tf(a), trunc_tf(b), trunc_tf(c), trunc_tf(d));
   sts128(hi_tile + off, h);
-  sts128(lo_tile + off, l);
+  sts128(lo_tile + off, make_float4(a - h.x, b - h.y, c - h.z, d - h.w));
 }
-__device__ __forceinline__ void store_elem(uint32_t hi_tile, uint32_t lo_tile, int row, int col, float x) {
-  float h, l;
-  split_tf(x, h, l);
-  const uint32_t off = row * TCS_ROW + ((((col >> 2) ^ (row & 7))) << 4) + ((col & 3) << 2);
+__device__ __forceinline__ void store1_tf(uint32_t hi_tile, uint32_t lo_tile, int row, int col, float x) {
+  const uint32_t off = row * 128 + ((((col >> 2) ^ (row & 7))) << 4) + ((col & 3) << 2);
+  const float h = trunc_tf(x);
   sts32(hi_tile + off, h);
-  sts32(lo_tile + off, l);
+  sts32(lo_tile + off, x - h);
 }
-
-template <int NI, int H1, int H2, int NOUT>
-struct MlpTc {
-  static_assert(NI + 1 <= 8, "inputs + the bias one fill one K step of 8");
-  static_assert(H1 <= TCS_N && H2 <= TCS_N && H1 % 4 == 0 && H2 % 4 == 0, "hidden widths up to 32, whole 16-byte chunks");
-  static_assert(NOUT <= 2, "two outputs on the CUDA cores");
-  static constexpr int KS2 = (H1 + 7) / 8;      // K steps of the second layer
-  static constexpr int NL1 = (H1 + 7) / 8;      // 8-column TMEM loads per accumulator row
-  static constexpr int NL2 = (H2 + 7) / 8;
-
-  // shared memory (dynamic, 1024-byte aligned): activation tile hi | lo, W1 hi | lo, W2 hi | lo, then small tables
-  static constexpr int O_A_HI = 0, O_A_LO = TCS_A_BYTES, O_W1_HI = 2 * TCS_A_BYTES, O_W1_LO = O_W1_HI + TCS_W_BYTES,
-                       O_W2_HI = O_W1_LO + TCS_W_BYTES, O_W2_LO = O_W2_HI + TCS_W_BYTES, O_TAB = O_W2_LO + TCS_W_BYTES;
-  static constexpr int TAB_FLOATS = TCS_N + TCS_N * 2;   // prescaled b2 | W3[j][k]
-  static constexpr int SMEM_BYTES = O_TAB + TAB_FLOATS * 4 + 1024;
-
-  __device__ static float wfetch(const Cfg<float>& cfg, const float* __restrict__ phi, int l, int nin, int nout, int i, int j) {
-    return (i < nin && j < nout) ? phi[cfg.woff[l] + i * nout + j] : 0.0f;
-  }
-  // B operands [n = output feature][k = input feature]; row NI of W1 is the bias b1 (multiplies the constant-1 input)
-  __device__ static void build_weights(const Cfg<float>& cfg, const float* __restrict__ phi, uint32_t sm, int tid, int nthr) {
-    for (int e = tid; e < TCS_N * TCS_N; e += nthr) {
-      const int j = e >> 5, i = e & 31;
-      float w1 = wfetch(cfg, phi, 0, NI, H1, i, j);
-      if (i == NI && j < H1) w1 = phi[cfg.boff[0] + j];
-      store_elem(sm + O_W1_HI, sm + O_W1_LO, j, i, w1);
-      store_elem(sm + O_W2_HI, sm + O_W2_LO, j, i, wfetch(cfg, phi, 1, H1, H2, i, j));
-    }
-    const uint32_t tab = sm + O_TAB;
-    for (int e = tid; e < TCS_N; e += nthr) sts32(tab + 4 * e, e < H2 ? phi[cfg.boff[1] + e] * K2LOG2E : 0.0f);
-    for (int e = tid; e < TCS_N * 2; e += nthr) {
-      const int j = e >> 1, k = e & 1;
-      sts32(tab + 4 * (TCS_N + e), (j < H2 && k < NOUT) ? phi[cfg.woff[2] + j * NOUT + k] : 0.0f);
-    }
-  }
-
-  // inputs of this thread's column: x[0..NI) then the constant 1; columns beyond the batch are all zero but the 1
-  __device__ __forceinline__ static void load_x(const Cfg<float>& cfg, const float* __restrict__ phi, const float* __restrict__ xM,
-                                                const float* __restrict__ zetaP, int M_units, int m, int64_t site, int64_t nb,
-                                                float (&xv)[8]) {
-    const bool in = site < nb;
-    const float* row = xM + (in ? site : nb - 1) * cfg.nC;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      float v = 0.0f;
-      if (i < NI) {
-        if (i < cfg.nC) v = row[i];
-        else {
-          const int idx = cfg.pbm_covar_idx[i - cfg.nC];
-          v = M_units > 0 ? zetaP[(size_t)idx * M_units + m] : phi[cfg.o_muP + idx];
-        }
-        if (!in) v = 0.0f;
-      } else if (i == NI) v = 1.0f;
-      xv[i] = v;
-    }
-  }
-  __device__ __forceinline__ static void store_x(uint32_t sm, int row, const float (&xv)[8]) {
-    const float a[4] = {xv[0], xv[1], xv[2], xv[3]}, b[4] = {xv[4], xv[5], xv[6], xv[7]};
-    store_chunk(sm + O_A_HI, sm + O_A_LO, row, 0, a);
-    store_chunk(sm + O_A_HI, sm + O_A_LO, row, 1, b);
-  }
-  // D(tmem_d) = A·Bᵀ over `ks` K steps of 8, three products per step (issued by one thread)
-  __device__ __forceinline__ static void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int ks) {
-    for (int s = 0; s < ks; s++) {
-      const uint32_t o = s * 32;
-      umma_tf32(tmem_d, make_desc(a_lo + o), make_desc(b_hi + o), TCS_IDESC, s > 0 ? 1u : 0u);
-      umma_tf32(tmem_d, make_desc(a_hi + o), make_desc(b_lo + o), TCS_IDESC, 1u);
-      umma_tf32(tmem_d, make_desc(a_hi + o), make_desc(b_hi + o), TCS_IDESC, 1u);
-    }
-  }
-  // h = tanh(z) of this thread's accumulator row (bias already inside z), features >= H are not computed
-  template <int H, int NLD>
-  __device__ __forceinline__ static void load_tanh(uint32_t taddr, uint32_t bias_scaled, float (&h)[8 * NLD]) {
-    float z[NLD][8];
-#pragma unroll
-    for (int c = 0; c < NLD; c++) tmem_ld8(taddr + 8 * c, z[c]);
-    float b[8 * NLD];
-    if (bias_scaled) {
-#pragma unroll
-      for (int c = 0; c < 2 * NLD; c++) {
-        const float4 v = lds128(bias_scaled + 16 * c);
-        b[4 * c] = v.x; b[4 * c + 1] = v.y; b[4 * c + 2] = v.z; b[4 * c + 3] = v.w;
-      }
-    }
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 8 * NLD; j++) {
-      if (j < H) {
-        const float a = bias_scaled ? fmaf(z[j >> 3][j & 7], K2LOG2E, b[j]) : z[j >> 3][j & 7] * K2LOG2E;
-        h[j] = fmaf(-2.0f, rcpa(ex2a(a) + 1.0f), 1.0f);
-      } else h[j] = 0.0f;
-    }
-  }
-};
-
-constexpr int TCS_CTAS_PER_SM = 4;
-
-template <int NI, int H1, int H2, int NOUT>
-__global__ void __launch_bounds__(TCS_BM, TCS_CTAS_PER_SM)
-k_mlp3_tc_fwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ phi, const float* __restrict__ xM,
-              const float* __restrict__ zetaP, int M_units, int64_t nb, float* __restrict__ mu) {
-  using N = MlpTc<NI, H1, H2, NOUT>;
-  extern __shared__ unsigned char smem_raw[];
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tmem_base_s;
-  const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int t = threadIdx.x, warp = t >> 5;
-  if (t == 0) {
-    mbar_init(&bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(64));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  N::build_weights(cfg, phi, sm, t, TCS_BM);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's lane quarter
-  const uint32_t a_hi = sm + N::O_A_HI, a_lo = sm + N::O_A_LO;
-  const uint32_t w1_hi = sm + N::O_W1_HI, w1_lo = sm + N::O_W1_LO;
-  const uint32_t w2_hi = sm + N::O_W2_HI, w2_lo = sm + N::O_W2_LO;
-  const uint32_t tab = sm + N::O_TAB;
-
-  const int64_t ntiles = (nb + TCS_BM - 1) / TCS_BM;
-  const int64_t ntot = ntiles * (M_units > 0 ? M_units : 1);
-  uint32_t phase = 0;
-  float xv[8];
-  int64_t tile = blockIdx.x;
-  int m = 0;
-  int64_t site = 0;
-  if (tile < ntot) {
-    m = M_units > 0 ? (int)(tile / ntiles) : 0;
-    site = (tile - (int64_t)m * ntiles) * TCS_BM + t;
-    N::load_x(cfg, phi, xM, zetaP, M_units, m, site, nb, xv);
-  }
-  for (; tile < ntot; tile += gridDim.x) {
-    const int m_cur = m;
-    const int64_t site_cur = site;
-    // ---- layer 1: [x ; 1] · [W1 ; b1]
-    N::store_x(sm, t, xv);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (t == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      N::issue_layer(tmem, a_hi, a_lo, w1_hi, w1_lo, 1);
-      umma_commit_(&bar);
-    }
-    // the next tile's inputs travel while the tensor core works
-    if (tile + gridDim.x < ntot) {
-      const int64_t nt = tile + gridDim.x;
-      m = M_units > 0 ? (int)(nt / ntiles) : 0;
-      site = (nt - (int64_t)m * ntiles) * TCS_BM + t;
-      N::load_x(cfg, phi, xM, zetaP, M_units, m, site, nb, xv);
-    }
-    mbar_wait(&bar, phase);
-    phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
-      float h1[8 * N::NL1];
-      N::template load_tanh<H1, N::NL1>(trow, 0u, h1);
-#pragma unroll
-      for (int c = 0; c < 2 * N::KS2; c++) {
-        const float v[4] = {h1[4 * c], h1[4 * c + 1], h1[4 * c + 2], h1[4 * c + 3]};
-        store_chunk(sm + N::O_A_HI, sm + N::O_A_LO, t, c, v);
-      }
-    }
-    // ---- layer 2
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (t == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      N::issue_layer(tmem + TCS_N, a_hi, a_lo, w2_hi, w2_lo, N::KS2);
-      umma_commit_(&bar);
-    }
-    mbar_wait(&bar, phase);
-    phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float h2[8 * N::NL2];
-    N::template load_tanh<H2, N::NL2>(trow + TCS_N, tab, h2);
-    // ---- layer 3 (NOUT <= 2 outputs), logistic, NormalScaling on the CUDA cores
-    float z3[2] = {0.0f, 0.0f};
-#pragma unroll
-    for (int j = 0; j < H2; j++) {
-      const float2 w = lds64(tab + 4 * (TCS_N + 2 * j));
-      z3[0] = fmaf(h2[j], w.x, z3[0]);
-      z3[1] = fmaf(h2[j], w.y, z3[1]);
-    }
-    if (site_cur < nb) {
-#pragma unroll
-      for (int k = 0; k < NOUT; k++) {
-        if (k < cfg.nM) {
-          const float p = rcpa(1.0f + ex2a(-1.4426950408889634f * z3[k]));
-          const float v = (cfg.scale_kind == HVI_SCALE_RANGE) ? p * cfg.scale_b[k] + cfg.scale_a[k]
-                                                               : cfg.scale_a[k] + cfg.scale_b[k] * normcdfinvf(p);
-          if (M_units > 0) mu[((size_t)m_cur * cfg.nM + k) * nb + site_cur] = v;
-          else mu[site_cur * cfg.nM + k] = v;
-        }
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(64));
-}
-
-// =====================================================================================================
-// Backward (hand adjoint of g): recompute forward, δ3 from μ̄_ζ through Φ⁻¹ and the logistic, δ2, δ1, and EVERY weight
-// gradient of the tile as ONE tensor-core product.
-//
-// Shared-memory tiles (bf16 hi/lo planes, [column of the tile][64 features] = one 128-byte swizzle row):
-//     U = [ h1 (HP) | h2 (HP) | x, 1 (8) ]          V = [ δ2 (HP) | δ3 (8) | δ1 (HP) ]          HP = 24
-//   P2  z2    = U[:, h1]·W2          K-major A (first 32 features of U; the weight rows beyond H1 are zero), 3xBF16
-//   P3  δ1pre = V[:, δ2]·W2ᵀ         K-major A (first 32 features of V),                                  3xBF16
-//   P4  G    += [U_hi | U_lo]ᵀ·V     MN-major operands: the SAME tiles, contraction over the tile's 128 columns.
-//       M = 128 = the 64 features of the hi plane and the 64 of the lo plane (descriptor LBO = distance of the
-//       planes), so the two MMAs per K step (B = V_hi, V_lo) give all four hi/lo products; the halves are added
-//       when the accumulator is read, once per CTA.  G holds ∇W2 = h1ᵀδ2, ∇b2 = 1ᵀδ2, ∇W3 = h2ᵀδ3, ∇W1 = xᵀδ1,
-//       ∇b1 = 1ᵀδ1 (and cross blocks nobody reads) and stays in TMEM over all tiles of the CTA.
-// Layer 1 runs on the CUDA cores in exact fp32; with pbm covariates the CTA walks the draws of one site tile, so the
-// site part of the pre-activation (W1[:nC]ᵀ xM + b1) is computed once per site tile and each draw adds the rank-1 term
-// of its covariates (src/elbo.jl:508-515: only ζP[idx] changes between the draws of a site).
-// =====================================================================================================
-constexpr int TCB_HP = 24;                       // padded hidden width inside the U / V rows (three 16-byte chunks)
-constexpr int TCB_NV = 2 * TCB_HP + 8;           // features of V = N of the gradient product (56)
-constexpr int TCB_OX = 2 * TCB_HP;               // first feature of [x, 1] in U
-constexpr int TCB_OD3 = TCB_HP, TCB_OD1 = TCB_HP + 8;
-constexpr int TCB_PLANE = TCS_BM * 128;          // 16 KB
-// D = F32, A = B = BF16 (format 1), N >> 3 [17,23), M >> 4 [24,29); bits 15/16: A/B MN-major
-constexpr uint32_t TCB_IDESC_K = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-constexpr uint32_t TCB_IDESC_G = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TCB_NV >> 3) << 17) |
-                                 ((uint32_t)(128 >> 4) << 24);
-constexpr int TCB_TMEM_COLS = 128;               // G (64) | z2 (32) | δ1pre (32)
-
-__device__ __forceinline__ void umma_bf16_(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// MN-major SWIZZLE_128B descriptor: atoms of 64 features (128 B) x 8 rows; LBO = distance between 64-feature atoms
-// (here: from the hi plane to the lo plane), SBO = distance between 8-row groups (1024 B)
-__device__ __forceinline__ uint64_t make_desc_mn_(uint32_t saddr, uint32_t lbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void sts128u(uint32_t a, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-// bf16 hi/lo split of two floats, x0 in the low half
+// ---- bf16 tiles [row][64 bf16]: hi = bf16(x), lo = bf16(x − hi); x0 in the low half of the packed word
 __device__ __forceinline__ void split_bf2(float x0, float x1, uint32_t& h, uint32_t& l) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
   const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xffff0000u);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(x1 - h1), "f"(x0 - h0));
 }
-// eight consecutive features (one 16-byte chunk) of row `row` of a [128][64 bf16] SWIZZLE_128B tile pair
-__device__ __forceinline__ void store_chunk_bf(uint32_t hi_tile, uint32_t lo_tile, int row, int chunk, const float (&v)[8]) {
-  uint4 h, l;
-  split_bf2(v[0], v[1], h.x, l.x); split_bf2(v[2], v[3], h.y, l.y); split_bf2(v[4], v[5], h.z, l.z); split_bf2(v[6], v[7], h.w, l.w);
-  const uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
-  sts128u(hi_tile + off, h);
-  sts128u(lo_tile + off, l);
+// four consecutive features starting at feature f (multiple of 4) of row `row`: half a 16-byte chunk
+__device__ __forceinline__ void store4_bf(uint32_t hi_tile, uint32_t lo_tile, int row, int f, float a, float b, float c, float d) {
+  uint32_t h0, l0, h1, l1;
+  split_bf2(a, b, h0, l0);
+  split_bf2(c, d, h1, l1);
+  const uint32_t off = row * 128 + ((((f >> 3) ^ (row & 7))) << 4) + ((f & 4) << 1);
+  sts64u(hi_tile + off, h0, h1);
+  sts64u(lo_tile + off, l0, l1);
 }
-__device__ __forceinline__ void store_elem_bf(uint32_t hi_tile, uint32_t lo_tile, int row, int col, float x) {
+__device__ __forceinline__ void store1_bf(uint32_t hi_tile, uint32_t lo_tile, int row, int col, float x) {
   const __nv_bfloat16 h = __float2bfloat16_rn(x);
   const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
   const uint32_t off = row * 128 + ((((col >> 3) ^ (row & 7))) << 4) + ((col & 7) << 1);
@@ -386,128 +171,63 @@ __device__ __forceinline__ void store_elem_bf(uint32_t hi_tile, uint32_t lo_tile
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(lo_tile + off), "h"(__bfloat16_as_ushort(l)) : "memory");
 }
 
+// tables shared by both kernels (floats): W1 rows [8][HP] (row NI = b1) | b2·K2LOG2E [HP] | W3 [HP][2]
+constexpr int T_W1 = 0, T_B2 = 8 * TC_HP, T_W3 = T_B2 + TC_HP, TAB_FLOATS = T_W3 + 2 * TC_HP;
+constexpr int TAB_BYTES = (TAB_FLOATS * 4 + 15) & ~15;
+
 template <int NI, int H1, int H2, int NOUT>
-struct MlpTcB {
-  static_assert(NI + 1 <= 8 && H1 <= TCB_HP && H2 <= TCB_HP && H1 % 4 == 0 && H2 % 4 == 0 && NOUT <= 2, "shape");
-  // shared memory: U hi | U lo | V hi | V lo | W hi | W lo (rows n: [W2[k][n] k<32 | W2ᵀ: W2[n][k] k<32]) | tables | xw | red
-  static constexpr int O_U_HI = 0, O_U_LO = TCB_PLANE, O_V_HI = 2 * TCB_PLANE, O_V_LO = 3 * TCB_PLANE, O_W_HI = 4 * TCB_PLANE,
-                       O_W_LO = O_W_HI + 32 * 128, O_TAB = O_W_LO + 32 * 128;
-  // tables (floats): W1 rows [8][HP] (row NI = b1) | b2 prescaled [HP] | W3 [HP][2]
-  static constexpr int T_W1 = 0, T_B2 = 8 * TCB_HP, T_W3 = T_B2 + TCB_HP, TAB_FLOATS = T_W3 + 2 * TCB_HP;
-  static constexpr int O_SLOT = O_TAB + ((TAB_FLOATS * 4 + 15) & ~15);  // float slot[4 warps][8]: per-tile covariate cotangents
-  static constexpr int O_XW = O_SLOT + 4 * 8 * 4;                       // double xw[nxa]
-  __host__ __device__ static constexpr int smem_bytes(int nxa) { return O_XW + nxa * 8 + 1024; }
+struct MlpTc {
+  static_assert(NI + 1 <= 8 && H1 <= TC_HP && H2 <= TC_HP && H1 % 4 == 0 && H2 % 4 == 0 && NOUT <= 2, "shape");
 
   __device__ static float wfetch(const Cfg<float>& cfg, const float* __restrict__ phi, int l, int nin, int nout, int i, int j) {
     return (i < nin && j < nout) ? phi[cfg.woff[l] + i * nout + j] : 0.0f;
   }
-  __device__ static void build(const Cfg<float>& cfg, const float* __restrict__ phi, uint32_t sm, int tid, int nthr, int nxa) {
-    // zero the operand tiles: padding features must be finite (they meet zero weight rows in P2 / P3)
-    for (int e = tid; e < (4 * TCB_PLANE) / 16; e += nthr) sts128u(sm + 16 * e, make_uint4(0u, 0u, 0u, 0u));
-    for (int e = tid; e < 32 * 64; e += nthr) {
-      const int n = e >> 6, k = e & 63;
-      const float w = k < 32 ? wfetch(cfg, phi, 1, H1, H2, k, n) : wfetch(cfg, phi, 1, H1, H2, n, k - 32);
-      store_elem_bf(sm + O_W_HI, sm + O_W_LO, n, k, w);
-    }
-    const uint32_t tab = sm + O_TAB;
-    for (int e = tid; e < 8 * TCB_HP; e += nthr) {
-      const int i = e / TCB_HP, j = e % TCB_HP;
+  __device__ static void build_tables(const Cfg<float>& cfg, const float* __restrict__ phi, uint32_t tab, int tid, int nthr) {
+    for (int e = tid; e < 8 * TC_HP; e += nthr) {
+      const int i = e / TC_HP, j = e % TC_HP;
       float w = wfetch(cfg, phi, 0, NI, H1, i, j);
       if (i == NI && j < H1) w = phi[cfg.boff[0] + j];
       sts32(tab + 4 * (T_W1 + e), w);
     }
-    for (int e = tid; e < TCB_HP; e += nthr) sts32(tab + 4 * (T_B2 + e), e < H2 ? phi[cfg.boff[1] + e] * K2LOG2E : 0.0f);
-    for (int e = tid; e < 2 * TCB_HP; e += nthr) {
+    for (int e = tid; e < TC_HP; e += nthr) sts32(tab + 4 * (T_B2 + e), e < H2 ? phi[cfg.boff[1] + e] * K2LOG2E : 0.0f);
+    for (int e = tid; e < 2 * TC_HP; e += nthr) {
       const int j = e >> 1, k = e & 1;
       sts32(tab + 4 * (T_W3 + e), (j < H2 && k < NOUT) ? phi[cfg.woff[2] + j * NOUT + k] : 0.0f);
     }
-    for (int e = tid; e < nxa * 2; e += nthr) sts32(sm + O_XW + 4 * e, 0.0f);
   }
-};
 
-constexpr int TCB_CTAS_PER_SM = 3;
-
-template <int NI, int H1, int H2, int NOUT>
-__global__ void __launch_bounds__(TCS_BM, TCB_CTAS_PER_SM)
-k_mlp3_tc_bwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ phi, const float* __restrict__ xM,
-              const float* __restrict__ zetaP, const float* __restrict__ mubar, int M_units, int64_t nb,
-              double* __restrict__ part, double* __restrict__ part_x) {
-  using N = MlpTcB<NI, H1, H2, NOUT>;
-  constexpr int HP = TCB_HP;
-  extern __shared__ unsigned char smem_raw[];
-  __shared__ uint64_t bar, barG;
-  __shared__ uint32_t tmem_base_s;
-  const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int Mu = M_units > 0 ? M_units : 1;
-  const int nxa = Mu * cfg.npc;
-  if (t == 0) {
-    mbar_init(&bar, 1);
-    mbar_init(&barG, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TCB_TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  N::build(cfg, phi, sm, t, TCS_BM, nxa);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t tG = tmem, tZ2 = tmem + 64, tD1 = tmem + 96;
-  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-  const uint32_t u_hi = sm + N::O_U_HI, u_lo = sm + N::O_U_LO, v_hi = sm + N::O_V_HI, v_lo = sm + N::O_V_LO;
-  const uint32_t w_hi = sm + N::O_W_HI, w_lo = sm + N::O_W_LO, tab = sm + N::O_TAB;
-
-  // this CTA's contiguous range of units u = site_tile·Mu + m (draws of one site tile are consecutive)
-  const int64_t ntiles = (nb + TCS_BM - 1) / TCS_BM;
-  const int64_t ntot = ntiles * Mu;
-  const int64_t u0 = ntot * blockIdx.x / gridDim.x, u1 = ntot * (blockIdx.x + 1) / gridDim.x;
-  uint32_t phase = 0, phaseG = 0;
-  bool g_pending = false, first = true;
-  int64_t st_prev = -1;
-  float base[HP];
-  float xs[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) xs[i] = 0.0f;
-
-  for (int64_t u = u0; u < u1; u++) {
-    const int64_t st = u / Mu;
-    const int m = (int)(u - st * Mu);
-    const int64_t site = st * TCS_BM + t;
+  // site part of the layer-1 pre-activation of this thread's features: b1 + Σ_{i < nC} x_i W1[i][f]; also returns the inputs
+  template <int HALF>
+  __device__ __forceinline__ static void site_base(const Cfg<float>& cfg, uint32_t tab, const float* __restrict__ xM, int64_t site,
+                                                   int64_t nb, float (&xs)[8], float (&base)[TC_HF]) {
     const bool in = site < nb;
-    // cotangent of this column's outputs (in flight during E1)
-    float mb[2] = {0.0f, 0.0f};
-    if (in) {
+    const float* row = xM + (in ? site : nb - 1) * cfg.nC;
 #pragma unroll
-      for (int k = 0; k < NOUT; k++)
-        if (k < cfg.nM) mb[k] = M_units > 0 ? mubar[((size_t)m * cfg.nM + k) * nb + site] : mubar[site * cfg.nM + k];
+    for (int i = 0; i < 8; i++) xs[i] = (i < NI && i < cfg.nC && in) ? row[i] : (i == NI ? 1.0f : 0.0f);
+#pragma unroll
+    for (int j4 = 0; j4 < TC_HF / 4; j4++) {
+      const float4 b = lds128(tab + 4 * (T_W1 + NI * TC_HP + HALF * TC_HF + 4 * j4));
+      base[4 * j4] = b.x; base[4 * j4 + 1] = b.y; base[4 * j4 + 2] = b.z; base[4 * j4 + 3] = b.w;
     }
-    // ---- E1: layer 1 on the CUDA cores
-    if (st != st_prev) {
-      st_prev = st;
-      const float* row = xM + (in ? site : nb - 1) * cfg.nC;
 #pragma unroll
-      for (int i = 0; i < 8; i++) xs[i] = (i < NI && i < cfg.nC && in) ? row[i] : (i == NI ? 1.0f : 0.0f);
+    for (int i = 0; i < NI; i++) {
+      if (i < cfg.nC) {
 #pragma unroll
-      for (int j = 0; j < HP; j++) base[j] = lds32(tab + 4 * (N::T_W1 + NI * HP + j));
-#pragma unroll
-      for (int i = 0; i < NI; i++) {
-        if (i < cfg.nC) {
-#pragma unroll
-          for (int j4 = 0; j4 < HP / 4; j4++) {
-            const float4 w = lds128(tab + 4 * (N::T_W1 + i * HP + 4 * j4));
-            base[4 * j4] = fmaf(xs[i], w.x, base[4 * j4]); base[4 * j4 + 1] = fmaf(xs[i], w.y, base[4 * j4 + 1]);
-            base[4 * j4 + 2] = fmaf(xs[i], w.z, base[4 * j4 + 2]); base[4 * j4 + 3] = fmaf(xs[i], w.w, base[4 * j4 + 3]);
-          }
+        for (int j4 = 0; j4 < TC_HF / 4; j4++) {
+          const float4 w = lds128(tab + 4 * (T_W1 + i * TC_HP + HALF * TC_HF + 4 * j4));
+          base[4 * j4] = fmaf(xs[i], w.x, base[4 * j4]); base[4 * j4 + 1] = fmaf(xs[i], w.y, base[4 * j4 + 1]);
+          base[4 * j4 + 2] = fmaf(xs[i], w.z, base[4 * j4 + 2]); base[4 * j4 + 3] = fmaf(xs[i], w.w, base[4 * j4 + 3]);
         }
       }
     }
-    float h1[HP];
+  }
+  // h1 of this thread's features for one unit: tanh(base + Σ_covariates ζP[idx]·W1[nC + c][f]); records the covariates in xs
+  template <int HALF>
+  __device__ __forceinline__ static void layer1(const Cfg<float>& cfg, uint32_t tab, const float* __restrict__ phi,
+                                                const float* __restrict__ zetaP, int M_units, int m, bool in, const float (&base)[TC_HF],
+                                                float (&xs)[8], float (&h1)[TC_HF]) {
 #pragma unroll
-    for (int j = 0; j < HP; j++) h1[j] = base[j];
+    for (int j = 0; j < TC_HF; j++) h1[j] = base[j];
 #pragma unroll
     for (int i = 0; i < NI; i++) {
       if (i >= cfg.nC) {   // pbm covariates: ζP[idx] of this draw (pass 1: μP[idx])
@@ -515,162 +235,350 @@ k_mlp3_tc_bwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ 
         const float sv = in ? (M_units > 0 ? zetaP[(size_t)idx * M_units + m] : phi[cfg.o_muP + idx]) : 0.0f;
         xs[i] = sv;
 #pragma unroll
-        for (int j4 = 0; j4 < HP / 4; j4++) {
-          const float4 w = lds128(tab + 4 * (N::T_W1 + i * HP + 4 * j4));
+        for (int j4 = 0; j4 < TC_HF / 4; j4++) {
+          const float4 w = lds128(tab + 4 * (T_W1 + i * TC_HP + HALF * TC_HF + 4 * j4));
           h1[4 * j4] = fmaf(sv, w.x, h1[4 * j4]); h1[4 * j4 + 1] = fmaf(sv, w.y, h1[4 * j4 + 1]);
           h1[4 * j4 + 2] = fmaf(sv, w.z, h1[4 * j4 + 2]); h1[4 * j4 + 3] = fmaf(sv, w.w, h1[4 * j4 + 3]);
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < HP; j++) h1[j] = j < H1 ? fmaf(-2.0f, rcpa(ex2a(h1[j] * K2LOG2E) + 1.0f), 1.0f) : 0.0f;
-    // U is free once the gradient product of the previous tile has read it
-    if (g_pending) { mbar_wait(&barG, phaseG); phaseG ^= 1; g_pending = false; }
+    for (int j = 0; j < TC_HF; j++) h1[j] = (HALF * TC_HF + j < H1) ? tanh_scaled(h1[j] * K2LOG2E) : 0.0f;
+  }
+  // h2 of this thread's features from its accumulator columns, and its partial sums of the last layer
+  template <int HALF>
+  __device__ __forceinline__ static void layer2_epi(uint32_t tab, const float (&z)[TC_HF], float (&h2)[TC_HF], float (&z3)[2]) {
+    float b[TC_HF];
 #pragma unroll
-    for (int c = 0; c < HP / 8; c++) {
-      const float v[8] = {h1[8 * c], h1[8 * c + 1], h1[8 * c + 2], h1[8 * c + 3], h1[8 * c + 4], h1[8 * c + 5], h1[8 * c + 6], h1[8 * c + 7]};
-      store_chunk_bf(u_hi, u_lo, t, c, v);
+    for (int j4 = 0; j4 < TC_HF / 4; j4++) {
+      const float4 v = lds128(tab + 4 * (T_B2 + HALF * TC_HF + 4 * j4));
+      b[4 * j4] = v.x; b[4 * j4 + 1] = v.y; b[4 * j4 + 2] = v.z; b[4 * j4 + 3] = v.w;
     }
-    store_chunk_bf(u_hi, u_lo, t, TCB_OX / 8, xs);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (t == 0) {   // P2: z2 = h1·W2
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    z3[0] = z3[1] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < TC_HF; j++) {
+      if (HALF * TC_HF + j < H2) {
+        h2[j] = tanh_scaled(fmaf(z[j], K2LOG2E, b[j]));
+        const float2 w = lds64(tab + 4 * (T_W3 + 2 * (HALF * TC_HF + j)));
+        z3[0] = fmaf(h2[j], w.x, z3[0]);
+        z3[1] = fmaf(h2[j], w.y, z3[1]);
+      } else h2[j] = 0.0f;
+    }
+  }
+};
+
+__device__ __forceinline__ void tc_prologue(uint64_t* bar0, uint64_t* bar1, uint32_t* tmem_slot, int ncols_pow2) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    if (bar1) mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols_pow2));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+}
+// generic-proxy writes of the tiles → visible to the tensor core; TMEM reads ordered before the next MMA
+__device__ __forceinline__ void tc_publish() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cta_sync();
+}
+__device__ __forceinline__ void tc_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// =====================================================================================================
+// Forward
+// =====================================================================================================
+// shared memory: A hi | A lo ([128][32 tf32]: h1) | W2 hi | W2 lo ([32 n][32 k]) | tables | exchange float2 [2][128]
+constexpr int TF_O_A_HI = 0, TF_O_A_LO = TC_PLANE, TF_O_W_HI = 2 * TC_PLANE, TF_O_W_LO = TF_O_W_HI + 32 * 128,
+              TF_O_TAB = TF_O_W_LO + 32 * 128, TF_O_XCH = TF_O_TAB + TAB_BYTES, TF_SMEM = TF_O_XCH + 2 * TC_COLS * 8 + 1024;
+// D = F32 [4,6) = 1, A = B = TF32 [7,10) = [10,13) = 2, K-major both, N >> 3 [17,23), M >> 4 [24,29)
+constexpr uint32_t TF_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr int TF_CTAS_PER_SM = 4;
+
+template <int NI, int H1, int H2, int NOUT, int HALF>
+__device__ __forceinline__ void tc_fwd_body(const Cfg<float>& cfg, const float* __restrict__ phi, const float* __restrict__ xM,
+                                            const float* __restrict__ zetaP, int M_units, int64_t nb, float* __restrict__ mu,
+                                            uint32_t sm, uint32_t tmem, uint64_t* bar) {
+  using N = MlpTc<NI, H1, H2, NOUT>;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, q = warp & 3;
+  const int r = q * 32 + lane;
+  const uint32_t a_hi = sm + TF_O_A_HI, a_lo = sm + TF_O_A_LO, w_hi = sm + TF_O_W_HI, w_lo = sm + TF_O_W_LO, tab = sm + TF_O_TAB;
+  const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + HALF * TC_HF;
+  const int Mu = M_units > 0 ? M_units : 1;
+  const int64_t ntiles = (nb + TC_COLS - 1) / TC_COLS;
+  const int64_t ntot = ntiles * Mu;
+  const int64_t u0 = ntot * blockIdx.x / gridDim.x, u1 = ntot * (blockIdx.x + 1) / gridDim.x;
+  constexpr int KS = (H1 + 7) / 8;
+  uint32_t phase = 0;
+  float base[TC_HF], xs[8], h1[TC_HF];
+  int64_t st_prev = -1;
+  auto prepare = [&](int64_t u) {   // layer 1 of unit u into h1
+    const int64_t st = u / Mu;
+    const int m = (int)(u - st * Mu);
+    const int64_t site = st * TC_COLS + r;
+    if (st != st_prev) { st_prev = st; N::template site_base<HALF>(cfg, tab, xM, site, nb, xs, base); }
+    N::template layer1<HALF>(cfg, tab, phi, zetaP, M_units, m, site < nb, base, xs, h1);
+  };
+  if (u0 < u1) prepare(u0);
+  for (int64_t u = u0; u < u1; u++) {
+    const int64_t st = u / Mu;
+    const int m = (int)(u - st * Mu);
+    const int64_t site = st * TC_COLS + r;
+#pragma unroll
+    for (int c = 0; c < TC_HF / 4; c++)
+      store4_tf(a_hi, a_lo, r, (HALF * TC_HF) / 4 + c, h1[4 * c], h1[4 * c + 1], h1[4 * c + 2], h1[4 * c + 3]);
+    tc_publish();
+    if (HALF == 0 && t == 0) {   // z2 = h1·W2: three products per K step of 8
+      tc_after_sync();
+#pragma unroll
+      for (int s = 0; s < KS; s++) {
+        const uint32_t o = s * 32;
+        umma_tf32(tmem, make_desc(a_lo + o), make_desc(w_hi + o), TF_IDESC, s > 0 ? 1u : 0u);
+        umma_tf32(tmem, make_desc(a_hi + o), make_desc(w_lo + o), TF_IDESC, 1u);
+        umma_tf32(tmem, make_desc(a_hi + o), make_desc(w_hi + o), TF_IDESC, 1u);
+      }
+      umma_commit_(bar);
+    }
+    if (u + 1 < u1) prepare(u + 1);   // layer 1 of the next unit while the tensor core works
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_after_sync();
+    float z[TC_HF], h2[TC_HF], z3[2];
+    tmem_ld12(trow, z);
+    N::template layer2_epi<HALF>(tab, z, h2, z3);
+    // the column's two threads exchange their partial sums; thread HALF finishes output k = HALF
+    sts64(sm + TF_O_XCH + 8 * (HALF * TC_COLS + r), z3[0], z3[1]);
+    pair_sync(q);
+    const float2 o = lds64(sm + TF_O_XCH + 8 * ((1 - HALF) * TC_COLS + r));
+    constexpr int k = HALF;
+    if (k < NOUT && k < cfg.nM && site < nb) {
+      const float zk = (k == 0 ? z3[0] + o.x : z3[1] + o.y);
+      const float p = rcpa(1.0f + ex2a(-1.4426950408889634f * zk));
+      const float v = (cfg.scale_kind == HVI_SCALE_RANGE) ? p * cfg.scale_b[k] + cfg.scale_a[k]
+                                                           : cfg.scale_a[k] + cfg.scale_b[k] * normcdfinvf(p);
+      if (M_units > 0) mu[((size_t)m * cfg.nM + k) * nb + site] = v;
+      else mu[site * cfg.nM + k] = v;
+    }
+  }
+}
+
+template <int NI, int H1, int H2, int NOUT>
+__global__ void __launch_bounds__(TC_THREADS, TF_CTAS_PER_SM)
+k_mlp3_tc_fwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ phi, const float* __restrict__ xM,
+              const float* __restrict__ zetaP, int M_units, int64_t nb, float* __restrict__ mu) {
+  using N = MlpTc<NI, H1, H2, NOUT>;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int t = threadIdx.x;
+  tc_prologue(&bar, nullptr, &tmem_base_s, 32);
+  // the A tile must hold finite values everywhere the MMAs read
+  for (int e = t; e < 2 * TC_PLANE / 16; e += TC_THREADS) sts128u(sm + 16 * e, make_uint4(0u, 0u, 0u, 0u));
+  for (int e = t; e < 32 * 32; e += TC_THREADS) {   // B operand [n = output feature j][k = input feature i]
+    const int j = e >> 5, i = e & 31;
+    store1_tf(sm + TF_O_W_HI, sm + TF_O_W_LO, j, i, N::wfetch(cfg, phi, 1, H1, H2, i, j));
+  }
+  N::build_tables(cfg, phi, sm + TF_O_TAB, t, TC_THREADS);
+  tc_publish();
+  tc_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (t < TC_THREADS / 2) tc_fwd_body<NI, H1, H2, NOUT, 0>(cfg, phi, xM, zetaP, M_units, nb, mu, sm, tmem, &bar);
+  else tc_fwd_body<NI, H1, H2, NOUT, 1>(cfg, phi, xM, zetaP, M_units, nb, mu, sm, tmem, &bar);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cta_sync();
+  if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32));
+}
+
+// =====================================================================================================
+// Backward (hand adjoint of g): recompute forward, δ3 from μ̄_ζ through Φ⁻¹ and the logistic, δ2, δ1, and EVERY weight
+// gradient of the tile as ONE tensor-core product.
+//
+// Shared-memory tiles (bf16 hi/lo planes, [column of the tile][64 features] = one 128-byte swizzle row):
+//     U = [ h1 (24) | h2 (24) | x, 1 (8) | - ]          V = [ δ2 (24) | δ3 (8) | δ1 (24) | scratch ]
+//   P2  z2    = U[:, h1]·W2          K-major A (first 32 features of U; the weight rows beyond H1 are zero), 3xBF16
+//   P3  δ1pre = V[:, δ2]·W2ᵀ         K-major A (first 32 features of V),                                  3xBF16
+//   P4  G    += [U_hi | U_lo]ᵀ·V     MN-major operands: the SAME tiles, contraction over the tile's 128 columns.
+//       M = 128 = the 64 features of the hi plane and the 64 of the lo plane (descriptor LBO = distance of the
+//       planes), N = 56, so the two MMAs per K step (B = V_hi, V_lo) give all four hi/lo products; the halves are
+//       added when the accumulator is read, once per CTA.  G holds ∇W2 = h1ᵀδ2, ∇b2 = 1ᵀδ2, ∇W3 = h2ᵀδ3, ∇W1 = xᵀδ1,
+//       ∇b1 = 1ᵀδ1 (and cross blocks nobody reads) and stays in TMEM over all tiles of the CTA.
+//   The last 16 bytes of a V row (features 56..63) are read by no product: they are the exchange scratch of the column's
+//   two threads.
+// =====================================================================================================
+constexpr int TB_NV = 2 * TC_HP + 8;           // features of V = N of the gradient product (56)
+constexpr int TB_OX = 2 * TC_HP;               // first feature of [x, 1] in U
+constexpr int TB_OD3 = TC_HP, TB_OD1 = TC_HP + 8;
+// shared memory: U hi | U lo | V hi | V lo | W hi | W lo (rows n: [W2[k][n], k < 32 | W2[n][k − 32]]) | tables | slots | xw
+constexpr int TB_O_U_HI = 0, TB_O_U_LO = TC_PLANE, TB_O_V_HI = 2 * TC_PLANE, TB_O_V_LO = 3 * TC_PLANE, TB_O_W_HI = 4 * TC_PLANE,
+              TB_O_W_LO = TB_O_W_HI + 32 * 128, TB_O_TAB = TB_O_W_LO + 32 * 128, TB_O_SLOT = TB_O_TAB + TAB_BYTES,
+              TB_O_XW = TB_O_SLOT + 8 * 8 * 4;
+__host__ __device__ constexpr int tb_smem_bytes(int nxa) { return TB_O_XW + nxa * 8 + 1024; }
+// D = F32, A = B = BF16 (format 1), N >> 3 [17,23), M >> 4 [24,29); bits 15/16: A/B MN-major
+constexpr uint32_t TB_IDESC_K = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t TB_IDESC_G = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TB_NV >> 3) << 17) |
+                                ((uint32_t)(128 >> 4) << 24);
+constexpr int TB_TMEM_COLS = 128;              // G (64) | z2 (32) | δ1pre (32)
+constexpr int TB_CTAS_PER_SM = 3;
+
+template <int NI, int H1, int H2, int NOUT, int HALF>
+__device__ __forceinline__ void tc_bwd_body(const Cfg<float>& cfg, const float* __restrict__ phi, const float* __restrict__ xM,
+                                            const float* __restrict__ zetaP, const float* __restrict__ mubar, int M_units, int64_t nb,
+                                            bool want_x, uint32_t sm, uint32_t tmem, uint64_t* bar, uint64_t* barG, int64_t u0, int64_t u1) {
+  using N = MlpTc<NI, H1, H2, NOUT>;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, q = warp & 3;
+  const int r = q * 32 + lane;
+  const uint32_t u_hi = sm + TB_O_U_HI, u_lo = sm + TB_O_U_LO, v_hi = sm + TB_O_V_HI, v_lo = sm + TB_O_V_LO;
+  const uint32_t w_hi = sm + TB_O_W_HI, w_lo = sm + TB_O_W_LO, tab = sm + TB_O_TAB;
+  const uint32_t tG = tmem, tZ2 = tmem + 64, tD1 = tmem + 96;
+  const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+  // exchange scratch of this column: chunk 7 of its V rows (hi plane: partial sums of the last layer, lo plane: δ3)
+  const uint32_t xch_z = v_hi + r * 128 + ((7 ^ (r & 7)) << 4), xch_d = v_lo + r * 128 + ((7 ^ (r & 7)) << 4);
+  const int Mu = M_units > 0 ? M_units : 1;
+  constexpr int F0 = HALF * TC_HF;   // this thread's first feature
+  uint32_t phase = 0, phaseG = 0;
+  bool g_pending = false, first = true;
+  float base[TC_HF], xs[8];
+  int64_t st_prev = -1;
+  for (int64_t u = u0; u < u1; u++) {
+    const int64_t st = u / Mu;
+    const int m = (int)(u - st * Mu);
+    const int64_t site = st * TC_COLS + r;
+    const bool in = site < nb;
+    // cotangent of this thread's output k = HALF (in flight during layer 1)
+    float mb = 0.0f;
+    if (in && HALF < NOUT && HALF < cfg.nM)
+      mb = M_units > 0 ? mubar[((size_t)m * cfg.nM + HALF) * nb + site] : mubar[site * cfg.nM + HALF];
+    // ---- E1: layer 1 on the CUDA cores
+    if (st != st_prev) { st_prev = st; N::template site_base<HALF>(cfg, tab, xM, site, nb, xs, base); }
+    float h1[TC_HF];
+    N::template layer1<HALF>(cfg, tab, phi, zetaP, M_units, m, in, base, xs, h1);
+    // U is free once the gradient product of the previous tile has read it
+    if (g_pending) { mbar_wait(barG, phaseG); phaseG ^= 1; g_pending = false; }
+#pragma unroll
+    for (int c = 0; c < TC_HF / 4; c++) store4_bf(u_hi, u_lo, r, F0 + 4 * c, h1[4 * c], h1[4 * c + 1], h1[4 * c + 2], h1[4 * c + 3]);
+    if (HALF == 0) {
+      store4_bf(u_hi, u_lo, r, TB_OX, xs[0], xs[1], xs[2], xs[3]);
+      store4_bf(u_hi, u_lo, r, TB_OX + 4, xs[4], xs[5], xs[6], xs[7]);
+    }
+    tc_publish();
+    if (HALF == 0 && t == 0) {   // P2: z2 = h1·W2
+      tc_after_sync();
 #pragma unroll
       for (int s = 0; s < 2; s++) {
         const uint32_t o = s * 32;
-        umma_bf16_(tZ2, make_desc(u_lo + o), make_desc(w_hi + o), TCB_IDESC_K, s > 0 ? 1u : 0u);
-        umma_bf16_(tZ2, make_desc(u_hi + o), make_desc(w_lo + o), TCB_IDESC_K, 1u);
-        umma_bf16_(tZ2, make_desc(u_hi + o), make_desc(w_hi + o), TCB_IDESC_K, 1u);
+        umma_bf16_(tZ2, make_desc(u_lo + o), make_desc(w_hi + o), TB_IDESC_K, s > 0 ? 1u : 0u);
+        umma_bf16_(tZ2, make_desc(u_hi + o), make_desc(w_lo + o), TB_IDESC_K, 1u);
+        umma_bf16_(tZ2, make_desc(u_hi + o), make_desc(w_hi + o), TB_IDESC_K, 1u);
       }
-      umma_commit_(&bar);
+      umma_commit_(bar);
     }
-    mbar_wait(&bar, phase);
+    mbar_wait(bar, phase);
     phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_after_sync();
     // ---- E2: h2, outputs, δ3, δ2
-    float d2[HP];
-    float d3[2] = {0.0f, 0.0f};
     {
-      float z[HP];
+      float z[TC_HF], h2[TC_HF], z3[2];
+      tmem_ld12(tZ2 + lane_sel + F0, z);
+      N::template layer2_epi<HALF>(tab, z, h2, z3);
 #pragma unroll
-      for (int c = 0; c < HP / 8; c++) {
-        float v[8];
-        tmem_ld8(tZ2 + lane_sel + 8 * c, v);
-#pragma unroll
-        for (int q = 0; q < 8; q++) z[8 * c + q] = v[q];
-      }
-      tmem_wait_ld();
-      float h2[HP];
-      float z3[2] = {0.0f, 0.0f};
-#pragma unroll
-      for (int j = 0; j < HP; j++) {
-        if (j < H2) {
-          h2[j] = fmaf(-2.0f, rcpa(ex2a(fmaf(z[j], K2LOG2E, lds32(tab + 4 * (N::T_B2 + j)))) + 1.0f), 1.0f);
-          const float2 w = lds64(tab + 4 * (N::T_W3 + 2 * j));
-          z3[0] = fmaf(h2[j], w.x, z3[0]);
-          z3[1] = fmaf(h2[j], w.y, z3[1]);
-        } else h2[j] = 0.0f;
-      }
-      // δ3 = μ̄ · dμ/dp · p(1−p)   (NormalScaling: dμ/dp = σ·√(2π)·exp(q²/2), q = Φ⁻¹(p); src/ModelApplicator.jl:168)
-#pragma unroll
-      for (int k = 0; k < NOUT; k++) {
-        if (k < cfg.nM) {
-          const float pk = rcpa(1.0f + ex2a(-1.4426950408889634f * z3[k]));
-          float d;
-          if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb[k] * cfg.scale_b[k];
-          else {
-            const float q = normcdfinvf(pk);
-            d = mb[k] * cfg.scale_b[k] * 2.50662827463100050242f * ex2a(0.72134752044448170368f * q * q);
-          }
-          d3[k] = in ? d * pk * (1.0f - pk) : 0.0f;
+      for (int c = 0; c < TC_HF / 4; c++)
+        store4_bf(u_hi, u_lo, r, TC_HP + F0 + 4 * c, h2[4 * c], h2[4 * c + 1], h2[4 * c + 2], h2[4 * c + 3]);
+      sts64(xch_z + 8 * HALF, z3[0], z3[1]);
+      pair_sync(q);
+      const float2 o = lds64(xch_z + 8 * (1 - HALF));
+      // δ3[k] = μ̄ · dμ/dp · p(1−p)   (NormalScaling: dμ/dp = σ·√(2π)·exp(q²/2), q = Φ⁻¹(p); src/ModelApplicator.jl:168), k = HALF
+      constexpr int k = HALF;
+      float d3k = 0.0f;
+      if (k < NOUT && k < cfg.nM) {
+        const float zk = (k == 0 ? z3[0] + o.x : z3[1] + o.y);
+        const float pk = rcpa(1.0f + ex2a(-1.4426950408889634f * zk));
+        float d;
+        if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb * cfg.scale_b[k];
+        else {
+          const float qn = normcdfinvf(pk);
+          d = mb * cfg.scale_b[k] * 2.50662827463100050242f * ex2a(0.72134752044448170368f * qn * qn);
         }
+        d3k = in ? d * pk * (1.0f - pk) : 0.0f;
       }
+      sts32(xch_d + 4 * HALF, d3k);
+      pair_sync(q);
+      const float2 d3 = lds64(xch_d);
+      if (HALF == 0) {
+        store4_bf(v_hi, v_lo, r, TB_OD3, d3.x, d3.y, 0.0f, 0.0f);
+        store4_bf(v_hi, v_lo, r, TB_OD3 + 4, 0.0f, 0.0f, 0.0f, 0.0f);
+      }
+      float d2[TC_HF];
 #pragma unroll
-      for (int j = 0; j < HP; j++) {
-        if (j < H2) {
-          const float2 w = lds64(tab + 4 * (N::T_W3 + 2 * j));
-          d2[j] = fmaf(d3[0], w.x, d3[1] * w.y) * fmaf(-h2[j], h2[j], 1.0f);
+      for (int j = 0; j < TC_HF; j++) {
+        if (F0 + j < H2) {
+          const float2 w = lds64(tab + 4 * (T_W3 + 2 * (F0 + j)));
+          d2[j] = fmaf(d3.x, w.x, d3.y * w.y) * fmaf(-h2[j], h2[j], 1.0f);
         } else d2[j] = 0.0f;
       }
 #pragma unroll
-      for (int c = 0; c < HP / 8; c++) {
-        const float v[8] = {h2[8 * c], h2[8 * c + 1], h2[8 * c + 2], h2[8 * c + 3], h2[8 * c + 4], h2[8 * c + 5], h2[8 * c + 6], h2[8 * c + 7]};
-        store_chunk_bf(u_hi, u_lo, t, HP / 8 + c, v);
-        const float w[8] = {d2[8 * c], d2[8 * c + 1], d2[8 * c + 2], d2[8 * c + 3], d2[8 * c + 4], d2[8 * c + 5], d2[8 * c + 6], d2[8 * c + 7]};
-        store_chunk_bf(v_hi, v_lo, t, c, w);
-      }
-      const float v3[8] = {d3[0], d3[1], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-      store_chunk_bf(v_hi, v_lo, t, TCB_OD3 / 8, v3);
+      for (int c = 0; c < TC_HF / 4; c++) store4_bf(v_hi, v_lo, r, F0 + 4 * c, d2[4 * c], d2[4 * c + 1], d2[4 * c + 2], d2[4 * c + 3]);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (t == 0) {   // P3: δ1pre = δ2·W2ᵀ  (the transposed weights sit in features 32..63 of the W rows)
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_publish();
+    if (HALF == 0 && t == 0) {   // P3: δ1pre = δ2·W2ᵀ  (the transposed weights sit in features 32..63 of the W rows)
+      tc_after_sync();
 #pragma unroll
       for (int s = 0; s < 2; s++) {
         const uint32_t o = s * 32;
-        umma_bf16_(tD1, make_desc(v_lo + o), make_desc(w_hi + 64 + o), TCB_IDESC_K, s > 0 ? 1u : 0u);
-        umma_bf16_(tD1, make_desc(v_hi + o), make_desc(w_lo + 64 + o), TCB_IDESC_K, 1u);
-        umma_bf16_(tD1, make_desc(v_hi + o), make_desc(w_hi + 64 + o), TCB_IDESC_K, 1u);
+        umma_bf16_(tD1, make_desc(v_lo + o), make_desc(w_hi + 64 + o), TB_IDESC_K, s > 0 ? 1u : 0u);
+        umma_bf16_(tD1, make_desc(v_hi + o), make_desc(w_lo + 64 + o), TB_IDESC_K, 1u);
+        umma_bf16_(tD1, make_desc(v_hi + o), make_desc(w_hi + 64 + o), TB_IDESC_K, 1u);
       }
-      umma_commit_(&bar);
+      umma_commit_(bar);
     }
-    mbar_wait(&bar, phase);
+    mbar_wait(bar, phase);
     phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_after_sync();
     // ---- E3: δ1 = δ1pre ⊙ (1 − h1²), cotangent of the pbm covariates
     {
-      float d1[HP];
+      float d1[TC_HF];
+      tmem_ld12(tD1 + lane_sel + F0, d1);
 #pragma unroll
-      for (int c = 0; c < HP / 8; c++) {
-        float v[8];
-        tmem_ld8(tD1 + lane_sel + 8 * c, v);
+      for (int j = 0; j < TC_HF; j++) d1[j] = (F0 + j < H1) ? d1[j] * fmaf(-h1[j], h1[j], 1.0f) : 0.0f;
 #pragma unroll
-        for (int q = 0; q < 8; q++) d1[8 * c + q] = v[q];
-      }
-      tmem_wait_ld();
-#pragma unroll
-      for (int j = 0; j < HP; j++) d1[j] = j < H1 ? d1[j] * fmaf(-h1[j], h1[j], 1.0f) : 0.0f;
-#pragma unroll
-      for (int c = 0; c < HP / 8; c++) {
-        const float v[8] = {d1[8 * c], d1[8 * c + 1], d1[8 * c + 2], d1[8 * c + 3], d1[8 * c + 4], d1[8 * c + 5], d1[8 * c + 6], d1[8 * c + 7]};
-        store_chunk_bf(v_hi, v_lo, t, TCB_OD1 / 8 + c, v);
-      }
-      if (part_x) {
+      for (int c = 0; c < TC_HF / 4; c++)
+        store4_bf(v_hi, v_lo, r, TB_OD1 + F0 + 4 * c, d1[4 * c], d1[4 * c + 1], d1[4 * c + 2], d1[4 * c + 3]);
+      if (want_x) {
 #pragma unroll
         for (int i = 0; i < NI; i++) {
-          if (i >= cfg.nC) {   // x̄[i] = Σ_j W1[i][j] δ1[j], summed over the warp's columns (fixed-order butterfly)
+          if (i >= cfg.nC) {   // x̄[i] = Σ_j W1[i][j] δ1[j]: this thread's features, summed over the warp's columns (fixed-order butterfly)
             float sx = 0.0f;
 #pragma unroll
-            for (int j = 0; j < H1; j++) sx = fmaf(lds32(tab + 4 * (N::T_W1 + i * HP + j)), d1[j], sx);
+            for (int j4 = 0; j4 < TC_HF / 4; j4++) {
+              const float4 w = lds128(tab + 4 * (T_W1 + i * TC_HP + F0 + 4 * j4));
+              sx = fmaf(w.x, d1[4 * j4], sx); sx = fmaf(w.y, d1[4 * j4 + 1], sx);
+              sx = fmaf(w.z, d1[4 * j4 + 2], sx); sx = fmaf(w.w, d1[4 * j4 + 3], sx);
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
-            if (lane == 0) sts32(sm + N::O_SLOT + 4 * (warp * 8 + (i - cfg.nC)), sx);
+            if (lane == 0) sts32(sm + TB_O_SLOT + 4 * (warp * 8 + (i - cfg.nC)), sx);
           }
         }
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (t == 0) {   // P4: G += [U_hi | U_lo]ᵀ·(V_hi + V_lo), contraction over the 128 columns of the tile
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_publish();
+    if (HALF == 0 && t == 0) {   // P4: G += [U_hi | U_lo]ᵀ·(V_hi + V_lo), contraction over the 128 columns of the tile
+      tc_after_sync();
 #pragma unroll
-      for (int s = 0; s < TCS_BM / 16; s++) {
+      for (int s = 0; s < TC_COLS / 16; s++) {
         const uint32_t o = s * 2048;
-        umma_bf16_(tG, make_desc_mn_(u_hi + o, TCB_PLANE), make_desc_mn_(v_lo + o, TCB_PLANE), TCB_IDESC_G, (first && s == 0) ? 0u : 1u);
-        umma_bf16_(tG, make_desc_mn_(u_hi + o, TCB_PLANE), make_desc_mn_(v_hi + o, TCB_PLANE), TCB_IDESC_G, 1u);
+        umma_bf16_(tG, make_desc_mn_(u_hi + o, TC_PLANE), make_desc_mn_(v_lo + o, TC_PLANE), TB_IDESC_G, (first && s == 0) ? 0u : 1u);
+        umma_bf16_(tG, make_desc_mn_(u_hi + o, TC_PLANE), make_desc_mn_(v_hi + o, TC_PLANE), TB_IDESC_G, 1u);
       }
-      umma_commit_(&barG);
+      umma_commit_(barG);
     }
-    if (part_x && t == 32) {   // the four warps' covariate cotangents of this tile, fixed order, into the draw's double sum
+    if (want_x && HALF == 1 && t == TC_THREADS / 2) {   // the eight warps' covariate cotangents of this tile, fixed order
       for (int c = 0; c < cfg.npc; c++) {
-        const float sx = (lds32(sm + N::O_SLOT + 4 * c) + lds32(sm + N::O_SLOT + 4 * (8 + c))) +
-                         (lds32(sm + N::O_SLOT + 4 * (16 + c)) + lds32(sm + N::O_SLOT + 4 * (24 + c)));
-        const uint32_t a = sm + N::O_XW + 8 * ((M_units > 0 ? m : 0) * cfg.npc + c);
+        float sx = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) sx += lds32(sm + TB_O_SLOT + 4 * (w * 8 + c));
+        const uint32_t a = sm + TB_O_XW + 8 * ((M_units > 0 ? m : 0) * cfg.npc + c);
         double acc;
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(acc) : "r"(a));
         acc += (double)sx;
@@ -680,65 +588,97 @@ k_mlp3_tc_bwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ 
     first = false;
     g_pending = true;
   }
-  if (g_pending) { mbar_wait(&barG, phaseG); phaseG ^= 1; }
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  // ---- read G: lane r < 64 holds the hi-plane row of feature r, lane 64 + r the lo-plane row; add, scatter into ϕg's layout
-  float* red = reinterpret_cast<float*>(smem_raw) + ((sm - smem_u32(smem_raw)) >> 2);   // reuse of the U planes: [64][TCB_NV]
-  float g[TCB_NV];
-  if (u1 > u0) {
-#pragma unroll
-    for (int c = 0; c < TCB_NV / 8; c++) {
-      float v[8];
-      tmem_ld8(tG + lane_sel + 8 * c, v);
-#pragma unroll
-      for (int q = 0; q < 8; q++) g[8 * c + q] = v[q];
-    }
-    tmem_wait_ld();
-  } else {
-#pragma unroll
-    for (int q = 0; q < TCB_NV; q++) g[q] = 0.0f;
+  if (g_pending) { mbar_wait(barG, phaseG); phaseG ^= 1; }
+}
+
+template <int NI, int H1, int H2, int NOUT>
+__global__ void __launch_bounds__(TC_THREADS, TB_CTAS_PER_SM)
+k_mlp3_tc_bwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ phi, const float* __restrict__ xM,
+              const float* __restrict__ zetaP, const float* __restrict__ mubar, int M_units, int64_t nb,
+              double* __restrict__ part, double* __restrict__ part_x) {
+  using N = MlpTc<NI, H1, H2, NOUT>;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ uint64_t bar, barG;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int Mu = M_units > 0 ? M_units : 1;
+  const int nxa = Mu * cfg.npc;
+  tc_prologue(&bar, &barG, &tmem_base_s, TB_TMEM_COLS);
+  // zero the operand tiles: padding features must be finite (they meet zero weight rows in P2 / P3)
+  for (int e = t; e < (4 * TC_PLANE) / 16; e += TC_THREADS) sts128u(sm + 16 * e, make_uint4(0u, 0u, 0u, 0u));
+  for (int e = t; e < 32 * 64; e += TC_THREADS) {
+    const int n = e >> 6, k = e & 63;
+    const float w = k < 32 ? N::wfetch(cfg, phi, 1, H1, H2, k, n) : N::wfetch(cfg, phi, 1, H1, H2, n, k - 32);
+    store1_bf(sm + TB_O_W_HI, sm + TB_O_W_LO, n, k, w);
   }
-  if (t >= 64) {
+  N::build_tables(cfg, phi, sm + TB_O_TAB, t, TC_THREADS);
+  for (int e = t; e < nxa * 2; e += TC_THREADS) sts32(sm + TB_O_XW + 4 * e, 0.0f);
+  tc_publish();
+  tc_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  // this CTA's contiguous range of units u = site_tile·Mu + m (draws of one site tile are consecutive)
+  const int64_t ntot = ((nb + TC_COLS - 1) / TC_COLS) * Mu;
+  const int64_t u0 = ntot * blockIdx.x / gridDim.x, u1 = ntot * (blockIdx.x + 1) / gridDim.x;
+  if (t < TC_THREADS / 2) tc_bwd_body<NI, H1, H2, NOUT, 0>(cfg, phi, xM, zetaP, mubar, M_units, nb, part_x != nullptr, sm, tmem, &bar, &barG, u0, u1);
+  else tc_bwd_body<NI, H1, H2, NOUT, 1>(cfg, phi, xM, zetaP, mubar, M_units, nb, part_x != nullptr, sm, tmem, &bar, &barG, u0, u1);
+  tc_after_sync();
+  // ---- read G: lane r < 64 holds the hi-plane row of feature r, lane 64 + r the lo-plane row; add, scatter into ϕg's layout.
+  // warps 0-3 read columns 0..27 of their lane quarter, warps 4-7 columns 28..55
+  float* red = reinterpret_cast<float*>(smem_raw) + ((sm - smem_u32(smem_raw)) >> 2);   // reuse of the U planes: [128][TB_NV]
+  cta_sync();   // every thread has seen the last gradient product complete before U is overwritten
+  {
+    const int q = warp & 3, hf = warp >> 2, r = q * 32 + lane;
+    float g[28];
+    if (u1 > u0) {
+      const uint32_t a = tmem + ((uint32_t)(q * 32) << 16) + 28 * hf;
+      tmem_ld8(a, g); tmem_ld8(a + 8, g + 8); tmem_ld8(a + 16, g + 16); tmem_ld4(a + 24, g + 24);
+      tmem_wait_ld();
+    } else {
 #pragma unroll
-    for (int q = 0; q < TCB_NV; q++) red[(t - 64) * TCB_NV + q] = g[q];
+      for (int c = 0; c < 28; c++) g[c] = 0.0f;
+    }
+#pragma unroll
+    for (int c = 0; c < 28; c++) red[r * TB_NV + 28 * hf + c] = g[c];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   double* out = part + (size_t)blockIdx.x * cfg.nphig;
-  if (t < 64) {
-#pragma unroll
-    for (int q = 0; q < TCB_NV; q++) g[q] += red[t * TCB_NV + q];
-    if (t < H1) {                       // row h1[t]: ∇W2[t][j]
-#pragma unroll
-      for (int j = 0; j < H2; j++) out[cfg.woff[1] + t * H2 + j] = (double)g[j];
-    } else if (t >= HP && t < HP + H2) {   // row h2[t − HP]: ∇W3[·][k]
-#pragma unroll
-      for (int k = 0; k < NOUT; k++) out[cfg.woff[2] + (t - HP) * NOUT + k] = (double)g[TCB_OD3 + k];
-    } else if (t >= TCB_OX && t < TCB_OX + NI) {   // row x[i]: ∇W1[i][j]
-#pragma unroll
-      for (int j = 0; j < H1; j++) out[cfg.woff[0] + (t - TCB_OX) * H1 + j] = (double)g[TCB_OD1 + j];
-    } else if (t == TCB_OX + NI) {       // row of the constant 1: ∇b1 = 1ᵀδ1, ∇b2 = 1ᵀδ2
-#pragma unroll
-      for (int j = 0; j < H1; j++) out[cfg.boff[0] + j] = (double)g[TCB_OD1 + j];
-#pragma unroll
-      for (int j = 0; j < H2; j++) out[cfg.boff[1] + j] = (double)g[j];
+  for (int e = t; e < 64 * TB_NV; e += TC_THREADS) {
+    const int f = e / TB_NV, c = e % TB_NV;   // feature f of U (row of G), feature c of V (column of G)
+    const double v = (double)red[f * TB_NV + c] + (double)red[(64 + f) * TB_NV + c];
+    if (f < TC_HP) {                                   // row h1[f]: ∇W2[f][j]
+      if (f < H1 && c < H2) out[cfg.woff[1] + f * H2 + c] = v;
+    } else if (f < 2 * TC_HP) {                        // row h2[f − HP]: ∇W3[·][k]
+      const int j = f - TC_HP, k = c - TB_OD3;
+      if (j < H2 && k >= 0 && k < NOUT) out[cfg.woff[2] + j * NOUT + k] = v;
+    } else {                                           // rows x[i] and the constant 1
+      const int i = f - TB_OX;
+      if (i < NI) {
+        const int j = c - TB_OD1;
+        if (j >= 0 && j < H1) out[cfg.woff[0] + i * H1 + j] = v;
+      } else if (i == NI) {                            // ∇b1 = 1ᵀδ1, ∇b2 = 1ᵀδ2
+        if (c < H2) out[cfg.boff[1] + c] = v;
+        const int j = c - TB_OD1;
+        if (j >= 0 && j < H1) out[cfg.boff[0] + j] = v;
+      }
     }
   }
   if (part_x) {
-    for (int e = t; e < nxa; e += TCS_BM) {
+    for (int e = t; e < nxa; e += TC_THREADS) {
       double v;
-      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sm + N::O_XW + 8 * (uint32_t)e));
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sm + TB_O_XW + 8 * (uint32_t)e));
       part_x[(size_t)blockIdx.x * nxa + e] = v;
     }
   }
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TCB_TMEM_COLS));
+  if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TB_TMEM_COLS));
 }
 
 bool tc_match(const Cfg<float>& c, int ni, int h1, int h2, int no) {
   return c.nL == 3 && c.l_in[0] == ni && c.l_out[0] == h1 && c.l_out[1] == h2 && c.l_out[2] == no &&
          c.l_act[0] == HVI_ACT_TANH && c.l_act[1] == HVI_ACT_TANH && c.l_act[2] == HVI_ACT_LOGISTIC && c.l_bias[0] &&
-         c.l_bias[1] && !c.l_bias[2] && c.nM <= no && c.nC <= ni;
+         c.l_bias[1] && !c.l_bias[2] && c.nM <= no && c.nC <= ni && c.npc <= 8;
 }
 int tc_mode() {   // HVI_MLP_TC: 0 off, 1 forward only, 2 (default) forward and backward
   const char* e = getenv("HVI_MLP_TC");
@@ -762,15 +702,14 @@ cudaError_t launch_mlp3_tc_fwd(const Launch& L, const Cfg<float>& cfg, const flo
   if (tc_mode() < 1) return cudaErrorNotSupported;
 #define X(NI, H1, H2, NO_)                                                                                  \
   if (tc_match(cfg, NI, H1, H2, NO_)) {                                                                     \
-    using N = MlpTc<NI, H1, H2, NO_>;                                                                       \
     auto kern = k_mlp3_tc_fwd<NI, H1, H2, NO_>;                                                             \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, N::SMEM_BYTES); \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM);       \
     if (e != cudaSuccess) return e;                                                                         \
-    const int64_t ntot = ((nb + TCS_BM - 1) / TCS_BM) * (M_units > 0 ? M_units : 1);                        \
+    const int64_t ntot = ((nb + TC_COLS - 1) / TC_COLS) * (M_units > 0 ? M_units : 1);                      \
     int64_t blocks = ntot;                                                                                  \
-    if (blocks > (int64_t)L.sm_count * TCS_CTAS_PER_SM) blocks = (int64_t)L.sm_count * TCS_CTAS_PER_SM;     \
+    if (blocks > (int64_t)L.sm_count * TF_CTAS_PER_SM) blocks = (int64_t)L.sm_count * TF_CTAS_PER_SM;       \
     if (blocks < 1) blocks = 1;                                                                             \
-    kern<<<(int)blocks, TCS_BM, N::SMEM_BYTES, L.stream>>>(cfg, phi, xM, zetaP, M_units, nb, mu);           \
+    kern<<<(int)blocks, TC_THREADS, TF_SMEM, L.stream>>>(cfg, phi, xM, zetaP, M_units, nb, mu);             \
     HVI_TC_CHECK();                                                                                         \
     return cudaSuccess;                                                                                     \
   }
@@ -785,19 +724,18 @@ cudaError_t launch_mlp3_tc_bwd(const Launch& L, const Cfg<float>& cfg, const flo
   if (tc_mode() < 2) return cudaErrorNotSupported;
 #define X(NI, H1, H2, NO_)                                                                                  \
   if (tc_match(cfg, NI, H1, H2, NO_)) {                                                                     \
-    using N = MlpTcB<NI, H1, H2, NO_>;                                                                      \
     const int nxa = (M_units > 0 ? M_units : 1) * cfg.npc;                                                  \
-    const int smem = N::smem_bytes(nxa);                                                                    \
+    const int smem = tb_smem_bytes(nxa);                                                                    \
     if (smem > 200 * 1024) return cudaErrorNotSupported;                                                    \
     auto kern = k_mlp3_tc_bwd<NI, H1, H2, NO_>;                                                             \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
     if (e != cudaSuccess) return e;                                                                         \
-    const int64_t ntot = ((nb + TCS_BM - 1) / TCS_BM) * (M_units > 0 ? M_units : 1);                        \
+    const int64_t ntot = ((nb + TC_COLS - 1) / TC_COLS) * (M_units > 0 ? M_units : 1);                      \
     int64_t blocks = ntot;                                                                                  \
-    const int64_t cap = nblk_max < L.sm_count * TCB_CTAS_PER_SM ? nblk_max : L.sm_count * TCB_CTAS_PER_SM;  \
+    const int64_t cap = nblk_max < L.sm_count * TB_CTAS_PER_SM ? nblk_max : L.sm_count * TB_CTAS_PER_SM;    \
     if (blocks > cap) blocks = cap;                                                                         \
     if (blocks < 1) blocks = 1;                                                                             \
-    kern<<<(int)blocks, TCS_BM, smem, L.stream>>>(cfg, phi, xM, zetaP, mubar, M_units, nb, part, part_x);   \
+    kern<<<(int)blocks, TC_THREADS, smem, L.stream>>>(cfg, phi, xM, zetaP, mubar, M_units, nb, part, part_x); \
     HVI_TC_CHECK();                                                                                         \
     *nblk_out = (int)blocks;                                                                                \
     return cudaSuccess;                                                                                     \
