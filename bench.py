@@ -222,7 +222,9 @@ def dominant_roofline(args, prob, nb, M, kt, peaks, sampler, local):
     alg_flop = 3.0 * 2.0 * mac * cols
     peak = float(peaks.get("bf16_tflops_sustained", 1384.0))
     achieved = alg_flop / (g_ms * 1e-3) / 1e12
-    kernel = "k_gemm_bf3 chain (tcgen05 kind::f16, TMA)" if wide else "k_mlp3_mma_fwd + k_mlp3_mma_bwd (mma.sync)"
+    tc_small = os.environ.get("HVI_MLP_TC", "2") != "0"
+    kernel = ("k_gemm_bf3 chain (tcgen05 kind::f16, TMA)" if wide else
+              "k_mlp3_tc_fwd + k_mlp3_tc_bwd (tcgen05, TMEM accumulators)" if tc_small else "k_mlp3_mma_fwd + k_mlp3_mma_bwd (mma.sync)")
     return {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": None,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)" if peaks
