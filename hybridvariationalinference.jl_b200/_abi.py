@@ -11,7 +11,7 @@ import os
 HVI_MAX_PAR = 8
 HVI_MAX_LAYERS = 8
 
-HVI_OK, HVI_EINVAL, HVI_ECUDA, HVI_ENONFINITE, HVI_ENODATA, HVI_ENOMEM = range(6)
+HVI_OK, HVI_EINVAL, HVI_ECUDA, HVI_ENONFINITE, HVI_ENODATA, HVI_ENOMEM, HVI_ENCCL = range(7)
 HVI_F32, HVI_F64 = 0, 1
 HVI_MEM_HOST, HVI_MEM_DEVICE = 0, 1
 HVI_TR_IDENTITY, HVI_TR_EXP, HVI_TR_LOGISTIC = 0, 1, 2
@@ -83,6 +83,11 @@ SYMBOLS = [
     ("hvi_neg_elbo_grad", _INT, [_P, _I32, _P, _P, _P, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_rng", _INT, [_P, _I32, _P, _U64, _I64, _INT, _DP, _DP, _P]),
     ("hvi_neg_elbo_grad_async", _INT, [_P, _I32, _P, _P, _P, _U64, _I64, _P, _P]),
+    ("hvi_nccl_unique_id", _INT, [_P]),
+    ("hvi_plan_comm_init", _INT, [_P, _P, _I32, _I32]),
+    ("hvi_plan_comm_destroy", _INT, [_P]),
+    ("hvi_allreduce_result", _INT, [_P, _P, _P]),
+    ("hvi_neg_elbo_grad_sharded", _INT, [_P, _I32, _P, _P, _P, _U64, _I64, _INT, _DP, _DP, _P]),
     ("hvi_loss_gf_grad", _INT, [_P, _P, _INT, _DP, _P]),
     ("hvi_adam_init", _INT, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double]),
     ("hvi_adam_run", _INT, [_P, _I32, _I32, _U64, _I64, _DP]),

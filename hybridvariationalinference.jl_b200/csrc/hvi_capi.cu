@@ -1,7 +1,9 @@
 // hvi_capi.cu -- plan management and the extern "C" boundary (include/hvi_b200.h).
 // Reference citations (file:line) are relative to /root/reference.
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -76,6 +78,8 @@ struct hvi_plan {
   double* d_red;
   void* d_grad;
   double* h_out;  // pinned
+  void* nccl_comm = nullptr;   // ncclComm_t of a site-sharded job (hvi_plan_comm_init), NULL otherwise
+  int nccl_rank = 0, nccl_world = 1;
   void* h_grad;   // pinned
   double* d_ls; int64_t cap_ls;       // per-warp Σ log σ partials of hvi_predict
   // device-resident Adam state (hvi_adam_*): ϕ in the working type, moments in double
@@ -332,6 +336,7 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->own_stream && p->own_stream != p->stream) cudaStreamSynchronize(p->own_stream);
   if (p->user_pending && p->ev_user) cudaEventSynchronize(p->ev_user);
+  if (p->nccl_comm) hvi_plan_comm_destroy(p);
   if (p->adam_graph) cudaGraphExecDestroy(p->adam_graph);
   if (p->gpbm) generic_pbm_destroy(p->gpbm);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
@@ -1062,9 +1067,57 @@ static int enqueue_fused(hvi_plan* p, int M, T* phi, double* out, T* grad_T, cud
   return HVI_OK;
 }
 
+// ---- NCCL through dlopen (the library does not link against it): one all-reduce per evaluation of a site-sharded job ----
+struct HviNcclId { char internal[128]; };   // ncclUniqueId, passed by value to ncclCommInitRank
+namespace {
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, HviNcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {getenv("HVI_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n) continue;
+      api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.h) break;
+    }
+    if (api.h) {
+      *(void**)(&api.GetUniqueId) = dlsym(api.h, "ncclGetUniqueId");
+      *(void**)(&api.CommInitRank) = dlsym(api.h, "ncclCommInitRank");
+      *(void**)(&api.CommDestroy) = dlsym(api.h, "ncclCommDestroy");
+      *(void**)(&api.AllReduce) = dlsym(api.h, "ncclAllReduce");
+      *(void**)(&api.GetErrorString) = dlsym(api.h, "ncclGetErrorString");
+      if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce) api.h = nullptr;
+    }
+  }
+  return api.h ? &api : nullptr;
+}
+#define NCCL_FAIL(p, rc_, what)                                                                                       \
+  PLAN_FAIL(p, HVI_ENCCL, "%s: %s", what, (nccl_api() && nccl_api()->GetErrorString) ? nccl_api()->GetErrorString(rc_) : "NCCL error")
+
+// Σ over the ranks of out[0 .. n_phi + 8) (double, in place) on stream s
+static int nccl_allreduce_out(hvi_plan* p, double* out_dev, cudaStream_t s) {
+  if (!p->nccl_comm) PLAN_FAIL(p, HVI_EINVAL, "hvi_plan_comm_init has not been called");
+  NcclApi* api = nccl_api();
+  if (!api) PLAN_FAIL(p, HVI_ENCCL, "libnccl.so.2 could not be loaded");
+  const int nphi = p->dtype == HVI_F32 ? cfg_of<float>(p).nphi : cfg_of<double>(p).nphi;
+  const int rc = api->AllReduce(out_dev, out_dev, (size_t)(nphi + 8), /* ncclFloat64 */ 8, /* ncclSum */ 0, p->nccl_comm, s);
+  if (rc != 0) NCCL_FAIL(p, rc, "ncclAllReduce");
+  return HVI_OK;
+}
+
 template <typename T>
 static int eval_sync_t(hvi_plan* p, int M, const void* phi, const void* zP, const void* zMs, bool use_rng, uint64_t seed,
-                       int64_t site_offset, int mem_kind, double comps[6], double* nL, void* grad) {
+                       int64_t site_offset, int mem_kind, double comps[6], double* nL, void* grad, bool reduce = false) {
   const Cfg<T>& cfg = cfg_of<T>(p);
   const int nphi = cfg.nphi;
   cudaStream_t s = p->stream;
@@ -1102,6 +1155,22 @@ static int eval_sync_t(hvi_plan* p, int M, const void* phi, const void* zP, cons
                  : enqueue_eval<T>(p, M, dphi, dzP, dzM, p->d_out, want_grad ? (T*)p->d_grad : nullptr, s, use_rng, seed,
                                    site_offset);
   if (rc) return rc;
+  if (reduce) {
+    // site-sharded job: Σ over the ranks of [∇ϕ; components; nL; non-finite] in double, on the same stream; the
+    // gradient is then taken from the reduced vector (d_grad holds this shard's part only)
+    rc = nccl_allreduce_out(p, p->d_out, s);
+    if (rc) return rc;
+    CU(p, cudaMemcpyAsync(p->h_out, p->d_out, sizeof(double) * (size_t)(nphi + 8), cudaMemcpyDeviceToHost, s));
+    if (p->anomalies < 0) CU(p, cudaMemcpyAsync(p->h_bconst, p->d_bconst, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+    CU(p, cudaStreamSynchronize(s));
+    if (p->anomalies < 0) p->anomalies = (int64_t)p->h_bconst[1];
+    if (want_grad) for (int i = 0; i < nphi; i++) ((T*)grad)[i] = (T)p->h_out[i];
+    const double* Cr = p->h_out + nphi;
+    if (comps) for (int i = 0; i < 6; i++) comps[i] = Cr[i];
+    if (nL) *nL = Cr[6];
+    if (Cr[7] != 0.0) PLAN_FAIL(p, HVI_ENONFINITE, "non-finite value or gradient, or an observation that is finite where a driver is not, on some rank (%g entries)", Cr[7]);
+    return HVI_OK;
+  }
   CU(p, cudaMemcpyAsync(p->h_out + nphi, p->d_out + nphi, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
   if (p->anomalies < 0) CU(p, cudaMemcpyAsync(p->h_bconst, p->d_bconst, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
   if (want_grad) {
@@ -1159,6 +1228,62 @@ extern "C" int hvi_neg_elbo_grad_rng(hvi_plan* p, int32_t n_MC, const void* phi,
   return p->dtype == HVI_F32
              ? eval_sync_t<float>(p, n_MC, phi, nullptr, nullptr, true, seed, site_offset, mem_kind, comps, nL, grad)
              : eval_sync_t<double>(p, n_MC, phi, nullptr, nullptr, true, seed, site_offset, mem_kind, comps, nL, grad);
+}
+
+// ---- site-sharded jobs: the collective behind the C ABI ------------------------------------------
+extern "C" int hvi_nccl_unique_id(void* id128) {
+  if (!id128) return HVI_EINVAL;
+  NcclApi* api = nccl_api();
+  if (!api) return HVI_ENCCL;
+  return api->GetUniqueId(id128) == 0 ? HVI_OK : HVI_ENCCL;
+}
+
+extern "C" int hvi_plan_comm_init(hvi_plan* p, const void* id128, int32_t rank, int32_t world) {
+  if (!p) return HVI_EINVAL;
+  if (!id128 || world < 1 || rank < 0 || rank >= world) PLAN_FAIL(p, HVI_EINVAL, "bad communicator arguments (rank %d of %d)", rank, world);
+  if (p->nccl_comm) PLAN_FAIL(p, HVI_EINVAL, "the plan already has a communicator");
+  NcclApi* api = nccl_api();
+  if (!api) PLAN_FAIL(p, HVI_ENCCL, "libnccl.so.2 could not be loaded (set HVI_NCCL_LIB)");
+  CU(p, cudaSetDevice(p->desc.device));
+  HviNcclId id;
+  memcpy(&id, id128, sizeof(id));
+  void* comm = nullptr;
+  const int rc = api->CommInitRank(&comm, world, id, rank);
+  if (rc != 0) NCCL_FAIL(p, rc, "ncclCommInitRank");
+  p->nccl_comm = comm; p->nccl_rank = rank; p->nccl_world = world;
+  return HVI_OK;
+}
+
+extern "C" int hvi_plan_comm_destroy(hvi_plan* p) {
+  if (!p) return HVI_EINVAL;
+  if (p->nccl_comm) {
+    NcclApi* api = nccl_api();
+    cudaSetDevice(p->desc.device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (api) api->CommDestroy(p->nccl_comm);
+    p->nccl_comm = nullptr; p->nccl_world = 1; p->nccl_rank = 0;
+  }
+  return HVI_OK;
+}
+
+extern "C" int hvi_allreduce_result(hvi_plan* p, double* out_dev, void* cuda_stream) {
+  if (!p) return HVI_EINVAL;
+  if (!out_dev) PLAN_FAIL(p, HVI_EINVAL, "out_dev is NULL");
+  CU(p, cudaSetDevice(p->desc.device));
+  return nccl_allreduce_out(p, out_dev, cuda_stream ? (cudaStream_t)cuda_stream : p->stream);
+}
+
+extern "C" int hvi_neg_elbo_grad_sharded(hvi_plan* p, int32_t n_MC, const void* phi, const void* zP, const void* zMs,
+                                         uint64_t seed, int64_t site_offset, int mem_kind, double comps[6], double* nL,
+                                         void* grad_host) {
+  int rc = check_eval_args(p, n_MC, phi, mem_kind);
+  if (rc) return rc;
+  if (!p->nccl_comm) PLAN_FAIL(p, HVI_EINVAL, "hvi_plan_comm_init has not been called");
+  if (zMs && p->desc.n_P > 0 && !zP) PLAN_FAIL(p, HVI_EINVAL, "zP is NULL");
+  const bool rng = zMs == nullptr;
+  return p->dtype == HVI_F32
+             ? eval_sync_t<float>(p, n_MC, phi, zP, zMs, rng, seed, site_offset, mem_kind, comps, nL, grad_host, true)
+             : eval_sync_t<double>(p, n_MC, phi, zP, zMs, rng, seed, site_offset, mem_kind, comps, nL, grad_host, true);
 }
 
 template <typename T>

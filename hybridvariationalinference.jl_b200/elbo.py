@@ -350,6 +350,42 @@ class NegElboPlan:
         self._check(self.lib.hvi_neg_elbo_grad_async(self._h, n_MC, _ptr(ϕ_dev), _ptr(zP_dev), _ptr(zMs_dev), seed,
                                                      site_offset, _ptr(out_dev), C.c_void_p(stream_ptr)))
 
+    # -- site-sharded jobs: the collective behind the C ABI ------------------------
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Join the NCCL communicator of a site-sharded job (`shard.nccl_unique_id()` on rank 0, handed to every rank)."""
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self.lib.hvi_plan_comm_init(self._h, buf, rank, world))
+
+    def comm_destroy(self):
+        self._check(self.lib.hvi_plan_comm_destroy(self._h))
+
+    def allreduce_result(self, out_dev, stream_ptr=0):
+        """Σ over the ranks of out_dev (float64 CUDA tensor, n_phi + 8) on the given stream (0: the plan's)."""
+        self._check(self.lib.hvi_allreduce_result(self._h, _ptr(out_dev), C.c_void_p(stream_ptr)))
+
+    def neg_elbo_withgradient_sharded(self, ϕ, zP=None, zMs=None, *, n_MC=None, seed=0, site_offset=0, allow_nonfinite=False):
+        """(nL, components, ∇ϕ) of the whole job on every rank: this rank's shard is evaluated, the result vector is summed
+        over the ranks by the library (ncclAllReduce on the evaluation's stream).  zMs: this rank's columns of the draws
+        (host arrays), or None for device draws keyed by the global site index (`site_offset` = first site of the shard)."""
+        comps = (C.c_double * 6)()
+        nL = C.c_double()
+        ϕ_ = np.ascontiguousarray(ϕ, dtype=self.dt)
+        grad = np.empty_like(ϕ_)
+        if zMs is None:
+            assert n_MC is not None
+            rc = self.lib.hvi_neg_elbo_grad_sharded(self._h, int(n_MC), _ptr(ϕ_), None, None, seed, site_offset, A.HVI_MEM_HOST,
+                                                    comps, C.byref(nL), _ptr(grad))
+        else:
+            zP_ = np.asfortranarray(zP, dtype=self.dt)
+            zMs_ = np.asfortranarray(zMs, dtype=self.dt)
+            M = zMs_.shape[0]
+            assert zMs_.shape == (M, self.prob.n_M * self.n_site), zMs_.shape
+            rc = self.lib.hvi_neg_elbo_grad_sharded(self._h, M, _ptr(ϕ_), _ptr(zP_), _ptr(zMs_), 0, site_offset, A.HVI_MEM_HOST,
+                                                    comps, C.byref(nL), _ptr(grad))
+        self._check(rc, allow_nonfinite)
+        return float(nL.value), NegElboComponents(*comps), grad
+
     def generate_ζ(self, ϕ, zP, zMs):
         """generate_ζ (src/elbo.jl:472-521): ζsP (n_θP×n_MC), ζsMs_tr (n_site×n_θM×n_MC), σ."""
         ϕ_ = np.ascontiguousarray(ϕ, dtype=self.dt)

@@ -25,6 +25,19 @@ def shard_batch(data: dict, zMs, n_M: int, rank: int, world: int):
     return d, zMs[:, lo * n_M:hi * n_M], lo
 
 
+def nccl_unique_id() -> bytes:
+    """128 bytes that identify a new NCCL communicator (hvi_nccl_unique_id): rank 0 creates them and hands them to every
+    rank by any means (a torch.distributed / MPI broadcast, a file); each rank then calls `plan.comm_init(id, rank, world)`."""
+    import ctypes as C
+    from . import _abi
+    lib = _abi.load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.hvi_nccl_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError("hvi_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
 def allreduce_result(out, dist=None):
     """Sum [∇ϕ ; components ; nL ; non-finite] over the ranks (torch tensor, in place)."""
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:

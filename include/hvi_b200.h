@@ -41,7 +41,8 @@ enum {
   HVI_ECUDA = 2,        /* CUDA runtime error, see hvi_last_error                   */
   HVI_ENONFINITE = 3,   /* result evaluated but not finite ("inspect non-finite")   */
   HVI_ENODATA = 4,      /* hvi_plan_set_data has not been called                    */
-  HVI_ENOMEM = 5
+  HVI_ENOMEM = 5,
+  HVI_ENCCL = 6         /* NCCL could not be loaded or a collective failed         */
 };
 
 enum { HVI_F32 = 0, HVI_F64 = 1 };
@@ -244,6 +245,26 @@ int hvi_neg_elbo_grad_rng(hvi_plan* plan, int32_t n_MC, const void* phi, uint64_
 int hvi_neg_elbo_grad_async(hvi_plan* plan, int32_t n_MC, const void* phi_dev,
                             const void* zP_dev, const void* zMs_dev, uint64_t seed,
                             int64_t site_offset, double* out_dev, void* cuda_stream);
+
+/* ---- the collective of site-sharded jobs ------------------------------------------------ */
+/* Site-sharded jobs: each GPU owns a contiguous site range, ϕ and zP are replicated, and ONE all-reduce(sum)
+ * of [∇ϕ; 6 components; nL; non-finite count] (n_phi + 8 doubles) finishes an evaluation -- ncclAllReduce over NVLink, issued by
+ * the library on the evaluation's stream (libnccl.so.2 is loaded at run time; HVI_NCCL_LIB overrides the name; HVI_ENCCL when
+ * it is missing or a call fails).  The reference is single-device (src/HybridSolver.jl:184-267); a Julia host needs nothing but
+ * ccall for the multi-GPU job:
+ *   rank 0: hvi_nccl_unique_id(id) and hands the 128 bytes to the other ranks (MPI.jl bcast, a file, a socket);
+ *   every rank: hvi_plan_create with desc.count_globals = (rank == 0), hvi_plan_comm_init(plan, id, rank, world),
+ *   hvi_plan_set_data(its sites), then hvi_neg_elbo_grad_sharded per evaluation with site_offset = first global site index of
+ *   the shard: zMs = this rank's columns of the draws, or NULL for device draws keyed by (seed, global site index, draw) --
+ *   identical results for any number of ranks.
+ * grad_host, comps, nL are host pointers and receive the job's totals on every rank.  hvi_allreduce_result is the collective
+ * alone, for the stream-ordered path (hvi_neg_elbo_grad_async → hvi_allreduce_result → hvi_adam_apply_dev). */
+int hvi_nccl_unique_id(void* id128);
+int hvi_plan_comm_init(hvi_plan* plan, const void* id128, int32_t rank, int32_t world);
+int hvi_plan_comm_destroy(hvi_plan* plan);
+int hvi_allreduce_result(hvi_plan* plan, double* out_dev, void* cuda_stream);
+int hvi_neg_elbo_grad_sharded(hvi_plan* plan, int32_t n_MC, const void* phi, const void* zP, const void* zMs, uint64_t seed,
+                              int64_t site_offset, int mem_kind, double comps[6], double* nL, void* grad_host);
 
 /* ---- point solver ------------------------------------------------------- */
 /* loss_gf of get_loss_gf (src/gf.jl:227-295; used by solve(prob, HybridPointSolver), src/HybridSolver.jl:9-140) and

@@ -302,6 +302,28 @@ function neg_elbo_withgradient(p::Plan, ϕ::Vector{T}, zP::Matrix{T}, zMs::Matri
 end
 
 "`loss_gf` and its gradient for ϕ = [ϕg; ϕP] (src/gf.jl:227-295), the point solver's cost function."
+# ---- site-sharded jobs: the collective lives in the library (ncclAllReduce on the evaluation's stream) ------------
+# rank 0: id = nccl_unique_id(); hand the 128 bytes to every rank (MPI.bcast, a file, ...); every rank: comm_init!(p, id, rank, world)
+# with a plan created with count_globals = (rank == 0) and its own site range registered by set_data!.
+function nccl_unique_id()
+    id = zeros(UInt8, 128)
+    rc = ccall((:hvi_nccl_unique_id, libhvi), Cint, (Ptr{UInt8},), id)
+    rc == 0 || error("hvi_nccl_unique_id failed ($rc): libnccl.so.2 not loadable?")
+    id
+end
+comm_init!(p::Plan, id::Vector{UInt8}, rank::Integer, world::Integer) =
+    check(p, ccall((:hvi_plan_comm_init, libhvi), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), p.h, id, rank, world))
+comm_destroy!(p::Plan) = check(p, ccall((:hvi_plan_comm_destroy, libhvi), Cint, (Ptr{Cvoid},), p.h))
+
+"(nL, comps, ∇ϕ) of the whole job on every rank; zMs_shard: this rank's columns of the draws; first_site: 0-based"
+function neg_elbo_withgradient_sharded(p::Plan, ϕ::Vector{T}, zP::Matrix{T}, zMs_shard::Matrix{T}, first_site::Integer) where {T}
+    comps = zeros(Float64, 6); nL = Ref{Float64}(0.0); grad = similar(ϕ)
+    check(p, ccall((:hvi_neg_elbo_grad_sharded, libhvi), Cint,
+                   (Ptr{Cvoid}, Int32, Ptr{T}, Ptr{T}, Ptr{T}, UInt64, Int64, Cint, Ptr{Float64}, Ref{Float64}, Ptr{T}),
+                   p.h, size(zMs_shard, 1), ϕ, zP, zMs_shard, 0, first_site, 0, comps, nL, grad))
+    nL[], comps, grad
+end
+
 function loss_gf_withgradient(p::Plan, ϕ::Vector{T}) where {T}
     comps = zeros(Float64, 3); grad = similar(ϕ)
     check(p, ccall((:hvi_loss_gf_grad, libhvi), Cint, (Ptr{Cvoid}, Ptr{T}, Cint, Ptr{Float64}, Ptr{T}), p.h, ϕ, 0, comps, grad))
