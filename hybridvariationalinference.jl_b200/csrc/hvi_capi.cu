@@ -1010,11 +1010,12 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
     part_g = p->d_gacc;
     nblk = 1; nblk2 = 0;
   } else {
+    // μ_ζ of the forward passes of this evaluation is still in d_mu / d_MU: the backward pass reads Φ⁻¹(p) off it
     CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_mubar, p->nb, p->d_part_mlp, &nblk, p->max_blk, 0,
-                            nullptr, part_xs));
+                            nullptr, part_xs, (const T*)p->d_mu));
     if (pbm)
       CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_MUBAR, p->nb,
-                              p->d_part_mlp + (size_t)nblk * cfg.nphig, &nblk2, p->max_blk, M, zetaP, part_xu));
+                              p->d_part_mlp + (size_t)nblk * cfg.nphig, &nblk2, p->max_blk, M, zetaP, part_xu, (const T*)p->d_MU));
   }
   MARK();
   CU(p, launch_finalize<T>(L, cfg, phi, zP, pdraw, ec, p->d_part_stream, nrows, part_g, nblk + nblk2, p->d_bconst,

@@ -145,7 +145,8 @@ cudaError_t launch_mlp_fwd(const Launch& L, const Cfg<T>& cfg, const T* phi, con
 template <typename T>
 cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, const T* mubar, int64_t nb,
                            double* part /*[nblk][nphig]*/, int* nblk_out, int nblk_max, int M_units = 0,
-                           const T* zetaP = nullptr, double* part_x = nullptr /*[nblk][max(M_units,1)*npc]*/);
+                           const T* zetaP = nullptr, double* part_x = nullptr /*[nblk][max(M_units,1)*npc]*/,
+                           const T* mu_fwd = nullptr /*μ_ζ written by launch_mlp_fwd for the same columns, if still valid*/);
 template <typename T>
 cudaError_t launch_stream(const Launch& L, const Cfg<T>& cfg, const StreamArgs<T>& a, int* nrows_out, int nrows_max);
 template <typename T>
@@ -200,7 +201,7 @@ cudaError_t launch_mlp3_tc_fwd(const Launch& L, const Cfg<float>& cfg, const flo
                                float* mu, int M_units, const float* zetaP);
 cudaError_t launch_mlp3_tc_bwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM,
                                const float* mubar, int64_t nb, double* part, int* nblk_out, int nblk_max, int M_units,
-                               const float* zetaP, double* part_x);
+                               const float* zetaP, double* part_x, const float* mufwd /*μ_ζ of the forward pass or NULL*/);
 // point-solver loss (hvi_point.cu)
 template <typename T>
 cudaError_t launch_point(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* rec, const T* mu, T* mubar, int64_t nb,

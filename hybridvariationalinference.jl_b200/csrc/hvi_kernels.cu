@@ -1240,9 +1240,10 @@ bool mlp_supports_pbm(const hvi_desc* d) {
 
 template <typename T>
 cudaError_t launch_mlp_bwd(const Launch& L, const Cfg<T>& cfg, const T* phi, const T* xM, const T* mubar, int64_t nb,
-                           double* part, int* nblk_out, int nblk_max, int M_units, const T* zetaP, double* part_x) {
+                           double* part, int* nblk_out, int nblk_max, int M_units, const T* zetaP, double* part_x,
+                           const T* mu_fwd) {
   if constexpr (sizeof(T) == 4) {
-    const cudaError_t et = launch_mlp3_tc_bwd(L, cfg, phi, xM, mubar, nb, part, nblk_out, nblk_max, M_units, zetaP, part_x);
+    const cudaError_t et = launch_mlp3_tc_bwd(L, cfg, phi, xM, mubar, nb, part, nblk_out, nblk_max, M_units, zetaP, part_x, mu_fwd);
     if (et != cudaErrorNotSupported) return et;
     const cudaError_t em = launch_mlp3_mma_bwd(L, cfg, phi, xM, mubar, nb, part, nblk_out, nblk_max, M_units, zetaP, part_x);
     if (em != cudaErrorNotSupported) return em;
@@ -1693,7 +1694,7 @@ cudaError_t launch_small_iter(const Launch& L, const Cfg<T>& cfg, SmallArgs<T> a
                                                    const unsigned long long*, int64_t, int64_t*);                         \
   template cudaError_t launch_mlp_fwd<T>(const Launch&, const Cfg<T>&, const T*, const T*, int64_t, T*, int, const T*);  \
   template cudaError_t launch_mlp_bwd<T>(const Launch&, const Cfg<T>&, const T*, const T*, const T*, int64_t, double*,   \
-                                         int*, int, int, const T*, double*);                                             \
+                                         int*, int, int, const T*, double*, const T*);                                   \
   template cudaError_t launch_finalize<T>(const Launch&, const Cfg<T>&, const T*, const T*, const T*,                    \
                                           const EvalConsts<T>*, const double*, int, const double*, int, const double*, int64_t, \
                                           int, double*, T*, double*, const double*, int, const double*, int, double*);                                                             \

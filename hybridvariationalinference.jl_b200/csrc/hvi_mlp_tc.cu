@@ -113,6 +113,15 @@ __device__ __forceinline__ float ex2a(float x) {
 }
 constexpr float K2LOG2E = 2.885390081777927f;   // 2·log2(e): tanh(z) = 1 − 2/(1 + 2^(K2LOG2E·z))
 __device__ __forceinline__ float tanh_scaled(float a) { return fmaf(-2.0f, rcpa(ex2a(a) + 1.0f), 1.0f); }   // a = K2LOG2E·z
+// two at a time: the FP32 parts as packed instructions (FADD2 / FFMA2: half the issue slots), the MUFU parts per element
+__device__ __forceinline__ float2 tanh2_scaled(float2 a) {
+  const float2 d = __fadd2_rn(make_float2(ex2a(a.x), ex2a(a.y)), make_float2(1.0f, 1.0f));
+  return __ffma2_rn(make_float2(-2.0f, -2.0f), make_float2(rcpa(d.x), rcpa(d.y)), make_float2(1.0f, 1.0f));
+}
+// x·(1 − h²) for a pair
+__device__ __forceinline__ float2 times_dtanh2(float2 x, float2 h) {
+  return __fmul2_rn(x, __ffma2_rn(make_float2(-h.x, -h.y), h, make_float2(1.0f, 1.0f)));
+}
 
 // shared-memory accesses by 32-bit shared-window address (the tiles are carved out of an aligned-up dynamic buffer)
 __device__ __forceinline__ void sts128u(uint32_t a, uint4 v) {
@@ -122,11 +131,6 @@ __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.sh
 __device__ __forceinline__ float lds32(uint32_t a) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ float2 lds64(uint32_t a) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
   return v;
 }
 __device__ __forceinline__ float4 lds128(uint32_t a) {
@@ -150,8 +154,9 @@ __device__ __forceinline__ void store1_tf(uint32_t hi_tile, uint32_t lo_tile, in
 // ---- bf16: hi = bf16(x), lo = bf16(x − hi); x0 in the low half of the packed word (even feature = lower K index)
 __device__ __forceinline__ void split_bf2(float x0, float x1, uint32_t& h, uint32_t& l) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
-  const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xffff0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(x1 - h1), "f"(x0 - h0));
+  const float2 d = __ffma2_rn(make_float2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u)), make_float2(-1.0f, -1.0f),
+                              make_float2(x0, x1));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(d.y), "f"(d.x));
 }
 // NW packed words (2·NW features) of row `row` starting at 16-byte chunk `chunk0` of a [128][64 bf16] SWIZZLE_128B tile
 template <int NW>
@@ -238,7 +243,12 @@ struct MlpTc {
       }
     }
 #pragma unroll
-    for (int j = 0; j < TC_HP; j++) h1[j] = j < H1 ? tanh_scaled(h1[j] * K2LOG2E) : 0.0f;
+    for (int j = 0; j < TC_HP; j += 2) {
+      if (j < H1) {
+        const float2 v = tanh2_scaled(__fmul2_rn(make_float2(h1[j], h1[j + 1]), make_float2(K2LOG2E, K2LOG2E)));
+        h1[j] = v.x; h1[j + 1] = v.y;
+      } else h1[j] = h1[j + 1] = 0.0f;
+    }
   }
   // h2 from the accumulator row and the pre-activations of the last layer
   __device__ __forceinline__ static void layer2_epi(uint32_t tab, const float (&z)[TC_HP], float (&h2)[TC_HP], float (&z3)[2]) {
@@ -248,10 +258,10 @@ struct MlpTc {
       if (4 * j4 < H2) {
         const float4 b = lds128(tab + 4 * (T_B2 + 4 * j4));
         const float4 wa = lds128(tab + 4 * (T_W3 + 8 * j4)), wb = lds128(tab + 4 * (T_W3 + 8 * j4 + 4));
-        h2[4 * j4] = tanh_scaled(fmaf(z[4 * j4], K2LOG2E, b.x));
-        h2[4 * j4 + 1] = tanh_scaled(fmaf(z[4 * j4 + 1], K2LOG2E, b.y));
-        h2[4 * j4 + 2] = tanh_scaled(fmaf(z[4 * j4 + 2], K2LOG2E, b.z));
-        h2[4 * j4 + 3] = tanh_scaled(fmaf(z[4 * j4 + 3], K2LOG2E, b.w));
+        const float2 k2 = make_float2(K2LOG2E, K2LOG2E);
+        const float2 ha = tanh2_scaled(__ffma2_rn(make_float2(z[4 * j4], z[4 * j4 + 1]), k2, make_float2(b.x, b.y)));
+        const float2 hb = tanh2_scaled(__ffma2_rn(make_float2(z[4 * j4 + 2], z[4 * j4 + 3]), k2, make_float2(b.z, b.w)));
+        h2[4 * j4] = ha.x; h2[4 * j4 + 1] = ha.y; h2[4 * j4 + 2] = hb.x; h2[4 * j4 + 3] = hb.y;
         z3[0] = fmaf(h2[4 * j4], wa.x, z3[0]); z3[1] = fmaf(h2[4 * j4], wa.y, z3[1]);
         z3[0] = fmaf(h2[4 * j4 + 1], wa.z, z3[0]); z3[1] = fmaf(h2[4 * j4 + 1], wa.w, z3[1]);
         z3[0] = fmaf(h2[4 * j4 + 2], wb.x, z3[0]); z3[1] = fmaf(h2[4 * j4 + 2], wb.y, z3[1]);
@@ -435,8 +445,8 @@ __device__ __forceinline__ void a_to_tmem(uint32_t trow, const uint32_t (&hw)[TC
 template <int NI, int H1, int H2, int NOUT>
 __global__ void __launch_bounds__(TC_BLOCK, TB_CTAS_PER_SM)
 k_mlp3_tc_bwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ phi, const float* __restrict__ xM,
-              const float* __restrict__ zetaP, const float* __restrict__ mubar, int M_units, int64_t nb,
-              double* __restrict__ part, double* __restrict__ part_x) {
+              const float* __restrict__ zetaP, const float* __restrict__ mubar, const float* __restrict__ mufwd, int M_units,
+              int64_t nb, double* __restrict__ part, double* __restrict__ part_x) {
   using N = MlpTc<NI, H1, H2, NOUT>;
   extern __shared__ unsigned char smem_raw[];
   __shared__ uint64_t bar, barG;
@@ -530,12 +540,16 @@ k_mlp3_tc_bwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ 
     const int m = (int)(u - st * Mu);
     const int64_t site = st * TC_COLS + t;
     const bool in = site < nb;
-    // cotangent of this column's outputs (in flight during layer 1)
-    float mb[2] = {0.0f, 0.0f};
+    // cotangent of this column's outputs and the forward pass's outputs (in flight during layer 1)
+    float mb[2] = {0.0f, 0.0f}, muf[2] = {0.0f, 0.0f};
     if (in) {
 #pragma unroll
       for (int k = 0; k < NOUT; k++)
-        if (k < cfg.nM) mb[k] = M_units > 0 ? mubar[((size_t)m * cfg.nM + k) * nb + site] : mubar[site * cfg.nM + k];
+        if (k < cfg.nM) {
+          const size_t o = M_units > 0 ? ((size_t)m * cfg.nM + k) * nb + site : (size_t)site * cfg.nM + k;
+          mb[k] = mubar[o];
+          if (mufwd) muf[k] = mufwd[o];
+        }
     }
     // ---- E1: layer 1 on the CUDA cores
     if (st != st_prev) { st_prev = st; N::site_base(cfg, tab, xM, site, nb, xs, base); }
@@ -573,7 +587,8 @@ k_mlp3_tc_bwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ 
           float d;
           if (cfg.scale_kind == HVI_SCALE_RANGE) d = mb[k] * cfg.scale_b[k];
           else {
-            const float qn = normcdfinvf(pk);
+            // q = Φ⁻¹(p): from the forward pass's μ_ζ = a + b·q when the caller kept it (3xTF32 there), else recomputed
+            const float qn = mufwd ? (muf[k] - cfg.scale_a[k]) * rcpa(cfg.scale_b[k]) : normcdfinvf(pk);
             d = mb[k] * cfg.scale_b[k] * 2.50662827463100050242f * ex2a(0.72134752044448170368f * qn * qn);
           }
           d3[k] = in ? d * pk * (1.0f - pk) : 0.0f;
@@ -588,10 +603,12 @@ k_mlp3_tc_bwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ 
       for (int j4 = 0; j4 < TC_HP / 4; j4++) {
         if (4 * j4 < H2) {
           const float4 wa = lds128(tab + 4 * (T_W3 + 8 * j4)), wb = lds128(tab + 4 * (T_W3 + 8 * j4 + 4));
-          d2[4 * j4] = fmaf(d3[0], wa.x, d3[1] * wa.y) * fmaf(-h2[4 * j4], h2[4 * j4], 1.0f);
-          d2[4 * j4 + 1] = fmaf(d3[0], wa.z, d3[1] * wa.w) * fmaf(-h2[4 * j4 + 1], h2[4 * j4 + 1], 1.0f);
-          d2[4 * j4 + 2] = fmaf(d3[0], wb.x, d3[1] * wb.y) * fmaf(-h2[4 * j4 + 2], h2[4 * j4 + 2], 1.0f);
-          d2[4 * j4 + 3] = fmaf(d3[0], wb.z, d3[1] * wb.w) * fmaf(-h2[4 * j4 + 3], h2[4 * j4 + 3], 1.0f);
+          const float2 D0 = make_float2(d3[0], d3[0]), D1 = make_float2(d3[1], d3[1]);
+          const float2 ta = __ffma2_rn(D0, make_float2(wa.x, wa.z), __fmul2_rn(D1, make_float2(wa.y, wa.w)));
+          const float2 tb = __ffma2_rn(D0, make_float2(wb.x, wb.z), __fmul2_rn(D1, make_float2(wb.y, wb.w)));
+          const float2 ra = times_dtanh2(ta, make_float2(h2[4 * j4], h2[4 * j4 + 1]));
+          const float2 rb = times_dtanh2(tb, make_float2(h2[4 * j4 + 2], h2[4 * j4 + 3]));
+          d2[4 * j4] = ra.x; d2[4 * j4 + 1] = ra.y; d2[4 * j4 + 2] = rb.x; d2[4 * j4 + 3] = rb.y;
         } else d2[4 * j4] = d2[4 * j4 + 1] = d2[4 * j4 + 2] = d2[4 * j4 + 3] = 0.0f;
       }
       split24(d2, hw, lw);
@@ -612,7 +629,12 @@ k_mlp3_tc_bwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ 
       float d1[TC_HP];
       tmem_ld24(trow + TB_T_ACC, d1);
 #pragma unroll
-      for (int j = 0; j < TC_HP; j++) d1[j] = j < H1 ? d1[j] * fmaf(-h1[j], h1[j], 1.0f) : 0.0f;
+      for (int j = 0; j < TC_HP; j += 2) {
+        if (j < H1) {
+          const float2 v = times_dtanh2(make_float2(d1[j], d1[j + 1]), make_float2(h1[j], h1[j + 1]));
+          d1[j] = v.x; d1[j + 1] = v.y;
+        } else d1[j] = d1[j + 1] = 0.0f;
+      }
       uint32_t hw[TC_HP / 2], lw[TC_HP / 2];
       split24(d1, hw, lw);
       store_words<TC_HP / 2>(v_hi, t, TB_OD1 / 8, hw);
@@ -745,7 +767,7 @@ cudaError_t launch_mlp3_tc_fwd(const Launch& L, const Cfg<float>& cfg, const flo
 
 cudaError_t launch_mlp3_tc_bwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM,
                                const float* mubar, int64_t nb, double* part, int* nblk_out, int nblk_max, int M_units,
-                               const float* zetaP, double* part_x) {
+                               const float* zetaP, double* part_x, const float* mufwd) {
   if (tc_mode() < 2) return cudaErrorNotSupported;
 #define X(NI, H1, H2, NO_)                                                                                  \
   if (tc_match(cfg, NI, H1, H2, NO_)) {                                                                     \
@@ -760,7 +782,7 @@ cudaError_t launch_mlp3_tc_bwd(const Launch& L, const Cfg<float>& cfg, const flo
     const int64_t cap = nblk_max < L.sm_count * TB_CTAS_PER_SM ? nblk_max : L.sm_count * TB_CTAS_PER_SM;    \
     if (blocks > cap) blocks = cap;                                                                         \
     if (blocks < 1) blocks = 1;                                                                             \
-    kern<<<(int)blocks, TC_BLOCK, smem, L.stream>>>(cfg, phi, xM, zetaP, mubar, M_units, nb, part, part_x); \
+    kern<<<(int)blocks, TC_BLOCK, smem, L.stream>>>(cfg, phi, xM, zetaP, mubar, mufwd, M_units, nb, part, part_x); \
     HVI_TC_CHECK();                                                                                         \
     *nblk_out = (int)blocks;                                                                                \
     return cudaSuccess;                                                                                     \
