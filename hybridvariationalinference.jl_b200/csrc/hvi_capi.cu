@@ -1031,7 +1031,12 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
 // after it) as ONE launch of one block
 template <typename T>
 static bool fused_ok(const hvi_plan* p, int64_t nb, int M) {
-  return p->use_fused && !p->wide && !p->gpbm && !p->profiling && nb <= 1024 && nb * (int64_t)M <= 16384 &&
+  // one block does the work of the whole GPU: the single launch wins only while its ≈ 35 µs + 0.3 µs per site stay below the
+  // ≈ 55 µs of the graph-replayed latency-bound launches (profiles/r02f_small_batch_latency.txt, Float32, µs per iteration:
+  // 20 x 3: 42 against 55; 50 x 12: 53 against 55; 200 x 12: 98 against 58; 800 x 12: 278 against 54) -- use_fused = 1 applies
+  // that break-even, 2 forces the path wherever it is supported
+  const bool fits = p->use_fused >= 2 ? (nb <= 1024 && nb * (int64_t)M <= 16384) : (nb <= 48 && nb * (int64_t)M <= 1024);
+  return p->use_fused && !p->wide && !p->gpbm && !p->profiling && fits &&
          small_iter_supported<T>(cfg_of<T>(const_cast<hvi_plan*>(p)), nb, M);
 }
 
@@ -1873,7 +1878,7 @@ extern "C" int hvi_adam_run_minibatches(hvi_plan* p, int32_t n_iter, int32_t n_M
 
 extern "C" int hvi_plan_use_fused(hvi_plan* p, int on) {
   if (!p) return HVI_EINVAL;
-  p->use_fused = on ? 1 : 0;
+  p->use_fused = on < 0 ? 0 : (on > 2 ? 2 : on);
   p->graph_valid = 0;
   return HVI_OK;
 }

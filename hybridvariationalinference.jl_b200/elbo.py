@@ -257,8 +257,9 @@ class NegElboPlan:
         names = ("gather", "zP_draws", "prologue", "g_fwd", "stream", "g_bwd", "reduce", "finalize", "adam")
         return {n: int(c[i + 1] - c[i]) for i, n in enumerate(names)}
 
-    def use_fused(self, on: bool):
-        """Small batches with device draws run as one launch (k_small_iter); False forces the multi-kernel path."""
+    def use_fused(self, on):
+        """Small batches with device draws run as one launch (k_small_iter): False / 0 forces the multi-kernel path, True / 1
+        (default) uses the single launch where it is the faster one (n_site <= 48), 2 wherever it is supported (n_site <= 1024)."""
         self._check(self.lib.hvi_plan_use_fused(self._h, int(on)))
 
     def adam_run_minibatches(self, n_iter, n_MC, batch_size, seed0=0, first_batch=0, trace=True):

@@ -299,8 +299,10 @@ int hvi_plan_use_graphs(hvi_plan* plan, int on);
 /* Small batches (the reference's operating point: 20 sites of 800, n_MC = 3 … 12, src/DoubleMM/f_doubleMM.jl:315-325,
  * src/HybridSolver.jl:147) with device draws run as ONE launch of one block per evaluation / optimiser iteration
  * (minibatch gather → draws → prologue → g → fused streaming phase → g backward → reductions → finalize → Adam)
- * instead of eight launches; hvi_plan_use_fused(plan, 0) forces the multi-kernel path (same results up to the
- * summation order of the per-block partial sums).  Applies to n_site <= 1024, n_site x n_MC <= 16384, the CUDA-core
+ * instead of eight launches (same results up to the summation order of the per-block partial sums).
+ * hvi_plan_use_fused(plan, on): 0 = always the multi-kernel path; 1 (default) = the single launch where it is the faster one
+ * (n_site <= 48 and n_site x n_MC <= 1024: one block against eight latency-bound launches breaks even at about 50 sites);
+ * 2 = the single launch wherever it is supported (n_site <= 1024, n_site x n_MC <= 16384).  Supported: the CUDA-core
  * applicator shapes, MeanHVIApproximationMat, no pbm covariates. */
 int hvi_plan_use_fused(hvi_plan* plan, int on);
 /* Profiling aid of that path: the first call (clocks may be NULL) switches the stamping on; later calls return the

@@ -46,12 +46,16 @@ for dtype in ("f32", "f64"):
 # (src/HybridSolver.jl:259-260); graph replay on / off
 print("minibatch loop on the device-resident dataset (hvi_adam_run_minibatches, 800 sites, 2000 iterations):")
 for dtype in ("f32", "f64"):
-    for bs, M in ((20, 3), (20, 12), (200, 12)):
-        for graphs in (True, False):
+    # fused: 2 = the single launch forced, 0 = the multi-kernel path, 1 = the library's choice (single launch up to 32 sites)
+    for bs, M, graphs, fused in ((20, 3, True, 1), (20, 3, False, 1), (20, 3, True, 0), (20, 12, True, 1), (20, 12, True, 0),
+                                 (32, 12, True, 2), (32, 12, True, 0), (50, 12, True, 2), (50, 12, True, 0), (200, 12, True, 2),
+                                 (200, 12, True, 0), (200, 12, True, 1)):
+        if True:
             prob = hvi_b200.DoubleMMCase(dtype=dtype)
             data = hvi_b200.gen_hybridproblem_synthetic(prob, 800)
             plan = hvi_b200.NegElboPlan(prob)
             plan.set_dataset(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+            plan.use_fused(fused)
             plan.use_graphs(graphs)
             plan.adam_init(prob.init_ϕ(), eta=0.02)
             plan.adam_run_minibatches(50, M, bs, seed0=0)
@@ -59,7 +63,7 @@ for dtype in ("f32", "f64"):
             t0 = time.perf_counter()
             tr = plan.adam_run_minibatches(n, M, bs, seed0=100)
             dt = (time.perf_counter() - t0) / n
-            print(f"{dtype} n_batch={bs:4d} n_MC={M:3d} graphs={graphs!s:5}: {dt * 1e6:8.1f} us per iteration  "
+            print(f"{dtype} n_batch={bs:4d} n_MC={M:3d} graphs={graphs!s:5} fused={fused}: {dt * 1e6:8.1f} us per iteration  "
                   f"loss {np.nanmean(tr[:40]):.4g} -> {np.nanmean(tr[-40:]):.4g}", flush=True)
 
 # where the single launch spends its time: SM clocks between the phase boundaries of k_small_iter (thread 0)
@@ -70,6 +74,7 @@ for dtype in ("f32", "f64"):
         data = hvi_b200.gen_hybridproblem_synthetic(prob, 800)
         plan = hvi_b200.NegElboPlan(prob)
         plan.set_dataset(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+        plan.use_fused(2)
         plan.adam_init(prob.init_ϕ(), eta=0.02)
         plan.fused_phase_clocks(start_only=True)
         plan.adam_run_minibatches(50, M, bs, seed0=0)

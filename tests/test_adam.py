@@ -116,6 +116,15 @@ def test_single_launch_evaluation_equals_the_multi_kernel_path(case, nb, M, dtyp
     ϕ = prob.init_ϕ(perturbed=True)
     plan = hvi_b200.NegElboPlan(prob)
     plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+    if nb <= 48:      # the default applies the break-even: the reference's batch size takes the single launch by itself
+        n0 = plan.launch_count
+        plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=77)
+        assert plan.launch_count - n0 == 1
+    else:             # a batch of hundreds of sites is faster as eight launches of the whole GPU
+        n0 = plan.launch_count
+        plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=77)
+        assert plan.launch_count - n0 >= 6
+    plan.use_fused(2)   # force the single launch wherever it is supported
     n0 = plan.launch_count
     nL, comps, g = plan.neg_elbo_withgradient(ϕ, n_MC=M, seed=77)
     assert plan.launch_count - n0 == 1
