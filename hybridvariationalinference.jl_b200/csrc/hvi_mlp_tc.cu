@@ -24,7 +24,8 @@
 //     μ_ζ feeds the σ- and ρ-gradients of the streaming kernel, which amplify its rounding.
 //     Backward: 3xBF16 like the mma.sync kernel it replaces; see the block comment above k_mlp3_tc_bwd.
 //   * the 2-output last layer, logistic and Φ⁻¹ run on the CUDA cores.
-// The mma.sync kernels (hvi_mlp_mma.cu) remain the fallback (HVI_MLP_TC=0) and the cross-check in the tests.
+// The mma.sync kernels (hvi_mlp_mma.cu) remain the path of batches below 5·10⁵ columns (the set-up of a CTA costs more than it
+// saves there; HVI_MLP_TC=3 takes the tcgen05 kernels at every size, HVI_MLP_TC=0 never) and the cross-check in the tests.
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
@@ -727,10 +728,16 @@ bool tc_match(const Cfg<float>& c, int ni, int h1, int h2, int no) {
          c.l_act[0] == HVI_ACT_TANH && c.l_act[1] == HVI_ACT_TANH && c.l_act[2] == HVI_ACT_LOGISTIC && c.l_bias[0] &&
          c.l_bias[1] && !c.l_bias[2] && c.nM <= no && c.nC <= ni && c.npc <= 8;
 }
-int tc_mode() {   // HVI_MLP_TC: 0 off, 1 forward only, 2 (default) forward and backward
+int tc_mode() {   // HVI_MLP_TC: 0 off, 1 forward only, 2 (default) forward and backward, 3 the same for every batch size
   const char* e = getenv("HVI_MLP_TC");
   return e ? atoi(e) : 2;
 }
+// The set-up of a CTA (operand tiles zeroed, weight tiles split and swizzled, TMEM allocation) and the read-out of the gradient
+// accumulator cost a few µs per launch: below ≈ 5·10⁵ columns the mma.sync kernels are the faster ones (forward + backward,
+// 10⁵ sites: 13 + 20 against 15 + 24 µs; 10⁶: 53 + 92 against 48 + 89; 1.25·10⁶: 64 + 113 against 57 + 105; 10⁷: 451 + 809
+// against 388 + 706)
+constexpr int64_t TC_MIN_COLUMNS = 500000;
+bool tc_worthwhile(int64_t nb, int M_units) { return tc_mode() >= 3 || nb * (int64_t)(M_units > 0 ? M_units : 1) >= TC_MIN_COLUMNS; }
 
 #define HVI_TC_CASES(X) X(5, 20, 20, 2) X(6, 24, 24, 2)
 
@@ -746,7 +753,7 @@ int tc_mode() {   // HVI_MLP_TC: 0 off, 1 forward only, 2 (default) forward and 
 // cudaErrorNotSupported: not one of the shapes (or switched off): the caller falls back to the mma.sync kernels
 cudaError_t launch_mlp3_tc_fwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb,
                                float* mu, int M_units, const float* zetaP) {
-  if (tc_mode() < 1) return cudaErrorNotSupported;
+  if (tc_mode() < 1 || !tc_worthwhile(nb, M_units)) return cudaErrorNotSupported;
 #define X(NI, H1, H2, NO_)                                                                                  \
   if (tc_match(cfg, NI, H1, H2, NO_)) {                                                                     \
     auto kern = k_mlp3_tc_fwd<NI, H1, H2, NO_>;                                                             \
@@ -768,7 +775,7 @@ cudaError_t launch_mlp3_tc_fwd(const Launch& L, const Cfg<float>& cfg, const flo
 cudaError_t launch_mlp3_tc_bwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM,
                                const float* mubar, int64_t nb, double* part, int* nblk_out, int nblk_max, int M_units,
                                const float* zetaP, double* part_x, const float* mufwd) {
-  if (tc_mode() < 2) return cudaErrorNotSupported;
+  if (tc_mode() < 2 || !tc_worthwhile(nb, M_units)) return cudaErrorNotSupported;
 #define X(NI, H1, H2, NO_)                                                                                  \
   if (tc_match(cfg, NI, H1, H2, NO_)) {                                                                     \
     const int nxa = (M_units > 0 ? M_units : 1) * cfg.npc;                                                  \

@@ -35,7 +35,7 @@ def main():
         zP, zMs = hvi_b200.draw_ξ(p32, nb, M)
         ϕ = p64.init_ϕ(perturbed=True).astype(np.float32).astype(np.float64)
         ref, _ = run(p64, data, ϕ, zP, zMs, 0)
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 3):
             got, dt = run(p32, d32, ϕ, zP, zMs, mode)
             line = f"scen={scen} nb={nb} M={M} HVI_MLP_TC={mode}: nL rel {abs(got[0] - ref[0]) / abs(ref[0]):.2e}"
             for blk, r in p32.positions().items():

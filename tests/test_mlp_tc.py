@@ -47,7 +47,7 @@ def test_tc_applicator_matches_oracle_and_mma(scen, nb, M):
     zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
     ϕ = prob.init_ϕ(perturbed=True)
     ref = O.value_and_grad(oracle_spec(prob), ϕ, data["xM"], data["xP"], data["y_o"], data["y_unc"], zP, zMs, "f32")
-    tc, _ = _eval(prob, data, ϕ, zP, zMs, 2)
+    tc, _ = _eval(prob, data, ϕ, zP, zMs, 3)     # 3: the tcgen05 kernels at every batch size (the default leaves small batches to mma.sync)
     mma, _ = _eval(prob, data, ϕ, zP, zMs, 0)
     _close(prob, tc, ref, TOL)
     _close(prob, mma, ref, TOL)
@@ -62,8 +62,8 @@ def test_tc_applicator_is_deterministic_and_shard_additive():
     data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=9)
     zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
     ϕ = prob.init_ϕ(perturbed=True)
-    a, _ = _eval(prob, data, ϕ, zP, zMs, 2)
-    b, _ = _eval(prob, data, ϕ, zP, zMs, 2)
+    a, _ = _eval(prob, data, ϕ, zP, zMs, 3)
+    b, _ = _eval(prob, data, ϕ, zP, zMs, 3)
     assert a[0] == b[0] and np.array_equal(a[2], b[2])
 
 
@@ -78,8 +78,44 @@ def test_tc_forward_feeds_generate_zeta():
     ϕ = prob.init_ϕ(perturbed=True)
     plan = hvi_b200.NegElboPlan(prob, device=0)
     plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
-    ζP, ζMs, σ = plan.generate_ζ(ϕ, zP, zMs)
+    os.environ["HVI_MLP_TC"] = "3"
+    try:
+        ζP, ζMs, σ = plan.generate_ζ(ϕ, zP, zMs)
+    finally:
+        os.environ.pop("HVI_MLP_TC", None)
     t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
     ζP_o, ζMs_o, σ_o = O.generate_zeta(oracle_spec(prob), t(ϕ), t(data["xM"]), t(zP), t(zMs))
     np.testing.assert_allclose(ζMs, ζMs_o.numpy(), rtol=2e-5, atol=2e-5)
     np.testing.assert_allclose(σ, σ_o.numpy(), rtol=2e-5)
+
+
+@pytest.mark.gpu
+def test_default_takes_tc_above_the_size_threshold_and_mma_below():
+    """10⁶ columns run on tcgen05 by default, 10⁴ on mma.sync; both agree with each other on the same inputs"""
+    prob = hvi_b200.DoubleMMCase(dtype="f32")
+    ϕ = prob.init_ϕ(perturbed=True)
+    for nb in (10_000, 1_000_000):
+        data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=2)
+        auto = _eval_rng(prob, data, ϕ, None)
+        forced_tc = _eval_rng(prob, data, ϕ, 3)
+        forced_mma = _eval_rng(prob, data, ϕ, 0)
+        same_as = forced_tc if nb >= 500_000 else forced_mma
+        assert auto[0] == same_as[0] and np.array_equal(auto[2], same_as[2])      # deterministic kernels: bit-identical
+        _close(prob, forced_tc, forced_mma, 2e-5)
+
+
+def _eval_rng(prob, data, ϕ, mode):
+    old = os.environ.get("HVI_MLP_TC")
+    if mode is None:
+        os.environ.pop("HVI_MLP_TC", None)
+    else:
+        os.environ["HVI_MLP_TC"] = str(mode)
+    try:
+        plan = hvi_b200.NegElboPlan(prob, device=0)
+        plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+        return plan.neg_elbo_withgradient(ϕ, n_MC=4, seed=21)
+    finally:
+        if old is None:
+            os.environ.pop("HVI_MLP_TC", None)
+        else:
+            os.environ["HVI_MLP_TC"] = old
