@@ -478,6 +478,16 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
         const T* buf = ztile + (g & 1) * (32 * NM * MCS);
         if (active) {
           const int nfull = nd / CH;
+          // pbm covariates: the per-draw means of the NEXT chunk travel while this chunk is computed
+          T mun[CH][NM];
+          if constexpr (PBM) {
+            if (nfull > 0) {
+#pragma unroll
+              for (int d = 0; d < CH; d++)
+#pragma unroll
+                for (int k = 0; k < NM; k++) mun[d][k] = a.MU[((size_t)(m0 + d) * NM + k) * a.nb + site];
+            }
+          }
           for (int q = 0; q < nfull; q++) {   // full chunks of CH draws, no guards
             const int mq = m0 + q * CH;
             T zc[NM][CH];
@@ -512,9 +522,17 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
             for (int d = 0; d < CH; d++)
 #pragma unroll
               for (int k = 0; k < NM; k++) {
-                mud[d][k] = PBM ? a.MU[((size_t)(mq + d) * NM + k) * a.nb + site] : st.mu[k];
+                if constexpr (PBM) mud[d][k] = mun[d][k]; else mud[d][k] = st.mu[k];
                 z[d][k] = zc[k][d];
               }
+            if constexpr (PBM) {
+              if (q + 1 < nfull) {
+#pragma unroll
+                for (int d = 0; d < CH; d++)
+#pragma unroll
+                  for (int k = 0; k < NM; k++) mun[d][k] = a.MU[((size_t)(mq + CH + d) * NM + k) * a.nb + site];
+              }
+            }
             if constexpr (ILV) {
               DrawTmp<T, NP, NM> dt[CH];
               T pbar[CH][4];
