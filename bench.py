@@ -185,7 +185,13 @@ def dominant_roofline(args, prob, nb, M, kt, peaks, sampler, local):
     cols = nb * (M + 1) if prob.pbm_covars else nb
     wide = max(max(i, o) for i, o, _, _ in prob.layers) > 64
     traffic = None
-    if kt["stream"] >= g_ms:
+    # wide applicator with pbm covariates: the evaluation walks blocks of sites (pass-2 forward -> stream -> pass-2 backward
+    # per block) and the library reports the whole loop in the "stream" slot; the streaming kernel itself is
+    # below 1 % of it, so the loop counts as applicator time
+    blocked = bool(wide and prob.pbm_covars)
+    if blocked:
+        g_ms += kt["stream"]
+    if kt["stream"] >= g_ms and not blocked:
         # site records + μ_ζ/μ̄_ζ hand-off + ξ (+ per-draw means and their cotangents with pbm covariates)
         alg_bytes = nb * (4 * 4 * nO + 2 * 4 * nM + 4 * nM * M + (2 * 4 * nM * M if prob.pbm_covars else 0))
         peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -229,7 +235,9 @@ def dominant_roofline(args, prob, nb, M, kt, peaks, sampler, local):
             "frac": achieved / peak, "traffic": None,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)" if peaks
                            else "fallback 1384 TFLOP/s",
-            "algorithmic_flop_per_step": alg_flop, "tensor_passes": 3, "columns": cols, "kernel_ms": kt}
+            "algorithmic_flop_per_step": alg_flop, "tensor_passes": 3, "columns": cols, "kernel_ms": kt,
+            **({"kernel_ms_note": "site-blocked schedule: 'stream' holds the per-block loop (g forward, k_stream, g backward)"}
+               if blocked else {})}
 
 
 # FP32-pipe slots per site·draw of k_stream's hot loop (DoubleMM, 8 observations): packed instructions count twice

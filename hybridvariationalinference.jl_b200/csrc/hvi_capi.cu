@@ -904,17 +904,54 @@ template <> const Cfg<float>& cfg_of<float>(const hvi_plan* p) { return p->cf; }
 template <> const Cfg<double>& cfg_of<double>(const hvi_plan* p) { return p->cd; }
 
 // g forward for all paths: register-tiled / generic CUDA-core kernels, or the wide tensor-core chain
+// (xM_sub / nb_sub: a range of the batch's sites instead of all of them)
 template <typename T>
 static int run_g_fwd(hvi_plan* p, const Launch& L, const Cfg<T>& cfg, const T* phi, T* out, int M_units, const T* zetaP,
-                     WideCache cache = WideCache{nullptr, 0, 0}) {
+                     WideCache cache = WideCache{nullptr, 0, 0}, const T* xM_sub = nullptr, int64_t nb_sub = -1) {
+  const T* xM = xM_sub ? xM_sub : (const T*)p->d_xM;
+  const int64_t nb = nb_sub >= 0 ? nb_sub : p->nb;
   if (p->wide) {
     int rc = ensure(p, &p->d_wide, &p->cap_wide, (int64_t)(sizeof(T) * wide_work_elems(cfg.max_width, cfg.nphig)));
     if (rc) return rc;
-    CU(p, launch_mlp_fwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, out, M_units, zetaP, (T*)p->d_wide, cache));
+    CU(p, launch_mlp_fwd_wide<T>(L, cfg, phi, xM, nb, out, M_units, zetaP, (T*)p->d_wide, cache));
     return HVI_OK;
   }
-  CU(p, launch_mlp_fwd<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, out, M_units, zetaP));
+  CU(p, launch_mlp_fwd<T>(L, cfg, phi, xM, nb, out, M_units, zetaP));
   return HVI_OK;
+}
+
+// Site blocks of the wide applicator with pbm covariates (BASELINE config 5).  Pass 2 runs g on n_MC columns per site and
+// its activations ((n_layers − 1)·width·4 bytes per column as bf16 hi/lo planes) exceed HBM by far, so an evaluation that
+// does forward(all) → stream(all) → backward(all) must recompute most of them in the backward pass.  The only coupling
+// between sites is the sum over sites at the very end, so the evaluation walks blocks of sites instead and does
+// forward → stream → backward per block while the block's activations are still in the cache: nothing is recomputed.
+// Returns the sites per block (0: one block = the unblocked schedule) and the rows of a cache slot.
+// HVI_WIDE_BLOCK_SITES forces a block size (tests), HVI_WIDE_CACHE_MB caps the cache.
+static int64_t wide_block_sites(hvi_plan* p, int nL, int maxw, int M, int64_t* slot_rows) {
+  *slot_rows = 0;
+  const int64_t col_bytes = (int64_t)(nL - 1) * maxw * 4;
+  const int64_t nch = bf3_chunks(p->nb), WIDE_CHUNK = bf3_chunk_rows();
+  if (const char* e = getenv("HVI_WIDE_BLOCK_SITES")) {
+    int64_t b = (atoll(e) + 127) / 128 * 128;
+    if (b <= 0 || b >= p->nb) return 0;
+    if (b < WIDE_CHUNK) *slot_rows = b; else b = b / WIDE_CHUNK * WIDE_CHUNK;
+    return b;
+  }
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return 0;
+  // what the cache may take: everything that is free now (plus what it holds already) minus head room for the buffers
+  // allocated after it (per-draw means of a block, caller's own allocations)
+  int64_t avail = (int64_t)fr + p->cap_wide_cache - ((int64_t)8 << 30);
+  if (const char* e = getenv("HVI_WIDE_CACHE_MB")) { const int64_t cap = atoll(e) << 20; if (cap < avail) avail = cap; }
+  if (avail >= nch * (1 + (int64_t)M) * (int64_t)bf3_cache_slot_bytes(nL, maxw)) return 0;   // everything fits: one block
+  const int64_t sites_max = avail / col_bytes / M;
+  if (sites_max < 4096) return 0;            // too little memory for useful blocks: unblocked with recomputation
+  if (sites_max >= WIDE_CHUNK) return sites_max / WIDE_CHUNK * WIDE_CHUNK;
+  const int64_t nblocks = (p->nb + sites_max - 1) / sites_max;
+  int64_t b = ((p->nb + nblocks - 1) / nblocks + 127) / 128 * 128;
+  if (b > sites_max) b = sites_max / 128 * 128;
+  *slot_rows = b;
+  return b;
 }
 
 // enqueue the whole evaluation on `s`; all pointers are device pointers
@@ -935,31 +972,49 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   MARK();
   const bool pbm = cfg.npc > 0;
   const T* zetaP = pdraw + (size_t)cfg.nP * M;
-  // wide Float32 applicator: keep the activations of as many chunks as half of the free memory holds
+  // wide Float32 applicator: the forward pass keeps the activations for the backward pass -- of every chunk where they fit,
+  // of one block of sites at a time where they do not (pbm covariates), of as many chunks as fit otherwise
   WideCache cache_s{nullptr, 0, 0}, cache_u{nullptr, 0, 0};
+  int64_t blk = 0, slot_rows = 0;   // blk > 0: site-blocked schedule
   if constexpr (sizeof(T) == 4) {
     if (p->wide && bf3_eligible(cfg)) {
-      const int64_t nch = bf3_chunks(p->nb), need = nch * (1 + (pbm ? M : 0));
-      const int64_t slot = (int64_t)bf3_cache_slot_bytes(cfg.nL, cfg.max_width);
-      if (p->cap_wide_cache < need * slot) {
-        size_t fr = 0, tot = 0;
-        CU(p, cudaMemGetInfo(&fr, &tot));
-        int64_t can = ((int64_t)fr + p->cap_wide_cache) / 2 / slot;
-        if (can > need) can = need;
-        if (can * slot > p->cap_wide_cache) {
-          rc = ensure(p, &p->d_wide_cache, &p->cap_wide_cache, can * slot);
-          if (rc) return rc;
-        }
+      if (pbm && !p->gpbm) {
+        // the work spaces first, so that the free memory seen by the block size is what is really left
+        rc = ensure(p, &p->d_wide, &p->cap_wide, (int64_t)(sizeof(T) * wide_work_elems(cfg.max_width, cfg.nphig)));
+        if (rc) return rc;
+        rc = ensure(p, &p->d_wide_bwd, &p->cap_wide_bwd, (int64_t)wide_bwd_work_bytes(cfg.nL, cfg.max_width, cfg.nphig));
+        if (rc) return rc;
+        blk = wide_block_sites(p, cfg.nL, cfg.max_width, M, &slot_rows);
       }
-      const int64_t have = p->cap_wide_cache / slot;
-      cache_s = WideCache{p->d_wide_cache, have, 0};
-      cache_u = WideCache{p->d_wide_cache, have, nch};
+      if (blk > 0) {
+        const int64_t need = (int64_t)M * bf3_chunks(blk) * (int64_t)bf3_cache_slot_bytes(cfg.nL, cfg.max_width, slot_rows);
+        rc = ensure(p, &p->d_wide_cache, &p->cap_wide_cache, need);
+        if (rc) return rc;
+        cache_u = WideCache{p->d_wide_cache, (int64_t)M * bf3_chunks(blk), 0, slot_rows};
+      } else {
+        const int64_t nch = bf3_chunks(p->nb), need = nch * (1 + (pbm ? M : 0));
+        const int64_t slot = (int64_t)bf3_cache_slot_bytes(cfg.nL, cfg.max_width);
+        if (p->cap_wide_cache < need * slot) {
+          size_t fr = 0, tot = 0;
+          CU(p, cudaMemGetInfo(&fr, &tot));
+          int64_t can = ((int64_t)fr + p->cap_wide_cache) / 2 / slot;
+          if (can > need) can = need;
+          if (can * slot > p->cap_wide_cache) {
+            rc = ensure(p, &p->d_wide_cache, &p->cap_wide_cache, can * slot);
+            if (rc) return rc;
+          }
+        }
+        const int64_t have = p->cap_wide_cache / slot;
+        cache_s = WideCache{p->d_wide_cache, have, 0};
+        cache_u = WideCache{p->d_wide_cache, have, nch};
+      }
     }
   }
+  const int64_t nbB_max = blk > 0 ? blk : p->nb;    // sites whose per-draw means are alive at once
   rc = run_g_fwd<T>(p, L, cfg, phi, (T*)p->d_mu, 0, nullptr, cache_s);
   if (rc) return rc;
   if (pbm) {  // pass 2: g([xM; ζP_m[idx]]) for every draw (src/elbo.jl:508-515)
-    const int64_t nmu = (int64_t)sizeof(T) * M * cfg.nM * p->nb;
+    const int64_t nmu = (int64_t)sizeof(T) * M * cfg.nM * nbB_max;
     rc = ensure(p, &p->d_MU, &p->cap_MU, nmu);
     if (rc) return rc;
     rc = ensure(p, &p->d_MUBAR, &p->cap_MUBAR, nmu);
@@ -968,18 +1023,25 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
     if (rc) return rc;
     rc = ensure(p, (void**)&p->d_xred, &p->cap_xred, (int64_t)sizeof(double) * (M + 1) * cfg.npc);
     if (rc) return rc;
-    rc = run_g_fwd<T>(p, L, cfg, phi, (T*)p->d_MU, M, zetaP, cache_u);
-    if (rc) return rc;
+    if (blk == 0) {
+      rc = run_g_fwd<T>(p, L, cfg, phi, (T*)p->d_MU, M, zetaP, cache_u);
+      if (rc) return rc;
+    }
   }
   MARK();
-  StreamArgs<T> a;
-  a.rec = (const T*)p->d_rec; a.mu = (const T*)p->d_mu; a.zMs = zMs;
-  a.pd = pdraw + (((size_t)4 * (cfg.nP > 0 ? cfg.nP : 1) * M + 3) & ~(size_t)3); a.pd_in_smem = 0;
-  a.ec = ec; a.mubar = (T*)p->d_mubar; a.partials = p->d_part_stream; a.nb = p->nb; a.M = M;
-  a.MU = pbm ? (const T*)p->d_MU : nullptr; a.MUBAR = pbm ? (T*)p->d_MUBAR : nullptr;
-  a.staged = !rng && (M % (16 / (int)sizeof(T)) == 0) && (((uintptr_t)zMs & 15) == 0);
-  a.rng = rng ? 1 : 0; a.seed = seed; a.seed_dev = seed_dev; a.col_offset = site_offset * cfg.nM;
-  a.phi = phi; a.i_sites = p->d_isites; a.out = out; a.grad_T = grad_T;
+  // the streaming kernel on sites [off, off + n) of the batch; per-draw means and cotangents are local to the range
+  auto stream_args = [&](int64_t off, int64_t n) {
+    StreamArgs<T> a;
+    a.rec = (const T*)p->d_rec + (size_t)off * 4 * cfg.nO; a.mu = (const T*)p->d_mu + (size_t)off * cfg.nM;
+    a.zMs = zMs ? zMs + (size_t)off * cfg.nM * M : nullptr;
+    a.pd = pdraw + (((size_t)4 * (cfg.nP > 0 ? cfg.nP : 1) * M + 3) & ~(size_t)3); a.pd_in_smem = 0;
+    a.ec = ec; a.mubar = (T*)p->d_mubar + (size_t)off * cfg.nM; a.partials = p->d_part_stream; a.nb = n; a.M = M;
+    a.MU = pbm ? (const T*)p->d_MU : nullptr; a.MUBAR = pbm ? (T*)p->d_MUBAR : nullptr;
+    a.staged = !rng && (M % (16 / (int)sizeof(T)) == 0) && (((uintptr_t)a.zMs & 15) == 0);
+    a.rng = rng ? 1 : 0; a.seed = seed; a.seed_dev = seed_dev; a.col_offset = (site_offset + off) * cfg.nM;
+    a.phi = phi; a.i_sites = p->d_isites ? p->d_isites + off : nullptr; a.out = out; a.grad_T = grad_T;
+    return a;
+  };
   if (cfg.sepvar) {   // sites outside the batch have zero gradient
     const size_t big = (size_t)cfg.nM * cfg.n_site_total;
     CU(p, cudaMemsetAsync(out + cfg.o_coef, 0, sizeof(double) * big, s));
@@ -987,35 +1049,62 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   }
   int nrows = 0, nblk = 0, nblk2 = 0;
   const bool penalty = generic_pbm_has_penalty(p->gpbm);
-  if (p->gpbm)
-    CU(p, launch_generic_stream<T>(L, p->gpbm, cfg, a, (const T*)p->d_xP, (const T*)p->d_yo, (const T*)p->d_yu, p->pbm_fix,
-                                   penalty ? p->d_pen : nullptr, &nrows, p->max_rows));
-  else
-    CU(p, launch_stream<T>(L, cfg, a, &nrows, p->max_rows));
-  MARK();
   double* part_xs = pbm ? p->d_part_x : nullptr;
   double* part_xu = pbm ? p->d_part_x + (size_t)p->max_blk * cfg.npc : nullptr;
   const double* part_g = p->d_part_mlp;
-  if (p->wide) {
-    // wide applicator: tensor-core backward into one double accumulator (a single "partial row")
-    rc = ensure(p, &p->d_wide_bwd, &p->cap_wide_bwd, (int64_t)wide_bwd_work_bytes(cfg.nL, cfg.max_width, cfg.nphig));
-    if (rc) return rc;
+  if (blk > 0) {
+    // site-blocked wide evaluation: pass-2 forward, stream and pass-2 backward per block (the time of the whole loop is
+    // reported in the "stream" slot of hvi_plan_kernel_times); the pass-1 backward follows once μ̄ of every site is known
     CU(p, cudaMemsetAsync(p->d_gacc, 0, sizeof(double) * (size_t)cfg.nphig, s));
-    if (pbm) CU(p, cudaMemsetAsync(p->d_part_x, 0, sizeof(double) * (size_t)2 * p->max_blk * (M + 1) * cfg.npc, s));
+    CU(p, cudaMemsetAsync(p->d_part_x, 0, sizeof(double) * (size_t)2 * p->max_blk * (M + 1) * cfg.npc, s));
+    for (int64_t off = 0; off < p->nb; off += blk) {
+      const int64_t n = p->nb - off < blk ? p->nb - off : blk;
+      const T* xM_b = (const T*)p->d_xM + (size_t)off * cfg.nC;
+      rc = run_g_fwd<T>(p, L, cfg, phi, (T*)p->d_MU, M, zetaP, cache_u, xM_b, n);
+      if (rc) return rc;
+      StreamArgs<T> a = stream_args(off, n);
+      a.partials = p->d_part_stream + (size_t)nrows * nacc(cfg.nP, cfg.nM);
+      int nr = 0;
+      CU(p, launch_stream<T>(L, cfg, a, &nr, p->max_rows - nrows));
+      nrows += nr;
+      CU(p, launch_mlp_bwd_wide<T>(L, cfg, phi, xM_b, n, (const T*)p->d_MUBAR, M, zetaP, p->d_wide_bwd, p->d_gacc, part_xu,
+                                   cache_u));
+      if (p->max_rows - nrows < 1) { p->err = "hvi: too many site blocks for the partial-sum rows"; return HVI_EINVAL; }
+    }
+    MARK();
     CU(p, launch_mlp_bwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (const T*)p->d_mubar, 0, nullptr, p->d_wide_bwd,
                                  p->d_gacc, part_xs, cache_s));
-    if (pbm)
-      CU(p, launch_mlp_bwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (const T*)p->d_MUBAR, M, zetaP, p->d_wide_bwd,
-                                   p->d_gacc, part_xu, cache_u));
     part_g = p->d_gacc;
     nblk = 1; nblk2 = 0;
   } else {
-    // μ_ζ of the forward passes of this evaluation is still in d_mu / d_MU: the backward pass reads Φ⁻¹(p) off it
-    CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_mubar, p->nb, p->d_part_mlp, &nblk, p->max_blk, 0,
-                            nullptr, part_xs, (const T*)p->d_mu));
-    if (pbm)
-      CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_MUBAR, p->nb,
-                              p->d_part_mlp + (size_t)nblk * cfg.nphig, &nblk2, p->max_blk, M, zetaP, part_xu, (const T*)p->d_MU));
+    StreamArgs<T> a = stream_args(0, p->nb);
+    if (p->gpbm)
+      CU(p, launch_generic_stream<T>(L, p->gpbm, cfg, a, (const T*)p->d_xP, (const T*)p->d_yo, (const T*)p->d_yu, p->pbm_fix,
+                                     penalty ? p->d_pen : nullptr, &nrows, p->max_rows));
+    else
+      CU(p, launch_stream<T>(L, cfg, a, &nrows, p->max_rows));
+    MARK();
+    if (p->wide) {
+      // wide applicator: tensor-core backward into one double accumulator (a single "partial row")
+      rc = ensure(p, &p->d_wide_bwd, &p->cap_wide_bwd, (int64_t)wide_bwd_work_bytes(cfg.nL, cfg.max_width, cfg.nphig));
+      if (rc) return rc;
+      CU(p, cudaMemsetAsync(p->d_gacc, 0, sizeof(double) * (size_t)cfg.nphig, s));
+      if (pbm) CU(p, cudaMemsetAsync(p->d_part_x, 0, sizeof(double) * (size_t)2 * p->max_blk * (M + 1) * cfg.npc, s));
+      CU(p, launch_mlp_bwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (const T*)p->d_mubar, 0, nullptr, p->d_wide_bwd,
+                                   p->d_gacc, part_xs, cache_s));
+      if (pbm)
+        CU(p, launch_mlp_bwd_wide<T>(L, cfg, phi, (const T*)p->d_xM, p->nb, (const T*)p->d_MUBAR, M, zetaP, p->d_wide_bwd,
+                                     p->d_gacc, part_xu, cache_u));
+      part_g = p->d_gacc;
+      nblk = 1; nblk2 = 0;
+    } else {
+      // μ_ζ of the forward passes of this evaluation is still in d_mu / d_MU: the backward pass reads Φ⁻¹(p) off it
+      CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_mubar, p->nb, p->d_part_mlp, &nblk, p->max_blk, 0,
+                              nullptr, part_xs, (const T*)p->d_mu));
+      if (pbm)
+        CU(p, launch_mlp_bwd<T>(L, cfg, phi, (const T*)p->d_xM, (const T*)p->d_MUBAR, p->nb,
+                                p->d_part_mlp + (size_t)nblk * cfg.nphig, &nblk2, p->max_blk, M, zetaP, part_xu, (const T*)p->d_MU));
+    }
   }
   MARK();
   CU(p, launch_finalize<T>(L, cfg, phi, zP, pdraw, ec, p->d_part_stream, nrows, part_g, nblk + nblk2, p->d_bconst,

@@ -763,13 +763,14 @@ static void carve(Bf3Work& w, void* work, int nL, int maxw, int nphig, bool bwd)
     w.db0 = reinterpret_cast<double*>(f);
   }
 }
-size_t bf3_cache_slot_bytes(int nL, int maxw) { return (size_t)(nL - 1) * WIDE_CHUNK * maxw * 4; }
+size_t bf3_cache_slot_bytes(int nL, int maxw, int64_t rows) { return (size_t)(nL - 1) * (size_t)(rows > 0 ? rows : WIDE_CHUNK) * maxw * 4; }
 int64_t bf3_chunks(int64_t nb) { return (nb + WIDE_CHUNK - 1) / WIDE_CHUNK; }
+int64_t bf3_chunk_rows() { return WIDE_CHUNK; }
 // the planes of slot `slot` of the activation cache, or false when the slot does not exist
 static bool cache_planes(const WideCache& c, int64_t slot, int nL, int maxw, Planes* H) {
   if (!c.base || slot < 0 || slot >= c.n_slots) return false;
-  const size_t cw = (size_t)WIDE_CHUNK * maxw;
-  bf16* p = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(c.base) + (size_t)slot * bf3_cache_slot_bytes(nL, maxw));
+  const size_t cw = (size_t)(c.rows > 0 ? c.rows : WIDE_CHUNK) * maxw;
+  bf16* p = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(c.base) + (size_t)slot * bf3_cache_slot_bytes(nL, maxw, c.rows));
   for (int l = 0; l < nL - 1; l++) { H[l].hi = p; p += cw; H[l].lo = p; p += cw; H[l].ld = 0; }
   return true;
 }

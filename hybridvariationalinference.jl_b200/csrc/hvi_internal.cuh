@@ -118,6 +118,7 @@ struct WideCache {
   void* base;
   int64_t n_slots;
   int64_t slot0;
+  int64_t rows;   // columns per slot; 0: WIDE_CHUNK (site-blocked evaluations use slots of one block's chunk)
 };
 
 // ---- kernel launchers (hvi_kernels.cu) -------------------------------------------------
@@ -182,8 +183,9 @@ size_t wide_bwd_work_bytes(int nL, int max_width, int nphig);
 bool bf3_eligible(const Cfg<float>& cfg);
 size_t bf3_fwd_work_bytes(int maxw, int nphig);
 size_t bf3_bwd_work_bytes(int nL, int maxw, int nphig);
-size_t bf3_cache_slot_bytes(int nL, int maxw);
+size_t bf3_cache_slot_bytes(int nL, int maxw, int64_t rows = 0);
 int64_t bf3_chunks(int64_t nb);
+int64_t bf3_chunk_rows();   // columns per chunk of the wide chain (WIDE_CHUNK)
 cudaError_t launch_mlp_fwd_bf3(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb, float* mu,
                                int M_units, const float* zetaP, void* work, WideCache cache);
 cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb, const float* mubar,

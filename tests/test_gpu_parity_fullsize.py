@@ -96,3 +96,36 @@ def test_c_port_against_autograd_at_size(scen):
     ref = O.value_and_grad(oracle_spec(prob), ϕ, data["xM"], data["xP"], data["y_o"], data["y_unc"], zP, zMs, "f64")
     got = c_oracle_value_and_grad(prob, ϕ, data, zP, zMs, nthreads=NTHREADS)
     _compare(prob, got, ref, 1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("block_sites", [512, 1024])
+def test_site_blocked_wide_evaluation(block_sites, monkeypatch):
+    """Config 5 shape with the evaluation walking blocks of sites (forward → stream → backward per block, the schedule that
+    keeps the activations of pass 2 in HBM at 10^6 sites x 64 draws): against the oracle, and equal to the one-block
+    schedule up to the order of the float sums; passed-in draws and device draws."""
+    name = "C5_shape_4x512_1.5e3x8"
+    scen, hidden, nb, M, _ = CONFIGS[name]
+    data, zP, zMs, ϕ, ref = _inputs_and_oracle(name)
+    prob = hvi_b200.DoubleMMCase(scen, dtype="f32", hidden=hidden)
+    ft = prob.np_dtype
+
+    def run(seed=None):
+        plan = hvi_b200.NegElboPlan(prob, device=0)
+        try:
+            plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+            if seed is None:
+                return plan.neg_elbo_withgradient(ϕ.astype(ft), zP.astype(ft), zMs.astype(ft)), plan.launch_count
+            return plan.neg_elbo_withgradient(ϕ.astype(ft), n_MC=M, seed=seed), plan.launch_count
+        finally:
+            plan.close()
+
+    whole, n_whole = run()
+    whole_rng, _ = run(seed=5)
+    monkeypatch.setenv("HVI_WIDE_BLOCK_SITES", str(block_sites))
+    blocked, n_blocked = run()
+    blocked_rng, _ = run(seed=5)
+    assert n_blocked > n_whole          # the blocks really were walked
+    _compare(prob, blocked, ref, TOL["f32"])
+    _compare(prob, blocked, whole, 2e-5)
+    _compare(prob, blocked_rng, whole_rng, 2e-5)
