@@ -694,6 +694,154 @@ __global__ void __launch_bounds__(256) k_thin_bwd_bf3(const float* __restrict__ 
   }
 }
 
+// Last layer of the backward pass in ONE pass over H_{L-1} (K ≤ 512): δ_L from μ̄ (as k_last_bf3<1>: a warp takes 32 rows,
+// the lanes share the features of a row, the output scaling runs one row per lane), then for the same 32 rows (second
+// read out of L2) δ_{L-1} = (δ_L W_Lᵀ) ⊙ act'(H_{L-1}) written as hi/lo planes, and the sums over the rows
+// ∇W_L[i][k] = Σ_r H_{L-1}[r][i]·δ_L[r][k] and ∇b_{L-1}[i] = Σ_r δ_{L-1}[r][i] in registers of the lane that owns
+// feature i.  Replaces k_last_bf3<1> + k_thin_bwd_bf3 + two skinny tensor-core products (three more reads of H_{L-1}
+// and one of δ_{L-1}).  Persistent: a warp walks row groups; one slice of partial sums per block:
+// P[block][K·NOUT (∇W_L, index i·NOUT + k) | K (∇b_{L-1})], summed in fixed order by k_accum.
+template <int NOUT>
+__global__ void __launch_bounds__(256) k_last_bwd_fused_bf3(const Cfg<float> cfg, const bf16* __restrict__ hi, const bf16* __restrict__ lo,
+                                                            int64_t ld, const float* __restrict__ Wref, int act, int act_prev,
+                                                            int64_t rows, int K, const float* __restrict__ mubar, int64_t site0,
+                                                            int m, int M_units, int64_t nb, Planes o, float* __restrict__ P) {
+  __shared__ float sacc[512 * (NOUT + 1)];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int WSTEPS = 2;
+  uint32_t wv[WSTEPS][8 * NOUT];
+  float gW[WSTEPS][8][NOUT], gb[WSTEPS][8];
+#pragma unroll
+  for (int st = 0; st < WSTEPS; st++) {
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      gb[st][c] = 0.f;
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) gW[st][c][k] = 0.f;
+    }
+    if (lane * 8 + 256 * st < K) {
+#pragma unroll
+      for (int g = 0; g < NOUT; g++) ldg256(Wref + (size_t)(lane * 8 + 256 * st) * NOUT + 8 * g, wv[st] + 8 * g);
+    } else {
+#pragma unroll
+      for (int g = 0; g < 8 * NOUT; g++) wv[st][g] = 0u;
+    }
+  }
+  const int64_t ngroups = (rows + 31) / 32;
+  for (int64_t grp = (int64_t)blockIdx.x * 8 + warp; grp < ngroups; grp += (int64_t)gridDim.x * 8) {
+    const int64_t r0 = grp * 32;
+    const int nr = rows - r0 < 32 ? (int)(rows - r0) : 32;
+    // ---- z_L of the 32 rows; lane i keeps row i's sums
+    float mine[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) mine[k] = 0.f;
+    for (int i = 0; i < nr; i++) {
+      const int64_t r = r0 + i;
+      float acc[NOUT];
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) acc[k] = 0.f;
+#pragma unroll
+      for (int st = 0; st < WSTEPS; st++) {
+        const int i0 = lane * 8 + 256 * st;
+        if (i0 < K) {
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + r * ld + i0)), b = __ldg(reinterpret_cast<const uint4*>(lo + r * ld + i0));
+          const float x[8] = {bf_lo(a.x) + bf_lo(b.x), bf_hi(a.x) + bf_hi(b.x), bf_lo(a.y) + bf_lo(b.y), bf_hi(a.y) + bf_hi(b.y),
+                              bf_lo(a.z) + bf_lo(b.z), bf_hi(a.z) + bf_hi(b.z), bf_lo(a.w) + bf_lo(b.w), bf_hi(a.w) + bf_hi(b.w)};
+#pragma unroll
+          for (int c = 0; c < 8; c++)
+#pragma unroll
+            for (int k = 0; k < NOUT; k++) acc[k] = fmaf(x[c], __uint_as_float(wv[st][c * NOUT + k]), acc[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) {
+        float sum = acc[k];
+        for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
+        if (lane == i) mine[k] = sum;
+      }
+    }
+    // ---- δ_L[k] = μ̄·scale'·act' of row r0 + lane
+    float d[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) d[k] = 0.f;
+    if (lane < nr) {
+      const int64_t site = site0 + r0 + lane;
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) {
+        if (k >= cfg.nM) continue;
+        const float p = act_apply<float>(act, mine[k]);
+        const float mb = M_units > 0 ? mubar[((size_t)m * cfg.nM + k) * nb + site] : mubar[site * cfg.nM + k];
+        float dv;
+        if (cfg.scale_kind == HVI_SCALE_RANGE) dv = mb * cfg.scale_b[k];
+        else { const float qn = (float)normcdfinv((double)p); dv = mb * cfg.scale_b[k] * 2.50662827463100050242f * expf(0.5f * qn * qn); }
+        dv *= (act == HVI_ACT_LOGISTIC) ? p * (1.f - p) : (act == HVI_ACT_TANH) ? 1.f - p * p : 1.f;
+        d[k] = dv;
+      }
+    }
+    // ---- δ_{L-1} of the 32 rows and the sums over the rows
+#pragma unroll 2
+    for (int i = 0; i < nr; i++) {
+      const int64_t r = r0 + i;
+      float dl[NOUT];
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) dl[k] = __shfl_sync(0xffffffffu, d[k], i);
+#pragma unroll
+      for (int st = 0; st < WSTEPS; st++) {
+        const int i0 = lane * 8 + 256 * st;
+        if (i0 < K) {
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + r * ld + i0)), b = __ldg(reinterpret_cast<const uint4*>(lo + r * ld + i0));
+          const float x[8] = {bf_lo(a.x) + bf_lo(b.x), bf_hi(a.x) + bf_hi(b.x), bf_lo(a.y) + bf_lo(b.y), bf_hi(a.y) + bf_hi(b.y),
+                              bf_lo(a.z) + bf_lo(b.z), bf_hi(a.z) + bf_hi(b.z), bf_lo(a.w) + bf_lo(b.w), bf_hi(a.w) + bf_hi(b.w)};
+          float z[8];
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < NOUT; k++) {
+              sum = fmaf(__uint_as_float(wv[st][c * NOUT + k]), dl[k], sum);
+              gW[st][c][k] = fmaf(x[c], dl[k], gW[st][c][k]);
+            }
+            z[c] = sum * act_deriv_f(act_prev, x[c]);
+            gb[st][c] += z[c];
+          }
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(z[2 * j], z[2 * j + 1]);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(z[2 * j] - __low2float(hh), z[2 * j + 1] - __high2float(hh));
+            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          *reinterpret_cast<uint4*>(o.hi + r * o.ld + i0) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(o.lo + r * o.ld + i0) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+    }
+  }
+  // ---- one slice of sums per block: the warps add their registers in warp order (deterministic)
+  const int slice = K * (NOUT + 1);
+  for (int e = threadIdx.x; e < slice; e += 256) sacc[e] = 0.f;
+  __syncthreads();
+  for (int w = 0; w < 8; w++) {
+    if (warp == w) {
+#pragma unroll
+      for (int st = 0; st < WSTEPS; st++) {
+        const int i0 = lane * 8 + 256 * st;
+        if (i0 < K) {
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+#pragma unroll
+            for (int k = 0; k < NOUT; k++) sacc[(i0 + c) * NOUT + k] += gW[st][c][k];
+            sacc[K * NOUT + i0 + c] += gb[st][c];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < slice; e += 256) P[(size_t)blockIdx.x * slice + e] = sacc[e];
+}
+
 #define HVI_NOUT_SWITCH(n, CALL)                                                               \
   switch (n) {                                                                                 \
     case 1: { constexpr int NOUT = 1; CALL; } break;                                           \
@@ -901,27 +1049,47 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
         e = chain_fwd(L, cfg, phi, xM, s0, rows, w, H);
         if (e != cudaSuccess) return e;
       }
-      // ---- last layer: δ_L, ∇W_L, δ_{L-1}
+      // ---- last layer: δ_L, ∇W_L, δ_{L-1} (and ∇b_{L-1} where the fused kernel applies)
       Planes Dcur = w.D[0], Dnxt = w.D[1];
+      bool bias_below_done = false;
       {
         const int l = nL - 1, K = cfg.l_in[l], no = cfg.l_out[l];
-        HVI_NOUT_SWITCH(no, (k_last_bf3<1, NOUT><<<(unsigned)((rows + 255) / 256), 256, 0, L.stream>>>(
-                                cfg, H[l - 1].hi, H[l - 1].lo, K, phi + cfg.woff[l], cfg.l_act[l], rows, K, nullptr, mubar, s0, m, M_units, nb,
-                                w.dlast, w.Sd.hi, w.Sd.lo)));
-        count();
-        Dcur.ld = K;
-        HVI_NOUT_SWITCH(no, (k_thin_bwd_bf3<NOUT><<<dim3((unsigned)((rows + 255) / 256), K / 64), 256, 0, L.stream>>>(
-                                w.dlast, phi + cfg.woff[l], H[l - 1].hi, H[l - 1].lo, K, cfg.l_act[l - 1], rows, Dcur)));
-        count();
-        e = skinny(w.Sd, no, H[l - 1], K, rows, &nslice);      // ∇W_L[i][k] = Σ_r δ_L[r][k] H_{L-1}[r][i]
-        if (e != cudaSuccess) return e;
-        k_accum<float><<<(no * K + 255) / 256, 256, 0, L.stream>>>(w.P, nslice, (size_t)no * K, no, K, grad_acc, cfg.woff[l], 1, no, nullptr);
-        count();
+        if (K <= 512 && !getenv("HVI_WIDE_LAST_UNFUSED")) {
+          int nblk = (int)((rows + 255) / 256);
+          if (nblk > 2 * sms) nblk = 2 * sms;
+          Dcur.ld = K;
+          HVI_NOUT_SWITCH(no, (k_last_bwd_fused_bf3<NOUT><<<nblk, 256, 0, L.stream>>>(
+                                  cfg, H[l - 1].hi, H[l - 1].lo, K, phi + cfg.woff[l], cfg.l_act[l], cfg.l_act[l - 1], rows, K, mubar, s0, m,
+                                  M_units, nb, Dcur, w.P)));
+          count();
+          const size_t sst = (size_t)K * (no + 1);
+          k_accum<float><<<(no * K + 255) / 256, 256, 0, L.stream>>>(w.P, nblk, sst, 1, no * K, grad_acc, cfg.woff[l], 0, 1, nullptr);
+          count();
+          if (cfg.l_bias[l - 1]) {
+            k_accum<float><<<(K + 255) / 256, 256, 0, L.stream>>>(w.P + (size_t)no * K, nblk, sst, 1, K, grad_acc, cfg.boff[l - 1], 0, 1,
+                                                                  l - 1 == 0 ? w.db0 : nullptr);
+            count();
+          }
+          bias_below_done = true;
+        } else {
+          HVI_NOUT_SWITCH(no, (k_last_bf3<1, NOUT><<<(unsigned)((rows + 255) / 256), 256, 0, L.stream>>>(
+                                  cfg, H[l - 1].hi, H[l - 1].lo, K, phi + cfg.woff[l], cfg.l_act[l], rows, K, nullptr, mubar, s0, m, M_units, nb,
+                                  w.dlast, w.Sd.hi, w.Sd.lo)));
+          count();
+          Dcur.ld = K;
+          HVI_NOUT_SWITCH(no, (k_thin_bwd_bf3<NOUT><<<dim3((unsigned)((rows + 255) / 256), K / 64), 256, 0, L.stream>>>(
+                                  w.dlast, phi + cfg.woff[l], H[l - 1].hi, H[l - 1].lo, K, cfg.l_act[l - 1], rows, Dcur)));
+          count();
+          e = skinny(w.Sd, no, H[l - 1], K, rows, &nslice);      // ∇W_L[i][k] = Σ_r δ_L[r][k] H_{L-1}[r][i]
+          if (e != cudaSuccess) return e;
+          k_accum<float><<<(no * K + 255) / 256, 256, 0, L.stream>>>(w.P, nslice, (size_t)no * K, no, K, grad_acc, cfg.woff[l], 1, no, nullptr);
+          count();
+        }
       }
       // ---- hidden layers l = nL-2 … 1: bias, weight gradient, δ of the layer below
       for (int l = nL - 2; l >= 1; l--) {
         const int N = cfg.l_out[l], K = cfg.l_in[l];   // Dcur: [rows][N]
-        if (cfg.l_bias[l]) {                           // ∇b_l = 1ᵀ δ_l: row K0 of Sxᵀ δ_l
+        if (cfg.l_bias[l] && !(bias_below_done && l == nL - 2)) {   // ∇b_l = 1ᵀ δ_l: row K0 of Sxᵀ δ_l
           e = skinny(w.Sx, K0 + 1, Dcur, N, rows, &nslice);
           if (e != cudaSuccess) return e;
           k_accum<float><<<(N + 255) / 256, 256, 0, L.stream>>>(w.P + (size_t)K0 * N, nslice, (size_t)(K0 + 1) * N, 1, N, grad_acc, cfg.boff[l], 0, 1, nullptr);
