@@ -88,6 +88,7 @@ struct GemmEpi {
   const bf16 *h_hi, *h_lo;   // MODE 1: activation of the layer below, normal planes
   int64_t ldh;
   float* P;              // MODE 2: [split][M][N]
+  float* colsum;         // MODE 1 (nullable): [row group of 32][N] column sums of the output (bias gradient of the layer below)
 };
 
 // ---- PTX ---------------------------------------------------------------------------------
@@ -196,6 +197,26 @@ __device__ __forceinline__ void load_planes32(const bf16* hi, const bf16* lo, in
     x[2 * j] = bf_lo(a[j]) + bf_lo(b[j]);
     x[2 * j + 1] = bf_hi(a[j]) + bf_hi(b[j]);
   }
+}
+
+// Σ over the 32 lanes of 32 values per lane: at every level half of the values go to the partner lane, so the tree costs
+// 31 shuffles; lane j ends with the total of value j (fixed order: deterministic).  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+  int n = 32;
+#pragma unroll
+  for (int b = 4; b >= 0; b--) {
+    n >>= 1;
+    const bool up = (lane >> b) & 1;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      if (i < n) {
+        const float send = up ? v[i] : v[i + n];
+        const float keep = up ? v[i + n] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << b);
+      }
+    }
+  }
+  return v[0];
 }
 
 // ---- the GEMM ------------------------------------------------------------------------------
@@ -375,6 +396,14 @@ k_gemm_bf3(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CU
           }
           if (ok && cb + 32 < (chalf + 1) * (BN / 2)) load_planes32_raw(ep.h_hi, ep.h_lo, ep.ldh, row, col0 + 32, ha, hb);
           store_planes32(ep.out, row, col0, x, ok);
+          if (ep.colsum) {   // column sums over this warp's 32 rows (rows beyond M count as zero)
+            if (!ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) x[j] = 0.f;
+            }
+            const float cs = warp_colsum32(x, lane);
+            ep.colsum[(size_t)(m0 / 32 + q) * sh.N + col0 + lane] = cs;
+          }
         } else if (ok) {
           float4* out = reinterpret_cast<float4*>(ep.P + ((size_t)split * sh.M + row) * sh.N + col0);
 #pragma unroll
@@ -691,6 +720,17 @@ __global__ void __launch_bounds__(256) k_thin_bwd_bf3(const float* __restrict__ 
       }
     }
     store_planes32(o, row, cb, z, ok);
+  }
+}
+
+// column sums, stage 1: block b adds its share of the R partial rows (one per 32 rows of the GEMM output) for every column
+__global__ void __launch_bounds__(256) k_colsum_rows(const float* __restrict__ cs, int R, int N, float* __restrict__ P2) {
+  const int per = (R + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per, r1 = r0 + per < R ? r0 + per : R;
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float s = 0.f;
+    for (int r = r0; r < r1; r++) s += cs[(size_t)r * N + n];
+    P2[(size_t)blockIdx.x * N + n] = s;
   }
 }
 
@@ -1087,9 +1127,11 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
         }
       }
       // ---- hidden layers l = nL-2 … 1: bias, weight gradient, δ of the layer below
+      bool bias_done = bias_below_done;   // ∇b_l already summed by the kernel that produced δ_l
+      const bool colsum_on = !getenv("HVI_WIDE_BIAS_SKINNY");
       for (int l = nL - 2; l >= 1; l--) {
         const int N = cfg.l_out[l], K = cfg.l_in[l];   // Dcur: [rows][N]
-        if (cfg.l_bias[l] && !(bias_below_done && l == nL - 2)) {   // ∇b_l = 1ᵀ δ_l: row K0 of Sxᵀ δ_l
+        if (cfg.l_bias[l] && !bias_done) {             // ∇b_l = 1ᵀ δ_l: row K0 of Sxᵀ δ_l
           e = skinny(w.Sx, K0 + 1, Dcur, N, rows, &nslice);
           if (e != cudaSuccess) return e;
           k_accum<float><<<(N + 255) / 256, 256, 0, L.stream>>>(w.P + (size_t)K0 * N, nslice, (size_t)(K0 + 1) * N, 1, N, grad_acc, cfg.boff[l], 0, 1, nullptr);
@@ -1106,15 +1148,27 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
           k_accum<float><<<(K * N + 255) / 256, 256, 0, L.stream>>>(w.P, ns_eff, (size_t)K * N, 1, K * N, grad_acc, cfg.woff[l], 0, 1, nullptr);
           count();
         }
-        {  // δ_{l-1} = (δ_l W_l) ⊙ act'(H_{l-1}): A = δ_l [rows x N], B = W_l in its own [in][out] layout
+        {  // δ_{l-1} = (δ_l W_l) ⊙ act'(H_{l-1}): A = δ_l [rows x N], B = W_l in its own [in][out] layout; where the layer
+           // below is a hidden one with a bias, the epilogue also leaves the column sums of δ_{l-1} per 32 rows (∇b_{l-1})
           GemmEpi ep;
           memset(&ep, 0, sizeof(ep));
           ep.act = cfg.l_act[l - 1];
           ep.h_hi = H[l - 1].hi; ep.h_lo = H[l - 1].lo; ep.ldh = K;
           Dnxt.ld = K;
           ep.out = Dnxt;
+          const bool cs = colsum_on && l - 1 >= 1 && cfg.l_bias[l - 1];
+          const int R = (int)((rows + G_BM - 1) / G_BM) * (G_BM / 32);
+          if (cs) ep.colsum = w.P;            // the partial tiles of the weight gradient have been summed: P is free
           e = launch_gemm_bf3<1>(L, Dcur.hi, Dcur.lo, N, rows, w.wn_hi + cfg.woff[l], w.wn_lo + cfg.woff[l], N, K, N, 1, ep);
           if (e != cudaSuccess) return e;
+          if (cs) {
+            const int nb1 = R < 128 ? R : 128;
+            float* P2 = w.P + (size_t)R * K;
+            k_colsum_rows<<<nb1, 256, 0, L.stream>>>(w.P, R, K, P2);
+            k_accum<float><<<(K + 255) / 256, 256, 0, L.stream>>>(P2, nb1, (size_t)K, 1, K, grad_acc, cfg.boff[l - 1], 0, 1, nullptr);
+            count(); count();
+          }
+          bias_done = cs;
         }
         Planes tmp = Dcur; Dcur = Dnxt; Dnxt = tmp;
       }

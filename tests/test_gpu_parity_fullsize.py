@@ -129,3 +129,39 @@ def test_site_blocked_wide_evaluation(block_sites, monkeypatch):
     _compare(prob, blocked, ref, TOL["f32"])
     _compare(prob, blocked, whole, 2e-5)
     _compare(prob, blocked_rng, whole_rng, 2e-5)
+
+
+@pytest.mark.gpu
+def test_wide_backward_fused_kernels_against_their_unfused_forms(monkeypatch):
+    """The one-pass last-layer backward kernel (k_last_bwd_fused_bf3) and the bias gradients taken as column sums in the
+    epilogue of the data-gradient GEMM, against the kernels they replace (k_last_bf3<1> + k_thin_bwd_bf3 + skinny
+    tensor-core products): every entry of ∇ϕg, relative to the largest entry of its layer's weights or biases."""
+    name = "C5_shape_4x512_1.5e3x8"
+    scen, hidden, nb, M, _ = CONFIGS[name]
+    data, zP, zMs, ϕ, ref = _inputs_and_oracle(name)
+    prob = hvi_b200.DoubleMMCase(scen, dtype="f32", hidden=hidden)
+    ft = prob.np_dtype
+
+    def run():
+        plan = hvi_b200.NegElboPlan(prob, device=0)
+        try:
+            plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+            return plan.neg_elbo_withgradient(ϕ.astype(ft), zP.astype(ft), zMs.astype(ft))
+        finally:
+            plan.close()
+
+    fused = run()
+    monkeypatch.setenv("HVI_WIDE_LAST_UNFUSED", "1")
+    monkeypatch.setenv("HVI_WIDE_BIAS_SKINNY", "1")
+    unfused = run()
+    _compare(prob, fused, ref, TOL["f32"])
+    g, g_u, g_o = (np.asarray(x[2], dtype=np.float64) for x in (fused, unfused, ref))
+    off = 0
+    for n_in, n_out, _, has_bias in prob.layers:           # per layer: weights [in][out], then the biases
+        for n in (n_in * n_out, n_out if has_bias else 0):
+            if n:
+                r = slice(off, off + n)
+                scale = np.max(np.abs(g_o[r]))
+                assert np.max(np.abs(g[r] - g_u[r])) <= 2e-5 * scale, (off, n)
+                assert np.max(np.abs(g[r] - g_o[r])) <= TOL["f32"] * scale, (off, n)
+                off += n
