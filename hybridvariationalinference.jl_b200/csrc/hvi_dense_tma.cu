@@ -734,15 +734,23 @@ __global__ void __launch_bounds__(256) k_colsum_rows(const float* __restrict__ c
   }
 }
 
-// Last layer of the backward pass in ONE pass over H_{L-1} (K ≤ 512): δ_L from μ̄ (as k_last_bf3<1>: a warp takes 32 rows,
-// the lanes share the features of a row, the output scaling runs one row per lane), then for the same 32 rows (second
-// read out of L2) δ_{L-1} = (δ_L W_Lᵀ) ⊙ act'(H_{L-1}) written as hi/lo planes, and the sums over the rows
+constexpr int LAST_STAGES = 4, LAST_STAGE_BYTES = 2048 + 32;   // ring of k_last_bwd_fused_bf3: rows in flight per warp
+__device__ __forceinline__ void cp_async16_g(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4_g(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+// Last layer of the backward pass in ONE pass over H_{L-1} (K ≤ 512): a warp takes one row at a time, the lanes share its
+// features (8 consecutive ones per lane and 256-feature step, as in k_last_bf3); z_L by a butterfly that leaves the sums
+// in every lane, δ_L = μ̄·scale'·act' in every lane (Φ⁻¹ in single precision: it only enters through exp(q²/2)), then
+// δ_{L-1} = (δ_L W_Lᵀ) ⊙ act'(H_{L-1}) written as hi/lo planes, and the sums over the rows
 // ∇W_L[i][k] = Σ_r H_{L-1}[r][i]·δ_L[r][k] and ∇b_{L-1}[i] = Σ_r δ_{L-1}[r][i] in registers of the lane that owns
 // feature i.  Replaces k_last_bf3<1> + k_thin_bwd_bf3 + two skinny tensor-core products (three more reads of H_{L-1}
-// and one of δ_{L-1}).  Persistent: a warp walks row groups; one slice of partial sums per block:
-// P[block][K·NOUT (∇W_L, index i·NOUT + k) | K (∇b_{L-1})], summed in fixed order by k_accum.
+// and one of δ_{L-1}).  The planes of the warp's next row travel while the current one is computed.  Persistent; one
+// slice of partial sums per block: P[block][K·NOUT (∇W_L, index i·NOUT + k) | K (∇b_{L-1})], summed in fixed order by k_accum.
 template <int NOUT>
-__global__ void __launch_bounds__(256) k_last_bwd_fused_bf3(const Cfg<float> cfg, const bf16* __restrict__ hi, const bf16* __restrict__ lo,
+__global__ void __launch_bounds__(256, 2) k_last_bwd_fused_bf3(const Cfg<float> cfg, const bf16* __restrict__ hi, const bf16* __restrict__ lo,
                                                             int64_t ld, const float* __restrict__ Wref, int act, int act_prev,
                                                             int64_t rows, int K, const float* __restrict__ mubar, int64_t site0,
                                                             int m, int M_units, int64_t nb, Planes o, float* __restrict__ P) {
@@ -767,97 +775,108 @@ __global__ void __launch_bounds__(256) k_last_bwd_fused_bf3(const Cfg<float> cfg
       for (int g = 0; g < 8 * NOUT; g++) wv[st][g] = 0u;
     }
   }
-  const int64_t ngroups = (rows + 31) / 32;
-  for (int64_t grp = (int64_t)blockIdx.x * 8 + warp; grp < ngroups; grp += (int64_t)gridDim.x * 8) {
-    const int64_t r0 = grp * 32;
-    const int nr = rows - r0 < 32 ? (int)(rows - r0) : 32;
-    // ---- z_L of the 32 rows; lane i keeps row i's sums
-    float mine[NOUT];
-#pragma unroll
-    for (int k = 0; k < NOUT; k++) mine[k] = 0.f;
-    for (int i = 0; i < nr; i++) {
-      const int64_t r = r0 + i;
-      float acc[NOUT];
-#pragma unroll
-      for (int k = 0; k < NOUT; k++) acc[k] = 0.f;
+  // per warp a ring of LAST_STAGES rows in shared memory (hi plane 1 KB | lo plane 1 KB | μ̄ of the row), filled with
+  // cp.async: every lane copies the 16-byte chunks it will read itself, lanes k < n_θM the row's cotangents
+  extern __shared__ __align__(16) unsigned char ring_raw[];
+  unsigned char* ring = ring_raw + (size_t)warp * LAST_STAGES * LAST_STAGE_BYTES;
+  const int64_t nw = (int64_t)gridDim.x * 8;
+  auto issue = [&](int64_t r, int stage) {
+    if (r < rows) {
+      unsigned char* dst = ring + (size_t)stage * LAST_STAGE_BYTES;
 #pragma unroll
       for (int st = 0; st < WSTEPS; st++) {
         const int i0 = lane * 8 + 256 * st;
         if (i0 < K) {
-          const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + r * ld + i0)), b = __ldg(reinterpret_cast<const uint4*>(lo + r * ld + i0));
-          const float x[8] = {bf_lo(a.x) + bf_lo(b.x), bf_hi(a.x) + bf_hi(b.x), bf_lo(a.y) + bf_lo(b.y), bf_hi(a.y) + bf_hi(b.y),
-                              bf_lo(a.z) + bf_lo(b.z), bf_hi(a.z) + bf_hi(b.z), bf_lo(a.w) + bf_lo(b.w), bf_hi(a.w) + bf_hi(b.w)};
-#pragma unroll
-          for (int c = 0; c < 8; c++)
-#pragma unroll
-            for (int k = 0; k < NOUT; k++) acc[k] = fmaf(x[c], __uint_as_float(wv[st][c * NOUT + k]), acc[k]);
+          cp_async16_g(dst + 2 * i0, hi + r * ld + i0);
+          cp_async16_g(dst + 1024 + 2 * i0, lo + r * ld + i0);
         }
       }
-#pragma unroll
-      for (int k = 0; k < NOUT; k++) {
-        float sum = acc[k];
-        for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
-        if (lane == i) mine[k] = sum;
+      if (lane < NOUT && lane < cfg.nM) {
+        const int64_t site = site0 + r;
+        cp_async4_g(dst + 2048 + 4 * lane, M_units > 0 ? mubar + ((size_t)m * cfg.nM + lane) * nb + site : mubar + site * cfg.nM + lane);
       }
     }
-    // ---- δ_L[k] = μ̄·scale'·act' of row r0 + lane
-    float d[NOUT];
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int64_t r = (int64_t)blockIdx.x * 8 + warp;
 #pragma unroll
-    for (int k = 0; k < NOUT; k++) d[k] = 0.f;
-    if (lane < nr) {
-      const int64_t site = site0 + r0 + lane;
+  for (int sg = 0; sg < LAST_STAGES - 1; sg++) issue(r + sg * nw, sg);
+  for (int it = 0; r < rows; r += nw, it++) {
+    issue(r + (LAST_STAGES - 1) * nw, (it + LAST_STAGES - 1) % LAST_STAGES);
+    asm volatile("cp.async.wait_group %0;" ::"n"(LAST_STAGES - 1) : "memory");
+    __syncwarp();
+    const unsigned char* src = ring + (size_t)(it % LAST_STAGES) * LAST_STAGE_BYTES;
+    float mb[NOUT];
 #pragma unroll
-      for (int k = 0; k < NOUT; k++) {
-        if (k >= cfg.nM) continue;
-        const float p = act_apply<float>(act, mine[k]);
-        const float mb = M_units > 0 ? mubar[((size_t)m * cfg.nM + k) * nb + site] : mubar[site * cfg.nM + k];
-        float dv;
-        if (cfg.scale_kind == HVI_SCALE_RANGE) dv = mb * cfg.scale_b[k];
-        else { const float qn = (float)normcdfinv((double)p); dv = mb * cfg.scale_b[k] * 2.50662827463100050242f * expf(0.5f * qn * qn); }
+    for (int k = 0; k < NOUT; k++) mb[k] = k < cfg.nM ? *reinterpret_cast<const float*>(src + 2048 + 4 * k) : 0.f;
+    float x[WSTEPS][8];
+    float acc[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) acc[k] = 0.f;
+#pragma unroll
+    for (int st = 0; st < WSTEPS; st++) {
+      const int i0 = lane * 8 + 256 * st;
+      uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+      if (i0 < K) {
+        a = *reinterpret_cast<const uint4*>(src + 2 * i0);
+        b = *reinterpret_cast<const uint4*>(src + 1024 + 2 * i0);
+      }
+      x[st][0] = bf_lo(a.x) + bf_lo(b.x); x[st][1] = bf_hi(a.x) + bf_hi(b.x);
+      x[st][2] = bf_lo(a.y) + bf_lo(b.y); x[st][3] = bf_hi(a.y) + bf_hi(b.y);
+      x[st][4] = bf_lo(a.z) + bf_lo(b.z); x[st][5] = bf_hi(a.z) + bf_hi(b.z);
+      x[st][6] = bf_lo(a.w) + bf_lo(b.w); x[st][7] = bf_hi(a.w) + bf_hi(b.w);
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+#pragma unroll
+        for (int k = 0; k < NOUT; k++) acc[k] = fmaf(x[st][c], __uint_as_float(wv[st][c * NOUT + k]), acc[k]);
+    }
+    // z_L in every lane, then δ_L[k] = μ̄·scale'·act'
+    float dl[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) {
+      float sum = acc[k];
+#pragma unroll
+      for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
+      float dv = 0.f;
+      if (k < cfg.nM) {
+        const float p = act_apply<float>(act, sum);
+        if (cfg.scale_kind == HVI_SCALE_RANGE) dv = mb[k] * cfg.scale_b[k];
+        else { const float qn = normcdfinvf(p); dv = mb[k] * cfg.scale_b[k] * 2.50662827463100050242f * expf(0.5f * qn * qn); }
         dv *= (act == HVI_ACT_LOGISTIC) ? p * (1.f - p) : (act == HVI_ACT_TANH) ? 1.f - p * p : 1.f;
-        d[k] = dv;
       }
+      dl[k] = dv;
     }
-    // ---- δ_{L-1} of the 32 rows and the sums over the rows
-#pragma unroll 2
-    for (int i = 0; i < nr; i++) {
-      const int64_t r = r0 + i;
-      float dl[NOUT];
 #pragma unroll
-      for (int k = 0; k < NOUT; k++) dl[k] = __shfl_sync(0xffffffffu, d[k], i);
+    for (int st = 0; st < WSTEPS; st++) {
+      const int i0 = lane * 8 + 256 * st;
+      if (i0 < K) {
+        float z[8];
 #pragma unroll
-      for (int st = 0; st < WSTEPS; st++) {
-        const int i0 = lane * 8 + 256 * st;
-        if (i0 < K) {
-          const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + r * ld + i0)), b = __ldg(reinterpret_cast<const uint4*>(lo + r * ld + i0));
-          const float x[8] = {bf_lo(a.x) + bf_lo(b.x), bf_hi(a.x) + bf_hi(b.x), bf_lo(a.y) + bf_lo(b.y), bf_hi(a.y) + bf_hi(b.y),
-                              bf_lo(a.z) + bf_lo(b.z), bf_hi(a.z) + bf_hi(b.z), bf_lo(a.w) + bf_lo(b.w), bf_hi(a.w) + bf_hi(b.w)};
-          float z[8];
+        for (int c = 0; c < 8; c++) {
+          float sum = 0.f;
 #pragma unroll
-          for (int c = 0; c < 8; c++) {
-            float sum = 0.f;
-#pragma unroll
-            for (int k = 0; k < NOUT; k++) {
-              sum = fmaf(__uint_as_float(wv[st][c * NOUT + k]), dl[k], sum);
-              gW[st][c][k] = fmaf(x[c], dl[k], gW[st][c][k]);
-            }
-            z[c] = sum * act_deriv_f(act_prev, x[c]);
-            gb[st][c] += z[c];
+          for (int k = 0; k < NOUT; k++) {
+            sum = fmaf(__uint_as_float(wv[st][c * NOUT + k]), dl[k], sum);
+            gW[st][c][k] = fmaf(x[st][c], dl[k], gW[st][c][k]);
           }
-          uint32_t h[4], l[4];
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(z[2 * j], z[2 * j + 1]);
-            const __nv_bfloat162 ll = __floats2bfloat162_rn(z[2 * j] - __low2float(hh), z[2 * j + 1] - __high2float(hh));
-            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
-            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
-          }
-          *reinterpret_cast<uint4*>(o.hi + r * o.ld + i0) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(o.lo + r * o.ld + i0) = make_uint4(l[0], l[1], l[2], l[3]);
+          z[c] = sum * act_deriv_f(act_prev, x[st][c]);
+          gb[st][c] += z[c];
         }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(z[2 * j], z[2 * j + 1]);
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(z[2 * j] - __low2float(hh), z[2 * j + 1] - __high2float(hh));
+          h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+          l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(o.hi + r * o.ld + i0) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(o.lo + r * o.ld + i0) = make_uint4(l[0], l[1], l[2], l[3]);
       }
     }
+    __syncwarp();   // every lane has read this stage's μ̄ before the stage is refilled
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   // ---- one slice of sums per block: the warps add their registers in warp order (deterministic)
   const int slice = K * (NOUT + 1);
   for (int e = threadIdx.x; e < slice; e += 256) sacc[e] = 0.f;
@@ -1098,7 +1117,9 @@ cudaError_t launch_mlp_bwd_bf3(const Launch& L, const Cfg<float>& cfg, const flo
           int nblk = (int)((rows + 255) / 256);
           if (nblk > 2 * sms) nblk = 2 * sms;
           Dcur.ld = K;
-          HVI_NOUT_SWITCH(no, (k_last_bwd_fused_bf3<NOUT><<<nblk, 256, 0, L.stream>>>(
+          const size_t ring_bytes = (size_t)8 * LAST_STAGES * LAST_STAGE_BYTES;
+          HVI_NOUT_SWITCH(no, (cudaFuncSetAttribute(k_last_bwd_fused_bf3<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)));
+          HVI_NOUT_SWITCH(no, (k_last_bwd_fused_bf3<NOUT><<<nblk, 256, ring_bytes, L.stream>>>(
                                   cfg, H[l - 1].hi, H[l - 1].lo, K, phi + cfg.woff[l], cfg.l_act[l], cfg.l_act[l - 1], rows, K, mubar, s0, m,
                                   M_units, nb, Dcur, w.P)));
           count();
