@@ -943,7 +943,8 @@ static int64_t wide_block_sites(hvi_plan* p, int nL, int maxw, int M, int64_t* s
   // allocated after it (per-draw means of a block, caller's own allocations)
   int64_t avail = (int64_t)fr + p->cap_wide_cache - ((int64_t)8 << 30);
   if (const char* e = getenv("HVI_WIDE_CACHE_MB")) { const int64_t cap = atoll(e) << 20; if (cap < avail) avail = cap; }
-  if (avail >= nch * (1 + (int64_t)M) * (int64_t)bf3_cache_slot_bytes(nL, maxw)) return 0;   // everything fits: one block
+  const int64_t rows1 = nch == 1 ? (p->nb + 127) / 128 * 128 : 0;
+  if (avail >= nch * (1 + (int64_t)M) * (int64_t)bf3_cache_slot_bytes(nL, maxw, rows1)) return 0;   // everything fits: one block
   const int64_t sites_max = avail / col_bytes / M;
   if (sites_max < 4096) return 0;            // too little memory for useful blocks: unblocked with recomputation
   if (sites_max >= WIDE_CHUNK) return sites_max / WIDE_CHUNK * WIDE_CHUNK;
@@ -993,7 +994,9 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
         cache_u = WideCache{p->d_wide_cache, (int64_t)M * bf3_chunks(blk), 0, slot_rows};
       } else {
         const int64_t nch = bf3_chunks(p->nb), need = nch * (1 + (pbm ? M : 0));
-        const int64_t slot = (int64_t)bf3_cache_slot_bytes(cfg.nL, cfg.max_width);
+        // batches below one chunk: slots of the batch's own size (a 1 500-site test problem would take 2 GB per slot otherwise)
+        const int64_t rows1 = nch == 1 ? (p->nb + 127) / 128 * 128 : 0;
+        const int64_t slot = (int64_t)bf3_cache_slot_bytes(cfg.nL, cfg.max_width, rows1);
         if (p->cap_wide_cache < need * slot) {
           size_t fr = 0, tot = 0;
           CU(p, cudaMemGetInfo(&fr, &tot));
@@ -1005,8 +1008,8 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
           }
         }
         const int64_t have = p->cap_wide_cache / slot;
-        cache_s = WideCache{p->d_wide_cache, have, 0};
-        cache_u = WideCache{p->d_wide_cache, have, nch};
+        cache_s = WideCache{p->d_wide_cache, have, 0, rows1};
+        cache_u = WideCache{p->d_wide_cache, have, nch, rows1};
       }
     }
   }

@@ -165,3 +165,30 @@ def test_wide_backward_fused_kernels_against_their_unfused_forms(monkeypatch):
                 assert np.max(np.abs(g[r] - g_u[r])) <= 2e-5 * scale, (off, n)
                 assert np.max(np.abs(g[r] - g_o[r])) <= TOL["f32"] * scale, (off, n)
                 off += n
+
+
+@pytest.mark.gpu
+def test_site_blocks_chosen_from_the_cache_size(monkeypatch):
+    """The block size the library derives itself from the memory it may take for the activation cache (here capped with
+    HVI_WIDE_CACHE_MB so that 10 000 sites x 4 draws need two blocks): same result as the one-block schedule."""
+    nb, M = 10_000, 4
+    prob = hvi_b200.DoubleMMCase(("covarK2",), dtype="f32", hidden=(512, 512, 512, 512))
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, nb, seed=5)
+    zP, zMs = hvi_b200.draw_ξ(prob, nb, M)
+    ft = prob.np_dtype
+    ϕ = prob.init_ϕ(perturbed=True).astype(ft)
+
+    def run():
+        plan = hvi_b200.NegElboPlan(prob, device=0)
+        try:
+            plan.set_data(data["xM"], data["xP"], data["y_o"], data["y_unc"])
+            return plan.neg_elbo_withgradient(ϕ, zP.astype(ft), zMs.astype(ft)), plan.launch_count
+        finally:
+            plan.close()
+
+    whole, n_whole = run()
+    monkeypatch.setenv("HVI_WIDE_CACHE_MB", "160")     # 160 MB / (8 KB per column x 4 draws) = 5 120 sites per block
+    blocked, n_blocked = run()
+    assert n_blocked > n_whole
+    assert np.isfinite(blocked[0]) and np.all(np.isfinite(blocked[2]))
+    _compare(prob, blocked, whole, 2e-5)
