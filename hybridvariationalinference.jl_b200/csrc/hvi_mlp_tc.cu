@@ -119,6 +119,19 @@ __device__ __forceinline__ float2 tanh2_scaled(float2 a) {
   const float2 d = __fadd2_rn(make_float2(ex2a(a.x), ex2a(a.y)), make_float2(1.0f, 1.0f));
   return __ffma2_rn(make_float2(-2.0f, -2.0f), make_float2(rcpa(d.x), rcpa(d.y)), make_float2(1.0f, 1.0f));
 }
+// the same with ONE reciprocal for the pair: 1/d.x = d.y/(d.x·d.y), 1/d.y = d.x/(d.x·d.y) -- a MUFU.RCP traded for three
+// FMUL where the MUFU pipe is the limit (forward kernel).  The arguments are capped at 60 so that the product of the two
+// denominators (≤ 2^120) stays finite; tanh is 1 to the last bit far below that.
+__device__ __forceinline__ float2 tanh2_scaled_shared(float2 a) {
+  const float2 d = __fadd2_rn(make_float2(ex2a(fminf(a.x, 60.0f)), ex2a(fminf(a.y, 60.0f))), make_float2(1.0f, 1.0f));
+  const float r = rcpa(d.x * d.y);
+  return __ffma2_rn(make_float2(-2.0f, -2.0f), make_float2(r * d.y, r * d.x), make_float2(1.0f, 1.0f));
+}
+template <bool SHR>
+__device__ __forceinline__ float2 tanh2_sel(float2 a) {
+  if constexpr (SHR) return tanh2_scaled_shared(a);
+  else return tanh2_scaled(a);
+}
 // x·(1 − h²) for a pair
 __device__ __forceinline__ float2 times_dtanh2(float2 x, float2 h) {
   return __fmul2_rn(x, __ffma2_rn(make_float2(-h.x, -h.y), h, make_float2(1.0f, 1.0f)));
@@ -224,6 +237,7 @@ struct MlpTc {
     }
   }
   // h1 for one unit: tanh(base + Σ_covariates ζP[idx]·W1[nC + c][·]); records the covariates in xs; features >= H1 are zero
+  template <bool SHR = false>
   __device__ __forceinline__ static void layer1(const Cfg<float>& cfg, uint32_t tab, const float* __restrict__ phi,
                                                 const float* __restrict__ zetaP, int M_units, int m, bool in, const float (&base)[TC_HP],
                                                 float (&xs)[8], float (&h1)[TC_HP]) {
@@ -246,12 +260,13 @@ struct MlpTc {
 #pragma unroll
     for (int j = 0; j < TC_HP; j += 2) {
       if (j < H1) {
-        const float2 v = tanh2_scaled(__fmul2_rn(make_float2(h1[j], h1[j + 1]), make_float2(K2LOG2E, K2LOG2E)));
+        const float2 v = tanh2_sel<SHR>(__fmul2_rn(make_float2(h1[j], h1[j + 1]), make_float2(K2LOG2E, K2LOG2E)));
         h1[j] = v.x; h1[j + 1] = v.y;
       } else h1[j] = h1[j + 1] = 0.0f;
     }
   }
   // h2 from the accumulator row and the pre-activations of the last layer
+  template <bool SHR = false>
   __device__ __forceinline__ static void layer2_epi(uint32_t tab, const float (&z)[TC_HP], float (&h2)[TC_HP], float (&z3)[2]) {
     z3[0] = z3[1] = 0.0f;
 #pragma unroll
@@ -260,8 +275,8 @@ struct MlpTc {
         const float4 b = lds128(tab + 4 * (T_B2 + 4 * j4));
         const float4 wa = lds128(tab + 4 * (T_W3 + 8 * j4)), wb = lds128(tab + 4 * (T_W3 + 8 * j4 + 4));
         const float2 k2 = make_float2(K2LOG2E, K2LOG2E);
-        const float2 ha = tanh2_scaled(__ffma2_rn(make_float2(z[4 * j4], z[4 * j4 + 1]), k2, make_float2(b.x, b.y)));
-        const float2 hb = tanh2_scaled(__ffma2_rn(make_float2(z[4 * j4 + 2], z[4 * j4 + 3]), k2, make_float2(b.z, b.w)));
+        const float2 ha = tanh2_sel<SHR>(__ffma2_rn(make_float2(z[4 * j4], z[4 * j4 + 1]), k2, make_float2(b.x, b.y)));
+        const float2 hb = tanh2_sel<SHR>(__ffma2_rn(make_float2(z[4 * j4 + 2], z[4 * j4 + 3]), k2, make_float2(b.z, b.w)));
         h2[4 * j4] = ha.x; h2[4 * j4 + 1] = ha.y; h2[4 * j4 + 2] = hb.x; h2[4 * j4 + 3] = hb.y;
         z3[0] = fmaf(h2[4 * j4], wa.x, z3[0]); z3[1] = fmaf(h2[4 * j4], wa.y, z3[1]);
         z3[0] = fmaf(h2[4 * j4 + 1], wa.z, z3[0]); z3[1] = fmaf(h2[4 * j4 + 1], wa.w, z3[1]);
@@ -304,7 +319,7 @@ constexpr int TF_TMEM_COLS = 128, TF_T_AHI = 32, TF_T_ALO = 64;
 constexpr uint32_t TF_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr int TF_CTAS_PER_SM = 4;
 
-template <int NI, int H1, int H2, int NOUT>
+template <int NI, int H1, int H2, int NOUT, bool SHR>
 __global__ void __launch_bounds__(TC_BLOCK, TF_CTAS_PER_SM)
 k_mlp3_tc_fwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ phi, const float* __restrict__ xM,
               const float* __restrict__ zetaP, int M_units, int64_t nb, float* __restrict__ mu) {
@@ -358,7 +373,7 @@ k_mlp3_tc_fwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ 
       const int m = (int)(u - st * Mu);
       const int64_t site = st * TC_COLS + t;
       if (st != st_prev) { st_prev = st; N::site_base(cfg, tab, xM, site, nb, xs, base); }
-      N::layer1(cfg, tab, phi, zetaP, M_units, m, site < nb, base, xs, h1);
+      N::template layer1<SHR>(cfg, tab, phi, zetaP, M_units, m, site < nb, base, xs, h1);
     };
     if (u0 < u1) prepare(u0);
     for (int64_t u = u0; u < u1; u++) {
@@ -383,7 +398,7 @@ k_mlp3_tc_fwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ 
       tc_after_sync();
       float z[TC_HP], h2[TC_HP], z3[2];
       tmem_ld24(trow, z);
-      N::layer2_epi(tab, z, h2, z3);
+      N::template layer2_epi<SHR>(tab, z, h2, z3);
       if (site < nb) {
 #pragma unroll
         for (int k = 0; k < NOUT; k++) {
@@ -754,9 +769,12 @@ bool tc_worthwhile(int64_t nb, int M_units) { return tc_mode() >= 3 || nb * (int
 cudaError_t launch_mlp3_tc_fwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb,
                                float* mu, int M_units, const float* zetaP) {
   if (tc_mode() < 1 || !tc_worthwhile(nb, M_units)) return cudaErrorNotSupported;
+  // HVI_TANH_SHARED=0: one reciprocal per tanh (two MUFU each); default: one reciprocal per pair of tanh
+  const char* shr_e = getenv("HVI_TANH_SHARED");
+  const bool shr = !(shr_e && atoi(shr_e) == 0);
 #define X(NI, H1, H2, NO_)                                                                                  \
   if (tc_match(cfg, NI, H1, H2, NO_)) {                                                                     \
-    auto kern = k_mlp3_tc_fwd<NI, H1, H2, NO_>;                                                             \
+    auto kern = shr ? k_mlp3_tc_fwd<NI, H1, H2, NO_, true> : k_mlp3_tc_fwd<NI, H1, H2, NO_, false>;         \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM);       \
     if (e != cudaSuccess) return e;                                                                         \
     const int64_t ntot = ((nb + TC_COLS - 1) / TC_COLS) * (M_units > 0 ? M_units : 1);                      \
