@@ -127,10 +127,26 @@ __device__ __forceinline__ float2 tanh2_scaled_shared(float2 a) {
   const float r = rcpa(d.x * d.y);
   return __ffma2_rn(make_float2(-2.0f, -2.0f), make_float2(r * d.y, r * d.x), make_float2(1.0f, 1.0f));
 }
-template <bool SHR>
+template <int SHR>
 __device__ __forceinline__ float2 tanh2_sel(float2 a) {
-  if constexpr (SHR) return tanh2_scaled_shared(a);
+  if constexpr (SHR > 0) return tanh2_scaled_shared(a);
   else return tanh2_scaled(a);
+}
+// four tanh with ONE reciprocal: r = 1/(d0 d1 d2 d3), 1/(d0 d1) = r·d2 d3, 1/d0 = d1/(d0 d1), ... (nine FMUL for three MUFU.RCP);
+// arguments capped at 30 (product of the four denominators ≤ 2^120; tanh is 1 to the last bit from 2x·log2(e) = 25 on)
+template <int SHR>
+__device__ __forceinline__ void tanh4_sel(float2 a, float2 b, float2& ta, float2& tb) {
+  if constexpr (SHR < 2) { ta = tanh2_sel<SHR>(a); tb = tanh2_sel<SHR>(b); }
+  else {
+    const float2 one = make_float2(1.0f, 1.0f), m2 = make_float2(-2.0f, -2.0f);
+    const float2 da = __fadd2_rn(make_float2(ex2a(fminf(a.x, 30.0f)), ex2a(fminf(a.y, 30.0f))), one);
+    const float2 db = __fadd2_rn(make_float2(ex2a(fminf(b.x, 30.0f)), ex2a(fminf(b.y, 30.0f))), one);
+    const float pa = da.x * da.y, pb = db.x * db.y;
+    const float r = rcpa(pa * pb);
+    const float ra = r * pb, rb = r * pa;
+    ta = __ffma2_rn(m2, make_float2(ra * da.y, ra * da.x), one);
+    tb = __ffma2_rn(m2, make_float2(rb * db.y, rb * db.x), one);
+  }
 }
 // x·(1 − h²) for a pair
 __device__ __forceinline__ float2 times_dtanh2(float2 x, float2 h) {
@@ -237,7 +253,7 @@ struct MlpTc {
     }
   }
   // h1 for one unit: tanh(base + Σ_covariates ζP[idx]·W1[nC + c][·]); records the covariates in xs; features >= H1 are zero
-  template <bool SHR = false>
+  template <int SHR = 0>
   __device__ __forceinline__ static void layer1(const Cfg<float>& cfg, uint32_t tab, const float* __restrict__ phi,
                                                 const float* __restrict__ zetaP, int M_units, int m, bool in, const float (&base)[TC_HP],
                                                 float (&xs)[8], float (&h1)[TC_HP]) {
@@ -257,16 +273,19 @@ struct MlpTc {
         }
       }
     }
+    static_assert(H1 % 4 == 0 && TC_HP % 4 == 0, "hidden widths in fours");
 #pragma unroll
-    for (int j = 0; j < TC_HP; j += 2) {
+    for (int j = 0; j < TC_HP; j += 4) {
       if (j < H1) {
-        const float2 v = tanh2_sel<SHR>(__fmul2_rn(make_float2(h1[j], h1[j + 1]), make_float2(K2LOG2E, K2LOG2E)));
-        h1[j] = v.x; h1[j + 1] = v.y;
-      } else h1[j] = h1[j + 1] = 0.0f;
+        const float2 k2 = make_float2(K2LOG2E, K2LOG2E);
+        float2 va, vb;
+        tanh4_sel<SHR>(__fmul2_rn(make_float2(h1[j], h1[j + 1]), k2), __fmul2_rn(make_float2(h1[j + 2], h1[j + 3]), k2), va, vb);
+        h1[j] = va.x; h1[j + 1] = va.y; h1[j + 2] = vb.x; h1[j + 3] = vb.y;
+      } else h1[j] = h1[j + 1] = h1[j + 2] = h1[j + 3] = 0.0f;
     }
   }
   // h2 from the accumulator row and the pre-activations of the last layer
-  template <bool SHR = false>
+  template <int SHR = 0>
   __device__ __forceinline__ static void layer2_epi(uint32_t tab, const float (&z)[TC_HP], float (&h2)[TC_HP], float (&z3)[2]) {
     z3[0] = z3[1] = 0.0f;
 #pragma unroll
@@ -275,8 +294,9 @@ struct MlpTc {
         const float4 b = lds128(tab + 4 * (T_B2 + 4 * j4));
         const float4 wa = lds128(tab + 4 * (T_W3 + 8 * j4)), wb = lds128(tab + 4 * (T_W3 + 8 * j4 + 4));
         const float2 k2 = make_float2(K2LOG2E, K2LOG2E);
-        const float2 ha = tanh2_sel<SHR>(__ffma2_rn(make_float2(z[4 * j4], z[4 * j4 + 1]), k2, make_float2(b.x, b.y)));
-        const float2 hb = tanh2_sel<SHR>(__ffma2_rn(make_float2(z[4 * j4 + 2], z[4 * j4 + 3]), k2, make_float2(b.z, b.w)));
+        float2 ha, hb;
+        tanh4_sel<SHR>(__ffma2_rn(make_float2(z[4 * j4], z[4 * j4 + 1]), k2, make_float2(b.x, b.y)),
+                       __ffma2_rn(make_float2(z[4 * j4 + 2], z[4 * j4 + 3]), k2, make_float2(b.z, b.w)), ha, hb);
         h2[4 * j4] = ha.x; h2[4 * j4 + 1] = ha.y; h2[4 * j4 + 2] = hb.x; h2[4 * j4 + 3] = hb.y;
         z3[0] = fmaf(h2[4 * j4], wa.x, z3[0]); z3[1] = fmaf(h2[4 * j4], wa.y, z3[1]);
         z3[0] = fmaf(h2[4 * j4 + 1], wa.z, z3[0]); z3[1] = fmaf(h2[4 * j4 + 1], wa.w, z3[1]);
@@ -319,7 +339,7 @@ constexpr int TF_TMEM_COLS = 128, TF_T_AHI = 32, TF_T_ALO = 64;
 constexpr uint32_t TF_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr int TF_CTAS_PER_SM = 4;
 
-template <int NI, int H1, int H2, int NOUT, bool SHR>
+template <int NI, int H1, int H2, int NOUT, int SHR>
 __global__ void __launch_bounds__(TC_BLOCK, TF_CTAS_PER_SM)
 k_mlp3_tc_fwd(const __grid_constant__ Cfg<float> cfg, const float* __restrict__ phi, const float* __restrict__ xM,
               const float* __restrict__ zetaP, int M_units, int64_t nb, float* __restrict__ mu) {
@@ -769,12 +789,13 @@ bool tc_worthwhile(int64_t nb, int M_units) { return tc_mode() >= 3 || nb * (int
 cudaError_t launch_mlp3_tc_fwd(const Launch& L, const Cfg<float>& cfg, const float* phi, const float* xM, int64_t nb,
                                float* mu, int M_units, const float* zetaP) {
   if (tc_mode() < 1 || !tc_worthwhile(nb, M_units)) return cudaErrorNotSupported;
-  // HVI_TANH_SHARED=0: one reciprocal per tanh (two MUFU each); default: one reciprocal per pair of tanh
+  // HVI_TANH_SHARED=0: one reciprocal per tanh (two MUFU each); 1: one per pair of tanh; 2: one per four
   const char* shr_e = getenv("HVI_TANH_SHARED");
-  const bool shr = !(shr_e && atoi(shr_e) == 0);
+  const int shr = shr_e ? atoi(shr_e) : 1;
 #define X(NI, H1, H2, NO_)                                                                                  \
   if (tc_match(cfg, NI, H1, H2, NO_)) {                                                                     \
-    auto kern = shr ? k_mlp3_tc_fwd<NI, H1, H2, NO_, true> : k_mlp3_tc_fwd<NI, H1, H2, NO_, false>;         \
+    auto kern = shr == 2 ? k_mlp3_tc_fwd<NI, H1, H2, NO_, 2> : shr == 1 ? k_mlp3_tc_fwd<NI, H1, H2, NO_, 1> \
+                                                                        : k_mlp3_tc_fwd<NI, H1, H2, NO_, 0>; \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM);       \
     if (e != cudaSuccess) return e;                                                                         \
     const int64_t ntot = ((nb + TC_COLS - 1) / TC_COLS) * (M_units > 0 ? M_units : 1);                      \
