@@ -93,13 +93,36 @@ __device__ __forceinline__ void gather_preprocess_body(int nC, int nO, int64_t n
       for (int c = 0; c < nC; c++) xM_b[site * nC + c] = ds_xM[src * nC + c];
       if (isites_out) isites_out[site] = src;   // MeanVarSep reads its per-site parameters through this map
     }
-    for (int o = 0; o < nO; o++) {
+    // Float32 rows of 8 observations (DoubleMM): a site's drivers, observations and uncertainties are 64 + 32 + 32 contiguous,
+    // 16-byte aligned bytes -- fetched with 128-bit loads (whole sectors per lane), the raw drivers stored the same way
+    T va[8], vb[8], vy[8], vu[8];
+    bool vec = false;
+    if constexpr (sizeof(T) == 4) {
+      vec = nO == 8 && ((reinterpret_cast<uintptr_t>(ds_xP) | reinterpret_cast<uintptr_t>(xP_b) | reinterpret_cast<uintptr_t>(ds_yo) |
+                         reinterpret_cast<uintptr_t>(ds_yu)) & 15) == 0;
+      if (vec && site < nb) {
+        const float4* xp = reinterpret_cast<const float4*>(ds_xP + src * 16);
+        const float4 a0 = xp[0], a1 = xp[1], b0 = xp[2], b1 = xp[3];
+        float4* xo = reinterpret_cast<float4*>(xP_b + site * 16);
+        xo[0] = a0; xo[1] = a1; xo[2] = b0; xo[3] = b1;
+        va[0] = a0.x; va[1] = a0.y; va[2] = a0.z; va[3] = a0.w; va[4] = a1.x; va[5] = a1.y; va[6] = a1.z; va[7] = a1.w;
+        vb[0] = b0.x; vb[1] = b0.y; vb[2] = b0.z; vb[3] = b0.w; vb[4] = b1.x; vb[5] = b1.y; vb[6] = b1.z; vb[7] = b1.w;
+        if (ds_yo) {
+          const float4* yp = reinterpret_cast<const float4*>(ds_yo + src * 8);
+          const float4 y0 = yp[0], y1 = yp[1];
+          vy[0] = y0.x; vy[1] = y0.y; vy[2] = y0.z; vy[3] = y0.w; vy[4] = y1.x; vy[5] = y1.y; vy[6] = y1.z; vy[7] = y1.w;
+        }
+        if (ds_yu) {
+          const float4* up = reinterpret_cast<const float4*>(ds_yu + src * 8);
+          const float4 u0 = up[0], u1 = up[1];
+          vu[0] = u0.x; vu[1] = u0.y; vu[2] = u0.z; vu[3] = u0.w; vu[4] = u1.x; vu[5] = u1.y; vu[6] = u1.z; vu[7] = u1.w;
+        }
+      }
+    }
+    // one observation of this lane's site into the tile's records (mask folded into the weight, as k_preprocess)
+    auto emit = [&](int o, T a, T b, T y, T u) {
       T s1 = T(1), s2 = T(1), yo = T(0), w = T(0);
       if (site < nb) {
-        const T a = ds_xP[src * 2 * nO + o], b = ds_xP[src * 2 * nO + nO + o];
-        xP_b[site * 2 * nO + o] = a;
-        xP_b[site * 2 * nO + nO + o] = b;
-        const T y = ds_yo ? ds_yo[src * nO + o] : T(NAN), u = ds_yu ? ds_yu[src * nO + o] : T(0);
         const bool valid = isfinite(a) && isfinite(b);
         const bool obs = !isnan(y);
         if (valid) { s1 = a; s2 = b; }
@@ -110,6 +133,22 @@ __device__ __forceinline__ void gather_preprocess_body(int nC, int nO, int64_t n
       r[(1 * nO + o) * 32] = s2;
       r[(2 * nO + o) * 32] = yo;
       r[(3 * nO + o) * 32] = w;
+    };
+    if (vec) {
+#pragma unroll
+      for (int o = 0; o < 8; o++) emit(o, va[o], vb[o], ds_yo ? vy[o] : T(NAN), ds_yu ? vu[o] : T(0));
+    } else {
+      for (int o = 0; o < nO; o++) {
+        T a = T(0), b = T(0), y = T(NAN), u = T(0);
+        if (site < nb) {
+          a = ds_xP[src * 2 * nO + o]; b = ds_xP[src * 2 * nO + nO + o];
+          xP_b[site * 2 * nO + o] = a;
+          xP_b[site * 2 * nO + nO + o] = b;
+          if (ds_yo) y = ds_yo[src * nO + o];
+          if (ds_yu) u = ds_yu[src * nO + o];
+        }
+        emit(o, a, b, y, u);
+      }
     }
   }
   cst = warp_sum(cst);
