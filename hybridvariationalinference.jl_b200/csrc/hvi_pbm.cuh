@@ -261,11 +261,11 @@ __device__ __forceinline__ void normal4(u64 seed, u64 gcol, int m4, float (&n4)[
   const u32 r[4] = {c0, c1, c2, c3};
 #pragma unroll
   for (int h = 0; h < 2; h++) {
-    const float u1 = ((float)(r[2 * h] >> 8) + 1.0f) * 5.9604644775390625e-08f;
-    const float u2 = (float)(r[2 * h + 1] >> 8) * 5.9604644775390625e-08f;
-    const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));
+    const float u1 = fmaf((float)(r[2 * h] >> 8), 5.9604644775390625e-08f, 5.9604644775390625e-08f);
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u1)));
     float sn, cs;
-    __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &sn, &cs);
+    __sincosf(fmaf((float)(r[2 * h + 1] >> 8), 6.283185307179586f * 5.9604644775390625e-08f, -3.141592653589793f), &sn, &cs);
     n4[2 * h] = rad * cs; n4[2 * h + 1] = rad * sn;
   }
 }

@@ -27,11 +27,14 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t gcol, int m4, fl
   philox4x32_10((uint32_t)gcol, (uint32_t)(gcol >> 32), (uint32_t)m4, 0x5eedu, (uint32_t)seed, (uint32_t)(seed >> 32), r);
 #pragma unroll
   for (int h = 0; h < 2; h++) {
-    const float u1 = ((float)(r[2 * h] >> 8) + 1.0f) * 5.9604644775390625e-08f;   // (0, 1], 24 bits
-    const float u2 = (float)(r[2 * h + 1] >> 8) * 5.9604644775390625e-08f;        // [0, 1)
-    const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));                    // sqrt(−2 ln u1)
+    // u1 = (k + 1)·2⁻²⁴ in (0, 1], angle = 2π·k'·2⁻²⁴ − π in [−π, π): one FFMA each after the conversion (the same values
+    // as the two-step forms, the scalings are powers of two); sqrt on the MUFU pipe (sqrt.approx: 1 ulp, a draw does not
+    // need the IEEE square root's fix-up sequence)
+    const float u1 = fmaf((float)(r[2 * h] >> 8), 5.9604644775390625e-08f, 5.9604644775390625e-08f);
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u1)));   // sqrt(−2 ln u1)
     float sn, cs;
-    __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &sn, &cs);             // argument in [−π, π)
+    __sincosf(fmaf((float)(r[2 * h + 1] >> 8), 6.283185307179586f * 5.9604644775390625e-08f, -3.141592653589793f), &sn, &cs);
     n4[2 * h] = rad * cs; n4[2 * h + 1] = rad * sn;
   }
 }
