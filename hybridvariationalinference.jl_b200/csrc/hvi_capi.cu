@@ -927,7 +927,7 @@ static int run_g_fwd(hvi_plan* p, const Launch& L, const Cfg<T>& cfg, const T* p
 // forward → stream → backward per block while the block's activations are still in the cache: nothing is recomputed.
 // Returns the sites per block (0: one block = the unblocked schedule) and the rows of a cache slot.
 // HVI_WIDE_BLOCK_SITES forces a block size (tests), HVI_WIDE_CACHE_MB caps the cache.
-static int64_t wide_block_sites(hvi_plan* p, int nL, int maxw, int M, int64_t* slot_rows) {
+static int64_t wide_block_sites(hvi_plan* p, int nL, int maxw, int M, int64_t* slot_rows, int shrink = 0) {
   *slot_rows = 0;
   const int64_t col_bytes = (int64_t)(nL - 1) * maxw * 4;
   const int64_t nch = bf3_chunks(p->nb), WIDE_CHUNK = bf3_chunk_rows();
@@ -943,6 +943,7 @@ static int64_t wide_block_sites(hvi_plan* p, int nL, int maxw, int M, int64_t* s
   // allocated after it (per-draw means of a block, caller's own allocations)
   int64_t avail = (int64_t)fr + p->cap_wide_cache - ((int64_t)8 << 30);
   if (const char* e = getenv("HVI_WIDE_CACHE_MB")) { const int64_t cap = atoll(e) << 20; if (cap < avail) avail = cap; }
+  avail >>= shrink;   // after a failed allocation (fragmented free memory): half, a quarter, ...
   const int64_t rows1 = nch == 1 ? (p->nb + 127) / 128 * 128 : 0;
   if (avail >= nch * (1 + (int64_t)M) * (int64_t)bf3_cache_slot_bytes(nL, maxw, rows1)) return 0;   // everything fits: one block
   const int64_t sites_max = avail / col_bytes / M;
@@ -987,10 +988,16 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
         if (rc) return rc;
         blk = wide_block_sites(p, cfg.nL, cfg.max_width, M, &slot_rows);
       }
-      if (blk > 0) {
+      // the cache of one block; a failed allocation (free memory in pieces) is retried with smaller blocks
+      for (int shrink = 1; blk > 0; shrink++) {
         const int64_t need = (int64_t)M * bf3_chunks(blk) * (int64_t)bf3_cache_slot_bytes(cfg.nL, cfg.max_width, slot_rows);
         rc = ensure(p, &p->d_wide_cache, &p->cap_wide_cache, need);
-        if (rc) return rc;
+        if (rc == HVI_OK) break;
+        (void)cudaGetLastError();
+        if (shrink > 3) return rc;
+        blk = wide_block_sites(p, cfg.nL, cfg.max_width, M, &slot_rows, shrink);   // 0: the unblocked schedule below
+      }
+      if (blk > 0) {
         cache_u = WideCache{p->d_wide_cache, (int64_t)M * bf3_chunks(blk), 0, slot_rows};
       } else {
         const int64_t nch = bf3_chunks(p->nb), need = nch * (1 + (pbm ? M : 0));
