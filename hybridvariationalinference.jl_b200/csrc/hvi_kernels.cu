@@ -816,31 +816,36 @@ static bool mlp3_match(const Cfg<T>& c, int ni, int h1, int h2, int no) {
 constexpr int FIN_THREADS = 256;
 
 __device__ __noinline__ double block_sum_fixed(double v, double* sred) {
-  // fixed-shape tree: deterministic run to run
-  const int t = threadIdx.x;
-  sred[t] = v;
+  // fixed shape (butterfly inside each warp, then the warps' totals in warp order): deterministic run to run
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  constexpr int NW = FIN_THREADS / 32;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();   // sred may still be read by an earlier call's last step
+  if (lane == 0) sred[warp] = v;
   __syncthreads();
-  for (int s = FIN_THREADS / 2; s > 0; s >>= 1) {
-    if (t < s) sred[t] += sred[t + s];
-    __syncthreads();
-  }
-  const double r = sred[0];
+  double sum = 0.0;
+  for (int w = 0; w < NW; w++) sum += sred[w];
   __syncthreads();
-  return r;
+  return sum;
 }
 
-// the same tree for n values per thread at once (one pass of barriers instead of n): sums[i] = Σ_threads v[i],
-// bit-identical to n separate calls; sred holds n·FIN_THREADS doubles, sums is shared memory
+// the same for n values per thread at once: sums[i] = Σ_threads v[i], bit-identical to n separate calls; sred holds at
+// least 8·n doubles, sums is shared memory
 __device__ __noinline__ void block_sum_fixed_n(const double* v, int n, double* sred, double* sums) {
-  const int t = threadIdx.x;
-  for (int i = 0; i < n; i++) sred[i * FIN_THREADS + t] = v[i];
-  __syncthreads();
-  for (int s = FIN_THREADS / 2; s > 0; s >>= 1) {
-    if (t < s)
-      for (int i = 0; i < n; i++) sred[i * FIN_THREADS + t] += sred[i * FIN_THREADS + t + s];
-    __syncthreads();
+  // butterfly inside each warp, then the warps' totals in warp order: two barriers instead of one per tree level
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  constexpr int NW = FIN_THREADS / 32;
+  for (int i = 0; i < n; i++) {
+    double x = v[i];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sred[i * NW + warp] = x;
   }
-  if (t < n) sums[t] = sred[t * FIN_THREADS];
+  __syncthreads();
+  if (t < n) {
+    double sum = 0.0;
+    for (int w = 0; w < NW; w++) sum += sred[t * NW + w];
+    sums[t] = sum;
+  }
   __syncthreads();
 }
 
@@ -977,11 +982,13 @@ __device__ __noinline__ void finalize_body(const Cfg<T>& cfg, const T* __restric
   // round trip instead of one dependent global load after the other
   __shared__ EvalConsts<T> sec;
   __shared__ T sls2P[MAXP];
+  __shared__ double sbc[2];   // the two constants of the registered batch
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(ecp);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sec);
     _Pragma("unroll 1") for (int e = t; e < (int)(sizeof(EvalConsts<T>) / 4); e += FIN_THREADS) dst[e] = src[e];
     if (t < nP) sls2P[t] = phi[cfg.o_ls2P + t];
+    if (t < 2) sbc[t] = batch_consts[t];
   }
   double bad = 0.0;
   _Pragma("unroll 1") for (int e = t; e < nred_blocks; e += FIN_THREADS) bad += red[128 + e];
@@ -1033,7 +1040,7 @@ __device__ __noinline__ void finalize_body(const Cfg<T>& cfg, const T* __restric
     const double* cPs = aPs + nP;
     // G(o): slot of ϕ position o (≥ nphig, outside the logσ2_ζMs block) in the compressed vector
     auto Gp = [&](int o) -> double* { return sq + (o - cfg.nphig - ((cfg.sepvar && o >= cfg.o_coef + big) ? big : 0)); };
-    double nLy = 0.5 * w * sacc[ACC_NLY] + batch_consts[0];
+    double nLy = 0.5 * w * sacc[ACC_NLY] + sbc[0];
     double nlp = w * sacc[ACC_PRIOR];
     double lj = w * sacc[ACC_LJ];
     double logsig = sacc[ACC_LOGSIG];
@@ -1095,7 +1102,7 @@ __device__ __noinline__ void finalize_body(const Cfg<T>& cfg, const T* __restric
   // an observation that is finite where a driver is not makes the reference's loss NaN: the masked
   // value is evaluated, and the anomaly count joins the non-finite count so that no caller of the device-resident result
   // (optimiser loop, all-reduce) takes the iteration for a clean one
-  if (t == 0) bad += batch_consts[1];
+  if (t == 0) bad += sbc[1];
   bad = block_sum_fixed(bad, sred);
   if (t == 0) out[cfg.nphi + 7] = bad;
 }
