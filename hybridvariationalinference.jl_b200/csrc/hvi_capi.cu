@@ -1141,7 +1141,7 @@ static bool fused_ok(const hvi_plan* p, int64_t nb, int M) {
 
 template <typename T>
 static int enqueue_fused(hvi_plan* p, int M, T* phi, double* out, T* grad_T, cudaStream_t s, uint64_t seed, int64_t site_offset,
-                         bool adam, int64_t batch_size, int64_t first_batch) {
+                         bool adam, int64_t batch_size, int64_t first_batch, int n_inner = 1) {
   const Cfg<T>& cfg = cfg_of<T>(p);
   int rc = ensure(p, &p->d_pdraw, &p->cap_pdraw, (int64_t)(sizeof(T) * pdraw_elems(cfg.nP, M)));
   if (rc) return rc;
@@ -1167,6 +1167,7 @@ static int enqueue_fused(hvi_plan* p, int M, T* phi, double* out, T* grad_T, cud
     a.eta = p->adam_eta; a.b1 = p->adam_b1; a.b2 = p->adam_b2; a.eps = p->adam_eps; a.ctr = p->d_ctr;
   }
   a.clocks = p->d_clocks;
+  a.n_inner = n_inner;
   Launch L{s, p->sm_count, &p->launches};
   CU(p, launch_small_iter<T>(L, cfg, a));
   return HVI_OK;
@@ -1904,7 +1905,16 @@ static int adam_run_t(hvi_plan* p, int n_iter, int M, uint64_t seed0, int64_t si
   rc = adam_iteration<T>(p, M, site_offset, batch_size, first_batch, s);
   if (rc) return rc;
   it = 1;
-  const bool use_graph = !p->wide && !p->profiling && n_iter > 1 && p->use_graphs;
+  // single-launch iterations: the remaining ones as a loop inside ONE launch (chunks of 4096 iterations)
+  if (n_iter > 1 && !p->profiling && fused_ok<T>(p, batch_size > 0 ? batch_size : p->nb, M) && !getenv("HVI_SMALL_NO_LOOP")) {
+    while (it < n_iter) {
+      const int n = n_iter - it < 4096 ? n_iter - it : 4096;
+      rc = enqueue_fused<T>(p, M, (T*)p->d_phi_opt, p->d_out, nullptr, s, 0, site_offset, true, batch_size, first_batch, n);
+      if (rc) return rc;
+      it += n;
+    }
+  }
+  const bool use_graph = !p->wide && !p->profiling && n_iter > 1 && p->use_graphs && it < n_iter;
   if (use_graph) {
     GraphKey key;
     graph_key(p, M, site_offset, batch_size, first_batch, &key);

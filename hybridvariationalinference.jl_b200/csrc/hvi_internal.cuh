@@ -103,6 +103,7 @@ struct SmallArgs {
   double eta, b1, b2, eps;
   unsigned long long* ctr;
   long long* clocks;    // optional: clock64() at the phase boundaries (profiling aid), NULL otherwise
+  int n_inner;          // optimiser iterations run by ONE launch (the loop is inside the kernel); 0 or 1: one
 };
 
 struct Launch {

@@ -1596,9 +1596,14 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
   const int t = threadIdx.x;
   const int M = a.st.M;
   const int64_t nb = a.st.nb;
+  // the iterations of the optimiser loop run INSIDE the launch (n_inner > 1): from the second one on the code comes out
+  // of the instruction cache instead of L2 -- the single iteration is bound by instruction fetch.  Iteration counter,
+  // seed and minibatch index live in device memory (a.ctr) and are advanced by the Adam phase, as for graph replays.
+  const int n_inner = (a.n_inner > 1 && a.adam_m && a.ctr) ? a.n_inner : 1;
+#define HVI_STAMP() do { if (a.clocks && t == 0) a.clocks[stamp] = clock64(); ++stamp; } while (0)
+  _Pragma("unroll 1") for (int inner = 0; inner < n_inner; inner++) {
   const uint64_t seed = a.ctr ? (uint64_t)a.ctr[2] : a.st.seed;
   int stamp = 0;
-#define HVI_STAMP() do { if (a.clocks && t == 0) a.clocks[stamp] = clock64(); ++stamp; } while (0)
   HVI_STAMP();
   // 0. minibatch of the device-resident dataset (hvi_adam_run_minibatches): gather + re-tile + batch constants
   if (a.ds_xM) {
@@ -1693,6 +1698,8 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
     }
   }
   HVI_STAMP();
+  __syncthreads();   // counters and ϕ of this iteration are visible to every thread of the block before the next one
+  }
 #undef HVI_STAMP
 }
 
