@@ -1643,7 +1643,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
   {
     StreamArgs<T> sa = a.st;
     sa.seed = seed; sa.seed_dev = nullptr; sa.rng = 1; sa.phi = a.phi;
-    stream_body<TR, T, NP, NM, NO, SMALL_THREADS, false, true, (NP > 0), false, true>(cfg, sa, smem_raw, 0, 1);
+    stream_body<TR, T, NP, NM, NO, SMALL_THREADS, false, true, (NP > 0), false, true, true>(cfg, sa, smem_raw, 0, 1);
   }
   __syncthreads();
   HVI_STAMP();

@@ -307,8 +307,10 @@ __host__ __device__ constexpr size_t stream_smem_bytes(size_t szT, int nwarp, in
 // generic loads); ILV: two draws share one pass of the observation loop
 // SPF: the site records and means of the next tile are prefetched into shared memory (costs (4·n_obs + n_θM)·128
 // bytes per warp; switched off by the launcher where that would cost a resident block)
+// COMPACT: every draw goes through the rolled one-draw loop (one copy of the per-draw code instead of five): the
+// single-launch iteration of small batches is bound by instruction fetch, not by issue
 template <class TR, typename T, int NP, int NM, int NO, int STREAM_THREADS, bool PBM, bool RNG, bool PDS = true, bool ILV = true,
-          bool SPF = true>
+          bool SPF = true, bool COMPACT = false>
 __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<T>& a, unsigned char* smem_raw, int bid,
                                             int nblk) {
   constexpr int CH = 16 / sizeof(T);  // elements per 16-byte chunk
@@ -477,7 +479,7 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
         const int nd = mode == 1 ? ((M - m0) < MCS ? (M - m0) : MCS) : M;   // draws of this stage
         const T* buf = ztile + (g & 1) * (32 * NM * MCS);
         if (active) {
-          const int nfull = nd / CH;
+          const int nfull = COMPACT ? 0 : nd / CH;
           // pbm covariates: the per-draw means of the NEXT chunk travel while this chunk is computed
           T mun[CH][NM];
           if constexpr (PBM) {

@@ -12,5 +12,5 @@ plan = hvi_b200.NegElboPlan(prob)
 plan.set_dataset(data["xM"], data["xP"], data["y_o"], data["y_unc"])
 plan.adam_init(prob.init_ϕ(), eta=0.02)
 plan.use_fused(1)
-tr = plan.adam_run_minibatches(40, 3, 20, seed0=1)
+tr = plan.adam_run_minibatches(400, 3, 20, seed0=1)
 print(tr[-3:])
