@@ -1130,10 +1130,11 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
 // after it) as ONE launch of one block
 template <typename T>
 static bool fused_ok(const hvi_plan* p, int64_t nb, int M) {
-  // one block does the work of the whole GPU: the single launch wins only while its ≈ 35 µs + 0.3 µs per site stay below the
-  // ≈ 55 µs of the graph-replayed latency-bound launches (profiles/r02f_small_batch_latency.txt, Float32, µs per iteration:
-  // 20 x 3: 42 against 55; 50 x 12: 53 against 55; 200 x 12: 98 against 58; 800 x 12: 278 against 54) -- use_fused = 1 applies
-  // that break-even, 2 forces the path wherever it is supported
+  // one block does the work of the whole GPU: the single launch wins only while its ≈ 25 µs + 0.3 µs per site stay below the
+  // ≈ 45 µs of the graph-replayed latency-bound launches (profiles/r02s_small_batch_latency_loop_in_kernel.txt, Float32, µs
+  // per iteration with the optimiser loop inside the launch: 20 x 3: 29 against 43; 20 x 12: 33 against 47; 50 x 12: 41
+  // against 47; 200 x 12: 87 against 47; a single evaluation without the loop: 37 against 43 at 20 x 3) -- use_fused = 1
+  // applies that break-even, 2 forces the path wherever it is supported
   const bool fits = p->use_fused >= 2 ? (nb <= 1024 && nb * (int64_t)M <= 16384) : (nb <= 48 && nb * (int64_t)M <= 1024);
   return p->use_fused && !p->wide && !p->gpbm && !p->profiling && fits &&
          small_iter_supported<T>(cfg_of<T>(const_cast<hvi_plan*>(p)), nb, M);
