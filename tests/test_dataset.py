@@ -189,6 +189,35 @@ def test_adam_run_minibatches_matches_host_loop(scen, dtype, tol):
     assert np.all(np.isfinite(tr3))
 
 
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_optimiser_loop_inside_the_launch_equals_one_launch_per_iteration(dtype, monkeypatch):
+    """k_small_iter runs the iterations of a call as a loop inside ONE launch (counters, seed and minibatch index in device
+    memory); HVI_SMALL_NO_LOOP=1 launches it once per iteration: bit-identical loss trace and parameters, fewer launches"""
+    prob = hvi_b200.DoubleMMCase(dtype=dtype)
+    data = hvi_b200.gen_hybridproblem_synthetic(prob, 100, seed=3)
+    ϕ0 = prob.init_ϕ()
+    bs, M, n_iter = 20, 3, 23
+
+    def run():
+        plan = hvi_b200.NegElboPlan(prob)
+        try:
+            plan.set_dataset(*(data[k] for k in KEYS))
+            plan.adam_init(ϕ0, eta=0.02)
+            n0 = plan.launch_count
+            tr = plan.adam_run_minibatches(n_iter, M, bs, seed0=5, first_batch=1)
+            tr_b = plan.adam_run_minibatches(7, M, bs, seed0=50)          # a second call continues the trajectory
+            return np.concatenate([tr, tr_b]), plan.adam_phi(), plan.launch_count - n0
+        finally:
+            plan.close()
+
+    tr, ϕ, n_loop = run()
+    monkeypatch.setenv("HVI_SMALL_NO_LOOP", "1")
+    tr1, ϕ1, n_single = run()
+    assert np.all(np.isfinite(tr))
+    assert np.array_equal(tr, tr1) and np.array_equal(ϕ, ϕ1)
+    assert n_loop < n_single and n_loop <= 8 and n_single >= n_iter + 7
+
+
 def test_adam_skips_anomalous_minibatch_without_counting_it():
     """a finite observation under a missing driver makes the reference's loss NaN: on the device
     loop that minibatch is skipped (NaN in the trace) and does not advance the Adam step count"""
