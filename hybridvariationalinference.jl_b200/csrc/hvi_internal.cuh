@@ -104,6 +104,7 @@ struct SmallArgs {
   unsigned long long* ctr;
   long long* clocks;    // optional: clock64() at the phase boundaries (profiling aid), NULL otherwise
   int n_inner;          // optimiser iterations run by ONE launch (the loop is inside the kernel); 0 or 1: one
+  int units_mode;       // > 0: shared-memory bytes the (site, draw)-parallel streaming phase may use; 0: thread per site
 };
 
 struct Launch {

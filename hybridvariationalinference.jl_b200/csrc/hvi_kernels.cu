@@ -1643,7 +1643,11 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
   {
     StreamArgs<T> sa = a.st;
     sa.seed = seed; sa.seed_dev = nullptr; sa.rng = 1; sa.phi = a.phi;
-    stream_body<TR, T, NP, NM, NO, SMALL_THREADS, false, true, (NP > 0), false, true, true>(cfg, sa, smem_raw, 0, 1);
+    // few sites: one thread per (site, draw) unit (stream_units_body); otherwise one thread per site (stream_body)
+    const bool units_mode = a.units_mode && nb < 128 &&
+                            stream_units_smem(sizeof(T), nb, M, stream_units_nv<NP, NM>(), nacc(NP, NM)) <= (size_t)a.units_mode;
+    if (units_mode) stream_units_body<TR, T, NP, NM, NO, SMALL_THREADS>(cfg, sa, smem_raw, seed);
+    else stream_body<TR, T, NP, NM, NO, SMALL_THREADS, false, true, (NP > 0), false, true, true>(cfg, sa, smem_raw, 0, 1);
   }
   __syncthreads();
   HVI_STAMP();
@@ -1725,6 +1729,8 @@ cudaError_t launch_small_iter(const Launch& L, const Cfg<T>& cfg, SmallArgs<T> a
   a.st.pd_in_smem = cfg.nP > 0 ? 1 : 0;
   a.st.staged = 0; a.st.rng = 1;
   const size_t smem = small_iter_smem(cfg, a.st.M);
+  // bytes of shared memory the (site, draw) form of the streaming phase may use (0: thread-per-site form, HVI_SMALL_UNITS=0)
+  { const char* e = getenv("HVI_SMALL_UNITS"); a.units_mode = (e && atoi(e) == 0) ? 0 : (int)smem; }
 #define X(P, M_, O)                                                                              \
   if (cfg.nP == P && cfg.nM == M_ && cfg.nO == O) {                                              \
     auto kern = k_small_iter<DynTraits, T, P, M_, O>;                                            \

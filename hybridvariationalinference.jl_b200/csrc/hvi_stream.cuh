@@ -653,6 +653,153 @@ __device__ __forceinline__ void stream_body(const Cfg<T>& cfg, const StreamArgs<
 }
 
 
+// ---------------------------------------------------------------------------------------
+// The streaming phase of a SMALL batch inside one block (k_small_iter): one thread per (site, draw) unit instead of one
+// per site -- 20 sites x 12 draws keep 240 threads busy instead of 20 lanes of one warp.  A unit runs the per-draw code
+// once (do_draw, device draws) and hands its contributions to shared memory; one thread per site then adds its draws
+// in draw order and applies the end-of-site formulas of stream_body; the sites are added in site order (double).
+// No MeanVarSep, no pbm covariates (k_small_iter supports neither).
+// ---------------------------------------------------------------------------------------
+template <int NP, int NM>
+__host__ __device__ constexpr int stream_units_nv() { return NM + tri(NM) + (NP > 0 ? NP + tri(NP) : 0) + 5; }
+__host__ __device__ constexpr size_t stream_units_smem(size_t szT, int64_t nb, int M, int nv, int nacc_) {
+  return ((size_t)nb * M * nv + (size_t)nb * nacc_) * szT;
+}
+
+template <class TR, typename T, int NP, int NM, int NO, int THREADS>
+__device__ __forceinline__ void stream_units_body(const Cfg<T>& cfg, const StreamArgs<T>& a, unsigned char* smem_raw, uint64_t seed) {
+  constexpr int NUM = tri(NM), NUP = tri(NP), NACC = nacc(NP, NM);
+  constexpr int NV = stream_units_nv<NP, NM>();
+  constexpr int PD = pd_stride(NP);
+  constexpr int REC = 4 * NO * 32;
+  using ST = SiteState<T, NP, NM, NO>;
+  const int t = threadIdx.x;
+  const int M = a.M;
+  const int nb = (int)a.nb, units = nb * M;
+  T* vals = reinterpret_cast<T*>(smem_raw);          // [units][NV]
+  T* accs = vals + (size_t)units * NV;               // [nb][NACC]
+  T cA[NM], cB[NM], U[NUM];
+#pragma unroll
+  for (int k = 0; k < NM; k++) {
+    cA[k] = a.ec->coefA[k];
+    cB[k] = a.ec->coefB[k];
+#pragma unroll
+    for (int j = 0; j <= k; j++) U[ut(j, k)] = a.ec->UM[j][k];
+  }
+  const T wM = T(1) / T(M);
+  // ---- one (site, draw) unit per thread
+  for (int u = t; u < units; u += THREADS) {
+    const int site = u / M, m = u - site * M;
+    ST st;
+    {
+      const T* r = a.rec + (size_t)(site >> 5) * REC + (site & 31);
+#pragma unroll
+      for (int o = 0; o < ST::NOP; o++) {
+        const bool two = (2 * o + 1 < NO);
+        const int o0 = 2 * o, o1 = two ? 2 * o + 1 : 2 * o;
+        st.S1[o] = mk2(r[(0 * NO + o0) * 32], r[(0 * NO + o1) * 32]);
+        st.S2[o] = mk2(r[(1 * NO + o0) * 32], r[(1 * NO + o1) * 32]);
+        st.nyo[o] = mk2(-r[(2 * NO + o0) * 32], -r[(2 * NO + o1) * 32]);
+        st.w[o] = mk2(r[(3 * NO + o0) * 32], two ? r[(3 * NO + o1) * 32] : T(0));
+        st.S12[o] = pmul(st.S1[o], st.S2[o]);
+        st.q[o] = mk2(T(0), T(0));
+      }
+    }
+    T z[NM], zb[NM];
+#pragma unroll
+    for (int k = 0; k < NM; k++) {
+      st.mu[k] = a.mu[(size_t)site * NM + k];
+      const T sig = exp_t(T(0.5) * fma(cB[k], st.mu[k], cA[k]));
+      st.smu[k] = T(0);
+#pragma unroll
+      for (int j = 0; j <= k; j++) st.sU[ut(j, k)] = sig * U[ut(j, k)];
+      float n4[4];
+      normal4(seed, (uint64_t)(a.col_offset + (int64_t)site * NM + k), m / 4, n4);
+      z[k] = (T)((m & 3) == 0 ? n4[0] : (m & 3) == 1 ? n4[1] : (m & 3) == 2 ? n4[2] : n4[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < NUM; i++) st.sz[i] = T(0);
+#pragma unroll
+    for (int i = 0; i < (NP > 0 ? NP : 1); i++) st.aP[i] = T(0);
+#pragma unroll
+    for (int i = 0; i < (NP > 0 ? NUP : 1); i++) st.cP[i] = T(0);
+    st.prior = st.lj = st.u2 = st.ljln = T(0);
+    do_draw<TR, T, NP, NM, NO>(cfg, st, z, a.pd + (size_t)m * PD, st.mu, zb);
+    T* v = vals + (size_t)u * NV;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < NM; k++) v[c++] = st.smu[k];
+#pragma unroll
+    for (int i = 0; i < NUM; i++) v[c++] = st.sz[i];
+    if constexpr (NP > 0) {
+#pragma unroll
+      for (int j = 0; j < NP; j++) v[c++] = st.aP[j];
+#pragma unroll
+      for (int i = 0; i < NUP; i++) v[c++] = st.cP[i];
+    }
+    v[c++] = st.prior; v[c++] = st.lj; v[c++] = st.u2; v[c++] = st.ljln;
+    {
+      typename PairT<T>::type s2 = mk2(T(0), T(0));
+#pragma unroll
+      for (int o = 0; o < ST::NOP; o++) s2 = pfma(st.w[o], st.q[o], s2);
+      v[c++] = s2.x + s2.y;
+    }
+  }
+  __syncthreads();
+  // ---- one thread per site: its draws in draw order, then the end of site (σ-path, entropy, μ̄_ζ) as in stream_body
+  for (int site = t; site < nb; site += THREADS) {
+    T sum[NV];
+#pragma unroll
+    for (int c = 0; c < NV; c++) sum[c] = T(0);
+    for (int m = 0; m < M; m++) {
+      const T* v = vals + ((size_t)site * M + m) * NV;
+#pragma unroll
+      for (int c = 0; c < NV; c++) sum[c] += v[c];
+    }
+    const T* smu = sum;
+    const T* sz = sum + NM;
+    const T* aP = sz + NUM;
+    const T* cP = aP + (NP > 0 ? NP : 0);
+    const T* tail = sum + NV - 5;   // prior, lj, u2, ljln, nly
+    T acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) acc[i] = T(0);
+    acc[ACC_NLY] = tail[4];
+    acc[ACC_LJ] = tail[1];
+    acc[ACC_PRIOR] = tail[0] + T(0.5) * tail[2] + (all_exp_ln<TR, NM>() ? tail[1] : tail[3]);
+#pragma unroll
+    for (int k = 0; k < NM; k++) {
+      const T mu = a.mu[(size_t)site * NM + k];
+      const T ls = fma(cB[k], mu, cA[k]);
+      const T sig = exp_t(T(0.5) * ls);
+      T sr = T(0);
+#pragma unroll
+      for (int j = 0; j <= k; j++) sr = fma(sig * U[ut(j, k)], sz[ut(j, k)], sr);
+      const T lsb = T(0.5) * wM * sr - T(0.5);
+      acc[ACC_LOGSIG] += T(0.5) * ls;
+      acc[ACC_FIRST_VEC + k] = lsb;
+      acc[ACC_FIRST_VEC + NM + k] = lsb * mu;
+      a.mubar[(size_t)site * NM + k] = fma(wM, smu[k], lsb * cB[k]);
+#pragma unroll
+      for (int j = 0; j <= k; j++) acc[ACC_FIRST_VEC + 2 * NM + ut(j, k)] = sig * sz[ut(j, k)];
+    }
+    if constexpr (NP > 0) {
+#pragma unroll
+      for (int j = 0; j < NP; j++) acc[ACC_FIRST_VEC + 2 * NM + NUM + j] = aP[j];
+#pragma unroll
+      for (int i = 0; i < NUP; i++) acc[ACC_FIRST_VEC + 2 * NM + NUM + NP + i] = cP[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NACC; i++) accs[(size_t)site * NACC + i] = acc[i];
+  }
+  __syncthreads();
+  for (int i = t; i < NACC; i += THREADS) {
+    double tot = 0.0;
+    for (int site = 0; site < nb; site++) tot += (double)accs[(size_t)site * NACC + i];
+    a.partials[i] = tot;
+  }
+}
+
 // (n_θP, n_θM, n_obs) shapes with a compiled streaming kernel
 #define HVI_STREAM_CASES(X) \
   X(0, 2, 8) X(1, 2, 8) X(2, 2, 8) X(0, 3, 8) X(1, 3, 8) X(2, 3, 8) X(3, 2, 8) X(2, 1, 8) X(2, 2, 4)
