@@ -1029,21 +1029,26 @@ __device__ __noinline__ void finalize_body(const Cfg<T>& cfg, const T* __restric
     }
   }
   __syncthreads();
+  // the serial part runs on two warps: thread 0 takes the likelihood/prior scalars, the log σ² coefficients and the M block,
+  // thread 32 the global (P) block; they write disjoint entries of ∇ϕq, the P block's scalar contributions travel through
+  // shared memory and thread 0 assembles the components afterwards
+  __shared__ double sPpart[3];   // P block's parts of nlp, lj, logsig
+  const double w = 1.0 / (double)M;
+  const int NUM = tri(nM);
+  const double* abar = sacc + ACC_FIRST_VEC;
+  const double* bbar = abar + nM;
+  const double* cU = bbar + nM;
+  const double* aPs = cU + NUM;
+  const double* cPs = aPs + nP;
+  // G(o): slot of ϕ position o (≥ nphig, outside the logσ2_ζMs block) in the compressed vector
+  auto Gp = [&](int o) -> double* { return sq + (o - cfg.nphig - ((cfg.sepvar && o >= cfg.o_coef + big) ? big : 0)); };
+  double nLy = 0.0, nlp = 0.0, lj = 0.0, logsig = 0.0;
   if (t == 0) {
     const EvalConsts<T>& ec = sec;
-    const double w = 1.0 / (double)M;
-    const int NUM = tri(nM);
-    const double* abar = sacc + ACC_FIRST_VEC;
-    const double* bbar = abar + nM;
-    const double* cU = bbar + nM;
-    const double* aPs = cU + NUM;
-    const double* cPs = aPs + nP;
-    // G(o): slot of ϕ position o (≥ nphig, outside the logσ2_ζMs block) in the compressed vector
-    auto Gp = [&](int o) -> double* { return sq + (o - cfg.nphig - ((cfg.sepvar && o >= cfg.o_coef + big) ? big : 0)); };
-    double nLy = 0.5 * w * sacc[ACC_NLY] + sbc[0];
-    double nlp = w * sacc[ACC_PRIOR];
-    double lj = w * sacc[ACC_LJ];
-    double logsig = sacc[ACC_LOGSIG];
+    nLy = 0.5 * w * sacc[ACC_NLY] + sbc[0];
+    nlp = w * sacc[ACC_PRIOR];
+    lj = w * sacc[ACC_LJ];
+    logsig = sacc[ACC_LOGSIG];
     if (!cfg.omit_priors)
       _Pragma("unroll 1") for (int k = 0; k < nM; k++) nlp += (double)nb * cfg.prM_c0[k];
     // coefficients of log σ²
@@ -1054,17 +1059,20 @@ __device__ __noinline__ void finalize_body(const Cfg<T>& cfg, const T* __restric
     _Pragma("unroll 1") for (int k = 0; k < nM; k++)
       _Pragma("unroll 1") for (int j = 0; j <= k; j++) Ubar[j][k] = w * cU[k * (k + 1) / 2 + j];
     build_U_adj<T>(nM, cfg.blkM_start, cfg.rhoM_off, ec.UM, ec.nrmM, Ubar, Gp(cfg.o_rhoM));
+  } else if (t == 32) {
+    const EvalConsts<T>& ec = sec;
     // global block
-    double CP[MAXP][MAXP];
+    double nlpP = 0.0, ljP = 0.0, logsigP = 0.0;
+    double Ubar[MAXP][MAXP], CP[MAXP][MAXP];
     _Pragma("unroll 1") for (int j = 0; j < nP; j++) {
       double aP = w * aPs[j];
       _Pragma("unroll 1") for (int jj = 0; jj <= j; jj++) CP[jj][j] = w * cPs[j * (j + 1) / 2 + jj];
       if (cfg.count_globals) {
         aP += w * sPg[j][2];
         _Pragma("unroll 1") for (int jj = 0; jj <= j; jj++) CP[jj][j] += w * sPg[j][3 + jj];
-        nlp += w * sPg[j][0] + (cfg.omit_priors ? 0.0 : cfg.prP_c0[j]);
-        lj += w * sPg[j][1];
-        logsig += 0.5 * (double)sls2P[j];
+        nlpP += w * sPg[j][0] + (cfg.omit_priors ? 0.0 : cfg.prP_c0[j]);
+        ljP += w * sPg[j][1];
+        logsigP += 0.5 * (double)sls2P[j];
       }
       if (xu) {
         aP += sPx[j][0];
@@ -1082,6 +1090,12 @@ __device__ __noinline__ void finalize_body(const Cfg<T>& cfg, const T* __restric
     // pass 1 of g took μP[idx] as input (src/elbo.jl:491)
     if (xs)
       _Pragma("unroll 1") for (int c = 0; c < cfg.npc; c++) *Gp(cfg.o_muP + cfg.pbm_covar_idx[c]) += xs[c];
+    sPpart[0] = nlpP; sPpart[1] = ljP; sPpart[2] = logsigP;
+  }
+  __syncthreads();
+  if (t == 0) {
+    // the sums in the order of the one-thread form: the M block's terms first, then the P block's
+    nlp += sPpart[0]; lj += sPpart[1]; logsig += sPpart[2];
     const double Kdim = (double)nM * (double)nb + (cfg.count_globals ? nP : 0);
     const double ent = 0.5 * Kdim * 2.8378770664093454836 + logsig;   // (K·log(2πe) + 2Σlog σ)/2, logden_normal.jl:74
     const double nlj = -lj;
