@@ -211,17 +211,24 @@ __device__ __forceinline__ void prologue_body(const Cfg<T>& cfg, const T* __rest
                                               int M, EvalConsts<T>* __restrict__ ec, T* __restrict__ pdraw) {
   __shared__ EvalConsts<T> s;
   const int nP = cfg.nP, nM = cfg.nM;
+  // two serial sections on two warps: the M block's factor and the log σ² coefficients (thread 0), the P block's factor, σP
+  // and μP (thread 32); the constants then go to global memory with one word per thread
   if (threadIdx.x == 0) {
-    build_U<T>(nP, cfg.blkP_start, cfg.rhoP_off, phi + cfg.o_rhoP, s.UP, s.nrmP);
     build_U<T>(nM, cfg.blkM_start, cfg.rhoM_off, phi + cfg.o_rhoM, s.UM, s.nrmM);
     _Pragma("unroll 1") for (int k = 0; k < nM; k++) {   // intercept and slope of log σ² (src/elbo.jl:652-653); MeanVarSep has neither
       s.coefA[k] = cfg.sepvar ? T(0) : phi[cfg.o_coef + 2 * k];
       s.coefB[k] = cfg.sepvar ? T(0) : phi[cfg.o_coef + 2 * k + 1];
     }
+  } else if (threadIdx.x == 32) {
+    build_U<T>(nP, cfg.blkP_start, cfg.rhoP_off, phi + cfg.o_rhoP, s.UP, s.nrmP);
     _Pragma("unroll 1") for (int j = 0; j < nP; j++) { s.sigP[j] = exp_t(phi[cfg.o_ls2P + j] / T(2)); s.muP[j] = phi[cfg.o_muP + j]; }
-    *ec = s;
   }
   __syncthreads();
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&s);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(ec);
+    _Pragma("unroll 1") for (int e = threadIdx.x; e < (int)(sizeof(EvalConsts<T>) / 4); e += blockDim.x) dst[e] = src[e];
+  }
   T* rP = pdraw;
   T* zetaP = pdraw + (size_t)nP * M;
   T* thP = pdraw + (size_t)2 * nP * M;
