@@ -1256,7 +1256,7 @@ static size_t mlp_fwd_smem(const Cfg<T>& cfg) {
   return sizeof(T) * (((cfg.nphig + 3) & ~3) + (size_t)cfg.sum_width * MLP_BS);
 }
 template <typename T>
-static size_t mlp_bwd_smem(const Cfg<T>& cfg) {
+__host__ __device__ static size_t mlp_bwd_smem(const Cfg<T>& cfg) {
   return (sizeof(double) + sizeof(int2)) * cfg.nphig +
          sizeof(T) * (((cfg.nphig + 3) & ~3) + (size_t)(cfg.sum_width + cfg.sum_out) * MLP_BS);
 }
@@ -1510,7 +1510,9 @@ __device__ __forceinline__ void small_mlp_forward_tile(const Cfg<T>& cfg, const 
 template <typename T>
 __device__ __forceinline__ void small_mlp_fwd(const Cfg<T>& cfg, const T* __restrict__ phi, const T* __restrict__ xM,
                                               int64_t nb, T* __restrict__ mu, unsigned char* smem_raw) {
-  T* sW = reinterpret_cast<T*>(smem_raw);
+  // the layout of small_mlp_bwd (gradient accumulator | table | weights | activations | deltas): the backward phase
+  // finds weights and activations of a one-tile batch where this phase left them
+  T* sW = reinterpret_cast<T*>(reinterpret_cast<int2*>(reinterpret_cast<double*>(smem_raw) + cfg.nphig) + cfg.nphig);
   T* acts = sW + ((cfg.nphig + 3) & ~3);
   const int t = threadIdx.x, NT = blockDim.x;
   for (int e = t; e < cfg.nphig; e += NT) sW[e] = phi[e];
@@ -1534,14 +1536,16 @@ __device__ __forceinline__ void small_mlp_fwd(const Cfg<T>& cfg, const T* __rest
 template <typename T>
 __device__ __forceinline__ void small_mlp_bwd(const Cfg<T>& cfg, const T* __restrict__ phi, const T* __restrict__ xM,
                                               const T* __restrict__ mubar, int64_t nb, double* __restrict__ part,
-                                              unsigned char* smem_raw) {
+                                              unsigned char* smem_raw, bool reuse = false) {
   double* gacc = reinterpret_cast<double*>(smem_raw);                 // [nphig]
   int2* tab = reinterpret_cast<int2*>(gacc + cfg.nphig);              // [nphig] (delta row, act row | -1)
   T* sW = reinterpret_cast<T*>(tab + cfg.nphig);                      // [nphig]
   T* acts = sW + ((cfg.nphig + 3) & ~3);                              // [sum_width][BS]
   T* dl = acts + (size_t)cfg.sum_width * MLP_BS;                      // [sum_out][BS]
   const int t = threadIdx.x, NT = blockDim.x;
-  for (int e = t; e < cfg.nphig; e += NT) { sW[e] = phi[e]; gacc[e] = 0.0; }
+  // reuse: weights and the activations of the batch's only tile are still in place from small_mlp_fwd
+  reuse = reuse && nb <= MLP_BS;
+  for (int e = t; e < cfg.nphig; e += NT) { if (!reuse) sW[e] = phi[e]; gacc[e] = 0.0; }
   {
     int row_in = 0, drow = 0;
     for (int l = 0; l < cfg.nL; l++) {
@@ -1556,9 +1560,13 @@ __device__ __forceinline__ void small_mlp_bwd(const Cfg<T>& cfg, const T* __rest
   const int nlast = cfg.l_out[cfg.nL - 1];
   for (int64_t s0 = 0; s0 < nb; s0 += MLP_BS) {
     const int ns = (int)(nb - s0 < MLP_BS ? nb - s0 : MLP_BS);
-    for (int e = t; e < ns * cfg.nC; e += NT) acts[(e % cfg.nC) * MLP_BS + e / cfg.nC] = xM[s0 * cfg.nC + e];
-    __syncthreads();
-    small_mlp_forward_tile<T>(cfg, sW, acts, ns);
+    if (!reuse) {
+      for (int e = t; e < ns * cfg.nC; e += NT) acts[(e % cfg.nC) * MLP_BS + e / cfg.nC] = xM[s0 * cfg.nC + e];
+      __syncthreads();
+      small_mlp_forward_tile<T>(cfg, sW, acts, ns);
+    } else {
+      __syncthreads();   // the table and the zeroed accumulator
+    }
     // output delta: μ̄_ζ · σ_k · √(2π) e^{q²/2} · p(1−p)
     int drow = cfg.sum_out - nlast;
     for (int e = t; e < ns * nlast; e += NT) {
@@ -1656,6 +1664,11 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
   prologue_body<T>(cfg, a.phi, a.zP, M, const_cast<EvalConsts<T>*>(a.st.ec), a.pdraw);
   __syncthreads();
   HVI_STAMP();
+  // few sites: the streaming phase runs one thread per (site, draw) unit in shared memory BEHIND the applicator's, so that
+  // the backward phase finds the forward phase's weights and activations in place (no recomputation)
+  const size_t mlp_bytes = (mlp_bwd_smem<T>(cfg) + 15) & ~(size_t)15;
+  const bool units_mode = a.units_mode && nb < 128 &&
+                          mlp_bytes + stream_units_smem(sizeof(T), nb, M, stream_units_nv<NP, NM>(), nacc(NP, NM)) <= (size_t)a.units_mode;
   // 3. μ_ζ = g(xM; ϕg)
   small_mlp_fwd<T>(cfg, a.phi, a.xM, nb, const_cast<T*>(a.st.mu), smem_raw);
   __syncthreads();
@@ -1665,15 +1678,13 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
     StreamArgs<T> sa = a.st;
     sa.seed = seed; sa.seed_dev = nullptr; sa.rng = 1; sa.phi = a.phi;
     // few sites: one thread per (site, draw) unit (stream_units_body); otherwise one thread per site (stream_body)
-    const bool units_mode = a.units_mode && nb < 128 &&
-                            stream_units_smem(sizeof(T), nb, M, stream_units_nv<NP, NM>(), nacc(NP, NM)) <= (size_t)a.units_mode;
-    if (units_mode) stream_units_body<TR, T, NP, NM, NO, SMALL_THREADS>(cfg, sa, smem_raw, seed);
+    if (units_mode) stream_units_body<TR, T, NP, NM, NO, SMALL_THREADS>(cfg, sa, smem_raw + mlp_bytes, seed);
     else stream_body<TR, T, NP, NM, NO, SMALL_THREADS, false, true, (NP > 0), false, true, true>(cfg, sa, smem_raw, 0, 1);
   }
   __syncthreads();
   HVI_STAMP();
   // 5. μ̄_ζ → ∇ϕg (one row of partial sums)
-  small_mlp_bwd<T>(cfg, a.phi, a.xM, a.st.mubar, nb, a.part_mlp, smem_raw);
+  small_mlp_bwd<T>(cfg, a.phi, a.xM, a.st.mubar, nb, a.part_mlp, smem_raw, units_mode);
   __syncthreads();
   HVI_STAMP();
   // 6. what k_reduce does for a single row of partial sums: ∇ϕg and its non-finite count per group of 32 entries, the
@@ -1749,7 +1760,13 @@ template <typename T>
 cudaError_t launch_small_iter(const Launch& L, const Cfg<T>& cfg, SmallArgs<T> a) {
   a.st.pd_in_smem = cfg.nP > 0 ? 1 : 0;
   a.st.staged = 0; a.st.rng = 1;
-  const size_t smem = small_iter_smem(cfg, a.st.M);
+  size_t smem = small_iter_smem(cfg, a.st.M);
+  if (a.st.nb < 128) {   // room for the (site, draw) form of the streaming phase behind the applicator's shared memory
+    const size_t need = ((mlp_bwd_smem(cfg) + 15) & ~(size_t)15) +
+                        stream_units_smem(sizeof(T), a.st.nb, a.st.M, cfg.nM + tri(cfg.nM) + (cfg.nP > 0 ? cfg.nP + tri(cfg.nP) : 0) + 5,
+                                          nacc(cfg.nP, cfg.nM));
+    if (need > smem && need <= 200 * 1024) smem = need;
+  }
   // bytes of shared memory the (site, draw) form of the streaming phase may use (0: thread-per-site form, HVI_SMALL_UNITS=0)
   { const char* e = getenv("HVI_SMALL_UNITS"); a.units_mode = (e && atoi(e) == 0) ? 0 : (int)smem; }
 #define X(P, M_, O)                                                                              \
