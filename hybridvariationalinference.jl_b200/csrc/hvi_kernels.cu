@@ -1536,7 +1536,7 @@ __device__ __forceinline__ void small_mlp_fwd(const Cfg<T>& cfg, const T* __rest
 template <typename T>
 __device__ __forceinline__ void small_mlp_bwd(const Cfg<T>& cfg, const T* __restrict__ phi, const T* __restrict__ xM,
                                               const T* __restrict__ mubar, int64_t nb, double* __restrict__ part,
-                                              unsigned char* smem_raw, bool reuse = false) {
+                                              unsigned char* smem_raw, bool reuse = false, bool tab_ready = false) {
   double* gacc = reinterpret_cast<double*>(smem_raw);                 // [nphig]
   int2* tab = reinterpret_cast<int2*>(gacc + cfg.nphig);              // [nphig] (delta row, act row | -1)
   T* sW = reinterpret_cast<T*>(tab + cfg.nphig);                      // [nphig]
@@ -1546,7 +1546,7 @@ __device__ __forceinline__ void small_mlp_bwd(const Cfg<T>& cfg, const T* __rest
   // reuse: weights and the activations of the batch's only tile are still in place from small_mlp_fwd
   reuse = reuse && nb <= MLP_BS;
   for (int e = t; e < cfg.nphig; e += NT) { if (!reuse) sW[e] = phi[e]; gacc[e] = 0.0; }
-  {
+  if (!(reuse && tab_ready)) {   // the table depends on the network only: inside a launch it is built once
     int row_in = 0, drow = 0;
     for (int l = 0; l < cfg.nL; l++) {
       const int ni = cfg.l_in[l], no = cfg.l_out[l];
@@ -1684,7 +1684,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
   __syncthreads();
   HVI_STAMP();
   // 5. μ̄_ζ → ∇ϕg (one row of partial sums)
-  small_mlp_bwd<T>(cfg, a.phi, a.xM, a.st.mubar, nb, a.part_mlp, smem_raw, units_mode);
+  small_mlp_bwd<T>(cfg, a.phi, a.xM, a.st.mubar, nb, a.part_mlp, smem_raw, units_mode, inner > 0);
   __syncthreads();
   HVI_STAMP();
   // 6. what k_reduce does for a single row of partial sums: ∇ϕg and its non-finite count per group of 32 entries, the
@@ -1716,8 +1716,13 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_iter(const __grid_co
     const unsigned long long t_applied = a.ctr[0], it = a.ctr[1];
     const bool bad = a.out[n + 7] != 0.0 || !isfinite(a.out[n + 6]);
     if (!bad) {
-      const double tt = (double)(t_applied + 1);
-      const double c1 = 1.0 / (1.0 - pow(a.b1, tt)), c2 = 1.0 / (1.0 - pow(a.b2, tt));
+      // β^t by repeated squaring (t is an integer): ≈ 2 log2(t) multiplications instead of two double-precision pow()
+      double p1 = 1.0, p2 = 1.0, q1 = a.b1, q2 = a.b2;
+      _Pragma("unroll 1") for (unsigned long long e = t_applied + 1; e > 0; e >>= 1) {
+        if (e & 1) { p1 *= q1; p2 *= q2; }
+        q1 *= q1; q2 *= q2;
+      }
+      const double c1 = 1.0 / (1.0 - p1), c2 = 1.0 / (1.0 - p2);
       for (int64_t i = t; i < n; i += SMALL_THREADS) {
         const double g = a.out[i];
         const double mi = a.b1 * a.adam_m[i] + (1.0 - a.b1) * g, vi = a.b2 * a.adam_v[i] + (1.0 - a.b2) * g * g;
