@@ -1129,13 +1129,16 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
 // small batches with device draws: the whole evaluation (and optionally the minibatch gather before it and the Adam update
 // after it) as ONE launch of one block
 template <typename T>
-static bool fused_ok(const hvi_plan* p, int64_t nb, int M) {
+static bool fused_ok(const hvi_plan* p, int64_t nb, int M, bool looped = false) {
   // one block does the work of the whole GPU: the single launch wins only while its ≈ 25 µs + 0.3 µs per site stay below the
   // ≈ 45 µs of the graph-replayed latency-bound launches (profiles/r02s_small_batch_latency_loop_in_kernel.txt, Float32, µs
   // per iteration with the optimiser loop inside the launch: 20 x 3: 29 against 43; 20 x 12: 33 against 47; 50 x 12: 41
   // against 47; 200 x 12: 87 against 47; a single evaluation without the loop: 37 against 43 at 20 x 3) -- use_fused = 1
   // applies that break-even, 2 forces the path wherever it is supported
-  const bool fits = p->use_fused >= 2 ? (nb <= 1024 && nb * (int64_t)M <= 16384) : (nb <= 48 && nb * (int64_t)M <= 1024);
+  // looped: the iterations of an optimiser call run inside one launch (no launch, warm instruction cache): the single block
+  // stays ahead up to ≈ 72 sites (50 x 12: 32 against 43 µs) instead of 48 for a lone evaluation
+  const int64_t nb_max = looped ? 72 : 48;
+  const bool fits = p->use_fused >= 2 ? (nb <= 1024 && nb * (int64_t)M <= 16384) : (nb <= nb_max && nb * (int64_t)M <= 1024);
   return p->use_fused && !p->wide && !p->gpbm && !p->profiling && fits &&
          small_iter_supported<T>(cfg_of<T>(const_cast<hvi_plan*>(p)), nb, M);
 }
@@ -1845,10 +1848,11 @@ extern "C" int hvi_adam_init(hvi_plan* p, const void* phi0, double eta, double b
 // one optimiser iteration on `s`: [minibatch selection] → draws of the global block → evaluation → Adam update.
 // Everything that varies between iterations (seed, minibatch, step count, trace slot) is read from p->d_ctr.
 template <typename T>
-static int adam_iteration(hvi_plan* p, int M, int64_t site_offset, int64_t batch_size, int64_t first_batch, cudaStream_t s) {
+static int adam_iteration(hvi_plan* p, int M, int64_t site_offset, int64_t batch_size, int64_t first_batch, cudaStream_t s,
+                          bool looped = false) {
   const Cfg<T>& cfg = cfg_of<T>(p);
   Launch L{s, p->sm_count, &p->launches};
-  if (fused_ok<T>(p, batch_size > 0 ? batch_size : p->nb, M)) {   // the reference's operating point: one launch per iteration
+  if (fused_ok<T>(p, batch_size > 0 ? batch_size : p->nb, M, looped)) {   // the reference's operating point: one launch per iteration
     if (batch_size > 0) {
       int rc = select_prepare<T>(p, batch_size);
       if (rc) return rc;
@@ -1903,11 +1907,13 @@ static int adam_run_t(hvi_plan* p, int n_iter, int M, uint64_t seed0, int64_t si
   // the first iteration runs eagerly (it sizes every scratch buffer); the rest replay one captured iteration.  The wide
   // applicator issues thousands of launches per evaluation through its own chunk loop and is not captured.
   int it = 0;
-  rc = adam_iteration<T>(p, M, site_offset, batch_size, first_batch, s);
+  const bool looped = n_iter > 1 && !p->profiling && !getenv("HVI_SMALL_NO_LOOP") &&
+                      fused_ok<T>(p, batch_size > 0 ? batch_size : p->nb, M, true);
+  rc = adam_iteration<T>(p, M, site_offset, batch_size, first_batch, s, looped);
   if (rc) return rc;
   it = 1;
   // single-launch iterations: the remaining ones as a loop inside ONE launch (chunks of 4096 iterations)
-  if (n_iter > 1 && !p->profiling && fused_ok<T>(p, batch_size > 0 ? batch_size : p->nb, M) && !getenv("HVI_SMALL_NO_LOOP")) {
+  if (looped) {
     while (it < n_iter) {
       const int n = n_iter - it < 4096 ? n_iter - it : 4096;
       rc = enqueue_fused<T>(p, M, (T*)p->d_phi_opt, p->d_out, nullptr, s, 0, site_offset, true, batch_size, first_batch, n);
