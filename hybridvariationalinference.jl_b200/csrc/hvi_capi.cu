@@ -40,6 +40,8 @@ struct hvi_plan {
   int has_obs;
   // next batch being uploaded by hvi_plan_prefetch_data while the current one is evaluated
   cudaStream_t copy_stream;
+  // the prologue of an evaluation runs beside the applicator's forward pass (neither needs the other): aux stream + fork/join events
+  cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_copied;
   void *d_xM_next, *d_xP_next;
   int64_t cap_cur, cap_next;   // capacity in sites of (d_xM, d_xP) and of their _next twins
@@ -340,6 +342,9 @@ extern "C" int hvi_plan_destroy(hvi_plan* p) {
   if (p->adam_graph) cudaGraphExecDestroy(p->adam_graph);
   if (p->gpbm) generic_pbm_destroy(p->gpbm);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
+  if (p->aux_stream) { cudaStreamSynchronize(p->aux_stream); cudaStreamDestroy(p->aux_stream); }
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
   if (p->ev_copied) cudaEventDestroy(p->ev_copied);
   void* dev[] = {p->d_clocks, p->d_yo, p->d_yu, p->d_pen, p->d_bconst, p->d_ctr, p->ds_xM, p->ds_xP, p->ds_yo, p->ds_yu, p->d_idx, p->d_ls, p->d_phi_opt, p->d_adam_m, p->d_adam_v, p->d_trace, p->d_xM_next, p->d_xP_next, p->d_isites, p->d_xP, p->d_xM, p->d_rec, p->d_mu, p->d_mubar, p->d_phi, p->d_zP, p->d_zMs, p->d_ec, p->d_pdraw,
                  p->d_part_stream, p->d_part_mlp, p->d_out, p->d_red, p->d_grad, p->d_MU, p->d_MUBAR, p->d_part_x, p->d_xred, p->d_stage, p->d_wide, p->d_wide_bwd, p->d_gacc, p->d_wide_cache};
@@ -970,7 +975,24 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   int iev = 0;
 #define MARK() do { if (p->profiling) CU(p, cudaEventRecord(p->ev[iev++], s)); } while (0)
   MARK();
-  CU(p, launch_prologue<T>(L, cfg, phi, zP, M, ec, pdraw));
+  // ϕq → factors and per-draw θP is a single block of latency (≈ 11 µs) that only the streaming kernel waits for: it runs
+  // on an auxiliary stream beside the applicator's forward pass (HVI_NO_OVERLAP=1 or profiling: in line)
+  static const bool no_overlap = getenv("HVI_NO_OVERLAP") != nullptr;
+  const bool overlap = !p->profiling && !no_overlap;
+  if (overlap) {
+    if (!p->aux_stream) {
+      CU(p, cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
+      CU(p, cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+      CU(p, cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    }
+    CU(p, cudaEventRecord(p->ev_fork, s));
+    CU(p, cudaStreamWaitEvent(p->aux_stream, p->ev_fork, 0));
+    Launch La{p->aux_stream, p->sm_count, &p->launches};
+    CU(p, launch_prologue<T>(La, cfg, phi, zP, M, ec, pdraw));
+    CU(p, cudaEventRecord(p->ev_join, p->aux_stream));
+  } else {
+    CU(p, launch_prologue<T>(L, cfg, phi, zP, M, ec, pdraw));
+  }
   MARK();
   const bool pbm = cfg.npc > 0;
   const T* zetaP = pdraw + (size_t)cfg.nP * M;
@@ -1023,6 +1045,7 @@ static int enqueue_eval(hvi_plan* p, int M, const T* phi, const T* zP, const T* 
   const int64_t nbB_max = blk > 0 ? blk : p->nb;    // sites whose per-draw means are alive at once
   rc = run_g_fwd<T>(p, L, cfg, phi, (T*)p->d_mu, 0, nullptr, cache_s);
   if (rc) return rc;
+  if (overlap) CU(p, cudaStreamWaitEvent(s, p->ev_join, 0));   // pass 2 of g and the streaming kernel read the prologue's output
   if (pbm) {  // pass 2: g([xM; ζP_m[idx]]) for every draw (src/elbo.jl:508-515)
     const int64_t nmu = (int64_t)sizeof(T) * M * cfg.nM * nbB_max;
     rc = ensure(p, &p->d_MU, &p->cap_MU, nmu);
